@@ -1,0 +1,150 @@
+/* pixray_b200 -- C ABI of the B200-native engine for pixray's per-iteration hot path.
+ *
+ * Plain C: pointers and sizes only, no torch types.  Every entry point below replaces one method the reference's
+ * Python loop calls each iteration (file:line are relative to the reference checkout, pixray/pixray @ 37b03cf):
+ *
+ *   pxr_synth          <- drawer.synth(cur_iteration)          pixray.py:1206, vqgan.py:190-195, fast_pixeldrawer.py:89-91
+ *   pxr_make_cutouts   <- MakeCutouts.forward(out)             pixray.py:445-511 (cached-transform semantics 480-486)
+ *   pxr_encode_image   <- CLIP_Base.encode_image(cutouts)      slip.py:21-42, 52-66
+ *   pxr_prompt_loss    <- Prompt.forward(embeds) per prompt    pixray.py:268-280 (spherical_dist_loss 262-265)
+ *   pxr_backward       <- sum(lossAll).backward()              pixray.py:1481-1482
+ *   pxr_step           <- opt.step(); drawer.clip_z()          pixray.py:1484-1487, 538-539, vqgan.py:202-204
+ *   pxr_iterate        <- one pass of train()                  pixray.py:1436-1512 (ascend_txt 1243-1406)
+ *
+ * Conventions: functions return 0 on success and a negative code on failure; pxr_last_error() gives the message.
+ * All work is enqueued on ONE engine-owned CUDA stream; only pxr_sync, pxr_read_* and the *_host variants block.
+ * A handle is owned by one host thread (the reference keeps its session in module globals, pixray.py:1022-1063:
+ * one session per process, not re-entrant).  Buffers passed in are device pointers unless the name says host;
+ * layouts at the boundary are the reference's: NCHW fp32 images, [cutn, D] fp32 embeddings.
+ * There is no CPU fallback: without a CUDA device pxr_create fails.
+ */
+#ifndef PIXRAY_B200_H
+#define PIXRAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pxr_engine* pxr_handle;
+
+enum { PXR_DRAWER_VQGAN = 0, PXR_DRAWER_PIXEL = 1 };
+enum { PXR_PAD_REFLECTION = 0, PXR_PAD_BORDER = 1, PXR_PAD_ZEROS = 2 };
+enum { PXR_DTYPE_F16 = 0, PXR_DTYPE_BF16 = 1 };
+/* module ids for pxr_load_weight */
+enum { PXR_MOD_VQGAN = 0, PXR_MOD_CLIP0 = 1, PXR_MOD_CLIP1 = 2 };
+
+typedef struct {
+  int width;     /* transformer width (768 for ViT-B) */
+  int layers;    /* 12 */
+  int heads;     /* 12 */
+  int patch;     /* 16 or 32 */
+  int image_res; /* 224 == MakeCutouts cut_size (pixray.py:643-649) */
+  int out_dim;   /* 512 */
+} pxr_clip_cfg;
+
+typedef struct {
+  int device;            /* CUDA ordinal */
+  int rank, world;       /* cutout-shard rank / number of ranks (1 = single GPU) */
+  int drawer;            /* PXR_DRAWER_* */
+  int image_h, image_w;  /* canvas (vqgan: multiple of 16) */
+  /* taming Decoder hyper-parameters (vqgan.py:122-142: model.decoder / model.quantize) */
+  int z_channels, n_embed, ch, num_res_blocks, attn_resolution, n_levels, resolution;
+  int ch_mult[8];
+  /* pixel drawer grid (fast_pixeldrawer.py:37-63) */
+  int grid_rows, grid_cols;
+  /* MakeCutouts(cut_size, cutn) pixray.py:400-443; cutn is the GLOBAL count, this rank owns a slice */
+  int cutn, cut_size;
+  int n_clip;
+  pxr_clip_cfg clip[2];
+  float noise_fac;       /* pixray.py:439 (0.1) */
+  uint64_t seed;
+  int op_dtype;          /* PXR_DTYPE_*: tensor-core operand type (accumulation is always fp32) */
+  float grad_scale;      /* backward runs on grad_scale * dL (fp16 range management); 0 = default */
+  float beta1, beta2, adam_eps; /* optim.Adam defaults 0.9 / 0.999 / 1e-8 when 0 */
+  int reserved[8];
+} pxr_config;
+
+/* Per-iteration cutout parameters: what kornia's augmentations sample per cutout, made explicit.
+ * transforms[cutn*9]: row-major 3x3 "dst_pix <- src_pix" homographies exactly as MakeCutouts.transforms caches them
+ * (pixray.py:498); indices [0, int(0.6*cutn)) form the zoom group, the rest the wide group (pixray.py:407, 493-494). */
+typedef struct {
+  const float* transforms; /* host, [cutn, 3, 3] */
+  int zoom_padding;        /* PXR_PAD_REFLECTION on even iterations, PXR_PAD_BORDER on odd (pixray.py:1250-1253) */
+  float fill;              /* wide-group fill grey = random.random() (pixray.py:1255-1258) */
+  const float* noise_facs; /* host, [cutn] ~ U(0, noise_fac) (pixray.py:509); NULL = engine Philox */
+  const float* noise;      /* DEVICE, [cutn,3,cs,cs] standard normal (pixray.py:510); NULL = engine Philox */
+} pxr_cut_params;
+
+const char* pxr_last_error(pxr_handle h); /* h may be NULL for creation errors */
+const char* pxr_version(void);
+
+int pxr_create(const pxr_config* cfg, pxr_handle* out);
+void pxr_destroy(pxr_handle h);
+
+/* Weights by the reference's state_dict key (e.g. "decoder.conv_in.weight", "quantize.embedding.weight",
+ * "visual.transformer.resblocks.0.attn.in_proj_weight").  data: fp32, host or device; copied and repacked. */
+int pxr_load_weight(pxr_handle h, int module_id, const char* name, const float* data, const int64_t* dims, int ndim);
+/* After all weights: builds every kernel plan / workspace.  Fails listing the first missing weight. */
+int pxr_finalize(pxr_handle h);
+
+/* Prompt(embed, weight, stop) list of one perceptor (pixray.py:859-915).  embeds host [n, D]. */
+int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int D, const float* weights,
+                    const float* stops);
+
+/* Multi-GPU: 128-byte ncclUniqueId from rank 0; the engine owns the communicator. */
+int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world);
+int pxr_get_unique_id(void* out128);
+
+int pxr_synth(pxr_handle h, const float* z, float* out_img /* [3,H,W] */);
+int pxr_make_cutouts(pxr_handle h, const float* img, const pxr_cut_params* p, int iter,
+                     float* out_batch /* [cutn_local,3,cs,cs] */);
+int pxr_encode_image(pxr_handle h, int clip_idx, const float* batch, float* out_embeds /* [cutn_local, D] */);
+int pxr_prompt_loss(pxr_handle h, int clip_idx, const float* embeds, float* out_losses /* [n_prompts] */);
+int pxr_backward(pxr_handle h, float* z_grad);
+int pxr_step(pxr_handle h, float* z, float lr, int iter);
+int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params* p,
+                float* out_losses_host /* pinned or pageable; may be NULL */);
+int pxr_reset_optimizer(pxr_handle h); /* rebuild_optimisers: fresh Adam state (pixray.py:520-555, 1511) */
+int pxr_sync(pxr_handle h);
+
+/* Introspection used by tests and bench.py */
+int pxr_num_kernel_launches(pxr_handle h, int64_t* out); /* launches issued since create */
+int pxr_get_stream(pxr_handle h, void** out);
+int pxr_z_numel(pxr_handle h, int64_t* out);
+int pxr_z_bounds(pxr_handle h, float* zmin, float* zmax); /* device [z_channels]: codebook per-channel min/max */
+
+/* ---------------------------------------------------------------- test hooks (used only by tests/) */
+typedef struct {
+  const void* a;
+  int a_mode; /* 0 K-major, 1 MN-major */
+  long long lda, a_mn_extent, a_k_extent, a_bs0, a_bs1;
+  const void* b;
+  int b_mode, b_batched;
+  long long ldb, b_mn_extent, b_k_extent, b_bs0, b_bs1;
+  int nb0, nb1;
+  int M, N, K, block_n, fmt;
+  float alpha;
+  const float* bias;
+  int bias_per_row, act;
+  const void* aux_in;
+  void* aux_out;
+  const float* res_f32;
+  const void* res_f16;
+  float* out_f32;
+  void* out_f16;
+  long long ldc, c_bs0, c_bs1;
+  void* stream;
+  int repeat;
+} pxr_test_gemm_desc;
+
+int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen);
+/* implicit-GEMM conv over NHWC fp16: d->a = input (pixel stride lda), d->b = weights [taps*cout_pad, c_in] */
+int pxr_test_conv(const pxr_test_gemm_desc* d, int batch, int H, int W, int c_in, int cout_pad, int ksize, char* err,
+                  int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,505 @@
+"""CPU oracle: torch-fp32 restatement of pixray's per-iteration hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported by the product (pixray_b200/); only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and only as the checker or
+the CPU baseline.
+
+Parity status: the reference's own tests pin nothing on this path -> "parity unpinned" for the
+un-vendored third-party leaves restated here (kornia 0.6.2 warps, openai-CLIP VisionTransformer, taming Decoder).
+The in-tree parts (Prompt, spherical_dist_loss, vector_quantize, ClampWithGrad, MakeCutouts pooling / group split /
+noise, CLIP_Base.preprocess, FastPixelDrawer.synth, Adam + clip_z) ARE pinned: oracle/make_golden.py imports the
+real reference (under oracle/shim.py) in the authoring container and writes tests/golden/*.npz, which
+tests/test_oracle_golden.py checks this file against.  The ViT restatement is additionally cross-checked against
+transformers' CLIPVisionModelWithProjection (hidden_act="quick_gelu") with copied weights.
+
+Every function cites the reference file:line it follows (paths relative to the pixray checkout).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)  # slip.py:55
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+# ------------------------------------------------------------------------------------------------ small autograd ops
+
+
+class _ReplaceGrad(torch.autograd.Function):
+    """pixray.py:249-259 / vqgan.py:48-58: forward value of the first arg, gradient routed to the second."""
+
+    @staticmethod
+    def forward(ctx, x_forward, x_backward):
+        ctx.shape = x_backward.shape
+        return x_forward
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, g.sum_to_size(ctx.shape)
+
+
+replace_grad = _ReplaceGrad.apply
+
+
+class _ClampWithGrad(torch.autograd.Function):
+    """vqgan.py:66-79: clamp forward; backward keeps the gradient only where it points back into range."""
+
+    @staticmethod
+    def forward(ctx, x, lo, hi):
+        ctx.lo, ctx.hi = lo, hi
+        ctx.save_for_backward(x)
+        return x.clamp(lo, hi)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * (g * (x - x.clamp(ctx.lo, ctx.hi)) >= 0), None, None
+
+
+clamp_with_grad = _ClampWithGrad.apply
+
+
+def spherical_dist_loss(x, y):
+    """pixray.py:262-265."""
+    x = F.normalize(x, dim=-1)
+    y = F.normalize(y, dim=-1)
+    return (x - y).norm(dim=-1).div(2).arcsin().pow(2).mul(2)
+
+
+def prompt_loss(embeds, embed, weight, stop):
+    """Prompt.forward, pixray.py:275-280.  embeds [cutn, D]; embed [n, D]; scalar weight / stop."""
+    weight = torch.as_tensor(weight, dtype=embeds.dtype)
+    stop = torch.as_tensor(stop, dtype=embeds.dtype)
+    input_normed = F.normalize(embeds.unsqueeze(1), dim=2)
+    embed_normed = F.normalize(embed.unsqueeze(0), dim=2)
+    dists = input_normed.sub(embed_normed).norm(dim=2).div(2).arcsin().pow(2).mul(2)
+    dists = dists * weight.sign()
+    return weight.abs() * replace_grad(dists, torch.maximum(dists, stop)).mean()
+
+
+# ------------------------------------------------------------------------------------------------ MakeCutouts
+
+
+def adaptive_pool_bounds(in_size, out_size):
+    """Integer window bounds of Adaptive{Avg,Max}Pool2d (pixray.py:442-443 -> ATen start_index / end_index):
+    start = floor(i * in / out), end = ceil((i + 1) * in / out).  Bit-exact bookkeeping, returned as int lists."""
+    starts = [(i * in_size) // out_size for i in range(out_size)]
+    ends = [-((-(i + 1) * in_size) // out_size) for i in range(out_size)]
+    return starts, ends
+
+
+def pool_avg_max(img, cut_size):
+    """pixray.py:463: (av_pool(input) + max_pool(input)) / 2 on the whole image -> [1, C, cs, cs]."""
+    return (F.adaptive_avg_pool2d(img, (cut_size, cut_size)) + F.adaptive_max_pool2d(img, (cut_size, cut_size))) / 2
+
+
+def _normal_transform_pixel(h, w):
+    """kornia 0.6.2 normal_transform_pixel: pixel -> [-1, 1] with the (size-1)/2 convention."""
+    eps = 1e-14
+    tr = torch.tensor([[1.0, 0.0, -1.0], [0.0, 1.0, -1.0], [0.0, 0.0, 1.0]])
+    tr[0, 0] = tr[0, 0] * 2.0 / (w - 1.0 if w != 1 else eps)
+    tr[1, 1] = tr[1, 1] * 2.0 / (h - 1.0 if h != 1 else eps)
+    return tr[None]
+
+
+def normalize_homography(dst_pix_trans_src_pix, dsize_src, dsize_dst):
+    """kornia 0.6.2 normalize_homography (used by warp_perspective, pixray.py:482-485)."""
+    src_h, src_w = dsize_src
+    dst_h, dst_w = dsize_dst
+    src_norm_trans_src_pix = _normal_transform_pixel(src_h, src_w).to(dst_pix_trans_src_pix)
+    src_pix_trans_src_norm = torch.inverse(src_norm_trans_src_pix)
+    dst_norm_trans_dst_pix = _normal_transform_pixel(dst_h, dst_w).to(dst_pix_trans_src_pix)
+    return dst_norm_trans_dst_pix @ (dst_pix_trans_src_pix @ src_pix_trans_src_norm)
+
+
+def _transform_points(trans, pts):
+    """kornia transform_points on a [B, H, W, 2] grid with [B, 3, 3] transforms (homogeneous divide, eps 1e-8)."""
+    ones = torch.ones_like(pts[..., :1])
+    ph = torch.cat([pts, ones], dim=-1)  # B,H,W,3
+    out = torch.einsum("bij,bhwj->bhwi", trans, ph)
+    z = out[..., 2:3]
+    scale = torch.where(z.abs() > 1e-8, 1.0 / z, torch.ones_like(z))
+    return out[..., :2] * scale
+
+
+def warp_grid(M, src_hw, dst_hw):
+    """Sampling grid of kornia warp_perspective(src, M, dsize) in normalised coords, [B, h_out, w_out, 2]."""
+    B = M.shape[0]
+    h_out, w_out = dst_hw
+    dst_norm_trans_src_norm = normalize_homography(M, src_hw, dst_hw)
+    src_norm_trans_dst_norm = torch.inverse(dst_norm_trans_src_norm)
+    xs = torch.linspace(-1, 1, w_out)
+    ys = torch.linspace(-1, 1, h_out)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    grid = torch.stack([gx, gy], dim=-1)[None].repeat(B, 1, 1, 1).to(M.dtype)
+    return _transform_points(src_norm_trans_dst_norm, grid)
+
+
+def warp_perspective(src, M, dsize, padding_mode="zeros", fill_value=None, align_corners=True):
+    """kornia 0.6.2 warp_perspective as called on MakeCutouts' cached path (pixray.py:480-486; default
+    align_corners=True, bilinear).  padding_mode 'fill' = grid_sample(zeros) + (1 - grid_sample(ones)) * fill
+    (kornia _fill_and_warp; pixray.py:351-352, 364-365, 484-485)."""
+    grid = warp_grid(M, src.shape[-2:], dsize)
+    if padding_mode == "fill":
+        ones = torch.ones_like(src)
+        inv = 1 - F.grid_sample(ones, grid, align_corners=align_corners, mode="bilinear", padding_mode="zeros")
+        fv = torch.as_tensor(fill_value, dtype=src.dtype).reshape(1, -1, 1, 1)
+        return F.grid_sample(src, grid, align_corners=align_corners, mode="bilinear", padding_mode="zeros") + inv * fv
+    return F.grid_sample(src, grid, align_corners=align_corners, mode="bilinear", padding_mode=padding_mode)
+
+
+def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None, noise=None, cutn_zoom=None):
+    """MakeCutouts.forward on explicit (cached) transforms, pixray.py:445-511.
+
+    img [1, 3, H, W]; transforms [cutn, 3, 3]; zoom group = first int(0.6 * cutn) (pixray.py:407) warped with
+    `zoom_padding` ('reflection' | 'border'); wide group with constant grey `fill`; then batch + facs * noise
+    (pixray.py:508-510) when both are given."""
+    cutn = transforms.shape[0]
+    if cutn_zoom is None:
+        cutn_zoom = int(0.6 * cutn)
+    pooled = pool_avg_max(img, cut_size)  # identical for every cutout (pixray.py:461-478)
+    src = pooled.expand(cutn, -1, -1, -1)
+    parts = []
+    if cutn_zoom > 0:
+        parts.append(warp_perspective(src[:cutn_zoom], transforms[:cutn_zoom], (cut_size, cut_size),
+                                      padding_mode=zoom_padding))
+    if cutn_zoom < cutn:
+        parts.append(warp_perspective(src[cutn_zoom:], transforms[cutn_zoom:], (cut_size, cut_size),
+                                      padding_mode="fill", fill_value=[fill, fill, fill]))
+    batch = torch.cat(parts)
+    if noise_facs is not None and noise is not None:
+        batch = batch + noise_facs.reshape(cutn, 1, 1, 1) * noise
+    return batch
+
+
+# ------------------------------------------------------------------------------------------------ perceptor
+
+
+def clip_preprocess(imgs):
+    """CLIP_Base.preprocess, slip.py:21-42, 52-60: global min/max range normalise, then per-channel mean/std.
+    (Resize / CenterCrop at 224 are identities for 224x224 cutouts.)"""
+    minv = imgs.min()
+    imgs = imgs - minv
+    maxv = imgs.max()
+    if maxv != 0:
+        imgs = imgs / maxv
+    mean = torch.tensor(CLIP_MEAN, dtype=imgs.dtype).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, dtype=imgs.dtype).view(1, 3, 1, 1)
+    return (imgs - mean) / std
+
+
+class QuickGELU(nn.Module):
+    """SLIP/models.py:27-29."""
+
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class ResidualAttentionBlock(nn.Module):
+    """SLIP/models.py:32-53 (vendored copy of openai-CLIP's block): pre-LN MHA + pre-LN MLP with QuickGELU."""
+
+    def __init__(self, d_model, n_head):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = nn.LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)), ("gelu", QuickGELU()),
+                                              ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = nn.LayerNorm(d_model)
+
+    def forward(self, x):
+        h = self.ln_1(x)
+        x = x + self.attn(h, h, h, need_weights=False)[0]
+        return x + self.mlp(self.ln_2(x))
+
+
+class Transformer(nn.Module):
+    """SLIP/models.py:56-64."""
+
+    def __init__(self, width, layers, heads):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
+
+    def forward(self, x):
+        return self.resblocks(x)
+
+
+class VisionTransformer(nn.Module):
+    """openai-CLIP clip/model.py VisionTransformer [UPSTREAM, un-vendored; call sites slip.py:49-50, 65]."""
+
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        self.input_resolution, self.output_dim = input_resolution, output_dim
+        self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+    def forward(self, x):
+        x = self.conv1(x)
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+        cls = self.class_embedding.to(x.dtype) + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype)
+        x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
+        x = self.ln_pre(x)
+        x = self.transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
+        x = self.ln_post(x[:, 0, :])
+        return x @ self.proj
+
+
+class ClipVisual(nn.Module):
+    """Holder giving the state_dict the reference's key names ('visual.*') and `encode_image` (slip.py:65)."""
+
+    def __init__(self, input_resolution=224, patch_size=16, width=768, layers=12, heads=12, output_dim=512):
+        super().__init__()
+        self.visual = VisionTransformer(input_resolution, patch_size, width, layers, heads, output_dim)
+
+    def encode_image(self, x):
+        return self.visual(x)
+
+
+def init_clip_weights(model, seed=0):
+    """Seeded synthetic CLIP-style init (pattern of SLIP/models.py:106-120; no pretrained weights offline)."""
+    g = torch.Generator().manual_seed(seed)
+    v = model.visual
+    W, L = v.transformer.width, v.transformer.layers
+    proj_std, attn_std, fc_std = (W ** -0.5) * ((2 * L) ** -0.5), W ** -0.5, (2 * W) ** -0.5
+    with torch.no_grad():
+        v.conv1.weight.copy_(torch.randn(v.conv1.weight.shape, generator=g) * (3 * v.conv1.kernel_size[0] ** 2) ** -0.5)
+        v.class_embedding.copy_(torch.randn(W, generator=g) * W ** -0.5)
+        v.positional_embedding.copy_(torch.randn(v.positional_embedding.shape, generator=g) * 0.01)
+        v.proj.copy_(torch.randn(v.proj.shape, generator=g) * W ** -0.5)
+        for blk in v.transformer.resblocks:
+            blk.attn.in_proj_weight.copy_(torch.randn(blk.attn.in_proj_weight.shape, generator=g) * attn_std)
+            blk.attn.in_proj_bias.copy_(torch.randn(3 * W, generator=g) * 0.02)
+            blk.attn.out_proj.weight.copy_(torch.randn(W, W, generator=g) * proj_std)
+            blk.attn.out_proj.bias.copy_(torch.randn(W, generator=g) * 0.02)
+            blk.mlp.c_fc.weight.copy_(torch.randn(4 * W, W, generator=g) * fc_std)
+            blk.mlp.c_fc.bias.copy_(torch.randn(4 * W, generator=g) * 0.02)
+            blk.mlp.c_proj.weight.copy_(torch.randn(W, 4 * W, generator=g) * proj_std)
+            blk.mlp.c_proj.bias.copy_(torch.randn(W, generator=g) * 0.02)
+            for ln in (blk.ln_1, blk.ln_2):
+                ln.weight.copy_(1 + 0.1 * torch.randn(W, generator=g))
+                ln.bias.copy_(0.05 * torch.randn(W, generator=g))
+        for ln in (v.ln_pre, v.ln_post):
+            ln.weight.copy_(1 + 0.1 * torch.randn(W, generator=g))
+            ln.bias.copy_(0.05 * torch.randn(W, generator=g))
+    return model.eval().requires_grad_(False)  # slip.py:176
+
+
+def encode_image(model, imgs):
+    """CLIP_Base.encode_image, slip.py:62-66."""
+    e = model.encode_image(clip_preprocess(imgs))
+    return e / e.norm(dim=-1, keepdim=True)
+
+
+# ------------------------------------------------------------------------------------------------ VQGAN drawer
+
+
+def vector_quantize(x, codebook):
+    """vqgan.py:60-64.  Returns (straight-through quantised x, argmin indices)."""
+    d = x.pow(2).sum(dim=-1, keepdim=True) + codebook.pow(2).sum(dim=1) - 2 * x @ codebook.T
+    indices = d.argmin(-1)
+    x_q = F.one_hot(indices, codebook.shape[0]).to(d.dtype) @ codebook
+    return replace_grad(x_q, x), indices
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def _gn(c):
+    return nn.GroupNorm(32, c, eps=1e-6, affine=True)
+
+
+class ResnetBlock(nn.Module):
+    """taming.modules.diffusionmodules.model.ResnetBlock with temb_channels=0 [UPSTREAM, un-vendored]."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.norm1, self.conv1 = _gn(cin), nn.Conv2d(cin, cout, 3, 1, 1)
+        self.norm2, self.conv2 = _gn(cout), nn.Conv2d(cout, cout, 3, 1, 1)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv2d(cin, cout, 1, 1, 0)
+
+    def forward(self, x):
+        h = self.conv1(_swish(self.norm1(x)))
+        h = self.conv2(_swish(self.norm2(h)))
+        if hasattr(self, "nin_shortcut"):
+            x = self.nin_shortcut(x)
+        return x + h
+
+
+class AttnBlock(nn.Module):
+    """taming AttnBlock: GN -> q,k,v 1x1 -> softmax(q^T k * C^-1/2) -> proj 1x1, residual [UPSTREAM]."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.norm = _gn(c)
+        self.q, self.k, self.v, self.proj_out = (nn.Conv2d(c, c, 1) for _ in range(4))
+
+    def forward(self, x):
+        h = self.norm(x)
+        q, k, v = self.q(h), self.k(h), self.v(h)
+        b, c, hh, ww = q.shape
+        q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
+        k = k.reshape(b, c, hh * ww)
+        w_ = torch.softmax(torch.bmm(q, k) * (int(c) ** -0.5), dim=2)
+        v = v.reshape(b, c, hh * ww)
+        h = torch.bmm(v, w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+        return x + self.proj_out(h)
+
+
+class _Up(nn.Module):
+    pass
+
+
+class _Upsample(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, 1, 1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class Decoder(nn.Module):
+    """taming Decoder (vqgan.py:195 via model.decode) [UPSTREAM].  Module names mirror the checkpoint keys."""
+
+    def __init__(self, ch=128, out_ch=3, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, attn_resolutions=(16,),
+                 resolution=256, z_channels=256):
+        super().__init__()
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        block_in = ch * ch_mult[-1]
+        curr_res = resolution // 2 ** (self.num_resolutions - 1)
+        self.conv_in = nn.Conv2d(z_channels, block_in, 3, 1, 1)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        ups = []
+        for i_level in reversed(range(self.num_resolutions)):
+            up = _Up()
+            up.block, up.attn = nn.ModuleList(), nn.ModuleList()
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks + 1):
+                up.block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    up.attn.append(AttnBlock(block_in))
+            if i_level != 0:
+                up.upsample = _Upsample(block_in)
+                curr_res *= 2
+            ups.insert(0, up)
+        self.up = nn.ModuleList(ups)
+        self.norm_out = _gn(block_in)
+        self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
+
+    def forward(self, z):
+        h = self.conv_in(z)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        for i_level in reversed(range(self.num_resolutions)):
+            up = self.up[i_level]
+            for i_block in range(self.num_res_blocks + 1):
+                h = up.block[i_block](h)
+                if len(up.attn) > 0:
+                    h = up.attn[i_block](h)
+            if i_level != 0:
+                h = up.upsample(h)
+        return self.conv_out(_swish(self.norm_out(h)))
+
+
+class VQModel(nn.Module):
+    """The slice of taming VQModel pixray uses (vqgan.py:122-142, 190-195): codebook, post_quant_conv, decoder."""
+
+    def __init__(self, n_embed=16384, embed_dim=256, **dd):
+        super().__init__()
+        self.quantize = nn.Module()
+        self.quantize.embedding = nn.Embedding(n_embed, embed_dim)
+        self.post_quant_conv = nn.Conv2d(embed_dim, dd.get("z_channels", 256), 1)
+        self.decoder = Decoder(**dd)
+
+    def decode(self, zq):
+        return self.decoder(self.post_quant_conv(zq))
+
+
+def init_vqgan_weights(model, seed=0):
+    """Seeded synthetic weights: default conv init under a fixed seed, GN affine perturbed, codebook spread so the
+    argmin is well separated."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name == "quantize.embedding.weight":
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            elif p.dim() == 4:
+                fan_in = p.shape[1] * p.shape[2] * p.shape[3]
+                p.copy_(torch.randn(p.shape, generator=g) * (1.0 / fan_in) ** 0.5)
+            elif "norm" in name and name.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    return model.eval().requires_grad_(False)  # vqgan.py:125
+
+
+def vqgan_synth(model, z):
+    """VqganDrawer.synth, vqgan.py:190-195.  z [1, C, h, w] -> image [1, 3, H, W] in [0, 1]."""
+    zq, _ = vector_quantize(z.movedim(1, 3), model.quantize.embedding.weight)
+    return clamp_with_grad(model.decode(zq.movedim(3, 1)).add(1).div(2), 0, 1)
+
+
+def vqgan_z_bounds(model):
+    """vqgan.py:141-142: per-channel codebook min / max, used by clip_z (vqgan.py:202-204)."""
+    w = model.quantize.embedding.weight
+    return w.min(dim=0).values[None, :, None, None], w.max(dim=0).values[None, :, None, None]
+
+
+def pixel_synth(z, out_hw):
+    """FastPixelDrawer.synth, fast_pixeldrawer.py:89-91: nearest upsample + clamp_with_grad."""
+    return clamp_with_grad(F.interpolate(z, size=out_hw, mode="nearest"), 0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ optimiser / loop
+
+
+class AdamState:
+    """optim.Adam([z], lr) as rebuilt by rebuild_optimisers (pixray.py:520-555): betas 0.9/0.999, eps 1e-8."""
+
+    def __init__(self, z, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.m = torch.zeros_like(z)
+        self.v = torch.zeros_like(z)
+        self.t = 0
+        self.b1, self.b2, self.eps = beta1, beta2, eps
+
+    def step(self, z, grad, lr):
+        self.t += 1
+        self.m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
+        self.v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
+        bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
+        denom = (self.v.sqrt() / math.sqrt(bc2)).add_(self.eps)
+        return z - (lr / bc1) * self.m / denom
+
+
+def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise):
+    """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
+
+    synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
+    (embed [n,D], weight, stop).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
+    z = z.detach().clone().requires_grad_(True)
+    out = synth_fn(z)
+    batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise)
+    losses, embeds = [], []
+    for model, pms in zip(clip_models, prompts):
+        iii = encode_image(model, batch).float()
+        embeds.append(iii)
+        for (embed, weight, stop) in pms:
+            losses.append(prompt_loss(iii, embed, weight, stop))
+    total = sum(losses)
+    total.backward()
+    return dict(image=out.detach(), batch=batch.detach(), embeds=[e.detach() for e in embeds],
+                losses=[l.detach() for l in losses], z_grad=z.grad.detach())

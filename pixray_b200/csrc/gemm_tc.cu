@@ -1,0 +1,522 @@
+// See gemm_tc.cuh for the contract.  sm_100a only (tcgen05 + TMA + TMEM).
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace pxr {
+using namespace ptx;
+
+namespace {
+
+constexpr uint32_t A_TILE_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KiB
+constexpr uint32_t MN_ATOM_BYTES = 64 * GEMM_BLOCK_K * 2;           // one 64(MN) x 64(K) MN-major TMA box
+
+struct TileCoord {
+  int tn, tm, z, b0, b1, n0, m0, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.tn = tile % p.tiles_n;
+  int r = tile / p.tiles_n;
+  t.tm = r % p.tiles_m;
+  t.z = r / p.tiles_m;
+  t.b0 = t.z % p.nb0;
+  t.b1 = t.z / p.nb0;
+  t.n0 = t.tn * p.block_n;
+  t.m0 = t.tm * GEMM_BLOCK_M;
+  t.h0 = 0;
+  t.w0 = 0;
+  if (p.a_mode == OP_CONV) {
+    t.h0 = (t.tm / p.tiles_w) * p.tile_h;
+    t.w0 = (t.tm % p.tiles_w) * p.tile_w;
+  }
+  return t;
+}
+
+__device__ __forceinline__ float quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quickgelu_grad(float u) {
+  float s = 1.f / (1.f + __expf(-1.702f * u));
+  return s * (1.f + 1.702f * u * (1.f - s));
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], long long row_off,
+                                               int row, int col0, bool full_vec) {
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+  if (p.bias) {
+    if (p.bias_per_row) {
+      float b = p.bias[row];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] += b;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.N) x[j] += p.bias[col0 + j];
+    }
+  }
+  const long long off = row_off + col0;
+  if (full_vec) {
+    if (p.act == ACT_QUICKGELU) {
+      if (p.aux_out) {
+        __align__(16) __half h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(x[j]);
+        uint4* dst = reinterpret_cast<uint4*>(p.aux_out + off);
+        dst[0] = reinterpret_cast<const uint4*>(h)[0];
+        dst[1] = reinterpret_cast<const uint4*>(h)[1];
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = quickgelu(x[j]);
+    } else if (p.act == ACT_QUICKGELU_BWD) {
+      __align__(16) __half h[16];
+      const uint4* src = reinterpret_cast<const uint4*>(p.aux_in + off);
+      reinterpret_cast<uint4*>(h)[0] = src[0];
+      reinterpret_cast<uint4*>(h)[1] = src[1];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] *= quickgelu_grad(__half2float(h[j]));
+    }
+    if (p.res_f32) {
+      const float4* src = reinterpret_cast<const float4*>(p.res_f32 + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 r = src[j];
+        x[4 * j + 0] += r.x;
+        x[4 * j + 1] += r.y;
+        x[4 * j + 2] += r.z;
+        x[4 * j + 3] += r.w;
+      }
+    }
+    if (p.res_f16) {
+      __align__(16) __half h[16];
+      const uint4* src = reinterpret_cast<const uint4*>(p.res_f16 + off);
+      reinterpret_cast<uint4*>(h)[0] = src[0];
+      reinterpret_cast<uint4*>(h)[1] = src[1];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] += __half2float(h[j]);
+    }
+    if (p.out_f32) {
+      float4* dst = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    }
+    if (p.out_f16) {
+      __align__(16) __half h[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(x[j]);
+      uint4* dst = reinterpret_cast<uint4*>(p.out_f16 + off);
+      dst[0] = reinterpret_cast<const uint4*>(h)[0];
+      dst[1] = reinterpret_cast<const uint4*>(h)[1];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (col0 + j >= p.N) continue;
+      float y = x[j];
+      if (p.act == ACT_QUICKGELU) {
+        if (p.aux_out) p.aux_out[off + j] = __float2half_rn(y);
+        y = quickgelu(y);
+      } else if (p.act == ACT_QUICKGELU_BWD) {
+        y *= quickgelu_grad(__half2float(p.aux_in[off + j]));
+      }
+      if (p.res_f32) y += p.res_f32[off + j];
+      if (p.res_f16) y += __half2float(p.res_f16[off + j]);
+      if (p.out_f32) p.out_f32[off + j] = y;
+      if (p.out_f16) p.out_f16[off + j] = __float2half_rn(y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
+  const uint32_t stage_bytes = A_TILE_BYTES + b_bytes;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const int tap = kb / p.k_blocks_per_tap;
+          const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          if (p.a_mode == OP_KMAJOR) {
+            tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
+          } else if (p.a_mode == OP_MNMAJOR) {
+            tma_load_4d(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
+            tma_load_4d(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+          } else {
+            int dy = 0, dx = 0;
+            if (p.num_taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            }
+            tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
+          }
+          if (p.b_mode == OP_KMAJOR) {
+            tma_load_4d(&p.tma_b, &full_bar[stage], sb, kk, t.n0 + tap * p.b_tap_rows, bb0, bb1);
+          } else {
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_4d(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, t.n0 + 64 * j, kk, bb0, bb1);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc =
+          make_idesc_f16(GEMM_BLOCK_M, p.block_n, p.fmt, p.a_mode == OP_MNMAJOR, p.b_mode == OP_MNMAJOR);
+      // K-major: 8-row groups 1024 B apart; K advance = 32 B inside the swizzled row.
+      // MN-major: 64-wide MN atoms 8192 B apart (LBO), 8-deep K groups 1024 B apart (SBO); K advance = 2048 B.
+      const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+      const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+      const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
+      const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (TMEM -> regs -> global)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+      bool valid;
+      long long row_off;
+      int row;
+      if (p.a_mode == OP_CONV) {
+        const int h = t.h0 + r / p.tile_w, w = t.w0 + r % p.tile_w;
+        valid = (h < p.conv_H) && (w < p.conv_W);
+        row = h * p.conv_W + w;
+        row_off = (static_cast<long long>(t.z) * p.conv_H * p.conv_W + row) * p.ldc;
+      } else {
+        row = t.m0 + r;
+        valid = row < p.M;
+        row_off = t.b0 * p.out_bs0 + t.b1 * p.out_bs1 + static_cast<long long>(row) * p.ldc;
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c, v);
+        tmem_ld_wait();
+        const int col0 = t.n0 + c;
+        if (valid && col0 < p.N) epilogue_chunk(p, v, row_off, row, col0, p.vec_ok && (col0 + 16 <= p.N));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+void set_err(char* err, int errlen, const char* msg) {
+  if (err && errlen > 0) snprintf(err, errlen, "%s", msg);
+}
+
+// 4-D fp16/bf16 tensor map, 128-byte swizzle, zero fill out of bounds.
+int encode_tmap4(CUtensorMap* out, const void* ptr, int fmt, const uint64_t dims[4], const uint64_t strides_elems[3],
+                 const uint32_t box[4], char* err, int errlen) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_err(err, errlen, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -1;
+  }
+  cuuint64_t gdims[4], gstrides[3];
+  cuuint32_t gbox[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    gstrides[i] = strides_elems[i] * 2;
+    if (gstrides[i] % 16 != 0 || gstrides[i] == 0) {
+      set_err(err, errlen, "TMA global stride must be a non-zero multiple of 16 bytes");
+      return -2;
+    }
+  }
+  if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0) {
+    set_err(err, errlen, "TMA global address must be 16-byte aligned");
+    return -3;
+  }
+  CUresult r = fn(out, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                  const_cast<void*>(ptr), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+             (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+    set_err(err, errlen, buf);
+    return -4;
+  }
+  return 0;
+}
+
+int encode_operand(CUtensorMap* out, const GemmOperand& op, int rows_box, int fmt, char* err, int errlen) {
+  // batch strides for extent-1 dims still need to be valid multiples of 16 bytes
+  long long bs0 = op.nb0 > 1 ? op.bs0 : 0, bs1 = op.nb1 > 1 ? op.bs1 : 0;
+  uint64_t dims[4], strides[3];
+  uint32_t box[4];
+  if (op.mode == OP_KMAJOR) {
+    dims[0] = op.k_extent;
+    dims[1] = op.mn_extent;
+    box[0] = GEMM_BLOCK_K;
+    box[1] = rows_box;
+  } else {
+    dims[0] = op.mn_extent;
+    dims[1] = op.k_extent;
+    box[0] = 64;
+    box[1] = GEMM_BLOCK_K;
+  }
+  dims[2] = op.nb0;
+  dims[3] = op.nb1;
+  box[2] = box[3] = 1;
+  strides[0] = op.ld;
+  strides[1] = bs0 ? bs0 : op.ld * dims[1];
+  strides[2] = bs1 ? bs1 : strides[1] * dims[2];
+  return encode_tmap4(out, op.ptr, fmt, dims, strides, box, err, errlen);
+}
+
+bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sms, char* err, int errlen) {
+  GemmParams& p = plan->p;
+  if (block_n < 16 || block_n > 256 || block_n % 16) {
+    set_err(err, errlen, "block_n must be a multiple of 16 in [16, 256]");
+    return -10;
+  }
+  if (p.b_mode == OP_MNMAJOR && block_n % 64) {
+    set_err(err, errlen, "MN-major B needs block_n % 64 == 0");
+    return -11;
+  }
+  p.block_n = block_n;
+  const int stage_bytes = A_TILE_BYTES + block_n * GEMM_BLOCK_K * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < 2 * block_n) cols <<= 1;
+  p.tmem_cols = cols;
+  p.alpha = epi.alpha;
+  p.bias = epi.bias;
+  p.bias_per_row = epi.bias_per_row;
+  p.act = epi.act;
+  p.aux_in = epi.aux_in;
+  p.aux_out = epi.aux_out;
+  p.res_f32 = epi.res_f32;
+  p.res_f16 = epi.res_f16;
+  p.out_f32 = epi.out_f32;
+  p.out_f16 = epi.out_f16;
+  p.ldc = epi.ldc;
+  p.out_bs0 = epi.bs0;
+  p.out_bs1 = epi.bs1;
+  p.vec_ok = (epi.ldc % 8 == 0) && (epi.bs0 % 8 == 0) && (epi.bs1 % 8 == 0) && aligned16(epi.aux_in) &&
+             aligned16(epi.aux_out) && aligned16(epi.res_f32) && aligned16(epi.res_f16) && aligned16(epi.out_f32) &&
+             aligned16(epi.out_f16);
+  plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  plan->smem_bytes = stages * stage_bytes + 1024 + 256;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  return 0;
+}
+
+}  // namespace
+
+int gemm_plan_make(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, int M, int N, int K,
+                   const GemmEpilogue& epi, int block_n, int fmt, int num_sms, char* err, int errlen) {
+  *plan = GemmPlan{};
+  GemmParams& p = plan->p;
+  if (A.mode == OP_CONV || B.mode == OP_CONV) {
+    set_err(err, errlen, "use conv_plan_make for conv operands");
+    return -20;
+  }
+  p.M = M;
+  p.N = N;
+  p.fmt = fmt;
+  p.a_mode = A.mode;
+  p.b_mode = B.mode;
+  p.num_taps = 1;
+  p.k_blocks_per_tap = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  p.num_k_blocks = p.k_blocks_per_tap;
+  p.tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.tiles_n = (N + block_n - 1) / block_n;
+  const int nb0 = A.nb0, nb1 = A.nb1;
+  p.nb0 = nb0;
+  p.b_batched = (B.nb0 > 1 || B.nb1 > 1) ? 1 : 0;
+  if (p.b_batched && (B.nb0 != nb0 || B.nb1 != nb1)) {
+    set_err(err, errlen, "batched B must have the same batch extents as A");
+    return -21;
+  }
+  p.total_tiles = p.tiles_m * p.tiles_n * nb0 * nb1;
+  int rc = encode_operand(&p.tma_a, A, GEMM_BLOCK_M, fmt, err, errlen);
+  if (rc) return rc;
+  rc = encode_operand(&p.tma_b, B, block_n, fmt, err, errlen);
+  if (rc) return rc;
+  plan->flops = 2.0 * M * N * K * nb0 * nb1;
+  return finish_plan(plan, epi, block_n, num_sms, err, errlen);
+}
+
+int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, int H, int W, int c_in, const void* wt,
+                   int cout_pad, int n_out, int ksize, const GemmEpilogue& epi, int block_n, int fmt, int num_sms,
+                   char* err, int errlen) {
+  *plan = GemmPlan{};
+  GemmParams& p = plan->p;
+  if (c_in % 64 || (ksize != 1 && ksize != 3)) {
+    set_err(err, errlen, "conv: c_in must be a multiple of 64 and ksize 1 or 3");
+    return -30;
+  }
+  int tile_w = W >= 16 ? 16 : 8;
+  if (W < 8 || (W % tile_w)) {
+    set_err(err, errlen, "conv: W must be a multiple of 8 (>= 8)");
+    return -31;
+  }
+  int tile_h = GEMM_BLOCK_M / tile_w;
+  p.M = H * W;
+  p.N = n_out;
+  p.fmt = fmt;
+  p.a_mode = OP_CONV;
+  p.b_mode = OP_KMAJOR;
+  p.num_taps = ksize * ksize;
+  p.k_blocks_per_tap = c_in / 64;
+  p.num_k_blocks = p.num_taps * p.k_blocks_per_tap;
+  p.conv_H = H;
+  p.conv_W = W;
+  p.tile_h = tile_h;
+  p.tile_w = tile_w;
+  p.tiles_w = W / tile_w;
+  p.tiles_m = p.tiles_w * ((H + tile_h - 1) / tile_h);
+  p.tiles_n = (n_out + block_n - 1) / block_n;
+  p.nb0 = batch;
+  p.b_batched = 0;
+  p.b_tap_rows = cout_pad;
+  p.total_tiles = p.tiles_m * p.tiles_n * batch;
+  {
+    uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)W, (uint64_t)H, (uint64_t)batch};
+    uint64_t strides[3] = {(uint64_t)in_ld, (uint64_t)in_ld * W, (uint64_t)in_ld * W * H};
+    uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, 1};
+    int rc = encode_tmap4(&p.tma_a, in, fmt, dims, strides, box, err, errlen);
+    if (rc) return rc;
+  }
+  {
+    GemmOperand B;
+    B.ptr = wt;
+    B.mode = OP_KMAJOR;
+    B.ld = c_in;
+    B.mn_extent = (long long)p.num_taps * cout_pad;
+    B.k_extent = c_in;
+    int rc = encode_operand(&p.tma_b, B, block_n, fmt, err, errlen);
+    if (rc) return rc;
+  }
+  plan->flops = 2.0 * H * W * (double)n_out * c_in * p.num_taps * batch;
+  GemmEpilogue e = epi;
+  return finish_plan(plan, e, block_n, num_sms, err, errlen);
+}
+
+void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+}
+
+}  // namespace pxr

@@ -1,0 +1,111 @@
+// Launchers of the non-GEMM kernels of the hot path (gather / pointwise / reduction; HBM-bound).
+// Every launcher enqueues on `st` and returns; none synchronises.  Layouts: decoder activations are NHWC fp16
+// ([pixels, C], C a multiple of 64); the CLIP residual stream is fp32 [tokens, W]; images are planar fp32 [3,H,W].
+// Gradient tensors in fp16 carry grad_scale * dL (see DESIGN.md "fp16 backward").
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pxr {
+
+typedef __half act_t;
+
+// ------------------------------------------------------------------ VQGAN drawer (vqgan.py:60-64, 190-195)
+// Nearest codebook row per latent position (exact fp32), straight-through output as NHWC fp16.
+//   z: [C, hw] fp32 (NCHW of the reference's z with N=1); cbT: [C, n_e] fp32; c2: [n_e] = sum_k cb^2
+//   part_d/part_i: scratch [hw, n_chunks]; idx: [hw]; zq: [hw, C] fp16; cb: [n_e, C] fp32
+void vq_nearest(const float* z, const float* cbT, const float* c2, const float* cb, int C, int hw, int n_e,
+                float* part_d, int* part_i, int* idx, act_t* zq, cudaStream_t st);
+// z_grad[C, hw] fp32 = dzq[hw, C] fp16 / grad_scale   (ReplaceGrad: gradient of z_q goes to z unchanged)
+void vq_backward(const act_t* dzq, float inv_scale, int C, int hw, float* z_grad, cudaStream_t st);
+
+// GroupNorm(32, C, eps) [+ swish] over NHWC fp16.  stats: [32][2] (mean, rstd); part: scratch [nblk][32][2].
+int gn_num_partials(int pixels, int C);
+void gn_stats(const act_t* x, int pixels, int C, float eps, float* part, float* stats, cudaStream_t st);
+void gn_apply(const act_t* x, const float* stats, const float* gamma, const float* beta, int pixels, int C, int swish,
+              act_t* y, cudaStream_t st);
+// dx = GroupNorm'(x) applied to dy (through swish when set) [+ dres]; part2 scratch like gn_stats.
+void gn_backward(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
+                 int pixels, int C, int swish, const act_t* dres, float* part, float* gstats, act_t* dx,
+                 cudaStream_t st);
+
+void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st);        // nearest, [H,W,C]->[2H,2W,C]
+void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st);       // adjoint: [2H,2W,C]->[H,W,C]
+
+// conv_out result [pixels, ld] fp32 (3 valid channels) -> image [3, pixels] = clamp((x+1)/2, 0, 1); pre = unclamped.
+void image_finish(const float* conv_out, int ld, int pixels, float* pre, float* img, cudaStream_t st);
+// ClampWithGrad backward (vqgan.py:76-79) + d/dx of (x+1)/2 -> fp16 [pixels, ld] (ld >= 3; other channels untouched)
+void image_finish_backward(const float* g_img, const float* pre, int pixels, int ld, act_t* g_out, cudaStream_t st);
+
+// FastPixelDrawer.synth (fast_pixeldrawer.py:89-91): nearest upsample [3,rows,cols] -> [3,H,W] + clamp; and adjoint.
+void pixel_synth(const float* z, int rows, int cols, int H, int W, float* pre, float* img, cudaStream_t st);
+void pixel_synth_backward(const float* g_img, const float* pre, int rows, int cols, int H, int W, float inv_scale,
+                          float* z_grad, cudaStream_t st);
+
+// ------------------------------------------------------------------ MakeCutouts (pixray.py:445-511)
+// (AdaptiveAvgPool2d + AdaptiveMaxPool2d) / 2 of the whole image, once (pixray.py:463); argmax kept for backward.
+void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* argmax, cudaStream_t st);
+void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st);
+
+struct CutoutArgs {
+  const float* pooled;     // [3, cs, cs]
+  const float* minv;       // [n_local, 9] src_pix <- dst_pix homographies (device)
+  const float* noise_facs; // [n_local]            (noise_mode 1)
+  const float* noise;      // [n_local, 3, cs, cs] (noise_mode 1)
+  int noise_mode;          // 0 none, 1 explicit facs + noise, 2 engine Philox (seed, iter)
+  float noise_fac;         // U(0, noise_fac) upper bound for mode 2 (pixray.py:439)
+  int cs, n_local, first_global, cutn_zoom, zoom_padding;
+  float fill;
+  uint64_t seed;
+  int iter;
+};
+int cutout_num_blocks(int n_local, int cs);
+// batch [n_local,3,cs,cs] fp32; block partial min/max (+ element index) for the global range normalise (slip.py:21-36)
+void cutout_forward(const CutoutArgs& a, float* batch, float* part_min, float* part_max, int* part_imin,
+                    int* part_imax, cudaStream_t st);
+// range[0]=min, range[1]=R (max of x-min, 1 if zero), irange[0]=argmin elem, irange[1]=argmax elem
+void minmax_reduce(const float* batch_or_null, const float* part_min, const float* part_max, const int* part_imin,
+                   const int* part_imax, int nparts, float* range, int* irange, cudaStream_t st);
+// patches[(n*gp + py)*gp + px, (c*P + iy)*P + ix] = ((x - min)/R - mean_c)/std_c   (slip.py:52-60 + conv1 im2col)
+void patchify_forward(const float* batch, const float* range, int n, int cs, int P, int ld, act_t* patches,
+                      cudaStream_t st);
+// g_batch (=|+=) d/d(batch) of the direct term; sums[0] += sum g_a, sums[1] += sum g_a * a / R  (fp32 atomics)
+void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
+                       int accumulate, float* g_batch, float* sums, cudaStream_t st);
+// adds the argmin / argmax terms of the global range normalise, then scatters through the bilinear taps
+void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* range, const int* irange,
+                     const float* sums, float* g_pooled, cudaStream_t st);
+
+// ------------------------------------------------------------------ CLIP ViT (slip.py:62-66; SLIP/models.py:18-64)
+// y = LN(x [+ pos[row % T]]) * gamma + beta ; x fp32 [rows, W]; outputs optional fp16 / fp32; stats [rows][2]
+void layernorm_forward(const float* x, const float* pos, int T, const float* gamma, const float* beta, int rows, int W,
+                       float eps, act_t* y16, float* y32, float* stats, cudaStream_t st);
+// gx (+)= LN'(x) applied to dy (fp16, scaled); also writes gx16 = fp16(gx).  accumulate=0 overwrites gx.
+void layernorm_backward(const act_t* dy, const float* x, const float* pos, int T, const float* stats,
+                        const float* gamma, int rows, int W, int accumulate, float* gx, act_t* gx16, cudaStream_t st);
+// in-place row softmax over the first `cols` of each row of length ld (pad columns zeroed); rows total
+void softmax_forward(act_t* s, int rows, int cols, int ld, cudaStream_t st);
+void softmax_backward(const act_t* p, act_t* dp_to_ds, int rows, int cols, int ld, cudaStream_t st);
+// ln_post on the class token + projection (openai-CLIP VisionTransformer tail) -> e [B, D] fp32
+void clip_head_forward(const float* x, int T, int W, int D, const float* gamma, const float* beta, const float* proj,
+                       int B, float eps, float* stats, float* e, cudaStream_t st);
+// gx[B*T, W] fp32 = 0 except class rows; gx16 likewise.  de: [B, D] fp32 (already scaled)
+void clip_head_backward(const float* de, const float* x, int T, int W, int D, const float* stats, const float* gamma,
+                        const float* proj, int B, float* gx, act_t* gx16, cudaStream_t st);
+// Prompt.forward for all prompts of one perceptor + its gradient w.r.t. the un-normalised embeds.
+//   e [B, D]; prompts [n, D] (unit rows), weights/stops [n]; losses [n] (+= partial, caller zeroes); de [B, D]
+void prompt_loss(const float* e, int B, int D, const float* prompts, const float* weights, const float* stops, int n,
+                 int cutn_global, float grad_scale, float* e_unit, float* losses, float* de, cudaStream_t st);
+
+// ------------------------------------------------------------------ optimiser (pixray.py:538-539, 1484-1487)
+// Adam (bias-corrected, torch.optim.Adam semantics) on z with gradient g * inv_scale, then clip_z to per-channel
+// [zmin, zmax] (vqgan.py:202-204) or [0,1] when zmin == nullptr && clip01.
+void adam_clip_step(float* z, float* m, float* v, const float* g, float inv_scale, int n, int per_channel,
+                    const float* zmin, const float* zmax, int clip01, float lr, float b1, float b2, float eps, int t,
+                    cudaStream_t st);
+
+void fill_f32(float* p, float v, long long n, cudaStream_t st);
+void cast_f32_to_f16(const float* x, act_t* y, long long n, float scale, cudaStream_t st);
+
+}  // namespace pxr

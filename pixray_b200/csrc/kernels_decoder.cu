@@ -1,0 +1,474 @@
+// VQGAN-drawer side kernels: nearest-code search, GroupNorm(+swish) fwd/bwd, nearest upsample and its adjoint,
+// image finish (clamp_with_grad) and the pixel drawer.  All HBM/L2-bound; vectorised 16-byte accesses on NHWC fp16.
+#include "kernels.cuh"
+#include <cfloat>
+
+namespace pxr {
+
+namespace {
+
+constexpr int VQ_POS = 16;    // latent positions per block
+constexpr int VQ_CODES = 1024;  // codes per block (4 per thread)
+
+// grid (n_e / VQ_CODES, ceil(hw / VQ_POS)), block 256.
+__global__ void __launch_bounds__(256) vq_partial_kernel(const float* __restrict__ z, const float* __restrict__ cbT,
+                                                         const float* __restrict__ c2, int C, int hw, int n_e,
+                                                         int n_chunks, float* __restrict__ part_d,
+                                                         int* __restrict__ part_i) {
+  extern __shared__ float xs[];  // [C][VQ_POS]
+  __shared__ float x2[VQ_POS];
+  __shared__ float red_d[8][VQ_POS];
+  __shared__ int red_i[8][VQ_POS];
+  const int p0 = blockIdx.y * VQ_POS;
+  const int j0 = blockIdx.x * VQ_CODES;
+  for (int i = threadIdx.x; i < C * VQ_POS; i += 256) {
+    int k = i / VQ_POS, p = i % VQ_POS;
+    xs[i] = (p0 + p < hw) ? z[(size_t)k * hw + p0 + p] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < VQ_POS) {
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s += xs[k * VQ_POS + threadIdx.x] * xs[k * VQ_POS + threadIdx.x];
+    x2[threadIdx.x] = s;
+  }
+  float acc[4][VQ_POS];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int p = 0; p < VQ_POS; ++p) acc[c][p] = 0.f;
+  for (int k = 0; k < C; ++k) {
+    float cv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int j = j0 + threadIdx.x + 256 * c;
+      cv[c] = j < n_e ? cbT[(size_t)k * n_e + j] : 0.f;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(xs + k * VQ_POS);
+#pragma unroll
+    for (int p4 = 0; p4 < VQ_POS / 4; ++p4) {
+      float4 xv = xr[p4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[c][4 * p4 + 0] = fmaf(xv.x, cv[c], acc[c][4 * p4 + 0]);
+        acc[c][4 * p4 + 1] = fmaf(xv.y, cv[c], acc[c][4 * p4 + 1]);
+        acc[c][4 * p4 + 2] = fmaf(xv.z, cv[c], acc[c][4 * p4 + 2]);
+        acc[c][4 * p4 + 3] = fmaf(xv.w, cv[c], acc[c][4 * p4 + 3]);
+      }
+    }
+  }
+  __syncthreads();
+  // d = (|x|^2 + |c|^2) - 2 x.c   (vqgan.py:61), first-minimum wins ties like argmin
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int p = 0; p < VQ_POS; ++p) {
+    float best = FLT_MAX;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int j = j0 + threadIdx.x + 256 * c;
+      if (j < n_e) {
+        float d = (x2[p] + c2[j]) - 2.f * acc[c][p];
+        if (d < best || (d == best && j < bi)) {
+          best = d;
+          bi = j;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float od = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < best || (od == best && oi < bi)) {
+        best = od;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      red_d[warp][p] = best;
+      red_i[warp][p] = bi;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < VQ_POS && p0 + threadIdx.x < hw) {
+    float best = red_d[0][threadIdx.x];
+    int bi = red_i[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) {
+      float od = red_d[w][threadIdx.x];
+      int oi = red_i[w][threadIdx.x];
+      if (od < best || (od == best && oi < bi)) {
+        best = od;
+        bi = oi;
+      }
+    }
+    part_d[(size_t)(p0 + threadIdx.x) * n_chunks + blockIdx.x] = best;
+    part_i[(size_t)(p0 + threadIdx.x) * n_chunks + blockIdx.x] = bi;
+  }
+}
+
+// one block per position: final argmin over chunks, gather the code row as fp16
+__global__ void vq_final_kernel(const float* __restrict__ part_d, const int* __restrict__ part_i, int n_chunks,
+                                const float* __restrict__ cb, int C, int* __restrict__ idx, act_t* __restrict__ zq) {
+  const int p = blockIdx.x;
+  __shared__ int s_idx;
+  if (threadIdx.x == 0) {
+    float best = part_d[(size_t)p * n_chunks];
+    int bi = part_i[(size_t)p * n_chunks];
+    for (int c = 1; c < n_chunks; ++c) {
+      float od = part_d[(size_t)p * n_chunks + c];
+      int oi = part_i[(size_t)p * n_chunks + c];
+      if (od < best || (od == best && oi < bi)) {
+        best = od;
+        bi = oi;
+      }
+    }
+    s_idx = bi;
+    idx[p] = bi;
+  }
+  __syncthreads();
+  const float* row = cb + (size_t)s_idx * C;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) zq[(size_t)p * C + k] = __float2half_rn(row[k]);
+}
+
+__global__ void vq_backward_kernel(const act_t* __restrict__ dzq, float inv_scale, int C, int hw,
+                                   float* __restrict__ z_grad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [C, hw]
+  if (i >= C * hw) return;
+  int k = i / hw, p = i % hw;
+  z_grad[i] = __half2float(dzq[(size_t)p * C + k]) * inv_scale;
+}
+
+// ------------------------------------------------------------------ GroupNorm
+constexpr int GN_G = 32;
+constexpr int GN_ROWS_PER_BLOCK = 256;  // pixels per block
+
+__device__ __forceinline__ void load8(const act_t* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(act_t* p, const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Accumulates, per group, sum(a) and sum(b) where (a, b) = F(element).  MODE 0: (x, x^2); MODE 1: backward sums
+// (dxh, dxh * xh).  Block: 256 threads = (256 / (C/8)) pixel lanes x (C/8) channel vectors.
+template <int MODE>
+__global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict__ x, const act_t* __restrict__ dy,
+                                                         const float* __restrict__ stats,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int pixels, int C, int swish,
+                                                         float* __restrict__ part) {
+  __shared__ float acc[GN_G][2];
+  if (threadIdx.x < GN_G * 2) (&acc[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int vecs = C / 8, cpg = C / GN_G;
+  const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = 256 / vecs;
+  const int c0 = vc * 8;
+  const int p_begin = blockIdx.x * GN_ROWS_PER_BLOCK;
+  const int p_end = min(pixels, p_begin + GN_ROWS_PER_BLOCK);
+  float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [half][a/b] : halves of the 8-vector (cpg == 4 splits groups)
+  float g8[8], b8[8], mean8[8], rstd8[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g8[i] = gamma[c0 + i];
+      b8[i] = beta[c0 + i];
+      int g = (c0 + i) / cpg;
+      mean8[i] = stats[2 * g];
+      rstd8[i] = stats[2 * g + 1];
+    }
+  }
+  for (int p = p_begin + pl; p < p_end; p += plane) {
+    float xv[8];
+    load8(x + (size_t)p * C + c0, xv);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i >> 2][0] += xv[i];
+        s[i >> 2][1] += xv[i] * xv[i];
+      }
+    } else {
+      float dv[8];
+      load8(dy + (size_t)p * C + c0, dv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float xh = (xv[i] - mean8[i]) * rstd8[i];
+        float d = dv[i];
+        if (swish) {
+          float a = g8[i] * xh + b8[i];
+          float sg = 1.f / (1.f + __expf(-a));
+          d *= sg * (1.f + a * (1.f - sg));
+        }
+        float dxh = d * g8[i];
+        s[i >> 2][0] += dxh;
+        s[i >> 2][1] += dxh * xh;
+      }
+    }
+  }
+  if (cpg >= 8) {
+    int g = c0 / cpg;
+    atomicAdd(&acc[g][0], s[0][0] + s[1][0]);
+    atomicAdd(&acc[g][1], s[0][1] + s[1][1]);
+  } else {  // cpg == 4
+    int g = c0 / 4;
+    atomicAdd(&acc[g][0], s[0][0]);
+    atomicAdd(&acc[g][1], s[0][1]);
+    atomicAdd(&acc[g + 1][0], s[1][0]);
+    atomicAdd(&acc[g + 1][1], s[1][1]);
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_G * 2) part[(size_t)blockIdx.x * GN_G * 2 + threadIdx.x] = (&acc[0][0])[threadIdx.x];
+}
+
+// MODE 0: stats[g] = (mean, rstd).  MODE 1: gstats[g] = (mean dxh, mean dxh*xh).   One block of 64 threads.
+template <int MODE>
+__global__ void gn_final_kernel(const float* __restrict__ part, int nblk, double count, float eps,
+                                float* __restrict__ out) {
+  int t = threadIdx.x;  // 0..63 : (group, which)
+  if (t >= GN_G * 2) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)part[(size_t)b * GN_G * 2 + t];
+  __shared__ double sh[GN_G * 2];
+  sh[t] = s / count;
+  __syncthreads();
+  if (MODE == 0) {
+    if ((t & 1) == 0) {
+      double mean = sh[t], ex2 = sh[t + 1];
+      double var = ex2 - mean * mean;
+      if (var < 0) var = 0;
+      out[t] = (float)mean;
+      out[t + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  } else {
+    out[t] = (float)sh[t];
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       long long nvec, int C, int swish, act_t* __restrict__ y) {
+  const int cpg = C / GN_G, vecs = C / 8;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % vecs) * 8;
+    float xv[8];
+    load8(x + v * 8, xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int g = (c0 + i) / cpg;
+      float a = (xv[i] - stats[2 * g]) * stats[2 * g + 1] * gamma[c0 + i] + beta[c0 + i];
+      xv[i] = swish ? a / (1.f + __expf(-a)) : a;
+    }
+    store8(y + v * 8, xv);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const act_t* __restrict__ dy, const act_t* __restrict__ x,
+                                                           const float* __restrict__ stats,
+                                                           const float* __restrict__ gstats,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, long long nvec, int C,
+                                                           int swish, const act_t* __restrict__ dres,
+                                                           act_t* __restrict__ dx) {
+  const int cpg = C / GN_G, vecs = C / 8;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % vecs) * 8;
+    float xv[8], dv[8], rv[8];
+    load8(x + v * 8, xv);
+    load8(dy + v * 8, dv);
+    if (dres) load8(dres + v * 8, rv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int g = (c0 + i) / cpg;
+      float rstd = stats[2 * g + 1];
+      float xh = (xv[i] - stats[2 * g]) * rstd;
+      float d = dv[i];
+      if (swish) {
+        float a = gamma[c0 + i] * xh + beta[c0 + i];
+        float sg = 1.f / (1.f + __expf(-a));
+        d *= sg * (1.f + a * (1.f - sg));
+      }
+      float dxh = d * gamma[c0 + i];
+      float r = rstd * (dxh - gstats[2 * g] - xh * gstats[2 * g + 1]);
+      xv[i] = dres ? r + rv[i] : r;
+    }
+    store8(dx + v * 8, xv);
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const act_t* __restrict__ x, int H, int W, int C,
+                                                         act_t* __restrict__ y) {
+  const int vecs = C / 8;
+  const long long n = (long long)4 * H * W * vecs;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    int vc = (int)(v % vecs);
+    long long p = v / vecs;
+    int ox = (int)(p % (2 * W)), oy = (int)(p / (2 * W));
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)(oy >> 1) * W + (ox >> 1)) * C) + vc;
+    reinterpret_cast<uint4*>(y)[v] = *src;
+  }
+}
+
+__global__ void __launch_bounds__(256) downsum2x_kernel(const act_t* __restrict__ gy, int H, int W, int C,
+                                                        act_t* __restrict__ gx) {
+  const int vecs = C / 8;
+  const long long n = (long long)H * W * vecs;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    int vc = (int)(v % vecs);
+    long long p = v / vecs;
+    int ix = (int)(p % W), iy = (int)(p / W);
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float t[8];
+        load8(gy + ((size_t)(2 * iy + dy) * (2 * W) + 2 * ix + dx) * C + vc * 8, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += t[i];
+      }
+    store8(gx + v * 8, s);
+  }
+}
+
+__global__ void image_finish_kernel(const float* __restrict__ conv_out, int ld, int pixels, float* __restrict__ pre,
+                                    float* __restrict__ img) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = (conv_out[(size_t)p * ld + c] + 1.f) / 2.f;  // decode(z_q).add(1).div(2), vqgan.py:195
+    pre[(size_t)c * pixels + p] = v;
+    img[(size_t)c * pixels + p] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+}
+
+__global__ void image_finish_bwd_kernel(const float* __restrict__ g_img, const float* __restrict__ pre, int pixels,
+                                        int ld, act_t* __restrict__ g_out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float g = g_img[(size_t)c * pixels + p];
+    float v = pre[(size_t)c * pixels + p];
+    float cl = fminf(fmaxf(v, 0.f), 1.f);
+    float keep = (g * (v - cl) >= 0.f) ? 1.f : 0.f;  // vqgan.py:79
+    g_out[(size_t)p * ld + c] = __float2half_rn(0.5f * g * keep);
+  }
+}
+
+__global__ void pixel_synth_kernel(const float* __restrict__ z, int rows, int cols, int H, int W,
+                                   float* __restrict__ pre, float* __restrict__ img) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * H * W) return;
+  int x = i % W, y = (i / W) % H, c = i / (W * H);
+  // F.interpolate(mode="nearest"): src = floor(dst * in / out)  (fast_pixeldrawer.py:90)
+  int sy = min((int)floorf(y * ((float)rows / H)), rows - 1);
+  int sx = min((int)floorf(x * ((float)cols / W)), cols - 1);
+  float v = z[((size_t)c * rows + sy) * cols + sx];
+  pre[i] = v;
+  img[i] = fminf(fmaxf(v, 0.f), 1.f);
+}
+
+__global__ void pixel_synth_bwd_kernel(const float* __restrict__ g_img, const float* __restrict__ pre, int rows,
+                                       int cols, int H, int W, float inv_scale, float* __restrict__ z_grad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [3, rows, cols]
+  if (i >= 3 * rows * cols) return;
+  int sx = i % cols, sy = (i / cols) % rows, c = i / (cols * rows);
+  // all output pixels whose nearest source is (sy, sx)
+  float s = 0.f;
+  int y0 = (int)ceilf(sy * ((float)H / rows)) - 1, y1 = (int)ceilf((sy + 1) * ((float)H / rows)) + 1;
+  int x0 = (int)ceilf(sx * ((float)W / cols)) - 1, x1 = (int)ceilf((sx + 1) * ((float)W / cols)) + 1;
+  for (int y = max(0, y0); y < min(H, y1); ++y) {
+    if (min((int)floorf(y * ((float)rows / H)), rows - 1) != sy) continue;
+    for (int x = max(0, x0); x < min(W, x1); ++x) {
+      if (min((int)floorf(x * ((float)cols / W)), cols - 1) != sx) continue;
+      size_t o = ((size_t)c * H + y) * W + x;
+      float g = g_img[o], v = pre[o];
+      float cl = fminf(fmaxf(v, 0.f), 1.f);
+      if (g * (v - cl) >= 0.f) s += g;
+    }
+  }
+  z_grad[i] = s * inv_scale;
+}
+
+inline int grid_for(long long n, int block, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+void vq_nearest(const float* z, const float* cbT, const float* c2, const float* cb, int C, int hw, int n_e,
+                float* part_d, int* part_i, int* idx, act_t* zq, cudaStream_t st) {
+  const int n_chunks = (n_e + VQ_CODES - 1) / VQ_CODES;
+  dim3 grid(n_chunks, (hw + VQ_POS - 1) / VQ_POS);
+  vq_partial_kernel<<<grid, 256, C * VQ_POS * sizeof(float), st>>>(z, cbT, c2, C, hw, n_e, n_chunks, part_d, part_i);
+  vq_final_kernel<<<hw, 128, 0, st>>>(part_d, part_i, n_chunks, cb, C, idx, zq);
+}
+
+void vq_backward(const act_t* dzq, float inv_scale, int C, int hw, float* z_grad, cudaStream_t st) {
+  vq_backward_kernel<<<(C * hw + 255) / 256, 256, 0, st>>>(dzq, inv_scale, C, hw, z_grad);
+}
+
+int gn_num_partials(int pixels, int C) { return (pixels + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK; }
+
+void gn_stats(const act_t* x, int pixels, int C, float eps, float* part, float* stats, cudaStream_t st) {
+  const int nblk = gn_num_partials(pixels, C);
+  gn_partial_kernel<0><<<nblk, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, part);
+  gn_final_kernel<0><<<1, 64, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), eps, stats);
+}
+
+void gn_apply(const act_t* x, const float* stats, const float* gamma, const float* beta, int pixels, int C, int swish,
+              act_t* y, cudaStream_t st) {
+  const long long nvec = (long long)pixels * C / 8;
+  gn_apply_kernel<<<grid_for(nvec, 256), 256, 0, st>>>(x, stats, gamma, beta, nvec, C, swish, y);
+}
+
+void gn_backward(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
+                 int pixels, int C, int swish, const act_t* dres, float* part, float* gstats, act_t* dx,
+                 cudaStream_t st) {
+  const int nblk = gn_num_partials(pixels, C);
+  gn_partial_kernel<1><<<nblk, 256, 0, st>>>(x, dy, stats, gamma, beta, pixels, C, swish, part);
+  gn_final_kernel<1><<<1, 64, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), 0.f, gstats);
+  const long long nvec = (long long)pixels * C / 8;
+  gn_bwd_apply_kernel<<<grid_for(nvec, 256), 256, 0, st>>>(dy, x, stats, gstats, gamma, beta, nvec, C, swish, dres,
+                                                           dx);
+}
+
+void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st) {
+  upsample2x_kernel<<<grid_for((long long)4 * H * W * C / 8, 256), 256, 0, st>>>(x, H, W, C, y);
+}
+void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st) {
+  downsum2x_kernel<<<grid_for((long long)H * W * C / 8, 256), 256, 0, st>>>(gy, H, W, C, gx);
+}
+
+void image_finish(const float* conv_out, int ld, int pixels, float* pre, float* img, cudaStream_t st) {
+  image_finish_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(conv_out, ld, pixels, pre, img);
+}
+void image_finish_backward(const float* g_img, const float* pre, int pixels, int ld, act_t* g_out, cudaStream_t st) {
+  image_finish_bwd_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(g_img, pre, pixels, ld, g_out);
+}
+
+void pixel_synth(const float* z, int rows, int cols, int H, int W, float* pre, float* img, cudaStream_t st) {
+  pixel_synth_kernel<<<(3 * H * W + 255) / 256, 256, 0, st>>>(z, rows, cols, H, W, pre, img);
+}
+void pixel_synth_backward(const float* g_img, const float* pre, int rows, int cols, int H, int W, float inv_scale,
+                          float* z_grad, cudaStream_t st) {
+  pixel_synth_bwd_kernel<<<(3 * rows * cols + 255) / 256, 256, 0, st>>>(g_img, pre, rows, cols, H, W, inv_scale,
+                                                                        z_grad);
+}
+
+}  // namespace pxr

@@ -1,0 +1,86 @@
+// C-ABI test hooks: expose single kernels of the engine so tests/ can check each against the oracle / torch.
+// These are not part of the reference-facing surface (include/pixray_b200.h lists them under "test hooks").
+#include "../../include/pixray_b200.h"
+#include "gemm_tc.cuh"
+#include <cstdio>
+#include <cstring>
+
+using namespace pxr;
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static void fill_epilogue(GemmEpilogue& e, const pxr_test_gemm_desc* d) {
+  e.alpha = d->alpha;
+  e.bias = d->bias;
+  e.bias_per_row = d->bias_per_row;
+  e.act = d->act;
+  e.aux_in = static_cast<const __half*>(d->aux_in);
+  e.aux_out = static_cast<__half*>(d->aux_out);
+  e.res_f32 = d->res_f32;
+  e.res_f16 = static_cast<const __half*>(d->res_f16);
+  e.out_f32 = d->out_f32;
+  e.out_f16 = static_cast<__half*>(d->out_f16);
+  e.ldc = d->ldc;
+  e.bs0 = d->c_bs0;
+  e.bs1 = d->c_bs1;
+}
+
+extern "C" int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen) {
+  GemmOperand A, B;
+  A.ptr = d->a;
+  A.mode = d->a_mode;
+  A.ld = d->lda;
+  A.mn_extent = d->a_mn_extent;
+  A.k_extent = d->a_k_extent;
+  A.nb0 = d->nb0;
+  A.nb1 = d->nb1;
+  A.bs0 = d->a_bs0;
+  A.bs1 = d->a_bs1;
+  B.ptr = d->b;
+  B.mode = d->b_mode;
+  B.ld = d->ldb;
+  B.mn_extent = d->b_mn_extent;
+  B.k_extent = d->b_k_extent;
+  B.nb0 = d->b_batched ? d->nb0 : 1;
+  B.nb1 = d->b_batched ? d->nb1 : 1;
+  B.bs0 = d->b_bs0;
+  B.bs1 = d->b_bs1;
+  GemmEpilogue e;
+  fill_epilogue(e, d);
+  GemmPlan plan;
+  int rc = gemm_plan_make(&plan, A, B, d->M, d->N, d->K, e, d->block_n, d->fmt, num_sms(), err, errlen);
+  if (rc) return rc;
+  for (int i = 0; i < (d->repeat > 0 ? d->repeat : 1); ++i) gemm_launch(plan, static_cast<cudaStream_t>(d->stream));
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    if (err) snprintf(err, errlen, "launch failed: %s", cudaGetErrorString(ce));
+    return -100;
+  }
+  return 0;
+}
+
+extern "C" int pxr_test_conv(const pxr_test_gemm_desc* d, int batch, int H, int W, int c_in, int cout_pad, int ksize,
+                             char* err, int errlen) {
+  GemmEpilogue e;
+  fill_epilogue(e, d);
+  GemmPlan plan;
+  int rc = conv_plan_make(&plan, d->a, d->lda, batch, H, W, c_in, d->b, cout_pad, d->N, ksize, e, d->block_n, d->fmt,
+                          num_sms(), err, errlen);
+  if (rc) return rc;
+  for (int i = 0; i < (d->repeat > 0 ? d->repeat : 1); ++i) gemm_launch(plan, static_cast<cudaStream_t>(d->stream));
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    if (err) snprintf(err, errlen, "launch failed: %s", cudaGetErrorString(ce));
+    return -100;
+  }
+  return 0;
+}

@@ -1,0 +1,155 @@
+"""GPU parity of the tcgen05 GEMM / implicit-GEMM conv kernel against torch fp32 matmul of the same fp16 inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gemm_util import run_conv, run_gemm
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).half()
+
+
+def _check(out, ref, tol, name):
+    err = (out.float() - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    print(f"{name}: max_abs_err={err:.3e} ref_max={mag:.3e}")
+    assert err <= tol * max(mag, 1.0), f"{name}: err {err} vs ref max {mag}"
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(300, 256, 192, 128), (128, 64, 64, 64), (197, 197, 64, 208), (1000, 768, 768, 256)])
+def test_gemm_kmajor(M, N, K, bn):
+    torch.manual_seed(0)
+    A, B = _rand(M, K), _rand(N, K)
+    out = torch.full((M, N), 7.0, device="cuda")
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=bn, out_f32=out, ldc=N)
+    _check(out, A.float() @ B.float().T, 2e-3, f"kmajor {M}x{N}x{K}")
+
+
+def test_gemm_epilogue_bias_gelu_residual():
+    torch.manual_seed(1)
+    M, N, K = 520, 384, 256
+    A, B = _rand(M, K, scale=0.2), _rand(N, K, scale=0.2)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    out16 = torch.zeros(M, N, device="cuda", dtype=torch.half)
+    out32 = torch.zeros(M, N, device="cuda")
+    aux = torch.zeros(M, N, device="cuda", dtype=torch.half)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, alpha=0.5, bias=bias, act=1, aux_out=aux, res_f32=res,
+             out_f32=out32, out_f16=out16, ldc=N)
+    u = 0.5 * (A.float() @ B.float().T) + bias
+    ref = u * torch.sigmoid(1.702 * u) + res
+    _check(aux, u, 2e-3, "aux(pre-act)")
+    _check(out32, ref, 2e-3, "gelu+res f32")
+    _check(out16, ref, 4e-3, "gelu+res f16")
+    # backward epilogue: multiply by quickgelu'(u)
+    g = torch.zeros(M, N, device="cuda")
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, act=2, aux_in=aux, out_f32=g, ldc=N)
+    uf = aux.float()
+    s = torch.sigmoid(1.702 * uf)
+    ref_g = (A.float() @ B.float().T) * (s * (1 + 1.702 * uf * (1 - s)))
+    _check(g, ref_g, 2e-3, "gelu bwd")
+
+
+def test_gemm_bias_per_row_and_tail():
+    torch.manual_seed(2)
+    M, N, K = 512, 250, 128
+    A, B = _rand(M, K), _rand(N, K)
+    bias = torch.randn(M, device="cuda")
+    out = torch.zeros(M, 256, device="cuda", dtype=torch.half)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, bias=bias, bias_per_row=1, out_f16=out, ldc=256)
+    ref = A.float() @ B.float().T + bias[:, None]
+    _check(out[:, :N], ref, 4e-3, "row-bias tail")
+    assert out[:, N:].abs().max().item() == 0.0
+
+
+def test_gemm_mn_major_b():
+    torch.manual_seed(3)
+    M, N, K = 260, 256, 200
+    A = _rand(M, K)
+    Bt = _rand(K, N)  # stored [K, N]: n contiguous -> MN-major B
+    out = torch.zeros(M, N, device="cuda")
+    run_gemm(A, Bt, M, N, K, lda=K, b_mode=1, ldb=N, block_n=128, out_f32=out, ldc=N)
+    _check(out, A.float() @ Bt.float(), 2e-3, "MN-major B")
+
+
+def test_gemm_mn_major_a():
+    torch.manual_seed(4)
+    M, N, K = 197, 64, 197
+    At = _rand(K, 208)  # stored [K, M(ld 208)]: m contiguous -> MN-major A
+    At[:, M:] = 0
+    B = _rand(N, K + 11)[:, :K]  # ld = K+11?  needs ld % 8 == 0 -> use 208
+    Bp = torch.zeros(N, 208, device="cuda", dtype=torch.half)
+    Bp[:, :K] = B
+    out = torch.zeros(M, N, device="cuda")
+    run_gemm(At, Bp, M, N, K, a_mode=1, lda=208, ldb=208, block_n=64, out_f32=out, ldc=N)
+    _check(out, At[:, :M].float().T @ Bp[:, :K].float().T, 2e-3, "MN-major A")
+
+
+def test_gemm_both_mn_major_batched_attention_shapes():
+    """dK = dS^T Q per (image, head): A = dS stored [q, k] (MN-major), B = Q stored [q, d] (MN-major)."""
+    torch.manual_seed(5)
+    imgs, heads, T, d, ldp = 3, 4, 197, 64, 208
+    dS = torch.zeros(imgs, heads, T, ldp, device="cuda", dtype=torch.half)
+    dS[..., :T] = _rand(imgs, heads, T, T, scale=0.1)
+    qkv = _rand(imgs, T, 3 * heads * d)
+    out = torch.zeros(imgs, T, heads * d, device="cuda", dtype=torch.half)
+    run_gemm(dS, qkv, T, d, T, a_mode=1, lda=ldp, a_mn=T, a_k=T, b_mode=1, ldb=3 * heads * d, b_mn=d, b_k=T,
+             nb0=heads, nb1=imgs, a_bs=(T * ldp, heads * T * ldp), b_bs=(d, T * 3 * heads * d), b_batched=1,
+             block_n=64, out_f16=out, ldc=heads * d, c_bs=(d, T * heads * d))
+    q = qkv[..., : heads * d].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    ref = torch.einsum("bhqk,bhqd->bhkd", dS[..., :T].float(), q).permute(0, 2, 1, 3).reshape(imgs, T, heads * d)
+    _check(out, ref, 4e-3, "batched both-MN")
+
+
+def test_gemm_batched_qk():
+    torch.manual_seed(6)
+    imgs, heads, T, d, ldp = 2, 12, 197, 64, 208
+    qkv = _rand(imgs, T, 3 * heads * d)
+    S = torch.zeros(imgs, heads, T, ldp, device="cuda", dtype=torch.half)
+    k_off = qkv.view(-1)[heads * d:]
+    run_gemm(qkv, k_off, T, T, d, lda=3 * heads * d, a_mn=T, a_k=d, ldb=3 * heads * d, b_mn=T, b_k=d, nb0=heads,
+             nb1=imgs, a_bs=(d, T * 3 * heads * d), b_bs=(d, T * 3 * heads * d), b_batched=1, block_n=208,
+             alpha=0.125, out_f16=S, ldc=ldp, c_bs=(T * ldp, heads * T * ldp))
+    q = qkv[..., : heads * d].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    k = qkv[..., heads * d: 2 * heads * d].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    ref = 0.125 * q @ k.transpose(-1, -2)
+    _check(S[..., :T], ref, 4e-3, "batched QK^T")
+    assert S[..., T:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,ks,bn", [(32, 32, 128, 128, 3, 128), (16, 16, 256, 512, 3, 128),
+                                                  (64, 64, 64, 3, 3, 16), (16, 16, 256, 256, 1, 64)])
+def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn):
+    torch.manual_seed(7)
+    x = _rand(1, H, W, Cin, scale=0.5)
+    w = _rand(Cout, Cin, ks, ks, scale=0.05)
+    bias = torch.randn(Cout, device="cuda")
+    cout_pad = max(16, (Cout + 15) // 16 * 16)
+    wt = torch.zeros(ks * ks, cout_pad, Cin, device="cuda", dtype=torch.half)
+    wt[:, :Cout] = w.permute(2, 3, 0, 1).reshape(ks * ks, Cout, Cin)
+    out = torch.zeros(1, H, W, cout_pad, device="cuda")
+    run_conv(x, wt, Cout, cout_pad, ks, block_n=bn, bias=bias, out_f32=out, ldc=cout_pad)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=ks // 2).permute(0, 2, 3, 1)
+    _check(out[..., :Cout], ref, 2e-3, f"conv{ks}x{ks} {H}x{W} {Cin}->{Cout}")
+
+
+def test_gemm_throughput_report():
+    """Not an assertion on speed: prints achieved TFLOP/s for the CLIP-sized GEMMs so the first GPU run is informative."""
+    torch.manual_seed(8)
+    for (M, N, K) in [(12608, 2304, 768), (12608, 3072, 768), (12608, 768, 3072), (12608, 768, 768)]:
+        A, B = _rand(M, K, scale=0.1), _rand(N, K, scale=0.1)
+        out = torch.zeros(M, N, device="cuda", dtype=torch.half)
+        run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=256, out_f16=out, ldc=N, repeat=3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=256, out_f16=out, ldc=N, repeat=20)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        ref = A.float() @ B.float().T
+        _check(out, ref, 4e-3, f"big {M}x{N}x{K}")
+        print(f"GEMM {M}x{N}x{K}: {ms * 1e3:.1f} us  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
