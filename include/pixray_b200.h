@@ -116,6 +116,9 @@ int pxr_z_numel(pxr_handle h, int64_t* out);
 int pxr_z_bounds(pxr_handle h, float* zmin, float* zmax); /* device [z_channels]: codebook per-channel min/max */
 
 /* ---------------------------------------------------------------- test hooks (used only by tests/) */
+/* copy a named internal buffer (e.g. "g_img", "batch", "clip0.gx") to `out` (host or device) */
+int pxr_debug_read(pxr_handle h, const char* name, void* out, int64_t nbytes);
+
 typedef struct {
   const void* a;
   int a_mode; /* 0 K-major, 1 MN-major */

@@ -1,0 +1,1342 @@
+// The engine behind include/pixray_b200.h: owns weights (repacked to the kernels' layouts), every activation /
+// gradient buffer, the pre-built kernel plans ("op lists") for forward and the hand-written backward chain, Adam state
+// and the per-iteration cutout parameters.  One handle = one rank = one CUDA stream.
+//
+// Hot path order per iteration (pixray.py:1243-1406, 1436-1512):
+//   drawer.synth -> pool -> cutouts -> [per perceptor: patchify -> ViT -> head -> Prompt loss]
+//   -> backward of all of the above by hand (dgrad only: every network is frozen, vqgan.py:125, slip.py:176)
+//   -> [allreduce z.grad] -> Adam -> clip_z
+#include "engine.cuh"
+#include "transforms.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+namespace pxr {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ===================================================================================================== Engine
+class Engine {
+ public:
+  pxr_config cfg;
+  cudaStream_t st = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = 148;
+  int fmt = 0;
+  float S = 4096.f;  // grad scale
+  std::map<std::string, HostWeight> weights[3];
+  std::vector<void*> allocs;
+  bool finalized = false;
+  std::map<std::string, std::pair<void*, size_t>> dbg;  // named internal buffers (tests / debugging)
+  void reg(const std::string& n, void* p, size_t bytes) { dbg[n] = {p, bytes}; }
+
+  // sharding
+  int n_local = 0, first_global = 0;
+
+  // ---- drawer
+  float* z_buf = nullptr;   // engine copy of z
+  float* z_grad = nullptr;
+  float *adam_m = nullptr, *adam_v = nullptr;
+  int adam_t = 0;
+  int64_t z_numel = 0;
+  float *zmin = nullptr, *zmax = nullptr;  // [z_channels]
+  float *img = nullptr, *img_pre = nullptr, *g_img = nullptr;  // [3,H,W]
+  OpList drawer_fwd, drawer_bwd;  // bwd stored in execution order
+
+  // ---- cutouts
+  float *pooled = nullptr, *g_pooled = nullptr, *batch = nullptr, *g_batch = nullptr;
+  int* pool_argmax = nullptr;
+  float *part_min = nullptr, *part_max = nullptr, *range = nullptr, *sums = nullptr;
+  int *part_imin = nullptr, *part_imax = nullptr, *irange = nullptr;
+  int n_parts = 0;
+  static constexpr int RING = 8;
+  float* minv_host[RING] = {nullptr};   // pinned
+  float* facs_host[RING] = {nullptr};
+  cudaEvent_t ring_ev[RING] = {nullptr};
+  int ring_pos = 0;
+  float *minv_dev = nullptr, *facs_dev = nullptr;
+  CutoutArgs cut_args;
+
+  // ---- perceptors
+  struct Clip {
+    pxr_clip_cfg c;
+    int T, np, Kp, ldT, M, B;
+    // weights
+    act_t* conv1 = nullptr;
+    float *cls = nullptr, *pos = nullptr, *proj = nullptr;
+    NormW ln_pre, ln_post;
+    struct Layer {
+      act_t *wqkv, *wo, *wfc, *wproj;
+      float *bqkv, *bo, *bfc, *bproj;
+      NormW ln1, ln2;
+      // saved activations
+      float *x_in, *x_mid, *stats1, *stats2;
+      act_t *qkv, *P, *u;
+    };
+    std::vector<Layer> layers;
+    // buffers
+    act_t *patches, *g_patches, *h16, *o16, *gact, *g4, *gh, *go, *gqkv, *dP, *gx16;
+    float *t, *x_out, *stats_pre, *stats_post, *e, *e_unit, *de, *gx;
+    // prompts
+    float *prompts = nullptr, *pweights = nullptr, *pstops = nullptr, *losses = nullptr;
+    int n_prompts = 0, loss_offset = 0;
+    OpList fwd, bwd;
+  };
+  Clip clip[2];
+  float* losses_dev = nullptr;   // [total prompts]
+  float* losses_host = nullptr;  // pinned
+  int total_prompts = 0;
+
+  // ---- comm (multi-GPU): see comm.cu
+  void* comm = nullptr;
+
+  explicit Engine(const pxr_config& c) : cfg(c) {}
+  ~Engine();
+
+  template <class T>
+  T* dalloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+    PXR_CUDA(cudaMalloc(&p, bytes));
+    if (zero) PXR_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+    allocs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  template <class T>
+  T* upload(const std::vector<T>& v) {
+    T* p = dalloc<T>(v.size(), false);
+    PXR_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    PXR_CUDA(cudaStreamSynchronize(st));  // v may be a temporary
+    return p;
+  }
+  act_t* upload_f16(const std::vector<float>& v) {
+    std::vector<act_t> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2half_rn(v[i]);
+    return upload(h);
+  }
+  const HostWeight& W(int mod, const std::string& name, std::initializer_list<int64_t> dims = {}) {
+    auto it = weights[mod].find(name);
+    if (it == weights[mod].end()) throw EngineError(-40, "missing weight '" + name + "' (module " + std::to_string(mod) + ")");
+    if (dims.size()) {
+      std::vector<int64_t> want(dims);
+      if (it->second.dims != want) {
+        std::string got;
+        for (auto d : it->second.dims) got += std::to_string(d) + ",";
+        throw EngineError(-41, "weight '" + name + "' has shape [" + got + "] which does not match the configured architecture");
+      }
+    }
+    return it->second;
+  }
+
+  void run(OpList& l) {
+    for (size_t i = 0; i < l.ops.size(); ++i) {
+      l.ops[i]();
+      launches += l.launches[i];
+    }
+  }
+  void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw EngineError(-201, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+
+  // ------------------------------------------------------------------ plan helpers
+  static GemmOperand opK(const void* p, long long ld, long long mn, long long k, int nb0 = 1, long long bs0 = 0,
+                         int nb1 = 1, long long bs1 = 0) {
+    GemmOperand o;
+    o.ptr = p;
+    o.mode = OP_KMAJOR;
+    o.ld = ld;
+    o.mn_extent = mn;
+    o.k_extent = k;
+    o.nb0 = nb0;
+    o.nb1 = nb1;
+    o.bs0 = bs0;
+    o.bs1 = bs1;
+    return o;
+  }
+  static GemmOperand opMN(const void* p, long long ld, long long mn, long long k, int nb0 = 1, long long bs0 = 0,
+                          int nb1 = 1, long long bs1 = 0) {
+    GemmOperand o = opK(p, ld, mn, k, nb0, bs0, nb1, bs1);
+    o.mode = OP_MNMAJOR;
+    return o;
+  }
+  static int pick_bn(int N, bool b_mn, long long m_tiles) {
+    int bn;
+    if (N % 256 == 0) bn = 256;
+    else if (N % 128 == 0) bn = 128;
+    else if (N <= 256) bn = round_up(N, b_mn ? 64 : 16);
+    else {
+      int parts = (N + 255) / 256;
+      bn = round_up((N + parts - 1) / parts, b_mn ? 64 : 16);
+    }
+    // few M tiles: prefer more, narrower CTAs
+    while (bn > 64 && bn % 128 == 0 && m_tiles * ((N + bn - 1) / bn) < 96) bn /= 2;
+    return bn;
+  }
+  void add_gemm(OpList& l, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& e,
+                int bn = 0) {
+    if (!bn) bn = pick_bn(N, B.mode == OP_MNMAJOR, (long long)((M + 127) / 128) * A.nb0 * A.nb1);
+    auto plan = std::make_shared<GemmPlan>();
+    char buf[256] = {0};
+    int rc = gemm_plan_make(plan.get(), A, B, M, N, K, e, bn, fmt, num_sms, buf, sizeof buf);
+    if (rc) throw EngineError(rc, std::string("gemm plan: ") + buf);
+    cudaStream_t s = st;
+    l.add(1, [plan, s] { gemm_launch(*plan, s); });
+  }
+  void add_conv(OpList& l, const act_t* in, int H, int Wd, int cin, const act_t* wt, int cout_pad, int n_out, int ks,
+                const GemmEpilogue& e) {
+    int bn = pick_bn(cout_pad < 64 ? cout_pad : n_out, false, (long long)(H * Wd + 127) / 128);
+    if (bn > cout_pad) bn = cout_pad;
+    auto plan = std::make_shared<GemmPlan>();
+    char buf[256] = {0};
+    int rc = conv_plan_make(plan.get(), in, cin, 1, H, Wd, cin, wt, cout_pad, n_out, ks, e, bn, fmt, num_sms, buf,
+                            sizeof buf);
+    if (rc) throw EngineError(rc, std::string("conv plan: ") + buf);
+    cudaStream_t s = st;
+    l.add(1, [plan, s] { gemm_launch(*plan, s); });
+  }
+
+  // ------------------------------------------------------------------ build steps
+  void create();
+  void finalize();
+  void build_vqgan();
+  void build_pixel();
+  void build_cutouts();
+  void build_clip(int i);
+  ConvW load_conv(const std::string& prefix, int cin, int cout, int ks);
+  NormW load_norm(int mod, const std::string& prefix, int c);
+  Act new_act(int H, int Wd, int C) {
+    Act a;
+    a.H = H;
+    a.W = Wd;
+    a.C = C;
+    a.p = dalloc<act_t>((size_t)H * Wd * C);
+    a.g = dalloc<act_t>((size_t)H * Wd * C);
+    return a;
+  }
+  // decoder blocks: append forward ops to drawer_fwd, push the backward closure list (reverse order) to bwd_stack
+  std::vector<OpList> bwd_stack;
+  float* gn_part = nullptr;  // scratch for GN partial sums (sized for the largest layer)
+  Act conv_fwd_bwd(const Act& x, const ConvW& w, OpList& bwd);
+  Act resblock(const Act& x, const std::string& prefix, int cin, int cout);
+  Act attnblock(const Act& x, const std::string& prefix, int c);
+  Act upsample(const Act& x, const std::string& prefix);
+  struct GNSaved {
+    float* stats;
+    float* gstats;
+  };
+  GNSaved add_gn(OpList& l, const Act& x, const NormW& n, int swish, act_t* y);
+
+  // ------------------------------------------------------------------ execution
+  void prepare_cut_params(const pxr_cut_params* p, int iter);
+  void forward_drawer() { run(drawer_fwd); }
+  void forward_cutouts();
+  void forward_clip(int i);
+  void loss_clip(int i);
+  void backward_all();
+  void step(float lr);
+};
+
+Engine::~Engine() {
+  if (st) cudaStreamSynchronize(st);
+  for (void* p : allocs) cudaFree(p);
+  for (int i = 0; i < RING; ++i) {
+    if (minv_host[i]) cudaFreeHost(minv_host[i]);
+    if (facs_host[i]) cudaFreeHost(facs_host[i]);
+    if (ring_ev[i]) cudaEventDestroy(ring_ev[i]);
+  }
+  if (losses_host) cudaFreeHost(losses_host);
+  if (st) cudaStreamDestroy(st);
+}
+
+void Engine::create() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw EngineError(-1, "no CUDA device: pixray_b200 has no CPU fallback");
+  if (cfg.device < 0 || cfg.device >= ndev) throw EngineError(-2, "invalid CUDA device ordinal");
+  PXR_CUDA(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  PXR_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+  if (prop.major != 10) throw EngineError(-3, std::string("pixray_b200 needs an sm_100 GPU (B200); found ") + prop.name);
+  num_sms = prop.multiProcessorCount;
+  PXR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (cfg.world < 1) cfg.world = 1;
+  if (cfg.cutn % cfg.world) throw EngineError(-4, "cutn must be divisible by world");
+  n_local = cfg.cutn / cfg.world;
+  first_global = cfg.rank * n_local;
+  fmt = cfg.op_dtype;
+  if (fmt != PXR_DTYPE_F16) throw EngineError(-5, "only PXR_DTYPE_F16 operands are wired through the pointwise kernels");
+  if (cfg.grad_scale > 0) S = cfg.grad_scale;
+  if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
+  if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
+  if (cfg.adam_eps <= 0) cfg.adam_eps = 1e-8f;
+  if (cfg.cut_size % 4) throw EngineError(-6, "cut_size must be a multiple of 4");
+}
+
+// ===================================================================================================== weights
+NormW Engine::load_norm(int mod, const std::string& prefix, int c) {
+  NormW n;
+  n.gamma = upload(W(mod, prefix + ".weight", {c}).data);
+  n.beta = upload(W(mod, prefix + ".bias", {c}).data);
+  return n;
+}
+
+ConvW Engine::load_conv(const std::string& prefix, int cin, int cout, int ks) {
+  const HostWeight& w = W(PXR_MOD_VQGAN, prefix + ".weight", {cout, cin, ks, ks});
+  const HostWeight& b = W(PXR_MOD_VQGAN, prefix + ".bias", {cout});
+  ConvW c;
+  c.cin = cin;
+  c.cout = cout;
+  c.ks = ks;
+  c.cout_pad = round_up(cout, 16);
+  c.cout_k = round_up(cout, 64);
+  c.cin_rows = round_up(cin, 16);
+  const int taps = ks * ks;
+  if (cin % 64) throw EngineError(-42, "conv '" + prefix + "': input channels must be a multiple of 64");
+  std::vector<float> f((size_t)taps * c.cout_pad * cin, 0.f), d((size_t)taps * c.cin_rows * c.cout_k, 0.f);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int ty = 0; ty < ks; ++ty)
+        for (int tx = 0; tx < ks; ++tx) {
+          float v = w.data[(((size_t)co * cin + ci) * ks + ty) * ks + tx];
+          int t = ty * ks + tx;
+          f[((size_t)t * c.cout_pad + co) * cin + ci] = v;
+          // dgrad: dx[p] = sum_t dy[p + off(t)] * W[.., flipped t]
+          int tf = (ks - 1 - ty) * ks + (ks - 1 - tx);
+          d[((size_t)tf * c.cin_rows + ci) * c.cout_k + co] = v;
+        }
+  c.w = upload_f16(f);
+  c.wd = upload_f16(d);
+  c.bias = upload(b.data);
+  return c;
+}
+
+// ===================================================================================================== VQGAN drawer
+Engine::GNSaved Engine::add_gn(OpList& l, const Act& x, const NormW& n, int swish, act_t* y) {
+  GNSaved s;
+  s.stats = dalloc<float>(64);
+  s.gstats = dalloc<float>(64);
+  const act_t* xp = x.p;
+  int px = x.pixels(), C = x.C;
+  float* part = gn_part;
+  float* stats = s.stats;
+  cudaStream_t cs = st;
+  NormW nn = n;
+  l.add(3, [=] {
+    gn_stats(xp, px, C, 1e-6f, part, stats, cs);
+    gn_apply(xp, stats, nn.gamma, nn.beta, px, C, swish, y, cs);
+  });
+  return s;
+}
+
+// y = conv(x) (+bias), returns y; appends dgrad op (x.g = conv_dgrad(y.g)) to bwd (caller orders it)
+Act Engine::conv_fwd_bwd(const Act& x, const ConvW& w, OpList& bwd) {
+  Act y = new_act(x.H, x.W, w.cout);
+  GemmEpilogue e;
+  e.bias = w.bias;
+  e.out_f16 = y.p;
+  e.ldc = y.C;
+  add_conv(drawer_fwd, x.p, x.H, x.W, x.C, w.w, w.cout_pad, w.cout, w.ks, e);
+  GemmEpilogue d;
+  d.out_f16 = x.g;
+  d.ldc = x.C;
+  add_conv(bwd, y.g, x.H, x.W, w.cout_k, w.wd, w.cin_rows, w.cin, w.ks, d);
+  return y;
+}
+
+Act Engine::resblock(const Act& x, const std::string& prefix, int cin, int cout) {
+  NormW n1 = load_norm(PXR_MOD_VQGAN, prefix + ".norm1", cin), n2 = load_norm(PXR_MOD_VQGAN, prefix + ".norm2", cout);
+  ConvW c1 = load_conv(prefix + ".conv1", cin, cout, 3), c2 = load_conv(prefix + ".conv2", cout, cout, 3);
+  const int H = x.H, Wd = x.W, px = x.pixels();
+  Act a1 = new_act(H, Wd, cin), h1 = new_act(H, Wd, cout), a2 = new_act(H, Wd, cout), out = new_act(H, Wd, cout);
+  cudaStream_t cs = st;
+  float* part = gn_part;
+  // ---- forward
+  GNSaved s1 = add_gn(drawer_fwd, x, n1, 1, a1.p);
+  {
+    GemmEpilogue e;
+    e.bias = c1.bias;
+    e.out_f16 = h1.p;
+    e.ldc = cout;
+    add_conv(drawer_fwd, a1.p, H, Wd, cin, c1.w, c1.cout_pad, cout, 3, e);
+  }
+  GNSaved s2 = add_gn(drawer_fwd, h1, n2, 1, a2.p);
+  ConvW sc;
+  if (cin != cout) {
+    sc = load_conv(prefix + ".nin_shortcut", cin, cout, 1);
+    GemmEpilogue e;
+    e.bias = sc.bias;
+    e.out_f16 = out.p;
+    e.ldc = cout;
+    add_conv(drawer_fwd, x.p, H, Wd, cin, sc.w, sc.cout_pad, cout, 1, e);
+  }
+  {
+    GemmEpilogue e;
+    e.bias = c2.bias;
+    e.res_f16 = (cin != cout) ? out.p : x.p;
+    e.out_f16 = out.p;
+    e.ldc = cout;
+    add_conv(drawer_fwd, a2.p, H, Wd, cout, c2.w, c2.cout_pad, cout, 3, e);
+  }
+  // ---- backward (execution order)
+  OpList b;
+  {
+    GemmEpilogue e;
+    e.out_f16 = a2.g;
+    e.ldc = cout;
+    add_conv(b, out.g, H, Wd, c2.cout_k, c2.wd, c2.cin_rows, cout, 3, e);
+  }
+  b.add(3, [=] { gn_backward(a2.g, h1.p, s2.stats, n2.gamma, n2.beta, px, cout, 1, nullptr, part, s2.gstats, h1.g, cs); });
+  {
+    GemmEpilogue e;
+    e.out_f16 = a1.g;
+    e.ldc = cin;
+    add_conv(b, h1.g, H, Wd, c1.cout_k, c1.wd, c1.cin_rows, cin, 3, e);
+  }
+  if (cin != cout) {
+    GemmEpilogue e;
+    e.out_f16 = x.g;
+    e.ldc = cin;
+    add_conv(b, out.g, H, Wd, sc.cout_k, sc.wd, sc.cin_rows, cin, 1, e);
+    b.add(3, [=] { gn_backward(a1.g, x.p, s1.stats, n1.gamma, n1.beta, px, cin, 1, x.g, part, s1.gstats, x.g, cs); });
+  } else {
+    b.add(3, [=] { gn_backward(a1.g, x.p, s1.stats, n1.gamma, n1.beta, px, cin, 1, out.g, part, s1.gstats, x.g, cs); });
+  }
+  bwd_stack.push_back(std::move(b));
+  return out;
+}
+
+Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
+  NormW n = load_norm(PXR_MOD_VQGAN, prefix + ".norm", c);
+  // fused q/k/v 1x1 convs: weight [3c, c]
+  std::vector<float> wq, bq;
+  for (const char* nm : {".q", ".k", ".v"}) {
+    const HostWeight& w = W(PXR_MOD_VQGAN, prefix + nm + ".weight", {c, c, 1, 1});
+    const HostWeight& b = W(PXR_MOD_VQGAN, prefix + nm + ".bias", {c});
+    wq.insert(wq.end(), w.data.begin(), w.data.end());
+    bq.insert(bq.end(), b.data.begin(), b.data.end());
+  }
+  act_t* wqkv = upload_f16(wq);
+  float* bqkv = upload(bq);
+  ConvW po = load_conv(prefix + ".proj_out", c, c, 1);
+  const int T = x.pixels(), ldT = round_up(T, 8);
+  const float alpha = 1.f / std::sqrt((float)c);
+  Act a = new_act(x.H, x.W, c), O = new_act(x.H, x.W, c), out = new_act(x.H, x.W, c);
+  act_t* qkv = dalloc<act_t>((size_t)T * 3 * c);
+  act_t* gqkv = dalloc<act_t>((size_t)T * 3 * c);
+  act_t* P = dalloc<act_t>((size_t)T * ldT);
+  act_t* dP = dalloc<act_t>((size_t)T * ldT);
+  cudaStream_t cs = st;
+  float* part = gn_part;
+  // ---- forward
+  GNSaved s = add_gn(drawer_fwd, x, n, 0, a.p);
+  {
+    GemmEpilogue e;
+    e.bias = bqkv;
+    e.out_f16 = qkv;
+    e.ldc = 3 * c;
+    add_gemm(drawer_fwd, opK(a.p, c, T, c), opK(wqkv, c, 3 * c, c), T, 3 * c, c, e);
+  }
+  {
+    GemmEpilogue e;
+    e.alpha = alpha;
+    e.out_f16 = P;
+    e.ldc = ldT;
+    add_gemm(drawer_fwd, opK(qkv, 3 * c, T, c), opK(qkv + c, 3 * c, T, c), T, T, c, e);
+  }
+  drawer_fwd.add(1, [=] { softmax_forward(P, T, T, ldT, cs); });
+  {
+    GemmEpilogue e;
+    e.out_f16 = O.p;
+    e.ldc = c;
+    add_gemm(drawer_fwd, opK(P, ldT, T, ldT), opMN(qkv + 2 * c, 3 * c, c, T), T, c, T, e);
+  }
+  {
+    GemmEpilogue e;
+    e.bias = po.bias;
+    e.res_f16 = x.p;
+    e.out_f16 = out.p;
+    e.ldc = c;
+    add_conv(drawer_fwd, O.p, x.H, x.W, c, po.w, po.cout_pad, c, 1, e);
+  }
+  // ---- backward
+  OpList b;
+  {
+    GemmEpilogue e;
+    e.out_f16 = O.g;
+    e.ldc = c;
+    add_conv(b, out.g, x.H, x.W, po.cout_k, po.wd, po.cin_rows, c, 1, e);
+  }
+  {  // dP = dO v^T
+    GemmEpilogue e;
+    e.out_f16 = dP;
+    e.ldc = ldT;
+    add_gemm(b, opK(O.g, c, T, c), opK(qkv + 2 * c, 3 * c, T, c), T, T, c, e);
+  }
+  b.add(1, [=] { softmax_backward(P, dP, T, T, ldT, cs); });
+  {  // dq = alpha dS k
+    GemmEpilogue e;
+    e.alpha = alpha;
+    e.out_f16 = gqkv;
+    e.ldc = 3 * c;
+    add_gemm(b, opK(dP, ldT, T, ldT), opMN(qkv + c, 3 * c, c, T), T, c, T, e);
+  }
+  {  // dk = alpha dS^T q
+    GemmEpilogue e;
+    e.alpha = alpha;
+    e.out_f16 = gqkv + c;
+    e.ldc = 3 * c;
+    add_gemm(b, opMN(dP, ldT, T, T), opMN(qkv, 3 * c, c, T), T, c, T, e);
+  }
+  {  // dv = P^T dO
+    GemmEpilogue e;
+    e.out_f16 = gqkv + 2 * c;
+    e.ldc = 3 * c;
+    add_gemm(b, opMN(P, ldT, T, T), opMN(O.g, c, c, T), T, c, T, e);
+  }
+  {  // da = dqkv Wqkv   (B = Wqkv stored [3c (k), c (n)] -> MN-major)
+    GemmEpilogue e;
+    e.out_f16 = a.g;
+    e.ldc = c;
+    add_gemm(b, opK(gqkv, 3 * c, T, 3 * c), opMN(wqkv, c, c, 3 * c), T, c, 3 * c, e);
+  }
+  b.add(3, [=] { gn_backward(a.g, x.p, s.stats, n.gamma, n.beta, T, c, 0, out.g, part, s.gstats, x.g, cs); });
+  bwd_stack.push_back(std::move(b));
+  return out;
+}
+
+Act Engine::upsample(const Act& x, const std::string& prefix) {
+  ConvW cw = load_conv(prefix + ".conv", x.C, x.C, 3);
+  Act u = new_act(2 * x.H, 2 * x.W, x.C);
+  cudaStream_t cs = st;
+  drawer_fwd.add(1, [=] { upsample2x(x.p, x.H, x.W, x.C, u.p, cs); });
+  OpList b;
+  Act out = conv_fwd_bwd(u, cw, b);
+  b.add(1, [=] { downsum2x(u.g, x.H, x.W, x.C, x.g, cs); });
+  bwd_stack.push_back(std::move(b));
+  return out;
+}
+
+void Engine::build_vqgan() {
+  const int zc = cfg.z_channels, ne = cfg.n_embed, L = cfg.n_levels;
+  if (L < 1 || L > 8) throw EngineError(-43, "n_levels must be in [1, 8]");
+  const int f = 1 << (L - 1);
+  if (cfg.image_h % f || cfg.image_w % f)
+    throw EngineError(-44, "image size must be a multiple of 2^(n_levels-1)");
+  const int h = cfg.image_h / f, w = cfg.image_w / f, hw = h * w;
+  if (w % 8) throw EngineError(-45, "latent width must be a multiple of 8 for the implicit-GEMM conv tiles");
+  z_numel = (int64_t)zc * hw;
+  // GN scratch sized for the largest activation
+  gn_part = dalloc<float>((size_t)gn_num_partials(cfg.image_h * cfg.image_w, 64) * 64 + 64);
+  // codebook
+  const HostWeight& cb = W(PXR_MOD_VQGAN, "quantize.embedding.weight", {ne, zc});
+  std::vector<float> cbT((size_t)zc * ne), c2(ne), mn(zc, 1e30f), mx(zc, -1e30f);
+  for (int j = 0; j < ne; ++j) {
+    float s = 0.f;
+    for (int k = 0; k < zc; ++k) {
+      float v = cb.data[(size_t)j * zc + k];
+      cbT[(size_t)k * ne + j] = v;
+      s += v * v;  // codebook.pow(2).sum(dim=1), vqgan.py:61
+      mn[k] = std::min(mn[k], v);
+      mx[k] = std::max(mx[k], v);
+    }
+    c2[j] = s;
+  }
+  float* d_cb = upload(cb.data);
+  float* d_cbT = upload(cbT);
+  float* d_c2 = upload(c2);
+  zmin = upload(mn);  // vqgan.py:141-142
+  zmax = upload(mx);
+  const int n_chunks = (ne + 1023) / 1024;
+  float* part_d = dalloc<float>((size_t)hw * n_chunks);
+  int* part_i = dalloc<int>((size_t)hw * n_chunks);
+  int* idx = dalloc<int>(hw);
+  Act zq = new_act(h, w, zc);
+  cudaStream_t cs = st;
+  float* zb = z_buf = dalloc<float>(z_numel);
+  z_grad = dalloc<float>(z_numel);
+  drawer_fwd.add(2, [=] { vq_nearest(zb, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq.p, cs); });
+
+  // post_quant_conv + decoder
+  ConvW pq = load_conv("post_quant_conv", zc, zc, 1);
+  OpList b_in;
+  Act hq = conv_fwd_bwd(zq, pq, b_in);
+  int block_in = cfg.ch * cfg.ch_mult[L - 1];
+  ConvW cin = load_conv("decoder.conv_in", zc, block_in, 3);
+  OpList b_in2;
+  Act hcur = conv_fwd_bwd(hq, cin, b_in2);
+  {
+    OpList b;  // execution order: conv_in dgrad, then post_quant dgrad, then vq backward
+    b.ops = b_in2.ops;
+    b.launches = b_in2.launches;
+    b.ops.insert(b.ops.end(), b_in.ops.begin(), b_in.ops.end());
+    b.launches.insert(b.launches.end(), b_in.launches.begin(), b_in.launches.end());
+    float* zg = z_grad;
+    float inv = 1.f / S;
+    b.add(1, [=] { vq_backward(zq.g, inv, zc, hw, zg, cs); });
+    bwd_stack.push_back(std::move(b));
+  }
+  hcur = resblock(hcur, "decoder.mid.block_1", block_in, block_in);
+  hcur = attnblock(hcur, "decoder.mid.attn_1", block_in);
+  hcur = resblock(hcur, "decoder.mid.block_2", block_in, block_in);
+  int curr_res = cfg.resolution / f;
+  for (int lv = L - 1; lv >= 0; --lv) {
+    int block_out = cfg.ch * cfg.ch_mult[lv];
+    for (int ib = 0; ib < cfg.num_res_blocks + 1; ++ib) {
+      std::string p = "decoder.up." + std::to_string(lv) + ".block." + std::to_string(ib);
+      hcur = resblock(hcur, p, block_in, block_out);
+      block_in = block_out;
+      if (curr_res == cfg.attn_resolution)
+        hcur = attnblock(hcur, "decoder.up." + std::to_string(lv) + ".attn." + std::to_string(ib), block_in);
+    }
+    if (lv != 0) {
+      hcur = upsample(hcur, "decoder.up." + std::to_string(lv) + ".upsample");
+      curr_res *= 2;
+    }
+  }
+  // norm_out, swish, conv_out -> image
+  NormW no = load_norm(PXR_MOD_VQGAN, "decoder.norm_out", block_in);
+  ConvW co = load_conv("decoder.conv_out", block_in, 3, 3);
+  Act a = new_act(hcur.H, hcur.W, block_in);
+  GNSaved s = add_gn(drawer_fwd, hcur, no, 1, a.p);
+  const int px = hcur.pixels();
+  float* co_out = dalloc<float>((size_t)px * co.cout_pad);
+  act_t* co_g = dalloc<act_t>((size_t)px * co.cout_k);
+  {
+    GemmEpilogue e;
+    e.bias = co.bias;
+    e.out_f32 = co_out;
+    e.ldc = co.cout_pad;
+    add_conv(drawer_fwd, a.p, hcur.H, hcur.W, block_in, co.w, co.cout_pad, 3, 3, e);
+  }
+  img = dalloc<float>((size_t)3 * px);
+  img_pre = dalloc<float>((size_t)3 * px);
+  g_img = dalloc<float>((size_t)3 * px);
+  {
+    float *ip = img_pre, *im = img;
+    int ld = co.cout_pad;
+    drawer_fwd.add(1, [=] { image_finish(co_out, ld, px, ip, im, cs); });
+  }
+  {
+    OpList b;
+    float *gi = g_img, *ip = img_pre;
+    int ldk = co.cout_k;
+    float* part = gn_part;
+    b.add(1, [=] { image_finish_backward(gi, ip, px, ldk, co_g, cs); });
+    GemmEpilogue e;
+    e.out_f16 = a.g;
+    e.ldc = block_in;
+    add_conv(b, co_g, hcur.H, hcur.W, co.cout_k, co.wd, co.cin_rows, block_in, 3, e);
+    Act hc = hcur;
+    b.add(3, [=] { gn_backward(a.g, hc.p, s.stats, no.gamma, no.beta, px, hc.C, 1, nullptr, part, s.gstats, hc.g, cs); });
+    bwd_stack.push_back(std::move(b));
+  }
+  // flatten backward stack in reverse block order
+  for (int i = (int)bwd_stack.size() - 1; i >= 0; --i) {
+    drawer_bwd.ops.insert(drawer_bwd.ops.end(), bwd_stack[i].ops.begin(), bwd_stack[i].ops.end());
+    drawer_bwd.launches.insert(drawer_bwd.launches.end(), bwd_stack[i].launches.begin(), bwd_stack[i].launches.end());
+  }
+  bwd_stack.clear();
+}
+
+void Engine::build_pixel() {
+  const int rows = cfg.grid_rows, cols = cfg.grid_cols, H = cfg.image_h, Wd = cfg.image_w;
+  if (rows < 1 || cols < 1) throw EngineError(-46, "pixel drawer needs grid_rows / grid_cols");
+  z_numel = (int64_t)3 * rows * cols;
+  z_buf = dalloc<float>(z_numel);
+  z_grad = dalloc<float>(z_numel);
+  img = dalloc<float>((size_t)3 * H * Wd);
+  img_pre = dalloc<float>((size_t)3 * H * Wd);
+  g_img = dalloc<float>((size_t)3 * H * Wd);
+  cudaStream_t cs = st;
+  float *zb = z_buf, *ip = img_pre, *im = img, *gi = g_img, *zg = z_grad;
+  float inv = 1.f / S;
+  drawer_fwd.add(1, [=] { pixel_synth(zb, rows, cols, H, Wd, ip, im, cs); });
+  drawer_bwd.add(1, [=] { pixel_synth_backward(gi, ip, rows, cols, H, Wd, inv, zg, cs); });
+}
+
+// ===================================================================================================== cutouts
+void Engine::build_cutouts() {
+  const int cs_ = cfg.cut_size;
+  pooled = dalloc<float>((size_t)3 * cs_ * cs_);
+  g_pooled = dalloc<float>((size_t)3 * cs_ * cs_);
+  pool_argmax = dalloc<int>((size_t)3 * cs_ * cs_);
+  batch = dalloc<float>((size_t)n_local * 3 * cs_ * cs_);
+  g_batch = dalloc<float>((size_t)n_local * 3 * cs_ * cs_);
+  n_parts = cutout_num_blocks(n_local, cs_);
+  part_min = dalloc<float>(n_parts);
+  part_max = dalloc<float>(n_parts);
+  part_imin = dalloc<int>(n_parts);
+  part_imax = dalloc<int>(n_parts);
+  range = dalloc<float>(4);
+  irange = dalloc<int>(4);
+  sums = dalloc<float>(4);
+  minv_dev = dalloc<float>((size_t)n_local * 9);
+  facs_dev = dalloc<float>(n_local);
+  for (int i = 0; i < RING; ++i) {
+    PXR_CUDA(cudaMallocHost((void**)&minv_host[i], sizeof(float) * n_local * 9));
+    PXR_CUDA(cudaMallocHost((void**)&facs_host[i], sizeof(float) * n_local));
+    PXR_CUDA(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming));
+  }
+  memset(&cut_args, 0, sizeof cut_args);
+  cut_args.pooled = pooled;
+  cut_args.minv = minv_dev;
+  cut_args.cs = cs_;
+  cut_args.n_local = n_local;
+  cut_args.first_global = first_global;
+  cut_args.cutn_zoom = (int)(0.6 * cfg.cutn);  // pixray.py:407
+  cut_args.seed = cfg.seed;
+  cut_args.noise_fac = cfg.noise_fac;
+}
+
+// Host side of MakeCutouts: invert the cached "dst <- src" transforms (pixray.py:498) to the sampling maps the
+// kernel uses (kornia warp_perspective inverts the normalised homography; with align_corners=True the
+// normalisations cancel and src_pix = M^-1 dst_pix), stage them through pinned memory.
+void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
+  const int slot = ring_pos;
+  ring_pos = (ring_pos + 1) % RING;
+  PXR_CUDA(cudaEventSynchronize(ring_ev[slot]));
+  std::vector<float> gen;
+  const float* T = p ? p->transforms : nullptr;
+  int zoom_padding = p ? p->zoom_padding : ((iter % 2 == 0) ? PXR_PAD_REFLECTION : PXR_PAD_BORDER);  // pixray.py:1250
+  float fill = p ? p->fill : 0.f;
+  if (!T) {  // engine RNG, keyed by (seed, iter, global cutout index)
+    gen.resize((size_t)cfg.cutn * 9);
+    sample_cutout_transforms(cfg.seed, iter, cfg.cutn, cfg.cut_size, gen.data());
+    T = gen.data();
+    if (!p) fill = sample_fill(cfg.seed, iter);
+  }
+  for (int n = 0; n < n_local; ++n) {
+    double m[9], inv[9];
+    for (int i = 0; i < 9; ++i) m[i] = T[(size_t)(first_global + n) * 9 + i];
+    if (!invert3x3(m, inv)) throw EngineError(-60, "singular cutout transform");
+    for (int i = 0; i < 9; ++i) minv_host[slot][n * 9 + i] = (float)inv[i];
+  }
+  PXR_CUDA(cudaMemcpyAsync(minv_dev, minv_host[slot], sizeof(float) * n_local * 9, cudaMemcpyHostToDevice, st));
+  cut_args.zoom_padding = zoom_padding;
+  cut_args.fill = fill;
+  cut_args.iter = iter;
+  cut_args.noise = nullptr;
+  cut_args.noise_facs = nullptr;
+  if (cfg.noise_fac <= 0.f) {
+    cut_args.noise_mode = 0;
+  } else if (p && p->noise && p->noise_facs) {
+    for (int n = 0; n < n_local; ++n) facs_host[slot][n] = p->noise_facs[first_global + n];
+    PXR_CUDA(cudaMemcpyAsync(facs_dev, facs_host[slot], sizeof(float) * n_local, cudaMemcpyHostToDevice, st));
+    cut_args.noise_mode = 1;
+    cut_args.noise = p->noise + (size_t)first_global * 3 * cfg.cut_size * cfg.cut_size;
+    cut_args.noise_facs = facs_dev;
+  } else if (p && (p->noise || p->noise_facs)) {
+    throw EngineError(-61, "pxr_cut_params: noise and noise_facs must be given together");
+  } else if (p && p->transforms) {
+    cut_args.noise_mode = 0;  // explicit transforms without noise: deterministic replay
+  } else {
+    cut_args.noise_mode = 2;
+  }
+  PXR_CUDA(cudaEventRecord(ring_ev[slot], st));
+}
+
+void Engine::forward_cutouts() {
+  pool_forward(img, cfg.image_h, cfg.image_w, cfg.cut_size, pooled, pool_argmax, st);
+  cutout_forward(cut_args, batch, part_min, part_max, part_imin, part_imax, st);
+  minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
+  launches += 3;
+  check_launch("cutouts forward");
+}
+
+// ===================================================================================================== CLIP ViT
+void Engine::build_clip(int i) {
+  Clip& C = clip[i];
+  C.c = cfg.clip[i];
+  const int mod = PXR_MOD_CLIP0 + i;
+  const int Wd = C.c.width, L = C.c.layers, Hh = C.c.heads, P = C.c.patch, D = C.c.out_dim;
+  if (C.c.image_res != cfg.cut_size) throw EngineError(-50, "clip image_res must equal cut_size");
+  if (Wd % 64 || Wd > 1024 || Wd / Hh != 64) throw EngineError(-51, "ViT width must be a multiple of 64 (<=1024) with 64-wide heads");
+  if (P % 8 || cfg.cut_size % P) throw EngineError(-52, "patch size must be a multiple of 8 dividing cut_size");
+  const int gp = cfg.cut_size / P, np = gp * gp, T = np + 1, B = n_local, M = B * T, d = 64;
+  const int Kp = round_up(3 * P * P, 64), ldT = round_up(T, 8);
+  C.T = T;
+  C.np = np;
+  C.Kp = Kp;
+  C.ldT = ldT;
+  C.M = M;
+  C.B = B;
+  cudaStream_t cs = st;
+  // ---- weights
+  {
+    const HostWeight& w = W(mod, "visual.conv1.weight", {Wd, 3, P, P});
+    std::vector<float> f((size_t)Wd * Kp, 0.f);
+    for (int o = 0; o < Wd; ++o)
+      for (int k = 0; k < 3 * P * P; ++k) f[(size_t)o * Kp + k] = w.data[(size_t)o * 3 * P * P + k];
+    C.conv1 = upload_f16(f);
+  }
+  C.cls = upload(W(mod, "visual.class_embedding", {Wd}).data);
+  C.pos = upload(W(mod, "visual.positional_embedding", {T, Wd}).data);
+  C.proj = upload(W(mod, "visual.proj", {Wd, D}).data);
+  C.ln_pre = load_norm(mod, "visual.ln_pre", Wd);
+  C.ln_post = load_norm(mod, "visual.ln_post", Wd);
+  // ---- buffers
+  C.patches = dalloc<act_t>((size_t)B * np * Kp);
+  C.g_patches = dalloc<act_t>((size_t)B * np * Kp);
+  C.t = dalloc<float>((size_t)M * Wd);
+  {  // class-token rows are constant: t[b*T + 0] = class_embedding
+    std::vector<float> t0((size_t)M * Wd, 0.f);
+    const auto& cls = W(mod, "visual.class_embedding").data;
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < Wd; ++k) t0[(size_t)b * T * Wd + k] = cls[k];
+    PXR_CUDA(cudaMemcpyAsync(C.t, t0.data(), t0.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    PXR_CUDA(cudaStreamSynchronize(st));
+  }
+  C.h16 = dalloc<act_t>((size_t)M * Wd);
+  C.o16 = dalloc<act_t>((size_t)M * Wd);
+  C.gact = dalloc<act_t>((size_t)M * 4 * Wd);
+  C.g4 = dalloc<act_t>((size_t)M * 4 * Wd);
+  C.gh = dalloc<act_t>((size_t)M * Wd);
+  C.go = dalloc<act_t>((size_t)M * Wd);
+  C.gqkv = dalloc<act_t>((size_t)M * 3 * Wd);
+  C.dP = dalloc<act_t>((size_t)B * Hh * T * ldT);
+  C.gx = dalloc<float>((size_t)M * Wd);
+  C.gx16 = dalloc<act_t>((size_t)M * Wd);
+  C.stats_pre = dalloc<float>((size_t)M * 2);
+  C.stats_post = dalloc<float>((size_t)B * 2);
+  C.e = dalloc<float>((size_t)B * D);
+  C.e_unit = dalloc<float>((size_t)B * D);
+  C.de = dalloc<float>((size_t)B * D);
+  float* x_cur = dalloc<float>((size_t)M * Wd);
+  float* x0 = x_cur;
+  C.layers.resize(L);
+  const float scale = 1.f / std::sqrt((float)d);
+  const int bnS = pick_bn(T, false, 1000);
+
+  // ---- forward: patch embed (conv1 as GEMM over im2col'd patches, written straight into the token rows 1..np)
+  {
+    GemmEpilogue e;
+    e.out_f32 = C.t + Wd;
+    e.ldc = Wd;
+    e.bs0 = (long long)T * Wd;
+    add_gemm(C.fwd, opK(C.patches, Kp, np, Kp, B, (long long)np * Kp), opK(C.conv1, Kp, Wd, Kp), np, Wd, Kp, e);
+  }
+  {
+    Clip* c = &C;
+    float* xo = x0;
+    C.fwd.add(1, [=] { layernorm_forward(c->t, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, nullptr, xo, c->stats_pre, cs); });
+  }
+  for (int l = 0; l < L; ++l) {
+    Clip::Layer& Ly = C.layers[l];
+    std::string p = "visual.transformer.resblocks." + std::to_string(l);
+    Ly.wqkv = upload_f16(W(mod, p + ".attn.in_proj_weight", {3 * Wd, Wd}).data);
+    Ly.bqkv = upload(W(mod, p + ".attn.in_proj_bias", {3 * Wd}).data);
+    Ly.wo = upload_f16(W(mod, p + ".attn.out_proj.weight", {Wd, Wd}).data);
+    Ly.bo = upload(W(mod, p + ".attn.out_proj.bias", {Wd}).data);
+    Ly.wfc = upload_f16(W(mod, p + ".mlp.c_fc.weight", {4 * Wd, Wd}).data);
+    Ly.bfc = upload(W(mod, p + ".mlp.c_fc.bias", {4 * Wd}).data);
+    Ly.wproj = upload_f16(W(mod, p + ".mlp.c_proj.weight", {Wd, 4 * Wd}).data);
+    Ly.bproj = upload(W(mod, p + ".mlp.c_proj.bias", {Wd}).data);
+    Ly.ln1 = load_norm(mod, p + ".ln_1", Wd);
+    Ly.ln2 = load_norm(mod, p + ".ln_2", Wd);
+    Ly.x_in = x_cur;
+    Ly.x_mid = dalloc<float>((size_t)M * Wd);
+    float* x_next = dalloc<float>((size_t)M * Wd);
+    Ly.stats1 = dalloc<float>((size_t)M * 2);
+    Ly.stats2 = dalloc<float>((size_t)M * 2);
+    Ly.qkv = dalloc<act_t>((size_t)M * 3 * Wd);
+    Ly.P = dalloc<act_t>((size_t)B * Hh * T * ldT);
+    Ly.u = dalloc<act_t>((size_t)M * 4 * Wd);
+    Clip::Layer ly = Ly;
+    Clip* c = &C;
+    C.fwd.add(1, [=] { layernorm_forward(ly.x_in, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); });
+    {
+      GemmEpilogue e;
+      e.bias = ly.bqkv;
+      e.out_f16 = ly.qkv;
+      e.ldc = 3 * Wd;
+      add_gemm(C.fwd, opK(C.h16, Wd, M, Wd), opK(ly.wqkv, Wd, 3 * Wd, Wd), M, 3 * Wd, Wd, e);
+    }
+    const long long qs0 = d, qs1 = (long long)T * 3 * Wd;           // (head, image) strides inside qkv
+    const long long ps0 = (long long)T * ldT, ps1 = (long long)Hh * T * ldT;  // inside P / dP
+    const long long os0 = d, os1 = (long long)T * Wd;              // inside [M, W] token-major buffers
+    {  // S = scale * q k^T  (nn.MultiheadAttention scales q by d^-1/2)
+      GemmEpilogue e;
+      e.alpha = scale;
+      e.out_f16 = ly.P;
+      e.ldc = ldT;
+      e.bs0 = ps0;
+      e.bs1 = ps1;
+      add_gemm(C.fwd, opK(ly.qkv, 3 * Wd, T, d, Hh, qs0, B, qs1), opK(ly.qkv + Wd, 3 * Wd, T, d, Hh, qs0, B, qs1), T, T,
+               d, e, bnS);
+    }
+    C.fwd.add(1, [=] { softmax_forward(ly.P, B * Hh * T, T, ldT, cs); });
+    {  // O = P v
+      GemmEpilogue e;
+      e.out_f16 = C.o16;
+      e.ldc = Wd;
+      e.bs0 = os0;
+      e.bs1 = os1;
+      add_gemm(C.fwd, opK(ly.P, ldT, T, ldT, Hh, ps0, B, ps1), opMN(ly.qkv + 2 * Wd, 3 * Wd, d, T, Hh, qs0, B, qs1), T, d,
+               T, e, 64);
+    }
+    {  // x_mid = x_in + O Wo^T + bo
+      GemmEpilogue e;
+      e.bias = ly.bo;
+      e.res_f32 = ly.x_in;
+      e.out_f32 = ly.x_mid;
+      e.ldc = Wd;
+      add_gemm(C.fwd, opK(C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
+    }
+    C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); });
+    {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u
+      GemmEpilogue e;
+      e.bias = ly.bfc;
+      e.act = ACT_QUICKGELU;
+      e.aux_out = ly.u;
+      e.out_f16 = C.gact;
+      e.ldc = 4 * Wd;
+      add_gemm(C.fwd, opK(C.h16, Wd, M, Wd), opK(ly.wfc, Wd, 4 * Wd, Wd), M, 4 * Wd, Wd, e);
+    }
+    {  // x_next = x_mid + gact Wproj^T + bproj
+      GemmEpilogue e;
+      e.bias = ly.bproj;
+      e.res_f32 = ly.x_mid;
+      e.out_f32 = x_next;
+      e.ldc = Wd;
+      add_gemm(C.fwd, opK(C.gact, 4 * Wd, M, 4 * Wd), opK(ly.wproj, 4 * Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
+    }
+    x_cur = x_next;
+  }
+  C.x_out = x_cur;
+  {
+    Clip* c = &C;
+    C.fwd.add(1, [=] { clip_head_forward(c->x_out, T, Wd, D, c->ln_post.gamma, c->ln_post.beta, c->proj, B, 1e-5f, c->stats_post, c->e, cs); });
+  }
+
+  // ---- backward (execution order).  Weight operands of the dgrad GEMMs are MN-major views of the forward weights.
+  {
+    Clip* c = &C;
+    C.bwd.add(3, [=] { clip_head_backward(c->de, c->x_out, T, Wd, D, c->stats_post, c->ln_post.gamma, c->proj, B, c->gx, c->gx16, cs); });
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    Clip::Layer ly = C.layers[l];
+    Clip* c = &C;
+    const long long qs0 = d, qs1 = (long long)T * 3 * Wd, ps0 = (long long)T * ldT, ps1 = (long long)Hh * T * ldT;
+    const long long os0 = d, os1 = (long long)T * Wd;
+    {  // g4 = (gx Wproj) * quickgelu'(u)
+      GemmEpilogue e;
+      e.act = ACT_QUICKGELU_BWD;
+      e.aux_in = ly.u;
+      e.out_f16 = C.g4;
+      e.ldc = 4 * Wd;
+      add_gemm(C.bwd, opK(C.gx16, Wd, M, Wd), opMN(ly.wproj, 4 * Wd, 4 * Wd, Wd), M, 4 * Wd, Wd, e);
+    }
+    {  // gh = g4 Wfc
+      GemmEpilogue e;
+      e.out_f16 = C.gh;
+      e.ldc = Wd;
+      add_gemm(C.bwd, opK(C.g4, 4 * Wd, M, 4 * Wd), opMN(ly.wfc, Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
+    }
+    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_mid, nullptr, T, ly.stats2, ly.ln2.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
+    {  // go = gx Wo
+      GemmEpilogue e;
+      e.out_f16 = C.go;
+      e.ldc = Wd;
+      add_gemm(C.bwd, opK(C.gx16, Wd, M, Wd), opMN(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
+    }
+    {  // dP = go v^T
+      GemmEpilogue e;
+      e.out_f16 = C.dP;
+      e.ldc = ldT;
+      e.bs0 = ps0;
+      e.bs1 = ps1;
+      add_gemm(C.bwd, opK(C.go, Wd, T, d, Hh, os0, B, os1), opK(ly.qkv + 2 * Wd, 3 * Wd, T, d, Hh, qs0, B, qs1), T, T, d,
+               e, bnS);
+    }
+    C.bwd.add(1, [=] { softmax_backward(ly.P, c->dP, B * Hh * T, T, ldT, cs); });
+    {  // dq = scale dS k
+      GemmEpilogue e;
+      e.alpha = scale;
+      e.out_f16 = C.gqkv;
+      e.ldc = 3 * Wd;
+      e.bs0 = qs0;
+      e.bs1 = qs1;
+      add_gemm(C.bwd, opK(C.dP, ldT, T, ldT, Hh, ps0, B, ps1), opMN(ly.qkv + Wd, 3 * Wd, d, T, Hh, qs0, B, qs1), T, d, T,
+               e, 64);
+    }
+    {  // dk = scale dS^T q
+      GemmEpilogue e;
+      e.alpha = scale;
+      e.out_f16 = C.gqkv + Wd;
+      e.ldc = 3 * Wd;
+      e.bs0 = qs0;
+      e.bs1 = qs1;
+      add_gemm(C.bwd, opMN(C.dP, ldT, T, T, Hh, ps0, B, ps1), opMN(ly.qkv, 3 * Wd, d, T, Hh, qs0, B, qs1), T, d, T, e, 64);
+    }
+    {  // dv = P^T go
+      GemmEpilogue e;
+      e.out_f16 = C.gqkv + 2 * Wd;
+      e.ldc = 3 * Wd;
+      e.bs0 = qs0;
+      e.bs1 = qs1;
+      add_gemm(C.bwd, opMN(ly.P, ldT, T, T, Hh, ps0, B, ps1), opMN(C.go, Wd, d, T, Hh, os0, B, os1), T, d, T, e, 64);
+    }
+    {  // gh = gqkv Wqkv
+      GemmEpilogue e;
+      e.out_f16 = C.gh;
+      e.ldc = Wd;
+      add_gemm(C.bwd, opK(C.gqkv, 3 * Wd, M, 3 * Wd), opMN(ly.wqkv, Wd, Wd, 3 * Wd), M, Wd, 3 * Wd, e);
+    }
+    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_in, nullptr, T, ly.stats1, ly.ln1.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
+  }
+  {  // ln_pre backward (x = t + pos), then patch-embed dgrad on token rows 1..np of every image
+    Clip* c = &C;
+    C.bwd.add(1, [=] { layernorm_backward(c->gx16, c->t, c->pos, T, c->stats_pre, c->ln_pre.gamma, M, Wd, 0, c->gx, c->gx16, cs); });
+    GemmEpilogue e;
+    e.out_f16 = C.g_patches;
+    e.ldc = Kp;
+    e.bs0 = (long long)np * Kp;
+    add_gemm(C.bwd, opK(C.gx16 + Wd, Wd, np, Wd, B, (long long)T * Wd), opMN(C.conv1, Kp, Kp, Wd), np, Kp, Wd, e);
+  }
+}
+
+void Engine::forward_clip(int i) {
+  Clip& C = clip[i];
+  patchify_forward(batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, C.patches, st);
+  launches += 1;
+  run(C.fwd);
+  check_launch("clip forward");
+}
+
+void Engine::loss_clip(int i) {
+  Clip& C = clip[i];
+  if (C.n_prompts == 0) throw EngineError(-70, "no prompts set for perceptor " + std::to_string(i));
+  prompt_loss(C.e, C.B, C.c.out_dim, C.prompts, C.pweights, C.pstops, C.n_prompts, cfg.cutn, S, C.e_unit,
+              losses_dev + C.loss_offset, C.de, st);
+  launches += 1;
+}
+
+void Engine::backward_all() {
+  PXR_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), st));
+  for (int i = 0; i < cfg.n_clip; ++i) {
+    Clip& C = clip[i];
+    run(C.bwd);
+    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, i > 0, g_batch, sums, st);
+    launches += 1;
+  }
+  // TODO(multi-GPU): allreduce(sums) across ranks belongs here
+  PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * 3 * cfg.cut_size * cfg.cut_size, st));
+  cutout_backward(cut_args, g_batch, range, irange, sums, g_pooled, st);
+  pool_backward(g_pooled, pool_argmax, cfg.image_h, cfg.image_w, cfg.cut_size, g_img, st);
+  launches += 2;
+  run(drawer_bwd);
+  check_launch("backward");
+}
+
+void Engine::step(float lr) {
+  ++adam_t;
+  const int per_channel = (cfg.drawer == PXR_DRAWER_VQGAN) ? (int)(z_numel / cfg.z_channels) : 1;
+  adam_clip_step(z_buf, adam_m, adam_v, z_grad, 1.f, (int)z_numel, per_channel, zmin, zmax,
+                 cfg.drawer == PXR_DRAWER_PIXEL, lr, cfg.beta1, cfg.beta2, cfg.adam_eps, adam_t, st);
+  launches += 1;
+}
+
+void Engine::finalize() {
+  if (finalized) return;
+  if (cfg.drawer == PXR_DRAWER_VQGAN) build_vqgan();
+  else if (cfg.drawer == PXR_DRAWER_PIXEL) build_pixel();
+  else throw EngineError(-47, "unknown drawer kind");
+  adam_m = dalloc<float>(z_numel);
+  adam_v = dalloc<float>(z_numel);
+  build_cutouts();
+  if (cfg.n_clip < 1 || cfg.n_clip > 2) throw EngineError(-53, "n_clip must be 1 or 2");
+  for (int i = 0; i < cfg.n_clip; ++i) build_clip(i);
+  losses_dev = dalloc<float>(64);
+  PXR_CUDA(cudaMallocHost((void**)&losses_host, 64 * sizeof(float)));
+  PXR_CUDA(cudaStreamSynchronize(st));
+  {
+    const size_t npx = (size_t)3 * cfg.image_h * cfg.image_w, ncs = (size_t)3 * cfg.cut_size * cfg.cut_size;
+    reg("img", img, npx * 4);
+    reg("img_pre", img_pre, npx * 4);
+    reg("g_img", g_img, npx * 4);
+    reg("pooled", pooled, ncs * 4);
+    reg("g_pooled", g_pooled, ncs * 4);
+    reg("batch", batch, ncs * n_local * 4);
+    reg("g_batch", g_batch, ncs * n_local * 4);
+    reg("range", range, 16);
+    reg("irange", irange, 16);
+    reg("sums", sums, 16);
+    reg("z_grad", z_grad, z_numel * 4);
+    reg("minv", minv_dev, (size_t)n_local * 36);
+    for (int i = 0; i < cfg.n_clip; ++i) {
+      Clip& C = clip[i];
+      std::string p = "clip" + std::to_string(i) + ".";
+      const size_t mw = (size_t)C.M * C.c.width;
+      reg(p + "patches", C.patches, (size_t)C.B * C.np * C.Kp * 2);
+      reg(p + "g_patches", C.g_patches, (size_t)C.B * C.np * C.Kp * 2);
+      reg(p + "t", C.t, mw * 4);
+      reg(p + "x0", C.layers[0].x_in, mw * 4);
+      reg(p + "x_mid0", C.layers[0].x_mid, mw * 4);
+      reg(p + "qkv0", C.layers[0].qkv, mw * 3 * 2);
+      reg(p + "P0", C.layers[0].P, (size_t)C.B * C.c.heads * C.T * C.ldT * 2);
+      reg(p + "x_out", C.x_out, mw * 4);
+      reg(p + "e", C.e, (size_t)C.B * C.c.out_dim * 4);
+      reg(p + "de", C.de, (size_t)C.B * C.c.out_dim * 4);
+      reg(p + "gx", C.gx, mw * 4);
+    }
+  }
+  for (auto& m : weights) m.clear();  // host copies no longer needed
+  finalized = true;
+}
+
+}  // namespace pxr
+
+// ===================================================================================================== C ABI
+using pxr::Engine;
+using pxr::EngineError;
+
+struct pxr_engine {
+  Engine* e;
+};
+static thread_local std::string g_create_err;
+
+#define PXR_TRY(h, body)                                  \
+  try {                                                   \
+    body;                                                 \
+    return 0;                                             \
+  } catch (const EngineError& ex) {                       \
+    (h)->e->err = ex.what();                              \
+    return ex.code;                                       \
+  } catch (const std::exception& ex) {                    \
+    (h)->e->err = ex.what();                              \
+    return -999;                                          \
+  }
+
+extern "C" {
+
+const char* pxr_version(void) { return "pixray_b200 0.1 (sm_100a)"; }
+const char* pxr_last_error(pxr_handle h) { return h ? h->e->err.c_str() : g_create_err.c_str(); }
+
+int pxr_create(const pxr_config* cfg, pxr_handle* out) {
+  if (!cfg || !out) return -10;
+  Engine* e = nullptr;
+  try {
+    e = new Engine(*cfg);
+    e->create();
+  } catch (const EngineError& ex) {
+    g_create_err = ex.what();
+    delete e;
+    return ex.code;
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    delete e;
+    return -999;
+  }
+  *out = new pxr_engine{e};
+  return 0;
+}
+
+void pxr_destroy(pxr_handle h) {
+  if (!h) return;
+  delete h->e;
+  delete h;
+}
+
+int pxr_load_weight(pxr_handle h, int module_id, const char* name, const float* data, const int64_t* dims, int ndim) {
+  PXR_TRY(h, {
+    if (module_id < 0 || module_id > 2) throw EngineError(-11, "bad module id");
+    if (h->e->finalized) throw EngineError(-12, "weights cannot change after pxr_finalize");
+    pxr::HostWeight w;
+    w.dims.assign(dims, dims + ndim);
+    w.data.resize((size_t)w.numel());
+    PXR_CUDA(cudaMemcpy(w.data.data(), data, w.data.size() * sizeof(float), cudaMemcpyDefault));
+    h->e->weights[module_id][name] = std::move(w);
+  });
+}
+
+int pxr_finalize(pxr_handle h) { PXR_TRY(h, h->e->finalize()); }
+
+int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int D, const float* weights,
+                    const float* stops) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (clip_idx < 0 || clip_idx >= e->cfg.n_clip) throw EngineError(-14, "bad clip index");
+    auto& C = e->clip[clip_idx];
+    if (D != C.c.out_dim) throw EngineError(-15, "prompt embedding width does not match the perceptor");
+    std::vector<float> pe((size_t)n * D);
+    for (int j = 0; j < n; ++j) {  // F.normalize(self.embed), pixray.py:277
+      double s = 0;
+      for (int k = 0; k < D; ++k) s += (double)embeds[(size_t)j * D + k] * embeds[(size_t)j * D + k];
+      double nrm = std::max(std::sqrt(s), 1e-12);
+      for (int k = 0; k < D; ++k) pe[(size_t)j * D + k] = (float)(embeds[(size_t)j * D + k] / nrm);
+    }
+    C.prompts = e->upload(pe);
+    C.pweights = e->upload(std::vector<float>(weights, weights + n));
+    C.pstops = e->upload(std::vector<float>(stops, stops + n));
+    C.n_prompts = n;
+    int off = 0;
+    for (int i = 0; i < e->cfg.n_clip; ++i) {
+      e->clip[i].loss_offset = off;
+      off += e->clip[i].n_prompts;
+    }
+    if (off > 64) throw EngineError(-16, "at most 64 prompts in total");
+    e->total_prompts = off;
+  });
+}
+
+int pxr_synth(pxr_handle h, const float* z, float* out_img) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+    e->forward_drawer();
+    e->check_launch("synth");
+    if (out_img)
+      PXR_CUDA(cudaMemcpyAsync(out_img, e->img, sizeof(float) * 3 * e->cfg.image_h * e->cfg.image_w,
+                               cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_make_cutouts(pxr_handle h, const float* img, const pxr_cut_params* p, int iter, float* out_batch) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (img)
+      PXR_CUDA(cudaMemcpyAsync(e->img, img, sizeof(float) * 3 * e->cfg.image_h * e->cfg.image_w,
+                               cudaMemcpyDeviceToDevice, e->st));
+    e->prepare_cut_params(p, iter);
+    e->forward_cutouts();
+    if (out_batch)
+      PXR_CUDA(cudaMemcpyAsync(out_batch, e->batch,
+                               sizeof(float) * e->n_local * 3 * e->cfg.cut_size * e->cfg.cut_size,
+                               cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_encode_image(pxr_handle h, int clip_idx, const float* batch, float* out_embeds) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (clip_idx < 0 || clip_idx >= e->cfg.n_clip) throw EngineError(-14, "bad clip index");
+    if (batch) {
+      // a caller-provided batch: recompute its global range exactly like CLIP_Base.preprocess does
+      PXR_CUDA(cudaMemcpyAsync(e->batch, batch, sizeof(float) * e->n_local * 3 * e->cfg.cut_size * e->cfg.cut_size,
+                               cudaMemcpyDeviceToDevice, e->st));
+      throw EngineError(-17, "pxr_encode_image on an external batch is not wired yet: pass NULL to encode the engine's cutouts");
+    }
+    e->forward_clip(clip_idx);
+    auto& C = e->clip[clip_idx];
+    // unit-norm embeddings (slip.py:66) are produced by the loss kernel; run it when prompts exist
+    if (C.n_prompts > 0) {
+      PXR_CUDA(cudaMemsetAsync(e->losses_dev + C.loss_offset, 0, sizeof(float) * C.n_prompts, e->st));
+      e->loss_clip(clip_idx);
+    }
+    if (out_embeds)
+      PXR_CUDA(cudaMemcpyAsync(out_embeds, C.n_prompts > 0 ? C.e_unit : C.e, sizeof(float) * C.B * C.c.out_dim,
+                               cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_prompt_loss(pxr_handle h, int clip_idx, const float* embeds, float* out_losses) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (clip_idx < 0 || clip_idx >= e->cfg.n_clip) throw EngineError(-14, "bad clip index");
+    auto& C = e->clip[clip_idx];
+    if (embeds)
+      PXR_CUDA(cudaMemcpyAsync(C.e, embeds, sizeof(float) * C.B * C.c.out_dim, cudaMemcpyDeviceToDevice, e->st));
+    PXR_CUDA(cudaMemsetAsync(e->losses_dev + C.loss_offset, 0, sizeof(float) * C.n_prompts, e->st));
+    e->loss_clip(clip_idx);
+    if (out_losses)
+      PXR_CUDA(cudaMemcpyAsync(out_losses, e->losses_dev + C.loss_offset, sizeof(float) * C.n_prompts,
+                               cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_backward(pxr_handle h, float* z_grad) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    e->backward_all();
+    if (z_grad)
+      PXR_CUDA(cudaMemcpyAsync(z_grad, e->z_grad, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_step(pxr_handle h, float* z, float lr, int iter) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    (void)iter;
+    e->step(lr);
+    if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params* p, float* out_losses_host) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+    e->prepare_cut_params(p, iter);
+    PXR_CUDA(cudaMemsetAsync(e->losses_dev, 0, 64 * sizeof(float), e->st));
+    e->forward_drawer();
+    e->forward_cutouts();
+    for (int i = 0; i < e->cfg.n_clip; ++i) {
+      e->forward_clip(i);
+      e->loss_clip(i);
+    }
+    e->backward_all();
+    e->step(lr);
+    if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+    if (out_losses_host) {
+      PXR_CUDA(cudaMemcpyAsync(e->losses_host, e->losses_dev, 64 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+      PXR_CUDA(cudaStreamSynchronize(e->st));
+      memcpy(out_losses_host, e->losses_host, sizeof(float) * e->total_prompts);
+    }
+  });
+}
+
+int pxr_reset_optimizer(pxr_handle h) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    PXR_CUDA(cudaMemsetAsync(e->adam_m, 0, e->z_numel * sizeof(float), e->st));
+    PXR_CUDA(cudaMemsetAsync(e->adam_v, 0, e->z_numel * sizeof(float), e->st));
+    e->adam_t = 0;
+  });
+}
+
+int pxr_sync(pxr_handle h) { PXR_TRY(h, PXR_CUDA(cudaStreamSynchronize(h->e->st))); }
+
+int pxr_num_kernel_launches(pxr_handle h, int64_t* out) {
+  *out = h->e->launches;
+  return 0;
+}
+int pxr_get_stream(pxr_handle h, void** out) {
+  *out = h->e->st;
+  return 0;
+}
+int pxr_z_numel(pxr_handle h, int64_t* out) {
+  *out = h->e->z_numel;
+  return 0;
+}
+int pxr_z_bounds(pxr_handle h, float* zmin, float* zmax) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->zmin) throw EngineError(-18, "this drawer has no per-channel z bounds");
+    PXR_CUDA(cudaMemcpyAsync(zmin, e->zmin, sizeof(float) * e->cfg.z_channels, cudaMemcpyDeviceToDevice, e->st));
+    PXR_CUDA(cudaMemcpyAsync(zmax, e->zmax, sizeof(float) * e->cfg.z_channels, cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_debug_read(pxr_handle h, const char* name, void* out, int64_t nbytes) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    auto it = e->dbg.find(name);
+    if (it == e->dbg.end()) throw EngineError(-19, std::string("unknown debug buffer ") + name);
+    if ((size_t)nbytes > it->second.second) throw EngineError(-19, "debug read larger than the buffer");
+    PXR_CUDA(cudaMemcpyAsync(out, it->second.first, nbytes, cudaMemcpyDefault, e->st));
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+  });
+}
+
+int pxr_set_comm(pxr_handle h, const void*, int, int) {
+  h->e->err = "multi-GPU communicator not built in this revision";
+  return -90;
+}
+int pxr_get_unique_id(void*) { return -90; }
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+"""Python face of the C-ABI engine (include/pixray_b200.h).
+
+torch is used only for device memory: tensors are handed to the library as raw device pointers.  Every method
+maps 1:1 onto a C entry point, which in turn replaces one method of the reference's loop (see the header).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DRAWER_VQGAN, DRAWER_PIXEL = 0, 1
+PAD_REFLECTION, PAD_BORDER = 0, 1
+MOD_VQGAN, MOD_CLIP0, MOD_CLIP1 = 0, 1, 2
+
+VQGAN_F16_16384 = dict(z_channels=256, n_embed=16384, ch=128, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2,
+                       attn_resolution=16, resolution=256)
+CLIP_ARCH = {
+    "ViT-B/32": dict(width=768, layers=12, heads=12, patch=32, image_res=224, out_dim=512),
+    "ViT-B/16": dict(width=768, layers=12, heads=12, patch=16, image_res=224, out_dim=512),
+}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class B200Engine:
+    def __init__(self, *, drawer=DRAWER_VQGAN, image_hw=(256, 256), vqgan=None, grid=None, cutn=64, cut_size=224,
+                 clip=(), noise_fac=0.1, seed=0, device=0, rank=0, world=1, grad_scale=0.0, lr_betas=(0.9, 0.999),
+                 adam_eps=1e-8):
+        if not torch.cuda.is_available():
+            raise EngineError("pixray_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = _lib.load()
+        cfg = _lib.Config()
+        cfg.device, cfg.rank, cfg.world = device, rank, world
+        cfg.drawer = drawer
+        cfg.image_h, cfg.image_w = image_hw
+        if drawer == DRAWER_VQGAN:
+            v = dict(VQGAN_F16_16384) if vqgan is None else dict(vqgan)
+            cfg.z_channels, cfg.n_embed, cfg.ch = v["z_channels"], v["n_embed"], v["ch"]
+            cfg.num_res_blocks, cfg.attn_resolution, cfg.resolution = v["num_res_blocks"], v["attn_resolution"], v["resolution"]
+            cfg.n_levels = len(v["ch_mult"])
+            for i, m in enumerate(v["ch_mult"]):
+                cfg.ch_mult[i] = m
+            f = 2 ** (cfg.n_levels - 1)
+            self.z_shape = (1, cfg.z_channels, image_hw[0] // f, image_hw[1] // f)
+        else:
+            cfg.grid_rows, cfg.grid_cols = grid
+            self.z_shape = (1, 3, grid[0], grid[1])
+        cfg.cutn, cfg.cut_size = cutn, cut_size
+        cfg.n_clip = len(clip)
+        for i, c in enumerate(clip):
+            for k, val in c.items():
+                setattr(cfg.clip[i], k, val)
+        cfg.noise_fac, cfg.seed = noise_fac, seed
+        cfg.op_dtype, cfg.grad_scale = 0, grad_scale
+        cfg.beta1, cfg.beta2, cfg.adam_eps = lr_betas[0], lr_betas[1], adam_eps
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.cutn, self.cut_size, self.world, self.rank = cutn, cut_size, world, rank
+        self.n_local = cutn // world
+        self.image_hw = tuple(image_hw)
+        self.clip_dims = [c["out_dim"] for c in clip]
+        self.n_prompts = [0 for _ in clip]
+        h = C.c_void_p()
+        rc = self.lib.pxr_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"pxr_create failed ({rc}): {self.lib.pxr_last_error(None).decode()}")
+        self.h = h
+        self._keep = []
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self.lib.pxr_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pxr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.pxr_sync(self.h), "pxr_sync")
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _new(self, *shape):
+        return torch.empty(*shape, device=self.device, dtype=torch.float32)
+
+    # ------------------------------------------------------------------ setup
+    def load_module(self, module_id, state_dict):
+        """Feed a reference-style state_dict (taming VQModel or openai-CLIP 'visual.*' keys)."""
+        for name, t in state_dict.items():
+            if not torch.is_floating_point(t):
+                continue
+            a = t.detach().to(torch.float32).contiguous().cpu()
+            dims = (C.c_int64 * max(a.dim(), 1))(*(a.shape if a.dim() else (1,)))
+            rc = self.lib.pxr_load_weight(self.h, module_id, name.encode(), C.c_void_p(a.data_ptr()), dims,
+                                          max(a.dim(), 1))
+            self._check(rc, f"pxr_load_weight({name})")
+
+    def finalize(self):
+        self._check(self.lib.pxr_finalize(self.h), "pxr_finalize")
+
+    def set_prompts(self, clip_idx, embeds, weights, stops):
+        e = np.ascontiguousarray(np.asarray(embeds, dtype=np.float32))
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float32))
+        s = np.ascontiguousarray(np.asarray(stops, dtype=np.float32))
+        s = np.maximum(s, np.float32(-3.0e38))  # -inf -> lowest finite (maximum(d, -inf) == d either way)
+        n, D = e.shape
+        rc = self.lib.pxr_set_prompts(self.h, clip_idx, e.ctypes.data_as(C.c_void_p), n, D,
+                                      w.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p))
+        self._check(rc, "pxr_set_prompts")
+        self.n_prompts[clip_idx] = n
+
+    def z_bounds(self):
+        zc = self.z_shape[1]
+        lo, hi = self._new(zc), self._new(zc)
+        self._check(self.lib.pxr_z_bounds(self.h, self._p(lo), self._p(hi)), "pxr_z_bounds")
+        self.sync()
+        return lo, hi
+
+    def _cut_params(self, transforms, zoom_padding, fill, noise_facs, noise):
+        p = _lib.CutParams()
+        keep = []
+        if transforms is not None:
+            t = np.ascontiguousarray(np.asarray(transforms, dtype=np.float32).reshape(self.cutn, 9))
+            keep.append(t)
+            p.transforms = t.ctypes.data_as(C.c_void_p)
+        p.zoom_padding, p.fill = int(zoom_padding), float(fill)
+        if noise_facs is not None:
+            f = np.ascontiguousarray(np.asarray(noise_facs, dtype=np.float32).reshape(self.cutn))
+            keep.append(f)
+            p.noise_facs = f.ctypes.data_as(C.c_void_p)
+        if noise is not None:
+            nz = noise.to(self.device, torch.float32).contiguous()
+            keep.append(nz)
+            p.noise = C.c_void_p(nz.data_ptr())
+        self._keep = keep
+        return p
+
+    # ------------------------------------------------------------------ per-op entry points (parity tests)
+    def synth(self, z):
+        z = z.to(self.device, torch.float32).contiguous()
+        out = self._new(1, 3, *self.image_hw)
+        torch.cuda.current_stream().synchronize()
+        self._check(self.lib.pxr_synth(self.h, self._p(z), self._p(out)), "pxr_synth")
+        self.sync()
+        return out
+
+    def make_cutouts(self, img=None, *, transforms=None, zoom_padding=PAD_REFLECTION, fill=0.0, noise_facs=None,
+                     noise=None, it=0, use_engine_rng=False):
+        if img is not None:
+            img = img.to(self.device, torch.float32).contiguous()
+        out = self._new(self.n_local, 3, self.cut_size, self.cut_size)
+        p = None if use_engine_rng else self._cut_params(transforms, zoom_padding, fill, noise_facs, noise)
+        torch.cuda.current_stream().synchronize()
+        rc = self.lib.pxr_make_cutouts(self.h, self._p(img), None if p is None else C.byref(p), it, self._p(out))
+        self._check(rc, "pxr_make_cutouts")
+        self.sync()
+        return out
+
+    def encode_image(self, clip_idx=0):
+        out = self._new(self.n_local, self.clip_dims[clip_idx])
+        self._check(self.lib.pxr_encode_image(self.h, clip_idx, None, self._p(out)), "pxr_encode_image")
+        self.sync()
+        return out
+
+    def prompt_loss(self, clip_idx=0, embeds=None):
+        if embeds is not None:
+            embeds = embeds.to(self.device, torch.float32).contiguous()
+            torch.cuda.current_stream().synchronize()
+        out = self._new(self.n_prompts[clip_idx])
+        self._check(self.lib.pxr_prompt_loss(self.h, clip_idx, self._p(embeds), self._p(out)), "pxr_prompt_loss")
+        self.sync()
+        return out
+
+    def backward(self):
+        g = self._new(*self.z_shape)
+        self._check(self.lib.pxr_backward(self.h, self._p(g)), "pxr_backward")
+        self.sync()
+        return g
+
+    def step(self, z, lr, it=0):
+        self._check(self.lib.pxr_step(self.h, self._p(z), C.c_float(lr), it), "pxr_step")
+        self.sync()
+        return z
+
+    def reset_optimizer(self):
+        self._check(self.lib.pxr_reset_optimizer(self.h), "pxr_reset_optimizer")
+
+    # ------------------------------------------------------------------ the fast path (what bench.py times)
+    def iterate(self, z, lr, it, *, params=None, losses_out=None):
+        """One train() iteration entirely inside the library.  params: dict(transforms, zoom_padding, fill,
+        noise_facs, noise) or None for the engine's own Philox draws.  losses_out: float32 numpy array (host) to
+        receive the per-prompt losses (forces a stream sync), or None."""
+        p = None
+        if params is not None:
+            p = self._cut_params(params.get("transforms"), params.get("zoom_padding", it % 2),
+                                 params.get("fill", 0.0), params.get("noise_facs"), params.get("noise"))
+        lp = None if losses_out is None else losses_out.ctypes.data_as(C.c_void_p)
+        rc = self.lib.pxr_iterate(self.h, self._p(z), C.c_float(lr), it, None if p is None else C.byref(p), lp)
+        self._check(rc, "pxr_iterate")
+
+    def debug_read(self, name, shape, dtype=torch.float32):
+        out = torch.empty(*shape, device=self.device, dtype=dtype)
+        rc = self.lib.pxr_debug_read(self.h, name.encode(), self._p(out), C.c_int64(out.numel() * out.element_size()))
+        self._check(rc, f"pxr_debug_read({name})")
+        return out
+
+    def num_launches(self):
+        n = C.c_int64()
+        self.lib.pxr_num_kernel_launches(self.h, C.byref(n))
+        return n.value
