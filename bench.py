@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: iterations/sec of pixray's per-iteration hot path at
+"vqgan imagenet_f16_16384 256x256, ViT-B/16, cutn=64" (configs[1]), synthetic seeded weights and prompts.
+
+    python bench.py --gpus 1 --steps K --warmup W            engine arm (this repo's CUDA engine)
+    python bench.py --impl reference --gpus N --steps K ...   reference arm: the reference's PyTorch path on the
+                                                              host cores (oracle/ref_path.py driving torch CPU ops)
+
+One "step" = one train() iteration (pixray.py:1436-1512): synth -> MakeCutouts -> encode_image -> Prompt losses ->
+backward -> Adam -> clip_z.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "iters/sec @ 256^2 VQGAN, ViT-B/16, cutn=64"
+WORKLOAD = "vqgan imagenet_f16_16384 256x256, ViT-B/16, cutn=64 (BASELINE.json configs[1])"
+CUTN, CUT_SIZE, IMAGE, LR = 64, 224, (256, 256), 0.2  # lr: pixray.py:1745 default learning_rate 0.2
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax = float(s[1])
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def build_models_cpu(seed=0):
+    from pixray_b200 import synthetic as S
+    from pixray_b200.engine import CLIP_ARCH, VQGAN_F16_16384
+    vq_sd = S.vqgan_state_dict(VQGAN_F16_16384, seed)
+    clip_sd = S.clip_state_dict(CLIP_ARCH["ViT-B/16"], seed + 1)
+    prompts = S.prompts(512, (1.0, 0.1), seed + 2)
+    z0 = S.z0_vqgan(vq_sd["quantize.embedding.weight"], (16, 16), seed + 3)
+    return vq_sd, clip_sd, prompts, z0
+
+
+# ---------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_iteration(vq, clip, prompts, z, adam, T, cutn_sample, it):
+    """The reference's per-iteration body on host cores (oracle restatement of pixray.train()).  Returns
+    (seconds for the drawer part, seconds for the cutout+CLIP part on cutn_sample cutouts)."""
+    from oracle import ref_path as R
+    t0 = time.perf_counter()
+    zz = z.detach().clone().requires_grad_(True)
+    out = R.vqgan_synth(vq, zz)
+    t1 = time.perf_counter()
+    g = torch.Generator().manual_seed(it)
+    facs = torch.rand(cutn_sample, generator=g) * 0.1
+    noise = torch.randn(cutn_sample, 3, CUT_SIZE, CUT_SIZE, generator=g)
+    out_d = out.detach().requires_grad_(True)
+    batch = R.make_cutouts(out_d, T[:cutn_sample], CUT_SIZE, "reflection" if it % 2 == 0 else "border", 0.5, facs,
+                           noise, cutn_zoom=int(0.6 * cutn_sample))
+    emb = R.encode_image(clip, batch).float()
+    loss = sum(R.prompt_loss(emb, *p) for p in prompts)
+    loss.backward()
+    t2 = time.perf_counter()
+    out.backward(out_d.grad)
+    z_new = adam.step(z, zz.grad, LR)
+    zmin, zmax = R.vqgan_z_bounds(vq)
+    z_new = torch.maximum(torch.minimum(z_new, zmax), zmin)
+    t3 = time.perf_counter()
+    return (t1 - t0) + (t3 - t2), (t2 - t1), z_new
+
+
+def run_cpu_reference(steps, warmup, budget_s, seed=0):
+    from oracle import ref_path as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vq_sd, clip_sd, prompts, z = build_models_cpu(seed)
+    vq = R.VQModel()
+    vq.load_state_dict(vq_sd)
+    vq.eval().requires_grad_(False)
+    clip = R.ClipVisual(224, 16, 768, 12, 12, 512)
+    clip.load_state_dict(clip_sd)
+    clip.eval().requires_grad_(False)
+    from pixray_b200.cutouts import sample_transforms as sample_transforms_np
+    T = torch.from_numpy(sample_transforms_np(CUTN, CUT_SIZE, seed))
+    adam = R.AdamState(z)
+    # calibration: one tiny step decides how many cutouts per step fit the budget
+    td, tc, z = cpu_reference_iteration(vq, clip, prompts, z, adam, T, 4, 0)
+    per_cut = tc / 4
+    cutn_sample = CUTN
+    while cutn_sample > 4 and (steps + warmup) * (td + per_cut * cutn_sample) > budget_s:
+        cutn_sample //= 2
+    for it in range(warmup):
+        _, _, z = cpu_reference_iteration(vq, clip, prompts, z, adam, T, cutn_sample, it)
+    tds, tcs = [], []
+    for it in range(warmup, warmup + steps):
+        a, b, z = cpu_reference_iteration(vq, clip, prompts, z, adam, T, cutn_sample, it)
+        tds.append(a)
+        tcs.append(b)
+    t_full = float(np.mean(tds)) + float(np.mean(tcs)) * (CUTN / cutn_sample)
+    sample = (f"{steps} steps of: full VQGAN synth fwd+bwd + Adam/clip_z, MakeCutouts+CLIP fwd+bwd on {cutn_sample} of "
+              f"{CUTN} cutouts (CLIP part scaled x{CUTN // cutn_sample} to the full cutn); torch fp32, {cores} threads")
+    return dict(value=1.0 / t_full, unit="iters/sec", cores=cores, kind="port", sample=sample,
+                ms_per_step=t_full * 1e3)
+
+
+# ---------------------------------------------------------------------------------------------- engine arm
+def run_engine(args, rank, world):
+    import torch.distributed as dist
+    from pixray_b200 import engine as E
+    from pixray_b200 import synthetic as S
+    from pixray_b200.cutouts import sample_transforms as sample_transforms_np
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    vq_sd, clip_sd, prompts, z0 = build_models_cpu(0)
+    # multi-GPU: independent replicas (weak scaling) until the cutout-sharded allreduce lands (DESIGN.md, row e)
+    eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=IMAGE, cutn=CUTN, clip=[E.CLIP_ARCH["ViT-B/16"]], noise_fac=0.1,
+                       seed=rank, device=local_rank)
+    eng.load_module(E.MOD_VQGAN, vq_sd)
+    eng.load_module(E.MOD_CLIP0, clip_sd)
+    eng.finalize()
+    eng.set_prompts(0, torch.cat([p[0] for p in prompts]).numpy(), [p[1] for p in prompts], [p[2] for p in prompts])
+    z = z0.clone().cuda()
+    ext = torch.cuda.ExternalStream(eng.stream_ptr())
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident arm: engine RNG for the cutouts, no host traffic inside the timed region
+    for it in range(args.warmup):
+        eng.iterate(z, LR, it)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = eng.num_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for it in range(args.warmup, args.warmup + args.steps):
+        eng.iterate(z, LR, it)
+    e1.record(ext)
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = eng.num_launches() - n0
+    # ---- e2e arm: host transforms in (H2D) and host losses out (D2H + sync) every step, through the Python plugin API
+    Ts = [sample_transforms_np(CUTN, CUT_SIZE, 1000 + i) for i in range(args.steps)]
+    losses = np.zeros(2, dtype=np.float32)
+    for it in range(min(3, args.warmup)):
+        eng.iterate(z, LR, it, params=dict(transforms=Ts[0], zoom_padding=it % 2, fill=0.5), losses_out=losses)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(ext)
+    for i in range(args.steps):
+        eng.iterate(z, LR, i, params=dict(transforms=Ts[i], zoom_padding=i % 2, fill=0.5), losses_out=losses)
+    f1.record(ext)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    # ---- per-kernel split for the roofline of the dominant kernel (gemm_tc_kernel)
+    prof = eng.profile_iteration(z, LR, args.warmup + args.steps)
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    clocks = sampler.summary()
+    S_flops = 2 * (CUTN * S.vit_fwd_flops(E.CLIP_ARCH["ViT-B/16"]) + S.vqgan_decoder_fwd_flops(E.VQGAN_F16_16384, IMAGE))
+    gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": "iters/sec", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cutn": CUTN, "image": "256x256", "clip": "ViT-B/16",
+                   "weights": "seeded random (no checkpoints offline)", "parallelism": f"{world} independent replicas",
+                   "l2": "per-step working set (saved activations ~3 GB) >> 126 MB L2, no explicit flush",
+                   "algorithmic_flops_per_iter": S_flops},
+        "clocks": clocks,
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "iters/sec",
+                "h2d_bytes_per_step": CUTN * 9 * 4, "d2h_bytes_per_step": 64 * 4},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",
+                     "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + ", sustained bf16/f16 GEMM figure",
+                     "launches_per_iter": prof["gemm_launches"], "gemm_ms_per_iter": prof["gemm_ms"],
+                     "other_ms_per_iter": prof["other_ms"], "iter_ms_profiled": prof["total_ms"],
+                     "algorithmic_flops_per_launch": prof["gemm_flops"] / max(1, prof["gemm_launches"]),
+                     "whole_iter_tflops": S_flops * args.steps / (ms * 1e-3) / 1e12},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_reference(steps=1, warmup=0, budget_s=25.0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_cpu_reference(args.steps, args.warmup, budget_s=150.0)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "iters/sec", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "cutn": CUTN, "image": "256x256", "clip": "ViT-B/16",
+                           "note": "reference PyTorch path on host cores (no GPU)"},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+    run_engine(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,9 @@ int pxr_sync(pxr_handle h);
 
 /* Introspection used by tests and bench.py */
 int pxr_num_kernel_launches(pxr_handle h, int64_t* out); /* launches issued since create */
+/* one iteration with CUDA events around every launch: out6 = {gemm ms, gemm launches, gemm algorithmic FLOPs,
+ * other ms, other launches, whole-iteration ms}; feeds bench.py's roofline object */
+int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* out6);
 int pxr_get_stream(pxr_handle h, void** out);
 int pxr_z_numel(pxr_handle h, int64_t* out);
 int pxr_z_bounds(pxr_handle h, float* zmin, float* zmax); /* device [z_channels]: codebook per-channel min/max */

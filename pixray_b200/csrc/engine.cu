@@ -131,9 +131,32 @@ class Engine {
     return it->second;
   }
 
+  // profiling (pxr_profile_iteration): CUDA-event pair around every op, split gemm_tc_kernel vs everything else
+  bool profiling = false;
+  struct ProfRec {
+    cudaEvent_t a, b;
+    double flops;
+    int launches;
+  };
+  std::vector<ProfRec> prof;
+  void prof_begin(ProfRec& r) {
+    PXR_CUDA(cudaEventCreate(&r.a));
+    PXR_CUDA(cudaEventCreate(&r.b));
+    PXR_CUDA(cudaEventRecord(r.a, st));
+  }
   void run(OpList& l) {
     for (size_t i = 0; i < l.ops.size(); ++i) {
-      l.ops[i]();
+      if (profiling) {
+        ProfRec r;
+        r.flops = l.flops[i];
+        r.launches = l.launches[i];
+        prof_begin(r);
+        l.ops[i]();
+        PXR_CUDA(cudaEventRecord(r.b, st));
+        prof.push_back(r);
+      } else {
+        l.ops[i]();
+      }
       launches += l.launches[i];
     }
   }
@@ -184,7 +207,7 @@ class Engine {
     int rc = gemm_plan_make(plan.get(), A, B, M, N, K, e, bn, fmt, num_sms, buf, sizeof buf);
     if (rc) throw EngineError(rc, std::string("gemm plan: ") + buf);
     cudaStream_t s = st;
-    l.add(1, [plan, s] { gemm_launch(*plan, s); });
+    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops);
   }
   void add_conv(OpList& l, const act_t* in, int H, int Wd, int cin, const act_t* wt, int cout_pad, int n_out, int ks,
                 const GemmEpilogue& e) {
@@ -196,7 +219,7 @@ class Engine {
                             sizeof buf);
     if (rc) throw EngineError(rc, std::string("conv plan: ") + buf);
     cudaStream_t s = st;
-    l.add(1, [plan, s] { gemm_launch(*plan, s); });
+    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops);
   }
 
   // ------------------------------------------------------------------ build steps
@@ -570,10 +593,8 @@ void Engine::build_vqgan() {
   Act hcur = conv_fwd_bwd(hq, cin, b_in2);
   {
     OpList b;  // execution order: conv_in dgrad, then post_quant dgrad, then vq backward
-    b.ops = b_in2.ops;
-    b.launches = b_in2.launches;
-    b.ops.insert(b.ops.end(), b_in.ops.begin(), b_in.ops.end());
-    b.launches.insert(b.launches.end(), b_in.launches.begin(), b_in.launches.end());
+    b.append(b_in2);
+    b.append(b_in);
     float* zg = z_grad;
     float inv = 1.f / S;
     b.add(1, [=] { vq_backward(zq.g, inv, zc, hw, zg, cs); });
@@ -635,10 +656,7 @@ void Engine::build_vqgan() {
     bwd_stack.push_back(std::move(b));
   }
   // flatten backward stack in reverse block order
-  for (int i = (int)bwd_stack.size() - 1; i >= 0; --i) {
-    drawer_bwd.ops.insert(drawer_bwd.ops.end(), bwd_stack[i].ops.begin(), bwd_stack[i].ops.end());
-    drawer_bwd.launches.insert(drawer_bwd.launches.end(), bwd_stack[i].launches.begin(), bwd_stack[i].launches.end());
-  }
+  for (int i = (int)bwd_stack.size() - 1; i >= 0; --i) drawer_bwd.append(bwd_stack[i]);
   bwd_stack.clear();
 }
 
@@ -1287,6 +1305,58 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
       PXR_CUDA(cudaStreamSynchronize(e->st));
       memcpy(out_losses_host, e->losses_host, sizeof(float) * e->total_prompts);
     }
+  });
+}
+
+// One full iteration with a CUDA-event pair around every op (engine stream).  out[0] = ms in gemm_tc_kernel launches,
+// out[1] = number of those launches, out[2] = their algorithmic FLOPs, out[3] = ms in all other kernels,
+// out[4] = number of other launches, out[5] = ms of the whole iteration (first event -> last event).
+int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* out6) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+    e->prepare_cut_params(nullptr, iter);
+    PXR_CUDA(cudaMemsetAsync(e->losses_dev, 0, 64 * sizeof(float), e->st));
+    e->prof.clear();
+    e->profiling = true;
+    cudaEvent_t t0;
+    cudaEvent_t t1;
+    PXR_CUDA(cudaEventCreate(&t0));
+    PXR_CUDA(cudaEventCreate(&t1));
+    PXR_CUDA(cudaEventRecord(t0, e->st));
+    e->forward_drawer();
+    e->forward_cutouts();
+    for (int i = 0; i < e->cfg.n_clip; ++i) {
+      e->forward_clip(i);
+      e->loss_clip(i);
+    }
+    e->backward_all();
+    e->step(lr);
+    PXR_CUDA(cudaEventRecord(t1, e->st));
+    e->profiling = false;
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    for (auto& r : e->prof) {
+      float ms = 0;
+      PXR_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      if (r.flops > 0) {
+        out6[0] += ms;
+        out6[1] += r.launches;
+        out6[2] += r.flops;
+      } else {
+        out6[3] += ms;
+        out6[4] += r.launches;
+      }
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    e->prof.clear();
+    float tot = 0;
+    PXR_CUDA(cudaEventElapsedTime(&tot, t0, t1));
+    out6[5] = tot;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
   });
 }
 

@@ -58,9 +58,16 @@ typedef std::function<void()> Op;
 struct OpList {
   std::vector<Op> ops;
   std::vector<int> launches;
-  void add(int n_launch, Op f) {
+  std::vector<double> flops;  // > 0: a gemm_tc_kernel launch with this many algorithmic FLOPs
+  void add(int n_launch, Op f, double fl = 0.0) {
     ops.push_back(std::move(f));
     launches.push_back(n_launch);
+    flops.push_back(fl);
+  }
+  void append(const OpList& o) {
+    ops.insert(ops.end(), o.ops.begin(), o.ops.end());
+    launches.insert(launches.end(), o.launches.begin(), o.launches.end());
+    flops.insert(flops.end(), o.flops.begin(), o.flops.end());
   }
 };
 

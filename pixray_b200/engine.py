@@ -218,6 +218,17 @@ class B200Engine:
         self._check(rc, f"pxr_debug_read({name})")
         return out
 
+    def profile_iteration(self, z, lr, it):
+        out = (C.c_double * 6)()
+        self._check(self.lib.pxr_profile_iteration(self.h, self._p(z), C.c_float(lr), it, out), "pxr_profile_iteration")
+        return dict(gemm_ms=out[0], gemm_launches=int(out[1]), gemm_flops=out[2], other_ms=out[3],
+                    other_launches=int(out[4]), total_ms=out[5])
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        self.lib.pxr_get_stream(self.h, C.byref(p))
+        return p.value
+
     def num_launches(self):
         n = C.c_int64()
         self.lib.pxr_num_kernel_launches(self.h, C.byref(n))

@@ -1,0 +1,159 @@
+"""CPU: pin oracle/ref_path.py against vectors produced by the REAL reference code (oracle/make_golden.py ran the
+reference's own pixray.py / vqgan.py / slip.py / fast_pixeldrawer.py under oracle/shim.py in the authoring container).
+Also cross-checks the restated CLIP VisionTransformer against transformers' CLIPVisionModelWithProjection."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_path as R
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+def t(name):
+    return torch.from_numpy(np.asarray(G[name]))
+
+
+def close(a, b, tol=1e-6):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= tol * max(1.0, b.abs().max().item()), err
+
+
+@pytest.mark.parametrize("tag", ["pos", "neg", "small"])
+def test_prompt_forward_backward(tag):
+    x = t("prompt_input").clone().requires_grad_(True)
+    val = R.prompt_loss(x, t(f"prompt_{tag}_embed"), float(G[f"prompt_{tag}_w"]), float(G[f"prompt_{tag}_stop"]))
+    val.backward()
+    close(val.detach(), t(f"prompt_{tag}_val"))
+    close(x.grad, t(f"prompt_{tag}_grad"))
+
+
+def test_spherical_dist_loss():
+    close(R.spherical_dist_loss(t("sph_x"), t("sph_y")), t("sph_out"))
+
+
+def test_vector_quantize():
+    x = t("vq_x").clone().requires_grad_(True)
+    out, idx = R.vector_quantize(x, t("vq_codebook"))
+    (out * t("vq_w")).sum().backward()
+    close(out.detach(), t("vq_out"))
+    close(x.grad, t("vq_grad"))
+    assert idx.dtype == torch.int64
+
+
+def test_clamp_with_grad():
+    x = t("clamp_x").clone().requires_grad_(True)
+    y = R.clamp_with_grad(x, 0, 1)
+    y.backward(t("clamp_g"))
+    close(y.detach(), t("clamp_y"))
+    close(x.grad, t("clamp_dx"))
+
+
+@pytest.mark.parametrize("mode", ["reflection", "border"])
+def test_make_cutouts_cached_path(mode):
+    img = t("cut_img").clone().requires_grad_(True)
+    T = t("cut_T")
+    cutn, cs = T.shape[0], 16
+    # replay the reference's draws (pixray.py:509-510): uniform_ for the factors, then randn_like
+    torch.manual_seed(77)
+    facs = torch.empty(cutn, 1, 1, 1).uniform_(0, 0.1)
+    noise = torch.randn(cutn, 3, cs, cs)
+    batch = R.make_cutouts(img, T, cs, mode, 0.3, facs, noise)
+    assert int(G["cut_zoom_n"]) == int(0.6 * cutn)
+    close(batch.detach(), t(f"cut_{mode}_batch"), 1e-6)
+    (batch * t("cut_w")).sum().backward()
+    close(img.grad, t(f"cut_{mode}_dimg"), 1e-5)
+
+
+def test_clip_base_preprocess_and_encode():
+    vit = R.init_clip_weights(R.ClipVisual(32, 8, 64, 2, 1, 16), 3)
+    imgs = t("clip_imgs").clone().requires_grad_(True)
+    close(R.clip_preprocess(imgs).detach(), t("clip_pre"))
+    emb = R.encode_image(vit, imgs)
+    close(emb.detach(), t("clip_emb"), 1e-5)
+    (emb * t("clip_w")).sum().backward()
+    close(imgs.grad, t("clip_dimgs"), 1e-4)
+
+
+def test_fast_pixel_synth():
+    z = t("pixel_z").clone().requires_grad_(True)
+    out = R.pixel_synth(z, tuple(t("pixel_out").shape[-2:]))
+    close(out.detach(), t("pixel_out"))
+    (out * t("pixel_w")).sum().backward()
+    close(z.grad, t("pixel_dz"))
+
+
+def test_vqgan_synth_and_clip_z():
+    vq = R.init_vqgan_weights(R.VQModel(n_embed=64, embed_dim=32, ch=32, ch_mult=(1, 2), num_res_blocks=1,
+                                        attn_resolutions=(4,), resolution=8, z_channels=32), 4)
+    z = t("vqsynth_z").clone().requires_grad_(True)
+    out = R.vqgan_synth(vq, z)
+    close(out.detach(), t("vqsynth_out"), 1e-5)
+    (out * t("vqsynth_w")).sum().backward()
+    close(z.grad, t("vqsynth_dz"), 1e-4)
+    zmin, zmax = R.vqgan_z_bounds(vq)
+    close(torch.maximum(torch.minimum(t("clipz_in"), zmax), zmin), t("clipz_out"))
+
+
+def test_adam_matches_torch_optim():
+    z = t("adam_z0").clone()
+    st = R.AdamState(z)
+    for k in range(3):
+        z = st.step(z, t(f"adam_g{k}"), 0.2)
+        close(z, t(f"adam_z{k + 1}"), 1e-6)
+
+
+def test_pool_window_bounds_are_atens():
+    """Integer bookkeeping: the window bounds the CUDA pool kernel uses must be ATen's, checked via the real op."""
+    for H, cs in [(256, 224), (512, 224), (32, 224), (24, 16), (20, 16)]:
+        starts, ends = R.adaptive_pool_bounds(H, cs)
+        x = torch.arange(H, dtype=torch.float32).reshape(1, 1, H, 1)
+        mx = torch.nn.functional.adaptive_max_pool2d(x, (cs, 1)).reshape(-1)
+        av = torch.nn.functional.adaptive_avg_pool2d(x, (cs, 1)).reshape(-1)
+        assert [int(v) + 1 for v in mx] == ends
+        assert all(abs(float(av[i]) - (starts[i] + ends[i] - 1) / 2) < 1e-4 for i in range(cs))
+
+
+def test_vit_restatement_matches_transformers_clip():
+    """Un-vendored leaf: openai-CLIP VisionTransformer.  Cross-check against HF transformers (quick_gelu)."""
+    tr = pytest.importorskip("transformers")
+    cfg = tr.CLIPVisionConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                              image_size=32, patch_size=8, projection_dim=16, hidden_act="quick_gelu",
+                              layer_norm_eps=1e-5, attn_implementation="eager")
+    hf = tr.CLIPVisionModelWithProjection(cfg).eval()
+    mine = R.init_clip_weights(R.ClipVisual(32, 8, 64, 2, 2, 16), 9)
+    v = mine.visual
+    sd = hf.state_dict()
+    with torch.no_grad():
+        sd["vision_model.embeddings.patch_embedding.weight"].copy_(v.conv1.weight)
+        sd["vision_model.embeddings.class_embedding"].copy_(v.class_embedding)
+        sd["vision_model.embeddings.position_embedding.weight"].copy_(v.positional_embedding)
+        for nm, ln in (("pre_layrnorm", v.ln_pre), ("post_layernorm", v.ln_post)):
+            sd[f"vision_model.{nm}.weight"].copy_(ln.weight)
+            sd[f"vision_model.{nm}.bias"].copy_(ln.bias)
+        sd["visual_projection.weight"].copy_(v.proj.T)
+        for i, blk in enumerate(v.transformer.resblocks):
+            p = f"vision_model.encoder.layers.{i}."
+            W, b = blk.attn.in_proj_weight, blk.attn.in_proj_bias
+            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                sd[p + f"self_attn.{nm}.weight"].copy_(W[j * 64:(j + 1) * 64])
+                sd[p + f"self_attn.{nm}.bias"].copy_(b[j * 64:(j + 1) * 64])
+            sd[p + "self_attn.out_proj.weight"].copy_(blk.attn.out_proj.weight)
+            sd[p + "self_attn.out_proj.bias"].copy_(blk.attn.out_proj.bias)
+            sd[p + "layer_norm1.weight"].copy_(blk.ln_1.weight)
+            sd[p + "layer_norm1.bias"].copy_(blk.ln_1.bias)
+            sd[p + "layer_norm2.weight"].copy_(blk.ln_2.weight)
+            sd[p + "layer_norm2.bias"].copy_(blk.ln_2.bias)
+            sd[p + "mlp.fc1.weight"].copy_(blk.mlp.c_fc.weight)
+            sd[p + "mlp.fc1.bias"].copy_(blk.mlp.c_fc.bias)
+            sd[p + "mlp.fc2.weight"].copy_(blk.mlp.c_proj.weight)
+            sd[p + "mlp.fc2.bias"].copy_(blk.mlp.c_proj.bias)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        a = mine.encode_image(x)
+        b = hf(pixel_values=x).image_embeds
+    close(a, b, 1e-4)

@@ -155,7 +155,10 @@ def test_intermediate_gradients_small():
 
 
 def test_adam_clip_and_iterate_small():
-    cutn, cs = 8, 224
+    """pxr_iterate = forward + backward + Adam + clip_z.  The VQ argmin makes the optimisation trajectory chaotic
+    (one flipped code changes the image), so each iteration is checked from the SAME z: losses and z.grad against the
+    oracle, and the fused Adam/clip_z update exactly against torch-semantics Adam fed the engine's own gradient."""
+    cutn, cs, lr = 8, 224, 0.05
     vq, clip, eng, prompts, z = build(cutn=cutn, seed=7)
     T = random_transforms(cutn, cs, 8)
     zmin, zmax = R.vqgan_z_bounds(vq)
@@ -163,22 +166,21 @@ def test_adam_clip_and_iterate_small():
     assert torch.equal(lo.cpu(), zmin.reshape(-1)) and torch.equal(hi.cpu(), zmax.reshape(-1))
     adam = R.AdamState(z)
     z_ref = z.clone()
-    z_eng = z.clone().cuda()
     losses = np.zeros(2, dtype=np.float32)
     for it in range(3):
         pad = "reflection" if it % 2 == 0 else "border"
         r = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z_ref, [clip], [prompts], torch.from_numpy(T), cs, pad, 0.5,
                       None, None)
-        z_ref = adam.step(z_ref, r["z_grad"], 0.05)
-        z_ref = torch.maximum(torch.minimum(z_ref, zmax), zmin)  # clip_z, vqgan.py:202-204
-        eng.iterate(z_eng, 0.05, it, params=dict(transforms=T, zoom_padding=it % 2, fill=0.5), losses_out=losses)
+        z_eng = z_ref.clone().cuda()
+        eng.iterate(z_eng, lr, it, params=dict(transforms=T, zoom_padding=it % 2, fill=0.5), losses_out=losses)
+        g_eng = eng.debug_read("z_grad", z.shape).cpu()
         ref_l = np.array([float(l) for l in r["losses"]], dtype=np.float32)
         print(f"[parity] iter {it}: losses engine {losses} oracle {ref_l}")
         assert np.abs(losses - ref_l).max() < 5e-3
-    err = (z_eng.cpu() - z_ref).abs().max().item()
-    print(f"[parity] z after 3 Adam steps: max_abs_err={err:.3e} (lr 0.05 => each step moves ~0.05)")
-    # Adam normalises the step to ~lr per element, so sign flips of tiny gradients cost up to 2*lr per step
-    frac_bad = ((z_eng.cpu() - z_ref).abs() > 0.02).float().mean().item()
-    print(f"[parity] fraction of z elements off by > 0.02: {frac_bad:.4f}")
-    assert frac_bad < 0.02
+        e_g, m_g = report(f"iter {it} z.grad", g_eng, r["z_grad"])
+        assert e_g <= 3e-2 * m_g
+        z_next = torch.maximum(torch.minimum(adam.step(z_ref, g_eng, lr), zmax), zmin)  # clip_z, vqgan.py:202-204
+        e_z, _ = report(f"iter {it} z after Adam+clip_z", z_eng, z_next)
+        assert e_z < 2e-5
+        z_ref = z_next
     assert eng.num_launches() > 0
