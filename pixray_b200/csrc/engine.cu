@@ -7,6 +7,7 @@
 //   -> backward of all of the above by hand (dgrad only: every network is frozen, vqgan.py:125, slip.py:176)
 //   -> [allreduce z.grad] -> Adam -> clip_z
 #include "engine.cuh"
+#include "comm.cuh"
 #include "transforms.h"
 #include <cmath>
 #include <cstdio>
@@ -90,8 +91,15 @@ class Engine {
   float* losses_host = nullptr;  // pinned
   int total_prompts = 0;
 
-  // ---- comm (multi-GPU): see comm.cu
+  // ---- comm (multi-GPU, cutout sharding): one NCCL communicator owned by the engine (comm.cuh)
   void* comm = nullptr;
+  float* xbuf = nullptr;  // {min, -max} exchange buffer
+  void nccl_check(int rc, const char* what) {
+    if (rc != 0) {
+      const char* m = Comm::api().err_str ? Comm::api().err_str(rc) : "?";
+      throw EngineError(-91, std::string(what) + ": NCCL error " + m);
+    }
+  }
 
   explicit Engine(const pxr_config& c) : cfg(c) {}
   ~Engine();
@@ -265,6 +273,7 @@ class Engine {
 
 Engine::~Engine() {
   if (st) cudaStreamSynchronize(st);
+  if (comm && Comm::api().destroy) Comm::api().destroy(comm);
   for (void* p : allocs) cudaFree(p);
   for (int i = 0; i < RING; ++i) {
     if (minv_host[i]) cudaFreeHost(minv_host[i]);
@@ -692,6 +701,7 @@ void Engine::build_cutouts() {
   range = dalloc<float>(4);
   irange = dalloc<int>(4);
   sums = dalloc<float>(4);
+  xbuf = dalloc<float>(4);
   minv_dev = dalloc<float>((size_t)n_local * 9);
   facs_dev = dalloc<float>(n_local);
   for (int i = 0; i < RING; ++i) {
@@ -762,6 +772,12 @@ void Engine::forward_cutouts() {
   cutout_forward(cut_args, batch, part_min, part_max, part_imin, part_imax, st);
   minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
   launches += 3;
+  if (comm) {  // global min / max over all ranks' cutouts (slip.py:21-36 reduces over the whole batch)
+    range_pack(range, xbuf, st);
+    nccl_check(Comm::api().all_reduce(xbuf, xbuf, 2, Comm::kFloat32, Comm::kMin, comm, st), "allreduce(min,max)");
+    range_unpack(xbuf, range, irange, st);
+    launches += 3;
+  }
   check_launch("cutouts forward");
 }
 
@@ -1041,11 +1057,24 @@ void Engine::backward_all() {
     patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, i > 0, g_batch, sums, st);
     launches += 1;
   }
-  // TODO(multi-GPU): allreduce(sums) across ranks belongs here
+  if (comm)  // d/dmin, d/dmax terms need the sums over ALL cutouts
+    nccl_check(Comm::api().all_reduce(sums, sums, 2, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(sums)");
   PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * 3 * cfg.cut_size * cfg.cut_size, st));
   cutout_backward(cut_args, g_batch, range, irange, sums, g_pooled, st);
   pool_backward(g_pooled, pool_argmax, cfg.image_h, cfg.image_w, cfg.cut_size, g_img, st);
   launches += 2;
+  if (comm) {
+    // The path's one exchange step.  It sits on the IMAGE gradient, not on z.grad: ClampWithGrad's backward
+    // (vqgan.py:76-79) masks by the sign of the incoming gradient, so the drawer backward is not linear in it and
+    // must see the gradient of ALL cutouts.  Every rank then runs the (replicated) drawer backward on identical bits.
+    Comm& c = Comm::api();
+    nccl_check(c.group_start(), "group start");
+    nccl_check(c.all_reduce(g_img, g_img, (size_t)3 * cfg.image_h * cfg.image_w, Comm::kFloat32, Comm::kSum, comm, st),
+               "allreduce(d loss / d image)");
+    nccl_check(c.all_reduce(losses_dev, losses_dev, 64, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(losses)");
+    nccl_check(c.group_end(), "group end");
+    launches += 2;
+  }
   run(drawer_bwd);
   check_launch("backward");
 }
@@ -1237,7 +1266,11 @@ int pxr_encode_image(pxr_handle h, int clip_idx, const float* batch, float* out_
       // a caller-provided batch: recompute its global range exactly like CLIP_Base.preprocess does
       PXR_CUDA(cudaMemcpyAsync(e->batch, batch, sizeof(float) * e->n_local * 3 * e->cfg.cut_size * e->cfg.cut_size,
                                cudaMemcpyDeviceToDevice, e->st));
-      throw EngineError(-17, "pxr_encode_image on an external batch is not wired yet: pass NULL to encode the engine's cutouts");
+      const int np_ = e->n_parts < 1024 ? e->n_parts : 1024;
+      pxr::minmax_partials(e->batch, (long long)e->n_local * 3 * e->cfg.cut_size * e->cfg.cut_size, np_, e->part_min,
+                           e->part_max, e->part_imin, e->part_imax, e->st);
+      pxr::minmax_reduce(nullptr, e->part_min, e->part_max, e->part_imin, e->part_imax, np_, e->range, e->irange, e->st);
+      e->launches += 2;
     }
     e->forward_clip(clip_idx);
     auto& C = e->clip[clip_idx];
@@ -1403,10 +1436,32 @@ int pxr_debug_read(pxr_handle h, const char* name, void* out, int64_t nbytes) {
   });
 }
 
-int pxr_set_comm(pxr_handle h, const void*, int, int) {
-  h->e->err = "multi-GPU communicator not built in this revision";
-  return -90;
+int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (world != e->cfg.world || rank != e->cfg.rank)
+      throw EngineError(-92, "pxr_set_comm: rank/world differ from the pxr_config the engine was created with");
+    if (world == 1) return 0;
+    std::string msg;
+    if (!pxr::Comm::api().load(&msg)) throw EngineError(-90, msg);
+    pxr::NcclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof id);
+    e->nccl_check(pxr::Comm::api().init_rank(&e->comm, world, id, rank), "ncclCommInitRank");
+  });
 }
-int pxr_get_unique_id(void*) { return -90; }
+int pxr_get_unique_id(void* out128) {
+  std::string msg;
+  if (!pxr::Comm::api().load(&msg)) {
+    g_create_err = msg;
+    return -90;
+  }
+  pxr::NcclUniqueId id;
+  if (pxr::Comm::api().get_unique_id(&id) != 0) {
+    g_create_err = "ncclGetUniqueId failed";
+    return -91;
+  }
+  memcpy(out128, &id, sizeof id);
+  return 0;
+}
 
 }  // extern "C"

@@ -64,7 +64,13 @@ int cutout_num_blocks(int n_local, int cs);
 // batch [n_local,3,cs,cs] fp32; block partial min/max (+ element index) for the global range normalise (slip.py:21-36)
 void cutout_forward(const CutoutArgs& a, float* batch, float* part_min, float* part_max, int* part_imin,
                     int* part_imax, cudaStream_t st);
-// range[0]=min, range[1]=R (max of x-min, 1 if zero), irange[0]=argmin elem, irange[1]=argmax elem
+// multi-rank range exchange helpers: xbuf = {min, -max} for one allreduce(min)
+void range_pack(const float* range, float* xbuf, cudaStream_t st);
+void range_unpack(const float* xbuf, float* range, int* irange, cudaStream_t st);
+// partials of an arbitrary buffer (same layout as cutout_forward's), nparts blocks
+void minmax_partials(const float* x, long long n, int nparts, float* part_min, float* part_max, int* part_imin,
+                     int* part_imax, cudaStream_t st);
+// range[0]=min, range[1]=R (max of x-min, 1 if zero), range[2]=max, range[3]=R!=0; irange = argmin / argmax element
 void minmax_reduce(const float* batch_or_null, const float* part_min, const float* part_max, const int* part_imin,
                    const int* part_imax, int nparts, float* range, int* irange, cudaStream_t st);
 // patches[(n*gp + py)*gp + px, (c*P + iy)*P + ix] = ((x - min)/R - mean_c)/std_c   (slip.py:52-60 + conv1 im2col)

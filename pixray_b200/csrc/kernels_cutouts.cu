@@ -251,6 +251,51 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_fwd_kernel(CutoutArgs a, f
   }
 }
 
+// block partial min / max (+ first element index) of an arbitrary fp32 buffer -- used when a caller hands
+// pxr_encode_image its own batch (CLIP_Base.preprocess recomputes the global range, slip.py:21-36)
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __restrict__ x, long long n,
+                                                             float* __restrict__ part_min,
+                                                             float* __restrict__ part_max,
+                                                             int* __restrict__ part_imin,
+                                                             int* __restrict__ part_imax) {
+  float tmin = FLT_MAX, tmax = -FLT_MAX;
+  int imin = 0x7fffffff, imax = 0x7fffffff;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (v < tmin || (v == tmin && (int)i < imin)) {
+      tmin = v;
+      imin = (int)i;
+    }
+    if (v > tmax || (v == tmax && (int)i < imax)) {
+      tmax = v;
+      imax = (int)i;
+    }
+  }
+  __shared__ float smin[256], smax[256];
+  __shared__ int simin[256], simax[256];
+  smin[threadIdx.x] = tmin;
+  smax[threadIdx.x] = tmax;
+  simin[threadIdx.x] = imin;
+  simax[threadIdx.x] = imax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 256; ++i) {
+      if (smin[i] < tmin || (smin[i] == tmin && simin[i] < imin)) {
+        tmin = smin[i];
+        imin = simin[i];
+      }
+      if (smax[i] > tmax || (smax[i] == tmax && simax[i] < imax)) {
+        tmax = smax[i];
+        imax = simax[i];
+      }
+    }
+    part_min[blockIdx.x] = tmin;
+    part_max[blockIdx.x] = tmax;
+    part_imin[blockIdx.x] = imin;
+    part_imax[blockIdx.x] = imax;
+  }
+}
+
 __global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restrict__ part_min,
                                                             const float* __restrict__ part_max,
                                                             const int* __restrict__ part_imin,
@@ -292,9 +337,28 @@ __global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restr
     range[0] = tmin;
     range[1] = (R != 0.f) ? R : 1.f;  // `if maxv != 0` (slip.py:33)
     range[2] = tmax;
+    range[3] = (R != 0.f) ? 1.f : 0.f;  // whether the division (and so d/dmax) happened
     irange[0] = imin;
-    irange[1] = (R != 0.f) ? imax : -1;
+    irange[1] = imax;
   }
+}
+
+// Cutout-sharded ranks: exchange buffer {min, -max} goes through one allreduce(min); afterwards every rank holds the
+// global range, and only the rank that owns the extreme element keeps its index (others get -1).
+__global__ void range_pack_kernel(const float* __restrict__ range, float* __restrict__ xbuf) {
+  xbuf[0] = range[0];
+  xbuf[1] = -range[2];
+}
+__global__ void range_unpack_kernel(const float* __restrict__ xbuf, float* __restrict__ range,
+                                    int* __restrict__ irange) {
+  const float gmin = xbuf[0], gmax = -xbuf[1];
+  if (range[0] != gmin) irange[0] = -1;
+  if (range[2] != gmax) irange[1] = -1;
+  const float R = gmax - gmin;
+  range[0] = gmin;
+  range[1] = (R != 0.f) ? R : 1.f;
+  range[2] = gmax;
+  range[3] = (R != 0.f) ? 1.f : 0.f;
 }
 
 // thread: 8 consecutive k of one patch row (ix..ix+7), requires P % 8 == 0
@@ -412,7 +476,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
 #pragma unroll
   for (int i = 0; i < 9; ++i) m[i] = a.minv[n * 9 + i];
   // global range normalise: dL/dR = -sum g_a * a / R ; argmax gets +dR, argmin gets -(sum g_a + dR)
-  const float dR = (irange[1] >= 0) ? -sums[1] : 0.f;
+  const float dR = (range[3] != 0.f) ? -sums[1] : 0.f;
   const float dMin = -(sums[0] + dR);
   float g[3][4];
 #pragma unroll
@@ -464,6 +528,16 @@ void cutout_forward(const CutoutArgs& a, float* batch, float* part_min, float* p
                     int* part_imax, cudaStream_t st) {
   dim3 grid((a.cs * a.cs / 4 + CUT_THREADS - 1) / CUT_THREADS, a.n_local);
   cutout_fwd_kernel<<<grid, CUT_THREADS, 0, st>>>(a, batch, part_min, part_max, part_imin, part_imax);
+}
+
+void range_pack(const float* range, float* xbuf, cudaStream_t st) { range_pack_kernel<<<1, 1, 0, st>>>(range, xbuf); }
+void range_unpack(const float* xbuf, float* range, int* irange, cudaStream_t st) {
+  range_unpack_kernel<<<1, 1, 0, st>>>(xbuf, range, irange);
+}
+
+void minmax_partials(const float* x, long long n, int nparts, float* part_min, float* part_max, int* part_imin,
+                     int* part_imax, cudaStream_t st) {
+  minmax_partial_kernel<<<nparts, 256, 0, st>>>(x, n, part_min, part_max, part_imin, part_imax);
 }
 
 void minmax_reduce(const float*, const float* part_min, const float* part_max, const int* part_imin,

@@ -123,6 +123,33 @@ class B200Engine:
         self._check(rc, "pxr_set_prompts")
         self.n_prompts[clip_idx] = n
 
+    def init_comm(self):
+        """Cutout-sharded multi-GPU mode: rank 0 draws an ncclUniqueId, torch.distributed (already initialised by the
+        launcher) broadcasts it, and the engine builds its own communicator (pxr_set_comm)."""
+        import os
+
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        if "PXR_NCCL_LIB" not in os.environ:
+            try:
+                import nvidia.nccl
+                cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["PXR_NCCL_LIB"] = cand
+            except Exception:
+                pass
+        buf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            rc = self.lib.pxr_get_unique_id(buf)
+            if rc != 0:
+                raise EngineError(f"pxr_get_unique_id failed ({rc}): {self.lib.pxr_last_error(None).decode()}")
+        dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        self._check(self.lib.pxr_set_comm(self.h, raw, self.rank, self.world), "pxr_set_comm")
+
     def z_bounds(self):
         zc = self.z_shape[1]
         lo, hi = self._new(zc), self._new(zc)
@@ -170,9 +197,13 @@ class B200Engine:
         self.sync()
         return out
 
-    def encode_image(self, clip_idx=0):
+    def encode_image(self, clip_idx=0, batch=None):
+        """Unit-norm embeddings of the engine's current cutouts, or of `batch` [cutn_local,3,cs,cs] when given."""
         out = self._new(self.n_local, self.clip_dims[clip_idx])
-        self._check(self.lib.pxr_encode_image(self.h, clip_idx, None, self._p(out)), "pxr_encode_image")
+        if batch is not None:
+            batch = batch.to(self.device, torch.float32).contiguous()
+            torch.cuda.current_stream().synchronize()
+        self._check(self.lib.pxr_encode_image(self.h, clip_idx, self._p(batch), self._p(out)), "pxr_encode_image")
         self.sync()
         return out
 

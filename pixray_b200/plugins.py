@@ -1,0 +1,289 @@
+"""pixray's plugin surface on top of the B200 engine.
+
+Same class / method names, argument meaning and error behaviour as the reference, so a pixray loop written against
+`drawer.synth`, `MakeCutouts.__call__`, `perceptor.encode_image`, `Prompt.__call__`, `opt.step()` / `drawer.clip_z()`
+runs unchanged -- each method forwards to one C entry point (include/pixray_b200.h).  Like the reference's module
+globals (pixray.py:1022-1063) there is ONE session per process: the plugin objects share one `B200Engine`.
+
+Gradients do not flow through torch autograd here: the engine owns the hand-written backward chain, so
+`Session.backward()` replaces `sum(lossAll).backward()` (pixray.py:1481-1482) and writes `drawer.z.grad`.
+"""
+import math
+
+import numpy as np
+import torch
+from torch.nn import functional as F
+
+from . import cutouts as cut_sampler
+from . import engine as E
+
+
+class DrawingInterface:
+    """DrawingInterface.py:1-12 -- the declared part of the drawer contract."""
+
+    @staticmethod
+    def add_settings(parser):
+        return parser
+
+    def __init__(self, settings):
+        self.settings = settings
+
+    def load_model(self, settings, device):
+        pass
+
+
+class Session:
+    """The shared engine + the per-iteration state the reference keeps in globals (cur_iteration,
+    global_padding_mode, global_fill_color: pixray.py:1250-1258)."""
+
+    def __init__(self, eng: E.B200Engine):
+        self.engine = eng
+        self.cur_iteration = 0
+        self.global_padding_mode = "reflection"
+        self.global_fill_color = 0.0
+
+    def begin_iteration(self, cur_iteration, fill=None, rng=None):
+        self.cur_iteration = cur_iteration
+        self.global_padding_mode = "reflection" if cur_iteration % 2 == 0 else "border"  # pixray.py:1250-1253
+        self.global_fill_color = float((rng or np.random).random()) if fill is None else float(fill)  # 1255-1258
+
+    def backward(self, drawer):
+        """loss.backward(): z.grad += d(sum of prompt losses)/dz (pixray.py:1481-1482)."""
+        g = self.engine.backward()
+        z = drawer.get_z()
+        z.grad = g if z.grad is None else z.grad + g
+        return g
+
+
+class VqganDrawer(DrawingInterface):
+    """vqgan.py:81-218 (synth 190-195, clip_z 202-204, get_z/set_z/get_z_copy 206-216)."""
+
+    @staticmethod
+    def add_settings(parser):
+        parser.add_argument("--vqgan_model", type=str, help="VQGAN model", default="imagenet_f16_16384", dest="vqgan_model")
+        return parser
+
+    def __init__(self, settings, session: Session):
+        super().__init__(settings)
+        self.session = session
+        self.z = None
+
+    def load_model(self, settings, device):
+        self.device = device
+        lo, hi = self.session.engine.z_bounds()
+        self.z_min, self.z_max = lo[None, :, None, None], hi[None, :, None, None]  # vqgan.py:141-142
+
+    def get_opts(self, decay_divisor):
+        return None  # engine builds Adam on get_z(), like pixray.py:537-539
+
+    def get_num_resolutions(self):
+        return self.session.engine.cfg.n_levels
+
+    def init_from_tensor(self, init_tensor):
+        raise NotImplementedError("the VQGAN encoder is init-time only and out of the hot-path scope (SURVEY.md 8f-3); "
+                                  "use set_z() with a latent")
+
+    def synth(self, cur_iteration):
+        return self.session.engine.synth(self.z)
+
+    def clip_z(self):
+        with torch.no_grad():
+            self.z.copy_(self.z.maximum(self.z_min).minimum(self.z_max))
+
+    def get_z(self):
+        return self.z
+
+    def set_z(self, new_z):
+        if self.z is None:
+            self.z = new_z.detach().to(self.session.engine.device, torch.float32).clone()
+            return self.z
+        with torch.no_grad():
+            return self.z.copy_(new_z)
+
+    def get_z_copy(self):
+        return self.z.clone()
+
+
+class FastPixelDrawer(DrawingInterface):
+    """fast_pixeldrawer.py:24-110: z = colour grid, synth = nearest upsample + clamp_with_grad."""
+
+    @staticmethod
+    def add_settings(parser):
+        parser.add_argument("--pixel_size", nargs=2, type=int, help="Pixel size (width height)", default=None, dest="pixel_size")
+        parser.add_argument("--pixel_scale", type=float, help="Pixel scale", default=None, dest="pixel_scale")
+        return parser
+
+    def __init__(self, settings, session: Session):
+        super().__init__(settings)
+        self.session = session
+        self.pixel_size = (session.engine.z_shape[2], session.engine.z_shape[3])
+        self.output_size = session.engine.image_hw
+        self.z = None
+
+    def get_opts(self, decay_divisor):
+        return None
+
+    def get_num_resolutions(self):
+        return None
+
+    def get_z_from_tensor(self, ref_tensor):
+        return F.interpolate((ref_tensor + 1) / 2, size=self.pixel_size, mode="bilinear", align_corners=False)
+
+    def init_from_tensor(self, init_tensor):
+        self.z = self.get_z_from_tensor(init_tensor).to(self.session.engine.device, torch.float32).contiguous()
+
+    def synth(self, cur_iteration):
+        return self.session.engine.synth(self.z)
+
+    def clip_z(self):
+        with torch.no_grad():
+            self.z.copy_(self.z.clip(0, 1))
+
+    def get_z(self):
+        return self.z
+
+    def set_z(self, new_z):
+        with torch.no_grad():
+            return self.z.copy_(new_z)
+
+    def get_z_copy(self):
+        return self.z.clone()
+
+
+class MakeCutouts:
+    """pixray.py:399-511.  `transforms` is the per-iteration cache of composed 3x3s (pixray.py:498); when it is None
+    a fresh set is sampled (the distributions of the reference's augmentation stacks, pixray_b200/cutouts.py)."""
+
+    def __init__(self, cut_size, cutn, session: Session, cut_pow=1.0, seed=0):
+        self.cut_size, self.cutn, self.cut_pow = cut_size, cutn, cut_pow
+        self.cutn_zoom = int(0.6 * cutn)
+        self.noise_fac = 0.1
+        self.transforms = None
+        self.session = session
+        self._rng = np.random.default_rng(seed)
+
+    def __call__(self, input, spot=None):
+        return self.forward(input, spot)
+
+    def forward(self, input, spot=None):
+        if spot is not None:
+            raise NotImplementedError("spot prompts are off by default and out of scope (SURVEY.md 8f-2)")
+        s = self.session
+        if self.transforms is None:
+            self.transforms = torch.from_numpy(
+                cut_sampler.sample_transforms(self.cutn, self.cut_size, int(self._rng.integers(1 << 31))))
+        pad = E.PAD_REFLECTION if s.global_padding_mode == "reflection" else E.PAD_BORDER
+        facs = noise = None
+        if self.noise_fac:
+            facs = (self._rng.random(self.cutn) * self.noise_fac).astype(np.float32)        # pixray.py:509
+            noise = torch.randn(self.cutn, 3, self.cut_size, self.cut_size, device=s.engine.device)  # pixray.py:510
+        return s.engine.make_cutouts(input, transforms=self.transforms.numpy(), zoom_padding=pad,
+                                     fill=s.global_fill_color, noise_facs=facs, noise=noise, it=s.cur_iteration)
+
+
+class Perceptor:
+    """CLIP_Base surface (slip.py:44-74): input_resolution, output_dim, encode_image -> unit-norm [N, D]."""
+
+    def __init__(self, session: Session, clip_idx=0):
+        self.session, self.clip_idx = session, clip_idx
+        self.device = session.engine.device
+        c = session.engine.cfg.clip[clip_idx]
+        self.input_resolution, self.output_dim = c.image_res, c.out_dim
+
+    def encode_image(self, imgs, input_range=None, apply_preprocess=True):
+        if input_range is not None or not apply_preprocess:
+            raise NotImplementedError("only the default preprocess path of the hot loop is implemented (pixray.py:1295)")
+        return self.session.engine.encode_image(self.clip_idx, imgs)
+
+    def encode_text(self, text):
+        raise NotImplementedError("text towers are init-time (SURVEY.md row 10); pass prompt embeddings")
+
+
+class Prompt:
+    """pixray.py:268-280.  Instances register themselves with the engine so the loss and its gradient stay on device."""
+
+    def __init__(self, embed, weight=1.0, stop=float("-inf")):
+        self.embed = torch.as_tensor(embed, dtype=torch.float32).reshape(-1, torch.as_tensor(embed).shape[-1])
+        self.weight = torch.as_tensor(float(weight))
+        self.stop = torch.as_tensor(float(stop))
+        self._session, self._clip_idx, self._index = None, 0, 0
+
+    @staticmethod
+    def register(session: Session, clip_idx, prompts):
+        """pmsTable[clip_model] = [Prompt, ...] (pixray.py:859-915)."""
+        if any(p.embed.shape[0] != 1 for p in prompts):
+            raise ValueError("one embedding row per Prompt (multi-row image prompts are out of scope, SURVEY.md 8f-2)")
+        session.engine.set_prompts(clip_idx, torch.cat([p.embed for p in prompts]).numpy(),
+                                   [float(p.weight) for p in prompts], [float(p.stop) for p in prompts])
+        for i, p in enumerate(prompts):
+            p._session, p._clip_idx, p._index = session, clip_idx, i
+
+    def __call__(self, input):
+        return self.forward(input)
+
+    def forward(self, input):
+        if self._session is None:
+            raise RuntimeError("Prompt.register(session, clip_idx, prompts) must be called first")
+        return self._session.engine.prompt_loss(self._clip_idx, input)[self._index]
+
+
+def parse_prompt(prompt):
+    """pixray.py:290-321: text, text:weight or text:weight:stop."""
+    def is_number(s):
+        try:
+            float(s)
+            return True
+        except ValueError:
+            return False
+
+    text, weight, stop = prompt, 1, float("-inf")
+    extra = []
+    keep = True
+    while len(extra) < 2 and keep:
+        vals = text.rsplit(":", 1)
+        if len(vals) > 1 and is_number(vals[1]):
+            extra.append(float(vals[1]))
+            text = vals[0]
+        else:
+            keep = False
+    if len(extra) == 1:
+        weight = extra[0]
+    elif len(extra) == 2:
+        weight, stop = extra[1], extra[0]
+    return text, weight, stop
+
+
+from .util import get_learning_rate_drops  # noqa: E402,F401  (pixray.py:1999-2003)
+
+
+class Optimizer:
+    """optim.Adam([drawer.get_z()], lr) as rebuild_optimisers builds it (pixray.py:520-555): zero_grad / step."""
+
+    def __init__(self, session: Session, drawer, lr):
+        self.session, self.drawer, self.lr = session, drawer, lr
+        session.engine.reset_optimizer()
+
+    def zero_grad(self):
+        z = self.drawer.get_z()
+        z.grad = None
+
+    def step(self):
+        self.session.engine.step(self.drawer.get_z(), self.lr, self.session.cur_iteration)
+
+
+def train_iteration(session: Session, drawer, make_cutouts, perceptors, prompt_table, opt):
+    """The body of train()/ascend_txt for the default settings (pixray.py:1243-1406, 1436-1512), expressed with the
+    plugin objects exactly like the reference does.  Returns the list of scalar losses."""
+    opt.zero_grad()
+    out = drawer.synth(session.cur_iteration)
+    cutouts = make_cutouts(out)
+    result = []
+    for i, perceptor in enumerate(perceptors):
+        iii = perceptor.encode_image(cutouts).float()
+        for prompt in prompt_table[i]:
+            result.append(prompt(iii))
+    make_cutouts.transforms = None  # clear the per-iteration cache (pixray.py:1339-1342)
+    session.backward(drawer)
+    opt.step()
+    drawer.clip_z()
+    return result

@@ -169,10 +169,14 @@ def test_adam_clip_and_iterate_small():
     losses = np.zeros(2, dtype=np.float32)
     for it in range(3):
         pad = "reflection" if it % 2 == 0 else "border"
+        g = torch.Generator().manual_seed(100 + it)
+        facs = torch.rand(cutn, generator=g) * 0.1
+        noise = torch.randn(cutn, 3, cs, cs, generator=g)  # continuous noise keeps the global min / max unique
         r = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z_ref, [clip], [prompts], torch.from_numpy(T), cs, pad, 0.5,
-                      None, None)
+                      facs, noise)
         z_eng = z_ref.clone().cuda()
-        eng.iterate(z_eng, lr, it, params=dict(transforms=T, zoom_padding=it % 2, fill=0.5), losses_out=losses)
+        eng.iterate(z_eng, lr, it, params=dict(transforms=T, zoom_padding=it % 2, fill=0.5, noise_facs=facs.numpy(),
+                                               noise=noise), losses_out=losses)
         g_eng = eng.debug_read("z_grad", z.shape).cpu()
         ref_l = np.array([float(l) for l in r["losses"]], dtype=np.float32)
         print(f"[parity] iter {it}: losses engine {losses} oracle {ref_l}")
