@@ -143,6 +143,7 @@ typedef struct {
   long long ldc, c_bs0, c_bs1;
   void* stream;
   int repeat;
+  int n_store; /* fused-softmax epilogues (act 3 / 4): zero-fill columns [N, n_store) */
 } pxr_test_gemm_desc;
 
 int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen);

@@ -81,6 +81,7 @@ class Engine {
     // buffers
     act_t *patches, *g_patches, *h16, *o16, *gact, *g4, *gh, *go, *gqkv, *dP, *gx16;
     float *t, *x_out, *stats_pre, *stats_post, *e, *e_unit, *de, *gx;
+    act_t *proj16, *hcls, *gcls, *de16;
     // prompts
     float *prompts = nullptr, *pweights = nullptr, *pstops = nullptr, *losses = nullptr;
     int n_prompts = 0, loss_offset = 0;
@@ -472,14 +473,19 @@ Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
     e.ldc = 3 * c;
     add_gemm(drawer_fwd, opK(a.p, c, T, c), opK(wqkv, c, 3 * c, c), T, 3 * c, c, e);
   }
+  const bool fuse_sm = T <= 256;  // whole row in one accumulator tile -> softmax lives in the GEMM epilogue
   {
     GemmEpilogue e;
     e.alpha = alpha;
     e.out_f16 = P;
     e.ldc = ldT;
-    add_gemm(drawer_fwd, opK(qkv, 3 * c, T, c), opK(qkv + c, 3 * c, T, c), T, T, c, e);
+    if (fuse_sm) {
+      e.act = ACT_SOFTMAX;
+      e.n_store = ldT;
+    }
+    add_gemm(drawer_fwd, opK(qkv, 3 * c, T, c), opK(qkv + c, 3 * c, T, c), T, T, c, e, fuse_sm ? round_up(T, 16) : 0);
   }
-  drawer_fwd.add(1, [=] { softmax_forward(P, T, T, ldT, cs); });
+  if (!fuse_sm) drawer_fwd.add(1, [=] { softmax_forward(P, T, T, ldT, cs); });
   {
     GemmEpilogue e;
     e.out_f16 = O.p;
@@ -502,23 +508,30 @@ Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
     e.ldc = c;
     add_conv(b, out.g, x.H, x.W, po.cout_k, po.wd, po.cin_rows, c, 1, e);
   }
-  {  // dP = dO v^T
+  {  // dP = dO v^T ; dS = alpha * P * (dP - <P, dP>) fused in the epilogue when the row fits one tile
     GemmEpilogue e;
     e.out_f16 = dP;
     e.ldc = ldT;
-    add_gemm(b, opK(O.g, c, T, c), opK(qkv + 2 * c, 3 * c, T, c), T, T, c, e);
+    if (fuse_sm) {
+      e.act = ACT_SOFTMAX_BWD;
+      e.aux_in = P;
+      e.alpha = alpha;
+      e.n_store = ldT;
+    }
+    add_gemm(b, opK(O.g, c, T, c), opK(qkv + 2 * c, 3 * c, T, c), T, T, c, e, fuse_sm ? round_up(T, 16) : 0);
   }
-  b.add(1, [=] { softmax_backward(P, dP, T, T, ldT, cs); });
+  if (!fuse_sm) b.add(1, [=] { softmax_backward(P, dP, T, T, ldT, cs); });
+  const float alpha_b = fuse_sm ? 1.f : alpha;  // fused path already carries alpha in dS
   {  // dq = alpha dS k
     GemmEpilogue e;
-    e.alpha = alpha;
+    e.alpha = alpha_b;
     e.out_f16 = gqkv;
     e.ldc = 3 * c;
     add_gemm(b, opK(dP, ldT, T, ldT), opMN(qkv + c, 3 * c, c, T), T, c, T, e);
   }
   {  // dk = alpha dS^T q
     GemmEpilogue e;
-    e.alpha = alpha;
+    e.alpha = alpha_b;
     e.out_f16 = gqkv + c;
     e.ldc = 3 * c;
     add_gemm(b, opMN(dP, ldT, T, T), opMN(qkv, 3 * c, c, T), T, c, T, e);
@@ -810,6 +823,7 @@ void Engine::build_clip(int i) {
   C.cls = upload(W(mod, "visual.class_embedding", {Wd}).data);
   C.pos = upload(W(mod, "visual.positional_embedding", {T, Wd}).data);
   C.proj = upload(W(mod, "visual.proj", {Wd, D}).data);
+  C.proj16 = upload_f16(W(mod, "visual.proj", {Wd, D}).data);
   C.ln_pre = load_norm(mod, "visual.ln_pre", Wd);
   C.ln_post = load_norm(mod, "visual.ln_post", Wd);
   // ---- buffers
@@ -839,11 +853,15 @@ void Engine::build_clip(int i) {
   C.e = dalloc<float>((size_t)B * D);
   C.e_unit = dalloc<float>((size_t)B * D);
   C.de = dalloc<float>((size_t)B * D);
+  C.de16 = dalloc<act_t>((size_t)B * D);
+  C.hcls = dalloc<act_t>((size_t)B * Wd);
+  C.gcls = dalloc<act_t>((size_t)B * Wd);
   float* x_cur = dalloc<float>((size_t)M * Wd);
   float* x0 = x_cur;
   C.layers.resize(L);
   const float scale = 1.f / std::sqrt((float)d);
-  const int bnS = pick_bn(T, false, 1000);
+  const bool fuse_sm = T <= 256;  // attention row fits one accumulator tile: softmax fused into the GEMM epilogue
+  const int bnS = fuse_sm ? round_up(T, 16) : pick_bn(T, false, 1000);
 
   // ---- forward: patch embed (conv1 as GEMM over im2col'd patches, written straight into the token rows 1..np)
   {
@@ -856,7 +874,7 @@ void Engine::build_clip(int i) {
   {
     Clip* c = &C;
     float* xo = x0;
-    C.fwd.add(1, [=] { layernorm_forward(c->t, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, nullptr, xo, c->stats_pre, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(c->t, Wd, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, nullptr, xo, c->stats_pre, cs); });
   }
   for (int l = 0; l < L; ++l) {
     Clip::Layer& Ly = C.layers[l];
@@ -881,7 +899,7 @@ void Engine::build_clip(int i) {
     Ly.u = dalloc<act_t>((size_t)M * 4 * Wd);
     Clip::Layer ly = Ly;
     Clip* c = &C;
-    C.fwd.add(1, [=] { layernorm_forward(ly.x_in, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(ly.x_in, Wd, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); });
     {
       GemmEpilogue e;
       e.bias = ly.bqkv;
@@ -899,10 +917,14 @@ void Engine::build_clip(int i) {
       e.ldc = ldT;
       e.bs0 = ps0;
       e.bs1 = ps1;
+      if (fuse_sm) {
+        e.act = ACT_SOFTMAX;
+        e.n_store = ldT;
+      }
       add_gemm(C.fwd, opK(ly.qkv, 3 * Wd, T, d, Hh, qs0, B, qs1), opK(ly.qkv + Wd, 3 * Wd, T, d, Hh, qs0, B, qs1), T, T,
                d, e, bnS);
     }
-    C.fwd.add(1, [=] { softmax_forward(ly.P, B * Hh * T, T, ldT, cs); });
+    if (!fuse_sm) C.fwd.add(1, [=] { softmax_forward(ly.P, B * Hh * T, T, ldT, cs); });
     {  // O = P v
       GemmEpilogue e;
       e.out_f16 = C.o16;
@@ -920,7 +942,7 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.fwd, opK(C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
     }
-    C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, Wd, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); });
     {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u
       GemmEpilogue e;
       e.bias = ly.bfc;
@@ -941,15 +963,28 @@ void Engine::build_clip(int i) {
     x_cur = x_next;
   }
   C.x_out = x_cur;
-  {
+  {  // head: ln_post on the class-token rows (row stride T*W), then e = ln @ proj as a GEMM (proj [W, D] is MN-major)
     Clip* c = &C;
-    C.fwd.add(1, [=] { clip_head_forward(c->x_out, T, Wd, D, c->ln_post.gamma, c->ln_post.beta, c->proj, B, 1e-5f, c->stats_post, c->e, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(c->x_out, (long long)T * Wd, nullptr, T, c->ln_post.gamma, c->ln_post.beta, B, Wd, 1e-5f, c->hcls, nullptr, c->stats_post, cs); });
+    GemmEpilogue e;
+    e.out_f32 = C.e;
+    e.ldc = D;
+    add_gemm(C.fwd, opK(C.hcls, Wd, B, Wd), opMN(C.proj16, D, D, Wd), B, D, Wd, e);
   }
 
   // ---- backward (execution order).  Weight operands of the dgrad GEMMs are MN-major views of the forward weights.
-  {
+  {  // head backward: gcls = de proj^T (proj [W, D] read K-major: n = W rows, k = D), then LN backward on class rows
     Clip* c = &C;
-    C.bwd.add(3, [=] { clip_head_backward(c->de, c->x_out, T, Wd, D, c->stats_post, c->ln_post.gamma, c->proj, B, c->gx, c->gx16, cs); });
+    GemmEpilogue e;
+    e.out_f16 = C.gcls;
+    e.ldc = Wd;
+    add_gemm(C.bwd, opK(C.de16, D, B, D), opK(C.proj16, D, Wd, D), B, Wd, D, e);
+    const size_t nbytes32 = (size_t)M * Wd * sizeof(float), nbytes16 = (size_t)M * Wd * sizeof(act_t);
+    C.bwd.add(1, [=] {
+      cudaMemsetAsync(c->gx, 0, nbytes32, cs);
+      cudaMemsetAsync(c->gx16, 0, nbytes16, cs);
+      layernorm_backward(c->gcls, c->x_out, (long long)T * Wd, nullptr, T, c->stats_post, c->ln_post.gamma, B, Wd, 0, c->gx, c->gx16, cs);
+    });
   }
   for (int l = L - 1; l >= 0; --l) {
     Clip::Layer ly = C.layers[l];
@@ -970,26 +1005,33 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.g4, 4 * Wd, M, 4 * Wd), opMN(ly.wfc, Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
     }
-    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_mid, nullptr, T, ly.stats2, ly.ln2.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
+    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_mid, Wd, nullptr, T, ly.stats2, ly.ln2.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
     {  // go = gx Wo
       GemmEpilogue e;
       e.out_f16 = C.go;
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.gx16, Wd, M, Wd), opMN(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
     }
-    {  // dP = go v^T
+    {  // dP = go v^T ; fused: dS = scale * P * (dP - <P, dP>)
       GemmEpilogue e;
       e.out_f16 = C.dP;
       e.ldc = ldT;
       e.bs0 = ps0;
       e.bs1 = ps1;
+      if (fuse_sm) {
+        e.act = ACT_SOFTMAX_BWD;
+        e.aux_in = ly.P;
+        e.alpha = scale;
+        e.n_store = ldT;
+      }
       add_gemm(C.bwd, opK(C.go, Wd, T, d, Hh, os0, B, os1), opK(ly.qkv + 2 * Wd, 3 * Wd, T, d, Hh, qs0, B, qs1), T, T, d,
                e, bnS);
     }
-    C.bwd.add(1, [=] { softmax_backward(ly.P, c->dP, B * Hh * T, T, ldT, cs); });
+    if (!fuse_sm) C.bwd.add(1, [=] { softmax_backward(ly.P, c->dP, B * Hh * T, T, ldT, cs); });
+    const float scale_b = fuse_sm ? 1.f : scale;
     {  // dq = scale dS k
       GemmEpilogue e;
-      e.alpha = scale;
+      e.alpha = scale_b;
       e.out_f16 = C.gqkv;
       e.ldc = 3 * Wd;
       e.bs0 = qs0;
@@ -999,7 +1041,7 @@ void Engine::build_clip(int i) {
     }
     {  // dk = scale dS^T q
       GemmEpilogue e;
-      e.alpha = scale;
+      e.alpha = scale_b;
       e.out_f16 = C.gqkv + Wd;
       e.ldc = 3 * Wd;
       e.bs0 = qs0;
@@ -1020,11 +1062,11 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.gqkv, 3 * Wd, M, 3 * Wd), opMN(ly.wqkv, Wd, Wd, 3 * Wd), M, Wd, 3 * Wd, e);
     }
-    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_in, nullptr, T, ly.stats1, ly.ln1.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
+    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_in, Wd, nullptr, T, ly.stats1, ly.ln1.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
   }
   {  // ln_pre backward (x = t + pos), then patch-embed dgrad on token rows 1..np of every image
     Clip* c = &C;
-    C.bwd.add(1, [=] { layernorm_backward(c->gx16, c->t, c->pos, T, c->stats_pre, c->ln_pre.gamma, M, Wd, 0, c->gx, c->gx16, cs); });
+    C.bwd.add(1, [=] { layernorm_backward(c->gx16, c->t, Wd, c->pos, T, c->stats_pre, c->ln_pre.gamma, M, Wd, 0, c->gx, c->gx16, cs); });
     GemmEpilogue e;
     e.out_f16 = C.g_patches;
     e.ldc = Kp;
@@ -1045,7 +1087,7 @@ void Engine::loss_clip(int i) {
   Clip& C = clip[i];
   if (C.n_prompts == 0) throw EngineError(-70, "no prompts set for perceptor " + std::to_string(i));
   prompt_loss(C.e, C.B, C.c.out_dim, C.prompts, C.pweights, C.pstops, C.n_prompts, cfg.cutn, S, C.e_unit,
-              losses_dev + C.loss_offset, C.de, st);
+              losses_dev + C.loss_offset, C.de, C.de16, st);
   launches += 1;
 }
 

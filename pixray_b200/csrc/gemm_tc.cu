@@ -36,96 +36,167 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-__device__ __forceinline__ float quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float quickgelu(float x) { return x * fast_sigmoid(1.702f * x); }
 __device__ __forceinline__ float quickgelu_grad(float u) {
-  float s = 1.f / (1.f + __expf(-1.702f * u));
+  float s = fast_sigmoid(1.702f * u);
   return s * (1.f + 1.702f * u * (1.f - s));
 }
 
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], long long row_off,
-                                               int row, int col0, bool full_vec) {
-  float x[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
-  if (p.bias) {
-    if (p.bias_per_row) {
-      float b = p.bias[row];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] += b;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < p.N) x[j] += p.bias[col0 + j];
-    }
+constexpr int TB_LD = 33;                       // transposer row pitch (floats): conflict-free both ways
+constexpr int TB_FLOATS = 32 * TB_LD;           // one 32 x 32 block per epilogue warp
+constexpr int GEMM_EPI_WARPS = 8;
+
+// Row <-> column layout exchange through the warp-private smem block.
+//   row layout : thread = accumulator row (TMEM lane), registers = columns     (what tcgen05.ld delivers)
+//   col layout : thread = column, loop over rows                               (what coalesced global access wants)
+struct RowInfo {
+  long long off;  // element offset of this thread's row in the output tensors
+  int row;        // logical row index (bias_per_row)
+  int valid;
+};
+
+__device__ __forceinline__ RowInfo row_info(const GemmParams& p, const TileCoord& t, int r_tile) {
+  RowInfo ri;
+  if (p.a_mode == OP_CONV) {
+    const int h = t.h0 + r_tile / p.tile_w, w = t.w0 + r_tile % p.tile_w;
+    ri.valid = (h < p.conv_H) && (w < p.conv_W);
+    ri.row = h * p.conv_W + w;
+    ri.off = (static_cast<long long>(t.z) * p.conv_H * p.conv_W + ri.row) * p.ldc;
+  } else {
+    ri.row = t.m0 + r_tile;
+    ri.valid = ri.row < p.M;
+    ri.off = t.b0 * p.out_bs0 + t.b1 * p.out_bs1 + static_cast<long long>(ri.row) * p.ldc;
   }
-  const long long off = row_off + col0;
-  if (full_vec) {
-    if (p.act == ACT_QUICKGELU) {
-      if (p.aux_out) {
-        __align__(16) __half h[16];
+  return ri;
+}
+
+// Load `width` (16 or 32) accumulator columns of this thread's row, starting at TMEM column `tcol`.
+__device__ __forceinline__ void load_acc(uint32_t taddr, int width, float (&v)[32]) {
+  uint32_t u[16];
+  tmem_ld_x16(taddr, u);
+  tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(x[j]);
-        uint4* dst = reinterpret_cast<uint4*>(p.aux_out + off);
-        dst[0] = reinterpret_cast<const uint4*>(h)[0];
-        dst[1] = reinterpret_cast<const uint4*>(h)[1];
-      }
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+  if (width > 16) {
+    tmem_ld_x16(taddr + 16, u);
+    tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = quickgelu(x[j]);
-    } else if (p.act == ACT_QUICKGELU_BWD) {
-      __align__(16) __half h[16];
-      const uint4* src = reinterpret_cast<const uint4*>(p.aux_in + off);
-      reinterpret_cast<uint4*>(h)[0] = src[0];
-      reinterpret_cast<uint4*>(h)[1] = src[1];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] *= quickgelu_grad(__half2float(h[j]));
-    }
-    if (p.res_f32) {
-      const float4* src = reinterpret_cast<const float4*>(p.res_f32 + off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 r = src[j];
-        x[4 * j + 0] += r.x;
-        x[4 * j + 1] += r.y;
-        x[4 * j + 2] += r.z;
-        x[4 * j + 3] += r.w;
-      }
-    }
-    if (p.res_f16) {
-      __align__(16) __half h[16];
-      const uint4* src = reinterpret_cast<const uint4*>(p.res_f16 + off);
-      reinterpret_cast<uint4*>(h)[0] = src[0];
-      reinterpret_cast<uint4*>(h)[1] = src[1];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] += __half2float(h[j]);
-    }
-    if (p.out_f32) {
-      float4* dst = reinterpret_cast<float4*>(p.out_f32 + off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-    }
-    if (p.out_f16) {
-      __align__(16) __half h[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(x[j]);
-      uint4* dst = reinterpret_cast<uint4*>(p.out_f16 + off);
-      dst[0] = reinterpret_cast<const uint4*>(h)[0];
-      dst[1] = reinterpret_cast<const uint4*>(h)[1];
-    }
+    for (int j = 0; j < 16; ++j) v[16 + j] = __uint_as_float(u[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (col0 + j >= p.N) continue;
-      float y = x[j];
-      if (p.act == ACT_QUICKGELU) {
-        if (p.aux_out) p.aux_out[off + j] = __float2half_rn(y);
-        y = quickgelu(y);
-      } else if (p.act == ACT_QUICKGELU_BWD) {
-        y *= quickgelu_grad(__half2float(p.aux_in[off + j]));
+    for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
+  }
+}
+
+// rows -> smem (row layout write), then the warp walks the 32 rows with lane = column
+__device__ __forceinline__ void to_col_layout(float* tb, const float (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tb[lane * TB_LD + j] = v[j];
+  __syncwarp();
+}
+
+// generic (non-softmax) epilogue for one 32-column slab, executed in column layout: coalesced global accesses
+__device__ __forceinline__ void epilogue_slab(const GemmParams& p, float* tb, const RowInfo& ri, int lane, int col,
+                                              bool col_ok) {
+  const float bias_c = (p.bias && !p.bias_per_row && col_ok) ? p.bias[col] : 0.f;
+  for (int r = 0; r < 32; ++r) {
+    const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
+    const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
+    const int row_r = __shfl_sync(0xffffffffu, ri.row, r);
+    if (!valid_r || !col_ok) continue;
+    const long long o = off_r + col;
+    float x = tb[r * TB_LD + lane] * p.alpha + bias_c;
+    if (p.bias && p.bias_per_row) x += p.bias[row_r];
+    if (p.act == ACT_QUICKGELU) {
+      if (p.aux_out) p.aux_out[o] = __float2half_rn(x);
+      x = quickgelu(x);
+    } else if (p.act == ACT_QUICKGELU_BWD) {
+      x *= quickgelu_grad(__half2float(p.aux_in[o]));
+    }
+    if (p.res_f32) x += p.res_f32[o];
+    if (p.res_f16) x += __half2float(p.res_f16[o]);
+    if (p.out_f32) p.out_f32[o] = x;
+    if (p.out_f16) p.out_f16[o] = __float2half_rn(x);
+  }
+  __syncwarp();
+}
+
+// Fused row softmax (attention probabilities straight out of the QK^T accumulator, nn.MultiheadAttention /
+// taming AttnBlock): requires the whole row in one tile (tiles_n == 1).  Thread = row.  Columns [N, n_store) are
+// written as zeros so the result can be consumed as a K-major operand with a padded row pitch.
+__device__ __forceinline__ void epilogue_softmax_fwd(const GemmParams& p, float* tb, const RowInfo& ri, uint32_t taddr,
+                                                     int lane) {
+  const int nslab = (p.block_n + 31) / 32;
+  float v[32];
+  float mx = -3.0e38f;
+  for (int s = 0; s < nslab; ++s) {
+    const int width = min(32, p.block_n - s * 32);
+    load_acc(taddr + s * 32, width, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (s * 32 + j < p.N) mx = fmaxf(mx, v[j] * p.alpha);
+  }
+  float sum = 0.f;
+  for (int s = 0; s < nslab; ++s) {
+    const int width = min(32, p.block_n - s * 32);
+    load_acc(taddr + s * 32, width, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (s * 32 + j < p.N) sum += __expf(v[j] * p.alpha - mx);
+  }
+  const float inv = __fdividef(1.f, sum);
+  for (int s = 0; s < nslab; ++s) {
+    const int width = min(32, p.block_n - s * 32);
+    load_acc(taddr + s * 32, width, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (s * 32 + j < p.N) ? __expf(v[j] * p.alpha - mx) * inv : 0.f;
+    to_col_layout(tb, v, lane);
+    const int col = s * 32 + lane;
+    for (int r = 0; r < 32; ++r) {
+      const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
+      const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
+      if (valid_r && col < p.n_store) p.out_f16[off_r + col] = __float2half_rn(tb[r * TB_LD + lane]);
+    }
+    __syncwarp();
+  }
+}
+
+// Fused softmax backward: accumulator = dP row, aux_in = P (fp16, same indexing as the output);
+// dS = alpha * P * (dP - sum_j P_j dP_j).
+__device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float* tb, const RowInfo& ri, uint32_t taddr,
+                                                     int lane) {
+  const int nslab = (p.block_n + 31) / 32;
+  float v[32];
+  float dot = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int s = 0; s < nslab; ++s) {
+      const int width = min(32, p.block_n - s * 32);
+      const int col = s * 32 + lane;
+      // P block: coalesced load (col layout) -> smem -> row layout
+      for (int r = 0; r < 32; ++r) {
+        const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
+        const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
+        tb[r * TB_LD + lane] = (valid_r && col < p.N) ? __half2float(p.aux_in[off_r + col]) : 0.f;
       }
-      if (p.res_f32) y += p.res_f32[off + j];
-      if (p.res_f16) y += __half2float(p.res_f16[off + j]);
-      if (p.out_f32) p.out_f32[off + j] = y;
-      if (p.out_f16) p.out_f16[off + j] = __float2half_rn(y);
+      __syncwarp();
+      load_acc(taddr + s * 32, width, v);
+      if (pass == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dot += tb[lane * TB_LD + j] * v[j];
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = p.alpha * tb[lane * TB_LD + j] * (v[j] - dot);
+        __syncwarp();
+        to_col_layout(tb, v, lane);
+        for (int r = 0; r < 32; ++r) {
+          const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
+          const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
+          if (valid_r && col < p.n_store) p.out_f16[off_r + col] = __float2half_rn(tb[r * TB_LD + lane]);
+        }
+        __syncwarp();
+      }
     }
   }
 }
@@ -144,6 +215,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint64_t* tmem_full_bar = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* tbuf_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tma_a);
@@ -154,7 +226,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);
+      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -246,8 +318,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (TMEM -> regs -> global)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
+    const int ew = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = ew >> 2;         // two warps share a quarter and split the 32-column slabs
+    float* tb = tbuf_base + ew * TB_FLOATS;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile);
@@ -255,27 +330,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      const int r = q * 32 + lane;
-      bool valid;
-      long long row_off;
-      int row;
-      if (p.a_mode == OP_CONV) {
-        const int h = t.h0 + r / p.tile_w, w = t.w0 + r % p.tile_w;
-        valid = (h < p.conv_H) && (w < p.conv_W);
-        row = h * p.conv_W + w;
-        row_off = (static_cast<long long>(t.z) * p.conv_H * p.conv_W + row) * p.ldc;
-      } else {
-        row = t.m0 + r;
-        valid = row < p.M;
-        row_off = t.b0 * p.out_bs0 + t.b1 * p.out_bs1 + static_cast<long long>(row) * p.ldc;
-      }
+      const RowInfo ri = row_info(p, t, q * 32 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr + c, v);
-        tmem_ld_wait();
-        const int col0 = t.n0 + c;
-        if (valid && col0 < p.N) epilogue_chunk(p, v, row_off, row, col0, p.vec_ok && (col0 + 16 <= p.N));
+      if (p.act == ACT_SOFTMAX) {
+        if (half == 0) epilogue_softmax_fwd(p, tb, ri, taddr, lane);
+      } else if (p.act == ACT_SOFTMAX_BWD) {
+        if (half == 0) epilogue_softmax_bwd(p, tb, ri, taddr, lane);
+      } else {
+        const int nslab = (p.block_n + 31) / 32;
+        for (int s = half; s < nslab; s += 2) {
+          const int width = min(32, p.block_n - s * 32);
+          float v[32];
+          load_acc(taddr + s * 32, width, v);
+          to_col_layout(tb, v, lane);
+          const int col = t.n0 + s * 32 + lane;
+          epilogue_slab(p, tb, ri, lane, col, (s * 32 + lane < p.block_n) && (col < p.N));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -391,7 +461,7 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
   }
   p.block_n = block_n;
   const int stage_bytes = A_TILE_BYTES + block_n * GEMM_BLOCK_K * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (188 * 1024) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -399,6 +469,11 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
   while (cols < 2 * block_n) cols <<= 1;
   p.tmem_cols = cols;
   p.alpha = epi.alpha;
+  p.n_store = epi.n_store > 0 ? epi.n_store : p.N;
+  if ((epi.act == ACT_SOFTMAX || epi.act == ACT_SOFTMAX_BWD) && (p.tiles_n != 1 || !epi.out_f16)) {
+    set_err(err, errlen, "fused softmax epilogue needs the whole row in one tile and an fp16 output");
+    return -12;
+  }
   p.bias = epi.bias;
   p.bias_per_row = epi.bias_per_row;
   p.act = epi.act;
@@ -415,7 +490,7 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
              aligned16(epi.aux_out) && aligned16(epi.res_f32) && aligned16(epi.res_f16) && aligned16(epi.out_f32) &&
              aligned16(epi.out_f16);
   plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  plan->smem_bytes = stages * stage_bytes + 1024 + 256;
+  plan->smem_bytes = stages * stage_bytes + 1024 + 256 + GEMM_EPI_WARPS * TB_FLOATS * 4;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -9,7 +9,8 @@
 //   * 3x3 / 1x1 convolutions of the VQGAN decoder as implicit GEMM: the A operand is fetched by a 4-D TMA
 //     box (C, W, H, B) shifted per filter tap, out-of-image halo zero-filled by TMA.
 //
-// Structure: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue.  smem ring of
+// Structure: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue (two per TMEM lane
+// quarter; accumulators are transposed through warp-private smem so every global access is coalesced).  smem ring of
 // `stages` {A 128x64, B block_n x 64} tiles (128-byte swizzle), two TMEM accumulator buffers so the epilogue of
 // tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -21,18 +22,19 @@
 namespace pxr {
 
 enum OperandMode : int { OP_KMAJOR = 0, OP_MNMAJOR = 1, OP_CONV = 2 };
-enum EpiAct : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_QUICKGELU_BWD = 2 };
+enum EpiAct : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_QUICKGELU_BWD = 2, ACT_SOFTMAX = 3, ACT_SOFTMAX_BWD = 4 };
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_MAX_STAGES = 8;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
   // tiling
   int M, N;            // logical output extent per batch (predication)
+  int n_store;         // softmax epilogues: columns [N, n_store) are written as zeros (padded row pitch)
   int block_n;         // multiple of 16, <= 256 (multiple of 64 when B is MN-major)
   int stages;
   int tmem_cols;       // power of two >= 2 * block_n
@@ -84,6 +86,7 @@ struct GemmEpilogue {
   float* out_f32 = nullptr;
   __half* out_f16 = nullptr;
   long long ldc = 0, bs0 = 0, bs1 = 0;
+  int n_store = 0;  // softmax modes: zero-fill columns [N, n_store)
 };
 
 struct GemmPlan {

@@ -85,24 +85,23 @@ void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* ran
 
 // ------------------------------------------------------------------ CLIP ViT (slip.py:62-66; SLIP/models.py:18-64)
 // y = LN(x [+ pos[row % T]]) * gamma + beta ; x fp32 [rows, W]; outputs optional fp16 / fp32; stats [rows][2]
-void layernorm_forward(const float* x, const float* pos, int T, const float* gamma, const float* beta, int rows, int W,
-                       float eps, act_t* y16, float* y32, float* stats, cudaStream_t st);
+// W in {128, 256, 512, 768, 1024}; row r of x starts at x + r * x_stride (class-token rows: stride T * W)
+void layernorm_forward(const float* x, long long x_stride, const float* pos, int T, const float* gamma,
+                       const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
+                       cudaStream_t st);
 // gx (+)= LN'(x) applied to dy (fp16, scaled); also writes gx16 = fp16(gx).  accumulate=0 overwrites gx.
-void layernorm_backward(const act_t* dy, const float* x, const float* pos, int T, const float* stats,
-                        const float* gamma, int rows, int W, int accumulate, float* gx, act_t* gx16, cudaStream_t st);
+// dy is compact [rows, W]; x, gx, gx16 rows are x_stride apart
+void layernorm_backward(const act_t* dy, const float* x, long long x_stride, const float* pos, int T,
+                        const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
+                        act_t* gx16, cudaStream_t st);
 // in-place row softmax over the first `cols` of each row of length ld (pad columns zeroed); rows total
 void softmax_forward(act_t* s, int rows, int cols, int ld, cudaStream_t st);
 void softmax_backward(const act_t* p, act_t* dp_to_ds, int rows, int cols, int ld, cudaStream_t st);
-// ln_post on the class token + projection (openai-CLIP VisionTransformer tail) -> e [B, D] fp32
-void clip_head_forward(const float* x, int T, int W, int D, const float* gamma, const float* beta, const float* proj,
-                       int B, float eps, float* stats, float* e, cudaStream_t st);
-// gx[B*T, W] fp32 = 0 except class rows; gx16 likewise.  de: [B, D] fp32 (already scaled)
-void clip_head_backward(const float* de, const float* x, int T, int W, int D, const float* stats, const float* gamma,
-                        const float* proj, int B, float* gx, act_t* gx16, cudaStream_t st);
 // Prompt.forward for all prompts of one perceptor + its gradient w.r.t. the un-normalised embeds.
 //   e [B, D]; prompts [n, D] (unit rows), weights/stops [n]; losses [n] (+= partial, caller zeroes); de [B, D]
 void prompt_loss(const float* e, int B, int D, const float* prompts, const float* weights, const float* stops, int n,
-                 int cutn_global, float grad_scale, float* e_unit, float* losses, float* de, cudaStream_t st);
+                 int cutn_global, float grad_scale, float* e_unit, float* losses, float* de, act_t* de16,
+                 cudaStream_t st);
 
 // ------------------------------------------------------------------ optimiser (pixray.py:538-539, 1484-1487)
 // Adam (bias-corrected, torch.optim.Adam semantics) on z with gradient g * inv_scale, then clip_z to per-channel

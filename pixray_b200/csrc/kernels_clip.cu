@@ -18,55 +18,77 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-constexpr int LN_MAX_PER_LANE = 32;  // W <= 1024
+constexpr int LN_MAX_VEC = 8;  // W <= 1024, W % 128 == 0: each lane owns W/128 float4 vectors of the row
 
-// one warp per row; W % 32 == 0
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos,
-                                                            int T, const float* __restrict__ gamma,
+__device__ __forceinline__ void st_half4(act_t* p, float a, float b, float c, float d) {
+  __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float4 ld_half4(const act_t* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x)), b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// one warp per row; 16-byte vector accesses; x rows are x_stride apart (class-token rows: T * W)
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long x_stride,
+                                                            const float* __restrict__ pos, int T,
+                                                            const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int rows, int W, float eps,
                                                             act_t* __restrict__ y16, float* __restrict__ y32,
                                                             float* __restrict__ stats) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int per = W / 32;
-  float v[LN_MAX_PER_LANE];
-  const float* xr = x + (size_t)row * W;
-  const float* pr = pos ? pos + (size_t)(row % T) * W : nullptr;
+  float4 v[NV];
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_stride);
+  const float4* pr = pos ? reinterpret_cast<const float4*>(pos + (size_t)(row % T) * W) : nullptr;
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i)
-    if (i < per) {
-      float t = xr[lane + 32 * i];
-      if (pr) t += pr[lane + 32 * i];
-      v[i] = t;
-      s += t;
+  for (int i = 0; i < NV; ++i) {
+    float4 t = xr[lane + 32 * i];
+    if (pr) {
+      float4 q = pr[lane + 32 * i];
+      t.x += q.x;
+      t.y += q.y;
+      t.z += q.z;
+      t.w += q.w;
     }
+    v[i] = t;
+    s += (t.x + t.y) + (t.z + t.w);
+  }
   const float mean = warp_sum(s) / W;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i)
-    if (i < per) {
-      float d = v[i] - mean;
-      q += d * d;
-    }
+  for (int i = 0; i < NV; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
   const float rstd = rsqrtf(warp_sum(q) / W + eps);
   if (lane == 0) {
     stats[2 * row] = mean;
     stats[2 * row + 1] = rstd;
   }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i)
-    if (i < per) {
-      int c = lane + 32 * i;
-      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
-      if (y16) y16[(size_t)row * W + c] = __float2half_rn(o);
-      if (y32) y32[(size_t)row * W + c] = o;
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 g = g4[c4], bb = b4[c4];
+    float o0 = (v[i].x - mean) * rstd * g.x + bb.x, o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+    float o2 = (v[i].z - mean) * rstd * g.z + bb.z, o3 = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (y16) st_half4(y16 + (size_t)row * W + 4 * c4, o0, o1, o2, o3);
+    if (y32) reinterpret_cast<float4*>(y32 + (size_t)row * W)[c4] = make_float4(o0, o1, o2, o3);
+  }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ pos, int T,
+                                                            long long x_stride, const float* __restrict__ pos, int T,
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, int rows, int W,
                                                             int accumulate, float* __restrict__ gx,
@@ -74,67 +96,106 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int per = W / 32;
   const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-  const float* xr = x + (size_t)row * W;
-  const float* pr = pos ? pos + (size_t)(row % T) * W : nullptr;
-  float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_stride);
+  const float4* pr = pos ? reinterpret_cast<const float4*>(pos + (size_t)(row % T) * W) : nullptr;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4* gxr = reinterpret_cast<float4*>(gx + (size_t)row * x_stride);
+  float4 g[NV], xh[NV], prev[NV];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i)
-    if (i < per) {
-      int c = lane + 32 * i;
-      float t = xr[c];
-      if (pr) t += pr[c];
-      xh[i] = (t - mean) * rstd;
-      g[i] = __half2float(dy[(size_t)row * W + c]) * gamma[c];
-      s1 += g[i];
-      s2 += g[i] * xh[i];
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 t = xr[c4];
+    if (pr) {
+      float4 q = pr[c4];
+      t.x += q.x;
+      t.y += q.y;
+      t.z += q.z;
+      t.w += q.w;
     }
+    if (accumulate) prev[i] = gxr[c4];
+    float4 d = ld_half4(dy + (size_t)row * W + 4 * c4), gm = g4[c4];
+    xh[i] = make_float4((t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd);
+    g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+    s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+    s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+  }
   s1 = warp_sum(s1) / W;
   s2 = warp_sum(s2) / W;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i)
-    if (i < per) {
-      int c = lane + 32 * i;
-      float d = rstd * (g[i] - s1 - xh[i] * s2);
-      size_t o = (size_t)row * W + c;
-      if (accumulate) d += gx[o];
-      gx[o] = d;
-      if (gx16) gx16[o] = __float2half_rn(d);
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 d;
+    d.x = rstd * (g[i].x - s1 - xh[i].x * s2);
+    d.y = rstd * (g[i].y - s1 - xh[i].y * s2);
+    d.z = rstd * (g[i].z - s1 - xh[i].z * s2);
+    d.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+    if (accumulate) {
+      d.x += prev[i].x;
+      d.y += prev[i].y;
+      d.z += prev[i].z;
+      d.w += prev[i].w;
     }
+    gxr[c4] = d;
+    if (gx16) st_half4(gx16 + (size_t)row * x_stride + 4 * c4, d.x, d.y, d.z, d.w);
+  }
 }
 
-// one warp per row, row length <= 1024 (cols), elements strided by lane
+// one warp per row; lane owns NV 16-byte vectors (8 halfs) of the row: ld % 8 == 0, ld <= 256 * NV
+template <int NV>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(act_t* __restrict__ s, long long rows, int cols, int ld) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   act_t* r = s + row * ld;
-  float v[32];
+  const int nvec = ld / 8;
+  float v[NV][8];
   float m = -FLT_MAX;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    int c = lane + 32 * i;
-    v[i] = (c < cols) ? __half2float(r[c]) : -FLT_MAX;
-    m = fmaxf(m, v[i]);
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      uint4 u = *reinterpret_cast<const uint4*>(r + vi * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (vi >= nvec || vi * 8 + j >= cols) v[i][j] = -FLT_MAX;
+      m = fmaxf(m, v[i][j]);
+    }
   }
   m = warp_max(m);
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    int c = lane + 32 * i;
-    v[i] = (c < cols) ? __expf(v[i] - m) : 0.f;
-    sum += v[i];
-  }
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane + 32 * i) * 8 + j;
+      v[i][j] = (c < cols) ? __expf(v[i][j] - m) : 0.f;
+      sum += v[i][j];
+    }
   const float inv = 1.f / warp_sum(sum);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    int c = lane + 32 * i;
-    if (c < ld) r[c] = __float2half_rn(v[i] * inv);
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      uint4 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i][2 * j] * inv, v[i][2 * j + 1] * inv);
+      *reinterpret_cast<uint4*>(r + vi * 8) = u;
+    }
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const act_t* __restrict__ p, act_t* __restrict__ dp,
                                                           long long rows, int cols, int ld) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -142,123 +203,46 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const act_t* __restric
   if (row >= rows) return;
   const act_t* pr = p + row * ld;
   act_t* dr = dp + row * ld;
-  float pv[32], dv[32];
+  const int nvec = ld / 8;
+  float pv[NV][8], dv[NV][8];
   float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    int c = lane + 32 * i;
-    pv[i] = (c < cols) ? __half2float(pr[c]) : 0.f;
-    dv[i] = (c < cols) ? __half2float(dr[c]) : 0.f;
-    dot += pv[i] * dv[i];
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      uint4 a = *reinterpret_cast<const uint4*>(pr + vi * 8), b = *reinterpret_cast<const uint4*>(dr + vi * 8);
+      const __half2* ha = reinterpret_cast<const __half2*>(&a);
+      const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+        pv[i][2 * j] = fa.x;
+        pv[i][2 * j + 1] = fa.y;
+        dv[i][2 * j] = fb.x;
+        dv[i][2 * j + 1] = fb.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (vi >= nvec || vi * 8 + j >= cols) {
+        pv[i][j] = 0.f;
+        dv[i][j] = 0.f;
+      }
+      dot += pv[i][j] * dv[i][j];
+    }
   }
   dot = warp_sum(dot);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    int c = lane + 32 * i;
-    if (c < ld) dr[c] = __float2half_rn(pv[i] * (dv[i] - dot));
-  }
-}
-
-// one block (256 threads) per image: LN of the class-token row, then e = ln @ proj
-__global__ void __launch_bounds__(256) clip_head_fwd_kernel(const float* __restrict__ x, int T, int W, int D,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta,
-                                                            const float* __restrict__ proj, float eps,
-                                                            float* __restrict__ stats, float* __restrict__ e) {
-  extern __shared__ float sh[];  // [W] normalised row
-  __shared__ float red[8];
-  __shared__ float s_mean, s_rstd;
-  const int b = blockIdx.x;
-  const float* xr = x + (size_t)b * T * W;
-  float s = 0.f;
-  for (int c = threadIdx.x; c < W; c += 256) s += xr[c];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    s_mean = t / W;
-  }
-  __syncthreads();
-  const float mean = s_mean;
-  float q = 0.f;
-  for (int c = threadIdx.x; c < W; c += 256) {
-    float d = xr[c] - mean;
-    q += d * d;
-  }
-  q = warp_sum(q);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    s_rstd = rsqrtf(t / W + eps);
-    stats[2 * b] = mean;
-    stats[2 * b + 1] = s_rstd;
-  }
-  __syncthreads();
-  const float rstd = s_rstd;
-  for (int c = threadIdx.x; c < W; c += 256) sh[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
-  __syncthreads();
-  for (int d = threadIdx.x; d < D; d += 256) {
-    float acc = 0.f;
-    for (int k = 0; k < W; ++k) acc = fmaf(sh[k], proj[(size_t)k * D + d], acc);
-    e[(size_t)b * D + d] = acc;
-  }
-}
-
-// one block per image: dln = proj @ de ; LN backward for the class row
-__global__ void __launch_bounds__(256) clip_head_bwd_kernel(const float* __restrict__ de, const float* __restrict__ x,
-                                                            int T, int W, int D, const float* __restrict__ stats,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ proj, float* __restrict__ gx,
-                                                            act_t* __restrict__ gx16) {
-  extern __shared__ float sh[];  // [D] de row, then [W] g
-  float* s_de = sh;
-  float* s_g = sh + D;
-  __shared__ float red[2][8];
-  __shared__ float s_s1, s_s2;
-  const int b = blockIdx.x;
-  for (int d = threadIdx.x; d < D; d += 256) s_de[d] = de[(size_t)b * D + d];
-  __syncthreads();
-  const float mean = stats[2 * b], rstd = stats[2 * b + 1];
-  const float* xr = x + (size_t)b * T * W;
-  float s1 = 0.f, s2 = 0.f;
-  for (int c = threadIdx.x; c < W; c += 256) {
-    float acc = 0.f;
-    const float* pr = proj + (size_t)c * D;
-    for (int d = 0; d < D; ++d) acc = fmaf(pr[d], s_de[d], acc);
-    float g = acc * gamma[c];
-    s_g[c] = g;
-    float xh = (xr[c] - mean) * rstd;
-    s1 += g;
-    s2 += g * xh;
-  }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = s1;
-    red[1][threadIdx.x >> 5] = s2;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, c = 0.f;
-    for (int i = 0; i < 8; ++i) {
-      a += red[0][i];
-      c += red[1][i];
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      uint4 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        h[j] = __floats2half2_rn(pv[i][2 * j] * (dv[i][2 * j] - dot), pv[i][2 * j + 1] * (dv[i][2 * j + 1] - dot));
+      *reinterpret_cast<uint4*>(dr + vi * 8) = u;
     }
-    s_s1 = a / W;
-    s_s2 = c / W;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < W; c += 256) {
-    float xh = (xr[c] - mean) * rstd;
-    float d = rstd * (s_g[c] - s_s1 - xh * s_s2);
-    size_t o = (size_t)b * T * W + c;
-    gx[o] = d;
-    gx16[o] = __float2half_rn(d);
   }
 }
 
@@ -268,7 +252,8 @@ __global__ void __launch_bounds__(128) prompt_loss_kernel(const float* __restric
                                                           const float* __restrict__ weights,
                                                           const float* __restrict__ stops, int n, float inv_count,
                                                           float grad_scale, float* __restrict__ e_unit,
-                                                          float* __restrict__ losses, float* __restrict__ de) {
+                                                          float* __restrict__ losses, float* __restrict__ de,
+                                                          act_t* __restrict__ de16) {
   extern __shared__ float sh[];  // en [D], gen [D]
   float* en = sh;
   float* gen = sh + D;
@@ -323,7 +308,11 @@ __global__ void __launch_bounds__(128) prompt_loss_kernel(const float* __restric
   float dot = 0.f;
   for (int d = threadIdx.x; d < D; d += 128) dot += gen[d] * en[d];
   dot = block_sum(dot);
-  for (int d = threadIdx.x; d < D; d += 128) de[(size_t)b * D + d] = (gen[d] - en[d] * dot) / nrm;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    float v = (gen[d] - en[d] * dot) / nrm;
+    de[(size_t)b * D + d] = v;
+    if (de16) de16[(size_t)b * D + d] = __float2half_rn(v);
+  }
 }
 
 __global__ void adam_clip_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
@@ -359,35 +348,46 @@ __global__ void cast_kernel(const float* x, act_t* y, long long n, float scale) 
 
 }  // namespace
 
-void layernorm_forward(const float* x, const float* pos, int T, const float* gamma, const float* beta, int rows, int W,
-                       float eps, act_t* y16, float* y32, float* stats, cudaStream_t st) {
-  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, pos, T, gamma, beta, rows, W, eps, y16, y32, stats);
+#define LN_DISPATCH(KERNEL, ...)                                                   \
+  switch (W / 128) {                                                              \
+    case 1: KERNEL<1><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
+    case 2: KERNEL<2><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
+    case 4: KERNEL<4><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
+    case 6: KERNEL<6><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
+    case 8: KERNEL<8><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
+    default: break;                                                               \
+  }
+
+void layernorm_forward(const float* x, long long x_stride, const float* pos, int T, const float* gamma,
+                       const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
+                       cudaStream_t st) {
+  LN_DISPATCH(layernorm_fwd_kernel, x, x_stride, pos, T, gamma, beta, rows, W, eps, y16, y32, stats)
 }
-void layernorm_backward(const act_t* dy, const float* x, const float* pos, int T, const float* stats,
-                        const float* gamma, int rows, int W, int accumulate, float* gx, act_t* gx16, cudaStream_t st) {
-  layernorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(dy, x, pos, T, stats, gamma, rows, W, accumulate, gx, gx16);
+void layernorm_backward(const act_t* dy, const float* x, long long x_stride, const float* pos, int T,
+                        const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
+                        act_t* gx16, cudaStream_t st) {
+  LN_DISPATCH(layernorm_bwd_kernel, dy, x, x_stride, pos, T, stats, gamma, rows, W, accumulate, gx, gx16)
 }
 void softmax_forward(act_t* s, int rows, int cols, int ld, cudaStream_t st) {
-  softmax_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(s, rows, cols, ld);
+  const int nv = (ld / 8 + 31) / 32;
+  const int grid = (rows + 7) / 8;
+  if (nv <= 1) softmax_fwd_kernel<1><<<grid, 256, 0, st>>>(s, rows, cols, ld);
+  else if (nv == 2) softmax_fwd_kernel<2><<<grid, 256, 0, st>>>(s, rows, cols, ld);
+  else softmax_fwd_kernel<4><<<grid, 256, 0, st>>>(s, rows, cols, ld);
 }
 void softmax_backward(const act_t* p, act_t* dp_to_ds, int rows, int cols, int ld, cudaStream_t st) {
-  softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
-}
-void clip_head_forward(const float* x, int T, int W, int D, const float* gamma, const float* beta, const float* proj,
-                       int B, float eps, float* stats, float* e, cudaStream_t st) {
-  clip_head_fwd_kernel<<<B, 256, W * sizeof(float), st>>>(x, T, W, D, gamma, beta, proj, eps, stats, e);
-}
-void clip_head_backward(const float* de, const float* x, int T, int W, int D, const float* stats, const float* gamma,
-                        const float* proj, int B, float* gx, act_t* gx16, cudaStream_t st) {
-  cudaMemsetAsync(gx, 0, (size_t)B * T * W * sizeof(float), st);
-  cudaMemsetAsync(gx16, 0, (size_t)B * T * W * sizeof(act_t), st);
-  clip_head_bwd_kernel<<<B, 256, (D + W) * sizeof(float), st>>>(de, x, T, W, D, stats, gamma, proj, gx, gx16);
+  const int nv = (ld / 8 + 31) / 32;
+  const int grid = (rows + 7) / 8;
+  if (nv <= 1) softmax_bwd_kernel<1><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
+  else if (nv == 2) softmax_bwd_kernel<2><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
+  else softmax_bwd_kernel<4><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
 }
 void prompt_loss(const float* e, int B, int D, const float* prompts, const float* weights, const float* stops, int n,
-                 int cutn_global, float grad_scale, float* e_unit, float* losses, float* de, cudaStream_t st) {
+                 int cutn_global, float grad_scale, float* e_unit, float* losses, float* de, act_t* de16,
+                 cudaStream_t st) {
   // Prompt.forward means over [cutn, n_embed=1] per prompt (pixray.py:280)
   prompt_loss_kernel<<<B, 128, 2 * D * sizeof(float), st>>>(e, D, prompts, weights, stops, n, 1.f / cutn_global,
-                                                           grad_scale, e_unit, losses, de);
+                                                           grad_scale, e_unit, losses, de, de16);
 }
 
 void adam_clip_step(float* z, float* m, float* v, const float* g, float inv_scale, int n, int per_channel,

@@ -139,7 +139,12 @@ __global__ void vq_backward_kernel(const act_t* __restrict__ dzq, float inv_scal
 
 // ------------------------------------------------------------------ GroupNorm
 constexpr int GN_G = 32;
-constexpr int GN_ROWS_PER_BLOCK = 256;  // pixels per block
+constexpr int GN_TARGET_BLOCKS = 592;  // ~4 per SM
+__host__ __device__ inline int gn_rows_per_block(int pixels) {
+  int r = (pixels + GN_TARGET_BLOCKS - 1) / GN_TARGET_BLOCKS;
+  r = (r + 31) / 32 * 32;
+  return r < 32 ? 32 : r;
+}
 
 __device__ __forceinline__ void load8(const act_t* p, float (&f)[8]) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -173,8 +178,9 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict
   const int vecs = C / 8, cpg = C / GN_G;
   const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = 256 / vecs;
   const int c0 = vc * 8;
-  const int p_begin = blockIdx.x * GN_ROWS_PER_BLOCK;
-  const int p_end = min(pixels, p_begin + GN_ROWS_PER_BLOCK);
+  const int rpb = gn_rows_per_block(pixels);
+  const int p_begin = blockIdx.x * rpb;
+  const int p_end = min(pixels, p_begin + rpb);
   float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [half][a/b] : halves of the 8-vector (cpg == 4 splits groups)
   float g8[8], b8[8], mean8[8], rstd8[8];
   if (MODE == 1) {
@@ -233,13 +239,16 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict
 template <int MODE>
 __global__ void gn_final_kernel(const float* __restrict__ part, int nblk, double count, float eps,
                                 float* __restrict__ out) {
-  int t = threadIdx.x;  // 0..63 : (group, which)
-  if (t >= GN_G * 2) return;
+  const int t = threadIdx.x & 63, q = threadIdx.x >> 6;  // 256 threads: slot (group, which) x quarter of the partials
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)part[(size_t)b * GN_G * 2 + t];
+  for (int b = q; b < nblk; b += 4) s += (double)part[(size_t)b * GN_G * 2 + t];
+  __shared__ double acc4[4][GN_G * 2];
   __shared__ double sh[GN_G * 2];
-  sh[t] = s / count;
+  acc4[q][t] = s;
   __syncthreads();
+  if (q == 0) sh[t] = (acc4[0][t] + acc4[1][t] + acc4[2][t] + acc4[3][t]) / count;
+  __syncthreads();
+  if (q != 0) return;
   if (MODE == 0) {
     if ((t & 1) == 0) {
       double mean = sh[t], ex2 = sh[t + 1];
@@ -423,12 +432,15 @@ void vq_backward(const act_t* dzq, float inv_scale, int C, int hw, float* z_grad
   vq_backward_kernel<<<(C * hw + 255) / 256, 256, 0, st>>>(dzq, inv_scale, C, hw, z_grad);
 }
 
-int gn_num_partials(int pixels, int C) { return (pixels + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK; }
+int gn_num_partials(int pixels, int C) {
+  const int rpb = gn_rows_per_block(pixels);
+  return (pixels + rpb - 1) / rpb;
+}
 
 void gn_stats(const act_t* x, int pixels, int C, float eps, float* part, float* stats, cudaStream_t st) {
   const int nblk = gn_num_partials(pixels, C);
   gn_partial_kernel<0><<<nblk, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, part);
-  gn_final_kernel<0><<<1, 64, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), eps, stats);
+  gn_final_kernel<0><<<1, 256, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), eps, stats);
 }
 
 void gn_apply(const act_t* x, const float* stats, const float* gamma, const float* beta, int pixels, int C, int swish,
@@ -442,7 +454,7 @@ void gn_backward(const act_t* dy, const act_t* x, const float* stats, const floa
                  cudaStream_t st) {
   const int nblk = gn_num_partials(pixels, C);
   gn_partial_kernel<1><<<nblk, 256, 0, st>>>(x, dy, stats, gamma, beta, pixels, C, swish, part);
-  gn_final_kernel<1><<<1, 64, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), 0.f, gstats);
+  gn_final_kernel<1><<<1, 256, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), 0.f, gstats);
   const long long nvec = (long long)pixels * C / 8;
   gn_bwd_apply_kernel<<<grid_for(nvec, 256), 256, 0, st>>>(dy, x, stats, gstats, gamma, beta, nvec, C, swish, dres,
                                                            dx);

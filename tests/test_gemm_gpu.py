@@ -120,6 +120,39 @@ def test_gemm_batched_qk():
     assert S[..., T:].abs().max().item() == 0.0
 
 
+def test_gemm_fused_softmax_forward_and_backward():
+    """Attention epilogues: P = softmax(alpha q k^T) straight from the accumulator, and
+    dS = alpha * P * (dP - <P, dP>) from the dP = dO v^T accumulator (batched, T = 197, padded pitch 200)."""
+    torch.manual_seed(9)
+    imgs, heads, T, d, ldp = 2, 3, 197, 64, 200
+    qkv = _rand(imgs, T, 3 * heads * d, scale=1.5)
+    P = torch.full((imgs, heads, T, ldp), 7.0, device="cuda", dtype=torch.half)
+    k_off = qkv.view(-1)[heads * d:]
+    st = (d, T * 3 * heads * d)
+    run_gemm(qkv, k_off, T, T, d, lda=3 * heads * d, a_mn=T, a_k=d, ldb=3 * heads * d, b_mn=T, b_k=d, nb0=heads,
+             nb1=imgs, a_bs=st, b_bs=st, b_batched=1, block_n=208, alpha=0.125, act=3, n_store=ldp, out_f16=P, ldc=ldp,
+             c_bs=(T * ldp, heads * T * ldp))
+    q = qkv[..., : heads * d].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    k = qkv[..., heads * d: 2 * heads * d].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    v = qkv[..., 2 * heads * d:].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    Pref = torch.softmax(0.125 * q @ k.transpose(-1, -2), dim=-1)
+    _check(P[..., :T], Pref, 2e-3, "fused softmax fwd")
+    assert P[..., T:].abs().max().item() == 0.0
+    # backward: dO random, dP = dO v^T, dS = alpha * P * (dP - rowsum(P * dP))
+    dO = _rand(imgs, T, heads * d, scale=0.5)
+    dS = torch.full((imgs, heads, T, ldp), 7.0, device="cuda", dtype=torch.half)
+    v_off = qkv.view(-1)[2 * heads * d:]
+    run_gemm(dO, v_off, T, T, d, lda=heads * d, a_mn=T, a_k=d, ldb=3 * heads * d, b_mn=T, b_k=d, nb0=heads, nb1=imgs,
+             a_bs=(d, T * heads * d), b_bs=st, b_batched=1, block_n=208, alpha=0.125, act=4, aux_in=P, n_store=ldp,
+             out_f16=dS, ldc=ldp, c_bs=(T * ldp, heads * T * ldp))
+    dOh = dO.reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
+    dP = dOh @ v.transpose(-1, -2)
+    Pf = P[..., :T].float()
+    dSref = 0.125 * Pf * (dP - (Pf * dP).sum(-1, keepdim=True))
+    _check(dS[..., :T], dSref, 4e-3, "fused softmax bwd")
+    assert dS[..., T:].abs().max().item() == 0.0
+
+
 @pytest.mark.parametrize("H,W,Cin,Cout,ks,bn", [(32, 32, 128, 128, 3, 128), (16, 16, 256, 512, 3, 128),
                                                   (64, 64, 64, 3, 3, 16), (16, 16, 256, 256, 1, 64)])
 def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn):
