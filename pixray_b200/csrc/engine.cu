@@ -195,18 +195,27 @@ class Engine {
     o.mode = OP_MNMAJOR;
     return o;
   }
-  static int pick_bn(int N, bool b_mn, long long m_tiles) {
-    int bn;
-    if (N % 256 == 0) bn = 256;
-    else if (N % 128 == 0) bn = 128;
-    else if (N <= 256) bn = round_up(N, b_mn ? 64 : 16);
-    else {
-      int parts = (N + 255) / 256;
-      bn = round_up((N + parts - 1) / parts, b_mn ? 64 : 16);
+  // Tile width by a wave-quantisation cost model: a persistent grid of num_sms CTAs runs ceil(tiles / num_sms) waves
+  // of tiles whose cost grows with bn (plus a fixed per-tile overhead); e.g. M = 12608, N = 768 is 297 tiles of 256
+  // (3 waves for 2.007 waves of work) but 396 tiles of 192 (3 cheaper waves).
+  int pick_bn(int N, bool b_mn, long long m_tiles) const {
+    const int step = b_mn ? 64 : 16;
+    if (N <= 256 && m_tiles * 1 >= num_sms / 2) return round_up(N, step);
+    int best = 0;
+    double best_cost = 1e30;
+    for (int bn = 256; bn >= 64; bn -= 64) {
+      if (bn % step) continue;
+      const long long tiles = m_tiles * ((N + bn - 1) / bn);
+      const long long waves = (tiles + num_sms - 1) / num_sms;
+      // narrower tiles re-read A more often and sit closer to the smem-bandwidth limit: mild penalty
+      const double cost = (double)waves * (bn + 40.0) * (bn >= 192 ? 1.0 : (bn == 128 ? 1.06 : 1.2));
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best = bn;
+      }
     }
-    // few M tiles: prefer more, narrower CTAs
-    while (bn > 64 && bn % 128 == 0 && m_tiles * ((N + bn - 1) / bn) < 96) bn /= 2;
-    return bn;
+    if (N < best) best = round_up(N, step);
+    return best;
   }
   void add_gemm(OpList& l, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& e,
                 int bn = 0) {

@@ -45,33 +45,35 @@ __device__ __forceinline__ float quickgelu_grad(float u) {
 
 constexpr int TB_LD = 33;                       // transposer row pitch (floats): conflict-free both ways
 constexpr int TB_FLOATS = 32 * TB_LD;           // one 32 x 32 block per epilogue warp
+constexpr int TB_WARP_BYTES = TB_FLOATS * 4 + 32 * 8 + 32 * 4;  // + per-row offset / row-index tables
 constexpr int GEMM_EPI_WARPS = 8;
 
 // Row <-> column layout exchange through the warp-private smem block.
-//   row layout : thread = accumulator row (TMEM lane), registers = columns     (what tcgen05.ld delivers)
-//   col layout : thread = column, loop over rows                               (what coalesced global access wants)
+//   row layout   : thread = accumulator row (TMEM lane), registers = columns     (what tcgen05.ld delivers)
+//   store layout : lane = (row_sub, 16-byte chunk of the row)                    (what coalesced global access wants)
 struct RowInfo {
-  long long off;  // element offset of this thread's row in the output tensors
+  long long off;  // element offset of this thread's row in the output tensors, -1 if the row is out of range
   int row;        // logical row index (bias_per_row)
-  int valid;
 };
 
 __device__ __forceinline__ RowInfo row_info(const GemmParams& p, const TileCoord& t, int r_tile) {
   RowInfo ri;
+  bool valid;
   if (p.a_mode == OP_CONV) {
     const int h = t.h0 + r_tile / p.tile_w, w = t.w0 + r_tile % p.tile_w;
-    ri.valid = (h < p.conv_H) && (w < p.conv_W);
+    valid = (h < p.conv_H) && (w < p.conv_W);
     ri.row = h * p.conv_W + w;
     ri.off = (static_cast<long long>(t.z) * p.conv_H * p.conv_W + ri.row) * p.ldc;
   } else {
     ri.row = t.m0 + r_tile;
-    ri.valid = ri.row < p.M;
+    valid = ri.row < p.M;
     ri.off = t.b0 * p.out_bs0 + t.b1 * p.out_bs1 + static_cast<long long>(ri.row) * p.ldc;
   }
+  if (!valid) ri.off = -1;
   return ri;
 }
 
-// Load `width` (16 or 32) accumulator columns of this thread's row, starting at TMEM column `tcol`.
+// Load `width` (16 or 32) accumulator columns of this thread's row, starting at TMEM address `taddr`.
 __device__ __forceinline__ void load_acc(uint32_t taddr, int width, float (&v)[32]) {
   uint32_t u[16];
   tmem_ld_x16(taddr, u);
@@ -89,98 +91,231 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, int width, float (&v)[3
   }
 }
 
-// rows -> smem (row layout write), then the warp walks the 32 rows with lane = column
-__device__ __forceinline__ void to_col_layout(float* tb, const float (&v)[32], int lane) {
+__device__ __forceinline__ void stage_rows(float* tb, const float (&v)[32], int lane) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) tb[lane * TB_LD + j] = v[j];
   __syncwarp();
 }
 
-// generic (non-softmax) epilogue for one 32-column slab, executed in column layout: coalesced global accesses
-__device__ __forceinline__ void epilogue_slab(const GemmParams& p, float* tb, const RowInfo& ri, int lane, int col,
-                                              bool col_ok) {
-  const float bias_c = (p.bias && !p.bias_per_row && col_ok) ? p.bias[col] : 0.f;
-  for (int r = 0; r < 32; ++r) {
-    const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
-    const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
-    const int row_r = __shfl_sync(0xffffffffu, ri.row, r);
-    if (!valid_r || !col_ok) continue;
-    const long long o = off_r + col;
-    float x = tb[r * TB_LD + lane] * p.alpha + bias_c;
-    if (p.bias && p.bias_per_row) x += p.bias[row_r];
-    if (p.act == ACT_QUICKGELU) {
-      if (p.aux_out) p.aux_out[o] = __float2half_rn(x);
-      x = quickgelu(x);
-    } else if (p.act == ACT_QUICKGELU_BWD) {
-      x *= quickgelu_grad(__half2float(p.aux_in[o]));
+template <int E>
+__device__ __forceinline__ void ld_f16(const __half* p, bool vec, int nv, float (&x)[E]) {
+  if (vec) {
+    if (E == 8) {
+      uint4 u = *reinterpret_cast<const uint4*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h[j]);
+        x[2 * j] = f.x;
+        x[2 * j + 1] = f.y;
+      }
+    } else {
+      uint2 u = *reinterpret_cast<const uint2*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float2 f = __half22float2(h[j]);
+        x[2 * j] = f.x;
+        x[2 * j + 1] = f.y;
+      }
     }
-    if (p.res_f32) x += p.res_f32[o];
-    if (p.res_f16) x += __half2float(p.res_f16[o]);
-    if (p.out_f32) p.out_f32[o] = x;
-    if (p.out_f16) p.out_f16[o] = __float2half_rn(x);
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; ++j) x[j] = (j < nv) ? __half2float(p[j]) : 0.f;
   }
-  __syncwarp();
+}
+template <int E>
+__device__ __forceinline__ void st_f16(__half* p, bool vec, int nv, const float (&x)[E]) {
+  if (vec) {
+    if (E == 8) {
+      uint4 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      *reinterpret_cast<uint4*>(p) = u;
+    } else {
+      uint2 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      *reinterpret_cast<uint2*>(p) = u;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+      if (j < nv) p[j] = __float2half_rn(x[j]);
+  }
+}
+template <int E>
+__device__ __forceinline__ void ld_f32(const float* p, bool vec, int nv, float (&x)[E]) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < E / 4; ++j) {
+      float4 f = reinterpret_cast<const float4*>(p)[j];
+      x[4 * j] = f.x;
+      x[4 * j + 1] = f.y;
+      x[4 * j + 2] = f.z;
+      x[4 * j + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; ++j) x[j] = (j < nv) ? p[j] : 0.f;
+  }
+}
+template <int E>
+__device__ __forceinline__ void st_f32(float* p, bool vec, int nv, const float (&x)[E]) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < E / 4; ++j)
+      reinterpret_cast<float4*>(p)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+      if (j < nv) p[j] = x[j];
+  }
+}
+
+// Generic epilogue of one staged 32 x 32 block.  E elements per lane: 8 when every tensor is fp16 (16-byte accesses,
+// 8 rows per warp instruction), 4 when an fp32 tensor takes part (16-byte accesses on the fp32 side, 4 rows).
+template <int E>
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, const float* tb, const long long* s_off,
+                                               const int* s_row, int lane, int col_base, int col_limit) {
+  constexpr int CH = 32 / E, RPI = 32 / CH;
+  const int chunk = lane % CH, rsub = lane / CH;
+  const int c0 = chunk * E;
+  const int col = col_base + c0;
+  int nv = col_limit - col;  // col_limit = min(N, end of this tile)
+  nv = nv < 0 ? 0 : (nv > E ? E : nv);
+  const bool vec = p.vec_ok && nv == E;
+  float bias[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) bias[j] = (p.bias && !p.bias_per_row && j < nv) ? p.bias[col + j] : 0.f;
+  if (nv == 0) return;
+#pragma unroll 2
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int r = it * RPI + rsub;
+    const long long off_r = s_off[r];
+    if (off_r < 0) continue;
+    const long long o = off_r + col;
+    float x[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) x[j] = tb[r * TB_LD + c0 + j] * p.alpha + bias[j];
+    if (p.bias && p.bias_per_row) {
+      const float b = p.bias[s_row[r]];
+#pragma unroll
+      for (int j = 0; j < E; ++j) x[j] += b;
+    }
+    if (p.act == ACT_QUICKGELU) {
+      if (p.aux_out) st_f16<E>(p.aux_out + o, vec, nv, x);
+#pragma unroll
+      for (int j = 0; j < E; ++j) x[j] = quickgelu(x[j]);
+    } else if (p.act == ACT_QUICKGELU_BWD) {
+      float u[E];
+      ld_f16<E>(p.aux_in + o, vec, nv, u);
+#pragma unroll
+      for (int j = 0; j < E; ++j) x[j] *= quickgelu_grad(u[j]);
+    }
+    if (p.res_f32) {
+      float t[E];
+      ld_f32<E>(p.res_f32 + o, vec, nv, t);
+#pragma unroll
+      for (int j = 0; j < E; ++j) x[j] += t[j];
+    }
+    if (p.res_f16) {
+      float t[E];
+      ld_f16<E>(p.res_f16 + o, vec, nv, t);
+#pragma unroll
+      for (int j = 0; j < E; ++j) x[j] += t[j];
+    }
+    if (p.out_f32) st_f32<E>(p.out_f32 + o, vec, nv, x);
+    if (p.out_f16) st_f16<E>(p.out_f16 + o, vec, nv, x);
+  }
+}
+
+// fp16 store of a staged block with zero fill up to n_store (softmax epilogues), lane = (8 rows, 4 chunks of 8)
+__device__ __forceinline__ void store_block_f16(const GemmParams& p, const float* tb, const long long* s_off, int lane,
+                                                int col_base) {
+  const int chunk = lane & 3, rsub = lane >> 2;
+  const int col = col_base + chunk * 8;
+  int nv = p.n_store - col;
+  nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
+  if (nv == 0) return;
+  const bool vec = p.vec_ok && nv == 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + rsub;
+    const long long off_r = s_off[r];
+    if (off_r < 0) continue;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = tb[r * TB_LD + chunk * 8 + j];
+    st_f16<8>(p.out_f16 + off_r + col, vec, nv, x);
+  }
 }
 
 // Fused row softmax (attention probabilities straight out of the QK^T accumulator, nn.MultiheadAttention /
 // taming AttnBlock): requires the whole row in one tile (tiles_n == 1).  Thread = row.  Columns [N, n_store) are
 // written as zeros so the result can be consumed as a K-major operand with a padded row pitch.
-__device__ __forceinline__ void epilogue_softmax_fwd(const GemmParams& p, float* tb, const RowInfo& ri, uint32_t taddr,
-                                                     int lane) {
+__device__ __forceinline__ void epilogue_softmax_fwd(const GemmParams& p, float* tb, const long long* s_off,
+                                                     uint32_t taddr, int lane) {
   const int nslab = (p.block_n + 31) / 32;
   float v[32];
   float mx = -3.0e38f;
   for (int s = 0; s < nslab; ++s) {
-    const int width = min(32, p.block_n - s * 32);
-    load_acc(taddr + s * 32, width, v);
+    load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (s * 32 + j < p.N) mx = fmaxf(mx, v[j] * p.alpha);
   }
   float sum = 0.f;
   for (int s = 0; s < nslab; ++s) {
-    const int width = min(32, p.block_n - s * 32);
-    load_acc(taddr + s * 32, width, v);
+    load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (s * 32 + j < p.N) sum += __expf(v[j] * p.alpha - mx);
   }
   const float inv = __fdividef(1.f, sum);
   for (int s = 0; s < nslab; ++s) {
-    const int width = min(32, p.block_n - s * 32);
-    load_acc(taddr + s * 32, width, v);
+    load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (s * 32 + j < p.N) ? __expf(v[j] * p.alpha - mx) * inv : 0.f;
-    to_col_layout(tb, v, lane);
-    const int col = s * 32 + lane;
-    for (int r = 0; r < 32; ++r) {
-      const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
-      const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
-      if (valid_r && col < p.n_store) p.out_f16[off_r + col] = __float2half_rn(tb[r * TB_LD + lane]);
-    }
+    stage_rows(tb, v, lane);
+    store_block_f16(p, tb, s_off, lane, s * 32);
     __syncwarp();
   }
 }
 
 // Fused softmax backward: accumulator = dP row, aux_in = P (fp16, same indexing as the output);
 // dS = alpha * P * (dP - sum_j P_j dP_j).
-__device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float* tb, const RowInfo& ri, uint32_t taddr,
-                                                     int lane) {
+__device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float* tb, const long long* s_off,
+                                                     uint32_t taddr, int lane) {
   const int nslab = (p.block_n + 31) / 32;
+  const int chunk = lane & 3, rsub = lane >> 2;
   float v[32];
   float dot = 0.f;
   for (int pass = 0; pass < 2; ++pass) {
     for (int s = 0; s < nslab; ++s) {
-      const int width = min(32, p.block_n - s * 32);
-      const int col = s * 32 + lane;
-      // P block: coalesced load (col layout) -> smem -> row layout
-      for (int r = 0; r < 32; ++r) {
-        const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
-        const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
-        tb[r * TB_LD + lane] = (valid_r && col < p.N) ? __half2float(p.aux_in[off_r + col]) : 0.f;
+      // P block: coalesced 16-byte loads (store layout) -> smem -> row layout
+      const int col = s * 32 + chunk * 8;
+      int nv = p.N - col;
+      nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
+      const bool vec = p.vec_ok && nv == 8;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + rsub;
+        const long long off_r = s_off[r];
+        float x[8];
+        if (off_r >= 0 && nv > 0) {
+          ld_f16<8>(p.aux_in + off_r + col, vec, nv, x);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tb[r * TB_LD + chunk * 8 + j] = x[j];
       }
       __syncwarp();
-      load_acc(taddr + s * 32, width, v);
+      load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
       if (pass == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) dot += tb[lane * TB_LD + j] * v[j];
@@ -189,12 +324,8 @@ __device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float*
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = p.alpha * tb[lane * TB_LD + j] * (v[j] - dot);
         __syncwarp();
-        to_col_layout(tb, v, lane);
-        for (int r = 0; r < 32; ++r) {
-          const long long off_r = __shfl_sync(0xffffffffu, ri.off, r);
-          const int valid_r = __shfl_sync(0xffffffffu, ri.valid, r);
-          if (valid_r && col < p.n_store) p.out_f16[off_r + col] = __float2half_rn(tb[r * TB_LD + lane]);
-        }
+        stage_rows(tb, v, lane);
+        store_block_f16(p, tb, s_off, lane, s * 32);
         __syncwarp();
       }
     }
@@ -322,29 +453,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int ew = warp - 2;          // 0..7
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = ew >> 2;         // two warps share a quarter and split the 32-column slabs
-    float* tb = tbuf_base + ew * TB_FLOATS;
+    uint8_t* wbase = reinterpret_cast<uint8_t*>(tbuf_base) + static_cast<size_t>(ew) * TB_WARP_BYTES;
+    float* tb = reinterpret_cast<float*>(wbase);
+    long long* s_off = reinterpret_cast<long long*>(wbase + TB_FLOATS * 4);
+    int* s_row = reinterpret_cast<int*>(wbase + TB_FLOATS * 4 + 32 * 8);
+    const bool wide = (p.out_f32 != nullptr) || (p.res_f32 != nullptr);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const RowInfo ri = row_info(p, t, q * 32 + lane);
+      s_off[lane] = ri.off;
+      s_row[lane] = ri.row;
+      __syncwarp();
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      const RowInfo ri = row_info(p, t, q * 32 + lane);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
       if (p.act == ACT_SOFTMAX) {
-        if (half == 0) epilogue_softmax_fwd(p, tb, ri, taddr, lane);
+        if (half == 0) epilogue_softmax_fwd(p, tb, s_off, taddr, lane);
       } else if (p.act == ACT_SOFTMAX_BWD) {
-        if (half == 0) epilogue_softmax_bwd(p, tb, ri, taddr, lane);
+        if (half == 0) epilogue_softmax_bwd(p, tb, s_off, taddr, lane);
       } else {
         const int nslab = (p.block_n + 31) / 32;
         for (int s = half; s < nslab; s += 2) {
-          const int width = min(32, p.block_n - s * 32);
           float v[32];
-          load_acc(taddr + s * 32, width, v);
-          to_col_layout(tb, v, lane);
-          const int col = t.n0 + s * 32 + lane;
-          epilogue_slab(p, tb, ri, lane, col, (s * 32 + lane < p.block_n) && (col < p.N));
+          load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
+          stage_rows(tb, v, lane);
+          const int col_limit = min(p.N, t.n0 + p.block_n);
+          if (wide) epilogue_block<4>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit);
+          else epilogue_block<8>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit);
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -490,7 +629,7 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
              aligned16(epi.aux_out) && aligned16(epi.res_f32) && aligned16(epi.res_f16) && aligned16(epi.out_f32) &&
              aligned16(epi.out_f16);
   plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  plan->smem_bytes = stages * stage_bytes + 1024 + 256 + GEMM_EPI_WARPS * TB_FLOATS * 4;
+  plan->smem_bytes = stages * stage_bytes + 1024 + 256 + GEMM_EPI_WARPS * TB_WARP_BYTES;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -60,13 +60,13 @@ def test_c2_iterate_runs_and_times():
 @pytest.mark.slow
 def test_c2_parity_gpu():
     """Full-size z.grad parity (the second half of BASELINE.json's metric).  Tolerance: 3e-2 * max|grad|."""
-    from test_pipeline_gpu import random_transforms, report
+    from test_pipeline_gpu import plant_extremes, random_transforms, report
     vq, clip, eng, prompts, z = build_c2(seed=3)
     T = random_transforms(64, 224, 5)
     g = torch.Generator().manual_seed(13)
-    facs = torch.rand(64, generator=g) * 0.1
-    noise = torch.randn(64, 3, 224, 224, generator=g)
-    torch.set_num_threads(max(1, torch.get_num_threads()))
+    facs, noise = plant_extremes(torch.rand(64, generator=g) * 0.1, torch.randn(64, 3, 224, 224, generator=g))
+    import bench
+    print("[c2] oracle threads:", bench.pick_threads())
     t0 = time.time()
     ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), 224, "reflection", 0.4,
                     facs, noise)

@@ -21,7 +21,7 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
-    from test_pipeline_gpu import SMALL_CLIP, SMALL_VQ, random_transforms
+    from test_pipeline_gpu import SMALL_CLIP, SMALL_VQ, plant_extremes, random_transforms
     from oracle import ref_path as R
     from pixray_b200 import engine as E
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -43,8 +43,7 @@ def _worker(rank, world, port, out_dir):
     idx = torch.randint(1024, (256,), generator=g)
     z = vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16).clone() + 0.05 * torch.randn(1, 128, 16, 16, generator=g)
     T = random_transforms(cutn, cs, 3)
-    facs = torch.rand(cutn, generator=g) * 0.1
-    noise = torch.randn(cutn, 3, cs, cs, generator=g)
+    facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
     zc = z.clone().cuda()
     losses = np.zeros(2, dtype=np.float32)
     eng.iterate(zc, 0.05, 0, params=dict(transforms=T, zoom_padding=0, fill=0.4, noise_facs=facs.numpy(), noise=noise),
