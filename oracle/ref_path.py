@@ -492,7 +492,9 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
     (embed [n,D], weight, stop).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
+    out.retain_grad()
     batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise)
+    batch.retain_grad()
     losses, embeds = [], []
     for model, pms in zip(clip_models, prompts):
         iii = encode_image(model, batch).float()
@@ -502,4 +504,5 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
     total = sum(losses)
     total.backward()
     return dict(image=out.detach(), batch=batch.detach(), embeds=[e.detach() for e in embeds],
-                losses=[l.detach() for l in losses], z_grad=z.grad.detach())
+                losses=[l.detach() for l in losses], z_grad=z.grad.detach(), image_grad=out.grad.detach(),
+                batch_grad=batch.grad.detach())

@@ -332,9 +332,12 @@ __device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float*
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+template <int EPI>  // 0 generic epilogue, 1 fused softmax forward, 2 fused softmax backward
+__device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer derived from the __shared__ symbol (offset arithmetic only) so smem accesses compile to LDS/STS
+  const uint32_t smem_base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -470,9 +473,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
-      if (p.act == ACT_SOFTMAX) {
+      if (EPI == 1) {
         if (half == 0) epilogue_softmax_fwd(p, tb, s_off, taddr, lane);
-      } else if (p.act == ACT_SOFTMAX_BWD) {
+      } else if (EPI == 2) {
         if (half == 0) epilogue_softmax_bwd(p, tb, s_off, taddr, lane);
       } else {
         const int nslab = (p.block_n + 31) / 32;
@@ -498,6 +501,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tc_body<0>(p);
+}
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_softmax_fwd_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tc_body<1>(p);
+}
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_softmax_bwd_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tc_body<2>(p);
 }
 
 // ------------------------------------------------------------------ host side
@@ -633,6 +646,8 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc_softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   return 0;
 }
@@ -730,7 +745,12 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
 }
 
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  if (plan.p.act == ACT_SOFTMAX)
+    gemm_tc_softmax_fwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.act == ACT_SOFTMAX_BWD)
+    gemm_tc_softmax_bwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else
+    gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
 }
 
 }  // namespace pxr

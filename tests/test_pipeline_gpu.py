@@ -194,6 +194,7 @@ def test_adam_clip_and_iterate_small():
         ref_l = np.array([float(l) for l in r["losses"]], dtype=np.float32)
         print(f"[parity] iter {it}: losses engine {losses} oracle {ref_l}")
         assert np.abs(losses - ref_l).max() < 5e-3
+        report(f"iter {it} d/d image", eng.debug_read("g_img", (1, 3, 32, 32)) / 4096.0, r["image_grad"])
         e_g, m_g = report(f"iter {it} z.grad", g_eng, r["z_grad"])
         assert e_g <= 3e-2 * m_g
         z_next = torch.maximum(torch.minimum(adam.step(z_ref, g_eng, lr), zmax), zmin)  # clip_z, vqgan.py:202-204
