@@ -28,6 +28,7 @@ class Engine {
   int num_sms = 148;
   int fmt = 0;
   float S = 4096.f;  // grad scale
+  bool fuse_softmax = false;  // PXR_FUSE_SOFTMAX=1: attention softmax inside the GEMM epilogue
   std::map<std::string, HostWeight> weights[3];
   std::vector<void*> allocs;
   bool finalized = false;
@@ -312,6 +313,7 @@ void Engine::create() {
   fmt = cfg.op_dtype;
   if (fmt != PXR_DTYPE_F16) throw EngineError(-5, "only PXR_DTYPE_F16 operands are wired through the pointwise kernels");
   if (cfg.grad_scale > 0) S = cfg.grad_scale;
+  if (const char* fs = getenv("PXR_FUSE_SOFTMAX")) fuse_softmax = atoi(fs) != 0;
   if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
   if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
   if (cfg.adam_eps <= 0) cfg.adam_eps = 1e-8f;
@@ -482,7 +484,7 @@ Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
     e.ldc = 3 * c;
     add_gemm(drawer_fwd, opK(a.p, c, T, c), opK(wqkv, c, 3 * c, c), T, 3 * c, c, e);
   }
-  const bool fuse_sm = T <= 256;  // whole row in one accumulator tile -> softmax lives in the GEMM epilogue
+  const bool fuse_sm = fuse_softmax && T <= 256;  // whole row in one accumulator tile -> softmax in the GEMM epilogue
   {
     GemmEpilogue e;
     e.alpha = alpha;
@@ -869,7 +871,7 @@ void Engine::build_clip(int i) {
   float* x0 = x_cur;
   C.layers.resize(L);
   const float scale = 1.f / std::sqrt((float)d);
-  const bool fuse_sm = T <= 256;  // attention row fits one accumulator tile: softmax fused into the GEMM epilogue
+  const bool fuse_sm = fuse_softmax && T <= 256;  // attention row fits one tile: softmax fused into the GEMM epilogue
   const int bnS = fuse_sm ? round_up(T, 16) : pick_bn(T, false, 1000);
 
   // ---- forward: patch embed (conv1 as GEMM over im2col'd patches, written straight into the token rows 1..np)

@@ -74,20 +74,16 @@ __device__ __forceinline__ RowInfo row_info(const GemmParams& p, const TileCoord
 }
 
 // Load `width` (16 or 32) accumulator columns of this thread's row, starting at TMEM address `taddr`.
+// Both 16-column loads are issued before the single tcgen05.wait::ld (the wait, not the load, is the expensive part).
 __device__ __forceinline__ void load_acc(uint32_t taddr, int width, float (&v)[32]) {
-  uint32_t u[16];
-  tmem_ld_x16(taddr, u);
+  uint32_t u0[16], u1[16];
+  tmem_ld_x16(taddr, u0);
+  if (width > 16) tmem_ld_x16(taddr + 16, u1);
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
-  if (width > 16) {
-    tmem_ld_x16(taddr + 16, u);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[16 + j] = __uint_as_float(u[j]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[16 + j] = 0.f;
+  for (int j = 0; j < 16; ++j) {
+    v[j] = __uint_as_float(u0[j]);
+    v[16 + j] = (width > 16) ? __uint_as_float(u1[j]) : 0.f;
   }
 }
 

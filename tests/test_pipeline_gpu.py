@@ -194,7 +194,22 @@ def test_adam_clip_and_iterate_small():
         ref_l = np.array([float(l) for l in r["losses"]], dtype=np.float32)
         print(f"[parity] iter {it}: losses engine {losses} oracle {ref_l}")
         assert np.abs(losses - ref_l).max() < 5e-3
+        report(f"iter {it} image", eng.debug_read("img", (1, 3, 32, 32)), r["image"])
+        report(f"iter {it} batch", eng.debug_read("batch", (cutn, 3, cs, cs)), r["batch"])
+        gb = eng.debug_read("g_batch", (cutn, 3, cs, cs)).cpu().reshape(-1) / 4096.0
+        rb = r["batch_grad"].reshape(-1).clone()
+        for i in (int(ir[0]), int(ir[1])):
+            gb[i] = rb[i] = 0.0  # the range terms are added to these two elements inside cutout_backward
+        report(f"iter {it} d/d batch (direct term)", gb, rb)
+        report(f"iter {it} d/d pooled", eng.debug_read("g_pooled", (1, 3, cs, cs)) / 4096.0,
+               torch.zeros(1, 3, cs, cs))  # magnitude only
         report(f"iter {it} d/d image", eng.debug_read("g_img", (1, 3, 32, 32)) / 4096.0, r["image_grad"])
+        # the same inputs through the per-op entry points must give the same gradient as pxr_iterate
+        eng.synth(z_ref)
+        eng.make_cutouts(None, transforms=T, zoom_padding=it % 2, fill=0.5, noise_facs=facs.numpy(), noise=noise, it=it)
+        eng.encode_image(0)
+        g_ops = eng.backward().cpu()
+        report(f"iter {it} z.grad per-op path vs pxr_iterate", g_ops, g_eng)
         e_g, m_g = report(f"iter {it} z.grad", g_eng, r["z_grad"])
         assert e_g <= 3e-2 * m_g
         z_next = torch.maximum(torch.minimum(adam.step(z_ref, g_eng, lr), zmax), zmin)  # clip_z, vqgan.py:202-204
@@ -202,3 +217,42 @@ def test_adam_clip_and_iterate_small():
         assert e_z < 2e-5
         z_ref = z_next
     assert eng.num_launches() > 0
+
+
+def test_two_perceptors_share_the_cutout_batch():
+    """BASELINE config 3 shape of the path: two CLIP models (patch 16 and patch 32) encode the SAME cutout batch
+    (one MakeCutouts per input_resolution, pixray.py:643-649); their gradients add into d loss / d batch."""
+    cutn, cs, seed = 8, 224, 31
+    torch.manual_seed(seed)
+    vq = R.init_vqgan_weights(R.VQModel(n_embed=1024, embed_dim=128, ch=128, ch_mult=(1, 2), num_res_blocks=1,
+                                        attn_resolutions=(16,), resolution=32, z_channels=128), seed)
+    cfg_a = dict(width=128, layers=2, heads=2, patch=32, image_res=224, out_dim=64)
+    cfg_b = dict(width=128, layers=1, heads=2, patch=16, image_res=224, out_dim=64)
+    clip_a = R.init_clip_weights(R.ClipVisual(224, 32, 128, 2, 2, 64), seed + 1)
+    clip_b = R.init_clip_weights(R.ClipVisual(224, 16, 128, 1, 2, 64), seed + 2)
+    eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=(32, 32), vqgan=SMALL_VQ, cutn=cutn, clip=[cfg_a, cfg_b],
+                       noise_fac=0.1, seed=seed)
+    eng.load_module(E.MOD_VQGAN, vq.state_dict())
+    eng.load_module(E.MOD_CLIP0, clip_a.state_dict())
+    eng.load_module(E.MOD_CLIP1, clip_b.state_dict())
+    eng.finalize()
+    g = torch.Generator().manual_seed(seed + 3)
+    pa = [(torch.randn(1, 64, generator=g), 1.0, float("-inf"))]
+    pb = [(torch.randn(1, 64, generator=g), 0.5, float("-inf")), (torch.randn(1, 64, generator=g), -0.2, float("-inf"))]
+    eng.set_prompts(0, pa[0][0].numpy(), [1.0], [float("-inf")])
+    eng.set_prompts(1, torch.cat([p[0] for p in pb]).numpy(), [0.5, -0.2], [float("-inf")] * 2)
+    idx = torch.randint(1024, (256,), generator=g)
+    z = vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16).clone() + 0.05 * torch.randn(1, 128, 16, 16, generator=g)
+    T = random_transforms(cutn, cs, 6)
+    facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
+    ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip_a, clip_b], [pa, pb], torch.from_numpy(T), cs, "border", 0.3,
+                    facs, noise)
+    zc = z.clone().cuda()
+    losses = np.zeros(3, dtype=np.float32)
+    eng.iterate(zc, 0.05, 1, params=dict(transforms=T, zoom_padding=E.PAD_BORDER, fill=0.3, noise_facs=facs.numpy(),
+                                         noise=noise), losses_out=losses)
+    ref_l = np.array([float(l) for l in ref["losses"]], dtype=np.float32)
+    print(f"[parity] two perceptors: losses engine {losses} oracle {ref_l}")
+    assert np.abs(losses - ref_l).max() < 5e-3
+    e_g, m_g = report("two perceptors z.grad", eng.debug_read("z_grad", z.shape), ref["z_grad"])
+    assert e_g <= 3e-2 * m_g
