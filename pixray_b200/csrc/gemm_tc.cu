@@ -171,13 +171,74 @@ __device__ __forceinline__ void st_f32(float* p, bool vec, int nv, const float (
   }
 }
 
+// Geometry of the store layout for E elements per lane (8: all-fp16 tensors, 4: an fp32 tensor takes part).
+template <int E>
+struct BlockMap {
+  static constexpr int CH = 32 / E;    // 16-byte chunks per 32-column row
+  static constexpr int RPI = 32 / CH;  // rows covered by one warp instruction
+  static constexpr int NIT = 32 / RPI; // iterations per block
+};
+
+// Which input tensor (if any) is prefetched for the block: residual fp32, residual fp16 or the saved pre-activation.
+__device__ __forceinline__ int prefetch_kind(const GemmParams& p) {
+  return p.res_f32 ? 1 : (p.res_f16 ? 2 : (p.act == ACT_QUICKGELU_BWD ? 3 : 0));
+}
+
+// Issue the global loads of the block's input tensor BEFORE the TMEM load / smem transpose, so their DRAM latency
+// overlaps it (a load-use chain per row made the fp32-residual GEMMs latency-bound).
+template <int E>
+__device__ __forceinline__ void prefetch_block(const GemmParams& p, const long long* s_off, int lane, int col_base,
+                                               int col_limit, int kind, uint4 (&pf)[BlockMap<E>::NIT]) {
+  using M = BlockMap<E>;
+  const int chunk = lane % M::CH, rsub = lane / M::CH;
+  const int col = col_base + chunk * E;
+  const bool vec = p.vec_ok && (col_limit - col >= E);
+  if (!vec || kind == 0) return;
+#pragma unroll
+  for (int it = 0; it < M::NIT; ++it) {
+    const long long off_r = s_off[it * M::RPI + rsub];
+    if (off_r < 0) continue;
+    const long long o = off_r + col;
+    if (kind == 1) {
+      if (E == 4) pf[it] = *reinterpret_cast<const uint4*>(p.res_f32 + o);
+    } else {
+      const __half* src = (kind == 2) ? p.res_f16 : p.aux_in;
+      if (E == 8) pf[it] = *reinterpret_cast<const uint4*>(src + o);
+      else {
+        uint2 u = *reinterpret_cast<const uint2*>(src + o);
+        pf[it].x = u.x;
+        pf[it].y = u.y;
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void unpack_pf(const uint4& u, int kind, float (&x)[E]) {
+  if (kind == 1) {
+    x[0] = __uint_as_float(u.x);
+    x[1] = __uint_as_float(u.y);
+    x[2] = __uint_as_float(u.z);
+    x[3] = __uint_as_float(u.w);
+  } else {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < E / 2; ++j) {
+      float2 f = __half22float2(h[j]);
+      x[2 * j] = f.x;
+      x[2 * j + 1] = f.y;
+    }
+  }
+}
+
 // Generic epilogue of one staged 32 x 32 block.  E elements per lane: 8 when every tensor is fp16 (16-byte accesses,
 // 8 rows per warp instruction), 4 when an fp32 tensor takes part (16-byte accesses on the fp32 side, 4 rows).
 template <int E>
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float* tb, const long long* s_off,
-                                               const int* s_row, int lane, int col_base, int col_limit) {
-  constexpr int CH = 32 / E, RPI = 32 / CH;
-  const int chunk = lane % CH, rsub = lane / CH;
+                                               const int* s_row, int lane, int col_base, int col_limit, int kind,
+                                               const uint4 (&pf)[BlockMap<E>::NIT]) {
+  using M = BlockMap<E>;
+  const int chunk = lane % M::CH, rsub = lane / M::CH;
   const int c0 = chunk * E;
   const int col = col_base + c0;
   int nv = col_limit - col;  // col_limit = min(N, end of this tile)
@@ -187,9 +248,9 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float*
 #pragma unroll
   for (int j = 0; j < E; ++j) bias[j] = (p.bias && !p.bias_per_row && j < nv) ? p.bias[col + j] : 0.f;
   if (nv == 0) return;
-#pragma unroll 2
-  for (int it = 0; it < 32 / RPI; ++it) {
-    const int r = it * RPI + rsub;
+#pragma unroll
+  for (int it = 0; it < M::NIT; ++it) {
+    const int r = it * M::RPI + rsub;
     const long long off_r = s_off[r];
     if (off_r < 0) continue;
     const long long o = off_r + col;
@@ -207,19 +268,22 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const float*
       for (int j = 0; j < E; ++j) x[j] = quickgelu(x[j]);
     } else if (p.act == ACT_QUICKGELU_BWD) {
       float u[E];
-      ld_f16<E>(p.aux_in + o, vec, nv, u);
+      if (vec && kind == 3) unpack_pf<E>(pf[it], 3, u);
+      else ld_f16<E>(p.aux_in + o, vec, nv, u);
 #pragma unroll
       for (int j = 0; j < E; ++j) x[j] *= quickgelu_grad(u[j]);
     }
     if (p.res_f32) {
       float t[E];
-      ld_f32<E>(p.res_f32 + o, vec, nv, t);
+      if (vec && kind == 1 && E == 4) unpack_pf<E>(pf[it], 1, t);
+      else ld_f32<E>(p.res_f32 + o, vec, nv, t);
 #pragma unroll
       for (int j = 0; j < E; ++j) x[j] += t[j];
     }
     if (p.res_f16) {
       float t[E];
-      ld_f16<E>(p.res_f16 + o, vec, nv, t);
+      if (vec && kind == 2) unpack_pf<E>(pf[it], 2, t);
+      else ld_f16<E>(p.res_f16 + o, vec, nv, t);
 #pragma unroll
       for (int j = 0; j < E; ++j) x[j] += t[j];
     }
@@ -475,13 +539,23 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
         if (half == 0) epilogue_softmax_bwd(p, tb, s_off, taddr, lane);
       } else {
         const int nslab = (p.block_n + 31) / 32;
+        const int col_limit = min(p.N, t.n0 + p.block_n);
+        const int kind = prefetch_kind(p);
         for (int s = half; s < nslab; s += 2) {
           float v[32];
-          load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
-          stage_rows(tb, v, lane);
-          const int col_limit = min(p.N, t.n0 + p.block_n);
-          if (wide) epilogue_block<4>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit);
-          else epilogue_block<8>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit);
+          if (wide) {
+            uint4 pf[BlockMap<4>::NIT];
+            prefetch_block<4>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
+            load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
+            stage_rows(tb, v, lane);
+            epilogue_block<4>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit, kind, pf);
+          } else {
+            uint4 pf[BlockMap<8>::NIT];
+            prefetch_block<8>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
+            load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
+            stage_rows(tb, v, lane);
+            epilogue_block<8>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit, kind, pf);
+          }
           __syncwarp();
         }
       }

@@ -70,6 +70,7 @@ class B200Engine:
             raise EngineError(f"pxr_create failed ({rc}): {self.lib.pxr_last_error(None).decode()}")
         self.h = h
         self._keep = []
+        self._ext = None  # torch view of the engine's stream (ordering against torch-side producers of z / noise)
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc, what):
@@ -239,6 +240,11 @@ class B200Engine:
         if params is not None:
             p = self._cut_params(params.get("transforms"), params.get("zoom_padding", it % 2),
                                  params.get("fill", 0.0), params.get("noise_facs"), params.get("noise"))
+        # z / noise may have been produced on torch's stream (e.g. an H2D copy still in flight): order the engine's
+        # non-blocking stream after it without a host sync
+        if self._ext is None:
+            self._ext = torch.cuda.ExternalStream(self.stream_ptr())
+        self._ext.wait_stream(torch.cuda.current_stream())
         lp = None if losses_out is None else losses_out.ctypes.data_as(C.c_void_p)
         rc = self.lib.pxr_iterate(self.h, self._p(z), C.c_float(lr), it, None if p is None else C.byref(p), lp)
         self._check(rc, "pxr_iterate")
