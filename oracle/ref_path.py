@@ -464,6 +464,45 @@ def pixel_synth(z, out_hw):
     return clamp_with_grad(F.interpolate(z, size=out_hw, mode="nearest"), 0, 1)
 
 
+# ------------------------------------------------------------------------------------------------ FFT drawer
+
+# aphantasia.image.to_valid_rgb's colour-correlation matrix [UPSTREAM pixray/aphantasia@7e6b3bb, un-vendored]
+_COLOR_SVD_SQRT = ((0.26, 0.09, 0.02), (0.27, 0.00, -0.05), (0.27, -0.09, 0.03))
+
+
+def fft_freq_scale(h, w, decay_power=1.5):
+    """aphantasia fft_image's per-frequency scale [UPSTREAM]: 1 / max(|f|, 4/max(h,w))**decay * sqrt(w*h) on the
+    rfft2 grid (SURVEY.md 8c).  Returns [h, w//2+1] float32."""
+    import numpy as np
+    fy = np.fft.fftfreq(h)[:, None]
+    fx = np.fft.fftfreq(w)[: w // 2 + 1]
+    freqs = np.sqrt(fx * fx + fy * fy)
+    scale = 1.0 / np.maximum(freqs, 4.0 / max(h, w)) ** decay_power
+    scale *= np.sqrt(w * h)
+    return torch.tensor(scale, dtype=torch.float32)
+
+
+def color_matrix(colors=1.5):
+    import numpy as np
+    m = np.asarray(_COLOR_SVD_SQRT, dtype=np.float32)
+    m = m / np.asarray([colors, 1.0, 1.0], dtype=np.float32)
+    m = m / np.max(np.linalg.norm(m, axis=0))
+    return torch.tensor(m, dtype=torch.float32)
+
+
+def fft_synth(spectrum, decay_power=1.5, colors=1.5, contrast=0.9):
+    """FftDrawer.synth, fftdrawer.py:78-84: to_valid_rgb(fft_image(...))(contrast=0.9).
+    spectrum [1, 3, H, W//2+1, 2] (real, imag); returns [1, 3, H, W] in (0, 1)."""
+    _, _, h, w2, _ = spectrum.shape
+    w = (w2 - 1) * 2
+    scaled = fft_freq_scale(h, w, decay_power)[None, None, :, :, None] * spectrum
+    image = torch.fft.irfftn(torch.view_as_complex(scaled.contiguous()), s=(h, w), norm="ortho")
+    image = image * contrast / image.std()
+    m = color_matrix(colors)
+    image = torch.matmul(image.permute(0, 2, 3, 1), m.T).permute(0, 3, 1, 2)
+    return torch.sigmoid(image)
+
+
 # ------------------------------------------------------------------------------------------------ optimiser / loop
 
 

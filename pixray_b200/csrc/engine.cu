@@ -1166,6 +1166,7 @@ void Engine::finalize() {
     reg("irange", irange, 16);
     reg("sums", sums, 16);
     reg("z_grad", z_grad, z_numel * 4);
+    reg("z", z_buf, z_numel * 4);
     reg("minv", minv_dev, (size_t)n_local * 36);
     for (int i = 0; i < cfg.n_clip; ++i) {
       Clip& C = clip[i];

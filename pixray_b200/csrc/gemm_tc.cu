@@ -392,7 +392,10 @@ __device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float*
   }
 }
 
-template <int EPI>  // 0 generic epilogue, 1 fused softmax forward, 2 fused softmax backward
+// EPI: 0 generic epilogue, 1 fused softmax forward, 2 fused softmax backward.  HAS_IN: the generic epilogue reads an
+// input tensor (residual / saved pre-activation) that is prefetched; kept out of the input-free kernel so that one
+// stays lean (the prefetch registers cost the plain GEMMs ~25 %).
+template <int EPI, bool HAS_IN>
 __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ symbol (offset arithmetic only) so smem accesses compile to LDS/STS
@@ -540,18 +543,18 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
       } else {
         const int nslab = (p.block_n + 31) / 32;
         const int col_limit = min(p.N, t.n0 + p.block_n);
-        const int kind = prefetch_kind(p);
+        const int kind = HAS_IN ? prefetch_kind(p) : 0;
         for (int s = half; s < nslab; s += 2) {
           float v[32];
           if (wide) {
             uint4 pf[BlockMap<4>::NIT];
-            prefetch_block<4>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
+            if (HAS_IN) prefetch_block<4>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
             load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
             stage_rows(tb, v, lane);
             epilogue_block<4>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit, kind, pf);
           } else {
             uint4 pf[BlockMap<8>::NIT];
-            prefetch_block<8>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
+            if (HAS_IN) prefetch_block<8>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
             load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
             stage_rows(tb, v, lane);
             epilogue_block<8>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit, kind, pf);
@@ -574,13 +577,16 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  gemm_tc_body<0>(p);
+  gemm_tc_body<0, false>(p);
+}
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_in_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tc_body<0, true>(p);
 }
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_softmax_fwd_kernel(const __grid_constant__ GemmParams p) {
-  gemm_tc_body<1>(p);
+  gemm_tc_body<1, false>(p);
 }
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_softmax_bwd_kernel(const __grid_constant__ GemmParams p) {
-  gemm_tc_body<2>(p);
+  gemm_tc_body<2, false>(p);
 }
 
 // ------------------------------------------------------------------ host side
@@ -716,6 +722,7 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
@@ -819,6 +826,8 @@ void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     gemm_tc_softmax_fwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else if (plan.p.act == ACT_SOFTMAX_BWD)
     gemm_tc_softmax_bwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.res_f32 || plan.p.res_f16 || plan.p.act == ACT_QUICKGELU_BWD)
+    gemm_tc_in_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else
     gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
 }

@@ -185,6 +185,7 @@ def test_adam_clip_and_iterate_small():
         r = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z_ref, [clip], [prompts], torch.from_numpy(T), cs, pad, 0.5,
                       facs, noise)
         z_eng = z_ref.clone().cuda()
+        torch.cuda.synchronize()
         eng.iterate(z_eng, lr, it, params=dict(transforms=T, zoom_padding=it % 2, fill=0.5, noise_facs=facs.numpy(),
                                                noise=noise), losses_out=losses)
         g_eng = eng.debug_read("z_grad", z.shape).cpu()
@@ -205,7 +206,9 @@ def test_adam_clip_and_iterate_small():
                torch.zeros(1, 3, cs, cs))  # magnitude only
         report(f"iter {it} d/d image", eng.debug_read("g_img", (1, 3, 32, 32)) / 4096.0, r["image_grad"])
         # the same inputs through the per-op entry points must give the same gradient as pxr_iterate
-        eng.synth(z_ref)
+        img_it = eng.debug_read("img", (1, 3, 32, 32)).cpu()
+        img_op = eng.synth(z_ref).cpu()
+        report(f"iter {it} image: per-op synth vs pxr_iterate (same engine)", img_it, img_op)
         eng.make_cutouts(None, transforms=T, zoom_padding=it % 2, fill=0.5, noise_facs=facs.numpy(), noise=noise, it=it)
         eng.encode_image(0)
         g_ops = eng.backward().cpu()
