@@ -3,7 +3,8 @@
  * Plain C: pointers and sizes only, no torch types.  Every entry point below replaces one method the reference's
  * Python loop calls each iteration (file:line are relative to the reference checkout, pixray/pixray @ 37b03cf):
  *
- *   pxr_synth          <- drawer.synth(cur_iteration)          pixray.py:1206, vqgan.py:190-195, fast_pixeldrawer.py:89-91
+ *   pxr_synth          <- drawer.synth(cur_iteration)          pixray.py:1206, vqgan.py:190-195, fast_pixeldrawer.py:89-91,
+ *                                                              fftdrawer.py:78-84
  *   pxr_make_cutouts   <- MakeCutouts.forward(out)             pixray.py:445-511 (cached-transform semantics 480-486)
  *   pxr_encode_image   <- CLIP_Base.encode_image(cutouts)      slip.py:21-42, 52-66
  *   pxr_prompt_loss    <- Prompt.forward(embeds) per prompt    pixray.py:268-280 (spherical_dist_loss 262-265)
@@ -29,7 +30,7 @@ extern "C" {
 
 typedef struct pxr_engine* pxr_handle;
 
-enum { PXR_DRAWER_VQGAN = 0, PXR_DRAWER_PIXEL = 1 };
+enum { PXR_DRAWER_VQGAN = 0, PXR_DRAWER_PIXEL = 1, PXR_DRAWER_FFT = 2 };
 enum { PXR_PAD_REFLECTION = 0, PXR_PAD_BORDER = 1, PXR_PAD_ZEROS = 2 };
 enum { PXR_DTYPE_F16 = 0, PXR_DTYPE_BF16 = 1 };
 /* module ids for pxr_load_weight */
@@ -63,7 +64,9 @@ typedef struct {
   int op_dtype;          /* PXR_DTYPE_*: tensor-core operand type (accumulation is always fp32) */
   float grad_scale;      /* backward runs on grad_scale * dL (fp16 range management); 0 = default */
   float beta1, beta2, adam_eps; /* optim.Adam defaults 0.9 / 0.999 / 1e-8 when 0 */
-  int reserved[8];
+  /* fft drawer (fftdrawer.py:16-22, 57-61): fft_image(decay_power) / to_valid_rgb(colors) / image_f(contrast) */
+  float fft_decay, fft_colors, fft_contrast; /* 0 -> 1.5 / 1.5 / 0.9 */
+  int reserved[5];
 } pxr_config;
 
 /* Per-iteration cutout parameters: what kornia's augmentations sample per cutout, made explicit.

@@ -28,7 +28,8 @@ class Config(C.Structure):
         ("noise_fac", C.c_float), ("seed", C.c_uint64),
         ("op_dtype", C.c_int), ("grad_scale", C.c_float),
         ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
-        ("reserved", C.c_int * 8),
+        ("fft_decay", C.c_float), ("fft_colors", C.c_float), ("fft_contrast", C.c_float),
+        ("reserved", C.c_int * 5),
     ]
 
 

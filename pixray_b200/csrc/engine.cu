@@ -246,6 +246,8 @@ class Engine {
   void finalize();
   void build_vqgan();
   void build_pixel();
+  void build_fft();
+  FftPlans* fft = nullptr;
   void build_cutouts();
   void build_clip(int i);
   ConvW load_conv(const std::string& prefix, int cin, int cout, int ks);
@@ -285,6 +287,7 @@ class Engine {
 Engine::~Engine() {
   if (st) cudaStreamSynchronize(st);
   if (comm && Comm::api().destroy) Comm::api().destroy(comm);
+  fft_plans_destroy(fft);
   for (void* p : allocs) cudaFree(p);
   for (int i = 0; i < RING; ++i) {
     if (minv_host[i]) cudaFreeHost(minv_host[i]);
@@ -707,6 +710,56 @@ void Engine::build_pixel() {
   float inv = 1.f / S;
   drawer_fwd.add(1, [=] { pixel_synth(zb, rows, cols, H, Wd, ip, im, cs); });
   drawer_bwd.add(1, [=] { pixel_synth_backward(gi, ip, rows, cols, H, Wd, inv, zg, cs); });
+}
+
+// FftDrawer.synth (fftdrawer.py:78-84): params = rfft2 spectrum [1,3,H,W/2+1,2]; see kernels_fft.cu
+void Engine::build_fft() {
+  const int H = cfg.image_h, Wd = cfg.image_w, W2 = Wd / 2 + 1;
+  if (Wd % 2) throw EngineError(-48, "fft drawer needs an even canvas width");
+  const float decay = cfg.fft_decay > 0 ? cfg.fft_decay : 1.5f, colors = cfg.fft_colors > 0 ? cfg.fft_colors : 1.5f;
+  const float contrast = cfg.fft_contrast > 0 ? cfg.fft_contrast : 0.9f;
+  const char* msg = nullptr;
+  fft = fft_plans_create(H, Wd, st, &msg);
+  if (!fft) throw EngineError(-49, msg ? msg : "cuFFT unavailable");
+  z_numel = (int64_t)3 * H * W2 * 2;
+  // aphantasia fft_image: scale = 1 / max(|f|, 4 / max(h, w)) ** decay * sqrt(w * h) on the rfft2 frequency grid
+  std::vector<float> sc((size_t)H * W2);
+  for (int y = 0; y < H; ++y) {
+    const double fy = (y < (H + 1) / 2 ? y : y - H) / (double)H;  // np.fft.fftfreq
+    for (int x = 0; x < W2; ++x) {
+      const double fx = (x < (Wd + 1) / 2 ? x : x - Wd) / (double)Wd;
+      const double f = std::sqrt(fx * fx + fy * fy);
+      sc[(size_t)y * W2 + x] = (float)(1.0 / std::pow(std::max(f, 4.0 / std::max(H, Wd)), (double)decay) * std::sqrt((double)Wd * H));
+    }
+  }
+  // to_valid_rgb: colour-correlation matrix, first column / colors, normalised by the largest column norm
+  const double base[3][3] = {{0.26, 0.09, 0.02}, {0.27, 0.00, -0.05}, {0.27, -0.09, 0.03}};
+  double m[3][3], maxn = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) m[r][c] = base[r][c] / (c == 0 ? colors : 1.0);
+  for (int c = 0; c < 3; ++c) maxn = std::max(maxn, std::sqrt(m[0][c] * m[0][c] + m[1][c] * m[1][c] + m[2][c] * m[2][c]));
+  std::vector<float> M(9);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) M[r * 3 + c] = (float)(m[r][c] / maxn);
+  float* d_scale = upload(sc);
+  float* d_M = upload(M);
+  const size_t px = (size_t)H * Wd;
+  z_buf = dalloc<float>(z_numel);
+  z_grad = dalloc<float>(z_numel);
+  img = dalloc<float>(3 * px);
+  img_pre = dalloc<float>(3 * px);  // irfft output x (unnormalised)
+  g_img = dalloc<float>(3 * px);
+  float* scaled = dalloc<float>(z_numel);
+  float* g1 = dalloc<float>(3 * px);
+  float* G = dalloc<float>(z_numel);
+  double* part = dalloc<double>(2 * 296 + 8);
+  float* stats = dalloc<float>(4);
+  cudaStream_t cs = st;
+  FftPlans* pl = fft;
+  float *zb = z_buf, *x = img_pre, *im = img, *gi = g_img, *zg = z_grad;
+  const float inv = 1.f / S;
+  drawer_fwd.add(5, [=] { fft_synth_forward(pl, zb, d_scale, d_M, contrast, scaled, x, part, stats, im, cs); });
+  drawer_bwd.add(4, [=] { fft_synth_backward(pl, gi, im, x, d_scale, d_M, contrast, stats, g1, G, part, inv, zg, cs); });
 }
 
 // ===================================================================================================== cutouts
@@ -1144,6 +1197,7 @@ void Engine::finalize() {
   if (finalized) return;
   if (cfg.drawer == PXR_DRAWER_VQGAN) build_vqgan();
   else if (cfg.drawer == PXR_DRAWER_PIXEL) build_pixel();
+  else if (cfg.drawer == PXR_DRAWER_FFT) build_fft();
   else throw EngineError(-47, "unknown drawer kind");
   adam_m = dalloc<float>(z_numel);
   adam_v = dalloc<float>(z_numel);

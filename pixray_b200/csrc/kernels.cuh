@@ -43,6 +43,17 @@ void pixel_synth(const float* z, int rows, int cols, int H, int W, float* pre, f
 void pixel_synth_backward(const float* g_img, const float* pre, int rows, int cols, int H, int W, float inv_scale,
                           float* z_grad, cudaStream_t st);
 
+// ------------------------------------------------------------------ FFT drawer (fftdrawer.py:78-84)
+struct FftPlans;  // cuFFT C2R / R2C plans (3 planes of H x W), resolved through dlopen
+FftPlans* fft_plans_create(int H, int W, cudaStream_t st, const char** err);
+void fft_plans_destroy(FftPlans* p);
+// spectrum [3,H,W/2+1,2] -> img [3,H,W] = sigmoid(M (irfft2(scale*spectrum, ortho) * contrast / std)); x, stats kept
+void fft_synth_forward(FftPlans* pl, const float* spectrum, const float* scale, const float* M, float contrast,
+                       float* scaled, float* x, double* part, float* stats, float* img, cudaStream_t st);
+void fft_synth_backward(FftPlans* pl, const float* g_img, const float* img, const float* x, const float* scale,
+                        const float* M, float contrast, const float* stats, float* g1, float* G, double* part,
+                        float inv_scale, float* z_grad, cudaStream_t st);
+
 // ------------------------------------------------------------------ MakeCutouts (pixray.py:445-511)
 // (AdaptiveAvgPool2d + AdaptiveMaxPool2d) / 2 of the whole image, once (pixray.py:463); argmax kept for backward.
 void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* argmax, cudaStream_t st);
