@@ -1254,9 +1254,9 @@ struct pxr_engine {
 };
 static thread_local std::string g_create_err;
 
-#define PXR_TRY(h, body)                                  \
+#define PXR_TRY(h, ...)                                   \
   try {                                                   \
-    body;                                                 \
+    __VA_ARGS__;                                          \
     return 0;                                             \
   } catch (const EngineError& ex) {                       \
     (h)->e->err = ex.what();                              \

@@ -95,6 +95,16 @@ class B200Engine:
     def _p(t):
         return None if t is None else C.c_void_p(t.data_ptr())
 
+    def _p_inplace(self, t, what):
+        """Raw pointer of a tensor the library reads AND writes in place: it must be a dense, contiguous fp32 CUDA
+        tensor (the C ABI sees plain NCHW memory; a permuted-stride tensor would be silently misread)."""
+        if t is None:
+            return None
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise EngineError(f"{what} must be a contiguous float32 CUDA tensor (got dtype={t.dtype}, "
+                              f"device={t.device}, strides={tuple(t.stride())})")
+        return C.c_void_p(t.data_ptr())
+
     def _new(self, *shape):
         return torch.empty(*shape, device=self.device, dtype=torch.float32)
 
@@ -224,7 +234,7 @@ class B200Engine:
         return g
 
     def step(self, z, lr, it=0):
-        self._check(self.lib.pxr_step(self.h, self._p(z), C.c_float(lr), it), "pxr_step")
+        self._check(self.lib.pxr_step(self.h, self._p_inplace(z, "z"), C.c_float(lr), it), "pxr_step")
         self.sync()
         return z
 
@@ -246,7 +256,7 @@ class B200Engine:
             self._ext = torch.cuda.ExternalStream(self.stream_ptr())
         self._ext.wait_stream(torch.cuda.current_stream())
         lp = None if losses_out is None else losses_out.ctypes.data_as(C.c_void_p)
-        rc = self.lib.pxr_iterate(self.h, self._p(z), C.c_float(lr), it, None if p is None else C.byref(p), lp)
+        rc = self.lib.pxr_iterate(self.h, self._p_inplace(z, "z"), C.c_float(lr), it, None if p is None else C.byref(p), lp)
         self._check(rc, "pxr_iterate")
 
     def debug_read(self, name, shape, dtype=torch.float32):
@@ -257,7 +267,8 @@ class B200Engine:
 
     def profile_iteration(self, z, lr, it):
         out = (C.c_double * 6)()
-        self._check(self.lib.pxr_profile_iteration(self.h, self._p(z), C.c_float(lr), it, out), "pxr_profile_iteration")
+        self._check(self.lib.pxr_profile_iteration(self.h, self._p_inplace(z, "z"), C.c_float(lr), it, out),
+                    "pxr_profile_iteration")
         return dict(gemm_ms=out[0], gemm_launches=int(out[1]), gemm_flops=out[2], other_ms=out[3],
                     other_launches=int(out[4]), total_ms=out[5])
 

@@ -95,7 +95,7 @@ class VqganDrawer(DrawingInterface):
 
     def set_z(self, new_z):
         if self.z is None:
-            self.z = new_z.detach().to(self.session.engine.device, torch.float32).clone()
+            self.z = new_z.detach().to(self.session.engine.device, torch.float32).contiguous().clone()
             return self.z
         with torch.no_grad():
             return self.z.copy_(new_z)

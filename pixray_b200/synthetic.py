@@ -107,8 +107,8 @@ def z0_vqgan(codebook, hw, seed=0):
     """z0 = seeded random codebook rows + small noise."""
     g = torch.Generator().manual_seed(seed)
     idx = torch.randint(codebook.shape[0], (hw[0] * hw[1],), generator=g)
-    z = codebook[idx].T.reshape(1, codebook.shape[1], hw[0], hw[1]).clone()
-    return z + 0.05 * torch.randn(z.shape, generator=g)
+    z = codebook[idx].T.reshape(1, codebook.shape[1], hw[0], hw[1]).contiguous()  # dense NCHW (not a permuted view)
+    return (z + 0.05 * torch.randn(z.shape, generator=g)).contiguous()
 
 
 def vit_fwd_flops(arch):

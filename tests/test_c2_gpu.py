@@ -25,8 +25,8 @@ def build_c2(cutn=64, seed=0):
     prompts = [(torch.randn(1, 512, generator=g), 1.0, float("-inf")), (torch.randn(1, 512, generator=g), 0.1, float("-inf"))]
     eng.set_prompts(0, torch.cat([p[0] for p in prompts]).numpy(), [p[1] for p in prompts], [p[2] for p in prompts])
     idx = torch.randint(16384, (256,), generator=g)
-    z = vq.quantize.embedding.weight[idx].T.reshape(1, 256, 16, 16).clone()
-    z = z + 0.05 * torch.randn(z.shape, generator=g)
+    z = vq.quantize.embedding.weight[idx].T.reshape(1, 256, 16, 16).contiguous()
+    z = (z + 0.05 * torch.randn(z.shape, generator=g)).contiguous()
     return vq, clip, eng, prompts, z
 
 

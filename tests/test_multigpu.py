@@ -41,7 +41,7 @@ def _worker(rank, world, port, out_dir):
     prompts = [(torch.randn(1, 64, generator=g), 1.0, float("-inf")), (torch.randn(1, 64, generator=g), -0.3, float("-inf"))]
     eng.set_prompts(0, torch.cat([p[0] for p in prompts]).numpy(), [1.0, -0.3], [float("-inf")] * 2)
     idx = torch.randint(1024, (256,), generator=g)
-    z = vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16).clone() + 0.05 * torch.randn(1, 128, 16, 16, generator=g)
+    z = (vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16) + 0.05 * torch.randn(1, 128, 16, 16, generator=g)).contiguous()
     T = random_transforms(cutn, cs, 3)
     facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
     zc = z.clone().cuda()

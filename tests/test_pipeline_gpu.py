@@ -53,8 +53,8 @@ def build(cutn=8, image=32, seed=0, clip_cfg=SMALL_CLIP, vq_cfg=SMALL_VQ, n_prom
     f = 2 ** (len(vq_cfg["ch_mult"]) - 1)
     hw = image // f
     idx = torch.randint(vq_cfg["n_embed"], (hw * hw,), generator=g)
-    z = vq.quantize.embedding.weight[idx].T.reshape(1, vq_cfg["z_channels"], hw, hw).clone()
-    z = z + 0.05 * torch.randn(z.shape, generator=g)
+    z = vq.quantize.embedding.weight[idx].T.reshape(1, vq_cfg["z_channels"], hw, hw).contiguous()
+    z = (z + 0.05 * torch.randn(z.shape, generator=g)).contiguous()
     return vq, clip, eng, prompts, z
 
 
@@ -245,7 +245,7 @@ def test_two_perceptors_share_the_cutout_batch():
     eng.set_prompts(0, pa[0][0].numpy(), [1.0], [float("-inf")])
     eng.set_prompts(1, torch.cat([p[0] for p in pb]).numpy(), [0.5, -0.2], [float("-inf")] * 2)
     idx = torch.randint(1024, (256,), generator=g)
-    z = vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16).clone() + 0.05 * torch.randn(1, 128, 16, 16, generator=g)
+    z = (vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16) + 0.05 * torch.randn(1, 128, 16, 16, generator=g)).contiguous()
     T = random_transforms(cutn, cs, 6)
     facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
     ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip_a, clip_b], [pa, pb], torch.from_numpy(T), cs, "border", 0.3,
