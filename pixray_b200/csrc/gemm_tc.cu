@@ -17,6 +17,24 @@ struct TileCoord {
   int tn, tm, z, b0, b1, n0, m0, h0, w0;
 };
 
+__device__ __forceinline__ TileCoord make_coord(const GemmParams& p, int tn, int tm, int z) {
+  TileCoord t;
+  t.tn = tn;
+  t.tm = tm;
+  t.z = z;
+  t.b0 = z % p.nb0;
+  t.b1 = z / p.nb0;
+  t.n0 = tn * p.block_n;
+  t.m0 = tm * GEMM_BLOCK_M;
+  t.h0 = 0;
+  t.w0 = 0;
+  if (p.a_mode == OP_CONV) {
+    t.h0 = (tm / p.tiles_w) * p.tile_h;
+    t.w0 = (tm % p.tiles_w) * p.tile_w;
+  }
+  return t;
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
   TileCoord t;
   t.tn = tile % p.tiles_n;
@@ -574,6 +592,205 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ cta_group::2
+// Two CTAs of a cluster (one TPC) cooperate on a 256 x block_n tile pair: each CTA holds its own 128 rows of A and
+// HALF of the B tile, one tcgen05.mma.cta_group::2 (issued by the rank-0 CTA) consumes both CTAs' shared memory and
+// writes each CTA's 128 x block_n accumulator into its own TMEM.  Per k-block a CTA loads 16 KB + block_n/2 * 128 B
+// instead of 16 KB + block_n * 128 B: with 128 x 256 tiles per SM the single-CTA kernel needs ~96 B/clk/SM of L2->SM
+// traffic at tensor peak, more than the ~43 B/clk/SM the L2 can deliver, so it is L2-bound at < 50 % of peak.
+template <bool HAS_IN>
+__device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int half_n = p.block_n / 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(half_n) * GEMM_BLOCK_K * 2;
+  const uint32_t stage_bytes = A_TILE_BYTES + b_bytes;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* tbuf_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's copy is the live one: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(&empty_bar[i], 1);  // one multicast tcgen05.commit per CTA
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 2 * GEMM_EPI_WARPS);  // leader's copy: epilogue warps of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+  tc_fence_before();
+  cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int pairs_m = (p.tiles_m + 1) / 2;
+  const int total_pairs = pairs_m * p.tiles_n * (p.total_tiles / (p.tiles_m * p.tiles_n));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tp = cluster_id; tp < total_pairs; tp += num_clusters) {
+        const int tn = tp % p.tiles_n, r = tp / p.tiles_n;
+        const TileCoord t = make_coord(p, tn, 2 * (r % pairs_m) + (int)rank, r / pairs_m);
+        const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
+        const int nb = t.n0 + (int)rank * half_n;  // this CTA's half of the B tile
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const int tap = kb / p.k_blocks_per_tap;
+          const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          if (p.a_mode == OP_KMAJOR) {
+            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
+          } else if (p.a_mode == OP_MNMAJOR) {
+            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
+            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+          } else {
+            int dy = 0, dx = 0;
+            if (p.num_taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            }
+            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
+          }
+          if (p.b_mode == OP_KMAJOR) {
+            tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb, kk, nb + tap * p.b_tap_rows, bb0, bb1);
+          } else {
+            for (int j = 0; j < half_n / 64; ++j)
+              tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, nb + 64 * j, kk, bb0, bb1);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(2 * GEMM_BLOCK_M, p.block_n, p.fmt, p.a_mode == OP_MNMAJOR,
+                                            p.b_mode == OP_MNMAJOR);
+      const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+      const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+      const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
+      const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tp = cluster_id; tp < total_pairs; tp += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);  // frees the smem slot in both CTAs
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full_bar[as], 3);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    uint8_t* wbase = reinterpret_cast<uint8_t*>(tbuf_base) + static_cast<size_t>(ew) * TB_WARP_BYTES;
+    float* tb = reinterpret_cast<float*>(wbase);
+    long long* s_off = reinterpret_cast<long long*>(wbase + TB_FLOATS * 4);
+    int* s_row = reinterpret_cast<int*>(wbase + TB_FLOATS * 4 + 32 * 8);
+    const bool wide = (p.out_f32 != nullptr) || (p.res_f32 != nullptr);
+    int it = 0;
+    for (int tp = cluster_id; tp < total_pairs; tp += num_clusters, ++it) {
+      const int tn = tp % p.tiles_n, r = tp / p.tiles_n;
+      const int tm = 2 * (r % pairs_m) + (int)rank;
+      const TileCoord t = make_coord(p, tn, tm, r / pairs_m);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      RowInfo ri = row_info(p, t, q * 32 + lane);
+      if (tm >= p.tiles_m) ri.off = -1;  // odd tile count: the peer's last tile does not exist
+      s_off[lane] = ri.off;
+      s_row[lane] = ri.row;
+      __syncwarp();
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
+      const int nslab = (p.block_n + 31) / 32;
+      const int col_limit = min(p.N, t.n0 + p.block_n);
+      const int kind = HAS_IN ? prefetch_kind(p) : 0;
+      for (int s = half; s < nslab; s += 2) {
+        float v[32];
+        if (wide) {
+          uint4 pf[BlockMap<4>::NIT];
+          if (HAS_IN) prefetch_block<4>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
+          load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
+          stage_rows(tb, v, lane);
+          epilogue_block<4>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit, kind, pf);
+        } else {
+          uint4 pf[BlockMap<8>::NIT];
+          if (HAS_IN) prefetch_block<8>(p, s_off, lane, t.n0 + s * 32, col_limit, kind, pf);
+          load_acc(taddr + s * 32, min(32, p.block_n - s * 32), v);
+          stage_rows(tb, v, lane);
+          epilogue_block<8>(p, tb, s_off, s_row, lane, t.n0 + s * 32, col_limit, kind, pf);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty_bar[as]);
+        else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the leader's MMAs read the peer's smem: nobody leaves before everything is consumed
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tc2_body<false>(p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc2_in_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tc2_body<true>(p);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {

@@ -459,6 +459,71 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
   }
 }
 
+// Any patch size (e.g. ViT-L/14: P = 14): one thread per patch element, coalesced over k.
+__global__ void __launch_bounds__(256) patchify_fwd_generic_kernel(const float* __restrict__ batch,
+                                                                   const float* __restrict__ range, int n, int cs,
+                                                                   int P, int ld, act_t* __restrict__ patches) {
+  const int gp = cs / P, K = 3 * P * P;
+  const long long total = (long long)n * gp * gp * K;
+  const float mn = range[0], R = range[1];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t % K);
+    const long long row = t / K;
+    const int px = (int)(row % gp), py = (int)((row / gp) % gp), b = (int)(row / (gp * gp));
+    const int ix = k % P, iy = (k / P) % P, c = k / (P * P);
+    const float v = batch[(((size_t)b * 3 + c) * cs + py * P + iy) * cs + px * P + ix];
+    patches[(size_t)row * ld + k] = __float2half_rn((((v - mn) / R) - c_clip_mean[c]) / c_clip_std[c]);
+  }
+}
+
+// one thread per batch element (coalesced over x), gathers its gradient from the patch matrix
+__global__ void __launch_bounds__(256) patchify_bwd_generic_kernel(const act_t* __restrict__ g_patches,
+                                                                   const float* __restrict__ batch,
+                                                                   const float* __restrict__ range, int n, int cs,
+                                                                   int P, int ld, int accumulate,
+                                                                   float* __restrict__ g_batch,
+                                                                   float* __restrict__ sums) {
+  const int gp = cs / P;
+  const long long total = (long long)n * 3 * cs * cs;
+  const float mn = range[0], R = range[1];
+  float s1 = 0.f, s2 = 0.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % cs), y = (int)((t / cs) % cs), c = (int)((t / ((long long)cs * cs)) % 3);
+    const int b = (int)(t / ((long long)3 * cs * cs));
+    float g = 0.f;
+    if (y < gp * P && x < gp * P) {
+      const long long row = ((long long)b * gp + y / P) * gp + x / P;
+      const int k = (c * P + y % P) * P + x % P;
+      g = __half2float(g_patches[(size_t)row * ld + k]) / (c_clip_std[c] * R);
+    }
+    s1 += g;
+    s2 += g * (batch[t] - mn) / R;
+    g_batch[t] = accumulate ? g_batch[t] + g : g;
+  }
+  __shared__ float r1[8], r2[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    r1[threadIdx.x >> 5] = s1;
+    r2[threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b2 = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      a += r1[i];
+      b2 += r2[i];
+    }
+    atomicAdd(&sums[0], a);
+    atomicAdd(&sums[1], b2);
+  }
+}
+
 __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, const float* __restrict__ g_batch,
                                                                  const float* __restrict__ range,
                                                                  const int* __restrict__ irange,
@@ -553,11 +618,22 @@ static int patch_grid(long long total) {
 
 void patchify_forward(const float* batch, const float* range, int n, int cs, int P, int ld, act_t* patches,
                       cudaStream_t st) {
+  if (P % 8) {
+    const long long tot = (long long)n * (cs / P) * (cs / P) * 3 * P * P;
+    patchify_fwd_generic_kernel<<<patch_grid(tot), 256, 0, st>>>(batch, range, n, cs, P, ld, patches);
+    return;
+  }
   const long long total = (long long)n * (cs / P) * (cs / P) * (3 * P * P / 8);
   patchify_fwd_kernel<<<patch_grid(total), 256, 0, st>>>(batch, range, n, cs, P, ld, patches);
 }
 void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
                        int accumulate, float* g_batch, float* sums, cudaStream_t st) {
+  if (P % 8) {
+    const long long tot = (long long)n * 3 * cs * cs;
+    patchify_bwd_generic_kernel<<<patch_grid(tot), 256, 0, st>>>(g_patches, batch, range, n, cs, P, ld, accumulate,
+                                                                 g_batch, sums);
+    return;
+  }
   const long long total = (long long)n * (cs / P) * (cs / P) * (3 * P * P / 8);
   patchify_bwd_kernel<<<patch_grid(total), 256, 0, st>>>(g_patches, batch, range, n, cs, P, ld, accumulate, g_batch,
                                                          sums);

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-DRAWER_VQGAN, DRAWER_PIXEL = 0, 1
+DRAWER_VQGAN, DRAWER_PIXEL, DRAWER_FFT = 0, 1, 2
 PAD_REFLECTION, PAD_BORDER = 0, 1
 MOD_VQGAN, MOD_CLIP0, MOD_CLIP1 = 0, 1, 2
 
@@ -19,6 +19,7 @@ VQGAN_F16_16384 = dict(z_channels=256, n_embed=16384, ch=128, ch_mult=(1, 1, 2, 
 CLIP_ARCH = {
     "ViT-B/32": dict(width=768, layers=12, heads=12, patch=32, image_res=224, out_dim=512),
     "ViT-B/16": dict(width=768, layers=12, heads=12, patch=16, image_res=224, out_dim=512),
+    "ViT-L/14": dict(width=1024, layers=24, heads=16, patch=14, image_res=224, out_dim=768),
 }
 
 
@@ -46,6 +47,9 @@ class B200Engine:
                 cfg.ch_mult[i] = m
             f = 2 ** (cfg.n_levels - 1)
             self.z_shape = (1, cfg.z_channels, image_hw[0] // f, image_hw[1] // f)
+        elif drawer == DRAWER_FFT:
+            # FftDrawer params (fftdrawer.py:57-61): rfft2 spectrum [1, 3, H, W/2+1, 2]
+            self.z_shape = (1, 3, image_hw[0], image_hw[1] // 2 + 1, 2)
         else:
             cfg.grid_rows, cfg.grid_cols = grid
             self.z_shape = (1, 3, grid[0], grid[1])
