@@ -147,6 +147,7 @@ class Engine {
     cudaEvent_t a, b;
     double flops;
     int launches;
+    std::string name;
   };
   std::vector<ProfRec> prof;
   void prof_begin(ProfRec& r) {
@@ -160,6 +161,7 @@ class Engine {
         ProfRec r;
         r.flops = l.flops[i];
         r.launches = l.launches[i];
+        r.name = l.names[i];
         prof_begin(r);
         l.ops[i]();
         PXR_CUDA(cudaEventRecord(r.b, st));
@@ -204,10 +206,15 @@ class Engine {
     if (N <= 256 && m_tiles * 1 >= num_sms / 2) return round_up(N, step);
     int best = 0;
     double best_cost = 1e30;
+    // CTA pairs (cta_group::2) schedule 256-row tile pairs over num_sms / 2 clusters
+    const bool paired = m_tiles >= 2 && gemm_default_cta_group() == 2;
+    const long long m_units = paired ? (m_tiles + 1) / 2 : m_tiles;
+    const long long sm_units = paired ? num_sms / 2 : num_sms;
     for (int bn = 256; bn >= 64; bn -= 64) {
       if (bn % step) continue;
-      const long long tiles = m_tiles * ((N + bn - 1) / bn);
-      const long long waves = (tiles + num_sms - 1) / num_sms;
+      if (paired && b_mn && bn % 128) continue;
+      const long long tiles = m_units * ((N + bn - 1) / bn);
+      const long long waves = (tiles + sm_units - 1) / sm_units;
       // narrower tiles re-read A more often and sit closer to the smem-bandwidth limit: mild penalty
       const double cost = (double)waves * (bn + 40.0) * (bn >= 192 ? 1.0 : (bn == 128 ? 1.06 : 1.2));
       if (cost < best_cost - 1e-9) {
@@ -226,7 +233,15 @@ class Engine {
     int rc = gemm_plan_make(plan.get(), A, B, M, N, K, e, bn, fmt, num_sms, buf, sizeof buf);
     if (rc) throw EngineError(rc, std::string("gemm plan: ") + buf);
     cudaStream_t s = st;
-    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops);
+    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label("gemm", *plan, A.mode, B.mode, e));
+  }
+  static std::string gemm_label(const char* kind, const GemmPlan& p, int am, int bm, const GemmEpilogue& e) {
+    char b[256];
+    snprintf(b, sizeof b, "%s M=%d N=%d K=%d batch=%d bn=%d cg=%d A%s B%s act=%d%s%s%s%s%s%s", kind, p.p.M, p.p.N,
+             p.p.num_k_blocks * GEMM_BLOCK_K, p.p.total_tiles / (p.p.tiles_m * p.p.tiles_n), p.p.block_n, p.p.cta_group, am == OP_MNMAJOR ? "mn" : "k", bm == OP_MNMAJOR ? "mn" : "k",
+             e.act, e.bias ? " bias" : "", e.res_f32 ? " res32" : "", e.res_f16 ? " res16" : "", e.out_f32 ? " o32" : "",
+             e.out_f16 ? " o16" : "", e.aux_out ? " aux" : "");
+    return b;
   }
   void add_conv(OpList& l, const act_t* in, int H, int Wd, int cin, const act_t* wt, int cout_pad, int n_out, int ks,
                 const GemmEpilogue& e) {
@@ -238,7 +253,9 @@ class Engine {
                             sizeof buf);
     if (rc) throw EngineError(rc, std::string("conv plan: ") + buf);
     cudaStream_t s = st;
-    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops);
+    char kind[32];
+    snprintf(kind, sizeof kind, "conv%dx%d", ks, ks);
+    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e));
   }
 
   // ------------------------------------------------------------------ build steps
@@ -1477,9 +1494,13 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
     e->profiling = false;
     PXR_CUDA(cudaStreamSynchronize(e->st));
     for (int i = 0; i < 6; ++i) out6[i] = 0;
+    FILE* dump = nullptr;
+    if (const char* path = getenv("PXR_PROFILE_DUMP")) dump = fopen(path, "w");
+    if (dump) fprintf(dump, "op,ms,gflop,launches\n");
     for (auto& r : e->prof) {
       float ms = 0;
       PXR_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      if (dump) fprintf(dump, "%s,%.4f,%.3f,%d\n", r.name.empty() ? "op" : r.name.c_str(), ms, r.flops * 1e-9, r.launches);
       if (r.flops > 0) {
         out6[0] += ms;
         out6[1] += r.launches;
@@ -1492,6 +1513,7 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
       cudaEventDestroy(r.b);
     }
     e->prof.clear();
+    if (dump) fclose(dump);
     float tot = 0;
     PXR_CUDA(cudaEventElapsedTime(&tot, t0, t1));
     out6[5] = tot;

@@ -894,6 +894,29 @@ int encode_operand(CUtensorMap* out, const GemmOperand& op, int rows_box, int fm
 
 bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
+}  // namespace
+
+// Measured on B200 (tests/test_gemm_gpu.py::test_gemm_throughput_report): CTA pairs are within +-8% of single-CTA tiles
+// on the CLIP GEMM shapes (ahead only at K = 3072), so single-CTA tiles stay the default; PXR_GEMM_CTA_GROUP=2 turns
+// pairs on wherever the tile shape allows it.
+int gemm_default_cta_group() {
+  static const int env_cg = [] {
+    const char* e = getenv("PXR_GEMM_CTA_GROUP");
+    return e && atoi(e) == 2 ? 2 : 1;
+  }();
+  return env_cg;
+}
+
+namespace {
+// CTA pairs need (see gemm_tc2_body): a generic epilogue, an even split of the B tile, at least two M tiles.
+int decide_cta_group(const GemmParams& p, const GemmEpilogue& epi, int block_n, int num_sms) {
+  const bool softmax_epi = epi.act == ACT_SOFTMAX || epi.act == ACT_SOFTMAX_BWD;
+  const bool can_pair = !softmax_epi && block_n % 32 == 0 && (p.b_mode != OP_MNMAJOR || block_n % 128 == 0) &&
+                        p.tiles_m >= 2 && num_sms >= 2;
+  const int want = epi.cta_group ? epi.cta_group : gemm_default_cta_group();
+  return (want == 1 || !can_pair) ? 1 : 2;
+}
+
 int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sms, char* err, int errlen) {
   GemmParams& p = plan->p;
   if (block_n < 16 || block_n > 256 || block_n % 16) {
@@ -905,7 +928,7 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
     return -11;
   }
   p.block_n = block_n;
-  const int stage_bytes = A_TILE_BYTES + block_n * GEMM_BLOCK_K * 2;
+  const int stage_bytes = A_TILE_BYTES + (p.cta_group == 2 ? block_n / 2 : block_n) * GEMM_BLOCK_K * 2;
   int stages = (188 * 1024) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
@@ -934,12 +957,21 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
   p.vec_ok = (epi.ldc % 8 == 0) && (epi.bs0 % 8 == 0) && (epi.bs1 % 8 == 0) && aligned16(epi.aux_in) &&
              aligned16(epi.aux_out) && aligned16(epi.res_f32) && aligned16(epi.res_f16) && aligned16(epi.out_f32) &&
              aligned16(epi.out_f16);
-  plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  if (p.cta_group == 2) {
+    const int batches = p.total_tiles / (p.tiles_m * p.tiles_n);
+    const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n * batches;
+    const int max_clusters = num_sms / 2;
+    plan->grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
+  } else {
+    plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  }
   plan->smem_bytes = stages * stage_bytes + 1024 + 256 + GEMM_EPI_WARPS * TB_WARP_BYTES;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc2_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
@@ -976,7 +1008,8 @@ int gemm_plan_make(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
   p.total_tiles = p.tiles_m * p.tiles_n * nb0 * nb1;
   int rc = encode_operand(&p.tma_a, A, GEMM_BLOCK_M, fmt, err, errlen);
   if (rc) return rc;
-  rc = encode_operand(&p.tma_b, B, block_n, fmt, err, errlen);
+  p.cta_group = decide_cta_group(p, epi, block_n, num_sms);
+  rc = encode_operand(&p.tma_b, B, p.cta_group == 2 ? block_n / 2 : block_n, fmt, err, errlen);
   if (rc) return rc;
   plan->flops = 2.0 * M * N * K * nb0 * nb1;
   return finish_plan(plan, epi, block_n, num_sms, err, errlen);
@@ -1030,7 +1063,8 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
     B.ld = c_in;
     B.mn_extent = (long long)p.num_taps * cout_pad;
     B.k_extent = c_in;
-    int rc = encode_operand(&p.tma_b, B, block_n, fmt, err, errlen);
+    p.cta_group = decide_cta_group(p, epi, block_n, num_sms);
+    int rc = encode_operand(&p.tma_b, B, p.cta_group == 2 ? block_n / 2 : block_n, fmt, err, errlen);
     if (rc) return rc;
   }
   plan->flops = 2.0 * H * W * (double)n_out * c_in * p.num_taps * batch;
@@ -1043,6 +1077,10 @@ void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     gemm_tc_softmax_fwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else if (plan.p.act == ACT_SOFTMAX_BWD)
     gemm_tc_softmax_bwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.cta_group == 2 && (plan.p.res_f32 || plan.p.res_f16 || plan.p.act == ACT_QUICKGELU_BWD))
+    gemm_tc2_in_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.cta_group == 2)
+    gemm_tc2_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else if (plan.p.res_f32 || plan.p.res_f16 || plan.p.act == ACT_QUICKGELU_BWD)
     gemm_tc_in_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else

@@ -61,6 +61,7 @@ struct GemmParams {
   __half* out_f16;
   long long ldc, out_bs0, out_bs1;
   int vec_ok;          // 16-byte vector epilogue accesses allowed (alignment checked on host)
+  int cta_group;       // 1: one CTA per tile; 2: CTA pairs (cta_group::2) on 256 x block_n tile pairs
 };
 
 // Host-side description of one operand.
@@ -87,6 +88,7 @@ struct GemmEpilogue {
   __half* out_f16 = nullptr;
   long long ldc = 0, bs0 = 0, bs1 = 0;
   int n_store = 0;  // softmax modes: zero-fill columns [N, n_store)
+  int cta_group = 0;  // 0 = auto, 1 / 2 = force
 };
 
 struct GemmPlan {
@@ -109,5 +111,8 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
                    int num_sms, char* err, int errlen);
 
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+
+// 1 (single-CTA tiles) unless PXR_GEMM_CTA_GROUP=2 asks for CTA pairs where the shape allows them.
+int gemm_default_cta_group();
 
 }  // namespace pxr

@@ -33,6 +33,7 @@ static void fill_epilogue(GemmEpilogue& e, const pxr_test_gemm_desc* d) {
   e.bs0 = d->c_bs0;
   e.bs1 = d->c_bs1;
   e.n_store = d->n_store;
+  e.cta_group = d->cta_group;
 }
 
 extern "C" int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen) {

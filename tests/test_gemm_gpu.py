@@ -19,16 +19,21 @@ def _check(out, ref, tol, name):
     assert err <= tol * max(mag, 1.0), f"{name}: err {err} vs ref max {mag}"
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(300, 256, 192, 128), (128, 64, 64, 64), (197, 197, 64, 208), (1000, 768, 768, 256)])
-def test_gemm_kmajor(M, N, K, bn):
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,N,K,bn", [(300, 256, 192, 128), (128, 64, 64, 64), (197, 197, 64, 208), (1000, 768, 768, 256),
+                                      (1000, 768, 768, 192), (2000, 100, 320, 64)])
+def test_gemm_kmajor(M, N, K, bn, cg):
+    """cg=1: one CTA per 128 x bn tile; cg=2: CTA pairs on 256 x bn tile pairs (tcgen05 cta_group::2) where the shape
+    allows it (falls back to single-CTA tiles otherwise, e.g. one M tile or bn % 32 != 0)."""
     torch.manual_seed(0)
     A, B = _rand(M, K), _rand(N, K)
     out = torch.full((M, N), 7.0, device="cuda")
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=bn, out_f32=out, ldc=N)
-    _check(out, A.float() @ B.float().T, 2e-3, f"kmajor {M}x{N}x{K}")
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=bn, out_f32=out, ldc=N, cta_group=cg)
+    _check(out, A.float() @ B.float().T, 2e-3, f"kmajor cg{cg} {M}x{N}x{K}")
 
 
-def test_gemm_epilogue_bias_gelu_residual():
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_epilogue_bias_gelu_residual(cg):
     torch.manual_seed(1)
     M, N, K = 520, 384, 256
     A, B = _rand(M, K, scale=0.2), _rand(N, K, scale=0.2)
@@ -38,7 +43,7 @@ def test_gemm_epilogue_bias_gelu_residual():
     out32 = torch.zeros(M, N, device="cuda")
     aux = torch.zeros(M, N, device="cuda", dtype=torch.half)
     run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, alpha=0.5, bias=bias, act=1, aux_out=aux, res_f32=res,
-             out_f32=out32, out_f16=out16, ldc=N)
+             out_f32=out32, out_f16=out16, ldc=N, cta_group=cg)
     u = 0.5 * (A.float() @ B.float().T) + bias
     ref = u * torch.sigmoid(1.702 * u) + res
     _check(aux, u, 2e-3, "aux(pre-act)")
@@ -46,7 +51,7 @@ def test_gemm_epilogue_bias_gelu_residual():
     _check(out16, ref, 4e-3, "gelu+res f16")
     # backward epilogue: multiply by quickgelu'(u)
     g = torch.zeros(M, N, device="cuda")
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, act=2, aux_in=aux, out_f32=g, ldc=N)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, act=2, aux_in=aux, out_f32=g, ldc=N, cta_group=cg)
     uf = aux.float()
     s = torch.sigmoid(1.702 * uf)
     ref_g = (A.float() @ B.float().T) * (s * (1 + 1.702 * uf * (1 - s)))
@@ -65,14 +70,15 @@ def test_gemm_bias_per_row_and_tail():
     assert out[:, N:].abs().max().item() == 0.0
 
 
-def test_gemm_mn_major_b():
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_mn_major_b(cg):
     torch.manual_seed(3)
     M, N, K = 260, 256, 200
     A = _rand(M, K)
     Bt = _rand(K, N)  # stored [K, N]: n contiguous -> MN-major B
     out = torch.zeros(M, N, device="cuda")
-    run_gemm(A, Bt, M, N, K, lda=K, b_mode=1, ldb=N, block_n=128, out_f32=out, ldc=N)
-    _check(out, A.float() @ Bt.float(), 2e-3, "MN-major B")
+    run_gemm(A, Bt, M, N, K, lda=K, b_mode=1, ldb=N, block_n=128, out_f32=out, ldc=N, cta_group=cg)
+    _check(out, A.float() @ Bt.float(), 2e-3, f"MN-major B cg{cg}")
 
 
 def test_gemm_mn_major_a():
@@ -88,7 +94,8 @@ def test_gemm_mn_major_a():
     _check(out, At[:, :M].float().T @ Bp[:, :K].float().T, 2e-3, "MN-major A")
 
 
-def test_gemm_both_mn_major_batched_attention_shapes():
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_both_mn_major_batched_attention_shapes(cg):
     """dK = dS^T Q per (image, head): A = dS stored [q, k] (MN-major), B = Q stored [q, d] (MN-major)."""
     torch.manual_seed(5)
     imgs, heads, T, d, ldp = 3, 4, 197, 64, 208
@@ -98,7 +105,7 @@ def test_gemm_both_mn_major_batched_attention_shapes():
     out = torch.zeros(imgs, T, heads * d, device="cuda", dtype=torch.half)
     run_gemm(dS, qkv, T, d, T, a_mode=1, lda=ldp, a_mn=T, a_k=T, b_mode=1, ldb=3 * heads * d, b_mn=d, b_k=T,
              nb0=heads, nb1=imgs, a_bs=(T * ldp, heads * T * ldp), b_bs=(d, T * 3 * heads * d), b_batched=1,
-             block_n=64, out_f16=out, ldc=heads * d, c_bs=(d, T * heads * d))
+             block_n=64, out_f16=out, ldc=heads * d, c_bs=(d, T * heads * d), cta_group=cg)
     q = qkv[..., : heads * d].reshape(imgs, T, heads, d).permute(0, 2, 1, 3).float()
     ref = torch.einsum("bhqk,bhqd->bhkd", dS[..., :T].float(), q).permute(0, 2, 1, 3).reshape(imgs, T, heads * d)
     _check(out, ref, 4e-3, "batched both-MN")
@@ -153,9 +160,10 @@ def test_gemm_fused_softmax_forward_and_backward():
     assert dS[..., T:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("H,W,Cin,Cout,ks,bn", [(32, 32, 128, 128, 3, 128), (16, 16, 256, 512, 3, 128),
                                                   (64, 64, 64, 3, 3, 16), (16, 16, 256, 256, 1, 64)])
-def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn):
+def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn, cg):
     torch.manual_seed(7)
     x = _rand(1, H, W, Cin, scale=0.5)
     w = _rand(Cout, Cin, ks, ks, scale=0.05)
@@ -164,7 +172,7 @@ def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn):
     wt = torch.zeros(ks * ks, cout_pad, Cin, device="cuda", dtype=torch.half)
     wt[:, :Cout] = w.permute(2, 3, 0, 1).reshape(ks * ks, Cout, Cin)
     out = torch.zeros(1, H, W, cout_pad, device="cuda")
-    run_conv(x, wt, Cout, cout_pad, ks, block_n=bn, bias=bias, out_f32=out, ldc=cout_pad)
+    run_conv(x, wt, Cout, cout_pad, ks, block_n=bn, bias=bias, out_f32=out, ldc=cout_pad, cta_group=cg)
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=ks // 2).permute(0, 2, 3, 1)
     _check(out[..., :Cout], ref, 2e-3, f"conv{ks}x{ks} {H}x{W} {Cin}->{Cout}")
 
@@ -174,15 +182,16 @@ def test_gemm_throughput_report():
     torch.manual_seed(8)
     for (M, N, K) in [(12608, 2304, 768), (12608, 3072, 768), (12608, 768, 3072), (12608, 768, 768)]:
         A, B = _rand(M, K, scale=0.1), _rand(N, K, scale=0.1)
-        out = torch.zeros(M, N, device="cuda", dtype=torch.half)
-        run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=256, out_f16=out, ldc=N, repeat=3)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=256, out_f16=out, ldc=N, repeat=20)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
         ref = A.float() @ B.float().T
-        _check(out, ref, 4e-3, f"big {M}x{N}x{K}")
-        print(f"GEMM {M}x{N}x{K}: {ms * 1e3:.1f} us  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+        for cg, bn in [(1, 256), (2, 256), (2, 192)]:
+            out = torch.zeros(M, N, device="cuda", dtype=torch.half)
+            run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=bn, out_f16=out, ldc=N, repeat=3, cta_group=cg)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=bn, out_f16=out, ldc=N, repeat=20, cta_group=cg)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            _check(out, ref, 4e-3, f"big {M}x{N}x{K} cg{cg} bn{bn}")
+            print(f"GEMM {M}x{N}x{K} cta_group {cg} bn {bn}: {ms * 1e3:.1f} us  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
