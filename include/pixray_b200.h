@@ -148,6 +148,7 @@ typedef struct {
   int repeat;
   int n_store; /* fused-softmax epilogues (act 3 / 4): zero-fill columns [N, n_store) */
   int cta_group; /* 0 auto, 1 single-CTA tiles, 2 CTA pairs (tcgen05 cta_group::2) */
+  int tma_epi;   /* 0 auto (tensor-map epilogue when the tensors allow it), -1 force the generic epilogue */
 } pxr_test_gemm_desc;
 
 int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen);

@@ -410,6 +410,90 @@ __device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float*
   }
 }
 
+// TMA producer (one lane): walks this CTA's tiles and fills the stage ring.
+__device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint32_t stage_bytes) {
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int tap = kb / p.k_blocks_per_tap;
+      const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+      uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+      uint8_t* sb = sa + A_TILE_BYTES;
+      if (p.a_mode == OP_KMAJOR) {
+        tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
+      } else if (p.a_mode == OP_MNMAJOR) {
+        tma_load_4d(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
+        tma_load_4d(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+      } else {
+        int dy = 0, dx = 0;
+        if (p.num_taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
+      }
+      if (p.b_mode == OP_KMAJOR) {
+        tma_load_4d(&p.tma_b, &full_bar[stage], sb, kk, t.n0 + tap * p.b_tap_rows, bb0, bb1);
+      } else {
+        for (int j = 0; j < p.block_n / 64; ++j)
+          tma_load_4d(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, t.n0 + 64 * j, kk, bb0, bb1);
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  }
+}
+
+// MMA issuer (one lane): tcgen05.mma over the stage ring into the double-buffered TMEM accumulator.
+__device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                         uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
+                                         uint32_t stage_bytes) {
+  const uint32_t idesc =
+      make_idesc_f16(GEMM_BLOCK_M, p.block_n, p.fmt, p.a_mode == OP_MNMAJOR, p.b_mode == OP_MNMAJOR);
+  // K-major: 8-row groups 1024 B apart; K advance = 32 B inside the swizzled row.
+  // MN-major: 64-wide MN atoms 8192 B apart (LBO), 8-deep K groups 1024 B apart (SBO); K advance = 2048 B.
+  const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+  const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+  const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
+  const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+      const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+      for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+        const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+        const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[stage]);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit(&tmem_full_bar[as]);
+  }
+}
+
 // EPI: 0 generic epilogue, 1 fused softmax forward, 2 fused softmax backward.  HAS_IN: the generic epilogue reads an
 // input tensor (residual / saved pre-activation) that is prefetched; kept out of the input-free kernel so that one
 // stays lean (the prefetch registers cost the plain GEMMs ~25 %).
@@ -452,86 +536,9 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          const int tap = kb / p.k_blocks_per_tap;
-          const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sb = sa + A_TILE_BYTES;
-          if (p.a_mode == OP_KMAJOR) {
-            tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
-          } else if (p.a_mode == OP_MNMAJOR) {
-            tma_load_4d(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
-            tma_load_4d(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
-          } else {
-            int dy = 0, dx = 0;
-            if (p.num_taps == 9) {
-              dy = tap / 3 - 1;
-              dx = tap % 3 - 1;
-            }
-            tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
-          }
-          if (p.b_mode == OP_KMAJOR) {
-            tma_load_4d(&p.tma_b, &full_bar[stage], sb, kk, t.n0 + tap * p.b_tap_rows, bb0, bb1);
-          } else {
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_4d(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, t.n0 + 64 * j, kk, bb0, bb1);
-          }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
+    if (lane == 0) producer_loop(p, smem, full_bar, empty_bar, stage_bytes);
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc =
-          make_idesc_f16(GEMM_BLOCK_M, p.block_n, p.fmt, p.a_mode == OP_MNMAJOR, p.b_mode == OP_MNMAJOR);
-      // K-major: 8-row groups 1024 B apart; K advance = 32 B inside the swizzled row.
-      // MN-major: 64-wide MN atoms 8192 B apart (LBO), 8-deep K groups 1024 B apart (SBO); K advance = 2048 B.
-      const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
-      const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
-      const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
-      const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + A_TILE_BYTES;
-#pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit(&tmem_full_bar[as]);
-      }
-    }
+    if (lane == 0) mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, stage_bytes);
   } else {
     // ------------------------------------------------------------ epilogue (TMEM -> regs -> smem transpose -> global)
     const int ew = warp - 2;          // 0..7
@@ -584,6 +591,240 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ tensor-map epilogue
+// The generic epilogue above is instruction- and latency-bound (ncu: 8 epilogue warps busy ~85 % of the time, tensor pipe
+// 43 % on the plain 12608 x 3072 x 768 GEMM, 20 % with the QuickGELU-backward epilogue): transposing every 32 x 32 block
+// through shared memory costs ~10 instructions per element and every input tensor is a dependent global load.
+// Here each lane keeps its accumulator ROW: it writes 64 contiguous bytes (32 fp16 / 16 fp32 columns) of that row into a
+// 32-row x 64-byte box in shared memory (64B-swizzled, conflict-free), and one lane hands the box to a TMA store.
+// Input tensors (residual, saved pre-activation) come in through TMA loads into the same box, two blocks ahead, and the
+// result overwrites them in place.  ~2 instructions per element, no dependent global loads, clipping by the tensor map.
+constexpr int TE_BUF_BYTES = 2048;  // 32 rows x 64 bytes
+constexpr int TE_BUFS = 4;          // boxes per epilogue warp
+constexpr int TE_WARP_BYTES = TE_BUFS * TE_BUF_BYTES;
+constexpr int TE_BAR_BYTES = 1024;  // barrier block (stage ring, TMEM, per-warp input barriers)
+
+// byte offset of 16-byte chunk c (0..3) of row r (0..31) in a CU_TENSOR_MAP_SWIZZLE_64B box (chunk ^= address bits 7..8)
+__device__ __forceinline__ uint32_t te_off(int r, int c) {
+  return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+  return u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* x) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* wbuf, uint64_t* in_bar,
+                                                  uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
+                                                  int warp, int lane) {
+  constexpr bool F32 = (MODE == TE_RES32);
+  constexpr bool IN = (MODE == TE_GELU_BWD || MODE == TE_RES32 || MODE == TE_RES16);
+  constexpr int BW = F32 ? 16 : 32;  // columns per 64-byte box row
+  const int q = warp & 3;            // TMEM lane quarter
+  const int half = (warp - 2) >> 2;  // the two warps of a quarter alternate over the column blocks
+  uint32_t cnt = 0;                  // blocks this warp has processed: box rotation and input-barrier parity
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const TileCoord t = decode_tile(p, tile);
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    // tensor-map coordinates of this warp's 32 rows: (col, row, b0, b1) or, for conv, (col, w, h, image)
+    int c1, c2, c3;
+    if (p.a_mode == OP_CONV) {
+      c1 = t.w0;
+      c2 = t.h0 + (q * 32) / p.tile_w;
+      c3 = t.z;
+    } else {
+      c1 = t.m0 + q * 32;
+      c2 = t.b0;
+      c3 = t.b1;
+    }
+    // blocks with at least one column inside N; this warp takes s = half, half + 2, ...
+    const int ncols = min(p.N - t.n0, p.block_n);
+    const int nblk = (ncols + BW - 1) / BW;
+    const int my = (nblk - half + 1) / 2;
+    if (IN && lane == 0) {
+      bulk_wait_group_read<1>();
+      for (int j = 0; j < 2 && j < my; ++j) {
+        const uint32_t b = (cnt + j) & 3;
+        mbar_arrive_expect_tx(&in_bar[b], TE_BUF_BYTES);
+        tma_load_4d(&p.tma_d, &in_bar[b], wbuf + b * TE_BUF_BYTES, t.n0 + (half + 2 * j) * BW, c1, c2, c3);
+      }
+    }
+    mbar_wait(&tmem_full_bar[as], aphase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
+    for (int j = 0; j < my; ++j) {
+      const int s = half + 2 * j;
+      const int col = t.n0 + s * BW;
+      const uint32_t k = cnt + j;
+      uint8_t* buf = wbuf + ((MODE == TE_GELU) ? (k & 1) * 2 : (k & 3)) * TE_BUF_BYTES;
+      if (lane == 0) {
+        if (IN) {
+          if (j + 2 < my) {
+            const uint32_t b = (k + 2) & 3;
+            bulk_wait_group_read<1>();  // the box's previous store (two blocks back) has drained
+            mbar_arrive_expect_tx(&in_bar[b], TE_BUF_BYTES);
+            tma_load_4d(&p.tma_d, &in_bar[b], wbuf + b * TE_BUF_BYTES, t.n0 + (s + 4) * BW, c1, c2, c3);
+          }
+        } else if (MODE == TE_GELU) {
+          bulk_wait_group_read<1>();
+        } else {
+          bulk_wait_group_read<3>();
+        }
+      }
+      __syncwarp();
+      // accumulator columns of this row
+      float x[BW];
+      {
+        uint32_t a0[16], a1[16];
+        const bool second = !F32 && (p.block_n - s * BW > 16);  // block_n % 32 == 16: the last block is half wide
+        tmem_ld_x16(taddr + s * BW, a0);
+        if (second) tmem_ld_x16(taddr + s * BW + 16, a1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(a0[i]) * p.alpha;
+        if constexpr (!F32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[16 + i] = second ? __uint_as_float(a1[i]) * p.alpha : 0.f;
+        }
+      }
+      if (p.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+        for (int i = 0; i < BW / 4; ++i) {
+          const float4 b = __ldg(bp + i);
+          x[4 * i] += b.x;
+          x[4 * i + 1] += b.y;
+          x[4 * i + 2] += b.z;
+          x[4 * i + 3] += b.w;
+        }
+      }
+      if (IN) mbar_wait(&in_bar[k & 3], (k >> 2) & 1);
+      if (MODE == TE_F16) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + te_off(lane, c)) = pack8(x + 8 * c);
+      } else if (MODE == TE_GELU) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + te_off(lane, c)) = pack8(x + 8 * c);
+#pragma unroll
+        for (int i = 0; i < BW; ++i) x[i] = quickgelu(x[i]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + TE_BUF_BYTES + te_off(lane, c)) = pack8(x + 8 * c);
+      } else if (MODE == TE_GELU_BWD || MODE == TE_RES16) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4* ptr = reinterpret_cast<uint4*>(buf + te_off(lane, c));
+          float u[8];
+          unpack8(*ptr, u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (MODE == TE_GELU_BWD) x[8 * c + i] *= quickgelu_grad(u[i]);
+            else x[8 * c + i] += u[i];
+          }
+          *ptr = pack8(x + 8 * c);
+        }
+      } else {  // TE_RES32
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4* ptr = reinterpret_cast<float4*>(buf + te_off(lane, c));
+          const float4 r = *ptr;
+          *ptr = make_float4(x[4 * c] + r.x, x[4 * c + 1] + r.y, x[4 * c + 2] + r.z, x[4 * c + 3] + r.w);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (MODE == TE_GELU) {
+          tma_store_4d(&p.tma_d, buf, col, c1, c2, c3);
+          tma_store_4d(&p.tma_c, buf + TE_BUF_BYTES, col, c1, c2, c3);
+        } else {
+          tma_store_4d(&p.tma_c, buf, col, c1, c2, c3);
+        }
+        bulk_commit_group();
+      }
+    }
+    cnt += my;
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+  }
+  if (lane == 0) bulk_wait_group<0>();
+  __syncwarp();
+}
+
+template <int MODE>
+__device__ __forceinline__ void gemm_tce_body(const GemmParams& p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = A_TILE_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
+
+  uint8_t* bar_block = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_block);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* in_bars = reinterpret_cast<uint64_t*>(bar_block + 256);  // [GEMM_EPI_WARPS][TE_BUFS]
+  uint8_t* boxes = bar_block + TE_BAR_BYTES;                          // 1024-byte aligned
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    prefetch_tmap(&p.tma_c);
+    if (MODE != TE_F16) prefetch_tmap(&p.tma_d);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);
+    }
+    for (int i = 0; i < GEMM_EPI_WARPS * TE_BUFS; ++i) mbar_init(&in_bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(p, smem, full_bar, empty_bar, stage_bytes);
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, stage_bytes);
+  } else {
+    const int ew = warp - 2;
+    tma_epilogue_loop<MODE>(p, boxes + static_cast<size_t>(ew) * TE_WARP_BYTES, in_bars + ew * TE_BUFS, tmem_full_bar,
+                            tmem_empty_bar, tmem_base, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -806,6 +1047,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_softmax_bwd_kernel(co
   gemm_tc_body<2, false>(p);
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tce_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tce_body<MODE>(p);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -828,9 +1074,10 @@ void set_err(char* err, int errlen, const char* msg) {
   if (err && errlen > 0) snprintf(err, errlen, "%s", msg);
 }
 
-// 4-D fp16/bf16 tensor map, 128-byte swizzle, zero fill out of bounds.
+// 4-D tensor map, zero fill out of bounds.  fmt 0 = fp16, 1 = bf16, 2 = fp32; operands use the 128-byte swizzle, the
+// epilogue boxes (64-byte rows) the 64-byte swizzle.
 int encode_tmap4(CUtensorMap* out, const void* ptr, int fmt, const uint64_t dims[4], const uint64_t strides_elems[3],
-                 const uint32_t box[4], char* err, int errlen) {
+                 const uint32_t box[4], char* err, int errlen, bool swizzle64 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_err(err, errlen, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -843,7 +1090,7 @@ int encode_tmap4(CUtensorMap* out, const void* ptr, int fmt, const uint64_t dims
     gbox[i] = box[i];
   }
   for (int i = 0; i < 3; ++i) {
-    gstrides[i] = strides_elems[i] * 2;
+    gstrides[i] = strides_elems[i] * (fmt == 2 ? 4 : 2);
     if (gstrides[i] % 16 != 0 || gstrides[i] == 0) {
       set_err(err, errlen, "TMA global stride must be a non-zero multiple of 16 bytes");
       return -2;
@@ -853,9 +1100,11 @@ int encode_tmap4(CUtensorMap* out, const void* ptr, int fmt, const uint64_t dims
     set_err(err, errlen, "TMA global address must be 16-byte aligned");
     return -3;
   }
-  CUresult r = fn(out, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                  const_cast<void*>(ptr), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                          : (fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  CUresult r = fn(out, dt, 4, const_cast<void*>(ptr), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[160];
     snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r,
@@ -917,6 +1166,68 @@ int decide_cta_group(const GemmParams& p, const GemmEpilogue& epi, int block_n, 
   return (want == 1 || !can_pair) ? 1 : 2;
 }
 
+// Tensor-map epilogue (see tma_epilogue_loop) when the epilogue is one of its shapes and every tensor can be described
+// by a tensor map; anything else keeps the generic epilogue.  PXR_GEMM_TMA_EPI=0 disables it globally.
+int decide_tma_epi(const GemmParams& p, const GemmEpilogue& e, int block_n) {
+  static const bool enabled = [] {
+    const char* v = getenv("PXR_GEMM_TMA_EPI");
+    return !(v && atoi(v) == 0);
+  }();
+  if (!enabled || e.tma_epi < 0 || p.cta_group == 2 || e.bias_per_row || p.fmt != 0) return TE_NONE;
+  int mode = TE_NONE;
+  const bool no_res = !e.res_f32 && !e.res_f16;
+  if (e.act == ACT_NONE && e.out_f16 && !e.out_f32 && !e.res_f32 && !e.aux_out) mode = e.res_f16 ? TE_RES16 : TE_F16;
+  else if (e.act == ACT_QUICKGELU && e.aux_out && e.out_f16 && !e.out_f32 && no_res) mode = TE_GELU;
+  else if (e.act == ACT_QUICKGELU_BWD && e.aux_in && e.out_f16 && !e.out_f32 && no_res) mode = TE_GELU_BWD;
+  else if (e.act == ACT_NONE && e.out_f32 && !e.out_f16 && e.res_f32 && !e.res_f16 && !e.aux_out) mode = TE_RES32;
+  if (mode == TE_NONE) return TE_NONE;
+  const int bw = mode == TE_RES32 ? 16 : 32;
+  const int eb = mode == TE_RES32 ? 4 : 2;
+  if (block_n % bw && p.tiles_n != 1) return TE_NONE;  // a partial last block would spill into the next tile's columns
+  if (e.bias && (!aligned16(e.bias) || p.N % bw)) return TE_NONE;
+  if ((e.ldc * eb) % 16 || (e.bs0 * eb) % 16 || (e.bs1 * eb) % 16) return TE_NONE;
+  if (!aligned16(e.out_f16) || !aligned16(e.out_f32) || !aligned16(e.aux_in) || !aligned16(e.aux_out) ||
+      !aligned16(e.res_f32) || !aligned16(e.res_f16))
+    return TE_NONE;
+  if (p.a_mode == OP_CONV && (32 % p.tile_w)) return TE_NONE;
+  // TMA clips the innermost dimension at 16-byte granularity: a ragged N overwrites the columns up to the next 16-byte
+  // boundary (with alpha * 0 when B's out-of-range rows are zero-filled), so they must be padding inside the row pitch
+  const int gran = 16 / eb;
+  if (p.N % gran && (e.ldc < (p.N + gran - 1) / gran * gran || e.bias)) return TE_NONE;
+  return mode;
+}
+
+int encode_epilogue_map(CUtensorMap* out, const void* ptr, bool f32, const GemmParams& p, const GemmEpilogue& e,
+                        char* err, int errlen) {
+  uint64_t dims[4], strides[3];
+  uint32_t box[4];
+  const uint64_t ldc = static_cast<uint64_t>(e.ldc);
+  dims[0] = p.N;
+  box[0] = f32 ? 16 : 32;
+  if (p.a_mode == OP_CONV) {
+    dims[1] = p.conv_W;
+    dims[2] = p.conv_H;
+    dims[3] = p.nb0;
+    strides[0] = ldc;
+    strides[1] = ldc * p.conv_W;
+    strides[2] = ldc * p.conv_W * p.conv_H;
+    box[1] = p.tile_w;
+    box[2] = 32 / p.tile_w;
+    box[3] = 1;
+  } else {
+    const int nb1 = p.total_tiles / (p.tiles_m * p.tiles_n * p.nb0);
+    dims[1] = p.M;
+    dims[2] = p.nb0;
+    dims[3] = nb1;
+    strides[0] = ldc;
+    strides[1] = p.nb0 > 1 ? static_cast<uint64_t>(e.bs0) : ldc * p.M;
+    strides[2] = nb1 > 1 ? static_cast<uint64_t>(e.bs1) : strides[1] * p.nb0;
+    box[1] = 32;
+    box[2] = box[3] = 1;
+  }
+  return encode_tmap4(out, ptr, f32 ? 2 : 0, dims, strides, box, err, errlen, true);
+}
+
 int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sms, char* err, int errlen) {
   GemmParams& p = plan->p;
   if (block_n < 16 || block_n > 256 || block_n % 16) {
@@ -928,8 +1239,23 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
     return -11;
   }
   p.block_n = block_n;
+  p.tma_epi = decide_tma_epi(p, epi, block_n);
+  if (p.tma_epi != TE_NONE) {
+    const bool f32 = p.tma_epi == TE_RES32;
+    int rc = encode_epilogue_map(&p.tma_c, f32 ? static_cast<const void*>(epi.out_f32) : epi.out_f16, f32, p, epi, err,
+                                 errlen);
+    const void* second = p.tma_epi == TE_GELU       ? static_cast<const void*>(epi.aux_out)
+                         : p.tma_epi == TE_GELU_BWD ? static_cast<const void*>(epi.aux_in)
+                         : p.tma_epi == TE_RES32    ? static_cast<const void*>(epi.res_f32)
+                         : p.tma_epi == TE_RES16    ? static_cast<const void*>(epi.res_f16)
+                                                    : nullptr;
+    if (!rc && second) rc = encode_epilogue_map(&p.tma_d, second, f32, p, epi, err, errlen);
+    if (rc) p.tma_epi = TE_NONE;  // a stride the tensor map cannot express: generic epilogue
+  }
   const int stage_bytes = A_TILE_BYTES + (p.cta_group == 2 ? block_n / 2 : block_n) * GEMM_BLOCK_K * 2;
-  int stages = (188 * 1024) / stage_bytes;
+  const int epi_smem = p.tma_epi != TE_NONE ? TE_BAR_BYTES + GEMM_EPI_WARPS * TE_WARP_BYTES
+                                             : 256 + GEMM_EPI_WARPS * TB_WARP_BYTES;
+  int stages = (227 * 1024 - 1024 - epi_smem) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -965,7 +1291,7 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
   } else {
     plan->grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   }
-  plan->smem_bytes = stages * stage_bytes + 1024 + 256 + GEMM_EPI_WARPS * TB_WARP_BYTES;
+  plan->smem_bytes = stages * stage_bytes + 1024 + epi_smem;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -974,6 +1300,11 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
     cudaFuncSetAttribute(gemm_tc2_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tc_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce_kernel<TE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce_kernel<TE_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce_kernel<TE_GELU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce_kernel<TE_RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce_kernel<TE_RES16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   return 0;
 }
@@ -1073,7 +1404,17 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
 }
 
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  if (plan.p.act == ACT_SOFTMAX)
+  if (plan.p.tma_epi == TE_F16)
+    gemm_tce_kernel<TE_F16><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.tma_epi == TE_GELU)
+    gemm_tce_kernel<TE_GELU><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.tma_epi == TE_GELU_BWD)
+    gemm_tce_kernel<TE_GELU_BWD><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.tma_epi == TE_RES32)
+    gemm_tce_kernel<TE_RES32><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.tma_epi == TE_RES16)
+    gemm_tce_kernel<TE_RES16><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+  else if (plan.p.act == ACT_SOFTMAX)
     gemm_tc_softmax_fwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else if (plan.p.act == ACT_SOFTMAX_BWD)
     gemm_tc_softmax_bwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);

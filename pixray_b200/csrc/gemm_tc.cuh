@@ -62,7 +62,14 @@ struct GemmParams {
   long long ldc, out_bs0, out_bs1;
   int vec_ok;          // 16-byte vector epilogue accesses allowed (alignment checked on host)
   int cta_group;       // 1: one CTA per tile; 2: CTA pairs (cta_group::2) on 256 x block_n tile pairs
+  // tensor-map epilogue (tma_epi != TE_NONE): outputs leave through TMA stores of 32-row x 64-byte boxes staged in
+  // shared memory in the accumulator's own row-per-lane layout; input tensors arrive the same way (prefetched)
+  int tma_epi;
+  CUtensorMap tma_c;   // main output (out_f16 / out_f32)
+  CUtensorMap tma_d;   // second tensor: aux_out (TE_GELU), aux_in (TE_GELU_BWD), res_f32 (TE_RES32), res_f16 (TE_RES16)
 };
+
+enum TmaEpi : int { TE_NONE = 0, TE_F16 = 1, TE_GELU = 2, TE_GELU_BWD = 3, TE_RES32 = 4, TE_RES16 = 5 };
 
 // Host-side description of one operand.
 struct GemmOperand {
@@ -89,6 +96,7 @@ struct GemmEpilogue {
   long long ldc = 0, bs0 = 0, bs1 = 0;
   int n_store = 0;  // softmax modes: zero-fill columns [N, n_store)
   int cta_group = 0;  // 0 = auto, 1 / 2 = force
+  int tma_epi = 0;    // 0 = auto (tensor-map epilogue when the tensors allow it), -1 = force the generic epilogue
 };
 
 struct GemmPlan {

@@ -34,6 +34,7 @@ static void fill_epilogue(GemmEpilogue& e, const pxr_test_gemm_desc* d) {
   e.bs1 = d->c_bs1;
   e.n_store = d->n_store;
   e.cta_group = d->cta_group;
+  e.tma_epi = d->tma_epi;
 }
 
 extern "C" int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen) {
