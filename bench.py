@@ -187,12 +187,22 @@ def run_engine(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     vq_sd, clip_sd, prompts, z0 = build_models_cpu(0)
-    # multi-GPU: independent replicas (weak scaling) until the cutout-sharded allreduce lands (DESIGN.md, row e)
-    eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=IMAGE, cutn=CUTN, clip=[E.CLIP_ARCH["ViT-B/16"]], noise_fac=0.1,
-                       seed=rank, device=local_rank)
+    # multi-GPU (DESIGN.md, row e).  "shard" (default): ONE optimisation problem, the 64 cutouts split over the ranks,
+    # drawer replicated, NCCL allreduce of {min, max}, the range-gradient sums and the image gradient -> strong scaling.
+    # "replicas": N independent problems, no collective -> weak scaling.
+    shard = world > 1 and args.parallel == "shard"
+    if shard:
+        eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=IMAGE, cutn=CUTN, clip=[E.CLIP_ARCH["ViT-B/16"]],
+                           noise_fac=0.1, seed=0, device=local_rank, rank=rank, world=world)
+    else:
+        eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=IMAGE, cutn=CUTN, clip=[E.CLIP_ARCH["ViT-B/16"]],
+                           noise_fac=0.1, seed=rank, device=local_rank)
     eng.load_module(E.MOD_VQGAN, vq_sd)
     eng.load_module(E.MOD_CLIP0, clip_sd)
     eng.finalize()
+    if shard:
+        eng.init_comm()
+    jobs = 1 if (shard or world == 1) else world
     eng.set_prompts(0, torch.cat([p[0] for p in prompts]).numpy(), [p[1] for p in prompts], [p[2] for p in prompts])
     z = z0.clone().cuda()
     ext = torch.cuda.ExternalStream(eng.stream_ptr())
@@ -247,18 +257,22 @@ def run_engine(args, rank, world):
     S_flops = 2 * (CUTN * S.vit_fwd_flops(E.CLIP_ARCH["ViT-B/16"]) + S.vqgan_decoder_fwd_flops(E.VQGAN_F16_16384, IMAGE))
     gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
     line = {
-        "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": "iters/sec", "n_gpus": world,
+        "metric": METRIC, "value": jobs * args.steps / (ms * 1e-3), "unit": "iters/sec", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+        "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate",
+        "data": "synthetic",
         "config": {"workload": WORKLOAD, "cutn": CUTN, "image": "256x256", "clip": "ViT-B/16",
-                   "weights": "seeded random (no checkpoints offline)", "parallelism": f"{world} independent replicas",
+                   "weights": "seeded random (no checkpoints offline)",
+                   "parallelism": (f"one problem, {CUTN} cutouts sharded over {world} ranks ({CUTN // world} each), drawer "
+                                   "replicated, NCCL allreduce of min/max + range-gradient sums + image gradient"
+                                   if shard else f"{world} independent replica(s)"),
                    "l2": "per-step working set (saved activations ~3 GB) >> 126 MB L2, no explicit flush",
                    "algorithmic_flops_per_iter": S_flops},
         "clocks": clocks,
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "iters/sec",
+        "e2e": {"value": jobs * args.steps / (ms_e2e * 1e-3), "unit": "iters/sec",
                 "h2d_bytes_per_step": CUTN * 9 * 4, "d2h_bytes_per_step": 64 * 4},
         "gpu_launches": launches,
-        "roofline": {"kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)", "bound": "tensor",
+        "roofline": {"kernel": "gemm_tc*/gemm_tce* (tcgen05 GEMM / implicit-GEMM conv family)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": None,
                      "peak_source": peaks["source"] + ", sustained bf16/f16 GEMM figure",
@@ -281,6 +295,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="shard", choices=["shard", "replicas"],
+                    help="N > 1: shard the cutouts of one problem over the ranks (default) or run N independent replicas")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

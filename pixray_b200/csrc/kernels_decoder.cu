@@ -173,8 +173,6 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict
                                                          const float* __restrict__ beta, int pixels, int C, int swish,
                                                          float* __restrict__ part) {
   __shared__ float acc[GN_G][2];
-  if (threadIdx.x < GN_G * 2) (&acc[0][0])[threadIdx.x] = 0.f;
-  __syncthreads();
   const int vecs = C / 8, cpg = C / GN_G;
   const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = 256 / vecs;
   const int c0 = vc * 8;
@@ -220,16 +218,33 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict
       }
     }
   }
-  if (cpg >= 8) {
-    int g = c0 / cpg;
-    atomicAdd(&acc[g][0], s[0][0] + s[1][0]);
-    atomicAdd(&acc[g][1], s[0][1] + s[1][1]);
-  } else {  // cpg == 4
-    int g = c0 / 4;
-    atomicAdd(&acc[g][0], s[0][0]);
-    atomicAdd(&acc[g][1], s[0][1]);
-    atomicAdd(&acc[g + 1][0], s[1][0]);
-    atomicAdd(&acc[g + 1][1], s[1][1]);
+  // Fixed-order block reduction (no atomics: every rank of the cutout-sharded mode must produce the same bits, and so
+  // must every run): pixel lanes -> channel vector -> group.
+  __shared__ float red[4][256];
+  red[0][threadIdx.x] = s[0][0];
+  red[1][threadIdx.x] = s[0][1];
+  red[2][threadIdx.x] = s[1][0];
+  red[3][threadIdx.x] = s[1][1];
+  __syncthreads();
+  if (pl == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < plane; ++l)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += red[k][l * vecs + vc];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[k][vc] = t[k];  // slot vc belongs to lane pl == 0 of this vector: no hazard
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_G * 2) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float t = 0.f;
+    if (cpg >= 8) {
+      const int vpg = cpg / 8;
+      for (int v = g * vpg; v < (g + 1) * vpg; ++v) t += red[which][v] + red[2 + which][v];
+    } else {  // cpg == 4: a vector holds two groups
+      t = red[(g & 1) * 2 + which][g >> 1];
+    }
+    acc[g][which] = t;
   }
   __syncthreads();
   if (threadIdx.x < GN_G * 2) part[(size_t)blockIdx.x * GN_G * 2 + threadIdx.x] = (&acc[0][0])[threadIdx.x];

@@ -63,7 +63,7 @@ def _worker(rank, world, port, out_dir):
 def test_cutout_sharded_two_ranks(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    r0, r1, ref = (torch.load(tmp_path / n) for n in ("rank0.pt", "rank1.pt", "ref.pt"))
+    r0, r1, ref = (torch.load(tmp_path / n, weights_only=False) for n in ("rank0.pt", "rank1.pt", "ref.pt"))
     assert torch.equal(r0["zg"], r1["zg"]), "replicated drawer backward must be bit-identical across ranks"
     assert torch.equal(r0["z"], r1["z"])
     err = (r0["zg"] - ref["zg"]).abs().max().item()
