@@ -254,6 +254,13 @@ def run_engine(args, rank, world):
         return
     peaks = measured_peaks()
     clocks = sampler.summary()
+    # DRAM bytes per GEMM launch from the committed ncu pass over one iteration (not measurable live without a profiler)
+    traffic, traffic_src = None, None
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp) and world == 1:
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["gemm_dram_bytes_per_launch"], tj["source"]
     S_flops = 2 * (CUTN * S.vit_fwd_flops(E.CLIP_ARCH["ViT-B/16"]) + S.vqgan_decoder_fwd_flops(E.VQGAN_F16_16384, IMAGE))
     gemm_tflops = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
     line = {
@@ -274,7 +281,8 @@ def run_engine(args, rank, world):
         "gpu_launches": launches,
         "roofline": {"kernel": "gemm_tc*/gemm_tce* (tcgen05 GEMM / implicit-GEMM conv family)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": None,
+                     "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write)",
+                     "traffic_source": traffic_src,
                      "peak_source": peaks["source"] + ", sustained bf16/f16 GEMM figure",
                      "launches_per_iter": prof["gemm_launches"], "gemm_ms_per_iter": prof["gemm_ms"],
                      "other_ms_per_iter": prof["other_ms"], "iter_ms_profiled": prof["total_ms"],

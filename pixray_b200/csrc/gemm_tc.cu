@@ -636,7 +636,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* x) {
   }
 }
 
-template <int MODE>
+template <int MODE, bool PAIR>
 __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* wbuf, uint64_t* in_bar,
                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
                                                   int warp, int lane) {
@@ -647,8 +647,27 @@ __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* 
   const int half = (warp - 2) >> 2;  // the two warps of a quarter alternate over the column blocks
   uint32_t cnt = 0;                  // blocks this warp has processed: box rotation and input-barrier parity
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-    const TileCoord t = decode_tile(p, tile);
+  // work items: tiles of this CTA, or (PAIR) this CTA's half of the tile pairs of its cluster
+  uint32_t rank = 0;
+  int w_begin = blockIdx.x, w_step = gridDim.x, w_end = p.total_tiles, pairs_m = 1;
+  if (PAIR) {
+    rank = cluster_ctarank();
+    w_begin = blockIdx.x >> 1;
+    w_step = gridDim.x >> 1;
+    pairs_m = (p.tiles_m + 1) / 2;
+    w_end = pairs_m * p.tiles_n * (p.total_tiles / (p.tiles_m * p.tiles_n));
+  }
+  for (int w = w_begin; w < w_end; w += w_step, ++it) {
+    TileCoord t;
+    bool exists = true;
+    if (PAIR) {
+      const int tn = w % p.tiles_n, r = w / p.tiles_n;
+      const int tm = 2 * (r % pairs_m) + static_cast<int>(rank);
+      t = make_coord(p, tn, tm, r / pairs_m);
+      exists = tm < p.tiles_m;  // odd tile count: the peer's last tile does not exist
+    } else {
+      t = decode_tile(p, w);
+    }
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
     // tensor-map coordinates of this warp's 32 rows: (col, row, b0, b1) or, for conv, (col, w, h, image)
@@ -665,7 +684,7 @@ __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* 
     // blocks with at least one column inside N; this warp takes s = half, half + 2, ...
     const int ncols = min(p.N - t.n0, p.block_n);
     const int nblk = (ncols + BW - 1) / BW;
-    const int my = (nblk - half + 1) / 2;
+    const int my = exists ? (nblk - half + 1) / 2 : 0;
     if (IN && lane == 0) {
       bulk_wait_group_read<1>();
       for (int j = 0; j < 2 && j < my; ++j) {
@@ -770,7 +789,10 @@ __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* 
     cnt += my;
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    if (lane == 0) {
+      if (!PAIR || rank == 0) mbar_arrive(&tmem_empty_bar[as]);
+      else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+    }
   }
   if (lane == 0) bulk_wait_group<0>();
   __syncwarp();
@@ -823,8 +845,8 @@ __device__ __forceinline__ void gemm_tce_body(const GemmParams& p) {
     if (lane == 0) mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, stage_bytes);
   } else {
     const int ew = warp - 2;
-    tma_epilogue_loop<MODE>(p, boxes + static_cast<size_t>(ew) * TE_WARP_BYTES, in_bars + ew * TE_BUFS, tmem_full_bar,
-                            tmem_empty_bar, tmem_base, warp, lane);
+    tma_epilogue_loop<MODE, false>(p, boxes + static_cast<size_t>(ew) * TE_WARP_BYTES, in_bars + ew * TE_BUFS,
+                                   tmem_full_bar, tmem_empty_bar, tmem_base, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -842,6 +864,111 @@ __device__ __forceinline__ void gemm_tce_body(const GemmParams& p) {
 // writes each CTA's 128 x block_n accumulator into its own TMEM.  Per k-block a CTA loads 16 KB + block_n/2 * 128 B
 // instead of 16 KB + block_n * 128 B: with 128 x 256 tiles per SM the single-CTA kernel needs ~96 B/clk/SM of L2->SM
 // traffic at tensor peak, more than the ~43 B/clk/SM the L2 can deliver, so it is L2-bound at < 50 % of peak.
+// Pair geometry shared by the three roles of the cta_group::2 kernels.
+struct PairInfo {
+  uint32_t rank;
+  bool leader;
+  int cluster_id, num_clusters, pairs_m, total_pairs, half_n;
+};
+__device__ __forceinline__ PairInfo pair_info(const GemmParams& p) {
+  PairInfo pi;
+  pi.rank = cluster_ctarank();
+  pi.leader = pi.rank == 0;
+  pi.cluster_id = blockIdx.x >> 1;
+  pi.num_clusters = gridDim.x >> 1;
+  pi.pairs_m = (p.tiles_m + 1) / 2;
+  pi.total_pairs = pi.pairs_m * p.tiles_n * (p.total_tiles / (p.tiles_m * p.tiles_n));
+  pi.half_n = p.block_n / 2;
+  return pi;
+}
+
+__device__ __forceinline__ void producer2_loop(const GemmParams& p, const PairInfo& pi, uint8_t* smem, uint64_t* full_bar,
+                                               uint64_t* empty_bar, uint32_t stage_bytes) {
+  const uint32_t rank = pi.rank;
+  const bool leader = pi.leader;
+  const int cluster_id = pi.cluster_id, num_clusters = pi.num_clusters, pairs_m = pi.pairs_m,
+            total_pairs = pi.total_pairs, half_n = pi.half_n;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tp = cluster_id; tp < total_pairs; tp += num_clusters) {
+    const int tn = tp % p.tiles_n, r = tp / p.tiles_n;
+    const TileCoord t = make_coord(p, tn, 2 * (r % pairs_m) + (int)rank, r / pairs_m);
+    const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
+    const int nb = t.n0 + (int)rank * half_n;  // this CTA's half of the B tile
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int tap = kb / p.k_blocks_per_tap;
+      const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+      uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+      uint8_t* sb = sa + A_TILE_BYTES;
+      if (p.a_mode == OP_KMAJOR) {
+        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
+      } else if (p.a_mode == OP_MNMAJOR) {
+        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
+        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+      } else {
+        int dy = 0, dx = 0;
+        if (p.num_taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
+      }
+      if (p.b_mode == OP_KMAJOR) {
+        tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb, kk, nb + tap * p.b_tap_rows, bb0, bb1);
+      } else {
+        for (int j = 0; j < half_n / 64; ++j)
+          tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, nb + 64 * j, kk, bb0, bb1);
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mma2_loop(const GemmParams& p, const PairInfo& pi, uint8_t* smem, uint64_t* full_bar,
+                                          uint64_t* empty_bar, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+                                          uint32_t tmem_base, uint32_t stage_bytes) {
+  const int cluster_id = pi.cluster_id, num_clusters = pi.num_clusters, total_pairs = pi.total_pairs;
+  const uint32_t idesc = make_idesc_f16(2 * GEMM_BLOCK_M, p.block_n, p.fmt, p.a_mode == OP_MNMAJOR,
+                                        p.b_mode == OP_MNMAJOR);
+  const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+  const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
+  const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
+  const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  for (int tp = cluster_id; tp < total_pairs; tp += num_clusters, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+      const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+      for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+        const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+        const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+        umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit_2sm(&empty_bar[stage], 3);  // frees the smem slot in both CTAs
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit_2sm(&tmem_full_bar[as], 3);
+  }
+}
+
 template <bool HAS_IN>
 __device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
@@ -882,89 +1009,15 @@ __device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int pairs_m = (p.tiles_m + 1) / 2;
-  const int total_pairs = pairs_m * p.tiles_n * (p.total_tiles / (p.tiles_m * p.tiles_n));
+  const PairInfo pinfo = pair_info(p);
+  const int cluster_id = pinfo.cluster_id, num_clusters = pinfo.num_clusters, pairs_m = pinfo.pairs_m,
+            total_pairs = pinfo.total_pairs;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tp = cluster_id; tp < total_pairs; tp += num_clusters) {
-        const int tn = tp % p.tiles_n, r = tp / p.tiles_n;
-        const TileCoord t = make_coord(p, tn, 2 * (r % pairs_m) + (int)rank, r / pairs_m);
-        const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
-        const int nb = t.n0 + (int)rank * half_n;  // this CTA's half of the B tile
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          const int tap = kb / p.k_blocks_per_tap;
-          const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
-          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sb = sa + A_TILE_BYTES;
-          if (p.a_mode == OP_KMAJOR) {
-            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
-          } else if (p.a_mode == OP_MNMAJOR) {
-            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
-            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
-          } else {
-            int dy = 0, dx = 0;
-            if (p.num_taps == 9) {
-              dy = tap / 3 - 1;
-              dx = tap % 3 - 1;
-            }
-            tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
-          }
-          if (p.b_mode == OP_KMAJOR) {
-            tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb, kk, nb + tap * p.b_tap_rows, bb0, bb1);
-          } else {
-            for (int j = 0; j < half_n / 64; ++j)
-              tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, nb + 64 * j, kk, bb0, bb1);
-          }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
+    if (lane == 0) producer2_loop(p, pinfo, smem, full_bar, empty_bar, stage_bytes);
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_f16(2 * GEMM_BLOCK_M, p.block_n, p.fmt, p.a_mode == OP_MNMAJOR,
-                                            p.b_mode == OP_MNMAJOR);
-      const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
-      const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
-      const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
-      const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tp = cluster_id; tp < total_pairs; tp += num_clusters, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + A_TILE_BYTES;
-#pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_2sm(&empty_bar[stage], 3);  // frees the smem slot in both CTAs
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit_2sm(&tmem_full_bar[as], 3);
-      }
-    }
+    if (lane == 0 && leader)
+      mma2_loop(p, pinfo, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, stage_bytes);
   } else {
     const int ew = warp - 2;
     const int q = warp & 3;
@@ -1025,6 +1078,68 @@ __device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
   }
 }
 
+// CTA pairs with the tensor-map epilogue: the pair halves the L2 -> SM operand traffic per FLOP (the single-CTA 128 x 256
+// tile is capped near 45 % of tensor peak by the ~43 B/clk/SM the L2 delivers), the epilogue keeps out of its way.
+template <int MODE>
+__device__ __forceinline__ void gemm_tce2_body(const GemmParams& p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const PairInfo pinfo = pair_info(p);
+  const uint32_t stage_bytes = A_TILE_BYTES + static_cast<uint32_t>(pinfo.half_n) * GEMM_BLOCK_K * 2;
+
+  uint8_t* bar_block = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_block);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* in_bars = reinterpret_cast<uint64_t*>(bar_block + 256);
+  uint8_t* boxes = bar_block + TE_BAR_BYTES;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    prefetch_tmap(&p.tma_c);
+    if (MODE != TE_F16) prefetch_tmap(&p.tma_d);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 2 * GEMM_EPI_WARPS);
+    }
+    for (int i = 0; i < GEMM_EPI_WARPS * TE_BUFS; ++i) mbar_init(&in_bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, static_cast<uint32_t>(p.tmem_cols));
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) producer2_loop(p, pinfo, smem, full_bar, empty_bar, stage_bytes);
+  } else if (warp == 1) {
+    if (lane == 0 && pinfo.leader)
+      mma2_loop(p, pinfo, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, stage_bytes);
+  } else {
+    const int ew = warp - 2;
+    tma_epilogue_loop<MODE, true>(p, boxes + static_cast<size_t>(ew) * TE_WARP_BYTES, in_bars + ew * TE_BUFS,
+                                  tmem_full_bar, tmem_empty_bar, tmem_base, warp, lane);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
   gemm_tc2_body<false>(p);
@@ -1050,6 +1165,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_softmax_bwd_kernel(co
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tce_kernel(const __grid_constant__ GemmParams p) {
   gemm_tce_body<MODE>(p);
+}
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tce2_kernel(const __grid_constant__ GemmParams p) {
+  gemm_tce2_body<MODE>(p);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1173,7 +1293,7 @@ int decide_tma_epi(const GemmParams& p, const GemmEpilogue& e, int block_n) {
     const char* v = getenv("PXR_GEMM_TMA_EPI");
     return !(v && atoi(v) == 0);
   }();
-  if (!enabled || e.tma_epi < 0 || p.cta_group == 2 || e.bias_per_row || p.fmt != 0) return TE_NONE;
+  if (!enabled || e.tma_epi < 0 || e.bias_per_row || p.fmt != 0) return TE_NONE;
   int mode = TE_NONE;
   const bool no_res = !e.res_f32 && !e.res_f16;
   if (e.act == ACT_NONE && e.out_f16 && !e.out_f32 && !e.res_f32 && !e.aux_out) mode = e.res_f16 ? TE_RES16 : TE_F16;
@@ -1305,6 +1425,11 @@ int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sm
     cudaFuncSetAttribute(gemm_tce_kernel<TE_GELU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tce_kernel<TE_RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gemm_tce_kernel<TE_RES16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce2_kernel<TE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce2_kernel<TE_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce2_kernel<TE_GELU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce2_kernel<TE_RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tce2_kernel<TE_RES16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   return 0;
 }
@@ -1403,7 +1528,20 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
   return finish_plan(plan, e, block_n, num_sms, err, errlen);
 }
 
+#define PXR_LAUNCH_TCE2(MODE) \
+  gemm_tce2_kernel<MODE><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p)
+
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  if (plan.p.tma_epi != TE_NONE && plan.p.cta_group == 2) {
+    switch (plan.p.tma_epi) {
+      case TE_F16: PXR_LAUNCH_TCE2(TE_F16); break;
+      case TE_GELU: PXR_LAUNCH_TCE2(TE_GELU); break;
+      case TE_GELU_BWD: PXR_LAUNCH_TCE2(TE_GELU_BWD); break;
+      case TE_RES32: PXR_LAUNCH_TCE2(TE_RES32); break;
+      default: PXR_LAUNCH_TCE2(TE_RES16); break;
+    }
+    return;
+  }
   if (plan.p.tma_epi == TE_F16)
     gemm_tce_kernel<TE_F16><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
   else if (plan.p.tma_epi == TE_GELU)

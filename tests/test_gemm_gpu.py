@@ -177,8 +177,8 @@ def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn, cg):
     _check(out[..., :Cout], ref, 2e-3, f"conv{ks}x{ks} {H}x{W} {Cin}->{Cout}")
 
 
-@pytest.mark.parametrize("te", [0, -1])
-def test_gemm_tensor_map_epilogue_modes(te):
+@pytest.mark.parametrize("te,cg", [(0, 1), (-1, 1), (0, 2)])
+def test_gemm_tensor_map_epilogue_modes(te, cg):
     """The five tensor-map epilogue shapes (te=0: chosen automatically; te=-1: the generic epilogue on the same
     problem) on a GEMM with an M tail, several N tiles and a padded row pitch."""
     torch.manual_seed(21)
@@ -188,42 +188,42 @@ def test_gemm_tensor_map_epilogue_modes(te):
     acc = A.float() @ B.float().T
     # TE_F16 (alpha, bias)
     o = torch.full((M, ld), 3.0, device="cuda", dtype=torch.half)
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, alpha=0.5, bias=bias, out_f16=o, ldc=ld, tma_epi=te)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, alpha=0.5, bias=bias, out_f16=o, ldc=ld, tma_epi=te, cta_group=cg)
     _check(o[:, :N], 0.5 * acc + bias, 3e-3, "f16 out")
     assert (o[:, N:] == 3.0).all(), "columns past N must stay untouched"
     # TE_GELU
     o = torch.zeros(M, ld, device="cuda", dtype=torch.half)
     aux = torch.zeros(M, ld, device="cuda", dtype=torch.half)
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=192, bias=bias, act=1, aux_out=aux, out_f16=o, ldc=ld, tma_epi=te)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=192, bias=bias, act=1, aux_out=aux, out_f16=o, ldc=ld, tma_epi=te, cta_group=cg)
     u = acc + bias
     _check(aux[:, :N], u, 3e-3, "gelu aux")
     _check(o[:, :N], u * torch.sigmoid(1.702 * u), 3e-3, "gelu out")
     # TE_GELU_BWD with an MN-major B (the fc2 dgrad shape)
     Bt = B.t().contiguous()  # [K, N]
     g = torch.zeros(M, ld, device="cuda", dtype=torch.half)
-    run_gemm(A, Bt, M, N, K, lda=K, b_mode=1, ldb=N, block_n=128, act=2, aux_in=aux, out_f16=g, ldc=ld, tma_epi=te)
+    run_gemm(A, Bt, M, N, K, lda=K, b_mode=1, ldb=N, block_n=128, act=2, aux_in=aux, out_f16=g, ldc=ld, tma_epi=te, cta_group=cg)
     uf = aux[:, :N].float()
     sg = torch.sigmoid(1.702 * uf)
     _check(g[:, :N], acc * (sg * (1 + 1.702 * uf * (1 - sg))), 3e-3, "gelu bwd")
     # TE_RES32
     res = torch.randn(M, ld, device="cuda")
     o32 = torch.full((M, ld), 5.0, device="cuda")
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=192, bias=bias, res_f32=res, out_f32=o32, ldc=ld, tma_epi=te)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=192, bias=bias, res_f32=res, out_f32=o32, ldc=ld, tma_epi=te, cta_group=cg)
     _check(o32[:, :N], acc + bias + res[:, :N], 2e-3, "res32")
     assert (o32[:, N:] == 5.0).all()
     # in place (out == res), as the residual stream does
     r2 = res.clone()
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=192, bias=bias, res_f32=r2, out_f32=r2, ldc=ld, tma_epi=te)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=192, bias=bias, res_f32=r2, out_f32=r2, ldc=ld, tma_epi=te, cta_group=cg)
     _check(r2[:, :N], acc + bias + res[:, :N], 2e-3, "res32 in place")
     # TE_RES16
     r16 = _rand(M, ld)
     o = torch.zeros(M, ld, device="cuda", dtype=torch.half)
-    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, res_f16=r16, out_f16=o, ldc=ld, tma_epi=te)
+    run_gemm(A, B, M, N, K, lda=K, ldb=K, block_n=128, res_f16=r16, out_f16=o, ldc=ld, tma_epi=te, cta_group=cg)
     _check(o[:, :N], acc + r16[:, :N].float(), 3e-3, "res16")
 
 
-@pytest.mark.parametrize("te", [0, -1])
-def test_gemm_tensor_map_epilogue_batched_ragged(te):
+@pytest.mark.parametrize("te,cg", [(0, 1), (-1, 1), (0, 2)])
+def test_gemm_tensor_map_epilogue_batched_ragged(te, cg):
     """Attention-score shape: 197 x 197 per (image, head), row pitch 200, rows of one batch must not spill into the next."""
     torch.manual_seed(22)
     imgs, heads, T, d, ldp = 3, 4, 197, 64, 200
@@ -231,7 +231,7 @@ def test_gemm_tensor_map_epilogue_batched_ragged(te):
     S = torch.full((imgs, heads, T, ldp), 9.0, device="cuda", dtype=torch.half)
     run_gemm(qkv, qkv[:, heads * d:], T, T, d, lda=3 * heads * d, ldb=3 * heads * d, nb0=heads, nb1=imgs,
              a_bs=(d, T * 3 * heads * d), b_bs=(d, T * 3 * heads * d), b_batched=1, block_n=208, alpha=0.125, out_f16=S,
-             ldc=ldp, c_bs=(T * ldp, heads * T * ldp), tma_epi=te)
+             ldc=ldp, c_bs=(T * ldp, heads * T * ldp), tma_epi=te, cta_group=cg)
     x = qkv.float().view(imgs, T, 3, heads, d)
     ref = 0.125 * torch.einsum("ithd,ishd->ihts", x[:, :, 0], x[:, :, 1])
     _check(S[..., :T], ref, 3e-3, "batched scores")
@@ -241,9 +241,9 @@ def test_gemm_tensor_map_epilogue_batched_ragged(te):
     assert ((pad == 9.0) | (pad == 0.0)).all()
 
 
-@pytest.mark.parametrize("te", [0, -1])
+@pytest.mark.parametrize("te,cg", [(0, 1), (-1, 1), (0, 2)])
 @pytest.mark.parametrize("H,W,Cin,Cout,bn", [(32, 32, 128, 128, 128), (16, 16, 256, 512, 64), (24, 8, 64, 64, 64)])
-def test_conv_tensor_map_epilogue(H, W, Cin, Cout, bn, te):
+def test_conv_tensor_map_epilogue(H, W, Cin, Cout, bn, te, cg):
     torch.manual_seed(23)
     x = _rand(1, H, W, Cin, scale=0.5)
     w = _rand(Cout, Cin, 3, 3, scale=0.05)
@@ -252,9 +252,9 @@ def test_conv_tensor_map_epilogue(H, W, Cin, Cout, bn, te):
     wt = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous()
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
     out = torch.zeros(1, H, W, Cout, device="cuda", dtype=torch.half)
-    run_conv(x, wt, Cout, Cout, 3, block_n=bn, bias=bias, out_f16=out, ldc=Cout, tma_epi=te)
+    run_conv(x, wt, Cout, Cout, 3, block_n=bn, bias=bias, out_f16=out, ldc=Cout, tma_epi=te, cta_group=cg)
     _check(out, ref, 3e-3, f"conv f16 {H}x{W}")
-    run_conv(x, wt, Cout, Cout, 3, block_n=bn, bias=bias, res_f16=res, out_f16=out, ldc=Cout, tma_epi=te)
+    run_conv(x, wt, Cout, Cout, 3, block_n=bn, bias=bias, res_f16=res, out_f16=out, ldc=Cout, tma_epi=te, cta_group=cg)
     _check(out, ref + res.float(), 3e-3, f"conv res16 {H}x{W}")
 
 
@@ -303,22 +303,23 @@ def test_gemm_epilogue_throughput_report():
     qkv = _rand(M, 2304, scale=0.3)
     S = torch.zeros(64 * 12 * 197, 200, device="cuda", dtype=torch.half)
     cases = {
-        "fc1 bias+gelu+aux": lambda te, r: run_gemm(A768, W1, M, 3072, 768, lda=768, ldb=768, block_n=192, bias=b3072, act=1,
-                                                    aux_out=aux, out_f16=o3072, ldc=3072, repeat=r, tma_epi=te),
-        "fc2 dgrad gelu-bwd (B mn)": lambda te, r: run_gemm(A768, W2, M, 3072, 768, lda=768, b_mode=1, ldb=3072, block_n=192,
-                                                            act=2, aux_in=aux, out_f16=o3072, ldc=3072, repeat=r, tma_epi=te),
-        "fc2 bias+res32": lambda te, r: run_gemm(A3072, W2, M, 768, 3072, lda=3072, ldb=3072, block_n=192, bias=b768,
-                                                 res_f32=res32, out_f32=o32, ldc=768, repeat=r, tma_epi=te),
-        "proj bias+res32": lambda te, r: run_gemm(A768, Wp, M, 768, 768, lda=768, ldb=768, block_n=192, bias=b768,
-                                                  res_f32=res32, out_f32=o32, ldc=768, repeat=r, tma_epi=te),
-        "proj dgrad f16 (B mn)": lambda te, r: run_gemm(A768, Wp, M, 768, 768, lda=768, b_mode=1, ldb=768, block_n=192,
-                                                        out_f16=o768, ldc=768, repeat=r, tma_epi=te),
-        "scores 197x197x64 x768": lambda te, r: run_gemm(qkv, qkv[:, 768:], 197, 197, 64, lda=2304, ldb=2304, nb0=12, nb1=64,
+        "fc1 bias+gelu+aux": lambda te, r, cg=1: run_gemm(A768, W1, M, 3072, 768, lda=768, ldb=768, block_n=192, bias=b3072, act=1,
+                                                    aux_out=aux, out_f16=o3072, ldc=3072, repeat=r, tma_epi=te, cta_group=cg),
+        "fc2 dgrad gelu-bwd (B mn)": lambda te, r, cg=1: run_gemm(A768, W2, M, 3072, 768, lda=768, b_mode=1, ldb=3072, block_n=192,
+                                                            act=2, aux_in=aux, out_f16=o3072, ldc=3072, repeat=r, tma_epi=te, cta_group=cg),
+        "fc2 bias+res32": lambda te, r, cg=1: run_gemm(A3072, W2, M, 768, 3072, lda=3072, ldb=3072, block_n=192, bias=b768,
+                                                 res_f32=res32, out_f32=o32, ldc=768, repeat=r, tma_epi=te, cta_group=cg),
+        "proj bias+res32": lambda te, r, cg=1: run_gemm(A768, Wp, M, 768, 768, lda=768, ldb=768, block_n=192, bias=b768,
+                                                  res_f32=res32, out_f32=o32, ldc=768, repeat=r, tma_epi=te, cta_group=cg),
+        "proj dgrad f16 (B mn)": lambda te, r, cg=1: run_gemm(A768, Wp, M, 768, 768, lda=768, b_mode=1, ldb=768, block_n=192,
+                                                        out_f16=o768, ldc=768, repeat=r, tma_epi=te, cta_group=cg),
+        "scores 197x197x64 x768": lambda te, r, cg=1: run_gemm(qkv, qkv[:, 768:], 197, 197, 64, lda=2304, ldb=2304, nb0=12, nb1=64,
                                                          a_bs=(64, 197 * 2304), b_bs=(64, 197 * 2304), b_batched=1,
                                                          block_n=208, alpha=0.125, out_f16=S, ldc=200,
-                                                         c_bs=(197 * 200, 12 * 197 * 200), repeat=r, tma_epi=te),
+                                                         c_bs=(197 * 200, 12 * 197 * 200), repeat=r, tma_epi=te, cta_group=cg),
     }
     for name, fn in cases.items():
         t_gen = _time(lambda r: fn(-1, r))
         t_tma = _time(lambda r: fn(0, r))
-        print(f"{name:32s} generic {t_gen:7.1f} us   tensor-map {t_tma:7.1f} us")
+        t_pair = _time(lambda r: fn(0, r, 2))
+        print(f"{name:32s} generic {t_gen:7.1f} us   tensor-map {t_tma:7.1f} us   tensor-map + CTA pairs {t_pair:7.1f} us")
