@@ -156,6 +156,11 @@ int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen);
 int pxr_test_conv(const pxr_test_gemm_desc* d, int batch, int H, int W, int c_in, int cout_pad, int ksize, char* err,
                   int errlen);
 
+/* fused ViT attention (attn_tc.cu): forward, and backward when d_o != NULL.  qkv [B*T, 3W], o / d_o [B*T, W],
+ * gqkv [B*T, 3W] fp16 device tensors, lse [B*H*T] fp32; heads are 64 wide (W = 64 H), T <= 256 */
+int pxr_test_attention(const void* qkv, void* o, float* lse, const void* d_o, void* gqkv, int B, int T, int H, int W,
+                       float scale, int repeat, char* err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,571 @@
+// See attn_tc.cuh.  sm_100a only (tcgen05 + TMA + TMEM).
+//
+// Shared-memory operand layouts are the ones gemm_tc.cu uses (and verifies on hardware): every operand tile is a stack
+// of 128-byte rows (64 fp16) with the 128-byte swizzle, 8-row groups 1024 B apart.  A tile loaded as rows = tokens,
+// columns = head channels is at the same time
+//   * a K-major operand whose reduction runs over the channels  (S = Q K^T, dP = dO V^T), and
+//   * an MN-major operand whose reduction runs over the tokens   (O = P V, dQ = dS K, dV = P^T dO, dK = dS^T Q),
+// so Q, K, V and dO are each loaded once per (image, head) and serve every product.  P / dS are written by the
+// softmax threads straight into that layout (chunk index XOR row % 8), one 128 x 64 atom per 64 key columns.
+#include "attn_tc.cuh"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+#include <cstdio>
+#include <mutex>
+
+namespace pxr {
+using namespace ptx;
+
+namespace {
+
+constexpr int ATT_THREADS = 576;  // warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..17 softmax / epilogue
+constexpr int ATT_EPI_WARPS = 16;  // four per TMEM lane quarter: they split the score columns of a row
+constexpr uint32_t KiB = 1024;
+constexpr uint32_t ATOM = 16 * KiB;  // 128 rows x 128 bytes
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint4 pack8h(const float* x) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+  return u;
+}
+// 8 accumulator words (fp32 bit patterns) scaled by `mul` -> 8 fp16
+__device__ __forceinline__ uint4 pack8h_acc(const uint32_t* r, float mul) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(__uint_as_float(r[2 * j]) * mul, __uint_as_float(r[2 * j + 1]) * mul);
+  return u;
+}
+__device__ __forceinline__ void unpack8h(const uint4& u, float* x) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+}
+
+// byte offset of the 8 fp16 starting at column j0 (multiple of 8) of row r in a [128 x n] K-major operand made of
+// 128 x 64 atoms (128-byte swizzle: 16-byte chunk index XOR (row % 8))
+__device__ __forceinline__ uint32_t op_off(int r, int j0) {
+  return static_cast<uint32_t>(j0 >> 6) * ATOM + static_cast<uint32_t>(r) * 128u +
+         (static_cast<uint32_t>(((j0 & 63) >> 3) ^ (r & 7)) << 4);
+}
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return make_smem_desc_sw128(addr, 0, 1024); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo) { return make_smem_desc_sw128(addr, lbo, 1024); }
+
+// Visit the 16-column blocks first, first + step, ... (< nblk) of this thread's accumulator row with the TMEM load of
+// the next block in flight while the current one is processed.  f(regs, blk).
+template <class F>
+__device__ __forceinline__ void for_blocks(uint32_t taddr, int first, int step, int nblk, F&& f) {
+  uint32_t a[16], b[16];
+  int blk = first;
+  if (blk >= nblk) return;
+  tmem_ld_x16(taddr + blk * 16, a);
+  while (true) {
+    tmem_ld_wait();
+    const int nb = blk + step;
+    if (nb < nblk) tmem_ld_x16(taddr + nb * 16, b);
+    f(a, blk);
+    if (nb >= nblk) break;
+    tmem_ld_wait();
+    blk = nb + step;
+    if (blk < nblk) tmem_ld_x16(taddr + blk * 16, a);
+    f(b, nb);
+    if (blk >= nblk) break;
+  }
+}
+
+__device__ __forceinline__ uint32_t kv_slot_bytes(int n_pad) { return (static_cast<uint32_t>(n_pad) * 128u + 1023u) & ~1023u; }
+
+// ------------------------------------------------------------------------------------------------ forward
+// smem: Q (two 128-row tiles) 32 KiB | K | V (n_pad rows each) | P tile 0 | P tile 1 (64 KiB each) | barriers | exchange.
+// TMEM: S tile mt at columns [256 mt, 256 mt + n_pad); O tile mt re-uses the first 64 columns of its S tile.
+// The next pair's Q / K are fetched as soon as both S tiles are complete, its V once both PV products are.
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
+  const int n_mt = p.n_mt, n_pad = p.n_pad, T = p.T;
+  const uint32_t kvb = kv_slot_bytes(n_pad);
+  const uint32_t F_Q = 0, F_K = 32 * KiB, F_V = F_K + kvb, F_P0 = F_V + kvb, F_P1 = F_P0 + 64 * KiB, F_BAR = F_P1 + 64 * KiB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_BAR);
+  uint64_t* bar_qk = bars;        // TMA: Q, K landed
+  uint64_t* bar_v = bars + 1;     // TMA: V landed
+  uint64_t* bar_s = bars + 2;     // both S tiles complete (Q / K consumed)
+  uint64_t* bar_p = bars + 3;     // [2] P tile written by its eight warps
+  uint64_t* bar_o = bars + 5;     // [2] O tile complete (P tile / V consumed)
+  uint64_t* bar_free = bars + 7;  // all epilogue warps done with TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xmax = reinterpret_cast<float*>(smem + F_BAR + 256);  // [2 tiles][2 halves][128 rows]
+  float* xsum = xmax + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tm_q);
+    prefetch_tmap(&p.tm_kv);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(&bar_p[0], 8);
+    mbar_init(&bar_p[1], 8);
+    mbar_init(&bar_o[0], 1);
+    mbar_init(&bar_o[1], 1);
+    mbar_init(bar_free, ATT_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t s_base = smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t kv_bytes = static_cast<uint32_t>(n_pad) * 128u;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item % p.H;
+        if (it > 0) mbar_wait(bar_s, (it - 1) & 1);  // the previous pair's S products have consumed Q and K
+        mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>(n_mt) * ATOM + kv_bytes);
+        for (int mt = 0; mt < n_mt; ++mt) tma_load_4d(&p.tm_q, bar_qk, smem + F_Q + mt * ATOM, h * 64, mt * 128, b, 0);
+        tma_load_4d(&p.tm_kv, bar_qk, smem + F_K, p.W + h * 64, 0, b, 0);
+        if (it > 0)
+          for (int mt = 0; mt < n_mt; ++mt) mbar_wait(&bar_o[mt], (it - 1) & 1);  // ... and its PV products V
+        mbar_arrive_expect_tx(bar_v, kv_bytes);
+        tma_load_4d(&p.tm_kv, bar_v, smem + F_V, 2 * p.W + h * 64, 0, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_f16(128, n_pad, 0, 0, 0);
+      const uint32_t id_pv = make_idesc_f16(128, 64, 0, 0, 1);
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        mbar_wait(bar_qk, it & 1);
+        if (it > 0) mbar_wait(bar_free, (it - 1) & 1);
+        tc_fence_after();
+        for (int mt = 0; mt < n_mt; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + mt * 256, desc_k(s_base + F_Q + mt * ATOM + k * 32), desc_k(s_base + F_K + k * 32), id_s,
+                     k ? 1u : 0u);
+        }
+        umma_commit(bar_s);
+        mbar_wait(bar_v, it & 1);
+        for (int mt = 0; mt < n_mt; ++mt) {
+          mbar_wait(&bar_p[mt], it & 1);
+          tc_fence_after();
+          const uint32_t pb = s_base + (mt ? F_P1 : F_P0);
+          for (int k = 0; k < n_pad / 16; ++k)
+            umma_f16(tmem_base + mt * 256, desc_k(pb + (k >> 2) * ATOM + (k & 3) * 32), desc_mn(s_base + F_V + k * 2048, 8192),
+                     id_pv, k ? 1u : 0u);
+          umma_commit(&bar_o[mt]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, sub = (warp - 2) >> 2;
+    const int mt = sub >> 1, half = sub & 1;  // tile, and which of the two warps sharing this tile's lane quarter
+    const int row = q * 32 + lane;
+    const float sc = p.scale * LOG2E;
+    const int nblk = n_pad / 16;  // 16-column blocks
+    const int pair_bar = 1 + mt * 4 + q;
+    float* my_max = xmax + (mt * 2 + half) * 128 + row;
+    float* other_max = xmax + (mt * 2 + (half ^ 1)) * 128 + row;
+    float* my_sum = xsum + (mt * 2 + half) * 128 + row;
+    float* other_sum = xsum + (mt * 2 + (half ^ 1)) * 128 + row;
+    uint8_t* prow = smem + (mt ? F_P1 : F_P0);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * 256);
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int b = item / p.H, h = item % p.H;
+      if (mt < n_mt) {
+        const int i = mt * 128 + row;
+        mbar_wait(bar_s, it & 1);
+        tc_fence_after();
+        // ---- row maximum (columns split between the two warps of the pair)
+        float m4[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+        for_blocks(taddr, half, 2, nblk, [&](const uint32_t(&r)[16], int blk) {
+          const int c0 = blk * 16;
+          if (c0 + 16 <= T) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < T) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[j]));
+          }
+        });
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        *my_max = mx;
+        named_bar_sync(pair_bar, 64);
+        mx = fmaxf(mx, *other_max);
+        const float mxs = mx * sc;
+        // ---- P~ = exp(S - max) as fp16 into the operand layout; partial row sums
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for_blocks(taddr, half, 2, nblk, [&](const uint32_t(&r)[16], int blk) {
+          const int c0 = blk * 16;
+          const bool full = c0 + 16 <= T;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = ex2_approx(fmaf(__uint_as_float(r[8 * g + j]), sc, -mxs));
+              if (!full && c0 + 8 * g + j >= T) x = 0.f;
+              e[j] = x;
+              s4[j & 3] += x;
+            }
+            *reinterpret_cast<uint4*>(prow + op_off(row, c0 + 8 * g)) = pack8h(e);
+          }
+        });
+        const float sum_part = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        *my_sum = sum_part;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[mt]);
+        // ---- O = (P~ V) / sum : this warp writes 32 of the 64 head channels
+        mbar_wait(&bar_o[mt], it & 1);
+        tc_fence_after();
+        named_bar_sync(pair_bar, 64);
+        const float sum = sum_part + *other_sum;
+        const float inv = __fdividef(1.f, sum);
+        uint32_t o[32];
+        tmem_ld_x32(taddr + half * 32, o);
+        tmem_ld_wait();
+        if (i < T) {
+          __half* dst = p.o + (static_cast<size_t>(b) * T + i) * p.W + h * 64 + half * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) reinterpret_cast<uint4*>(dst)[c] = pack8h_acc(o + 8 * c, inv);
+          if (half == 0) p.lse[(static_cast<size_t>(b) * p.H + h) * T + i] = mx * p.scale + __logf(sum);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// smem: Q 32 KiB (two 128-row tiles) | K | V (n_pad rows each) | dO 32 KiB | PS 64 KiB (P, then dS in place).
+// TMEM: region A = columns [0, 256): S, then dP, then dQ (first 64 columns) of the current 128 query rows;
+//       dK key tile jt at [256 + 64 jt, +64), dV at [384 + 64 jt, +64) -- accumulated over both query tiles.
+// Per query tile:  S -> P (threads) -> {dP, dV += P^T dO} -> dS (threads) -> {dQ, dK += dS^T Q} -> dQ out (threads).
+// The four warps of a TMEM lane quarter split the 32-column blocks of their rows.
+constexpr uint32_t TM_DK = 256, TM_DV = 384;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
+  const int n_mt = p.n_mt, n_pad = p.n_pad, T = p.T;
+  const uint32_t kvb = kv_slot_bytes(n_pad);
+  const uint32_t B_Q = 0, B_K = 32 * KiB, B_V = B_K + kvb, B_DO = B_V + kvb, B_PS = B_DO + 32 * KiB, B_BAR = B_PS + 64 * KiB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BAR);
+  uint64_t* bar_load = bars;        // per pair: Q, K, V, dO landed
+  uint64_t* bar_s = bars + 1;       // per query tile: S complete
+  uint64_t* bar_p = bars + 2;       // P written (16 warps)
+  uint64_t* bar_dp = bars + 3;      // dP complete
+  uint64_t* bar_pfree = bars + 4;   // dV products have consumed P
+  uint64_t* bar_ds = bars + 5;      // dS written (16 warps)
+  uint64_t* bar_dq = bars + 6;      // dQ complete
+  uint64_t* bar_dsfree = bars + 7;  // dK products have consumed dS
+  uint64_t* bar_afree = bars + 8;   // region A read out (16 warps)
+  uint64_t* bar_done = bars + 9;    // per pair: dK / dV read out (16 warps)
+  uint64_t* bar_smem = bars + 10;   // per pair: every product has consumed its operands
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xd = reinterpret_cast<float*>(smem + B_BAR + 256);  // [4 column quarters][128 rows] partial D
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tm_q);
+    prefetch_tmap(&p.tm_kv);
+    prefetch_tmap(&p.tm_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, ATT_EPI_WARPS);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_pfree, 1);
+    mbar_init(bar_ds, ATT_EPI_WARPS);
+    mbar_init(bar_dq, 1);
+    mbar_init(bar_dsfree, 1);
+    mbar_init(bar_afree, ATT_EPI_WARPS);
+    mbar_init(bar_done, ATT_EPI_WARPS);
+    mbar_init(bar_smem, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t s_base = smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = 2u * static_cast<uint32_t>(n_mt) * ATOM + 2u * static_cast<uint32_t>(n_pad) * 128u;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item % p.H;
+        if (it > 0) mbar_wait(bar_smem, (it - 1) & 1);
+        mbar_arrive_expect_tx(bar_load, bytes);
+        for (int mt = 0; mt < n_mt; ++mt) {
+          tma_load_4d(&p.tm_q, bar_load, smem + B_Q + mt * ATOM, h * 64, mt * 128, b, 0);
+          tma_load_4d(&p.tm_do, bar_load, smem + B_DO + mt * ATOM, h * 64, mt * 128, b, 0);
+        }
+        tma_load_4d(&p.tm_kv, bar_load, smem + B_K, p.W + h * 64, 0, b, 0);
+        tma_load_4d(&p.tm_kv, bar_load, smem + B_V, 2 * p.W + h * 64, 0, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc_f16(128, n_pad, 0, 0, 0);   // S, dP: both operands K-major
+      const uint32_t id_dq = make_idesc_f16(128, 64, 0, 0, 1);     // dQ = dS K: A K-major, B MN-major
+      const uint32_t id_t = make_idesc_f16(128, 64, 0, 1, 1);      // dV = P^T dO, dK = dS^T Q: both MN-major
+      const uint32_t tA = tmem_base;
+      int it = 0, cnt = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        mbar_wait(bar_load, it & 1);
+        if (it > 0) mbar_wait(bar_done, (it - 1) & 1);
+        tc_fence_after();
+        for (int mt = 0; mt < n_mt; ++mt, ++cnt) {
+          if (cnt > 0) {
+            mbar_wait(bar_afree, (cnt - 1) & 1);
+            tc_fence_after();
+          }
+          const int rows_left = T - mt * 128;
+          const int ksi = rows_left >= 128 ? 8 : (rows_left + 15) / 16;  // 16-row reduction steps over this tile's queries
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tA, desc_k(s_base + B_Q + mt * ATOM + k * 32), desc_k(s_base + B_K + k * 32), id_s, k ? 1u : 0u);
+          umma_commit(bar_s);
+          mbar_wait(bar_p, cnt & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tA, desc_k(s_base + B_DO + mt * ATOM + k * 32), desc_k(s_base + B_V + k * 32), id_s, k ? 1u : 0u);
+          umma_commit(bar_dp);
+          for (int jt = 0; jt < n_mt; ++jt)
+            for (int ks = 0; ks < ksi; ++ks)
+              umma_f16(tmem_base + TM_DV + jt * 64, desc_mn(s_base + B_PS + 2 * jt * ATOM + ks * 2048, ATOM),
+                       desc_mn(s_base + B_DO + mt * ATOM + ks * 2048, 8192), id_t, (mt | ks) ? 1u : 0u);
+          umma_commit(bar_pfree);
+          mbar_wait(bar_ds, cnt & 1);
+          tc_fence_after();
+          for (int k = 0; k < n_pad / 16; ++k)
+            umma_f16(tA, desc_k(s_base + B_PS + (k >> 2) * ATOM + (k & 3) * 32), desc_mn(s_base + B_K + k * 2048, 8192),
+                     id_dq, k ? 1u : 0u);
+          umma_commit(bar_dq);
+          for (int jt = 0; jt < n_mt; ++jt)
+            for (int ks = 0; ks < ksi; ++ks)
+              umma_f16(tmem_base + TM_DK + jt * 64, desc_mn(s_base + B_PS + 2 * jt * ATOM + ks * 2048, ATOM),
+                       desc_mn(s_base + B_Q + mt * ATOM + ks * 2048, 8192), id_t, (mt | ks) ? 1u : 0u);
+          umma_commit(bar_dsfree);
+        }
+        umma_commit(bar_smem);
+      }
+    }
+  } else {
+    const int q = warp & 3, cq = (warp - 2) >> 2;  // lane quarter; which of its four warps (column blocks cq, cq + 4)
+    const int row = q * 32 + lane;
+    const float sc = p.scale * LOG2E;
+    const int nblk = n_pad / 16;  // 16-column blocks
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* ps = smem + B_PS;
+    int it = 0, cnt = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int b = item / p.H, h = item % p.H;
+      mbar_wait(bar_load, it & 1);
+      for (int mt = 0; mt < n_mt; ++mt, ++cnt) {
+        const int i = mt * 128 + row;
+        const bool valid = i < T;
+        // D_i = dO_i . O_i : each of the quarter's four warps takes 16 of the 64 channels
+        float dpart = 0.f;
+        float lse2 = 3.0e38f;  // invalid rows: exp2(x - huge) = 0
+        if (valid) {
+          lse2 = p.lse[(static_cast<size_t>(b) * p.H + h) * T + i] * LOG2E;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.o + (static_cast<size_t>(b) * T + i) * p.W + h * 64);
+          const uint8_t* drow = smem + B_DO + mt * ATOM;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float a[8], g[8];
+            unpack8h(__ldg(orow + 2 * cq + c), a);
+            unpack8h(*reinterpret_cast<const uint4*>(drow + op_off(row, 8 * (2 * cq + c))), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dpart += a[j] * g[j];
+          }
+        }
+        xd[cq * 128 + row] = dpart;
+        named_bar_sync(1 + q, 128);
+        const float D = (xd[row] + xd[128 + row]) + (xd[256 + row] + xd[384 + row]);
+        mbar_wait(bar_s, cnt & 1);
+        tc_fence_after();
+        if (mt > 0) mbar_wait(bar_dsfree, (cnt - 1) & 1);  // the previous tile's dS is consumed: PS may be rewritten
+        for_blocks(lane_addr, cq, 4, nblk, [&](const uint32_t(&r)[16], int blk) {
+          const int c0 = blk * 16;
+          const bool full = c0 + 16 <= T;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = ex2_approx(fmaf(__uint_as_float(r[8 * g + j]), sc, -lse2));
+              if (!full && c0 + 8 * g + j >= T) x = 0.f;
+              e[j] = x;
+            }
+            *reinterpret_cast<uint4*>(ps + op_off(row, c0 + 8 * g)) = pack8h(e);
+          }
+        });
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+        // ---- dS = scale * P * (dP - D), in place over P
+        mbar_wait(bar_dp, cnt & 1);
+        tc_fence_after();
+        mbar_wait(bar_pfree, cnt & 1);
+        for_blocks(lane_addr, cq, 4, nblk, [&](const uint32_t(&r)[16], int blk) {
+          const int c0 = blk * 16;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4* ptr = reinterpret_cast<uint4*>(ps + op_off(row, c0 + 8 * g));
+            float e[8];
+            unpack8h(*ptr, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = p.scale * e[j] * (__uint_as_float(r[8 * g + j]) - D);
+            *ptr = pack8h(e);
+          }
+        });
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ds);
+        // ---- dQ rows out (this warp: 16 of the 64 head channels)
+        mbar_wait(bar_dq, cnt & 1);
+        tc_fence_after();
+        {
+          uint32_t u[16];
+          tmem_ld_x16(lane_addr + cq * 16, u);
+          tmem_ld_wait();
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.gqkv + (static_cast<size_t>(b) * T + i) * 3 * p.W + h * 64 + cq * 16);
+            dst[0] = pack8h_acc(u, 1.f);
+            dst[1] = pack8h_acc(u + 8, 1.f);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afree);
+      }
+      // ---- dK (cq 0, 1) / dV (cq 2, 3) rows of key tile cq & 1
+      mbar_wait(bar_dsfree, (cnt - 1) & 1);
+      tc_fence_after();
+      {
+        const int jt = cq & 1, which = cq >> 1;
+        if (jt < n_mt) {
+          const int j = jt * 128 + row;
+          const uint32_t src = lane_addr + (which ? TM_DV : TM_DK) + jt * 64;
+          uint4* dst = reinterpret_cast<uint4*>(p.gqkv + (static_cast<size_t>(b) * T + (j < T ? j : 0)) * 3 * p.W + (which + 1) * p.W + h * 64);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t a0[32];
+            tmem_ld_x32(src + hh * 32, a0);
+            tmem_ld_wait();
+            if (j < T) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) dst[hh * 4 + c] = pack8h_acc(a0 + 8 * c, 1.f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_done);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int fwd_smem_bytes(int n_pad) { return 32 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 128 * 1024 + 256 + 4096 + 1024; }
+int bwd_smem_bytes(int n_pad) { return 64 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 64 * 1024 + 256 + 2048 + 1024; }
+
+}  // namespace
+
+// T <= 240: the forward keeps Q, K, V and both P tiles resident (<= 227 KiB of shared memory)
+bool attn_supported(int T, int head_dim, int W) { return head_dim == 64 && T >= 1 && T <= 240 && W % 64 == 0; }
+
+int attn_plan_make(AttnPlan* plan, const __half* qkv, __half* o, const __half* d_o, __half* gqkv, float* lse, int B,
+                   int T, int H, int W, float scale, int num_sms, char* err, int errlen) {
+  *plan = AttnPlan{};
+  if (!attn_supported(T, W / H, W)) {
+    if (err && errlen > 0) snprintf(err, errlen, "fused attention needs 64-wide heads and T <= 240");
+    return -1;
+  }
+  AttnParams& p = plan->p;
+  p.T = T;
+  p.n_pad = (T + 15) / 16 * 16;
+  p.H = H;
+  p.B = B;
+  p.W = W;
+  p.n_mt = (T + 127) / 128;
+  p.items = B * H;
+  p.scale = scale;
+  p.o = o;
+  p.lse = lse;
+  p.gqkv = gqkv;
+  const uint64_t qd[4] = {(uint64_t)3 * W, (uint64_t)T, (uint64_t)B, 1};
+  const uint64_t qs[3] = {(uint64_t)3 * W, (uint64_t)T * 3 * W, (uint64_t)T * 3 * W * B};
+  const uint32_t box_q[4] = {64, 128, 1, 1};
+  const uint32_t box_kv[4] = {64, (uint32_t)p.n_pad, 1, 1};
+  int rc = tmap_encode_4d(&p.tm_q, qkv, 0, qd, qs, box_q, err, errlen);
+  if (!rc) rc = tmap_encode_4d(&p.tm_kv, qkv, 0, qd, qs, box_kv, err, errlen);
+  if (!rc && d_o) {
+    const uint64_t dd[4] = {(uint64_t)W, (uint64_t)T, (uint64_t)B, 1};
+    const uint64_t ds[3] = {(uint64_t)W, (uint64_t)T * W, (uint64_t)T * W * B};
+    rc = tmap_encode_4d(&p.tm_do, d_o, 0, dd, ds, box_q, err, errlen);
+  }
+  if (rc) return rc;
+  plan->grid = p.items < num_sms ? p.items : num_sms;
+  plan->smem_fwd = fwd_smem_bytes(p.n_pad);
+  plan->smem_bwd = bwd_smem_bytes(p.n_pad);
+  const double tt = (double)T * T * 64 * 2 * p.items;
+  plan->flops_fwd = 2 * tt;  // QK^T, PV
+  plan->flops_bwd = 4 * tt;  // dP, dQ, dK, dV (the recomputed S is not algorithmic work)
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(240));
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(240));
+  });
+  return 0;
+}
+
+void attn_forward_launch(const AttnPlan& plan, cudaStream_t st) {
+  attn_fwd_kernel<<<plan.grid, ATT_THREADS, plan.smem_fwd, st>>>(plan.p);
+}
+void attn_backward_launch(const AttnPlan& plan, cudaStream_t st) {
+  attn_bwd_kernel<<<plan.grid, ATT_THREADS, plan.smem_bwd, st>>>(plan.p);
+}
+
+}  // namespace pxr

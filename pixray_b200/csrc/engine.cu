@@ -8,7 +8,9 @@
 //   -> [allreduce z.grad] -> Adam -> clip_z
 #include "engine.cuh"
 #include "comm.cuh"
+#include "attn_tc.cuh"
 #include "transforms.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -29,6 +31,8 @@ class Engine {
   int fmt = 0;
   float S = 4096.f;  // grad scale
   bool fuse_softmax = false;  // PXR_FUSE_SOFTMAX=1: attention softmax inside the GEMM epilogue
+  bool gn_coop = true;        // PXR_GN_COOP=0: three-kernel GroupNorm instead of the cooperative single-kernel one
+  bool fused_attn = true;     // PXR_FUSED_ATTN=0: fall back to the batched-GEMM attention (attn_tc.cu covers T <= 256)
   std::map<std::string, HostWeight> weights[3];
   std::vector<void*> allocs;
   bool finalized = false;
@@ -77,6 +81,9 @@ class Engine {
       // saved activations
       float *x_in, *x_mid, *stats1, *stats2;
       act_t *qkv, *P, *u;
+      act_t* o = nullptr;     // fused attention: per-layer attention output (backward needs D = dO . O)
+      float* lse = nullptr;   // fused attention: row log-sum-exp [B, heads, T]
+      std::shared_ptr<AttnPlan> attn;
     };
     std::vector<Layer> layers;
     // buffers
@@ -290,6 +297,8 @@ class Engine {
     float* gstats;
   };
   GNSaved add_gn(OpList& l, const Act& x, const NormW& n, int swish, act_t* y);
+  void add_gn_bwd(OpList& l, const act_t* dy, const act_t* x, const GNSaved& s, const NormW& n, int px, int C, int swish,
+                  const act_t* dres, act_t* dx);
 
   // ------------------------------------------------------------------ execution
   void prepare_cut_params(const pxr_cut_params* p, int iter);
@@ -334,6 +343,8 @@ void Engine::create() {
   if (fmt != PXR_DTYPE_F16) throw EngineError(-5, "only PXR_DTYPE_F16 operands are wired through the pointwise kernels");
   if (cfg.grad_scale > 0) S = cfg.grad_scale;
   if (const char* fs = getenv("PXR_FUSE_SOFTMAX")) fuse_softmax = atoi(fs) != 0;
+  if (const char* fa = getenv("PXR_FUSED_ATTN")) fused_attn = atoi(fa) != 0;
+  if (const char* gc = getenv("PXR_GN_COOP")) gn_coop = atoi(gc) != 0;
   if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
   if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
   if (cfg.adam_eps <= 0) cfg.adam_eps = 1e-8f;
@@ -389,11 +400,27 @@ Engine::GNSaved Engine::add_gn(OpList& l, const Act& x, const NormW& n, int swis
   float* stats = s.stats;
   cudaStream_t cs = st;
   NormW nn = n;
-  l.add(3, [=] {
-    gn_stats(xp, px, C, 1e-6f, part, stats, cs);
-    gn_apply(xp, stats, nn.gamma, nn.beta, px, C, swish, y, cs);
-  });
+  const int nsm = num_sms;
+  if (gn_coop && gn_coop_supported(px, C, nsm)) {
+    l.add(1, [=] { gn_forward_coop(xp, nn.gamma, nn.beta, px, C, swish, 1e-6f, part, stats, y, nsm, cs); });
+  } else {
+    l.add(3, [=] {
+      gn_stats(xp, px, C, 1e-6f, part, stats, cs);
+      gn_apply(xp, stats, nn.gamma, nn.beta, px, C, swish, y, cs);
+    });
+  }
   return s;
+}
+
+void Engine::add_gn_bwd(OpList& l, const act_t* dy, const act_t* x, const GNSaved& s, const NormW& n, int px, int C,
+                        int swish, const act_t* dres, act_t* dx) {
+  float* part = gn_part;
+  cudaStream_t cs = st;
+  const int nsm = num_sms;
+  if (gn_coop && gn_coop_supported(px, C, nsm))
+    l.add(1, [=] { gn_backward_coop(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, dx, nsm, cs); });
+  else
+    l.add(3, [=] { gn_backward(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, s.gstats, dx, cs); });
 }
 
 // y = conv(x) (+bias), returns y; appends dgrad op (x.g = conv_dgrad(y.g)) to bwd (caller orders it)
@@ -453,7 +480,7 @@ Act Engine::resblock(const Act& x, const std::string& prefix, int cin, int cout)
     e.ldc = cout;
     add_conv(b, out.g, H, Wd, c2.cout_k, c2.wd, c2.cin_rows, cout, 3, e);
   }
-  b.add(3, [=] { gn_backward(a2.g, h1.p, s2.stats, n2.gamma, n2.beta, px, cout, 1, nullptr, part, s2.gstats, h1.g, cs); });
+  add_gn_bwd(b, a2.g, h1.p, s2, n2, px, cout, 1, nullptr, h1.g);
   {
     GemmEpilogue e;
     e.out_f16 = a1.g;
@@ -465,9 +492,9 @@ Act Engine::resblock(const Act& x, const std::string& prefix, int cin, int cout)
     e.out_f16 = x.g;
     e.ldc = cin;
     add_conv(b, out.g, H, Wd, sc.cout_k, sc.wd, sc.cin_rows, cin, 1, e);
-    b.add(3, [=] { gn_backward(a1.g, x.p, s1.stats, n1.gamma, n1.beta, px, cin, 1, x.g, part, s1.gstats, x.g, cs); });
+    add_gn_bwd(b, a1.g, x.p, s1, n1, px, cin, 1, x.g, x.g);
   } else {
-    b.add(3, [=] { gn_backward(a1.g, x.p, s1.stats, n1.gamma, n1.beta, px, cin, 1, out.g, part, s1.gstats, x.g, cs); });
+    add_gn_bwd(b, a1.g, x.p, s1, n1, px, cin, 1, out.g, x.g);
   }
   bwd_stack.push_back(std::move(b));
   return out;
@@ -579,7 +606,7 @@ Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
     e.ldc = c;
     add_gemm(b, opK(gqkv, 3 * c, T, 3 * c), opMN(wqkv, c, c, 3 * c), T, c, 3 * c, e);
   }
-  b.add(3, [=] { gn_backward(a.g, x.p, s.stats, n.gamma, n.beta, T, c, 0, out.g, part, s.gstats, x.g, cs); });
+  add_gn_bwd(b, a.g, x.p, s, n, T, c, 0, out.g, x.g);
   bwd_stack.push_back(std::move(b));
   return out;
 }
@@ -606,7 +633,8 @@ void Engine::build_vqgan() {
   if (w % 8) throw EngineError(-45, "latent width must be a multiple of 8 for the implicit-GEMM conv tiles");
   z_numel = (int64_t)zc * hw;
   // GN scratch sized for the largest activation
-  gn_part = dalloc<float>((size_t)gn_num_partials(cfg.image_h * cfg.image_w, 64) * 64 + 64);
+  // (the cooperative kernels use up to one block per SM, the three-kernel path gn_num_partials blocks)
+  gn_part = dalloc<float>((size_t)std::max(gn_num_partials(cfg.image_h * cfg.image_w, 64), num_sms + 1) * 64 + 64);
   // codebook
   const HostWeight& cb = W(PXR_MOD_VQGAN, "quantize.embedding.weight", {ne, zc});
   std::vector<float> cbT((size_t)zc * ne), c2(ne), mn(zc, 1e30f), mx(zc, -1e30f);
@@ -705,7 +733,7 @@ void Engine::build_vqgan() {
     e.ldc = block_in;
     add_conv(b, co_g, hcur.H, hcur.W, co.cout_k, co.wd, co.cin_rows, block_in, 3, e);
     Act hc = hcur;
-    b.add(3, [=] { gn_backward(a.g, hc.p, s.stats, no.gamma, no.beta, px, hc.C, 1, nullptr, part, s.gstats, hc.g, cs); });
+    add_gn_bwd(b, a.g, hc.p, s, no, px, hc.C, 1, nullptr, hc.g);
     bwd_stack.push_back(std::move(b));
   }
   // flatten backward stack in reverse block order
@@ -926,7 +954,8 @@ void Engine::build_clip(int i) {
   C.gh = dalloc<act_t>((size_t)M * Wd);
   C.go = dalloc<act_t>((size_t)M * Wd);
   C.gqkv = dalloc<act_t>((size_t)M * 3 * Wd);
-  C.dP = dalloc<act_t>((size_t)B * Hh * T * ldT);
+  const bool fuse_attn = fused_attn && attn_supported(T, d, Wd);  // attn_tc.cu: one kernel per direction, T <= 256
+  C.dP = fuse_attn ? nullptr : dalloc<act_t>((size_t)B * Hh * T * ldT);
   C.gx = dalloc<float>((size_t)M * Wd);
   C.gx16 = dalloc<act_t>((size_t)M * Wd);
   C.stats_pre = dalloc<float>((size_t)M * 2);
@@ -976,8 +1005,17 @@ void Engine::build_clip(int i) {
     Ly.stats1 = dalloc<float>((size_t)M * 2);
     Ly.stats2 = dalloc<float>((size_t)M * 2);
     Ly.qkv = dalloc<act_t>((size_t)M * 3 * Wd);
-    Ly.P = dalloc<act_t>((size_t)B * Hh * T * ldT);
+    Ly.P = fuse_attn ? nullptr : dalloc<act_t>((size_t)B * Hh * T * ldT);
     Ly.u = dalloc<act_t>((size_t)M * 4 * Wd);
+    if (fuse_attn) {
+      Ly.o = dalloc<act_t>((size_t)M * Wd);
+      Ly.lse = dalloc<float>((size_t)B * Hh * T);
+      Ly.attn = std::make_shared<AttnPlan>();
+      char buf[256] = {0};
+      int rc = attn_plan_make(Ly.attn.get(), Ly.qkv, Ly.o, C.go, C.gqkv, Ly.lse, B, T, Hh, Wd, scale, num_sms, buf,
+                              sizeof buf);
+      if (rc) throw EngineError(rc, std::string("attention plan: ") + buf);
+    }
     Clip::Layer ly = Ly;
     Clip* c = &C;
     C.fwd.add(1, [=] { layernorm_forward(ly.x_in, Wd, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); });
@@ -991,6 +1029,12 @@ void Engine::build_clip(int i) {
     const long long qs0 = d, qs1 = (long long)T * 3 * Wd;           // (head, image) strides inside qkv
     const long long ps0 = (long long)T * ldT, ps1 = (long long)Hh * T * ldT;  // inside P / dP
     const long long os0 = d, os1 = (long long)T * Wd;              // inside [M, W] token-major buffers
+    if (fuse_attn) {  // S, softmax and PV in one kernel; S / P never leave the SM
+      std::shared_ptr<AttnPlan> ap = ly.attn;
+      char lab[96];
+      snprintf(lab, sizeof lab, "attn_fwd B=%d T=%d heads=%d", B, T, Hh);
+      C.fwd.add(1, [ap, cs] { attn_forward_launch(*ap, cs); }, ap->flops_fwd, lab);
+    } else {
     {  // S = scale * q k^T  (nn.MultiheadAttention scales q by d^-1/2)
       GemmEpilogue e;
       e.alpha = scale;
@@ -1015,13 +1059,14 @@ void Engine::build_clip(int i) {
       add_gemm(C.fwd, opK(ly.P, ldT, T, ldT, Hh, ps0, B, ps1), opMN(ly.qkv + 2 * Wd, 3 * Wd, d, T, Hh, qs0, B, qs1), T, d,
                T, e, 64);
     }
+    }
     {  // x_mid = x_in + O Wo^T + bo
       GemmEpilogue e;
       e.bias = ly.bo;
       e.res_f32 = ly.x_in;
       e.out_f32 = ly.x_mid;
       e.ldc = Wd;
-      add_gemm(C.fwd, opK(C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
+      add_gemm(C.fwd, opK(fuse_attn ? ly.o : C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
     }
     C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, Wd, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); });
     {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u
@@ -1093,6 +1138,12 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.gx16, Wd, M, Wd), opMN(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
     }
+    if (fuse_attn) {  // dQ, dK, dV in one kernel (recomputes P from Q, K and the saved log-sum-exp)
+      std::shared_ptr<AttnPlan> ap = ly.attn;
+      char lab[96];
+      snprintf(lab, sizeof lab, "attn_bwd B=%d T=%d heads=%d", B, T, Hh);
+      C.bwd.add(1, [ap, cs] { attn_backward_launch(*ap, cs); }, ap->flops_bwd, lab);
+    } else {
     {  // dP = go v^T ; fused: dS = scale * P * (dP - <P, dP>)
       GemmEpilogue e;
       e.out_f16 = C.dP;
@@ -1136,6 +1187,7 @@ void Engine::build_clip(int i) {
       e.bs0 = qs0;
       e.bs1 = qs1;
       add_gemm(C.bwd, opMN(ly.P, ldT, T, T, Hh, ps0, B, ps1), opMN(C.go, Wd, d, T, Hh, os0, B, os1), T, d, T, e, 64);
+    }
     }
     {  // gh = gqkv Wqkv
       GemmEpilogue e;
@@ -1249,7 +1301,7 @@ void Engine::finalize() {
       reg(p + "x0", C.layers[0].x_in, mw * 4);
       reg(p + "x_mid0", C.layers[0].x_mid, mw * 4);
       reg(p + "qkv0", C.layers[0].qkv, mw * 3 * 2);
-      reg(p + "P0", C.layers[0].P, (size_t)C.B * C.c.heads * C.T * C.ldT * 2);
+      if (C.layers[0].P) reg(p + "P0", C.layers[0].P, (size_t)C.B * C.c.heads * C.T * C.ldT * 2);
       reg(p + "x_out", C.x_out, mw * 4);
       reg(p + "e", C.e, (size_t)C.B * C.c.out_dim * 4);
       reg(p + "de", C.de, (size_t)C.B * C.c.out_dim * 4);

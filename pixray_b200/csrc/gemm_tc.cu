@@ -1265,6 +1265,11 @@ bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0;
 
 }  // namespace
 
+int tmap_encode_4d(CUtensorMap* out, const void* ptr, int fmt, const uint64_t dims[4], const uint64_t strides_elems[3],
+                   const uint32_t box[4], char* err, int errlen) {
+  return encode_tmap4(out, ptr, fmt, dims, strides_elems, box, err, errlen);
+}
+
 // Measured on B200 (tests/test_gemm_gpu.py::test_gemm_throughput_report): CTA pairs are within +-8% of single-CTA tiles
 // on the CLIP GEMM shapes (ahead only at K = 3072), so single-CTA tiles stay the default; PXR_GEMM_CTA_GROUP=2 turns
 // pairs on wherever the tile shape allows it.

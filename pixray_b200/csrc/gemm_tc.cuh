@@ -120,6 +120,11 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
 
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 
+// 4-D tiled tensor map, zero fill out of bounds, 128-byte swizzle (fmt 0 = fp16, 1 = bf16, 2 = fp32); strides in elements.
+// Shared with attn_tc.cu.  Returns 0 on success, otherwise writes a message to err.
+int tmap_encode_4d(CUtensorMap* out, const void* ptr, int fmt, const uint64_t dims[4], const uint64_t strides_elems[3],
+                   const uint32_t box[4], char* err, int errlen);
+
 // 1 (single-CTA tiles) unless PXR_GEMM_CTA_GROUP=2 asks for CTA pairs where the shape allows them.
 int gemm_default_cta_group();
 

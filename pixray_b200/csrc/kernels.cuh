@@ -30,6 +30,16 @@ void gn_backward(const act_t* dy, const act_t* x, const float* stats, const floa
                  int pixels, int C, int swish, const act_t* dres, float* part, float* gstats, act_t* dx,
                  cudaStream_t st);
 
+// The same two operations as ONE cooperative kernel each (grid-wide barrier between the statistics and the apply
+// phase, the block's slab of x kept in shared memory): 1 launch and 1 HBM pass instead of 3 launches and 2 passes.
+// `part` needs 64 floats per block (<= num_sms blocks).  gn_coop_supported: the slab of a block fits shared memory.
+bool gn_coop_supported(int pixels, int C, int num_sms);
+void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int pixels, int C, int swish, float eps,
+                     float* part, float* stats, act_t* y, int num_sms, cudaStream_t st);
+void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
+                      int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
+                      cudaStream_t st);
+
 void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st);        // nearest, [H,W,C]->[2H,2W,C]
 void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st);       // adjoint: [2H,2W,C]->[H,W,C]
 

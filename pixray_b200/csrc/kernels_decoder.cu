@@ -1,6 +1,7 @@
 // VQGAN-drawer side kernels: nearest-code search, GroupNorm(+swish) fwd/bwd, nearest upsample and its adjoint,
 // image finish (clamp_with_grad) and the pixel drawer.  All HBM/L2-bound; vectorised 16-byte accesses on NHWC fp16.
 #include "kernels.cuh"
+#include <cooperative_groups.h>
 #include <cfloat>
 
 namespace pxr {
@@ -330,6 +331,214 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const act_t* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm in ONE cooperative kernel per direction (replaces partial + final + apply: 3 launches, 2 passes over x).
+// The grid (<= one 1024-thread block per SM) splits the pixels into contiguous slabs; a block keeps its slab of x
+// (and dy when it fits) in shared memory, so every tensor is read from HBM once.  Statistics: block partials in a fixed
+// order -> global scratch -> grid-wide barrier -> every block folds all partials in the same fixed order (double
+// accumulation).  No atomics anywhere: identical bits on every run and on every rank of the cutout-sharded mode.
+namespace cg = cooperative_groups;
+constexpr int GNC_THREADS = 1024;
+
+// per-block fixed-order reduction of the thread partials s[half][a/b] to part_out[32 groups][2]
+__device__ __forceinline__ void gnc_block_partials(const float (&s)[2][2], float* red, int vecs, int cpg,
+                                                   float* __restrict__ part_out) {
+  const int tid = threadIdx.x, vc = tid % vecs, pl = tid / vecs, plane = GNC_THREADS / vecs;
+  red[0 * GNC_THREADS + tid] = s[0][0];
+  red[1 * GNC_THREADS + tid] = s[0][1];
+  red[2 * GNC_THREADS + tid] = s[1][0];
+  red[3 * GNC_THREADS + tid] = s[1][1];
+  __syncthreads();
+  if (pl == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < plane; ++l)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += red[k * GNC_THREADS + l * vecs + vc];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[k * GNC_THREADS + vc] = t[k];
+  }
+  __syncthreads();
+  if (tid < GN_G * 2) {
+    const int g = tid >> 1, which = tid & 1;
+    float t = 0.f;
+    if (cpg >= 8) {
+      const int vpg = cpg / 8;
+      for (int v = g * vpg; v < (g + 1) * vpg; ++v) t += red[which * GNC_THREADS + v] + red[(2 + which) * GNC_THREADS + v];
+    } else {  // cpg == 4: a vector holds two groups
+      t = red[((g & 1) * 2 + which) * GNC_THREADS + (g >> 1)];
+    }
+    part_out[tid] = t;
+  }
+}
+
+// every block: fold the nblk block partials (fixed order, double) -> sh[64] = per-(group, which) mean
+__device__ __forceinline__ void gnc_fold(const float* part, int nblk, double count, double* acc4, double* sh) {
+  const int tid = threadIdx.x;
+  if (tid < 256) {
+    const int slot = tid & 63, qd = tid >> 6;
+    double a = 0.0;
+    for (int b = qd; b < nblk; b += 4) a += (double)__ldcg(part + (size_t)b * GN_G * 2 + slot);
+    acc4[qd * 64 + slot] = a;
+  }
+  __syncthreads();
+  if (tid < 64) sh[tid] = (acc4[tid] + acc4[64 + tid] + acc4[128 + tid] + acc4[192 + tid]) / count;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GNC_THREADS, 1)
+    gn_coop_fwd_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       int pixels, int C, int swish, float eps, int rpb, float* part, float* __restrict__ stats_out,
+                       act_t* __restrict__ y) {
+  extern __shared__ __align__(16) uint8_t gnc_smem[];
+  float* red = reinterpret_cast<float*>(gnc_smem);                       // [4][1024]
+  act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);  // slab of x
+  __shared__ double acc4[256];
+  __shared__ double sh[64];
+  __shared__ float st[64];
+  const int vecs = C / 8, cpg = C / GN_G;
+  const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = GNC_THREADS / vecs;
+  const int c0 = vc * 8;
+  const int p_begin = blockIdx.x * rpb, p_end = min(pixels, p_begin + rpb);
+  float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 4
+  for (int p = p_begin + pl; p < p_end; p += plane) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)p * C + c0);
+    *reinterpret_cast<uint4*>(cx + (size_t)(p - p_begin) * C + c0) = u;
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(h[i]);
+      s[i >> 1][0] += t.x + t.y;
+      s[i >> 1][1] += t.x * t.x + t.y * t.y;
+    }
+  }
+  gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
+  __threadfence();
+  cg::this_grid().sync();
+  gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  if (threadIdx.x < GN_G) {
+    const double mean = sh[2 * threadIdx.x], ex2 = sh[2 * threadIdx.x + 1];
+    double var = ex2 - mean * mean;
+    if (var < 0) var = 0;
+    const float m = (float)mean, r = (float)(1.0 / sqrt(var + (double)eps));
+    st[2 * threadIdx.x] = m;
+    st[2 * threadIdx.x + 1] = r;
+    if (blockIdx.x == 0) {
+      stats_out[2 * threadIdx.x] = m;
+      stats_out[2 * threadIdx.x + 1] = r;
+    }
+  }
+  __syncthreads();
+  float sc8[8], sh8[8];  // y = x * sc + sh
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c0 + i) / cpg;
+    const float ga = gamma[c0 + i];
+    sc8[i] = st[2 * g + 1] * ga;
+    sh8[i] = beta[c0 + i] - st[2 * g] * st[2 * g + 1] * ga;
+  }
+#pragma unroll 4
+  for (int p = p_begin + pl; p < p_end; p += plane) {
+    float xv[8];
+    load8(cx + (size_t)(p - p_begin) * C + c0, xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = xv[i] * sc8[i] + sh8[i];
+      xv[i] = swish ? a / (1.f + __expf(-a)) : a;
+    }
+    store8(y + (size_t)p * C + c0, xv);
+  }
+}
+
+__global__ void __launch_bounds__(GNC_THREADS, 1)
+    gn_coop_bwd_kernel(const act_t* __restrict__ dy, const act_t* __restrict__ x, const float* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, int pixels, int C, int swish,
+                       const act_t* dres, int rpb, int cache_dy, float* part, act_t* dx) {
+  extern __shared__ __align__(16) uint8_t gnc_smem[];
+  float* red = reinterpret_cast<float*>(gnc_smem);
+  act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);
+  act_t* cd = cx + (size_t)rpb * C;  // only touched when cache_dy
+  __shared__ double acc4[256];
+  __shared__ double sh[64];
+  const int vecs = C / 8, cpg = C / GN_G;
+  const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = GNC_THREADS / vecs;
+  const int c0 = vc * 8;
+  const int p_begin = blockIdx.x * rpb, p_end = min(pixels, p_begin + rpb);
+  float g8[8], b8[8], mean2[2], rstd2[2];  // cpg >= 4: elements 0..3 and 4..7 of the vector each sit in one group
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    g8[i] = gamma[c0 + i];
+    b8[i] = beta[c0 + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int g = (c0 + 4 * i) / cpg;
+    mean2[i] = stats[2 * g];
+    rstd2[i] = stats[2 * g + 1];
+  }
+  float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 2
+  for (int p = p_begin + pl; p < p_end; p += plane) {
+    const uint4 ux = *reinterpret_cast<const uint4*>(x + (size_t)p * C + c0);
+    const uint4 ud = *reinterpret_cast<const uint4*>(dy + (size_t)p * C + c0);
+    *reinterpret_cast<uint4*>(cx + (size_t)(p - p_begin) * C + c0) = ux;
+    if (cache_dy) *reinterpret_cast<uint4*>(cd + (size_t)(p - p_begin) * C + c0) = ud;
+    const __half2* hx = reinterpret_cast<const __half2*>(&ux);
+    const __half2* hd = reinterpret_cast<const __half2*>(&ud);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 tx = __half22float2(hx[i]), td = __half22float2(hd[i]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = 2 * i + k;
+        const float xh = ((k ? tx.y : tx.x) - mean2[e >> 2]) * rstd2[e >> 2];
+        float d = k ? td.y : td.x;
+        if (swish) {
+          const float a = g8[e] * xh + b8[e];
+          const float sg = 1.f / (1.f + __expf(-a));
+          d *= sg * (1.f + a * (1.f - sg));
+        }
+        const float dxh = d * g8[e];
+        s[e >> 2][0] += dxh;
+        s[e >> 2][1] += dxh * xh;
+      }
+    }
+  }
+  gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
+  __threadfence();
+  cg::this_grid().sync();
+  gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  float gs0[2], gs1[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int g = (c0 + 4 * i) / cpg;
+    gs0[i] = (float)sh[2 * g];
+    gs1[i] = (float)sh[2 * g + 1];
+  }
+#pragma unroll 2
+  for (int p = p_begin + pl; p < p_end; p += plane) {
+    float xv[8], dv[8], rv[8];
+    load8(cx + (size_t)(p - p_begin) * C + c0, xv);
+    if (cache_dy) load8(cd + (size_t)(p - p_begin) * C + c0, dv);
+    else load8(dy + (size_t)p * C + c0, dv);
+    if (dres) load8(dres + (size_t)p * C + c0, rv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (xv[i] - mean2[i >> 2]) * rstd2[i >> 2];
+      float d = dv[i];
+      if (swish) {
+        const float a = g8[i] * xh + b8[i];
+        const float sg = 1.f / (1.f + __expf(-a));
+        d *= sg * (1.f + a * (1.f - sg));
+      }
+      const float dxh = d * g8[i];
+      const float r = rstd2[i >> 2] * (dxh - gs0[i >> 2] - xh * gs1[i >> 2]);
+      xv[i] = dres ? r + rv[i] : r;
+    }
+    store8(dx + (size_t)p * C + c0, xv);
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_kernel(const act_t* __restrict__ x, int H, int W, int C,
                                                          act_t* __restrict__ y) {
   const int vecs = C / 8;
@@ -473,6 +682,50 @@ void gn_backward(const act_t* dy, const act_t* x, const float* stats, const floa
   const long long nvec = (long long)pixels * C / 8;
   gn_bwd_apply_kernel<<<grid_for(nvec, 256), 256, 0, st>>>(dy, x, stats, gstats, gamma, beta, nvec, C, swish, dres,
                                                            dx);
+}
+
+namespace {
+constexpr int GNC_SMEM_MAX = 216 * 1024;
+int gnc_rows_per_block(int pixels, int num_sms) {
+  int r = (pixels + num_sms - 1) / num_sms;
+  return r < 16 ? 16 : r;
+}
+void gnc_init() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(gn_coop_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  cudaFuncSetAttribute(gn_coop_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  done = true;
+}
+}  // namespace
+
+bool gn_coop_supported(int pixels, int C, int num_sms) {
+  if (C % 8 || (C / 8) > GNC_THREADS || GNC_THREADS % (C / 8) || (C % GN_G) || (C / GN_G != 4 && (C / GN_G) % 8)) return false;
+  const int rpb = gnc_rows_per_block(pixels, num_sms);
+  return 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2 <= (size_t)GNC_SMEM_MAX;
+}
+
+void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int pixels, int C, int swish, float eps,
+                     float* part, float* stats, act_t* y, int num_sms, cudaStream_t st) {
+  gnc_init();
+  int rpb = gnc_rows_per_block(pixels, num_sms);
+  const int grid = (pixels + rpb - 1) / rpb;
+  const size_t smem = 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2;
+  void* args[] = {&x, &gamma, &beta, &pixels, &C, &swish, &eps, &rpb, &part, &stats, &y};
+  cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_coop_fwd_kernel), dim3(grid), dim3(GNC_THREADS), args, smem, st);
+}
+
+void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
+                      int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
+                      cudaStream_t st) {
+  gnc_init();
+  int rpb = gnc_rows_per_block(pixels, num_sms);
+  const int grid = (pixels + rpb - 1) / rpb;
+  const size_t slab = (size_t)rpb * C * 2;
+  int cache_dy = (4 * GNC_THREADS * 4 + 2 * slab <= (size_t)GNC_SMEM_MAX) ? 1 : 0;
+  const size_t smem = 4 * GNC_THREADS * 4 + (cache_dy ? 2 : 1) * slab;
+  void* args[] = {&dy, &x, &stats, &gamma, &beta, &pixels, &C, &swish, &dres, &rpb, &cache_dy, &part, &dx};
+  cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_coop_bwd_kernel), dim3(grid), dim3(GNC_THREADS), args, smem, st);
 }
 
 void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st) {

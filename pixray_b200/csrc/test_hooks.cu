@@ -2,6 +2,7 @@
 // These are not part of the reference-facing surface (include/pixray_b200.h lists them under "test hooks").
 #include "../../include/pixray_b200.h"
 #include "gemm_tc.cuh"
+#include "attn_tc.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -80,6 +81,27 @@ extern "C" int pxr_test_conv(const pxr_test_gemm_desc* d, int batch, int H, int 
                           num_sms(), err, errlen);
   if (rc) return rc;
   for (int i = 0; i < (d->repeat > 0 ? d->repeat : 1); ++i) gemm_launch(plan, static_cast<cudaStream_t>(d->stream));
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    if (err) snprintf(err, errlen, "launch failed: %s", cudaGetErrorString(ce));
+    return -100;
+  }
+  return 0;
+}
+
+// Fused attention forward (+ backward when d_o != NULL) on caller tensors: qkv [B*T, 3W] fp16, o [B*T, W] fp16,
+// lse [B*H*T] fp32, d_o [B*T, W] fp16, gqkv [B*T, 3W] fp16.
+extern "C" int pxr_test_attention(const void* qkv, void* o, float* lse, const void* d_o, void* gqkv, int B, int T, int H,
+                                  int W, float scale, int repeat, char* err, int errlen) {
+  AttnPlan plan;
+  int rc = attn_plan_make(&plan, static_cast<const __half*>(qkv), static_cast<__half*>(o),
+                          static_cast<const __half*>(d_o), static_cast<__half*>(gqkv), lse, B, T, H, W, scale,
+                          num_sms(), err, errlen);
+  if (rc) return rc;
+  for (int i = 0; i < (repeat > 0 ? repeat : 1); ++i) {
+    attn_forward_launch(plan, nullptr);
+    if (d_o) attn_backward_launch(plan, nullptr);
+  }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     if (err) snprintf(err, errlen, "launch failed: %s", cudaGetErrorString(ce));
