@@ -109,6 +109,23 @@ int pxr_backward(pxr_handle h, float* z_grad);
 int pxr_step(pxr_handle h, float* z, float lr, int iter);
 int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params* p,
                 float* out_losses_host /* pinned or pageable; may be NULL */);
+/* Auxiliary losses: Losses/*.py behind LossInterface.get_loss, summed into the iteration's loss list by ascend_txt
+ * (pixray.py:1384-1393, custom_loss spec "name:weight").  Each becomes one more entry of the loss vector (after the
+ * prompts, in the order added) and one more term of the gradient.  params (host floats), by kind:
+ *   SYMMETRY   {symmetry_weight}                                            Losses/SymmetryLoss.py:14-17   (image)
+ *   SATURATION {saturation_weight}                                          Losses/SaturationLoss.py:15-30 (cutouts)
+ *   PALETTE    {palette_weight, r0,g0,b0, r1,g1,b1, ...}  colours in [0,1]  Losses/PaletteLoss.py:25-35    (cutouts)
+ *   SMOOTHNESS {smoothness_weight, type (0 default, 1 clipped, 2 log), spacing}   Losses/SmoothnessLoss.py:89-108
+ *   EDGE       {edge_color_weight, global_color_weight, left,right,upper,lower (pixels), r,g,b}  Losses/EdgeLoss.py:60-108
+ *   GAUSSIAN   {gaussian_weight, std_y, std_x, R,G,B (0..255)}              Losses/GaussianLoss.py:31-44   (image)
+ *   AESTHETIC  {aesthetic_target, bias, w[D]}  linear head on the last perceptor's embeddings  Losses/AestheticLoss.py:30-33 */
+enum { PXR_LOSS_SYMMETRY = 0, PXR_LOSS_SATURATION = 1, PXR_LOSS_PALETTE = 2, PXR_LOSS_SMOOTHNESS = 3, PXR_LOSS_EDGE = 4,
+       PXR_LOSS_GAUSSIAN = 5, PXR_LOSS_AESTHETIC = 6 };
+int pxr_add_aux_loss(pxr_handle h, int kind, float weight, const float* params, int n_params);
+int pxr_clear_aux_losses(pxr_handle h);
+int pxr_num_losses(pxr_handle h, int* out); /* prompts of every perceptor + auxiliary losses */
+int pxr_read_losses(pxr_handle h, float* out_host); /* blocking: the loss vector of the last forward / backward */
+
 int pxr_reset_optimizer(pxr_handle h); /* rebuild_optimisers: fresh Adam state (pixray.py:520-555, 1511) */
 int pxr_sync(pxr_handle h);
 

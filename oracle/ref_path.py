@@ -506,6 +506,107 @@ def fft_synth(spectrum, decay_power=1.5, colors=1.5, contrast=0.9):
 # ------------------------------------------------------------------------------------------------ optimiser / loop
 
 
+
+# ------------------------------------------------------------------------------------------------ auxiliary losses
+# Losses/*.py (LossInterface.get_loss(cur_cutouts, out, args, globals, lossGlobals)); `out` is the synthesised image
+# [1,3,H,W], `cutouts` the (noised) MakeCutouts batch [cutn,3,cs,cs], `embeds` the last perceptor's unit embeddings.
+
+
+def symmetry_loss(out, symmetry_weight=1.0):
+    """Losses/SymmetryLoss.py:14-17: MSE between the image and its horizontal mirror."""
+    return F.mse_loss(out, torch.flip(out, [3])) * symmetry_weight
+
+
+def saturation_loss(cutouts, saturation_weight=1.0):
+    """Losses/SaturationLoss.py:15-30: Hasler-Suesstrunk colourfulness over all cutout pixels, negated."""
+    px = cutouts.permute(0, 2, 3, 1).reshape(-1, 3)
+    rg = px[:, 0] - px[:, 1]
+    yb = 0.5 * (px[:, 0] + px[:, 1]) - px[:, 2]
+    rg_std, rg_mean = torch.std_mean(rg)
+    yb_std, yb_mean = torch.std_mean(yb)
+    std_rggb = torch.sqrt(rg_std ** 2 + yb_std ** 2)
+    mean_rggb = torch.sqrt(rg_mean ** 2 + yb_mean ** 2)
+    return -(std_rggb + 0.3 * mean_rggb) * saturation_weight / 10.0
+
+
+def palette_loss(cutouts, palette, palette_weight=1.0):
+    """Losses/PaletteLoss.py:25-35: L2 distance of every cutout pixel to its nearest palette colour.
+    Returns (loss, best_guesses) -- the argmin indices are the path's integer bookkeeping."""
+    target = torch.as_tensor(palette, dtype=torch.float32)
+    px = cutouts.permute(0, 2, 3, 1).reshape(-1, 3)
+    best = torch.cdist(target, px, p=2).argmin(axis=0)
+    diffs = px - target[best]
+    loss = torch.mean(torch.norm(diffs, 2, dim=1)) * cutouts.shape[0]
+    return loss * palette_weight / 10.0, best
+
+
+def smoothness_loss(cutouts, smoothness_weight=1.0, smoothness_type="default", spacing=1, edge_order=1):
+    """Losses/SmoothnessLoss.py:89-108 (smoothness_gaussian_kernel = 0).  NB the reference stacks the cutouts' rows:
+    `_pixels` is [cutn*H, W, 3], so the finite difference along dim 0 runs ACROSS cutout boundaries."""
+    px = cutouts.permute(0, 2, 3, 1).reshape(-1, cutouts.shape[2], 3)
+    sq = 0
+    for c in range(3):
+        gy, gx = torch.gradient(px[:, :, c], spacing=spacing, edge_order=edge_order)
+        sq = sq + gy ** 2 + gx ** 2
+    sharp = torch.sqrt(sq)
+    if smoothness_type == "clipped":
+        sharp = torch.clamp(sharp, max=0.5)
+    elif smoothness_type == "log":
+        sharp = torch.log(torch.ones_like(sharp) + sharp)
+    return torch.mean(sharp) * smoothness_weight
+
+
+def edge_margins_px(edge_margins, H, W):
+    """Losses/EdgeLoss.py:82-88: percent margins (left, right, up, down) -> pixels, util.map_number + int()."""
+    left, right, upper, lower = edge_margins
+    return (int(left / 100.0 * W), int(right / 100.0 * W), int(upper / 100.0 * H), int(lower / 100.0 * H))
+
+
+def edge_loss(out, edge_color, margins_px, edge_color_weight=0.1, global_color_weight=0.05):
+    """Losses/EdgeLoss.py:60-108, colour target, no input image / mask."""
+    lmax, rmax = out.shape[2], out.shape[3]
+    left, right, upper, lower = margins_px
+    zers = torch.zeros_like(out)
+    for c in range(3):
+        zers[:, c] = edge_color[c]
+    cur = torch.zeros(())
+    if left != 0:
+        cur = cur + F.mse_loss(out[:, :, :, :left], zers[:, :, :, :left])
+    if right != 0:
+        cur = cur + F.mse_loss(out[:, :, :, rmax - right:], zers[:, :, :, rmax - right:])
+    if upper != 0:
+        cur = cur + F.mse_loss(out[:, :, :upper, left:rmax - right], zers[:, :, :upper, left:rmax - right])
+    if lower != 0:
+        cur = cur + F.mse_loss(out[:, :, lmax - lower:, left:rmax - right], zers[:, :, lmax - lower:, left:rmax - right])
+    if global_color_weight:
+        cur = cur + F.mse_loss(out, zers) * global_color_weight
+    return cur * edge_color_weight
+
+
+def gaussian_window(ylen, xlen, stdy, stdx):
+    """Losses/GaussianLoss.py:6-17 (gaussian_fn / gkern)."""
+    def fn(M, std):
+        n = torch.arange(0, M) - (M - 1.0) / 2.0
+        return torch.exp(-n ** 2 / (2 * std * std))
+    return torch.outer(fn(ylen, stdy), fn(xlen, stdx))
+
+
+def gaussian_loss(out, gaussian_std=(40, 40), gaussian_color=(255, 255, 255), gaussian_weight=1.0):
+    """Losses/GaussianLoss.py:31-44."""
+    gaus = gaussian_window(out.shape[2], out.shape[3], *gaussian_std)
+    color = torch.zeros_like(out)
+    for c in range(3):
+        color[:, c] = gaussian_color[c] / 255
+    return torch.mean(torch.abs(out - color) * torch.abs(1 - gaus)) * gaussian_weight
+
+
+def aesthetic_loss(embeds, weight, bias, aesthetic_target=10.0):
+    """Losses/AestheticLoss.py:30-33: linear AVA head on the (re-)normalised embeddings, MSE to the target * 0.02."""
+    rating = F.linear(F.normalize(embeds, dim=-1), weight, bias)
+    target = torch.ones(embeds.shape[0], 1) * aesthetic_target
+    return (rating - target).square().mean() * 0.02
+
+
 class AdamState:
     """optim.Adam([z], lr) as rebuilt by rebuild_optimisers (pixray.py:520-555): betas 0.9/0.999, eps 1e-8."""
 
@@ -524,11 +625,12 @@ class AdamState:
         return z - (lr / bc1) * self.m / denom
 
 
-def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise):
+def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=()):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
-    (embed [n,D], weight, stop).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
+    (embed [n,D], weight, stop); aux: custom losses (pixray.py:1384-1393) as (weight, fn(out, batch, embeds) ->
+    scalar), appended to the loss list in order.  Returns dict(image, batch, embeds[], losses[], z_grad)."""
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
     out.retain_grad()
@@ -540,6 +642,8 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
         embeds.append(iii)
         for (embed, weight, stop) in pms:
             losses.append(prompt_loss(iii, embed, weight, stop))
+    for (lossweight, fn) in aux:
+        losses.append(lossweight * fn(out, batch, embeds[-1]))
     total = sum(losses)
     total.backward()
     return dict(image=out.detach(), batch=batch.detach(), embeds=[e.detach() for e in embeds],

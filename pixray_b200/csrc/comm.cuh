@@ -1,6 +1,6 @@
 // NCCL binding for the cutout-sharded multi-GPU mode.  libnccl.so.2 is resolved at run time with
 // dlopen (torch has normally loaded the same soname already); only the handful of symbols the hot path needs are
-// declared here, ABI-compatible with nccl.h 2.x (ncclUniqueId = 128 bytes, ncclSum = 0, ncclMin = 3, ncclFloat32 = 7).
+// declared here, ABI-compatible with nccl.h 2.x (ncclUniqueId = 128 bytes, ncclSum = 0, ncclMin = 3, ncclFloat32 = 7, ncclFloat64 = 8).
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -58,7 +58,7 @@ class Comm {
   DestroyFn destroy = nullptr;
   ErrStrFn err_str = nullptr;
   GroupFn group_start = nullptr, group_end = nullptr;
-  static constexpr int kSum = 0, kMin = 3, kFloat32 = 7;
+  static constexpr int kSum = 0, kMin = 3, kFloat32 = 7, kFloat64 = 8;
 
  private:
   void* lib_ = nullptr;

@@ -100,6 +100,26 @@ class Engine {
   float* losses_host = nullptr;  // pinned
   int total_prompts = 0;
 
+  // ---- auxiliary losses (Losses/*.py; pixray.py:1384-1393): extra loss-vector entries after the prompts
+  struct AuxLoss {
+    int kind;
+    float weight;
+    std::vector<float> prm;
+    float* dev = nullptr;  // palette colours / aesthetic head weights
+    int n_dev = 0;
+  };
+  std::vector<AuxLoss> aux;
+  double* aux_part = nullptr;   // reduction scratch
+  double* aux_sums = nullptr;   // saturation moments (4)
+  float* aux_A = nullptr;       // smoothness per-pixel factor
+  float* aux_halo = nullptr;    // smoothness rows of the neighbouring ranks
+  float* aux_xbuf = nullptr;    // smoothness halo exchange buffer
+  int* aux_best = nullptr;      // palette argmin per pixel (bookkeeping, also a debug buffer)
+  int num_losses() const { return total_prompts + (int)aux.size(); }
+  void aux_after_embed();   // aesthetic: needs de of the last perceptor (after its prompt_loss)
+  void aux_on_cutouts();    // saturation / palette / smoothness: add into g_batch
+  void aux_on_image();      // symmetry / edge / gaussian: add into g_img
+
   // ---- comm (multi-GPU, cutout sharding): one NCCL communicator owned by the engine (comm.cuh)
   void* comm = nullptr;
   float* xbuf = nullptr;  // {min, -max} exchange buffer
@@ -250,18 +270,57 @@ class Engine {
              e.out_f16 ? " o16" : "", e.aux_out ? " aux" : "");
     return b;
   }
+  // Small-spatial convolutions (16x16 / 32x32 latents: 2..64 output tiles, K up to 4608) leave most SMs idle and are
+  // bound by the per-SM operand feed; split-K spreads the taps over the idle SMs (fp32 partial sums to a workspace, then
+  // one fixed-order reduce + bias / residual / fp16 epilogue kernel: deterministic).
+  bool conv_splitk = true;  // PXR_CONV_SPLITK=0 disables
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_elems = 0;
   void add_conv(OpList& l, const act_t* in, int H, int Wd, int cin, const act_t* wt, int cout_pad, int n_out, int ks,
                 const GemmEpilogue& e) {
-    int bn = pick_bn(cout_pad < 64 ? cout_pad : n_out, false, (long long)(H * Wd + 127) / 128);
+    const long long m_tiles = (long long)(H * Wd + 127) / 128;
+    int bn = pick_bn(cout_pad < 64 ? cout_pad : n_out, false, m_tiles);
     if (bn > cout_pad) bn = cout_pad;
-    auto plan = std::make_shared<GemmPlan>();
-    char buf[256] = {0};
-    int rc = conv_plan_make(plan.get(), in, cin, 1, H, Wd, cin, wt, cout_pad, n_out, ks, e, bn, fmt, num_sms, buf,
-                            sizeof buf);
-    if (rc) throw EngineError(rc, std::string("conv plan: ") + buf);
     cudaStream_t s = st;
     char kind[32];
     snprintf(kind, sizeof kind, "conv%dx%d", ks, ks);
+    const int nkb = ks * ks * cin / 64;
+    const long long tiles = m_tiles * ((n_out + bn - 1) / bn);
+    int splits = 1;
+    if (conv_splitk && splitk_ws && e.out_f16 && !e.out_f32 && !e.res_f32 && !e.aux_out && e.act == ACT_NONE &&
+        n_out % 8 == 0 && e.ldc % 8 == 0 && tiles * 2 <= num_sms && nkb >= 8) {
+      const int want = (int)std::min<long long>(num_sms / tiles, nkb / 4);
+      if (want >= 2) {
+        const int kbps = (nkb + want - 1) / want;
+        splits = (nkb + kbps - 1) / kbps;
+      }
+      if ((size_t)splits * H * Wd * n_out > splitk_ws_elems) splits = 1;
+    }
+    auto plan = std::make_shared<GemmPlan>();
+    char buf[256] = {0};
+    if (splits > 1) {
+      GemmEpilogue pe;
+      pe.out_f32 = splitk_ws;
+      pe.ldc = n_out;
+      pe.k_splits = splits;
+      int rc = conv_plan_make(plan.get(), in, cin, 1, H, Wd, cin, wt, cout_pad, n_out, ks, pe, bn, fmt, num_sms, buf, sizeof buf);
+      if (rc) throw EngineError(rc, std::string("conv plan (split-K): ") + buf);
+      const float* ws = splitk_ws;
+      const float* bias = e.bias;
+      const act_t* res = e.res_f16;
+      act_t* out = e.out_f16;
+      const int ld_out = (int)e.ldc;
+      const long long px = (long long)H * Wd;
+      std::string label = gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e) + " splitK=" + std::to_string(plan->p.k_splits);
+      l.add(2, [=] {
+        gemm_launch(*plan, s);
+        splitk_reduce(ws, plan->p.k_splits, px, n_out, n_out, bias, res, out, ld_out, s);
+      }, plan->flops, label);
+      return;
+    }
+    int rc = conv_plan_make(plan.get(), in, cin, 1, H, Wd, cin, wt, cout_pad, n_out, ks, e, bn, fmt, num_sms, buf,
+                            sizeof buf);
+    if (rc) throw EngineError(rc, std::string("conv plan: ") + buf);
     l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e));
   }
 
@@ -288,6 +347,7 @@ class Engine {
   // decoder blocks: append forward ops to drawer_fwd, push the backward closure list (reverse order) to bwd_stack
   std::vector<OpList> bwd_stack;
   float* gn_part = nullptr;  // scratch for GN partial sums (sized for the largest layer)
+  GridBarrier gn_bar;        // grid barrier state of the single-kernel GroupNorm
   Act conv_fwd_bwd(const Act& x, const ConvW& w, OpList& bwd);
   Act resblock(const Act& x, const std::string& prefix, int cin, int cout);
   Act attnblock(const Act& x, const std::string& prefix, int c);
@@ -345,6 +405,7 @@ void Engine::create() {
   if (const char* fs = getenv("PXR_FUSE_SOFTMAX")) fuse_softmax = atoi(fs) != 0;
   if (const char* fa = getenv("PXR_FUSED_ATTN")) fused_attn = atoi(fa) != 0;
   if (const char* gc = getenv("PXR_GN_COOP")) gn_coop = atoi(gc) != 0;
+  if (const char* sk = getenv("PXR_CONV_SPLITK")) conv_splitk = atoi(sk) != 0;
   if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
   if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
   if (cfg.adam_eps <= 0) cfg.adam_eps = 1e-8f;
@@ -402,12 +463,14 @@ Engine::GNSaved Engine::add_gn(OpList& l, const Act& x, const NormW& n, int swis
   NormW nn = n;
   const int nsm = num_sms;
   if (gn_coop && gn_coop_supported(px, C, nsm)) {
-    l.add(1, [=] { gn_forward_coop(xp, nn.gamma, nn.beta, px, C, swish, 1e-6f, part, stats, y, nsm, cs); });
+    GridBarrier* gb = &gn_bar;
+    l.add(1, [=] { gn_forward_coop(xp, nn.gamma, nn.beta, px, C, swish, 1e-6f, part, stats, y, nsm, gb, cs); }, 0.0,
+          "gn_fwd_coop px=" + std::to_string(px) + " C=" + std::to_string(C));
   } else {
     l.add(3, [=] {
       gn_stats(xp, px, C, 1e-6f, part, stats, cs);
       gn_apply(xp, stats, nn.gamma, nn.beta, px, C, swish, y, cs);
-    });
+    }, 0.0, "gn_fwd_3k px=" + std::to_string(px) + " C=" + std::to_string(C));
   }
   return s;
 }
@@ -417,10 +480,13 @@ void Engine::add_gn_bwd(OpList& l, const act_t* dy, const act_t* x, const GNSave
   float* part = gn_part;
   cudaStream_t cs = st;
   const int nsm = num_sms;
+  GridBarrier* gb = &gn_bar;
   if (gn_coop && gn_coop_supported(px, C, nsm))
-    l.add(1, [=] { gn_backward_coop(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, dx, nsm, cs); });
+    l.add(1, [=] { gn_backward_coop(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, dx, nsm, gb, cs); }, 0.0,
+          "gn_bwd_coop px=" + std::to_string(px) + " C=" + std::to_string(C));
   else
-    l.add(3, [=] { gn_backward(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, s.gstats, dx, cs); });
+    l.add(3, [=] { gn_backward(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, s.gstats, dx, cs); }, 0.0,
+          "gn_bwd_3k px=" + std::to_string(px) + " C=" + std::to_string(C));
 }
 
 // y = conv(x) (+bias), returns y; appends dgrad op (x.g = conv_dgrad(y.g)) to bwd (caller orders it)
@@ -543,7 +609,7 @@ Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
     }
     add_gemm(drawer_fwd, opK(qkv, 3 * c, T, c), opK(qkv + c, 3 * c, T, c), T, T, c, e, fuse_sm ? round_up(T, 16) : 0);
   }
-  if (!fuse_sm) drawer_fwd.add(1, [=] { softmax_forward(P, T, T, ldT, cs); });
+  if (!fuse_sm) drawer_fwd.add(1, [=] { softmax_forward(P, T, T, ldT, cs); }, 0.0, "softmax_forward");
   {
     GemmEpilogue e;
     e.out_f16 = O.p;
@@ -578,7 +644,7 @@ Act Engine::attnblock(const Act& x, const std::string& prefix, int c) {
     }
     add_gemm(b, opK(O.g, c, T, c), opK(qkv + 2 * c, 3 * c, T, c), T, T, c, e, fuse_sm ? round_up(T, 16) : 0);
   }
-  if (!fuse_sm) b.add(1, [=] { softmax_backward(P, dP, T, T, ldT, cs); });
+  if (!fuse_sm) b.add(1, [=] { softmax_backward(P, dP, T, T, ldT, cs); }, 0.0, "softmax_backward");
   const float alpha_b = fuse_sm ? 1.f : alpha;  // fused path already carries alpha in dS
   {  // dq = alpha dS k
     GemmEpilogue e;
@@ -615,10 +681,10 @@ Act Engine::upsample(const Act& x, const std::string& prefix) {
   ConvW cw = load_conv(prefix + ".conv", x.C, x.C, 3);
   Act u = new_act(2 * x.H, 2 * x.W, x.C);
   cudaStream_t cs = st;
-  drawer_fwd.add(1, [=] { upsample2x(x.p, x.H, x.W, x.C, u.p, cs); });
+  drawer_fwd.add(1, [=] { upsample2x(x.p, x.H, x.W, x.C, u.p, cs); }, 0.0, "upsample2x");
   OpList b;
   Act out = conv_fwd_bwd(u, cw, b);
-  b.add(1, [=] { downsum2x(u.g, x.H, x.W, x.C, x.g, cs); });
+  b.add(1, [=] { downsum2x(u.g, x.H, x.W, x.C, x.g, cs); }, 0.0, "downsum2x");
   bwd_stack.push_back(std::move(b));
   return out;
 }
@@ -635,6 +701,9 @@ void Engine::build_vqgan() {
   // GN scratch sized for the largest activation
   // (the cooperative kernels use up to one block per SM, the three-kernel path gn_num_partials blocks)
   gn_part = dalloc<float>((size_t)std::max(gn_num_partials(cfg.image_h * cfg.image_w, 64), num_sms + 1) * 64 + 64);
+  gn_bar.counter = dalloc<unsigned long long>(1);
+  splitk_ws_elems = (size_t)8 << 20;  // 32 MiB of fp32 partial sums: covers every conv the split-K rule selects
+  splitk_ws = dalloc<float>(splitk_ws_elems, false);
   // codebook
   const HostWeight& cb = W(PXR_MOD_VQGAN, "quantize.embedding.weight", {ne, zc});
   std::vector<float> cbT((size_t)zc * ne), c2(ne), mn(zc, 1e30f), mx(zc, -1e30f);
@@ -662,7 +731,7 @@ void Engine::build_vqgan() {
   cudaStream_t cs = st;
   float* zb = z_buf = dalloc<float>(z_numel);
   z_grad = dalloc<float>(z_numel);
-  drawer_fwd.add(2, [=] { vq_nearest(zb, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq.p, cs); });
+  drawer_fwd.add(2, [=] { vq_nearest(zb, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq.p, cs); }, 0.0, "vq_nearest");
 
   // post_quant_conv + decoder
   ConvW pq = load_conv("post_quant_conv", zc, zc, 1);
@@ -678,7 +747,7 @@ void Engine::build_vqgan() {
     b.append(b_in);
     float* zg = z_grad;
     float inv = 1.f / S;
-    b.add(1, [=] { vq_backward(zq.g, inv, zc, hw, zg, cs); });
+    b.add(1, [=] { vq_backward(zq.g, inv, zc, hw, zg, cs); }, 0.0, "vq_backward");
     bwd_stack.push_back(std::move(b));
   }
   hcur = resblock(hcur, "decoder.mid.block_1", block_in, block_in);
@@ -720,14 +789,14 @@ void Engine::build_vqgan() {
   {
     float *ip = img_pre, *im = img;
     int ld = co.cout_pad;
-    drawer_fwd.add(1, [=] { image_finish(co_out, ld, px, ip, im, cs); });
+    drawer_fwd.add(1, [=] { image_finish(co_out, ld, px, ip, im, cs); }, 0.0, "image_finish");
   }
   {
     OpList b;
     float *gi = g_img, *ip = img_pre;
     int ldk = co.cout_k;
     float* part = gn_part;
-    b.add(1, [=] { image_finish_backward(gi, ip, px, ldk, co_g, cs); });
+    b.add(1, [=] { image_finish_backward(gi, ip, px, ldk, co_g, cs); }, 0.0, "image_finish_backward");
     GemmEpilogue e;
     e.out_f16 = a.g;
     e.ldc = block_in;
@@ -753,8 +822,8 @@ void Engine::build_pixel() {
   cudaStream_t cs = st;
   float *zb = z_buf, *ip = img_pre, *im = img, *gi = g_img, *zg = z_grad;
   float inv = 1.f / S;
-  drawer_fwd.add(1, [=] { pixel_synth(zb, rows, cols, H, Wd, ip, im, cs); });
-  drawer_bwd.add(1, [=] { pixel_synth_backward(gi, ip, rows, cols, H, Wd, inv, zg, cs); });
+  drawer_fwd.add(1, [=] { pixel_synth(zb, rows, cols, H, Wd, ip, im, cs); }, 0.0, "pixel_synth");
+  drawer_bwd.add(1, [=] { pixel_synth_backward(gi, ip, rows, cols, H, Wd, inv, zg, cs); }, 0.0, "pixel_synth_backward");
 }
 
 // FftDrawer.synth (fftdrawer.py:78-84): params = rfft2 spectrum [1,3,H,W/2+1,2]; see kernels_fft.cu
@@ -803,8 +872,8 @@ void Engine::build_fft() {
   FftPlans* pl = fft;
   float *zb = z_buf, *x = img_pre, *im = img, *gi = g_img, *zg = z_grad;
   const float inv = 1.f / S;
-  drawer_fwd.add(5, [=] { fft_synth_forward(pl, zb, d_scale, d_M, contrast, scaled, x, part, stats, im, cs); });
-  drawer_bwd.add(4, [=] { fft_synth_backward(pl, gi, im, x, d_scale, d_M, contrast, stats, g1, G, part, inv, zg, cs); });
+  drawer_fwd.add(5, [=] { fft_synth_forward(pl, zb, d_scale, d_M, contrast, scaled, x, part, stats, im, cs); }, 0.0, "fft_synth_forward");
+  drawer_bwd.add(4, [=] { fft_synth_backward(pl, gi, im, x, d_scale, d_M, contrast, stats, g1, G, part, inv, zg, cs); }, 0.0, "fft_synth_backward");
 }
 
 // ===================================================================================================== cutouts
@@ -890,6 +959,8 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
 }
 
 void Engine::forward_cutouts() {
+  if (!aux.empty())  // the cutout / embedding losses accumulate per-rank partial sums into their slots
+    PXR_CUDA(cudaMemsetAsync(losses_dev + total_prompts, 0, sizeof(float) * aux.size(), st));
   pool_forward(img, cfg.image_h, cfg.image_w, cfg.cut_size, pooled, pool_argmax, st);
   cutout_forward(cut_args, batch, part_min, part_max, part_imin, part_imax, st);
   minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
@@ -984,7 +1055,7 @@ void Engine::build_clip(int i) {
   {
     Clip* c = &C;
     float* xo = x0;
-    C.fwd.add(1, [=] { layernorm_forward(c->t, Wd, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, nullptr, xo, c->stats_pre, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(c->t, Wd, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, nullptr, xo, c->stats_pre, cs); }, 0.0, "layernorm_forward");
   }
   for (int l = 0; l < L; ++l) {
     Clip::Layer& Ly = C.layers[l];
@@ -1018,7 +1089,7 @@ void Engine::build_clip(int i) {
     }
     Clip::Layer ly = Ly;
     Clip* c = &C;
-    C.fwd.add(1, [=] { layernorm_forward(ly.x_in, Wd, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(ly.x_in, Wd, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); }, 0.0, "layernorm_forward");
     {
       GemmEpilogue e;
       e.bias = ly.bqkv;
@@ -1049,7 +1120,7 @@ void Engine::build_clip(int i) {
       add_gemm(C.fwd, opK(ly.qkv, 3 * Wd, T, d, Hh, qs0, B, qs1), opK(ly.qkv + Wd, 3 * Wd, T, d, Hh, qs0, B, qs1), T, T,
                d, e, bnS);
     }
-    if (!fuse_sm) C.fwd.add(1, [=] { softmax_forward(ly.P, B * Hh * T, T, ldT, cs); });
+    if (!fuse_sm) C.fwd.add(1, [=] { softmax_forward(ly.P, B * Hh * T, T, ldT, cs); }, 0.0, "softmax_forward");
     {  // O = P v
       GemmEpilogue e;
       e.out_f16 = C.o16;
@@ -1068,7 +1139,7 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.fwd, opK(fuse_attn ? ly.o : C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
     }
-    C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, Wd, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, Wd, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); }, 0.0, "layernorm_forward");
     {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u
       GemmEpilogue e;
       e.bias = ly.bfc;
@@ -1091,7 +1162,7 @@ void Engine::build_clip(int i) {
   C.x_out = x_cur;
   {  // head: ln_post on the class-token rows (row stride T*W), then e = ln @ proj as a GEMM (proj [W, D] is MN-major)
     Clip* c = &C;
-    C.fwd.add(1, [=] { layernorm_forward(c->x_out, (long long)T * Wd, nullptr, T, c->ln_post.gamma, c->ln_post.beta, B, Wd, 1e-5f, c->hcls, nullptr, c->stats_post, cs); });
+    C.fwd.add(1, [=] { layernorm_forward(c->x_out, (long long)T * Wd, nullptr, T, c->ln_post.gamma, c->ln_post.beta, B, Wd, 1e-5f, c->hcls, nullptr, c->stats_post, cs); }, 0.0, "layernorm_forward");
     GemmEpilogue e;
     e.out_f32 = C.e;
     e.ldc = D;
@@ -1131,7 +1202,7 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.g4, 4 * Wd, M, 4 * Wd), opMN(ly.wfc, Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
     }
-    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_mid, Wd, nullptr, T, ly.stats2, ly.ln2.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
+    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_mid, Wd, nullptr, T, ly.stats2, ly.ln2.gamma, M, Wd, 1, c->gx, c->gx16, cs); }, 0.0, "layernorm_backward");
     {  // go = gx Wo
       GemmEpilogue e;
       e.out_f16 = C.go;
@@ -1159,7 +1230,7 @@ void Engine::build_clip(int i) {
       add_gemm(C.bwd, opK(C.go, Wd, T, d, Hh, os0, B, os1), opK(ly.qkv + 2 * Wd, 3 * Wd, T, d, Hh, qs0, B, qs1), T, T, d,
                e, bnS);
     }
-    if (!fuse_sm) C.bwd.add(1, [=] { softmax_backward(ly.P, c->dP, B * Hh * T, T, ldT, cs); });
+    if (!fuse_sm) C.bwd.add(1, [=] { softmax_backward(ly.P, c->dP, B * Hh * T, T, ldT, cs); }, 0.0, "softmax_backward");
     const float scale_b = fuse_sm ? 1.f : scale;
     {  // dq = scale dS k
       GemmEpilogue e;
@@ -1195,11 +1266,11 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.gqkv, 3 * Wd, M, 3 * Wd), opMN(ly.wqkv, Wd, Wd, 3 * Wd), M, Wd, 3 * Wd, e);
     }
-    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_in, Wd, nullptr, T, ly.stats1, ly.ln1.gamma, M, Wd, 1, c->gx, c->gx16, cs); });
+    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_in, Wd, nullptr, T, ly.stats1, ly.ln1.gamma, M, Wd, 1, c->gx, c->gx16, cs); }, 0.0, "layernorm_backward");
   }
   {  // ln_pre backward (x = t + pos), then patch-embed dgrad on token rows 1..np of every image
     Clip* c = &C;
-    C.bwd.add(1, [=] { layernorm_backward(c->gx16, c->t, Wd, c->pos, T, c->stats_pre, c->ln_pre.gamma, M, Wd, 0, c->gx, c->gx16, cs); });
+    C.bwd.add(1, [=] { layernorm_backward(c->gx16, c->t, Wd, c->pos, T, c->stats_pre, c->ln_pre.gamma, M, Wd, 0, c->gx, c->gx16, cs); }, 0.0, "layernorm_backward");
     GemmEpilogue e;
     e.out_f16 = C.g_patches;
     e.ldc = Kp;
@@ -1222,6 +1293,69 @@ void Engine::loss_clip(int i) {
   prompt_loss(C.e, C.B, C.c.out_dim, C.prompts, C.pweights, C.pstops, C.n_prompts, cfg.cutn, S, C.e_unit,
               losses_dev + C.loss_offset, C.de, C.de16, st);
   launches += 1;
+  if (i == cfg.n_clip - 1 && !aux.empty()) aux_after_embed();
+}
+
+// ---- auxiliary losses.  Where each one enters the hand-written backward chain mirrors which tensor the reference
+// loss reads: `globals["embeds"]` (pixray.py:1372-1376, the LAST perceptor's embeddings), `cur_cutouts`, or `out`.
+void Engine::aux_after_embed() {
+  for (size_t k = 0; k < aux.size(); ++k) {
+    AuxLoss& a = aux[k];
+    if (a.kind != PXR_LOSS_AESTHETIC) continue;
+    Clip& C = clip[cfg.n_clip - 1];
+    if (a.n_dev != C.c.out_dim) throw EngineError(-81, "aesthetic head width does not match the last perceptor's embedding");
+    aux_aesthetic(C.e, C.B, C.c.out_dim, cfg.cutn, a.dev, a.prm[1], a.prm[0], a.weight, S, C.de, C.de16, aux_part,
+                  losses_dev + total_prompts + k, st);
+    launches += 2;
+  }
+}
+
+void Engine::aux_on_cutouts() {
+  const int cs_ = cfg.cut_size;
+  for (size_t k = 0; k < aux.size(); ++k) {
+    AuxLoss& a = aux[k];
+    float* slot = losses_dev + total_prompts + k;
+    if (a.kind == PXR_LOSS_SATURATION) {
+      aux_saturation_moments(batch, n_local, cs_, aux_part, aux_sums, st);
+      if (comm) nccl_check(Comm::api().all_reduce(aux_sums, aux_sums, 4, Comm::kFloat64, Comm::kSum, comm, st), "allreduce(saturation moments)");
+      // the value is a function of the GLOBAL moments: one rank contributes it to the (summed) loss vector
+      aux_saturation_grad(batch, n_local, cs_, cfg.cutn, aux_sums, a.weight * a.prm[0], S, cfg.rank == 0, g_batch, slot, st);
+      launches += 3;
+    } else if (a.kind == PXR_LOSS_PALETTE) {
+      aux_palette(batch, n_local, cs_, cfg.cutn, a.dev, a.n_dev / 3, a.weight * a.prm[0], S, g_batch, aux_best, aux_part, slot, st);
+      launches += 2;
+    } else if (a.kind == PXR_LOSS_SMOOTHNESS) {
+      if (comm) {  // torch.gradient runs over the stacked rows of ALL cutouts: two halo rows from each neighbour
+        PXR_CUDA(cudaMemsetAsync(aux_xbuf, 0, sizeof(float) * 12 * cs_ * cfg.world, st));
+        aux_smooth_pack_halo(batch, n_local, cs_, cfg.rank, aux_xbuf, st);
+        nccl_check(Comm::api().all_reduce(aux_xbuf, aux_xbuf, (size_t)12 * cs_ * cfg.world, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(smoothness halo)");
+        aux_smooth_unpack_halo(aux_xbuf, cs_, cfg.rank, cfg.world, aux_halo, st);
+        launches += 3;
+      }
+      aux_smoothness(batch, n_local, cs_, first_global, cfg.cutn, aux_halo, a.prm[2], (int)a.prm[1], a.weight * a.prm[0], S,
+                     aux_A, g_batch, aux_part, slot, st);
+      launches += 3;
+    }
+  }
+}
+
+void Engine::aux_on_image() {
+  const int H = cfg.image_h, Wd = cfg.image_w;
+  for (size_t k = 0; k < aux.size(); ++k) {
+    AuxLoss& a = aux[k];
+    float* slot = losses_dev + total_prompts + k;
+    if (a.kind == PXR_LOSS_SYMMETRY) {
+      aux_symmetry(img, H, Wd, a.weight * a.prm[0], S, g_img, aux_part, slot, st);
+      launches += 2;
+    } else if (a.kind == PXR_LOSS_EDGE) {
+      const int m[4] = {(int)a.prm[2], (int)a.prm[3], (int)a.prm[4], (int)a.prm[5]};
+      aux_edge(img, H, Wd, m, &a.prm[6], a.prm[0], a.prm[1], a.weight, S, g_img, aux_part, slot, st);
+      launches += 2;
+    } else if (a.kind == PXR_LOSS_GAUSSIAN) {
+      aux_gaussian(img, H, Wd, a.prm[1], a.prm[2], &a.prm[3], a.weight * a.prm[0], S, g_img, aux_part, slot, st);
+      launches += 2;
+    }
+  }
 }
 
 void Engine::backward_all() {
@@ -1232,6 +1366,7 @@ void Engine::backward_all() {
     patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, i > 0, g_batch, sums, st);
     launches += 1;
   }
+  if (!aux.empty()) aux_on_cutouts();
   if (comm)  // d/dmin, d/dmax terms need the sums over ALL cutouts
     nccl_check(Comm::api().all_reduce(sums, sums, 2, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(sums)");
   PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * 3 * cfg.cut_size * cfg.cut_size, st));
@@ -1250,6 +1385,8 @@ void Engine::backward_all() {
     nccl_check(c.group_end(), "group end");
     launches += 2;
   }
+  // image losses are replicated (every rank holds the same `out`): added after the exchange, values written, not summed
+  if (!aux.empty()) aux_on_image();
   run(drawer_bwd);
   check_launch("backward");
 }
@@ -1274,6 +1411,12 @@ void Engine::finalize() {
   if (cfg.n_clip < 1 || cfg.n_clip > 2) throw EngineError(-53, "n_clip must be 1 or 2");
   for (int i = 0; i < cfg.n_clip; ++i) build_clip(i);
   losses_dev = dalloc<float>(64);
+  aux_part = dalloc<double>(std::max(4 * AUX_MAX_BLOCKS, n_local) + 8);
+  aux_sums = dalloc<double>(4);
+  aux_A = dalloc<float>(((size_t)n_local * cfg.cut_size + 2) * cfg.cut_size);
+  aux_halo = dalloc<float>((size_t)12 * cfg.cut_size);
+  aux_xbuf = dalloc<float>((size_t)12 * cfg.cut_size * cfg.world);
+  aux_best = dalloc<int>((size_t)n_local * cfg.cut_size * cfg.cut_size);
   PXR_CUDA(cudaMallocHost((void**)&losses_host, 64 * sizeof(float)));
   PXR_CUDA(cudaStreamSynchronize(st));
   {
@@ -1290,6 +1433,8 @@ void Engine::finalize() {
     reg("sums", sums, 16);
     reg("z_grad", z_grad, z_numel * 4);
     reg("z", z_buf, z_numel * 4);
+    reg("losses", losses_dev, 64 * 4);
+    reg("palette_best", aux_best, ncs / 3 * n_local * 4);
     reg("minv", minv_dev, (size_t)n_local * 36);
     for (int i = 0; i < cfg.n_clip; ++i) {
       Clip& C = clip[i];
@@ -1403,7 +1548,7 @@ int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int 
       e->clip[i].loss_offset = off;
       off += e->clip[i].n_prompts;
     }
-    if (off > 64) throw EngineError(-16, "at most 64 prompts in total");
+    if (off + (int)e->aux.size() > 64) throw EngineError(-16, "at most 64 losses (prompts + auxiliary) in total");
     e->total_prompts = off;
   });
 }
@@ -1513,7 +1658,7 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
     if (out_losses_host) {
       PXR_CUDA(cudaMemcpyAsync(e->losses_host, e->losses_dev, 64 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
       PXR_CUDA(cudaStreamSynchronize(e->st));
-      memcpy(out_losses_host, e->losses_host, sizeof(float) * e->total_prompts);
+      memcpy(out_losses_host, e->losses_host, sizeof(float) * e->num_losses());
     }
   });
 }
@@ -1572,6 +1717,65 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_add_aux_loss(pxr_handle h, int kind, float weight, const float* params, int n_params) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (e->num_losses() >= 64) throw EngineError(-16, "at most 64 losses (prompts + auxiliary) in total");
+    auto need = [&](int n, const char* what) {
+      if (n_params < n || !params) throw EngineError(-80, std::string("pxr_add_aux_loss: ") + what);
+    };
+    Engine::AuxLoss a;
+    a.kind = kind;
+    a.weight = weight;
+    a.prm.assign(params, params + (n_params > 0 ? n_params : 0));
+    switch (kind) {
+      case PXR_LOSS_SYMMETRY: need(1, "symmetry needs {symmetry_weight}"); break;
+      case PXR_LOSS_SATURATION: need(1, "saturation needs {saturation_weight}"); break;
+      case PXR_LOSS_PALETTE:
+        need(4, "palette needs {palette_weight, r,g,b, ...}");
+        if ((n_params - 1) % 3) throw EngineError(-80, "pxr_add_aux_loss: palette colours come as r,g,b triples");
+        a.dev = e->upload(std::vector<float>(params + 1, params + n_params));
+        a.n_dev = n_params - 1;
+        break;
+      case PXR_LOSS_SMOOTHNESS:
+        need(3, "smoothness needs {smoothness_weight, type, spacing}");
+        if (params[1] < 0 || params[1] > 2 || params[2] <= 0) throw EngineError(-80, "pxr_add_aux_loss: smoothness type in {0,1,2}, spacing > 0");
+        break;
+      case PXR_LOSS_EDGE: need(9, "edge needs {edge_color_weight, global_color_weight, left,right,upper,lower, r,g,b}"); break;
+      case PXR_LOSS_GAUSSIAN:
+        need(6, "gaussian needs {gaussian_weight, std_y, std_x, R,G,B}");
+        if (params[1] <= 0 || params[2] <= 0) throw EngineError(-80, "pxr_add_aux_loss: gaussian std must be positive");
+        break;
+      case PXR_LOSS_AESTHETIC:
+        need(3, "aesthetic needs {target, bias, w[D]}");
+        a.dev = e->upload(std::vector<float>(params + 2, params + n_params));
+        a.n_dev = n_params - 2;
+        break;
+      default: throw EngineError(-80, "pxr_add_aux_loss: unknown loss kind");
+    }
+    e->aux.push_back(std::move(a));
+  });
+}
+
+int pxr_clear_aux_losses(pxr_handle h) {
+  PXR_TRY(h, h->e->aux.clear());
+}
+
+int pxr_num_losses(pxr_handle h, int* out) {
+  *out = h->e->num_losses();
+  return 0;
+}
+
+int pxr_read_losses(pxr_handle h, float* out_host) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    PXR_CUDA(cudaMemcpyAsync(e->losses_host, e->losses_dev, 64 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+    memcpy(out_host, e->losses_host, sizeof(float) * e->num_losses());
   });
 }
 

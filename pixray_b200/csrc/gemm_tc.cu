@@ -418,7 +418,10 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
     const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+    const int kb_begin = p.k_splits > 1 ? t.z * p.kb_per_split : 0;
+    const int kb_end = p.k_splits > 1 ? min(p.num_k_blocks, kb_begin + p.kb_per_split) : p.num_k_blocks;
+    const int img = p.k_splits > 1 ? 0 : t.z;  // split-K: z is the split, there is one image
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
       const int tap = kb / p.k_blocks_per_tap;
       const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
       mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -436,7 +439,7 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem
           dy = tap / 3 - 1;
           dx = tap % 3 - 1;
         }
-        tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
+        tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, img);
       }
       if (p.b_mode == OP_KMAJOR) {
         tma_load_4d(&p.tma_b, &full_bar[stage], sb, kk, t.n0 + tap * p.b_tap_rows, bb0, bb1);
@@ -473,7 +476,13 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uin
     mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+    int kb_begin = 0, kb_end = p.num_k_blocks;
+    if (p.k_splits > 1) {
+      const int z = tile / (p.tiles_m * p.tiles_n);
+      kb_begin = z * p.kb_per_split;
+      kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+    }
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
@@ -482,7 +491,7 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uin
       for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
         const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
         const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-        umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_f16(d_tmem, ad, bd, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
       }
       umma_commit(&empty_bar[stage]);
       if (++stage == p.stages) {
@@ -1285,7 +1294,7 @@ namespace {
 // CTA pairs need (see gemm_tc2_body): a generic epilogue, an even split of the B tile, at least two M tiles.
 int decide_cta_group(const GemmParams& p, const GemmEpilogue& epi, int block_n, int num_sms) {
   const bool softmax_epi = epi.act == ACT_SOFTMAX || epi.act == ACT_SOFTMAX_BWD;
-  const bool can_pair = !softmax_epi && block_n % 32 == 0 && (p.b_mode != OP_MNMAJOR || block_n % 128 == 0) &&
+  const bool can_pair = p.k_splits <= 1 && !softmax_epi && block_n % 32 == 0 && (p.b_mode != OP_MNMAJOR || block_n % 128 == 0) &&
                         p.tiles_m >= 2 && num_sms >= 2;
   const int want = epi.cta_group ? epi.cta_group : gemm_default_cta_group();
   return (want == 1 || !can_pair) ? 1 : 2;
@@ -1298,7 +1307,7 @@ int decide_tma_epi(const GemmParams& p, const GemmEpilogue& e, int block_n) {
     const char* v = getenv("PXR_GEMM_TMA_EPI");
     return !(v && atoi(v) == 0);
   }();
-  if (!enabled || e.tma_epi < 0 || e.bias_per_row || p.fmt != 0) return TE_NONE;
+  if (!enabled || e.tma_epi < 0 || e.bias_per_row || p.fmt != 0 || p.k_splits > 1) return TE_NONE;
   int mode = TE_NONE;
   const bool no_res = !e.res_f32 && !e.res_f16;
   if (e.act == ACT_NONE && e.out_f16 && !e.out_f32 && !e.res_f32 && !e.aux_out) mode = e.res_f16 ? TE_RES16 : TE_F16;
@@ -1467,6 +1476,8 @@ int gemm_plan_make(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
     return -21;
   }
   p.total_tiles = p.tiles_m * p.tiles_n * nb0 * nb1;
+  p.k_splits = 1;
+  p.kb_per_split = p.num_k_blocks;
   int rc = encode_operand(&p.tma_a, A, GEMM_BLOCK_M, fmt, err, errlen);
   if (rc) return rc;
   p.cta_group = decide_cta_group(p, epi, block_n, num_sms);
@@ -1510,6 +1521,18 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
   p.b_batched = 0;
   p.b_tap_rows = cout_pad;
   p.total_tiles = p.tiles_m * p.tiles_n * batch;
+  p.k_splits = 1;
+  p.kb_per_split = p.num_k_blocks;
+  if (epi.k_splits > 1) {
+    if (batch != 1 || !epi.out_f32 || epi.out_f16 || epi.bias || epi.res_f16 || epi.res_f32 || epi.act != ACT_NONE) {
+      set_err(err, errlen, "split-K conv: one image, plain fp32 partial sums only");
+      return -32;
+    }
+    p.kb_per_split = (p.num_k_blocks + epi.k_splits - 1) / epi.k_splits;
+    p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.nb0 = p.k_splits;  // decode_tile: z = split
+    p.total_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+  }
   {
     uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)W, (uint64_t)H, (uint64_t)batch};
     uint64_t strides[3] = {(uint64_t)in_ld, (uint64_t)in_ld * W, (uint64_t)in_ld * W * H};
@@ -1531,6 +1554,51 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
   plan->flops = 2.0 * H * W * (double)n_out * c_in * p.num_taps * batch;
   GemmEpilogue e = epi;
   return finish_plan(plan, e, block_n, num_sms, err, errlen);
+}
+
+namespace {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long pixels,
+                                                            int N, int ld_ws, const float* __restrict__ bias,
+                                                            const __half* __restrict__ res, __half* __restrict__ out,
+                                                            int ld_out) {
+  const int vecs = N / 8;
+  const long long n = pixels * vecs;
+  const size_t slab = static_cast<size_t>(pixels) * ld_ws;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long px = i / vecs;
+    const int c0 = static_cast<int>(i % vecs) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
+    const float* src = ws + static_cast<size_t>(px) * ld_ws + c0;
+    for (int s = 0; s < splits; ++s) {  // fixed order: deterministic
+      const float4 a = *reinterpret_cast<const float4*>(src + s * slab), b = *reinterpret_cast<const float4*>(src + s * slab + 4);
+      acc[0] += a.x;
+      acc[1] += a.y;
+      acc[2] += a.z;
+      acc[3] += a.w;
+      acc[4] += b.x;
+      acc[5] += b.y;
+      acc[6] += b.z;
+      acc[7] += b.w;
+    }
+    if (res) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + static_cast<size_t>(px) * ld_out + c0), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += r[j];
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(px) * ld_out + c0) = pack8(acc);
+  }
+}
+}  // namespace
+
+void splitk_reduce(const float* ws, int splits, long long pixels, int N, int ld_ws, const float* bias,
+                   const __half* res, __half* out, int ld_out, cudaStream_t stream) {
+  const long long n = pixels * (N / 8);
+  long long g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  splitk_reduce_kernel<<<static_cast<int>(g), 256, 0, stream>>>(ws, splits, pixels, N, ld_ws, bias, res, out, ld_out);
 }
 
 #define PXR_LAUNCH_TCE2(MODE) \

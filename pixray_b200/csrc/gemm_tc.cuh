@@ -62,6 +62,9 @@ struct GemmParams {
   long long ldc, out_bs0, out_bs1;
   int vec_ok;          // 16-byte vector epilogue accesses allowed (alignment checked on host)
   int cta_group;       // 1: one CTA per tile; 2: CTA pairs (cta_group::2) on 256 x block_n tile pairs
+  // split-K (conv only): the "batch" index of a tile selects the k-block range [z * kb_per_split, ...) and the fp32
+  // partial-sum slab z of the output workspace; k_splits == 1 otherwise
+  int k_splits, kb_per_split;
   // tensor-map epilogue (tma_epi != TE_NONE): outputs leave through TMA stores of 32-row x 64-byte boxes staged in
   // shared memory in the accumulator's own row-per-lane layout; input tensors arrive the same way (prefetched)
   int tma_epi;
@@ -97,6 +100,7 @@ struct GemmEpilogue {
   int n_store = 0;  // softmax modes: zero-fill columns [N, n_store)
   int cta_group = 0;  // 0 = auto, 1 / 2 = force
   int tma_epi = 0;    // 0 = auto (tensor-map epilogue when the tensors allow it), -1 = force the generic epilogue
+  int k_splits = 1;   // conv_plan_make only: > 1 writes fp32 partial sums [k_splits][pixels][ldc] to out_f32
 };
 
 struct GemmPlan {
@@ -119,6 +123,11 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
                    int num_sms, char* err, int errlen);
 
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+
+// out[p, n] = fp16( sum_s ws[s][p][n] + bias[n] + res[p][n] ), n < N: the epilogue of a split-K convolution.
+// ws: [splits][pixels][ld_ws] fp32; res / out: [pixels][ld_out] fp16 (res may be null); N, ld_* multiples of 8.
+void splitk_reduce(const float* ws, int splits, long long pixels, int N, int ld_ws, const float* bias,
+                   const __half* res, __half* out, int ld_out, cudaStream_t stream);
 
 // 4-D tiled tensor map, zero fill out of bounds, 128-byte swizzle (fmt 0 = fp16, 1 = bf16, 2 = fp32); strides in elements.
 // Shared with attn_tc.cu.  Returns 0 on success, otherwise writes a message to err.

@@ -30,15 +30,21 @@ void gn_backward(const act_t* dy, const act_t* x, const float* stats, const floa
                  int pixels, int C, int swish, const act_t* dres, float* part, float* gstats, act_t* dx,
                  cudaStream_t st);
 
-// The same two operations as ONE cooperative kernel each (grid-wide barrier between the statistics and the apply
+// The same two operations as ONE kernel each (grid <= one block per SM, grid-wide barrier between the statistics and the apply
 // phase, the block's slab of x kept in shared memory): 1 launch and 1 HBM pass instead of 3 launches and 2 passes.
 // `part` needs 64 floats per block (<= num_sms blocks).  gn_coop_supported: the slab of a block fits shared memory.
+// The grid-wide barrier is a monotonically growing device counter; `issued` mirrors on the host what the launches so far
+// will have added, so each launch knows the value it waits for (one GridBarrier per stream).
+struct GridBarrier {
+  unsigned long long* counter = nullptr;  // device, zero-initialised
+  unsigned long long issued = 0;
+};
 bool gn_coop_supported(int pixels, int C, int num_sms);
 void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int pixels, int C, int swish, float eps,
-                     float* part, float* stats, act_t* y, int num_sms, cudaStream_t st);
+                     float* part, float* stats, act_t* y, int num_sms, GridBarrier* gb, cudaStream_t st);
 void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
                       int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
-                      cudaStream_t st);
+                      GridBarrier* gb, cudaStream_t st);
 
 void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st);        // nearest, [H,W,C]->[2H,2W,C]
 void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st);       // adjoint: [2H,2W,C]->[H,W,C]
@@ -130,6 +136,38 @@ void prompt_loss(const float* e, int B, int D, const float* prompts, const float
 void adam_clip_step(float* z, float* m, float* v, const float* g, float inv_scale, int n, int per_channel,
                     const float* zmin, const float* zmax, int clip01, float lr, float b1, float b2, float eps, int t,
                     cudaStream_t st);
+
+// ------------------------------------------------------------------ auxiliary losses (Losses/*.py), kernels_losses.cu
+// Every launcher adds grad_scale * weight * dL/dx into the fp32 gradient buffer of the tensor the reference loss reads
+// and writes (image losses) or accumulates (cutout / embedding losses: per-rank partial sums) the weighted loss value.
+// `part`: scratch of max(4 * AUX_MAX_BLOCKS, n_local) doubles.  `weight` = the loss's own *_weight setting times the
+// custom_loss spec weight (pixray.py:1388).
+constexpr int AUX_MAX_BLOCKS = 1024;
+void aux_symmetry(const float* img, int H, int W, float weight, float grad_scale, float* g_img, double* part,
+                  float* loss_out, cudaStream_t st);
+// margins = (left, right, upper, lower) in pixels (EdgeLoss.py:82-88), colour in [0,1]
+void aux_edge(const float* img, int H, int W, const int margins[4], const float color[3], float edge_color_weight,
+              float global_color_weight, float weight, float grad_scale, float* g_img, double* part, float* loss_out,
+              cudaStream_t st);
+void aux_gaussian(const float* img, int H, int W, float stdy, float stdx, const float color255[3], float weight,
+                  float grad_scale, float* g_img, double* part, float* loss_out, cudaStream_t st);
+// best_out (optional): nearest-palette index per pixel [n_img * cs * cs] (the loss's integer bookkeeping)
+void aux_palette(const float* batch, int n_img, int cs, int cutn_global, const float* palette_dev, int n_colors,
+                 float weight, float grad_scale, float* g_batch, int* best_out, double* part, float* loss_out,
+                 cudaStream_t st);
+// saturation: local moment sums (4 doubles) -> [allreduce over ranks] -> gradient from the global moments
+void aux_saturation_moments(const float* batch, int n_img, int cs, double* part, double* sums, cudaStream_t st);
+void aux_saturation_grad(const float* batch, int n_img, int cs, int cutn_global, const double* sums, float weight,
+                         float grad_scale, int write_loss, float* g_batch, float* loss_out, cudaStream_t st);
+// A: scratch [(n_img * cs + 2) * cs] floats; halo: [2][2][3][cs] rows around this rank's slab (unused when world == 1)
+void aux_smoothness(const float* batch, int n_img, int cs, int first_global, int cutn_global, const float* halo,
+                    float spacing, int kind, float weight, float grad_scale, float* A, float* g_batch, double* part,
+                    float* loss_out, cudaStream_t st);
+void aux_smooth_pack_halo(const float* batch, int n_img, int cs, int rank, float* xbuf, cudaStream_t st);
+void aux_smooth_unpack_halo(const float* xbuf, int cs, int rank, int world, float* halo, cudaStream_t st);
+void aux_aesthetic(const float* e, int n_local, int D, int cutn_global, const float* w_dev, float bias, float target,
+                   float weight, float grad_scale, float* de, __half* de16, double* part, float* loss_out,
+                   cudaStream_t st);
 
 void fill_f32(float* p, float v, long long n, cudaStream_t st);
 void cast_f32_to_f16(const float* x, act_t* y, long long n, float scale, cudaStream_t st);

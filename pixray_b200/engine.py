@@ -11,6 +11,7 @@ import torch
 from . import _lib
 
 DRAWER_VQGAN, DRAWER_PIXEL, DRAWER_FFT = 0, 1, 2
+LOSS_SYMMETRY, LOSS_SATURATION, LOSS_PALETTE, LOSS_SMOOTHNESS, LOSS_EDGE, LOSS_GAUSSIAN, LOSS_AESTHETIC = range(7)
 PAD_REFLECTION, PAD_BORDER = 0, 1
 MOD_VQGAN, MOD_CLIP0, MOD_CLIP1 = 0, 1, 2
 
@@ -137,6 +138,28 @@ class B200Engine:
                                       w.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p))
         self._check(rc, "pxr_set_prompts")
         self.n_prompts[clip_idx] = n
+
+    def add_aux_loss(self, kind, weight, params):
+        """One more entry of the loss vector / term of the gradient (pxr_add_aux_loss; Losses/*.py).  Returns the
+        index of its value in the loss vector."""
+        a = np.ascontiguousarray(np.asarray(params, dtype=np.float32).reshape(-1))
+        rc = self.lib.pxr_add_aux_loss(self.h, int(kind), C.c_float(float(weight)), a.ctypes.data_as(C.c_void_p), int(a.size))
+        self._check(rc, "pxr_add_aux_loss")
+        return self.num_losses() - 1
+
+    def clear_aux_losses(self):
+        self._check(self.lib.pxr_clear_aux_losses(self.h), "pxr_clear_aux_losses")
+
+    def num_losses(self):
+        n = C.c_int()
+        self.lib.pxr_num_losses(self.h, C.byref(n))
+        return n.value
+
+    def read_losses(self):
+        """The loss vector of the last forward/backward: prompts of every perceptor, then the auxiliary losses."""
+        out = np.zeros(max(self.num_losses(), 1), dtype=np.float32)
+        self._check(self.lib.pxr_read_losses(self.h, out.ctypes.data_as(C.c_void_p)), "pxr_read_losses")
+        return out[:self.num_losses()]
 
     def init_comm(self):
         """Cutout-sharded multi-GPU mode: rank 0 draws an ncclUniqueId, torch.distributed (already initialised by the

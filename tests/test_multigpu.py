@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, with_aux=False):
     import torch.distributed as dist
     from test_pipeline_gpu import SMALL_CLIP, SMALL_VQ, plant_extremes, random_transforms
     from oracle import ref_path as R
@@ -44,15 +44,29 @@ def _worker(rank, world, port, out_dir):
     z = (vq.quantize.embedding.weight[idx].T.reshape(1, 128, 16, 16) + 0.05 * torch.randn(1, 128, 16, 16, generator=g)).contiguous()
     T = random_transforms(cutn, cs, 3)
     facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
+    aux = []
+    if with_aux:
+        # auxiliary losses under sharding: saturation needs the GLOBAL colour moments, smoothness the neighbouring ranks'
+        # boundary rows (the reference differentiates across the stacked cutouts), the image losses are replicated
+        pal = [[0.9, 0.1, 0.1], [0.1, 0.8, 0.2], [0.2, 0.2, 0.9]]
+        hw_ = torch.randn(1, 64, generator=torch.Generator().manual_seed(5)) * 0.3
+        eng.add_aux_loss(E.LOSS_SATURATION, 0.5, [1.3])
+        eng.add_aux_loss(E.LOSS_SMOOTHNESS, 2.0, [0.9, 0, 1])
+        eng.add_aux_loss(E.LOSS_PALETTE, 1.0, [0.8] + [c for row in pal for c in row])
+        eng.add_aux_loss(E.LOSS_SYMMETRY, 1.5, [0.7])
+        eng.add_aux_loss(E.LOSS_AESTHETIC, 0.8, [10.0, 0.7] + hw_.reshape(-1).tolist())
+        aux = [(0.5, lambda o, b, e: R.saturation_loss(b, 1.3)), (2.0, lambda o, b, e: R.smoothness_loss(b, 0.9)),
+               (1.0, lambda o, b, e: R.palette_loss(b, pal, 0.8)[0]), (1.5, lambda o, b, e: R.symmetry_loss(o, 0.7)),
+               (0.8, lambda o, b, e: R.aesthetic_loss(e, hw_, torch.tensor([0.7]), 10.0))]
     zc = z.clone().cuda()
-    losses = np.zeros(2, dtype=np.float32)
+    losses = np.zeros(2 + len(aux), dtype=np.float32)
     eng.iterate(zc, 0.05, 0, params=dict(transforms=T, zoom_padding=0, fill=0.4, noise_facs=facs.numpy(), noise=noise),
                 losses_out=losses)
     zg = eng.debug_read("z_grad", z.shape).cpu()
     torch.save(dict(zg=zg, losses=losses.copy(), z=zc.cpu()), os.path.join(out_dir, f"rank{rank}.pt"))
     if rank == 0:
         ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), cs, "reflection", 0.4,
-                        facs, noise)
+                        facs, noise, aux=aux)
         torch.save(dict(zg=ref["z_grad"], losses=torch.stack([l.reshape(()) for l in ref["losses"]])),
                    os.path.join(out_dir, "ref.pt"))
     dist.barrier()
@@ -71,3 +85,18 @@ def test_cutout_sharded_two_ranks(tmp_path):
     print(f"[parity] 2-rank sharded z.grad: max_abs_err={err:.3e} ref_max={mag:.3e}; losses {r0['losses']} vs {ref['losses']}")
     assert err <= 3e-2 * mag
     assert np.abs(r0["losses"] - ref["losses"].numpy()).max() < 5e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_cutout_sharded_two_ranks_with_aux_losses(tmp_path):
+    """Same, with auxiliary losses: their values and gradients must not depend on how the cutouts are sharded."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), True), nprocs=2, join=True)
+    r0, r1, ref = (torch.load(tmp_path / n, weights_only=False) for n in ("rank0.pt", "rank1.pt", "ref.pt"))
+    assert torch.equal(r0["zg"], r1["zg"]) and torch.equal(r0["z"], r1["z"])
+    err = (r0["zg"] - ref["zg"]).abs().max().item()
+    mag = ref["zg"].abs().max().item()
+    print(f"[parity] 2-rank sharded z.grad with aux losses: max_abs_err={err:.3e} ref_max={mag:.3e}; losses {r0['losses']} vs {ref['losses']}")
+    assert err <= 3e-2 * mag
+    assert np.abs(r0["losses"] - ref["losses"].numpy()).max() < 5e-3
+    assert np.array_equal(r0["losses"], r1["losses"])

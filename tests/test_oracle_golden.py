@@ -157,3 +157,57 @@ def test_vit_restatement_matches_transformers_clip():
         a = mine.encode_image(x)
         b = hf(pixel_values=x).image_embeds
     close(a, b, 1e-4)
+
+
+# ------------------------------------------------------------------ auxiliary losses (Losses/*.py), oracle/make_golden_aux.py
+GA = np.load(os.path.join(os.path.dirname(__file__), "golden", "aux_loss_vectors.npz"))
+
+
+def ta(name):
+    return torch.from_numpy(np.asarray(GA[name]))
+
+
+def _check_aux(tag, fn, on_cut):
+    x = (ta("cut") if on_cut else ta("out")).clone().requires_grad_(True)
+    val = fn(x)
+    val.backward()
+    close(val.detach(), ta(tag + "_val"), 2e-6)
+    close(x.grad, ta(tag + "_grad"), 2e-6)
+
+
+def test_aux_symmetry():
+    _check_aux("symmetry", lambda o: R.symmetry_loss(o, 0.7), False)
+
+
+def test_aux_saturation():
+    _check_aux("saturation", lambda c: R.saturation_loss(c, 1.3), True)
+
+
+def test_aux_palette():
+    _check_aux("palette", lambda c: R.palette_loss(c, ta("palette"), 0.8)[0], True)
+
+
+@pytest.mark.parametrize("kind", ["default", "clipped", "log"])
+def test_aux_smoothness(kind):
+    _check_aux("smooth_" + kind, lambda c: R.smoothness_loss(c, 0.9, kind), True)
+
+
+def test_aux_smoothness_spacing():
+    _check_aux("smooth_spacing2", lambda c: R.smoothness_loss(c, 1.0, "default", spacing=2), True)
+
+
+def test_aux_edge():
+    margins = R.edge_margins_px([10, 20, 15, 0], 20, 28)
+    _check_aux("edge", lambda o: R.edge_loss(o, ta("edge_color").tolist(), margins, 0.1, 0.05), False)
+
+
+def test_aux_gaussian():
+    _check_aux("gaussian", lambda o: R.gaussian_loss(o, (6.0, 9.0), (255, 128, 0), 0.6), False)
+
+
+def test_aux_aesthetic():
+    e = ta("aes_emb").clone().requires_grad_(True)
+    val = R.aesthetic_loss(e, ta("aes_w"), ta("aes_b"), 10.0)
+    val.backward()
+    close(val.detach(), ta("aes_val"), 2e-6)
+    close(e.grad, ta("aes_grad"), 2e-6)
