@@ -645,6 +645,27 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* x) {
   }
 }
 
+// QuickGELU and its derivative on packed fp16 pairs for the tensor-map epilogue (the fp32 form costs ~8 instructions per
+// element with two MUFU ops and made the fc1 / fc2-dgrad epilogues ALU-bound: ncu showed the 8 epilogue warps pacing
+// the tile loop at 1.6x the MMA time).  sigmoid(z) = 0.5 tanh(z / 2) + 0.5 with tanh.approx.f16x2: one MUFU per pair.
+// The operands are already fp16 here (u is stored as fp16; the reference runs its CLIP in fp16 on CUDA, slip.py:176).
+__device__ __forceinline__ __half2 tanh_h2(__half2 x) {
+  uint32_t r, a = *reinterpret_cast<uint32_t*>(&x);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ __half2 sigmoid1702_h2(__half2 u) {
+  const __half2 t = tanh_h2(__hmul2(u, __float2half2_rn(0.851f)));
+  return __hfma2(t, __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+}
+__device__ __forceinline__ __half2 quickgelu_h2(__half2 u) { return __hmul2(u, sigmoid1702_h2(u)); }
+__device__ __forceinline__ __half2 quickgelu_grad_h2(__half2 u) {
+  const __half2 s = sigmoid1702_h2(u);
+  const __half2 a = __hmul2(u, __float2half2_rn(1.702f));
+  const __half2 b = __hfma2(__hneg2(s), a, a);  // 1.702 u (1 - s)
+  return __hfma2(s, b, s);                       // s (1 + 1.702 u (1 - s))
+}
+
 template <int MODE, bool PAIR>
 __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* wbuf, uint64_t* in_bar,
                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
@@ -757,12 +778,27 @@ __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* 
         for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + te_off(lane, c)) = pack8(x + 8 * c);
       } else if (MODE == TE_GELU) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + te_off(lane, c)) = pack8(x + 8 * c);
+        for (int c = 0; c < 4; ++c) {
+          uint4 u = pack8(x + 8 * c);  // the saved pre-activation (fp16), and the activation of exactly that value
+          *reinterpret_cast<uint4*>(buf + te_off(lane, c)) = u;
+          __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-        for (int i = 0; i < BW; ++i) x[i] = quickgelu(x[i]);
+          for (int j = 0; j < 4; ++j) h[j] = quickgelu_h2(h[j]);
+          *reinterpret_cast<uint4*>(buf + TE_BUF_BYTES + te_off(lane, c)) = u;
+        }
+      } else if (MODE == TE_GELU_BWD) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(buf + TE_BUF_BYTES + te_off(lane, c)) = pack8(x + 8 * c);
-      } else if (MODE == TE_GELU_BWD || MODE == TE_RES16) {
+        for (int c = 0; c < 4; ++c) {
+          uint4* ptr = reinterpret_cast<uint4*>(buf + te_off(lane, c));
+          uint4 u = *ptr;
+          uint4 g = pack8(x + 8 * c);
+          const __half2* uh = reinterpret_cast<const __half2*>(&u);
+          __half2* gh = reinterpret_cast<__half2*>(&g);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gh[j] = __hmul2(gh[j], quickgelu_grad_h2(uh[j]));
+          *ptr = g;
+        }
+      } else if (MODE == TE_RES16) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4* ptr = reinterpret_cast<uint4*>(buf + te_off(lane, c));

@@ -88,7 +88,8 @@ def test_aux_loss_value_and_gradient(setup, name):
     assert np.isfinite(cur["losses"]).all()
     assert abs(cur["losses"][idx] - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
     assert np.allclose(cur["losses"][:2], base["losses"][:2], atol=0)  # prompt losses untouched
-    assert mag > 0 and err <= 1e-4 * mag + 1e-9
+    floor = 4 * 2.0 ** -24 * base[key].abs().max().item()  # fp32 rounding of the buffer the term is added into
+    assert mag > 0 and err <= 1e-4 * mag + floor
     if name == "palette":  # integer bookkeeping: nearest-palette index per pixel, bit-exact away from near-ties
         best = eng.debug_read("palette_best", (CUTN * CS * CS,), dtype=torch.int32).cpu().long()
         px = base["batch"].permute(0, 2, 3, 1).reshape(-1, 3)
