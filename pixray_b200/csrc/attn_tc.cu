@@ -146,6 +146,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     if (lane == 0) {
       const uint32_t id_s = make_idesc_f16(128, n_pad, 0, 0, 0);
       const uint32_t id_pv = make_idesc_f16(128, 64, 0, 0, 1);
+      // descriptors are built once; advancing an operand by X bytes adds X >> 4 to the address field (the single issuing
+      // thread is on the critical path of every phase: keep its instruction count down)
+      constexpr uint64_t AT = ATOM >> 4;
+      const uint64_t d_q = desc_k(s_base + F_Q), d_k = desc_k(s_base + F_K), d_v = desc_mn(s_base + F_V, 8192);
+      const uint64_t d_p0 = desc_k(s_base + F_P0), d_p1 = desc_k(s_base + F_P1);
+      const int n_k = n_pad / 16;
       int it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         mbar_wait(bar_qk, it & 1);
@@ -153,19 +159,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         tc_fence_after();
         for (int mt = 0; mt < n_mt; ++mt) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + mt * 256, desc_k(s_base + F_Q + mt * ATOM + k * 32), desc_k(s_base + F_K + k * 32), id_s,
-                     k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + mt * 256, d_q + mt * AT + 2 * k, d_k + 2 * k, id_s, k ? 1u : 0u);
         }
         umma_commit(bar_s);
         mbar_wait(bar_v, it & 1);
         for (int mt = 0; mt < n_mt; ++mt) {
           mbar_wait(&bar_p[mt], it & 1);
           tc_fence_after();
-          const uint32_t pb = s_base + (mt ? F_P1 : F_P0);
-          for (int k = 0; k < n_pad / 16; ++k)
-            umma_f16(tmem_base + mt * 256, desc_k(pb + (k >> 2) * ATOM + (k & 3) * 32), desc_mn(s_base + F_V + k * 2048, 8192),
-                     id_pv, k ? 1u : 0u);
+          const uint64_t pa = mt ? d_p1 : d_p0;
+          const uint32_t d_o = tmem_base + mt * 256;
+#pragma unroll 4
+          for (int k = 0; k < n_k; ++k)
+            umma_f16(d_o, pa + (k >> 2) * AT + (k & 3) * 2, d_v + k * 128, id_pv, k ? 1u : 0u);
           umma_commit(&bar_o[mt]);
         }
       }
@@ -339,6 +344,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
       const uint32_t id_dq = make_idesc_f16(128, 64, 0, 0, 1);     // dQ = dS K: A K-major, B MN-major
       const uint32_t id_t = make_idesc_f16(128, 64, 0, 1, 1);      // dV = P^T dO, dK = dS^T Q: both MN-major
       const uint32_t tA = tmem_base;
+      // descriptors built once, advanced by adds on the address field (see the forward kernel)
+      constexpr uint64_t AT = ATOM >> 4;
+      const uint64_t dk_q = desc_k(s_base + B_Q), dk_k = desc_k(s_base + B_K), dk_v = desc_k(s_base + B_V),
+                     dk_do = desc_k(s_base + B_DO), dk_ps = desc_k(s_base + B_PS);
+      const uint64_t dm_ps = desc_mn(s_base + B_PS, ATOM), dm_do = desc_mn(s_base + B_DO, 8192),
+                     dm_q = desc_mn(s_base + B_Q, 8192), dm_k = desc_mn(s_base + B_K, 8192);
+      const int n_k = n_pad / 16;
       int it = 0, cnt = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         mbar_wait(bar_load, it & 1);
@@ -352,30 +364,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
           const int rows_left = T - mt * 128;
           const int ksi = rows_left >= 128 ? 8 : (rows_left + 15) / 16;  // 16-row reduction steps over this tile's queries
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tA, desc_k(s_base + B_Q + mt * ATOM + k * 32), desc_k(s_base + B_K + k * 32), id_s, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tA, dk_q + mt * AT + 2 * k, dk_k + 2 * k, id_s, k ? 1u : 0u);
           umma_commit(bar_s);
           mbar_wait(bar_p, cnt & 1);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tA, desc_k(s_base + B_DO + mt * ATOM + k * 32), desc_k(s_base + B_V + k * 32), id_s, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tA, dk_do + mt * AT + 2 * k, dk_v + 2 * k, id_s, k ? 1u : 0u);
           umma_commit(bar_dp);
-          for (int jt = 0; jt < n_mt; ++jt)
+          for (int jt = 0; jt < n_mt; ++jt) {
+            const uint64_t a0 = dm_ps + 2 * jt * AT, b0 = dm_do + mt * AT;
+#pragma unroll 4
             for (int ks = 0; ks < ksi; ++ks)
-              umma_f16(tmem_base + TM_DV + jt * 64, desc_mn(s_base + B_PS + 2 * jt * ATOM + ks * 2048, ATOM),
-                       desc_mn(s_base + B_DO + mt * ATOM + ks * 2048, 8192), id_t, (mt | ks) ? 1u : 0u);
+              umma_f16(tmem_base + TM_DV + jt * 64, a0 + ks * 128, b0 + ks * 128, id_t, (mt | ks) ? 1u : 0u);
+          }
           umma_commit(bar_pfree);
           mbar_wait(bar_ds, cnt & 1);
           tc_fence_after();
-          for (int k = 0; k < n_pad / 16; ++k)
-            umma_f16(tA, desc_k(s_base + B_PS + (k >> 2) * ATOM + (k & 3) * 32), desc_mn(s_base + B_K + k * 2048, 8192),
-                     id_dq, k ? 1u : 0u);
+#pragma unroll 4
+          for (int k = 0; k < n_k; ++k)
+            umma_f16(tA, dk_ps + (k >> 2) * AT + (k & 3) * 2, dm_k + k * 128, id_dq, k ? 1u : 0u);
           umma_commit(bar_dq);
-          for (int jt = 0; jt < n_mt; ++jt)
+          for (int jt = 0; jt < n_mt; ++jt) {
+            const uint64_t a0 = dm_ps + 2 * jt * AT, b0 = dm_q + mt * AT;
+#pragma unroll 4
             for (int ks = 0; ks < ksi; ++ks)
-              umma_f16(tmem_base + TM_DK + jt * 64, desc_mn(s_base + B_PS + 2 * jt * ATOM + ks * 2048, ATOM),
-                       desc_mn(s_base + B_Q + mt * ATOM + ks * 2048, 8192), id_t, (mt | ks) ? 1u : 0u);
+              umma_f16(tmem_base + TM_DK + jt * 64, a0 + ks * 128, b0 + ks * 128, id_t, (mt | ks) ? 1u : 0u);
+          }
           umma_commit(bar_dsfree);
         }
         umma_commit(bar_smem);

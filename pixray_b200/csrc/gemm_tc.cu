@@ -411,8 +411,17 @@ __device__ __forceinline__ void epilogue_softmax_bwd(const GemmParams& p, float*
 }
 
 // TMA producer (one lane): walks this CTA's tiles and fills the stage ring.
-__device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
-                                              uint32_t stage_bytes) {
+// This single thread paces the whole kernel (one k-block of MMA work is ~512 cycles at block_n = 256): ncu showed the MMA
+// thread finding its stage not yet full on 93 % of the k-blocks while the producer never waited for a free slot -- the
+// loop body was ~160 dependent integer instructions (runtime divisions for the tap / k offset, operand-mode branches,
+// generic->shared address conversions).  The body below is specialised on the operand modes, carries (tap, kk) as
+// running counters and works on 32-bit shared addresses: ~25 instructions per k-block.
+template <int AM, int BM>
+__device__ __forceinline__ void producer_tiles(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                               uint32_t stage_bytes) {
+  const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const int k_per_tap = p.k_blocks_per_tap * GEMM_BLOCK_K;
+  const int n_atoms = p.block_n / 64;
   int stage = 0;
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -421,31 +430,46 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem
     const int kb_begin = p.k_splits > 1 ? t.z * p.kb_per_split : 0;
     const int kb_end = p.k_splits > 1 ? min(p.num_k_blocks, kb_begin + p.kb_per_split) : p.num_k_blocks;
     const int img = p.k_splits > 1 ? 0 : t.z;  // split-K: z is the split, there is one image
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      const int tap = kb / p.k_blocks_per_tap;
-      const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-      uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-      uint8_t* sb = sa + A_TILE_BYTES;
-      if (p.a_mode == OP_KMAJOR) {
-        tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
-      } else if (p.a_mode == OP_MNMAJOR) {
-        tma_load_4d(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
-        tma_load_4d(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+    int tap = 0, kk = 0, ty = -1, tx = -1;     // running tap index, k offset inside the tap, tap offset (dy, dx)
+    if (AM == OP_CONV) {
+      tap = kb_begin / p.k_blocks_per_tap;
+      kk = (kb_begin - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
+      if (p.num_taps == 9) {
+        ty = tap / 3 - 1;
+        tx = tap % 3 - 1;
       } else {
-        int dy = 0, dx = 0;
-        if (p.num_taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-        }
-        tma_load_4d(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, img);
+        ty = tx = 0;
       }
-      if (p.b_mode == OP_KMAJOR) {
-        tma_load_4d(&p.tma_b, &full_bar[stage], sb, kk, t.n0 + tap * p.b_tap_rows, bb0, bb1);
+    } else {
+      kk = kb_begin * GEMM_BLOCK_K;
+    }
+    int b_row = t.n0 + tap * p.b_tap_rows;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const uint32_t fb = full0 + stage * 8, sa = smem0 + stage * stage_bytes, sb = sa + A_TILE_BYTES;
+      mbar_wait_s(empty0 + stage * 8, phase ^ 1);
+      mbar_arrive_expect_tx_s(fb, stage_bytes);
+      if (AM == OP_KMAJOR) {
+        tma_load_4d_s(&p.tma_a, fb, sa, kk, t.m0, t.b0, t.b1);
+      } else if (AM == OP_MNMAJOR) {
+        tma_load_4d_s(&p.tma_a, fb, sa, t.m0, kk, t.b0, t.b1);
+        tma_load_4d_s(&p.tma_a, fb, sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
       } else {
-        for (int j = 0; j < p.block_n / 64; ++j)
-          tma_load_4d(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, t.n0 + 64 * j, kk, bb0, bb1);
+        tma_load_4d_s(&p.tma_a, fb, sa, kk, t.w0 + tx, t.h0 + ty, img);
+      }
+      if (BM == OP_KMAJOR) {
+        tma_load_4d_s(&p.tma_b, fb, sb, kk, b_row, bb0, bb1);
+      } else {
+        for (int j = 0; j < n_atoms; ++j)
+          tma_load_4d_s(&p.tma_b, fb, sb + j * MN_ATOM_BYTES, t.n0 + 64 * j, kk, bb0, bb1);
+      }
+      kk += GEMM_BLOCK_K;
+      if (AM == OP_CONV && kk == k_per_tap) {  // next filter tap
+        kk = 0;
+        b_row += p.b_tap_rows;
+        if (++tx == 2) {
+          tx = -1;
+          ++ty;
+        }
       }
       if (++stage == p.stages) {
         stage = 0;
@@ -455,7 +479,22 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem
   }
 }
 
-// MMA issuer (one lane): tcgen05.mma over the stage ring into the double-buffered TMEM accumulator.
+__device__ __forceinline__ void producer_loop(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint32_t stage_bytes) {
+  if (p.a_mode == OP_CONV) {
+    producer_tiles<OP_CONV, OP_KMAJOR>(p, smem, full_bar, empty_bar, stage_bytes);
+  } else if (p.a_mode == OP_KMAJOR) {
+    if (p.b_mode == OP_KMAJOR) producer_tiles<OP_KMAJOR, OP_KMAJOR>(p, smem, full_bar, empty_bar, stage_bytes);
+    else producer_tiles<OP_KMAJOR, OP_MNMAJOR>(p, smem, full_bar, empty_bar, stage_bytes);
+  } else {
+    if (p.b_mode == OP_KMAJOR) producer_tiles<OP_MNMAJOR, OP_KMAJOR>(p, smem, full_bar, empty_bar, stage_bytes);
+    else producer_tiles<OP_MNMAJOR, OP_MNMAJOR>(p, smem, full_bar, empty_bar, stage_bytes);
+  }
+}
+
+// MMA issuer (one lane): tcgen05.mma over the stage ring into the double-buffered TMEM accumulator.  The shared-memory
+// descriptors are built once; a stage / k-step advance is an add on their address field (bits [0,14) = address >> 4,
+// and the whole ring sits below 256 KiB, so the add never carries out of the field).
 __device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
                                          uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
                                          uint32_t stage_bytes) {
@@ -465,8 +504,13 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uin
   // MN-major: 64-wide MN atoms 8192 B apart (LBO), 8-deep K groups 1024 B apart (SBO); K advance = 2048 B.
   const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
   const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
-  const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
-  const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
+  const uint64_t a_kstep = ((p.a_mode == OP_MNMAJOR) ? 2048 : 32) >> 4;
+  const uint64_t b_kstep = ((p.b_mode == OP_MNMAJOR) ? 2048 : 32) >> 4;
+  const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint64_t a_desc0 = make_smem_desc_sw128(smem0, a_lbo, 1024);
+  const uint64_t b_desc0 = make_smem_desc_sw128(smem0 + A_TILE_BYTES, b_lbo, 1024);
+  const uint64_t stage_step = stage_bytes >> 4;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
   int stage = 0;
   uint32_t phase = 0;
   int it = 0;
@@ -476,24 +520,22 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uin
     mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
-    int kb_begin = 0, kb_end = p.num_k_blocks;
+    int n_kb = p.num_k_blocks;
     if (p.k_splits > 1) {
-      const int z = tile / (p.tiles_m * p.tiles_n);
-      kb_begin = z * p.kb_per_split;
-      kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+      const int kb_begin = (tile / tiles_mn) * p.kb_per_split;
+      n_kb = min(p.num_k_blocks, kb_begin + p.kb_per_split) - kb_begin;
     }
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait_s(full0 + stage * 8, phase);
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-      const uint32_t sb = sa + A_TILE_BYTES;
-#pragma unroll
-      for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-        const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-        const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-        umma_f16(d_tmem, ad, bd, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-      }
-      umma_commit(&empty_bar[stage]);
+      const uint64_t ad = a_desc0 + stage * stage_step, bd = b_desc0 + stage * stage_step;
+      umma_f16(d_tmem, ad, bd, idesc, acc);
+      umma_f16(d_tmem, ad + a_kstep, bd + b_kstep, idesc, 1u);
+      umma_f16(d_tmem, ad + 2 * a_kstep, bd + 2 * b_kstep, idesc, 1u);
+      umma_f16(d_tmem, ad + 3 * a_kstep, bd + 3 * b_kstep, idesc, 1u);
+      acc = 1u;
+      umma_commit_s(empty0 + stage * 8);
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1;
@@ -927,50 +969,67 @@ __device__ __forceinline__ PairInfo pair_info(const GemmParams& p) {
   return pi;
 }
 
-__device__ __forceinline__ void producer2_loop(const GemmParams& p, const PairInfo& pi, uint8_t* smem, uint64_t* full_bar,
-                                               uint64_t* empty_bar, uint32_t stage_bytes) {
+template <int AM, int BM>
+__device__ __forceinline__ void producer2_tiles(const GemmParams& p, const PairInfo& pi, uint8_t* smem, uint64_t* full_bar,
+                                                uint64_t* empty_bar, uint32_t stage_bytes) {
   const uint32_t rank = pi.rank;
   const bool leader = pi.leader;
-  const int cluster_id = pi.cluster_id, num_clusters = pi.num_clusters, pairs_m = pi.pairs_m,
-            total_pairs = pi.total_pairs, half_n = pi.half_n;
+  const int half_n = pi.half_n, n_atoms = half_n / 64;
+  const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const int k_per_tap = p.k_blocks_per_tap * GEMM_BLOCK_K;
   int stage = 0;
   uint32_t phase = 0;
-  for (int tp = cluster_id; tp < total_pairs; tp += num_clusters) {
+  for (int tp = pi.cluster_id; tp < pi.total_pairs; tp += pi.num_clusters) {
     const int tn = tp % p.tiles_n, r = tp / p.tiles_n;
-    const TileCoord t = make_coord(p, tn, 2 * (r % pairs_m) + (int)rank, r / pairs_m);
+    const TileCoord t = make_coord(p, tn, 2 * (r % pi.pairs_m) + (int)rank, r / pi.pairs_m);
     const int bb0 = p.b_batched ? t.b0 : 0, bb1 = p.b_batched ? t.b1 : 0;
     const int nb = t.n0 + (int)rank * half_n;  // this CTA's half of the B tile
+    int kk = 0, ty = p.num_taps == 9 ? -1 : 0, tx = ty, b_row = nb;
     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-      const int tap = kb / p.k_blocks_per_tap;
-      const int kk = (kb - tap * p.k_blocks_per_tap) * GEMM_BLOCK_K;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
-      uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-      uint8_t* sb = sa + A_TILE_BYTES;
-      if (p.a_mode == OP_KMAJOR) {
-        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.m0, t.b0, t.b1);
-      } else if (p.a_mode == OP_MNMAJOR) {
-        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, t.m0, kk, t.b0, t.b1);
-        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+      const uint32_t fb = full0 + stage * 8, sa = smem0 + stage * stage_bytes, sb = sa + A_TILE_BYTES;
+      mbar_wait_s(empty0 + stage * 8, phase ^ 1);
+      if (leader) mbar_arrive_expect_tx_s(fb, 2 * stage_bytes);
+      if (AM == OP_KMAJOR) {
+        tma_load_4d_2sm_s(&p.tma_a, fb, sa, kk, t.m0, t.b0, t.b1);
+      } else if (AM == OP_MNMAJOR) {
+        tma_load_4d_2sm_s(&p.tma_a, fb, sa, t.m0, kk, t.b0, t.b1);
+        tma_load_4d_2sm_s(&p.tma_a, fb, sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
       } else {
-        int dy = 0, dx = 0;
-        if (p.num_taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-        }
-        tma_load_4d_2sm(&p.tma_a, &full_bar[stage], sa, kk, t.w0 + dx, t.h0 + dy, t.z);
+        tma_load_4d_2sm_s(&p.tma_a, fb, sa, kk, t.w0 + tx, t.h0 + ty, t.z);
       }
-      if (p.b_mode == OP_KMAJOR) {
-        tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb, kk, nb + tap * p.b_tap_rows, bb0, bb1);
+      if (BM == OP_KMAJOR) {
+        tma_load_4d_2sm_s(&p.tma_b, fb, sb, kk, b_row, bb0, bb1);
       } else {
-        for (int j = 0; j < half_n / 64; ++j)
-          tma_load_4d_2sm(&p.tma_b, &full_bar[stage], sb + j * MN_ATOM_BYTES, nb + 64 * j, kk, bb0, bb1);
+        for (int j = 0; j < n_atoms; ++j)
+          tma_load_4d_2sm_s(&p.tma_b, fb, sb + j * MN_ATOM_BYTES, nb + 64 * j, kk, bb0, bb1);
+      }
+      kk += GEMM_BLOCK_K;
+      if (AM == OP_CONV && kk == k_per_tap) {
+        kk = 0;
+        b_row += p.b_tap_rows;
+        if (++tx == 2) {
+          tx = -1;
+          ++ty;
+        }
       }
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1;
       }
     }
+  }
+}
+
+__device__ __forceinline__ void producer2_loop(const GemmParams& p, const PairInfo& pi, uint8_t* smem, uint64_t* full_bar,
+                                               uint64_t* empty_bar, uint32_t stage_bytes) {
+  if (p.a_mode == OP_CONV) {
+    producer2_tiles<OP_CONV, OP_KMAJOR>(p, pi, smem, full_bar, empty_bar, stage_bytes);
+  } else if (p.a_mode == OP_KMAJOR) {
+    if (p.b_mode == OP_KMAJOR) producer2_tiles<OP_KMAJOR, OP_KMAJOR>(p, pi, smem, full_bar, empty_bar, stage_bytes);
+    else producer2_tiles<OP_KMAJOR, OP_MNMAJOR>(p, pi, smem, full_bar, empty_bar, stage_bytes);
+  } else {
+    if (p.b_mode == OP_KMAJOR) producer2_tiles<OP_MNMAJOR, OP_KMAJOR>(p, pi, smem, full_bar, empty_bar, stage_bytes);
+    else producer2_tiles<OP_MNMAJOR, OP_MNMAJOR>(p, pi, smem, full_bar, empty_bar, stage_bytes);
   }
 }
 
@@ -982,8 +1041,12 @@ __device__ __forceinline__ void mma2_loop(const GemmParams& p, const PairInfo& p
                                         p.b_mode == OP_MNMAJOR);
   const uint32_t a_lbo = (p.a_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
   const uint32_t b_lbo = (p.b_mode == OP_MNMAJOR) ? MN_ATOM_BYTES : 0;
-  const uint32_t a_kstep = (p.a_mode == OP_MNMAJOR) ? 2048 : 32;
-  const uint32_t b_kstep = (p.b_mode == OP_MNMAJOR) ? 2048 : 32;
+  const uint64_t a_kstep = ((p.a_mode == OP_MNMAJOR) ? 2048 : 32) >> 4;
+  const uint64_t b_kstep = ((p.b_mode == OP_MNMAJOR) ? 2048 : 32) >> 4;
+  const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint64_t a_desc0 = make_smem_desc_sw128(smem0, a_lbo, 1024);
+  const uint64_t b_desc0 = make_smem_desc_sw128(smem0 + A_TILE_BYTES, b_lbo, 1024);
+  const uint64_t stage_step = stage_bytes >> 4;
   int stage = 0;
   uint32_t phase = 0;
   int it = 0;
@@ -993,18 +1056,17 @@ __device__ __forceinline__ void mma2_loop(const GemmParams& p, const PairInfo& p
     mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+    uint32_t acc = 0;
     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait_s(full0 + stage * 8, phase);
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-      const uint32_t sb = sa + A_TILE_BYTES;
-#pragma unroll
-      for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-        const uint64_t ad = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-        const uint64_t bd = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-        umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-      }
-      umma_commit_2sm(&empty_bar[stage], 3);  // frees the smem slot in both CTAs
+      const uint64_t ad = a_desc0 + stage * stage_step, bd = b_desc0 + stage * stage_step;
+      umma_f16_2sm(d_tmem, ad, bd, idesc, acc);
+      umma_f16_2sm(d_tmem, ad + a_kstep, bd + b_kstep, idesc, 1u);
+      umma_f16_2sm(d_tmem, ad + 2 * a_kstep, bd + 2 * b_kstep, idesc, 1u);
+      umma_f16_2sm(d_tmem, ad + 3 * a_kstep, bd + 3 * b_kstep, idesc, 1u);
+      acc = 1u;
+      umma_commit_2sm_s(empty0 + stage * 8, 3);  // frees the smem slot in both CTAs
       if (++stage == p.stages) {
         stage = 0;
         phase ^= 1;
