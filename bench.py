@@ -279,7 +279,7 @@ def run_engine(args, rank, world):
         "e2e": {"value": jobs * args.steps / (ms_e2e * 1e-3), "unit": "iters/sec",
                 "h2d_bytes_per_step": CUTN * 9 * 4, "d2h_bytes_per_step": 64 * 4},
         "gpu_launches": launches,
-        "roofline": {"kernel": "gemm_tc*/gemm_tce* (tcgen05 GEMM / implicit-GEMM conv family)", "bound": "tensor",
+        "roofline": {"kernel": "tcgen05 family: gemm_tc*/gemm_tce* (GEMM / implicit-GEMM conv) + attn_fwd/attn_bwd (fused attention)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / peaks["tflops_sustained"], "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write)",
                      "traffic_source": traffic_src,

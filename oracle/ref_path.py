@@ -607,6 +607,203 @@ def aesthetic_loss(embeds, weight, bias, aesthetic_target=10.0):
     return (rating - target).square().mean() * 0.02
 
 
+# ------------------------------------------------------------------------------------------------ vdiff drawer (config 4)
+# v-diffusion-pytorch/diffusion/models/cc12m_1.py (CC12M1Model) restated table-driven.  Modules are created in the same
+# order, with the same torch constructors, as the reference's __init__ (skip projections before the main path:
+# cc12m_1.py:21, 43; net arguments left to right: 135-236), so `torch.manual_seed(s); VDiffCC12M1()` reproduces the
+# reference's own seeded initialisation bit for bit -- that is how tests/golden pins this restatement without a
+# 2.4 GB weight fixture.  `ref_state_dict()` returns the weights under the reference checkpoint's keys.
+
+VDIFF_C = 128
+
+
+def vdiff_spec(c=VDIFF_C):
+    """The `net` of cc12m_1.py:135-236 as nested tuples: ("b", c_in, c_mid, c_out, is_last), ("a", c, heads),
+    ("s", [children]) with AvgPool2d first and bilinear Upsample last inside every SkipBlock."""
+    cs = [c, c * 2, c * 2, c * 4, c * 4, c * 8, c * 8]
+
+    def stage(lv):
+        # the SkipBlock entered below resolution level lv - 1 (levels 1..6)
+        cin, cc = cs[lv - 1], cs[lv]
+        attn = lv >= 4
+        items = ["down"]
+        if lv < 6:
+            chain = [(cin, cc, cc), (cc, cc, cc), (cc, cc, cc), (cc, cc, cc)]
+            for (a, m, o) in chain:
+                items.append(("b", a, m, o, False))
+                if attn:
+                    items.append(("a", o, o // 64))
+            items.append(stage(lv + 1))
+            up = [(cc * 2, cc, cc), (cc, cc, cc), (cc, cc, cc), (cc, cc, cin)]
+            for (a, m, o) in up:
+                items.append(("b", a, m, o, False))
+                if attn:
+                    items.append(("a", o, o // 64))
+        else:  # 4x4 level: eight blocks, the last one narrows back (cc12m_1.py:183-199)
+            chain = [(cin, cc, cc)] + [(cc, cc, cc)] * 6 + [(cc, cc, cin)]
+            for (a, m, o) in chain:
+                items.append(("b", a, m, o, False))
+                items.append(("a", o, o // 64))
+        items.append("up")
+        return ("s", items)
+
+    top = [("b", 3 + 16, cs[0], cs[0], False)] + [("b", cs[0], cs[0], cs[0], False)] * 3
+    top.append(stage(1))
+    top += [("b", cs[0] * 2, cs[0], cs[0], False), ("b", cs[0], cs[0], cs[0], False), ("b", cs[0], cs[0], cs[0], False),
+            ("b", cs[0], cs[0], 3, True)]
+    return top
+
+
+class VDiffCC12M1(nn.Module):
+    def __init__(self, c=VDIFF_C):
+        super().__init__()
+        self.mods = nn.ModuleList()
+        self.keys = []  # (reference key prefix, module) in creation order
+
+        def reg(key, m):
+            self.mods.append(m)
+            self.keys.append((key, m))
+            return m
+
+        # cc12m_1.py:117-123: FourierFeatures(1, 128) (weight = randn [64, 1]), mapping = 2 ResLinearBlocks, *= sqrt(1/2)
+        self.map_ff = nn.Parameter(torch.randn(64, 1), requires_grad=False)
+        self.map_skip0 = reg("mapping.0.skip", nn.Linear(512 + 128, 1024, bias=False))  # cc12m_1.py:21 (before main)
+        self.map_00 = reg("mapping.0.main.0", nn.Linear(512 + 128, 1024))
+        self.map_02 = reg("mapping.0.main.2", nn.Linear(1024, 1024))
+        self.map_10 = reg("mapping.1.main.0", nn.Linear(1024, 1024))
+        self.map_12 = reg("mapping.1.main.2", nn.Linear(1024, 1024))
+        with torch.no_grad():
+            for m in (self.map_skip0, self.map_00, self.map_02, self.map_10, self.map_12):
+                for prm in m.parameters():
+                    prm *= 0.5 ** 0.5
+        self.t_ff = nn.Parameter(torch.randn(8, 1), requires_grad=False)  # timestep_embed = FourierFeatures(1, 16)
+        self.spec = vdiff_spec(c)
+        first_net = len(self.mods)
+
+        def build(items, prefix):
+            out = []
+            for i, it in enumerate(items):
+                key = f"{prefix}.{i}"
+                if it in ("down", "up"):
+                    out.append(it)
+                elif it[0] == "b":
+                    _, cin, cmid, cout, last = it
+                    skip = reg(key + ".skip", nn.Conv2d(cin, cout, 1, bias=False)) if cin != cout else None  # :43
+                    blk = dict(kind="b", last=last, skip=skip, conv1=reg(key + ".main.0", nn.Conv2d(cin, cmid, 3, padding=1)),
+                               mod1=reg(key + ".main.2.layer", nn.Linear(1024, cmid * 2, bias=False)),
+                               conv2=reg(key + ".main.4", nn.Conv2d(cmid, cout, 3, padding=1)),
+                               mod2=None if last else reg(key + ".main.6.layer", nn.Linear(1024, cout * 2, bias=False)))
+                    out.append(blk)
+                elif it[0] == "a":
+                    _, ch, heads = it
+                    out.append(dict(kind="a", heads=heads, norm=reg(key + ".norm", nn.GroupNorm(1, ch)),
+                                    qkv=reg(key + ".qkv_proj", nn.Conv2d(ch, ch * 3, 1)),
+                                    out=reg(key + ".out_proj", nn.Conv2d(ch, ch, 1))))
+                else:
+                    out.append(dict(kind="s", main=build(it[1], key + ".main")))
+            return out
+
+        self.net = build(self.spec, "net")
+        with torch.no_grad():  # cc12m_1.py:239-241
+            for m in list(self.mods)[first_net:]:
+                for prm in m.parameters():
+                    prm *= 0.5 ** 0.5
+
+    def ref_state_dict(self):
+        sd = OrderedDict()
+        sd["mapping_timestep_embed.weight"] = self.map_ff.detach()
+        sd["timestep_embed.weight"] = self.t_ff.detach()
+        for key, m in self.keys:
+            for n, prm in m.named_parameters():
+                sd[f"{key}.{n}"] = prm.detach()
+        return sd
+
+    @staticmethod
+    def fourier(t, w):  # cc12m_1.py:73-75
+        f = 2 * math.pi * t[:, None] @ w.T
+        return torch.cat([f.cos(), f.sin()], dim=-1)
+
+    def cond(self, t, clip_embed):  # cc12m_1.py:244-246
+        ce = F.normalize(clip_embed, dim=-1) * clip_embed.shape[-1] ** 0.5
+        h = torch.cat([ce, self.fourier(t, self.map_ff)], dim=1)
+        h = F.relu(self.map_02(F.relu(self.map_00(h)))) + self.map_skip0(h)
+        return self.map_12(F.relu(self.map_10(h))) + h  # is_last: no final ReLU, identity skip
+
+    def _run(self, items, x, cond):
+        for it in items:
+            if it == "down":
+                x = F.avg_pool2d(x, 2)
+            elif it == "up":
+                x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+            elif it["kind"] == "b":
+                def mod(lin, h):  # Modulation2d, cc12m_1.py:36-38
+                    sc, sh = lin(cond).chunk(2, dim=-1)
+                    return torch.addcmul(sh[..., None, None], h, sc[..., None, None] + 1)
+                h = it["conv1"](x)
+                h = F.relu(mod(it["mod1"], F.group_norm(h, 1)))
+                h = it["conv2"](h)
+                if not it["last"]:
+                    h = F.relu(mod(it["mod2"], F.group_norm(h, 1)))
+                x = h + (it["skip"](x) if it["skip"] is not None else x)
+            elif it["kind"] == "a":  # SelfAttention2d, cc12m_1.py:88-97
+                n, c, hh, ww = x.shape
+                qkv = it["qkv"](it["norm"](x)).view(n, it["heads"] * 3, c // it["heads"], hh * ww).transpose(2, 3)
+                q, k, v = qkv.chunk(3, dim=1)
+                scale = k.shape[3] ** -0.25
+                att = ((q * scale) @ (k.transpose(2, 3) * scale)).softmax(3)
+                y = (att @ v).transpose(2, 3).contiguous().view(n, c, hh, ww)
+                x = x + it["out"](y)
+            else:  # SkipBlock, cc12m_1.py:57-58
+                x = torch.cat([self._run(it["main"], x, cond), x], dim=1)
+        return x
+
+    def forward(self, x, t, clip_embed):
+        cond = self.cond(t, clip_embed)
+        te = self.fourier(t, self.t_ff)[..., None, None].repeat(1, 1, x.shape[2], x.shape[3])
+        return self._run(self.net, torch.cat([x, te], dim=1), cond)
+
+
+def vdiff_t_to_alpha_sigma(t):
+    """diffusion/utils.py:52-55."""
+    return torch.cos(t * math.pi / 2), torch.sin(t * math.pi / 2)
+
+
+def vdiff_schedule(iterations, vdiff_skip=0.0):
+    """VdiffDrawer.init_from_tensor (vdiff.py:113-126) with the default spliced DDPM/cosine schedule
+    (diffusion/utils.py:63-78): returns (steps, alphas, sigmas), each [iterations + 1]."""
+    top = 1.0 - vdiff_skip / 100.0
+    t = torch.linspace(top, 0, iterations + 2)[:-1]
+    ddpm_crossover, cosine_crossover = 0.48536712, 0.80074257
+    big_t = t * (1 + cosine_crossover - ddpm_crossover)
+    ddpm_t = big_t + ddpm_crossover - cosine_crossover
+    log_snr = -torch.special.expm1(1e-4 + 10 * ddpm_t ** 2).log()
+    alpha, sigma = log_snr.sigmoid().sqrt(), log_snr.neg().sigmoid().sqrt()
+    ddpm_part = torch.atan2(sigma, alpha) / math.pi * 2
+    steps = torch.where(big_t < cosine_crossover, big_t, ddpm_part)
+    a, s = vdiff_t_to_alpha_sigma(steps)
+    return steps, a, s
+
+
+def vdiff_synth(model, x, t, clip_embed, alpha, sigma):
+    """VdiffDrawer.synth (vdiff.py:159-172) through sampling.sample_step_pred (sampling.py:7-15): returns
+    (pixels in [0,1] with ClampWithGrad, pred, v)."""
+    v = model(x, t, clip_embed).float()
+    pred = x * alpha - v * sigma
+    return clamp_with_grad(pred.add(1).div(2), 0, 1), pred, v
+
+
+def vdiff_renoise(x, pred, v, alphas, sigmas, i, noise, eta=1.0):
+    """sampling.sample_step_noise (sampling.py:18-39) with the fresh noise passed in."""
+    eps = x * sigmas[i] + v * alphas[i]
+    if i < len(alphas) - 1:
+        ddim_sigma = eta * (sigmas[i + 1] ** 2 / sigmas[i] ** 2).sqrt() * (1 - alphas[i] ** 2 / alphas[i + 1] ** 2).sqrt()
+        adjusted_sigma = (sigmas[i + 1] ** 2 - ddim_sigma ** 2).sqrt()
+        x = pred * alphas[i + 1] + eps * adjusted_sigma
+        if eta:
+            x = x + noise * ddim_sigma
+    return x
+
+
 class AdamState:
     """optim.Adam([z], lr) as rebuilt by rebuild_optimisers (pixray.py:520-555): betas 0.9/0.999, eps 1e-8."""
 

@@ -39,12 +39,20 @@ struct GridBarrier {
   unsigned long long* counter = nullptr;  // device, zero-initialised
   unsigned long long issued = 0;
 };
+// Variants for the vdiff U-Net (cc12m_1.py:41-50, 78-97): GroupNorm(1, C) (one_group), gamma = modulation scale + 1
+// (gamma_add, gamma/beta may be null = 0), activation `swish` argument: 0 none, 1 swish, 2 ReLU, forward residual add.
+struct GnOpts {
+  int one_group = 0;
+  float gamma_add = 0.f;
+  const act_t* res = nullptr;  // forward only: y = act(norm(x)) + res
+};
 bool gn_coop_supported(int pixels, int C, int num_sms);
 void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int pixels, int C, int swish, float eps,
-                     float* part, float* stats, act_t* y, int num_sms, GridBarrier* gb, cudaStream_t st);
+                     float* part, float* stats, act_t* y, int num_sms, GridBarrier* gb, cudaStream_t st,
+                     GnOpts o = GnOpts());
 void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
                       int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
-                      GridBarrier* gb, cudaStream_t st);
+                      GridBarrier* gb, cudaStream_t st, GnOpts o = GnOpts());
 
 void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st);        // nearest, [H,W,C]->[2H,2W,C]
 void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st);       // adjoint: [2H,2W,C]->[H,W,C]

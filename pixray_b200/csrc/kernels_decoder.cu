@@ -402,10 +402,28 @@ __device__ __forceinline__ void gnc_fold(const float* part, int nblk, double cou
   __syncthreads();
 }
 
+// GroupNorm(1, C): the 32 equal-sized groups' means (of x, x^2 or of the backward sums) average to the whole-tensor mean
+__device__ __forceinline__ void gnc_merge_groups(double* sh) {
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int g = 0; g < GN_G; ++g) {
+      a += sh[2 * g];
+      b += sh[2 * g + 1];
+    }
+    a /= GN_G;
+    b /= GN_G;
+    for (int g = 0; g < GN_G; ++g) {
+      sh[2 * g] = a;
+      sh[2 * g + 1] = b;
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(GNC_THREADS, 1)
     gn_coop_fwd_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                        int pixels, int C, int swish, float eps, int rpb, float* part, float* __restrict__ stats_out,
-                       act_t* __restrict__ y, unsigned long long* bar, unsigned long long bar_target) {
+                       act_t* y, unsigned long long* bar, unsigned long long bar_target, GnOpts o) {
   extern __shared__ __align__(16) uint8_t gnc_smem[];
   float* red = reinterpret_cast<float*>(gnc_smem);                       // [4][1024]
   act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);  // slab of x
@@ -432,6 +450,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
   gnc_grid_barrier(bar, bar_target);
   gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  if (o.one_group) gnc_merge_groups(sh);  // GroupNorm(1, C): every group takes the statistics of the whole tensor
   if (threadIdx.x < GN_G) {
     const double mean = sh[2 * threadIdx.x], ex2 = sh[2 * threadIdx.x + 1];
     double var = ex2 - mean * mean;
@@ -449,18 +468,20 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c0 + i) / cpg;
-    const float ga = gamma[c0 + i];
+    const float ga = (gamma ? gamma[c0 + i] : 0.f) + o.gamma_add;
     sc8[i] = st[2 * g + 1] * ga;
-    sh8[i] = beta[c0 + i] - st[2 * g] * st[2 * g + 1] * ga;
+    sh8[i] = (beta ? beta[c0 + i] : 0.f) - st[2 * g] * st[2 * g + 1] * ga;
   }
 #pragma unroll 4
   for (int p = p_begin + pl; p < p_end; p += plane) {
-    float xv[8];
+    float xv[8], rv[8];
     load8(cx + (size_t)(p - p_begin) * C + c0, xv);
+    if (o.res) load8(o.res + (size_t)p * C + c0, rv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float a = xv[i] * sc8[i] + sh8[i];
-      xv[i] = swish ? a / (1.f + __expf(-a)) : a;
+      const float r = swish == 1 ? a / (1.f + __expf(-a)) : (swish == 2 ? fmaxf(a, 0.f) : a);
+      xv[i] = o.res ? r + rv[i] : r;
     }
     store8(y + (size_t)p * C + c0, xv);
   }
@@ -470,7 +491,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
     gn_coop_bwd_kernel(const act_t* __restrict__ dy, const act_t* __restrict__ x, const float* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int pixels, int C, int swish,
                        const act_t* dres, int rpb, int cache_dy, float* part, act_t* dx, unsigned long long* bar,
-                       unsigned long long bar_target) {
+                       unsigned long long bar_target, GnOpts o) {
   extern __shared__ __align__(16) uint8_t gnc_smem[];
   float* red = reinterpret_cast<float*>(gnc_smem);
   act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);
@@ -484,8 +505,8 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   float g8[8], b8[8], mean2[2], rstd2[2];  // cpg >= 4: elements 0..3 and 4..7 of the vector each sit in one group
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    g8[i] = gamma[c0 + i];
-    b8[i] = beta[c0 + i];
+    g8[i] = (gamma ? gamma[c0 + i] : 0.f) + o.gamma_add;
+    b8[i] = beta ? beta[c0 + i] : 0.f;
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -510,10 +531,12 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
         const int e = 2 * i + k;
         const float xh = ((k ? tx.y : tx.x) - mean2[e >> 2]) * rstd2[e >> 2];
         float d = k ? td.y : td.x;
-        if (swish) {
+        if (swish == 1) {
           const float a = g8[e] * xh + b8[e];
           const float sg = 1.f / (1.f + __expf(-a));
           d *= sg * (1.f + a * (1.f - sg));
+        } else if (swish == 2) {
+          d = (g8[e] * xh + b8[e]) > 0.f ? d : 0.f;
         }
         const float dxh = d * g8[e];
         s[e >> 2][0] += dxh;
@@ -524,6 +547,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
   gnc_grid_barrier(bar, bar_target);
   gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  if (o.one_group) gnc_merge_groups(sh);
   float gs0[2], gs1[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -542,10 +566,12 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
     for (int i = 0; i < 8; ++i) {
       const float xh = (xv[i] - mean2[i >> 2]) * rstd2[i >> 2];
       float d = dv[i];
-      if (swish) {
+      if (swish == 1) {
         const float a = g8[i] * xh + b8[i];
         const float sg = 1.f / (1.f + __expf(-a));
         d *= sg * (1.f + a * (1.f - sg));
+      } else if (swish == 2) {
+        d = (g8[i] * xh + b8[i]) > 0.f ? d : 0.f;
       }
       const float dxh = d * g8[i];
       const float r = rstd2[i >> 2] * (dxh - gs0[i >> 2] - xh * gs1[i >> 2]);
@@ -722,19 +748,19 @@ bool gn_coop_supported(int pixels, int C, int num_sms) {
 }
 
 void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int pixels, int C, int swish, float eps,
-                     float* part, float* stats, act_t* y, int num_sms, GridBarrier* gb, cudaStream_t st) {
+                     float* part, float* stats, act_t* y, int num_sms, GridBarrier* gb, cudaStream_t st, GnOpts o) {
   gnc_init();
   int rpb = gnc_rows_per_block(pixels, num_sms);
   const int grid = (pixels + rpb - 1) / rpb;
   const size_t smem = 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2;
   gn_coop_fwd_kernel<<<grid, GNC_THREADS, smem, st>>>(x, gamma, beta, pixels, C, swish, eps, rpb, part, stats, y,
-                                                      gb->counter, gb->issued + grid);
+                                                      gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;  // a rejected launch must not move the target
 }
 
 void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
                       int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
-                      GridBarrier* gb, cudaStream_t st) {
+                      GridBarrier* gb, cudaStream_t st, GnOpts o) {
   gnc_init();
   int rpb = gnc_rows_per_block(pixels, num_sms);
   const int grid = (pixels + rpb - 1) / rpb;
@@ -742,7 +768,7 @@ void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const
   int cache_dy = (4 * GNC_THREADS * 4 + 2 * slab <= (size_t)GNC_SMEM_MAX) ? 1 : 0;
   const size_t smem = 4 * GNC_THREADS * 4 + (cache_dy ? 2 : 1) * slab;
   gn_coop_bwd_kernel<<<grid, GNC_THREADS, smem, st>>>(dy, x, stats, gamma, beta, pixels, C, swish, dres, rpb, cache_dy,
-                                                      part, dx, gb->counter, gb->issued + grid);
+                                                      part, dx, gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;
 }
 

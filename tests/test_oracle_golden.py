@@ -211,3 +211,35 @@ def test_aux_aesthetic():
     val.backward()
     close(val.detach(), ta("aes_val"), 2e-6)
     close(e.grad, ta("aes_grad"), 2e-6)
+
+
+# ------------------------------------------------------------------ vdiff drawer (cc12m_1), oracle/make_golden_vdiff.py
+@pytest.mark.slow
+def test_vdiff_restatement_matches_the_reference_model():
+    """torch.manual_seed(0) + the same constructor order reproduce the reference's seeded weights, hence its outputs."""
+    GV = np.load(os.path.join(os.path.dirname(__file__), "golden", "vdiff_vectors.npz"))
+    torch.manual_seed(0)
+    m = R.VDiffCC12M1().eval().requires_grad_(False)
+    sd = m.ref_state_dict()
+    assert len(sd) == int(GV["n_tensors"]) and sum(p.numel() for p in sd.values()) == int(GV["n_params"])
+    for k in GV.files:
+        if k.startswith("w:"):
+            assert np.array_equal(sd[k[2:]].reshape(-1)[:64].numpy(), GV[k]), k
+    x = torch.from_numpy(GV["x"]).requires_grad_(True)
+    v = m(x, torch.from_numpy(GV["t"]), torch.from_numpy(GV["clip_embed"]))
+    (v * torch.from_numpy(GV["w"])).sum().backward()
+    close(v.detach(), torch.from_numpy(GV["v"]), 1e-5)
+    close(x.grad, torch.from_numpy(GV["dx"]), 1e-5)
+
+
+def test_vdiff_schedule_and_renoise():
+    GV = np.load(os.path.join(os.path.dirname(__file__), "golden", "vdiff_vectors.npz"))
+    steps, alphas, sigmas = R.vdiff_schedule(20)
+    close(steps, torch.from_numpy(GV["steps"]), 1e-6)
+    close(alphas, torch.from_numpy(GV["alphas"]), 1e-6)
+    close(sigmas, torch.from_numpy(GV["sigmas"]), 1e-6)
+    x, pred, v = (torch.from_numpy(GV[k]) for k in ("rn_x", "rn_pred", "rn_v"))
+    for i in (0, 7, 20):
+        torch.manual_seed(123)
+        noise = torch.randn_like(x)
+        close(R.vdiff_renoise(x, pred, v, alphas, sigmas, i, noise), torch.from_numpy(GV[f"renoise_{i}"]), 1e-6)
