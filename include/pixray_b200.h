@@ -4,7 +4,7 @@
  * Python loop calls each iteration (file:line are relative to the reference checkout, pixray/pixray @ 37b03cf):
  *
  *   pxr_synth          <- drawer.synth(cur_iteration)          pixray.py:1206, vqgan.py:190-195, fast_pixeldrawer.py:89-91,
- *                                                              fftdrawer.py:78-84
+ *                                                              fftdrawer.py:78-84, vdiff.py:159-172
  *   pxr_make_cutouts   <- MakeCutouts.forward(out)             pixray.py:445-511 (cached-transform semantics 480-486)
  *   pxr_encode_image   <- CLIP_Base.encode_image(cutouts)      slip.py:21-42, 52-66
  *   pxr_prompt_loss    <- Prompt.forward(embeds) per prompt    pixray.py:268-280 (spherical_dist_loss 262-265)
@@ -30,7 +30,7 @@ extern "C" {
 
 typedef struct pxr_engine* pxr_handle;
 
-enum { PXR_DRAWER_VQGAN = 0, PXR_DRAWER_PIXEL = 1, PXR_DRAWER_FFT = 2 };
+enum { PXR_DRAWER_VQGAN = 0, PXR_DRAWER_PIXEL = 1, PXR_DRAWER_FFT = 2, PXR_DRAWER_VDIFF = 3 };
 enum { PXR_PAD_REFLECTION = 0, PXR_PAD_BORDER = 1, PXR_PAD_ZEROS = 2 };
 enum { PXR_DTYPE_F16 = 0, PXR_DTYPE_BF16 = 1 };
 /* module ids for pxr_load_weight */
@@ -125,6 +125,18 @@ int pxr_add_aux_loss(pxr_handle h, int kind, float weight, const float* params, 
 int pxr_clear_aux_losses(pxr_handle h);
 int pxr_num_losses(pxr_handle h, int* out); /* prompts of every perceptor + auxiliary losses */
 int pxr_read_losses(pxr_handle h, float* out_host); /* blocking: the loss vector of the last forward / backward */
+
+/* vdiff drawer (PXR_DRAWER_VDIFF; VdiffDrawer, vdiff.py:58-190, over diffusion/models/cc12m_1.py).  z = x [1,3,H,W];
+ * weights under the checkpoint's own keys through pxr_load_weight(module PXR_MOD_VQGAN = the drawer slot).
+ *   set_schedule : sample_state's steps / alphas / sigmas (vdiff.py:113-126, sampling.py:41-51), n = iterations + 1
+ *   set_clip_embed: extra_args["clip_embed"] (pixray.py:880-885), host [512]
+ *   set_iteration: the schedule index the per-op pxr_synth uses (pxr_iterate uses its own `iter`)
+ *   renoise      : drawer.makenoise(cur_it) (vdiff.py:156-157, sampling.sample_step_noise 18-39) on the pred / v the last
+ *                  synth kept; noise: device [3,H,W] standard normal (torch.randn_like), or NULL for eta = 0 */
+int pxr_vdiff_set_schedule(pxr_handle h, const float* steps, const float* alphas, const float* sigmas, int n);
+int pxr_vdiff_set_clip_embed(pxr_handle h, const float* embed, int D);
+int pxr_vdiff_set_iteration(pxr_handle h, int i);
+int pxr_vdiff_renoise(pxr_handle h, float* z, int i, const float* noise);
 
 int pxr_reset_optimizer(pxr_handle h); /* rebuild_optimisers: fresh Adam state (pixray.py:520-555, 1511) */
 int pxr_sync(pxr_handle h);

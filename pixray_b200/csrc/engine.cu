@@ -20,6 +20,8 @@ namespace pxr {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+struct VSpec;  // one element of the vdiff U-Net description (engine_vdiff.inc)
+
 // ===================================================================================================== Engine
 class Engine {
  public:
@@ -360,9 +362,37 @@ class Engine {
   void add_gn_bwd(OpList& l, const act_t* dy, const act_t* x, const GNSaved& s, const NormW& n, int px, int C, int swish,
                   const act_t* dres, act_t* dx);
 
+  // ------------------------------------------------------------------ vdiff drawer (engine_vdiff.inc)
+  struct VConv;
+  void build_vdiff();
+  VConv vd_load_conv(const std::string& prefix, int cin_real, int cin, int cout, int ks, bool has_bias, bool tiny);
+  void vd_conv_fwd(OpList& l, const act_t* x, int H, int Wd, const VConv& v, GemmEpilogue e);
+  void vd_conv_bwd(OpList& l, const act_t* dy, int H, int Wd, const VConv& v, GemmEpilogue e);
+  GNSaved vd_norm(OpList& l, const Act& x, const float* gamma, const float* beta, float gamma_add, int act,
+                  const act_t* res, act_t* y);
+  void vd_norm_bwd(OpList& l, const act_t* dy, const Act& x, const GNSaved& s, const float* gamma, const float* beta,
+                   float gamma_add, int act, const act_t* dres, act_t* dx);
+  Act vd_block(const Act& x, const std::string& key, const VSpec& sp);
+  Act vd_attn(const Act& x, const std::string& key, const VSpec& sp);
+  Act vd_skip(const Act& x, const std::string& key, const VSpec& sp);
+  Act vd_elem(const Act& x, const std::string& key, const VSpec& sp);
+  int vd_add_modulation(const std::string& wkey, int c);
+  void vdiff_prepare(int iter);
+  void vdiff_forward();
+  void vdiff_backward();
+  std::vector<float> vd_steps, vd_alphas, vd_sigmas, vd_map_ff, vd_t_ff, vd_mod_host;
+  bool vd_have_embed = false;
+  int vd_iter = 0, vd_iter_request = 0, vd_mod_rows = 0;
+  float *vd_pred = nullptr, *vd_v = nullptr, *vd_gpred = nullptr, *vd_vout = nullptr, *vd_mod_out = nullptr,
+        *vd_h0 = nullptr, *vd_te = nullptr, *vd_tmp[5] = {nullptr}, *vd_b[5] = {nullptr};
+  act_t *vd_gv = nullptr, *vd_col = nullptr, *vd_xin = nullptr, *vd_gin = nullptr, *vd_wmod = nullptr, *vd_w[5] = {nullptr};
+
   // ------------------------------------------------------------------ execution
   void prepare_cut_params(const pxr_cut_params* p, int iter);
-  void forward_drawer() { run(drawer_fwd); }
+  void forward_drawer() {
+    if (cfg.drawer == PXR_DRAWER_VDIFF) vdiff_forward();
+    else run(drawer_fwd);
+  }
   void forward_cutouts();
   void forward_clip(int i);
   void loss_clip(int i);
@@ -1387,7 +1417,8 @@ void Engine::backward_all() {
   }
   // image losses are replicated (every rank holds the same `out`): added after the exchange, values written, not summed
   if (!aux.empty()) aux_on_image();
-  run(drawer_bwd);
+  if (cfg.drawer == PXR_DRAWER_VDIFF) vdiff_backward();
+  else run(drawer_bwd);
   check_launch("backward");
 }
 
@@ -1404,6 +1435,7 @@ void Engine::finalize() {
   if (cfg.drawer == PXR_DRAWER_VQGAN) build_vqgan();
   else if (cfg.drawer == PXR_DRAWER_PIXEL) build_pixel();
   else if (cfg.drawer == PXR_DRAWER_FFT) build_fft();
+  else if (cfg.drawer == PXR_DRAWER_VDIFF) build_vdiff();
   else throw EngineError(-47, "unknown drawer kind");
   adam_m = dalloc<float>(z_numel);
   adam_v = dalloc<float>(z_numel);
@@ -1434,6 +1466,10 @@ void Engine::finalize() {
     reg("z_grad", z_grad, z_numel * 4);
     reg("z", z_buf, z_numel * 4);
     reg("losses", losses_dev, 64 * 4);
+    if (vd_pred) {
+      reg("vd_pred", vd_pred, npx * 4);
+      reg("vd_v", vd_v, npx * 4);
+    }
     reg("palette_best", aux_best, ncs / 3 * n_local * 4);
     reg("minv", minv_dev, (size_t)n_local * 36);
     for (int i = 0; i < cfg.n_clip; ++i) {
@@ -1456,6 +1492,8 @@ void Engine::finalize() {
   for (auto& m : weights) m.clear();  // host copies no longer needed
   finalized = true;
 }
+
+#include "engine_vdiff.inc"
 
 }  // namespace pxr
 
@@ -1645,6 +1683,7 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
     Engine* e = h->e;
     if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
     e->prepare_cut_params(p, iter);
+    e->vd_iter_request = iter;
     PXR_CUDA(cudaMemsetAsync(e->losses_dev, 0, 64 * sizeof(float), e->st));
     e->forward_drawer();
     e->forward_cutouts();
@@ -1716,6 +1755,58 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
     out6[5] = tot;
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
+    if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_vdiff_set_schedule(pxr_handle h, const float* steps, const float* alphas, const float* sigmas, int n) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (e->cfg.drawer != PXR_DRAWER_VDIFF) throw EngineError(-59, "not a vdiff engine");
+    if (n < 1 || !steps || !alphas || !sigmas) throw EngineError(-59, "pxr_vdiff_set_schedule: empty schedule");
+    e->vd_steps.assign(steps, steps + n);
+    e->vd_alphas.assign(alphas, alphas + n);
+    e->vd_sigmas.assign(sigmas, sigmas + n);
+  });
+}
+
+int pxr_vdiff_set_clip_embed(pxr_handle h, const float* embed, int D) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (e->cfg.drawer != PXR_DRAWER_VDIFF || !e->finalized) throw EngineError(-59, "not a finalized vdiff engine");
+    if (D != 512) throw EngineError(-59, "cc12m_1 is conditioned on a 512-wide CLIP embedding");
+    // cc12m_1.py:244: F.normalize(clip_embed) * sqrt(D)
+    std::vector<float> ce(embed, embed + D);
+    double s = 0;
+    for (float v : ce) s += (double)v * v;
+    const double k = std::sqrt((double)D) / std::max(std::sqrt(s), 1e-12);
+    for (float& v : ce) v = (float)(v * k);
+    PXR_CUDA(cudaMemcpyAsync(e->vd_h0, ce.data(), sizeof(float) * D, cudaMemcpyHostToDevice, e->st));
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+    e->vd_have_embed = true;
+  });
+}
+
+int pxr_vdiff_set_iteration(pxr_handle h, int i) {
+  h->e->vd_iter_request = i;
+  return 0;
+}
+
+int pxr_vdiff_renoise(pxr_handle h, float* z, int i, const float* noise) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (e->cfg.drawer != PXR_DRAWER_VDIFF) throw EngineError(-59, "not a vdiff engine");
+    const int n = (int)e->vd_steps.size();
+    if (i < 0 || i >= n) throw EngineError(-59, "pxr_vdiff_renoise: iteration outside the schedule");
+    if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+    if (i < n - 1) {  // sampling.py:24-37 with eta = 1
+      const double a = e->vd_alphas[i], s = e->vd_sigmas[i], a1 = e->vd_alphas[i + 1], s1 = e->vd_sigmas[i + 1];
+      const double ddim = std::sqrt(s1 * s1 / (s * s)) * std::sqrt(std::max(0.0, 1.0 - a * a / (a1 * a1)));
+      const double adj = std::sqrt(std::max(0.0, s1 * s1 - ddim * ddim));
+      pxr::vd_renoise(e->z_buf, e->vd_pred, e->vd_v, noise, (float)a, (float)s, (float)a1, (float)adj, (float)ddim,
+                      e->z_numel, e->st);
+      e->launches += 1;
+    }
     if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
   });
 }

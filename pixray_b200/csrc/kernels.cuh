@@ -177,6 +177,30 @@ void aux_aesthetic(const float* e, int n_local, int D, int cutn_global, const fl
                    float weight, float grad_scale, float* de, __half* de16, double* part, float* loss_out,
                    cudaStream_t st);
 
+// ------------------------------------------------------------------ vdiff drawer (kernels_vdiff.cu; cc12m_1.py, sampling.py)
+struct VdFeatures {
+  float v[144];  // [cos, sin] Fourier features of t: 128 for the mapping network, 16 timestep planes
+};
+void vd_set_features(const VdFeatures& f, float* h0_tail, float* te, cudaStream_t st);
+void vd_input(const float* x, const float* te, int pixels, act_t* out, cudaStream_t st);  // [pixels, 64]: x | te | 0
+void avgpool2x(const act_t* x, int H, int W, int C, int ld_in, act_t* y, cudaStream_t st);
+void avgpool2x_backward(const act_t* gy, int H, int W, int C, int accumulate, act_t* gx, cudaStream_t st);
+void bilinear_up2x(const act_t* x, int H, int W, int C, act_t* y, int ld_out, cudaStream_t st);   // align_corners=False
+void bilinear_up2x_backward(const act_t* gy, int H, int W, int C, int ld_gy, act_t* gx, cudaStream_t st);
+void copy_channels(const act_t* src, int ld_src, act_t* dst, int ld_dst, int C, long long pixels, int accumulate,
+                   cudaStream_t st);
+void im2col3x3(const act_t* x, int H, int W, int C, act_t* A, cudaStream_t st);  // A [pixels, 9 C], tap-major
+void gemv_f16(const act_t* W, int K, int R, const float* x, const float* bias, int relu, const float* res, float* y,
+              cudaStream_t st);
+void vd_finish(const float* vout, int ld, const float* x, float alpha, float sigma, int pixels, float* v_planar,
+               float* pred, float* pre, float* img, cudaStream_t st);
+void vd_finish_backward(const float* g_img, const float* pre, float sigma, int pixels, int ld, float* g_pred, act_t* g_v,
+                        cudaStream_t st);
+void vd_zgrad(const float* g_pred, const act_t* g_in, int ld, float alpha, float inv_scale, int pixels, float* z_grad,
+              cudaStream_t st);
+void vd_renoise(float* x, const float* pred, const float* v, const float* noise, float alpha_i, float sigma_i,
+                float alpha_next, float adjusted_sigma, float ddim_sigma, long long n, cudaStream_t st);
+
 void fill_f32(float* p, float v, long long n, cudaStream_t st);
 void cast_f32_to_f16(const float* x, act_t* y, long long n, float scale, cudaStream_t st);
 

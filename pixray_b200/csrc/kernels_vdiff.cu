@@ -216,6 +216,12 @@ __global__ void __launch_bounds__(256) gemv_f16_kernel(const act_t* __restrict__
   }
 }
 
+__global__ void vd_set_features_kernel(VdFeatures f, float* __restrict__ h0_tail, float* __restrict__ te) {
+  const int i = threadIdx.x;
+  if (i < 128) h0_tail[i] = f.v[i];
+  else if (i < 144) te[i - 128] = f.v[i];
+}
+
 // pred = x alpha - v sigma; pixels = ClampWithGrad((pred + 1) / 2, 0, 1) (sampling.py:7-15, vdiff.py:159-163)
 __global__ void vd_finish_kernel(const float* __restrict__ vout, int ld, const float* __restrict__ x, float alpha,
                                  float sigma, int pixels, float* __restrict__ v_planar, float* __restrict__ pred,
@@ -272,6 +278,9 @@ __global__ void vd_renoise_kernel(float* __restrict__ x, const float* __restrict
 
 }  // namespace
 
+void vd_set_features(const VdFeatures& f, float* h0_tail, float* te, cudaStream_t st) {
+  vd_set_features_kernel<<<1, 160, 0, st>>>(f, h0_tail, te);
+}
 void vd_input(const float* x, const float* te, int pixels, act_t* out, cudaStream_t st) {
   vd_input_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(x, te, pixels, out);
 }

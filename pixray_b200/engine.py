@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-DRAWER_VQGAN, DRAWER_PIXEL, DRAWER_FFT = 0, 1, 2
+DRAWER_VQGAN, DRAWER_PIXEL, DRAWER_FFT, DRAWER_VDIFF = 0, 1, 2, 3
 LOSS_SYMMETRY, LOSS_SATURATION, LOSS_PALETTE, LOSS_SMOOTHNESS, LOSS_EDGE, LOSS_GAUSSIAN, LOSS_AESTHETIC = range(7)
 PAD_REFLECTION, PAD_BORDER = 0, 1
 MOD_VQGAN, MOD_CLIP0, MOD_CLIP1 = 0, 1, 2
@@ -48,6 +48,9 @@ class B200Engine:
                 cfg.ch_mult[i] = m
             f = 2 ** (cfg.n_levels - 1)
             self.z_shape = (1, cfg.z_channels, image_hw[0] // f, image_hw[1] // f)
+        elif drawer == DRAWER_VDIFF:
+            # VdiffDrawer's x (vdiff.py:118): [1, 3, gen_height, gen_width]
+            self.z_shape = (1, 3, image_hw[0], image_hw[1])
         elif drawer == DRAWER_FFT:
             # FftDrawer params (fftdrawer.py:57-61): rfft2 spectrum [1, 3, H, W/2+1, 2]
             self.z_shape = (1, 3, image_hw[0], image_hw[1] // 2 + 1, 2)
@@ -160,6 +163,30 @@ class B200Engine:
         out = np.zeros(max(self.num_losses(), 1), dtype=np.float32)
         self._check(self.lib.pxr_read_losses(self.h, out.ctypes.data_as(C.c_void_p)), "pxr_read_losses")
         return out[:self.num_losses()]
+
+    # ------------------------------------------------------------------ vdiff drawer
+    def vdiff_set_schedule(self, steps, alphas, sigmas):
+        """sample_state's steps / alphas / sigmas (vdiff.py:113-126, sampling.py:41-51)."""
+        a = [np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1)) for v in (steps, alphas, sigmas)]
+        rc = self.lib.pxr_vdiff_set_schedule(self.h, *(v.ctypes.data_as(C.c_void_p) for v in a), int(a[0].size))
+        self._check(rc, "pxr_vdiff_set_schedule")
+
+    def vdiff_set_clip_embed(self, embed):
+        e = np.ascontiguousarray(np.asarray(embed, dtype=np.float32).reshape(-1))
+        self._check(self.lib.pxr_vdiff_set_clip_embed(self.h, e.ctypes.data_as(C.c_void_p), int(e.size)), "pxr_vdiff_set_clip_embed")
+
+    def vdiff_set_iteration(self, i):
+        self.lib.pxr_vdiff_set_iteration(self.h, int(i))
+
+    def vdiff_renoise(self, z, i, noise=None):
+        """drawer.makenoise(cur_it) (vdiff.py:156-157): in place on z; noise [1,3,H,W] ~ N(0,1) or None (eta = 0)."""
+        if noise is not None:
+            noise = noise.to(self.device, torch.float32).contiguous()
+            torch.cuda.current_stream().synchronize()
+        rc = self.lib.pxr_vdiff_renoise(self.h, self._p_inplace(z, "z"), int(i), self._p(noise))
+        self._check(rc, "pxr_vdiff_renoise")
+        self.sync()
+        return z
 
     def init_comm(self):
         """Cutout-sharded multi-GPU mode: rank 0 draws an ncclUniqueId, torch.distributed (already initialised by the

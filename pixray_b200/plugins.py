@@ -150,6 +150,73 @@ class FastPixelDrawer(DrawingInterface):
         return self.z.clone()
 
 
+class VdiffDrawer(DrawingInterface):
+    """vdiff.py:58-190 (cc12m_1): z = the noisy image x; synth = one v-prediction step + ClampWithGrad; after every
+    optimiser step the loop re-noises x (`makenoise`, pixray.py:1489-1495) and builds a fresh Adam."""
+
+    @staticmethod
+    def add_settings(parser):
+        parser.add_argument("--vdiff_model", type=str, help="VDIFF model from [yfcc_2, yfcc_1, cc12m_1, cc12m_1_cfg]", default="yfcc_2", dest="vdiff_model")
+        parser.add_argument("--vdiff_schedule", type=str, help="VDIFF schedule [default, log]", default="default", dest="vdiff_schedule")
+        parser.add_argument("--vdiff_skip", type=float, help="skip a percentage of the way into the decay schedule (0-100)", default=0, dest="vdiff_skip")
+        return parser
+
+    def __init__(self, settings, session: Session):
+        super().__init__(settings)
+        self.session = session
+        self.iterations = settings.iterations
+        self.vdiff_skip = getattr(settings, "vdiff_skip", 0)
+        if getattr(settings, "vdiff_schedule", "default") != "default":
+            raise NotImplementedError("only the default (spliced DDPM/cosine) schedule is implemented")
+        self.clip_model = "ViT-B/16"  # cc12m_1.py:111
+        self.x = None
+
+    def load_model(self, settings, device):
+        self.device = device
+
+    def get_opts(self, decay_divisor):
+        return None
+
+    def get_num_resolutions(self):
+        return None
+
+    def init_from_tensor(self, init_tensor, seed=None):
+        from .util import vdiff_schedule
+        eng = self.session.engine
+        self.steps, self.alphas, self.sigmas = vdiff_schedule(self.iterations, self.vdiff_skip)
+        eng.vdiff_set_schedule(self.steps, self.alphas, self.sigmas)
+        g = None if seed is None else torch.Generator(device=eng.device).manual_seed(seed)
+        self.x = torch.randn(eng.z_shape, device=eng.device, generator=g)
+        if init_tensor is not None:  # vdiff.py:143: x = init * alpha_0 + noise * sigma_0
+            self.x = init_tensor.to(eng.device) * float(self.alphas[0]) + self.x * float(self.sigmas[0])
+        self.x = self.x.contiguous()
+
+    def set_clip_embed(self, clip_embed):
+        """sample_state[3] = {"clip_embed": ...} (pixray.py:880-885)."""
+        self.session.engine.vdiff_set_clip_embed(torch.as_tensor(clip_embed).detach().cpu().numpy())
+
+    def makenoise(self, cur_it):
+        noise = torch.randn_like(self.x)
+        return self.session.engine.vdiff_renoise(self.x, cur_it, noise)
+
+    def synth(self, cur_iteration):
+        self.session.engine.vdiff_set_iteration(cur_iteration)
+        return self.session.engine.synth(self.x)
+
+    def clip_z(self):
+        return None
+
+    def get_z(self):
+        return self.x
+
+    def set_z(self, new_z):
+        with torch.no_grad():
+            return self.x.copy_(new_z)
+
+    def get_z_copy(self):
+        return self.x.clone()
+
+
 class MakeCutouts:
     """pixray.py:399-511.  `transforms` is the per-iteration cache of composed 3x3s (pixray.py:498); when it is None
     a fresh set is sampled (the distributions of the reference's augmentation stacks, pixray_b200/cutouts.py)."""

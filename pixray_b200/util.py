@@ -54,3 +54,21 @@ def apply_overlay(args, cur_it):
     """pixray.py:1430-1433."""
     return (args.overlay_image is not None and (cur_it % args.overlay_every) == args.overlay_offset
             and (args.overlay_until is None or cur_it < args.overlay_until))
+
+
+def vdiff_schedule(iterations, vdiff_skip=0.0):
+    """VdiffDrawer.init_from_tensor's default schedule (vdiff.py:113-126): t = linspace(top, 0, iterations + 2)[:-1] through
+    the spliced DDPM / cosine schedule (diffusion/utils.py:63-78), then alpha = cos(pi t / 2), sigma = sin(pi t / 2)
+    (utils.py:52-55).  Returns float32 numpy arrays (steps, alphas, sigmas) of length iterations + 1."""
+    import numpy as np
+    top = 1.0 - vdiff_skip / 100.0  # util.map_number(vdiff_skip, 0, 100, 1, 0)
+    t = np.linspace(top, 0.0, iterations + 2, dtype=np.float32)[:-1].astype(np.float64)
+    ddpm_crossover, cosine_crossover = 0.48536712, 0.80074257
+    big_t = t * (1 + cosine_crossover - ddpm_crossover)
+    ddpm_t = big_t + ddpm_crossover - cosine_crossover
+    log_snr = -np.log(np.expm1(1e-4 + 10 * ddpm_t ** 2))
+    alpha, sigma = np.sqrt(1 / (1 + np.exp(-log_snr))), np.sqrt(1 / (1 + np.exp(log_snr)))
+    ddpm_part = np.arctan2(sigma, alpha) / np.pi * 2
+    steps = np.where(big_t < cosine_crossover, big_t, ddpm_part)
+    return (steps.astype(np.float32), np.cos(steps * np.pi / 2).astype(np.float32),
+            np.sin(steps * np.pi / 2).astype(np.float32))
