@@ -689,21 +689,22 @@ class VDiffCC12M1(nn.Module):
                 elif it[0] == "b":
                     _, cin, cmid, cout, last = it
                     skip = reg(key + ".skip", nn.Conv2d(cin, cout, 1, bias=False)) if cin != cout else None  # :43
-                    blk = dict(kind="b", last=last, skip=skip, conv1=reg(key + ".main.0", nn.Conv2d(cin, cmid, 3, padding=1)),
+                    blk = dict(kind="b", key=key, last=last, skip=skip, conv1=reg(key + ".main.0", nn.Conv2d(cin, cmid, 3, padding=1)),
                                mod1=reg(key + ".main.2.layer", nn.Linear(1024, cmid * 2, bias=False)),
                                conv2=reg(key + ".main.4", nn.Conv2d(cmid, cout, 3, padding=1)),
                                mod2=None if last else reg(key + ".main.6.layer", nn.Linear(1024, cout * 2, bias=False)))
                     out.append(blk)
                 elif it[0] == "a":
                     _, ch, heads = it
-                    out.append(dict(kind="a", heads=heads, norm=reg(key + ".norm", nn.GroupNorm(1, ch)),
+                    out.append(dict(kind="a", key=key, heads=heads, norm=reg(key + ".norm", nn.GroupNorm(1, ch)),
                                     qkv=reg(key + ".qkv_proj", nn.Conv2d(ch, ch * 3, 1)),
                                     out=reg(key + ".out_proj", nn.Conv2d(ch, ch, 1))))
                 else:
-                    out.append(dict(kind="s", main=build(it[1], key + ".main")))
+                    out.append(dict(kind="s", key=key, main=build(it[1], key + ".main")))
             return out
 
         self.net = build(self.spec, "net")
+        self.taps = None  # tests: set to a list to collect (key, output tensor) of every block / attention / skip
         with torch.no_grad():  # cc12m_1.py:239-241
             for m in list(self.mods)[first_net:]:
                 for prm in m.parameters():
@@ -755,6 +756,9 @@ class VDiffCC12M1(nn.Module):
                 x = x + it["out"](y)
             else:  # SkipBlock, cc12m_1.py:57-58
                 x = torch.cat([self._run(it["main"], x, cond), x], dim=1)
+            if self.taps is not None and isinstance(it, dict) and x.requires_grad:
+                x.retain_grad()
+                self.taps.append((it["key"], x))
         return x
 
     def forward(self, x, t, clip_embed):

@@ -1,6 +1,7 @@
 // VQGAN-drawer side kernels: nearest-code search, GroupNorm(+swish) fwd/bwd, nearest upsample and its adjoint,
 // image finish (clamp_with_grad) and the pixel drawer.  All HBM/L2-bound; vectorised 16-byte accesses on NHWC fp16.
 #include "kernels.cuh"
+#include <cooperative_groups.h>
 #include <cfloat>
 
 namespace pxr {
@@ -388,6 +389,25 @@ __device__ __forceinline__ void gnc_block_partials(const float (&s)[2][2], float
   }
 }
 
+// Thread-block-cluster variant for the small layers (the whole tensor fits the shared memory of <= 16 SMs): the block
+// partials stay in shared memory, the hardware cluster barrier replaces the global-memory grid barrier and every block
+// folds its peers' partials through distributed shared memory -- no global round trips between the two phases.
+__device__ __forceinline__ void gnc_cluster_fold(float* cpart, int nblk, double count, double* acc4, double* sh) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();  // every block's cpart is written
+  const int tid = threadIdx.x;
+  if (tid < 256) {
+    const int slot = tid & 63, qd = tid >> 6;
+    double a = 0.0;
+    for (int b = qd; b < nblk; b += 4) a += (double)cluster.map_shared_rank(cpart, b)[slot];  // fixed order
+    acc4[qd * 64 + slot] = a;
+  }
+  __syncthreads();
+  if (tid < 64) sh[tid] = (acc4[tid] + acc4[64 + tid] + acc4[128 + tid] + acc4[192 + tid]) / count;
+  cluster.sync();  // nobody leaves (or rewrites cpart) while a peer still reads it
+}
+
 // every block: fold the nblk block partials (fixed order, double) -> sh[64] = per-(group, which) mean
 __device__ __forceinline__ void gnc_fold(const float* part, int nblk, double count, double* acc4, double* sh) {
   const int tid = threadIdx.x;
@@ -420,6 +440,7 @@ __device__ __forceinline__ void gnc_merge_groups(double* sh) {
   __syncthreads();
 }
 
+template <bool CLUSTER>
 __global__ void __launch_bounds__(GNC_THREADS, 1)
     gn_coop_fwd_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                        int pixels, int C, int swish, float eps, int rpb, float* part, float* __restrict__ stats_out,
@@ -447,9 +468,15 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
       s[i >> 1][1] += t.x * t.x + t.y * t.y;
     }
   }
-  gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
-  gnc_grid_barrier(bar, bar_target);
-  gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  __shared__ float cpart[GN_G * 2];
+  if (CLUSTER) {
+    gnc_block_partials(s, red, vecs, cpg, cpart);
+    gnc_cluster_fold(cpart, gridDim.x, (double)pixels * cpg, acc4, sh);
+  } else {
+    gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
+    gnc_grid_barrier(bar, bar_target);
+    gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  }
   if (o.one_group) gnc_merge_groups(sh);  // GroupNorm(1, C): every group takes the statistics of the whole tensor
   if (threadIdx.x < GN_G) {
     const double mean = sh[2 * threadIdx.x], ex2 = sh[2 * threadIdx.x + 1];
@@ -487,6 +514,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   }
 }
 
+template <bool CLUSTER>
 __global__ void __launch_bounds__(GNC_THREADS, 1)
     gn_coop_bwd_kernel(const act_t* __restrict__ dy, const act_t* __restrict__ x, const float* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, int pixels, int C, int swish,
@@ -544,9 +572,15 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
       }
     }
   }
-  gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
-  gnc_grid_barrier(bar, bar_target);
-  gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  __shared__ float cpart[GN_G * 2];
+  if (CLUSTER) {
+    gnc_block_partials(s, red, vecs, cpg, cpart);
+    gnc_cluster_fold(cpart, gridDim.x, (double)pixels * cpg, acc4, sh);
+  } else {
+    gnc_block_partials(s, red, vecs, cpg, part + (size_t)blockIdx.x * GN_G * 2);
+    gnc_grid_barrier(bar, bar_target);
+    gnc_fold(part, gridDim.x, (double)pixels * cpg, acc4, sh);
+  }
   if (o.one_group) gnc_merge_groups(sh);
   float gs0[2], gs1[2];
 #pragma unroll
@@ -732,12 +766,43 @@ int gnc_rows_per_block(int pixels, int num_sms) {
   int r = (pixels + num_sms - 1) / num_sms;
   return r < 16 ? 16 : r;
 }
+bool g_gn_cluster = true;  // PXR_GN_CLUSTER=0: always the grid-barrier kernels
 void gnc_init() {
   static bool done = false;
   if (done) return;
-  cudaFuncSetAttribute(gn_coop_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
-  cudaFuncSetAttribute(gn_coop_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  cudaFuncSetAttribute(gn_coop_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  cudaFuncSetAttribute(gn_coop_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  cudaFuncSetAttribute(gn_coop_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  cudaFuncSetAttribute(gn_coop_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_SMEM_MAX);
+  cudaFuncSetAttribute(gn_coop_fwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(gn_coop_bwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (const char* e = getenv("PXR_GN_CLUSTER")) g_gn_cluster = atoi(e) != 0;
   done = true;
+}
+// one cluster of 8 or 16 blocks when the tensor is small enough for their shared memory (slabs bytes: fwd 1x, bwd 2x)
+int gnc_cluster_blocks(int pixels, int C, int slabs) {
+  if (!g_gn_cluster) return 0;
+  for (int nb : {8, 16}) {
+    const int rpb = (pixels + nb - 1) / nb;
+    if (4 * GNC_THREADS * 4 + (size_t)slabs * rpb * C * 2 <= (size_t)GNC_SMEM_MAX && rpb * nb >= pixels) return nb;
+  }
+  return 0;
+}
+template <class K, class... Args>
+void gnc_launch_cluster(K kernel, int nb, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nb);
+  cfg.blockDim = dim3(GNC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nb;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 }  // namespace
 
@@ -750,11 +815,17 @@ bool gn_coop_supported(int pixels, int C, int num_sms) {
 void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int pixels, int C, int swish, float eps,
                      float* part, float* stats, act_t* y, int num_sms, GridBarrier* gb, cudaStream_t st, GnOpts o) {
   gnc_init();
+  if (const int nb = gnc_cluster_blocks(pixels, C, 1)) {
+    const int rpb = (pixels + nb - 1) / nb;
+    gnc_launch_cluster(gn_coop_fwd_kernel<true>, nb, 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2, st, x, gamma, beta, pixels,
+                       C, swish, eps, rpb, part, stats, y, (unsigned long long*)nullptr, 0ULL, o);
+    return;
+  }
   int rpb = gnc_rows_per_block(pixels, num_sms);
   const int grid = (pixels + rpb - 1) / rpb;
   const size_t smem = 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2;
-  gn_coop_fwd_kernel<<<grid, GNC_THREADS, smem, st>>>(x, gamma, beta, pixels, C, swish, eps, rpb, part, stats, y,
-                                                      gb->counter, gb->issued + grid, o);
+  gn_coop_fwd_kernel<false><<<grid, GNC_THREADS, smem, st>>>(x, gamma, beta, pixels, C, swish, eps, rpb, part, stats, y,
+                                                             gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;  // a rejected launch must not move the target
 }
 
@@ -762,13 +833,19 @@ void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const
                       int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
                       GridBarrier* gb, cudaStream_t st, GnOpts o) {
   gnc_init();
+  if (const int nb = gnc_cluster_blocks(pixels, C, 2)) {
+    const int rpb = (pixels + nb - 1) / nb;
+    gnc_launch_cluster(gn_coop_bwd_kernel<true>, nb, 4 * GNC_THREADS * 4 + (size_t)2 * rpb * C * 2, st, dy, x, stats, gamma,
+                       beta, pixels, C, swish, dres, rpb, 1, part, dx, (unsigned long long*)nullptr, 0ULL, o);
+    return;
+  }
   int rpb = gnc_rows_per_block(pixels, num_sms);
   const int grid = (pixels + rpb - 1) / rpb;
   const size_t slab = (size_t)rpb * C * 2;
   int cache_dy = (4 * GNC_THREADS * 4 + 2 * slab <= (size_t)GNC_SMEM_MAX) ? 1 : 0;
   const size_t smem = 4 * GNC_THREADS * 4 + (cache_dy ? 2 : 1) * slab;
-  gn_coop_bwd_kernel<<<grid, GNC_THREADS, smem, st>>>(dy, x, stats, gamma, beta, pixels, C, swish, dres, rpb, cache_dy,
-                                                      part, dx, gb->counter, gb->issued + grid, o);
+  gn_coop_bwd_kernel<false><<<grid, GNC_THREADS, smem, st>>>(dy, x, stats, gamma, beta, pixels, C, swish, dres, rpb,
+                                                             cache_dy, part, dx, gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;
 }
 

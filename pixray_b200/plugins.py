@@ -353,4 +353,11 @@ def train_iteration(session: Session, drawer, make_cutouts, perceptors, prompt_t
     session.backward(drawer)
     opt.step()
     drawer.clip_z()
+    if isinstance(drawer, VdiffDrawer) and session.cur_iteration >= 1:
+        # pixray.py:1489-1495: re-noise x for the next timestep and start a fresh Adam with the schedule's step size
+        it = session.cur_iteration
+        lr = float(drawer.sigmas[it] / drawer.alphas[it])
+        drawer.makenoise(it)
+        opt.lr = min(lr * 0.001, 0.01)
+        session.engine.reset_optimizer()
     return result
