@@ -705,10 +705,24 @@ class VDiffCC12M1(nn.Module):
 
         self.net = build(self.spec, "net")
         self.taps = None  # tests: set to a list to collect (key, output tensor) of every block / attention / skip
+        # tests: quant = True rounds the stored activations to fp16 (straight-through) at the points where the engine
+        # stores fp16 tensors, so that ReLU branches are decided on (nearly) the same values as in the engine
+        self.quant = False
         with torch.no_grad():  # cc12m_1.py:239-241
             for m in list(self.mods)[first_net:]:
                 for prm in m.parameters():
                     prm *= 0.5 ** 0.5
+
+    def _q(self, t):
+        return t + (t.half().float() - t).detach() if self.quant else t
+
+    def round_weights_to_fp16_(self):
+        """Round every conv / linear weight to fp16 in place (biases and norm affines stay fp32, like in the engine)."""
+        with torch.no_grad():
+            for _, m in self.keys:
+                if isinstance(m, (nn.Conv2d, nn.Linear)):
+                    m.weight.copy_(m.weight.half().float())
+        return self
 
     def ref_state_dict(self):
         sd = OrderedDict()
@@ -733,27 +747,31 @@ class VDiffCC12M1(nn.Module):
     def _run(self, items, x, cond):
         for it in items:
             if it == "down":
-                x = F.avg_pool2d(x, 2)
+                x = self._q(F.avg_pool2d(x, 2))
             elif it == "up":
-                x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+                x = self._q(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
             elif it["kind"] == "b":
                 def mod(lin, h):  # Modulation2d, cc12m_1.py:36-38
                     sc, sh = lin(cond).chunk(2, dim=-1)
                     return torch.addcmul(sh[..., None, None], h, sc[..., None, None] + 1)
-                h = it["conv1"](x)
-                h = F.relu(mod(it["mod1"], F.group_norm(h, 1)))
+                q = self._q
+                h = q(it["conv1"](x))
+                h = q(F.relu(mod(it["mod1"], F.group_norm(h, 1))))
                 h = it["conv2"](h)
+                sk = q(it["skip"](x)) if it["skip"] is not None else x
                 if not it["last"]:
-                    h = F.relu(mod(it["mod2"], F.group_norm(h, 1)))
-                x = h + (it["skip"](x) if it["skip"] is not None else x)
+                    h = F.relu(mod(it["mod2"], F.group_norm(q(h), 1)))
+                    x = q(h + sk)
+                else:
+                    x = h + sk
             elif it["kind"] == "a":  # SelfAttention2d, cc12m_1.py:88-97
                 n, c, hh, ww = x.shape
-                qkv = it["qkv"](it["norm"](x)).view(n, it["heads"] * 3, c // it["heads"], hh * ww).transpose(2, 3)
+                qkv = self._q(it["qkv"](self._q(it["norm"](x)))).view(n, it["heads"] * 3, c // it["heads"], hh * ww).transpose(2, 3)
                 q, k, v = qkv.chunk(3, dim=1)
                 scale = k.shape[3] ** -0.25
                 att = ((q * scale) @ (k.transpose(2, 3) * scale)).softmax(3)
-                y = (att @ v).transpose(2, 3).contiguous().view(n, c, hh, ww)
-                x = x + it["out"](y)
+                y = self._q((att @ v).transpose(2, 3).contiguous().view(n, c, hh, ww))
+                x = self._q(x + it["out"](y))
             else:  # SkipBlock, cc12m_1.py:57-58
                 x = torch.cat([self._run(it["main"], x, cond), x], dim=1)
             if self.taps is not None and isinstance(it, dict) and x.requires_grad:
@@ -764,7 +782,7 @@ class VDiffCC12M1(nn.Module):
     def forward(self, x, t, clip_embed):
         cond = self.cond(t, clip_embed)
         te = self.fourier(t, self.t_ff)[..., None, None].repeat(1, 1, x.shape[2], x.shape[3])
-        return self._run(self.net, torch.cat([x, te], dim=1), cond)
+        return self._run(self.net, self._q(torch.cat([x, te], dim=1)), cond)
 
 
 def vdiff_t_to_alpha_sigma(t):
