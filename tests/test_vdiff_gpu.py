@@ -13,7 +13,8 @@ element changes its gradient entry by O(1).  profiles/r01_vdiff_layer_parity.log
 gradient scale.  The smooth drawers (swish / QuickGELU) do not have this effect and keep 3e-2; here the stated bound is
 max-abs-err <= 8e-2 max|z.grad|, relative L2 error <= 0.12 and cosine similarity >= 0.99 -- the reference's own CUDA path
 runs this U-Net under fp16 autocast (sampling.py:9-10) and differs from an fp32 evaluation in the same way.  At 256 x 256,
-where the direct alpha * g_pred term dominates z.grad, the measured error is 2.9e-3.
+where the direct alpha * g_pred term dominates z.grad, the measured error is 2.9e-3.  The matched-rounding test below
+removes the branch flips and brings the 64 x 64 gradient to 6.5e-3 max-abs / 1.0e-2 rel-L2.
 """
 import numpy as np
 import pytest
