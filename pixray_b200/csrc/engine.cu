@@ -326,6 +326,48 @@ class Engine {
     l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e));
   }
 
+  // Split-K for a plain K-major GEMM with few output tiles and a long reduction (the vdiff U-Net's 4x4 ... 1x1 levels:
+  // M <= 16 pixels, K = 9 * cin up to 18432): partial sums to the shared workspace, then the same fixed-order reduce.
+  void add_gemm_splitk(OpList& l, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, const GemmEpilogue& e) {
+    const int bn = pick_bn(N, false, (M + 127) / 128);
+    const int nkb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    const long long tiles = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
+    int splits = 1;
+    if (conv_splitk && splitk_ws && e.out_f16 && !e.out_f32 && !e.res_f32 && !e.aux_out && e.act == ACT_NONE && e.alpha == 1.f &&
+        N % 8 == 0 && e.ldc % 8 == 0 && tiles * 2 <= num_sms && nkb >= 8) {
+      const int want = (int)std::min<long long>(num_sms / tiles, nkb / 4);
+      if (want >= 2) {
+        const int kbps = (nkb + want - 1) / want;
+        splits = (nkb + kbps - 1) / kbps;
+      }
+      if ((size_t)splits * M * N > splitk_ws_elems) splits = 1;
+    }
+    if (splits <= 1) {
+      add_gemm(l, A, B, M, N, K, e);
+      return;
+    }
+    auto plan = std::make_shared<GemmPlan>();
+    char buf[256] = {0};
+    GemmEpilogue pe;
+    pe.out_f32 = splitk_ws;
+    pe.ldc = N;
+    pe.k_splits = splits;
+    pe.tma_epi = -1;
+    int rc = gemm_plan_make(plan.get(), A, B, M, N, K, pe, bn, fmt, num_sms, buf, sizeof buf);
+    if (rc) throw EngineError(rc, std::string("gemm plan (split-K): ") + buf);
+    cudaStream_t s = st;
+    const float* ws = splitk_ws;
+    const float* bias = e.bias;
+    const act_t* res = e.res_f16;
+    act_t* out = e.out_f16;
+    const int ld_out = (int)e.ldc;
+    std::string label = gemm_label("gemm", *plan, A.mode, B.mode, e) + " splitK=" + std::to_string(plan->p.k_splits);
+    l.add(2, [=] {
+      gemm_launch(*plan, s);
+      splitk_reduce(ws, plan->p.k_splits, M, N, N, bias, res, out, ld_out, s);
+    }, plan->flops, label);
+  }
+
   // ------------------------------------------------------------------ build steps
   void create();
   void finalize();

@@ -430,6 +430,7 @@ __device__ __forceinline__ void producer_tiles(const GemmParams& p, uint8_t* sme
     const int kb_begin = p.k_splits > 1 ? t.z * p.kb_per_split : 0;
     const int kb_end = p.k_splits > 1 ? min(p.num_k_blocks, kb_begin + p.kb_per_split) : p.num_k_blocks;
     const int img = p.k_splits > 1 ? 0 : t.z;  // split-K: z is the split, there is one image
+    const int ab0 = p.k_splits > 1 ? 0 : t.b0, ab1 = p.k_splits > 1 ? 0 : t.b1;  // ... and one (unbatched) A
     int tap = 0, kk = 0, ty = -1, tx = -1;     // running tap index, k offset inside the tap, tap offset (dy, dx)
     if (AM == OP_CONV) {
       tap = kb_begin / p.k_blocks_per_tap;
@@ -449,10 +450,10 @@ __device__ __forceinline__ void producer_tiles(const GemmParams& p, uint8_t* sme
       mbar_wait_s(empty0 + stage * 8, phase ^ 1);
       mbar_arrive_expect_tx_s(fb, stage_bytes);
       if (AM == OP_KMAJOR) {
-        tma_load_4d_s(&p.tma_a, fb, sa, kk, t.m0, t.b0, t.b1);
+        tma_load_4d_s(&p.tma_a, fb, sa, kk, t.m0, ab0, ab1);
       } else if (AM == OP_MNMAJOR) {
-        tma_load_4d_s(&p.tma_a, fb, sa, t.m0, kk, t.b0, t.b1);
-        tma_load_4d_s(&p.tma_a, fb, sa + MN_ATOM_BYTES, t.m0 + 64, kk, t.b0, t.b1);
+        tma_load_4d_s(&p.tma_a, fb, sa, t.m0, kk, ab0, ab1);
+        tma_load_4d_s(&p.tma_a, fb, sa + MN_ATOM_BYTES, t.m0 + 64, kk, ab0, ab1);
       } else {
         tma_load_4d_s(&p.tma_a, fb, sa, kk, t.w0 + tx, t.h0 + ty, img);
       }
@@ -1576,13 +1577,25 @@ int gemm_plan_make(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
   p.total_tiles = p.tiles_m * p.tiles_n * nb0 * nb1;
   p.k_splits = 1;
   p.kb_per_split = p.num_k_blocks;
+  GemmEpilogue epi_s = epi;
+  if (epi.k_splits > 1) {  // split-K: the batch index of a tile becomes the split (fp32 partial sums, slab z of out_f32)
+    if (nb0 != 1 || nb1 != 1 || !epi.out_f32 || epi.out_f16 || epi.bias || epi.res_f16 || epi.res_f32 || epi.act != ACT_NONE) {
+      set_err(err, errlen, "split-K GEMM: unbatched operands, plain fp32 partial sums only");
+      return -22;
+    }
+    p.kb_per_split = (p.num_k_blocks + epi.k_splits - 1) / epi.k_splits;
+    p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.nb0 = p.k_splits;
+    p.total_tiles = p.tiles_m * p.tiles_n * p.k_splits;
+    epi_s.bs0 = (long long)M * epi.ldc;
+  }
   int rc = encode_operand(&p.tma_a, A, GEMM_BLOCK_M, fmt, err, errlen);
   if (rc) return rc;
   p.cta_group = decide_cta_group(p, epi, block_n, num_sms);
   rc = encode_operand(&p.tma_b, B, p.cta_group == 2 ? block_n / 2 : block_n, fmt, err, errlen);
   if (rc) return rc;
   plan->flops = 2.0 * M * N * K * nb0 * nb1;
-  return finish_plan(plan, epi, block_n, num_sms, err, errlen);
+  return finish_plan(plan, epi_s, block_n, num_sms, err, errlen);
 }
 
 int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, int H, int W, int c_in, const void* wt,

@@ -47,14 +47,33 @@ for i in range(warm):
     one(i)
 eng.sync()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+w0 = time.time()
 e0.record(ext)
 for i in range(warm, iters):
     one(i)
 e1.record(ext)
 eng.sync()
 torch.cuda.synchronize()
+wall_ms = (time.time() - w0) * 1e3 / steps_n
 ms = e0.elapsed_time(e1) / steps_n
+print(f"events {ms:.3f} ms/step, wall {wall_ms:.3f} ms/step", flush=True)
+ms = max(ms, 0.0) if ms > 0.5 * wall_ms else wall_ms  # an ExternalStream event pair that does not bracket the work reads ~0
+os.makedirs("gpurun_out", exist_ok=True)
+os.environ["PXR_PROFILE_DUMP"] = "gpurun_out/vdiff_ops.tmp"
 prof = eng.profile_iteration(z, 0.001, iters - 1)
+import collections  # noqa: E402
+import csv  # noqa: E402
+agg = collections.OrderedDict()
+for row in csv.DictReader(open("gpurun_out/vdiff_ops.tmp")):
+    a = agg.setdefault(row["op"], [0, 0.0, 0.0])
+    a[0] += 1
+    a[1] += float(row["ms"])
+    a[2] += float(row["gflop"])
+with open("gpurun_out/vdiff_ops.csv", "w") as f:
+    f.write("op,count_per_iter,us_per_iter,us_each,tflops\n")
+    for k, (n, t_ms, gf) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"{k},{n},{t_ms * 1e3:.1f},{t_ms / n * 1e3:.1f},{gf / t_ms if gf else 0:.0f}\n")
 print(json.dumps({"workload": "vdiff cc12m_1 256x256, ViT-B/16, cutn=64 (BASELINE.json configs[3])", "n_gpus": 1,
                   "iters_per_sec": 1e3 / ms, "ms_per_step": ms, "steps": steps_n, "finite_z": bool(torch.isfinite(z).all()),
                   "tcgen05_family_ms": prof["gemm_ms"], "other_ms": prof["other_ms"],
