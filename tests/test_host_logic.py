@@ -60,3 +60,41 @@ def test_flop_accounting_matches_survey():
 def test_prompts_are_unit_norm_and_seeded():
     a, b = synthetic.prompts(512, (1.0, 0.1), 5), synthetic.prompts(512, (1.0, 0.1), 5)
     assert torch.equal(a[0][0], b[0][0]) and abs(a[1][0].norm().item() - 1) < 1e-5
+
+
+def test_loss_plugin_settings_match_the_reference():
+    """pixray_b200.losses mirrors Losses/*.py's add_settings: same option names, defaults, types and nargs
+    (tests/golden/loss_settings.json was dumped from the reference classes' own parsers under oracle/shim.py)."""
+    import argparse
+    import json
+    import os
+
+    from pixray_b200 import losses as L
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "loss_settings.json")))
+    for name, ref in want.items():
+        p = getattr(L, name).add_settings(argparse.ArgumentParser())
+        got = {a.dest: {"default": list(a.default) if isinstance(a.default, (tuple, list)) else a.default,
+                        "type": getattr(a.type, "__name__", None), "nargs": a.nargs} for a in p._actions if a.dest != "help"}
+        assert got == ref, name
+    assert set(L.loss_class_table) >= {"palette", "saturation", "symmetry", "smoothness", "edge", "aesthetic"}
+
+
+def test_edge_loss_parse_settings_follows_the_reference():
+    import types
+
+    from pixray_b200 import losses as L
+    a = types.SimpleNamespace(edge_thickness=7, edge_margins=None, edge_color="(255+128+0)", edge_input_image="", edge_mask_image="")
+    a = L.EdgeLoss(device=None).parse_settings(a)
+    assert a.edge_margins == (7, 7, 7, 7)  # EdgeLoss.py:33-35
+    assert [round(v, 6) for v in a.edge_color] == [1.0, round(128 / 255, 6), 0.0]  # util.parse_triple_to_rgb
+
+
+def test_vdiff_schedule_helper_matches_the_oracle():
+    import numpy as np
+
+    from oracle import ref_path as R
+    from pixray_b200 import util as U
+    for n, skip in ((20, 0.0), (300, 0.0), (50, 25.0)):
+        s, a, g = U.vdiff_schedule(n, skip)
+        rs, ra, rg = R.vdiff_schedule(n, skip)
+        assert np.allclose(s, rs.numpy(), atol=2e-6) and np.allclose(a, ra.numpy(), atol=2e-6) and np.allclose(g, rg.numpy(), atol=2e-6)
