@@ -230,15 +230,26 @@ def run_engine(args, rank, world):
     ms = e0.elapsed_time(e1)
     launches = eng.num_launches() - n0
     # ---- e2e arm: host transforms in (H2D) and host losses out (D2H + sync) every step, through the Python plugin API
+    # (what plugins.MakeCutouts hands over per iteration: homographies, ColorJitter rows and noise factors from the host,
+    # the N(0,1) noise tensor drawn on the device by torch like the reference's randn_like, pixray.py:509-510)
+    from pixray_b200.cutouts import sample_color_jitter as sample_jitter_np
     Ts = [sample_transforms_np(CUTN, CUT_SIZE, 1000 + i) for i in range(args.steps)]
+    Js = [sample_jitter_np(CUTN, 2000 + i) for i in range(args.steps)]
+    Fs = [(np.random.default_rng(3000 + i).random(CUTN) * 0.1).astype(np.float32) for i in range(args.steps)]
     losses = np.zeros(2, dtype=np.float32)
+
+    def e2e_step(i, it):
+        noise = torch.randn(CUTN, 3, CUT_SIZE, CUT_SIZE, device="cuda")
+        eng.iterate(z, LR, it, params=dict(transforms=Ts[i], zoom_padding=it % 2, fill=0.5, color_jitter=Js[i],
+                                           noise_facs=Fs[i], noise=noise), losses_out=losses)
+
     for it in range(min(3, args.warmup)):
-        eng.iterate(z, LR, it, params=dict(transforms=Ts[0], zoom_padding=it % 2, fill=0.5), losses_out=losses)
+        e2e_step(0, it)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(ext)
     for i in range(args.steps):
-        eng.iterate(z, LR, i, params=dict(transforms=Ts[i], zoom_padding=i % 2, fill=0.5), losses_out=losses)
+        e2e_step(i, i)
     f1.record(ext)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -277,7 +288,7 @@ def run_engine(args, rank, world):
                    "algorithmic_flops_per_iter": S_flops},
         "clocks": clocks,
         "e2e": {"value": jobs * args.steps / (ms_e2e * 1e-3), "unit": "iters/sec",
-                "h2d_bytes_per_step": CUTN * 9 * 4, "d2h_bytes_per_step": 64 * 4},
+                "h2d_bytes_per_step": CUTN * (9 + 3 + 1) * 4, "d2h_bytes_per_step": 64 * 4},
         "gpu_launches": launches,
         "roofline": {"kernel": "tcgen05 family: gemm_tc*/gemm_tce* (GEMM / implicit-GEMM conv) + attn_fwd/attn_bwd (fused attention)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",

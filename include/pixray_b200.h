@@ -78,6 +78,12 @@ typedef struct {
   float fill;              /* wide-group fill grey = random.random() (pixray.py:1255-1258) */
   const float* noise_facs; /* host, [cutn] ~ U(0, noise_fac) (pixray.py:509); NULL = engine Philox */
   const float* noise;      /* DEVICE, [cutn,3,cs,cs] standard normal (pixray.py:510); NULL = engine Philox */
+  /* K.ColorJitter(hue=0.1, saturation=0.1, p=0.8), the last stage of both stacks (pixray.py:416, 436): host
+   * [cutn, 3] rows {code, saturation_factor, hue_factor}.  code 0 = this cutout missed the Bernoulli(p); else
+   * 256 + o0 + 4*o1 + 16*o2 + 64*o3 with o_k the transform applied k-th (0 brightness, 1 contrast, 2 saturation,
+   * 3 hue: kornia's params["order"]).  NULL with explicit transforms = no jitter (the cached-transform replay,
+   * pixray.py:480-486); with transforms == NULL the engine draws these too (pxr_set_color_jitter). */
+  const float* color_jitter;
 } pxr_cut_params;
 
 const char* pxr_last_error(pxr_handle h); /* h may be NULL for creation errors */
@@ -101,6 +107,10 @@ int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world);
 int pxr_get_unique_id(void* out128);
 
 int pxr_synth(pxr_handle h, const float* z, float* out_img /* [3,H,W] */);
+/* Distribution of the engine-drawn ColorJitter: Bernoulli(p) per cutout, saturation_factor ~ U(1-s, 1+s),
+ * hue_factor ~ U(-hue, hue), one random order per group and iteration.  Defaults = the reference's call sites
+ * (0.8, 0.1, 0.1); p = 0 turns the stage off. */
+int pxr_set_color_jitter(pxr_handle h, float p, float saturation, float hue);
 int pxr_make_cutouts(pxr_handle h, const float* img, const pxr_cut_params* p, int iter,
                      float* out_batch /* [cutn_local,3,cs,cs] */);
 int pxr_encode_image(pxr_handle h, int clip_idx, const float* batch, float* out_embeds /* [cutn_local, D] */);
@@ -184,6 +194,10 @@ int pxr_test_gemm(const pxr_test_gemm_desc* d, char* err, int errlen);
 /* implicit-GEMM conv over NHWC fp16: d->a = input (pixel stride lda), d->b = weights [taps*cout_pad, c_in] */
 int pxr_test_conv(const pxr_test_gemm_desc* d, int batch, int H, int W, int c_in, int cout_pad, int ksize, char* err,
                   int errlen);
+
+/* host-side evaluation of the ColorJitter pixel body and its vector-Jacobian product (no GPU needed) */
+int pxr_test_color_jitter_host(const float* rgb, int n, int code, float saturation, float hue, const float* g_out,
+                               float* out, float* g_in);
 
 /* fused ViT attention (attn_tc.cu): forward, and backward when d_o != NULL.  qkv [B*T, 3W], o / d_o [B*T, W],
  * gqkv [B*T, 3W] fp16 device tensors, lse [B*H*T] fp32; heads are 64 wide (W = 64 H), T <= 256 */

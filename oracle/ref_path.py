@@ -150,12 +150,14 @@ def warp_perspective(src, M, dsize, padding_mode="zeros", fill_value=None, align
     return F.grid_sample(src, grid, align_corners=align_corners, mode="bilinear", padding_mode=padding_mode)
 
 
-def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None, noise=None, cutn_zoom=None):
+def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None, noise=None, cutn_zoom=None,
+                 jitter=None):
     """MakeCutouts.forward on explicit (cached) transforms, pixray.py:445-511.
 
     img [1, 3, H, W]; transforms [cutn, 3, 3]; zoom group = first int(0.6 * cutn) (pixray.py:407) warped with
-    `zoom_padding` ('reflection' | 'border'); wide group with constant grey `fill`; then batch + facs * noise
-    (pixray.py:508-510) when both are given."""
+    `zoom_padding` ('reflection' | 'border'); wide group with constant grey `fill`; then ColorJitter on the rows of
+    `jitter` (the live stacks' last stage, pixray.py:416, 436), then batch + facs * noise (pixray.py:508-510)
+    when both are given."""
     cutn = transforms.shape[0]
     if cutn_zoom is None:
         cutn_zoom = int(0.6 * cutn)
@@ -169,9 +171,94 @@ def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None,
         parts.append(warp_perspective(src[cutn_zoom:], transforms[cutn_zoom:], (cut_size, cut_size),
                                       padding_mode="fill", fill_value=[fill, fill, fill]))
     batch = torch.cat(parts)
+    if jitter is not None:
+        batch = color_jitter(batch, jitter)
     if noise_facs is not None and noise is not None:
         batch = batch + noise_facs.reshape(cutn, 1, 1, 1) * noise
     return batch
+
+
+# K.ColorJitter(hue=0.1, saturation=0.1, p=0.8, return_transform=True): last stage of augs_zoom and augs_wide
+# (pixray.py:416, 436).  kornia==0.6.2 (requirements.txt) is not vendored under /root/reference and not installed here:
+# the functions below restate its published algorithm (kornia/color/hsv.py rgb_to_hsv / hsv_to_rgb,
+# kornia/enhance/adjust.py adjust_{brightness,contrast,saturation,hue}, kornia/augmentation ColorJitter.apply_transform
+# with random_color_jitter_generator's parameters).  Parity for this stage is therefore UNPINNED against kornia itself;
+# it is anchored on the reference's call site (which factors, which probability) and on the kernel matching this
+# restatement forward and backward.
+
+
+def rgb_to_hsv(image, eps=1e-8):
+    """kornia.color.rgb_to_hsv: [*, 3, H, W] in [0, 1] -> h in [0, 2pi), s, v."""
+    max_rgb, argmax_rgb = image.max(-3)
+    min_rgb, _ = image.min(-3)
+    deltac = max_rgb - min_rgb
+    v = max_rgb
+    s = deltac / (max_rgb + eps)
+    deltac = torch.where(deltac == 0, torch.ones_like(deltac), deltac)
+    rc, gc, bc = torch.unbind(max_rgb.unsqueeze(-3) - image, dim=-3)
+    h = torch.stack(((bc - gc), (rc - bc) + 2.0 * deltac, (gc - rc) + 4.0 * deltac), dim=-3) / deltac.unsqueeze(-3)
+    h = torch.gather(h, dim=-3, index=argmax_rgb.unsqueeze(-3)).squeeze(-3)
+    h = (h / 6.0) % 1.0
+    h = 2.0 * math.pi * h
+    return torch.stack((h, s, v), dim=-3)
+
+
+def hsv_to_rgb(image):
+    """kornia.color.hsv_to_rgb: h in radians."""
+    h = image[..., 0, :, :] / (2 * math.pi)
+    s = image[..., 1, :, :]
+    v = image[..., 2, :, :]
+    hi = torch.floor(h * 6) % 6
+    f = ((h * 6) % 6) - hi
+    p = v * (1.0 - s)
+    q = v * (1.0 - f * s)
+    t = v * (1.0 - (1.0 - f) * s)
+    hi = hi.long()
+    indices = torch.stack([hi, hi + 6, hi + 12], dim=-3)
+    out = torch.stack((v, q, p, p, t, v, t, v, v, q, p, p, p, p, t, v, v, q), dim=-3)
+    return torch.gather(out, -3, indices)
+
+
+def _adjust_saturation(x, factor):
+    hsv = rgb_to_hsv(x)
+    h, s, v = torch.chunk(hsv, 3, dim=-3)
+    return hsv_to_rgb(torch.cat([h, torch.clamp(s * factor, 0, 1), v], dim=-3))
+
+
+def _adjust_hue(x, factor_rad):
+    hsv = rgb_to_hsv(x)
+    h, s, v = torch.chunk(hsv, 3, dim=-3)
+    return hsv_to_rgb(torch.cat([torch.fmod(h + factor_rad, 2 * math.pi), s, v], dim=-3))
+
+
+def jitter_code(order):
+    """Pack an application order (a permutation of 0 brightness, 1 contrast, 2 saturation, 3 hue) as the engine does."""
+    return 256 + order[0] + 4 * order[1] + 16 * order[2] + 64 * order[3]
+
+
+def color_jitter(batch, jitter):
+    """ColorJitter.apply_transform on the cutouts its Bernoulli(p) selected.  jitter [n, 3] float32 rows
+    {code, saturation_factor, hue_factor}: code 0 = not selected, else jitter_code(order); brightness=contrast=0 at
+    the call site, so those two stages are adjust_brightness(x, 0) / adjust_contrast(x, 1) = clamp(x, 0, 1)."""
+    out = []
+    for n in range(batch.shape[0]):
+        x = batch[n:n + 1]
+        code = int(jitter[n, 0])
+        if code:
+            sat = jitter[n, 1].to(x.dtype)
+            hue = jitter[n, 2].to(x.dtype) * 2 * math.pi
+            for k in range(4):
+                op = (code >> (2 * k)) & 3
+                if op == 0:
+                    x = torch.clamp(x + 0.0, 0.0, 1.0)
+                elif op == 1:
+                    x = torch.clamp(x * 1.0, 0.0, 1.0)
+                elif op == 2:
+                    x = _adjust_saturation(x, sat)
+                else:
+                    x = _adjust_hue(x, hue)
+        out.append(x)
+    return torch.cat(out)
 
 
 # ------------------------------------------------------------------------------------------------ perceptor
@@ -844,7 +931,8 @@ class AdamState:
         return z - (lr / bc1) * self.m / denom
 
 
-def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=()):
+def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=(),
+            jitter=None):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
@@ -853,7 +941,7 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
     out.retain_grad()
-    batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise)
+    batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise, jitter=jitter)
     batch.retain_grad()
     losses, embeds = [], []
     for model, pms in zip(clip_models, prompts):

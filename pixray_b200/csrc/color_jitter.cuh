@@ -1,0 +1,164 @@
+// K.ColorJitter(hue=0.1, saturation=0.1, p=0.8), the last stage of both augmentation stacks of MakeCutouts
+// (pixray.py:416, 436), per pixel.  kornia 0.6.2 is an un-vendored dependency of the reference (requirements.txt);
+// this restates its published algorithm:
+//   ColorJitter.apply_transform : four transforms applied in the order `params["order"]` (a randperm(4)):
+//        0 adjust_brightness(x, factor - 1) = clamp(x + (factor - 1), 0, 1)   factor == 1 with brightness=0
+//        1 adjust_contrast(x, factor)       = clamp(x * factor, 0, 1)         factor == 1 with contrast=0
+//        2 adjust_saturation(x, f)          = hsv_to_rgb(h, clamp(s * f, 0, 1), v)
+//        3 adjust_hue(x, f * 2pi)           = hsv_to_rgb(fmod(h + f * 2pi, 2pi), s, v)
+//   rgb_to_hsv (eps 1e-8): v = max, s = (max - min) / (max + eps), h from the arg-max channel, in radians;
+//   hsv_to_rgb: sector = floor(6h) mod 6, the usual (v, q, p, t) table.
+// One templated body serves the forward (T = float) and the backward: with T = Dual3 (value + the three partials
+// d/d{r,g,b}) it yields the 3x3 Jacobian of the whole chain, so the gradient is by construction the derivative of
+// the forward that was executed (max / min route to the first arg-max / arg-min channel as torch.max(dim) does on
+// ties, floor and the mods have zero / unit derivative, clamp passes the gradient on the closed interval).
+// Host-callable so the CPU suite can check the arithmetic against the oracle without a GPU (test_hooks.cu).
+#pragma once
+#include <cmath>
+#include <cuda_runtime.h>
+
+namespace pxr {
+
+struct Dual3 {
+  float v;
+  float d[3];
+};
+
+#define PXR_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define PXR_UNROLL _Pragma("unroll")
+#define PXR_NOUNROLL _Pragma("unroll 1")
+#else
+#define PXR_UNROLL
+#define PXR_NOUNROLL
+#endif
+
+PXR_HD float cj_val(float x) { return x; }
+PXR_HD float cj_val(const Dual3& x) { return x.v; }
+PXR_HD float cj_const(float, float c) { return c; }
+PXR_HD Dual3 cj_const(const Dual3&, float c) { return Dual3{c, {0.f, 0.f, 0.f}}; }
+
+PXR_HD Dual3 operator+(const Dual3& a, const Dual3& b) { return Dual3{a.v + b.v, {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2]}}; }
+PXR_HD Dual3 operator-(const Dual3& a, const Dual3& b) { return Dual3{a.v - b.v, {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2]}}; }
+PXR_HD Dual3 operator*(const Dual3& a, const Dual3& b) {
+  return Dual3{a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
+}
+PXR_HD Dual3 operator/(const Dual3& a, const Dual3& b) {
+  const float q = a.v / b.v, r = 1.f / b.v;
+  return Dual3{q, {(a.d[0] - q * b.d[0]) * r, (a.d[1] - q * b.d[1]) * r, (a.d[2] - q * b.d[2]) * r}};
+}
+PXR_HD Dual3 operator+(const Dual3& a, float b) { return Dual3{a.v + b, {a.d[0], a.d[1], a.d[2]}}; }
+PXR_HD Dual3 operator*(const Dual3& a, float b) { return Dual3{a.v * b, {a.d[0] * b, a.d[1] * b, a.d[2] * b}}; }
+PXR_HD Dual3 operator/(const Dual3& a, float b) { return Dual3{a.v / b, {a.d[0] / b, a.d[1] / b, a.d[2] / b}}; }
+PXR_HD Dual3 operator-(float a, const Dual3& b) { return Dual3{a - b.v, {-b.d[0], -b.d[1], -b.d[2]}}; }
+
+// replace the value, keep the partials (x mod m, fmod: derivative 1) / drop them (floor: derivative 0)
+PXR_HD float cj_with_value(float, float v) { return v; }
+PXR_HD Dual3 cj_with_value(const Dual3& x, float v) { return Dual3{v, {x.d[0], x.d[1], x.d[2]}}; }
+
+// torch.remainder (the `%` of the reference): sign of the divisor
+PXR_HD float cj_pymod(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.f && ((b < 0.f) != (m < 0.f))) m += b;
+  return m;
+}
+template <class T>
+PXR_HD T cj_clamp01(const T& x) {
+  const float v = cj_val(x);
+  if (v < 0.f) return cj_const(x, 0.f);
+  if (v > 1.f) return cj_const(x, 1.f);
+  return x;
+}
+
+constexpr float CJ_TWO_PI = 6.283185307179586f;
+
+template <class T>
+PXR_HD void cj_rgb_to_hsv(const T c[3], T& h, T& s, T& v) {
+  int imax = 0, imin = 0;  // first arg-max / arg-min on ties
+  {
+    const float v0 = cj_val(c[0]), v1 = cj_val(c[1]), v2 = cj_val(c[2]);
+    float hi = v0, lo = v0;
+    if (v1 > hi) { hi = v1; imax = 1; }
+    if (v2 > hi) { imax = 2; }
+    if (v1 < lo) { lo = v1; imin = 1; }
+    if (v2 < lo) { imin = 2; }
+  }
+  const T mx = imax == 0 ? c[0] : (imax == 1 ? c[1] : c[2]);
+  const T mn = imin == 0 ? c[0] : (imin == 1 ? c[1] : c[2]);
+  const T delta = mx - mn;
+  v = mx;
+  s = delta / (mx + 1e-8f);
+  const T dc = (cj_val(delta) == 0.f) ? cj_const(delta, 1.f) : delta;
+  const T rc = mx - c[0], gc = mx - c[1], bc = mx - c[2];
+  T hh;
+  if (imax == 0) hh = bc - gc;
+  else if (imax == 1) hh = (rc - bc) + dc * 2.0f;
+  else hh = (gc - rc) + dc * 4.0f;
+  hh = hh / dc;
+  hh = hh / 6.0f;
+  hh = cj_with_value(hh, cj_pymod(cj_val(hh), 1.0f));
+  h = hh * CJ_TWO_PI;
+}
+
+template <class T>
+PXR_HD void cj_hsv_to_rgb(const T& h_rad, const T& s, const T& v, T c[3]) {
+  const T h6 = (h_rad / CJ_TWO_PI) * 6.0f;
+  const float hi_f = cj_pymod(floorf(cj_val(h6)), 6.0f);
+  const T f = cj_with_value(h6, cj_pymod(cj_val(h6), 6.0f) - hi_f);
+  const T p = v * (1.0f - s);
+  const T q = v * (1.0f - f * s);
+  const T t = v * (1.0f - (1.0f - f) * s);
+  const int hi = (int)hi_f;
+  switch (hi) {
+    case 0: c[0] = v; c[1] = t; c[2] = p; break;
+    case 1: c[0] = q; c[1] = v; c[2] = p; break;
+    case 2: c[0] = p; c[1] = v; c[2] = t; break;
+    case 3: c[0] = p; c[1] = q; c[2] = v; break;
+    case 4: c[0] = t; c[1] = p; c[2] = v; break;
+    default: c[0] = v; c[1] = p; c[2] = q; break;
+  }
+}
+
+// code: 0 = this cutout is not jittered (Bernoulli(p) miss); else 256 + o0 + 4*o1 + 16*o2 + 64*o3, o_k = the
+// transform applied k-th.  sat = saturation_factor, hue = hue_factor (kornia's unit: fraction of a turn).
+template <class T>
+PXR_HD void cj_apply(T c[3], int code, float sat, float hue) {
+  if (code == 0) return;
+  const float hue_rad = hue * 2.f * 3.14159274101257324f;
+PXR_NOUNROLL
+  for (int k = 0; k < 4; ++k) {
+    const int op = (code >> (2 * k)) & 3;
+    if (op < 2) {
+PXR_UNROLL
+      for (int i = 0; i < 3; ++i) c[i] = cj_clamp01(c[i]);
+    } else {
+      T h, s, v;
+      cj_rgb_to_hsv(c, h, s, v);
+      if (op == 2) {
+        s = cj_clamp01(s * sat);
+      } else {
+        const T hs = h + hue_rad;
+        h = cj_with_value(hs, fmodf(cj_val(hs), CJ_TWO_PI));
+      }
+      cj_hsv_to_rgb(h, s, v, c);
+    }
+  }
+}
+
+// g_in = J^T g_out at the pre-jitter colour `rgb`
+PXR_HD void cj_vjp(const float rgb[3], int code, float sat, float hue, const float g_out[3], float g_in[3]) {
+  if (code == 0) {
+    g_in[0] = g_out[0];
+    g_in[1] = g_out[1];
+    g_in[2] = g_out[2];
+    return;
+  }
+  Dual3 c[3];
+PXR_UNROLL
+  for (int i = 0; i < 3; ++i) c[i] = Dual3{rgb[i], {i == 0 ? 1.f : 0.f, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f}};
+  cj_apply(c, code, sat, hue);
+PXR_UNROLL
+  for (int i = 0; i < 3; ++i) g_in[i] = c[0].d[i] * g_out[0] + c[1].d[i] * g_out[1] + c[2].d[i] * g_out[2];
+}
+
+}  // namespace pxr

@@ -66,6 +66,7 @@ class Engine {
   cudaEvent_t ring_ev[RING] = {nullptr};
   int ring_pos = 0;
   float *minv_dev = nullptr, *facs_dev = nullptr;
+  float cj_p = 0.8f, cj_sat = 0.1f, cj_hue = 0.1f;  // K.ColorJitter(hue=0.1, saturation=0.1, p=0.8), pixray.py:416, 436
   CutoutArgs cut_args;
 
   // ---- perceptors
@@ -965,10 +966,10 @@ void Engine::build_cutouts() {
   irange = dalloc<int>(4);
   sums = dalloc<float>(4);
   xbuf = dalloc<float>(4);
-  minv_dev = dalloc<float>((size_t)n_local * 9);
+  minv_dev = dalloc<float>((size_t)n_local * 12);  // 9 homography + 3 ColorJitter floats per cutout, one H2D copy
   facs_dev = dalloc<float>(n_local);
   for (int i = 0; i < RING; ++i) {
-    PXR_CUDA(cudaMallocHost((void**)&minv_host[i], sizeof(float) * n_local * 9));
+    PXR_CUDA(cudaMallocHost((void**)&minv_host[i], sizeof(float) * n_local * 12));
     PXR_CUDA(cudaMallocHost((void**)&facs_host[i], sizeof(float) * n_local));
     PXR_CUDA(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming));
   }
@@ -1006,7 +1007,19 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
     if (!invert3x3(m, inv)) throw EngineError(-60, "singular cutout transform");
     for (int i = 0; i < 9; ++i) minv_host[slot][n * 9 + i] = (float)inv[i];
   }
-  PXR_CUDA(cudaMemcpyAsync(minv_dev, minv_host[slot], sizeof(float) * n_local * 9, cudaMemcpyHostToDevice, st));
+  // ColorJitter rows: explicit, or drawn like the transforms when those are the engine's own
+  const float* J = p ? p->color_jitter : nullptr;
+  std::vector<float> genj;
+  if (!J && !(p && p->transforms) && cj_p > 0.f) {
+    genj.resize((size_t)cfg.cutn * 3);
+    sample_color_jitter(cfg.seed, iter, cfg.cutn, cj_p, cj_sat, cj_hue, genj.data());
+    J = genj.data();
+  }
+  float* jh = minv_host[slot] + (size_t)n_local * 9;
+  if (J)
+    for (int i = 0; i < n_local * 3; ++i) jh[i] = J[(size_t)first_global * 3 + i];
+  cut_args.jitter = J ? minv_dev + (size_t)n_local * 9 : nullptr;
+  PXR_CUDA(cudaMemcpyAsync(minv_dev, minv_host[slot], sizeof(float) * n_local * (J ? 12 : 9), cudaMemcpyHostToDevice, st));
   cut_args.zoom_padding = zoom_padding;
   cut_args.fill = fill;
   cut_args.iter = iter;
@@ -1642,6 +1655,16 @@ int pxr_synth(pxr_handle h, const float* z, float* out_img) {
     if (out_img)
       PXR_CUDA(cudaMemcpyAsync(out_img, e->img, sizeof(float) * 3 * e->cfg.image_h * e->cfg.image_w,
                                cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
+int pxr_set_color_jitter(pxr_handle h, float p, float saturation, float hue) {
+  PXR_TRY(h, {
+    if (!(p >= 0.f && p <= 1.f) || saturation < 0.f || saturation > 1.f || hue < 0.f || hue > 0.5f)
+      throw EngineError(-62, "pxr_set_color_jitter: p in [0,1], saturation in [0,1], hue in [0,0.5]");
+    h->e->cj_p = p;
+    h->e->cj_sat = saturation;
+    h->e->cj_hue = hue;
   });
 }
 

@@ -88,6 +88,7 @@ struct CutoutArgs {
   const float* minv;       // [n_local, 9] src_pix <- dst_pix homographies (device)
   const float* noise_facs; // [n_local]            (noise_mode 1)
   const float* noise;      // [n_local, 3, cs, cs] (noise_mode 1)
+  const float* jitter;     // [n_local, 3] {code, saturation_factor, hue_factor} (color_jitter.cuh) or nullptr
   int noise_mode;          // 0 none, 1 explicit facs + noise, 2 engine Philox (seed, iter)
   float noise_fac;         // U(0, noise_fac) upper bound for mode 2 (pixray.py:439)
   int cs, n_local, first_global, cutn_zoom, zoom_padding;

@@ -6,6 +6,7 @@
 //                     im2col of the ViT patch embedding, and its adjoint
 //   cutout_backward : adjoint of the resample (scatter-add through the bilinear taps) incl. the d/dmin, d/dmax terms
 #include "kernels.cuh"
+#include "color_jitter.cuh"
 #include "philox.cuh"
 #include <cfloat>
 
@@ -119,6 +120,25 @@ __device__ __forceinline__ void src_coord(const float* m, int u, int v, float& x
   ys = Y * s;
 }
 
+// one warped pixel, all three channels: bilinear taps (+ the wide group's fill under the uncovered weight)
+__device__ __forceinline__ void warp_sample(const float* __restrict__ pooled, const Taps& t, int cs, bool zoom,
+                                            float fill, float rgb[3]) {
+  float cover = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cover += t.in[k] ? t.w[k] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* p = pooled + (size_t)c * cs * cs;
+    float val = 0.f;
+    if (t.in[0]) val += t.w[0] * p[t.y0 * cs + t.x0];
+    if (t.in[1]) val += t.w[1] * p[t.y0 * cs + t.x0 + 1];
+    if (t.in[2]) val += t.w[2] * p[(t.y0 + 1) * cs + t.x0];
+    if (t.in[3]) val += t.w[3] * p[(t.y0 + 1) * cs + t.x0 + 1];
+    if (!zoom) val += (1.f - cover) * fill;  // kornia _fill_and_warp
+    rgb[c] = val;
+  }
+}
+
 constexpr int CUT_THREADS = 256;
 
 // grid (ceil(cs*cs/4 / 256), n_local); each thread: 4 consecutive u of one row v, all 3 channels
@@ -164,6 +184,13 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_fwd_kernel(CutoutArgs a, f
         philox_normal4(a.seed, (uint32_t)a.iter, 0u, e >> 2, nz[c]);
       }
     }
+    int cj_code = 0;
+    float cj_sat = 1.f, cj_hue = 0.f;
+    if (a.jitter) {  // K.ColorJitter, last stage of the stack (pixray.py:416, 436)
+      cj_code = (int)a.jitter[n * 3];
+      cj_sat = a.jitter[n * 3 + 1];
+      cj_hue = a.jitter[n * 3 + 2];
+    }
     float out[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -172,21 +199,11 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_fwd_kernel(CutoutArgs a, f
       xs = pad_coord(xs, cs, padding);
       ys = pad_coord(ys, cs, padding);
       Taps t = make_taps(xs, ys, cs);
-      float cover = 0.f;
+      float rgb[3];
+      warp_sample(a.pooled, t, cs, zoom, a.fill, rgb);
+      cj_apply(rgb, cj_code, cj_sat, cj_hue);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) cover += t.in[k] ? t.w[k] : 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* p = a.pooled + (size_t)c * cs * cs;
-        float val = 0.f;
-        if (t.in[0]) val += t.w[0] * p[t.y0 * cs + t.x0];
-        if (t.in[1]) val += t.w[1] * p[t.y0 * cs + t.x0 + 1];
-        if (t.in[2]) val += t.w[2] * p[(t.y0 + 1) * cs + t.x0];
-        if (t.in[3]) val += t.w[3] * p[(t.y0 + 1) * cs + t.x0 + 1];
-        if (!zoom) val += (1.f - cover) * a.fill;  // kornia _fill_and_warp
-        if (have_noise) val += fac * nz[c][j];     // pixray.py:508-510
-        out[c][j] = val;
-      }
+      for (int c = 0; c < 3; ++c) out[c][j] = have_noise ? rgb[c] + fac * nz[c][j] : rgb[c];  // pixray.py:508-510
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -540,6 +557,13 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
   float m[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) m[i] = a.minv[n * 9 + i];
+  int cj_code = 0;
+  float cj_sat = 1.f, cj_hue = 0.f;
+  if (a.jitter) {
+    cj_code = (int)a.jitter[n * 3];
+    cj_sat = a.jitter[n * 3 + 1];
+    cj_hue = a.jitter[n * 3 + 2];
+  }
   // global range normalise: dL/dR = -sum g_a * a / R ; argmax gets +dR, argmin gets -(sum g_a + dR)
   const float dR = (range[3] != 0.f) ? -sums[1] : 0.f;
   const float dMin = -(sums[0] + dR);
@@ -566,10 +590,17 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
     xs = pad_coord(xs, cs, padding);
     ys = pad_coord(ys, cs, padding);
     Taps t = make_taps(xs, ys, cs);
+    float gpre[3] = {g[0][j], g[1][j], g[2][j]};
+    if (cj_code) {  // through the ColorJitter Jacobian at the recomputed pre-jitter colour
+      float rgb[3];
+      warp_sample(a.pooled, t, cs, zoom, a.fill, rgb);
+      const float gout[3] = {gpre[0], gpre[1], gpre[2]};
+      cj_vjp(rgb, cj_code, cj_sat, cj_hue, gout, gpre);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float* p = g_pooled + (size_t)c * cs * cs;
-      float gv = g[c][j];
+      float gv = gpre[c];
       if (t.in[0]) atomicAdd(p + t.y0 * cs + t.x0, t.w[0] * gv);
       if (t.in[1]) atomicAdd(p + t.y0 * cs + t.x0 + 1, t.w[1] * gv);
       if (t.in[2]) atomicAdd(p + (t.y0 + 1) * cs + t.x0, t.w[2] * gv);

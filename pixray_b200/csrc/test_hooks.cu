@@ -3,6 +3,7 @@
 #include "../../include/pixray_b200.h"
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "color_jitter.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -106,6 +107,21 @@ extern "C" int pxr_test_attention(const void* qkv, void* o, float* lse, const vo
   if (ce != cudaSuccess) {
     if (err) snprintf(err, errlen, "launch failed: %s", cudaGetErrorString(ce));
     return -100;
+  }
+  return 0;
+}
+
+// Host evaluation of the per-pixel ColorJitter body the cutout kernels run (color_jitter.cuh is host+device code):
+// lets the CPU suite compare the arithmetic and its Jacobian with the oracle without a GPU.  rgb / g_out / out / g_in
+// are HOST [n, 3]; g_out and g_in may be NULL.
+extern "C" int pxr_test_color_jitter_host(const float* rgb, int n, int code, float saturation, float hue,
+                                          const float* g_out, float* out, float* g_in) {
+  if (!rgb || !out || n < 0) return -1;
+  for (int i = 0; i < n; ++i) {
+    float c[3] = {rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+    pxr::cj_apply(c, code, saturation, hue);
+    for (int k = 0; k < 3; ++k) out[3 * i + k] = c[k];
+    if (g_out && g_in) pxr::cj_vjp(rgb + 3 * i, code, saturation, hue, g_out + 3 * i, g_in + 3 * i);
   }
   return 0;
 }

@@ -136,6 +136,31 @@ inline void sample_cutout_transforms(uint64_t seed, int iter, int cutn, int cut_
   }
 }
 
+// K.ColorJitter(hue, saturation, p) parameters (pixray.py:416, 436; kornia random_color_jitter_generator):
+// per cutout Bernoulli(p), saturation_factor ~ U(1 - s, 1 + s), hue_factor ~ U(-h, h); one randperm(4) application
+// order per group (each stack is its own module, called once per iteration).  out: [cutn, 3] rows
+// {code, saturation_factor, hue_factor} in the encoding of color_jitter.cuh.
+inline void sample_color_jitter(uint64_t seed, int iter, int cutn, float p, float sat, float hue, float* out) {
+  const int cutn_zoom = (int)(0.6 * cutn);
+  int code[2];
+  for (int g = 0; g < 2; ++g) {
+    int order[4] = {0, 1, 2, 3};
+    for (int k = 3; k > 0; --k) {  // Fisher-Yates
+      int j = (int)(philox_uniform(seed, (uint32_t)iter, 5u, (uint64_t)g * 4 + k) * 0.999999f * (k + 1));
+      std::swap(order[k], order[j]);
+    }
+    code[g] = 256 + order[0] + 4 * order[1] + 16 * order[2] + 64 * order[3];
+  }
+  for (int n = 0; n < cutn; ++n) {
+    const uint64_t base = (uint64_t)n * 4;
+    const bool apply = philox_uniform(seed, (uint32_t)iter, 4u, base) <= p;
+    const float u1 = philox_uniform(seed, (uint32_t)iter, 4u, base + 1), u2 = philox_uniform(seed, (uint32_t)iter, 4u, base + 2);
+    out[n * 3] = apply ? (float)code[n < cutn_zoom ? 0 : 1] : 0.f;
+    out[n * 3 + 1] = 1.f - sat + 2.f * sat * u1;
+    out[n * 3 + 2] = -hue + 2.f * hue * u2;
+  }
+}
+
 // global_fill_color = random.random(), once per iteration (pixray.py:1255-1258)
 inline float sample_fill(uint64_t seed, int iter) { return philox_uniform(seed, (uint32_t)iter, 3u, 0); }
 

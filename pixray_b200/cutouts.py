@@ -63,3 +63,22 @@ def sample_transforms(cutn, cut_size, seed):
             H = _sample_perspective(g, cut_size, 0.20, 0.7) @ _sample_affine(g, cut_size, n_s, (1 - n_s) / 2)
         out[n] = H
     return out
+
+
+def jitter_code(order):
+    """Application order (a permutation of 0 brightness, 1 contrast, 2 saturation, 3 hue) -> the engine's code."""
+    return 256 + order[0] + 4 * order[1] + 16 * order[2] + 64 * order[3]
+
+
+def sample_color_jitter(cutn, seed, p=0.8, saturation=0.1, hue=0.1):
+    """[cutn, 3] float32 rows {code, saturation_factor, hue_factor} of K.ColorJitter(hue=0.1, saturation=0.1, p=0.8),
+    the last stage of both augmentation stacks (pixray.py:416, 436): Bernoulli(p) per cutout (code 0 = missed),
+    saturation_factor ~ U(1-s, 1+s), hue_factor ~ U(-h, h), one randperm(4) order per stack and call."""
+    g = np.random.default_rng(seed)
+    zoom = int(0.6 * cutn)
+    codes = [jitter_code(list(g.permutation(4))) for _ in range(2)]
+    out = np.zeros((cutn, 3), dtype=np.float32)
+    for n in range(cutn):
+        apply = g.uniform() <= p
+        out[n] = [codes[0 if n < zoom else 1] if apply else 0, g.uniform(1 - saturation, 1 + saturation), g.uniform(-hue, hue)]
+    return out

@@ -222,9 +222,18 @@ class B200Engine:
         self.sync()
         return lo, hi
 
-    def _cut_params(self, transforms, zoom_padding, fill, noise_facs, noise):
+    def set_color_jitter(self, p=0.8, saturation=0.1, hue=0.1):
+        """Distribution of the engine-drawn K.ColorJitter stage (pixray.py:416, 436); p=0 turns it off."""
+        self._check(self.lib.pxr_set_color_jitter(self.h, C.c_float(p), C.c_float(saturation), C.c_float(hue)),
+                    "pxr_set_color_jitter")
+
+    def _cut_params(self, transforms, zoom_padding, fill, noise_facs, noise, color_jitter=None):
         p = _lib.CutParams()
         keep = []
+        if color_jitter is not None:
+            cj = np.ascontiguousarray(np.asarray(color_jitter, dtype=np.float32).reshape(self.cutn, 3))
+            keep.append(cj)
+            p.color_jitter = cj.ctypes.data_as(C.c_void_p)
         if transforms is not None:
             t = np.ascontiguousarray(np.asarray(transforms, dtype=np.float32).reshape(self.cutn, 9))
             keep.append(t)
@@ -251,11 +260,12 @@ class B200Engine:
         return out
 
     def make_cutouts(self, img=None, *, transforms=None, zoom_padding=PAD_REFLECTION, fill=0.0, noise_facs=None,
-                     noise=None, it=0, use_engine_rng=False):
+                     noise=None, it=0, use_engine_rng=False, color_jitter=None):
         if img is not None:
             img = img.to(self.device, torch.float32).contiguous()
         out = self._new(self.n_local, 3, self.cut_size, self.cut_size)
-        p = None if use_engine_rng else self._cut_params(transforms, zoom_padding, fill, noise_facs, noise)
+        p = None if use_engine_rng else self._cut_params(transforms, zoom_padding, fill, noise_facs, noise,
+                                                                color_jitter)
         torch.cuda.current_stream().synchronize()
         rc = self.lib.pxr_make_cutouts(self.h, self._p(img), None if p is None else C.byref(p), it, self._p(out))
         self._check(rc, "pxr_make_cutouts")
@@ -298,12 +308,13 @@ class B200Engine:
     # ------------------------------------------------------------------ the fast path (what bench.py times)
     def iterate(self, z, lr, it, *, params=None, losses_out=None):
         """One train() iteration entirely inside the library.  params: dict(transforms, zoom_padding, fill,
-        noise_facs, noise) or None for the engine's own Philox draws.  losses_out: float32 numpy array (host) to
+        noise_facs, noise, color_jitter) or None for the engine's own Philox draws.  losses_out: float32 numpy array (host) to
         receive the per-prompt losses (forces a stream sync), or None."""
         p = None
         if params is not None:
             p = self._cut_params(params.get("transforms"), params.get("zoom_padding", it % 2),
-                                 params.get("fill", 0.0), params.get("noise_facs"), params.get("noise"))
+                                 params.get("fill", 0.0), params.get("noise_facs"), params.get("noise"),
+                                 params.get("color_jitter"))
         # z / noise may have been produced on torch's stream (e.g. an H2D copy still in flight): order the engine's
         # non-blocking stream after it without a host sync
         if self._ext is None:

@@ -226,6 +226,7 @@ class MakeCutouts:
         self.cutn_zoom = int(0.6 * cutn)
         self.noise_fac = 0.1
         self.transforms = None
+        self.color_jitter = None
         self.session = session
         self._rng = np.random.default_rng(seed)
 
@@ -239,13 +240,20 @@ class MakeCutouts:
         if self.transforms is None:
             self.transforms = torch.from_numpy(
                 cut_sampler.sample_transforms(self.cutn, self.cut_size, int(self._rng.integers(1 << 31))))
+            # the live stacks end in K.ColorJitter (pixray.py:416, 436); replays of the cached transforms within the
+            # same iteration (pixray.py:480-486) do not repeat it
+            jitter = cut_sampler.sample_color_jitter(self.cutn, int(self._rng.integers(1 << 31)))
+        else:
+            jitter = None
+        self.color_jitter = jitter
         pad = E.PAD_REFLECTION if s.global_padding_mode == "reflection" else E.PAD_BORDER
         facs = noise = None
         if self.noise_fac:
             facs = (self._rng.random(self.cutn) * self.noise_fac).astype(np.float32)        # pixray.py:509
             noise = torch.randn(self.cutn, 3, self.cut_size, self.cut_size, device=s.engine.device)  # pixray.py:510
         return s.engine.make_cutouts(input, transforms=self.transforms.numpy(), zoom_padding=pad,
-                                     fill=s.global_fill_color, noise_facs=facs, noise=noise, it=s.cur_iteration)
+                                     fill=s.global_fill_color, noise_facs=facs, noise=noise, it=s.cur_iteration,
+                                     color_jitter=jitter)
 
 
 class Perceptor:

@@ -32,7 +32,7 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(_lib.ClipCfg) == 24
     assert C.sizeof(_lib.Config) % 8 == 0
     assert _lib.Config.seed.offset % 8 == 0
-    assert C.sizeof(_lib.CutParams) == 8 + 4 + 4 + 8 + 8
+    assert C.sizeof(_lib.CutParams) == 8 + 4 + 4 + 8 + 8 + 8  # + color_jitter
 
 
 def test_version_string():

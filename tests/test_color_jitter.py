@@ -1,0 +1,154 @@
+"""K.ColorJitter stage of MakeCutouts (pixray.py:416, 436).
+
+CPU part: the per-pixel body the cutout kernels run (csrc/color_jitter.cuh, host+device code, evaluated on the host through
+the pxr_test_color_jitter_host hook) against the oracle's restatement of kornia 0.6.2 -- forward and the
+vector-Jacobian product -- plus the host samplers.  GPU part: the kernels themselves, through pxr_make_cutouts /
+pxr_iterate, against oracle.make_cutouts / oracle.iterate."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_path as R
+from pixray_b200 import _lib, cutouts
+
+E_PAD_BORDER = 1
+
+
+def _host_jitter(rgb, code, sat, hue, g_out=None):
+    lib = _lib.load()
+    rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+    out = np.zeros_like(rgb)
+    g_in = np.zeros_like(rgb)
+    g = None if g_out is None else np.ascontiguousarray(g_out, dtype=np.float32)
+    f = lib.pxr_test_color_jitter_host
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = f(rgb.ctypes.data, rgb.shape[0], int(code), float(sat), float(hue), None if g is None else g.ctypes.data,
+           out.ctypes.data, g_in.ctypes.data)
+    assert rc == 0
+    return out, g_in
+
+
+def _oracle_jitter(rgb, code, sat, hue, g_out=None):
+    x = torch.from_numpy(rgb).t().reshape(1, 3, 1, -1).clone().requires_grad_(True)  # [1,3,1,n]
+    j = torch.tensor([[float(code), sat, hue]], dtype=torch.float32)
+    y = R.color_jitter(x, j)
+    g_in = None
+    if g_out is not None:
+        y.backward(torch.from_numpy(g_out).t().reshape(1, 3, 1, -1))
+        g_in = x.grad.reshape(3, -1).t().numpy()
+    return y.detach().reshape(3, -1).t().numpy(), g_in
+
+
+def _colours(n, seed):
+    g = np.random.default_rng(seed)
+    rgb = g.uniform(0, 1, (n, 3)).astype(np.float32)
+    rgb[:8] = [[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0.25, 0.25, 0.75], [0.9, 0.2, 0.9]]
+    return rgb
+
+
+def test_pixel_body_matches_the_oracle_for_every_order():
+    rgb = _colours(4096, 0)
+    g = np.random.default_rng(1).standard_normal(rgb.shape).astype(np.float32)
+    worst_f = worst_g = 0.0
+    for k, order in enumerate(itertools.permutations(range(4))):
+        code = cutouts.jitter_code(list(order))
+        assert code == R.jitter_code(list(order))
+        sat = 0.9 + 0.2 * ((k * 7) % 24) / 23.0
+        hue = -0.1 + 0.2 * ((k * 5) % 24) / 23.0
+        out, g_in = _host_jitter(rgb, code, sat, hue, g)
+        ref, ref_g = _oracle_jitter(rgb, code, sat, hue, g)
+        worst_f = max(worst_f, float(np.abs(out - ref).max()))
+        # the Jacobian is piecewise: compare where neither side sits on a sector / clamp boundary (rounding may pick the
+        # other piece there); those are a vanishing fraction of random colours
+        err = np.abs(g_in - ref_g).max(axis=1)
+        tol = 2e-3 * (1.0 + np.abs(ref_g).max(axis=1))
+        assert (err > tol).mean() < 2e-3, (order, float((err > tol).mean()))
+        worst_g = max(worst_g, float(np.median(err)))
+    assert worst_f <= 2e-6, worst_f
+    assert worst_g <= 1e-5, worst_g
+
+
+def test_not_selected_cutouts_pass_through():
+    rgb = _colours(256, 2)
+    g = np.ones_like(rgb)
+    out, g_in = _host_jitter(rgb, 0, 1.1, 0.1, g)
+    assert np.array_equal(out, rgb) and np.array_equal(g_in, g)
+    # identity parameters reproduce the colour up to the hsv round trip
+    out, _ = _host_jitter(rgb, cutouts.jitter_code([0, 1, 2, 3]), 1.0, 0.0)
+    assert np.abs(out - rgb).max() <= 1e-6
+
+
+def test_host_sampler_distribution():
+    js = np.concatenate([cutouts.sample_color_jitter(64, s) for s in range(200)])
+    applied = js[:, 0] != 0
+    assert abs(applied.mean() - 0.8) < 0.02                              # Bernoulli(0.8)
+    assert js[:, 1].min() >= 0.9 and js[:, 1].max() <= 1.1 and abs(js[:, 1].mean() - 1.0) < 5e-3
+    assert js[:, 2].min() >= -0.1 and js[:, 2].max() <= 0.1 and abs(js[:, 2].mean()) < 5e-3
+    one = cutouts.sample_color_jitter(64, 7)
+    zoom = int(0.6 * 64)
+    for grp in (one[:zoom], one[zoom:]):                                  # one order per stack
+        codes = set(grp[grp[:, 0] != 0, 0].astype(int).tolist())
+        assert len(codes) == 1
+        c = codes.pop() - 256
+        assert sorted((c >> (2 * k)) & 3 for k in range(4)) == [0, 1, 2, 3]
+
+
+# ------------------------------------------------------------------------------------------------ GPU: the kernels
+@pytest.mark.gpu
+def test_cutout_kernels_apply_color_jitter_like_the_oracle():
+    import test_pipeline_gpu as P
+    cutn, cs = 8, 224
+    vq, clip, eng, prompts, z = P.build(cutn=cutn)
+    torch.manual_seed(5)
+    img = torch.rand(1, 3, 32, 32)
+    T = torch.from_numpy(P.random_transforms(cutn, cs, 11))
+    J = cutouts.sample_color_jitter(cutn, 12, p=1.0)
+    J[0, 0] = 0                                   # one cutout the Bernoulli missed
+    J[1, 0] = cutouts.jitter_code([3, 0, 2, 1])   # and a different order in the same batch
+    facs = torch.rand(cutn) * 0.1
+    noise = torch.randn(cutn, 3, cs, cs)
+    for pad_name, pad in (("reflection", 0), ("border", 1)):
+        got = eng.make_cutouts(img, transforms=T.numpy(), zoom_padding=pad, fill=0.4, noise_facs=facs.numpy(),
+                               noise=noise, color_jitter=J).cpu()
+        want = R.make_cutouts(img, T, cs, pad_name, 0.4, facs, noise, jitter=torch.from_numpy(J))
+        plain = R.make_cutouts(img, T, cs, pad_name, 0.4, facs, noise)
+        assert (want - plain).abs().max() > 1e-2                           # the stage does something
+        err = (got - want).abs()
+        frac = float((err > 1e-4).float().mean())
+        print(f"[parity] jittered cutouts ({pad_name}): max_abs_err={float(err.max()):.3e}  frac>1e-4={frac:.2e}")
+        # hue sectors are decided on fp32 values that differ in the last bits between the two bilinear samplers; the
+        # map is continuous across sectors, so the error stays small
+        assert err.max() <= 1e-3 and frac < 1e-4
+        assert (got[0] - plain[0]).abs().max() <= 1e-4                     # code 0 passes through
+
+
+@pytest.mark.gpu
+def test_iteration_gradient_with_color_jitter():
+    """z.grad of a whole iteration with every cutout jittered: the backward goes through the stage's Jacobian."""
+    import test_pipeline_gpu as P
+    cutn, cs = 8, 224
+    vq, clip, eng, prompts, z = P.build(cutn=cutn, seed=3)
+    T = P.random_transforms(cutn, cs, 13)
+    J = cutouts.sample_color_jitter(cutn, 22, p=1.0)
+    g = torch.Generator().manual_seed(19)
+    facs, noise = P.plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
+    ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), cs, "border", 0.3,
+                    facs, noise, jitter=torch.from_numpy(J))
+    ref_plain = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), cs, "border",
+                          0.3, facs, noise)
+    # the stage must matter for the gradient, or the comparison proves nothing
+    assert (ref["z_grad"] - ref_plain["z_grad"]).abs().max() > 0.05 * ref["z_grad"].abs().max()
+    eng.synth(z)
+    batch = eng.make_cutouts(None, transforms=T, zoom_padding=E_PAD_BORDER, fill=0.3, noise_facs=facs.numpy(),
+                             noise=noise, color_jitter=J)
+    e_b, _ = P.report("jittered batch (engine image in)", batch, ref["batch"])
+    eng.encode_image(0)
+    losses = eng.prompt_loss(0)
+    e_l, _ = P.report("prompt losses", losses, torch.stack([l.reshape(()) for l in ref["losses"]]))
+    zg = eng.backward()
+    e_g, m_g = P.report("z.grad with ColorJitter", zg, ref["z_grad"])
+    assert e_l < 2e-3
+    assert e_g <= 3e-2 * m_g
