@@ -102,6 +102,15 @@ int pxr_finalize(pxr_handle h);
 int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int D, const float* weights,
                     const float* stops);
 
+/* Image prompts (pixray.py:1308-1336, pmsImageTable): imgs host or device fp32 [n, 3, H, W] in [0, 1] at the output
+ * size (copied).  Every iteration -- inside pxr_iterate / pxr_make_cutouts, before the main pass -- each image is cut
+ * with that iteration's cached transforms (no ColorJitter on the cached path, pixray.py:480-486; fresh noise, or the
+ * explicit noise of pxr_cut_params replayed), encoded by every perceptor, and scored as a throwaway
+ * Prompt(embed [cutn, D], weights[k]) (weights NULL = 1, args.image_prompt_weight otherwise) whose loss follows that
+ * perceptor's text prompts in the loss vector.  Cutout-sharded ranks exchange the [cutn, D] rows (one allreduce).
+ * n = 0 clears. */
+int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* weights);
+
 /* Multi-GPU: 128-byte ncclUniqueId from rank 0; the engine owns the communicator. */
 int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world);
 int pxr_get_unique_id(void* out128);

