@@ -98,8 +98,10 @@ def cpu_reference_iteration(vq, clip, prompts, z, adam, T, cutn_sample, it):
     facs = torch.rand(cutn_sample, generator=g) * 0.1
     noise = torch.randn(cutn_sample, 3, CUT_SIZE, CUT_SIZE, generator=g)
     out_d = out.detach().requires_grad_(True)
+    from pixray_b200.cutouts import sample_color_jitter
+    jit = torch.from_numpy(sample_color_jitter(CUTN, 2000 + it)[:cutn_sample])  # K.ColorJitter rows (pixray.py:416, 436)
     batch = R.make_cutouts(out_d, T[:cutn_sample], CUT_SIZE, "reflection" if it % 2 == 0 else "border", 0.5, facs,
-                           noise, cutn_zoom=int(0.6 * cutn_sample))
+                           noise, cutn_zoom=int(0.6 * cutn_sample), jitter=jit)
     emb = R.encode_image(clip, batch).float()
     loss = sum(R.prompt_loss(emb, *p) for p in prompts)
     loss.backward()
@@ -302,12 +304,30 @@ def run_engine(args, rank, world):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu_reference(steps=1, warmup=0, budget_s=25.0)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE stdout line of the contract.  Library banners written to fd 1 while the job runs (NCCL prints its version
+    there) are diverted to stderr by main(); the JSON goes to the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -333,7 +353,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
     run_engine(args, rank, world)
 

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir, with_aux=False):
+def _worker(rank, world, port, out_dir, with_aux=0):
     import torch.distributed as dist
     from test_pipeline_gpu import SMALL_CLIP, SMALL_VQ, plant_extremes, random_transforms
     from oracle import ref_path as R
@@ -45,7 +45,7 @@ def _worker(rank, world, port, out_dir, with_aux=False):
     T = random_transforms(cutn, cs, 3)
     facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
     aux = []
-    if with_aux:
+    if with_aux == 1:
         # auxiliary losses under sharding: saturation needs the GLOBAL colour moments, smoothness the neighbouring ranks'
         # boundary rows (the reference differentiates across the stacked cutouts), the image losses are replicated
         pal = [[0.9, 0.1, 0.1], [0.1, 0.8, 0.2], [0.2, 0.2, 0.9]]
@@ -58,15 +58,26 @@ def _worker(rank, world, port, out_dir, with_aux=False):
         aux = [(0.5, lambda o, b, e: R.saturation_loss(b, 1.3)), (2.0, lambda o, b, e: R.smoothness_loss(b, 0.9)),
                (1.0, lambda o, b, e: R.palette_loss(b, pal, 0.8)[0]), (1.5, lambda o, b, e: R.symmetry_loss(o, 0.7)),
                (0.8, lambda o, b, e: R.aesthetic_loss(e, hw_, torch.tensor([0.7]), 10.0))]
+    jitter, targets = None, []
+    if with_aux == 2:
+        # image prompts (every rank needs all cutn rows of the target embeddings: one more allreduce) and the ColorJitter
+        # rows (per global cutout index) under sharding
+        from pixray_b200 import cutouts
+        aux = []
+        jitter = cutouts.sample_color_jitter(cutn, 31, p=1.0)
+        tg = torch.Generator().manual_seed(33)
+        targets = [(torch.rand(1, 3, 32, 32, generator=tg), 0.7), (torch.rand(1, 3, 32, 32, generator=tg) * 0.6, -0.5)]
+        eng.set_image_prompts(torch.cat([t for t, _ in targets]), [w for _, w in targets])
     zc = z.clone().cuda()
-    losses = np.zeros(2 + len(aux), dtype=np.float32)
-    eng.iterate(zc, 0.05, 0, params=dict(transforms=T, zoom_padding=0, fill=0.4, noise_facs=facs.numpy(), noise=noise),
-                losses_out=losses)
+    losses = np.zeros(2 + len(aux) + len(targets), dtype=np.float32)
+    eng.iterate(zc, 0.05, 0, params=dict(transforms=T, zoom_padding=0, fill=0.4, noise_facs=facs.numpy(), noise=noise,
+                                         color_jitter=jitter), losses_out=losses)
     zg = eng.debug_read("z_grad", z.shape).cpu()
     torch.save(dict(zg=zg, losses=losses.copy(), z=zc.cpu()), os.path.join(out_dir, f"rank{rank}.pt"))
     if rank == 0:
         ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), cs, "reflection", 0.4,
-                        facs, noise, aux=aux)
+                        facs, noise, aux=aux, jitter=None if jitter is None else torch.from_numpy(jitter),
+                        image_prompts=targets)
         torch.save(dict(zg=ref["z_grad"], losses=torch.stack([l.reshape(()) for l in ref["losses"]])),
                    os.path.join(out_dir, "ref.pt"))
     dist.barrier()
@@ -91,7 +102,7 @@ def test_cutout_sharded_two_ranks(tmp_path):
 def test_cutout_sharded_two_ranks_with_aux_losses(tmp_path):
     """Same, with auxiliary losses: their values and gradients must not depend on how the cutouts are sharded."""
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), True), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), 1), nprocs=2, join=True)
     r0, r1, ref = (torch.load(tmp_path / n, weights_only=False) for n in ("rank0.pt", "rank1.pt", "ref.pt"))
     assert torch.equal(r0["zg"], r1["zg"]) and torch.equal(r0["z"], r1["z"])
     err = (r0["zg"] - ref["zg"]).abs().max().item()
@@ -100,3 +111,19 @@ def test_cutout_sharded_two_ranks_with_aux_losses(tmp_path):
     assert err <= 3e-2 * mag
     assert np.abs(r0["losses"] - ref["losses"].numpy()).max() < 5e-3
     assert np.array_equal(r0["losses"], r1["losses"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_cutout_sharded_two_ranks_with_image_prompts_and_color_jitter(tmp_path):
+    """Image prompts + ColorJitter under sharding: loss vector as on one GPU, ranks bit-identical.  z.grad at the
+    whole-chain bound of the jittered path (tests/test_color_jitter.py)."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), 2), nprocs=2, join=True)
+    r0, r1, ref = (torch.load(tmp_path / n, weights_only=False) for n in ("rank0.pt", "rank1.pt", "ref.pt"))
+    assert torch.equal(r0["zg"], r1["zg"]) and torch.equal(r0["z"], r1["z"])
+    assert np.array_equal(r0["losses"], r1["losses"]) and r0["losses"].size == 4
+    err = (r0["zg"] - ref["zg"]).abs().max().item()
+    mag = ref["zg"].abs().max().item()
+    print(f"[parity] 2-rank sharded z.grad with image prompts + jitter: max_abs_err={err:.3e} ref_max={mag:.3e}; losses {r0['losses']} vs {ref['losses']}")
+    assert err <= 8e-2 * mag
+    assert np.abs(r0["losses"] - ref["losses"].numpy()).max() < 5e-3
