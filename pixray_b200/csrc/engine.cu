@@ -156,6 +156,17 @@ class Engine {
     allocs.push_back(p);
     return static_cast<T*>(p);
   }
+  // release one tracked allocation early (buffers that are rebuilt when prompts change); cudaFree waits for the device
+  template <class T>
+  void dfree(T*& p) {
+    if (!p) return;
+    auto it = std::find(allocs.begin(), allocs.end(), static_cast<void*>(p));
+    if (it != allocs.end()) {
+      cudaFree(*it);
+      allocs.erase(it);
+    }
+    p = nullptr;
+  }
   template <class T>
   T* upload(const std::vector<T>& v) {
     T* p = dalloc<T>(v.size(), false);
@@ -1407,6 +1418,11 @@ void Engine::rebuild_prompt_rows() {
         slot[j] = C.n_text + k;
         inv[j] = 1.f / cfg.cutn;
       }
+    dfree(C.prompts);
+    dfree(C.pweights);
+    dfree(C.pstops);
+    dfree(C.pinv);
+    dfree(C.pslot);
     if (rows > 0) {
       C.prompts = upload(pr);
       C.pweights = upload(w);
@@ -1743,6 +1759,7 @@ int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* w
     e->img_w.assign(n, 1.f);
     if (weights)
       for (int k = 0; k < n; ++k) e->img_w[k] = weights[k];
+    e->dfree(e->img_prompts);
     if (n > 0) {
       e->img_prompts = e->dalloc<float>(npx * n);
       PXR_CUDA(cudaMemcpyAsync(e->img_prompts, imgs, sizeof(float) * npx * n, cudaMemcpyDefault, e->st));

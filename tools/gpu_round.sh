@@ -1,5 +1,3 @@
 #!/bin/bash
-# scratch driver for one gpurun call: the bench exactly as the driver launches it
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$? lines=$(wc -l < gpurun_out/bench_default.json)"
-cut -c1-260 gpurun_out/bench_default.json; grep -o '"cpu_baseline": {[^}]*}' gpurun_out/bench_default.json | cut -c1-200; tail -2 gpurun_out/bench_default.err
+timeout 80 python -m pytest tests/test_image_prompts_gpu.py tests/test_pipeline_gpu.py -m gpu -q -x > gpurun_out/last_check.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/last_check.log
