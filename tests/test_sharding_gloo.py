@@ -43,7 +43,30 @@ def _setup():
     return vq, clip, z, cutn, cs, T, facs, noise, prompts
 
 
-def _sharded_grad(rank, world, port, out):
+def _extras():
+    """ColorJitter rows (per GLOBAL cutout index) and two image prompts for the second test."""
+    from pixray_b200 import cutouts
+    J = torch.from_numpy(cutouts.sample_color_jitter(6, 5, p=1.0))
+    J[1, 0] = 0
+    g = torch.Generator().manual_seed(9)
+    targets = [(torch.rand(1, 3, 8, 8, generator=g), 0.6), (torch.rand(1, 3, 8, 8, generator=g), -0.3)]
+    return J, targets
+
+
+def _local_cutouts(pooled, T, lo, n_local, zoom, cs, facs, noise, J=None):
+    parts = []
+    for n in range(lo, lo + n_local):
+        if n < zoom:
+            parts.append(R.warp_perspective(pooled, T[n:n + 1], (cs, cs), padding_mode="reflection"))
+        else:
+            parts.append(R.warp_perspective(pooled, T[n:n + 1], (cs, cs), padding_mode="fill", fill_value=[0.4] * 3))
+    batch = torch.cat(parts)
+    if J is not None:
+        batch = R.color_jitter(batch, J[lo:lo + n_local])
+    return batch + facs[lo:lo + n_local].reshape(-1, 1, 1, 1) * noise[lo:lo + n_local]
+
+
+def _sharded_grad(rank, world, port, out, extras=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
@@ -55,14 +78,25 @@ def _sharded_grad(rank, world, port, out):
     img = img_full.detach().requires_grad_(True)
     pooled = R.pool_avg_max(img, cs)
     zoom = int(0.6 * cutn)                                                # group split by GLOBAL index
-    parts = []
-    for n in range(lo, lo + n_local):
-        src = pooled
-        if n < zoom:
-            parts.append(R.warp_perspective(src, T[n:n + 1], (cs, cs), padding_mode="reflection"))
-        else:
-            parts.append(R.warp_perspective(src, T[n:n + 1], (cs, cs), padding_mode="fill", fill_value=[0.4] * 3))
-    batch = torch.cat(parts) + facs[lo:lo + n_local].reshape(-1, 1, 1, 1) * noise[lo:lo + n_local]
+    J, targets = _extras() if extras else (None, [])
+    mean = torch.tensor(R.CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(R.CLIP_STD).view(1, 3, 1, 1)
+    # image prompts first (engine.cu: encode_image_prompts): every rank cuts and encodes ITS slice of each target with the
+    # iteration's transforms (no ColorJitter on that path), the range normalise of the target batch is global too, and the
+    # [cutn, D] rows are completed with one allreduce(sum) over a buffer that is zero outside the rank's own rows
+    image_prompts = []
+    for (timg, w) in targets:
+        with torch.no_grad():
+            tb = _local_cutouts(R.pool_avg_max(timg, cs), T, lo, n_local, zoom, cs, facs, noise)
+            x = torch.stack([tb.min(), -tb.max()])
+            dist.all_reduce(x, op=dist.ReduceOp.MIN)
+            te = clip.encode_image(((tb - x[0]) / (-x[1] - x[0]) - mean) / std)
+            te = te / te.norm(dim=-1, keepdim=True)
+            rows = torch.zeros(cutn, te.shape[1])
+            rows[lo:lo + n_local] = te
+            dist.all_reduce(rows, op=dist.ReduceOp.SUM)
+        image_prompts.append((rows, w, float("-inf")))
+    batch = _local_cutouts(pooled, T, lo, n_local, zoom, cs, facs, noise, J)
     # global range: one allreduce(min) over {min, -max}; autograd ownership of the extreme element stays local
     lmin, lmax = batch.min(), batch.max()
     x = torch.stack([lmin.detach(), -lmax.detach()])
@@ -75,12 +109,10 @@ def _sharded_grad(rank, world, port, out):
     mx = gmax.clone().requires_grad_(True)
     a = batch - mn
     y = a / (mx - mn)
-    mean = torch.tensor(R.CLIP_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(R.CLIP_STD).view(1, 3, 1, 1)
     e = clip.encode_image((y - mean) / std)
     e = e / e.norm(dim=-1, keepdim=True)
     loss = 0
-    for (embed, w, stop) in prompts:
+    for (embed, w, stop) in list(prompts) + image_prompts:
         # Prompt.forward's mean runs over ALL cutn cutouts: each rank contributes sum / cutn_global
         loss = loss + R.prompt_loss(e, embed, w, stop) * (n_local / cutn)
     loss.backward(retain_graph=True)
@@ -108,6 +140,23 @@ def test_cutout_sharding_matches_single_process(tmp_path):
     out = str(tmp_path / "sharded.pt")
     port = _free_port()
     mp.spawn(_sharded_grad, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    err = (got["grad"] - ref["z_grad"]).abs().max().item()
+    mag = ref["z_grad"].abs().max().item()
+    assert mag > 0 and err <= 2e-5 * max(1.0, mag), (err, mag)
+    assert abs(float(got["loss"]) - float(sum(ref["losses"]))) < 1e-5
+
+
+@pytest.mark.timeout(300)
+def test_sharding_with_image_prompts_and_color_jitter(tmp_path):
+    """The two additions to the exchange: ColorJitter rows are per global cutout index (nothing to exchange), image
+    prompts need all cutn target rows on every rank (one allreduce per target and perceptor)."""
+    vq, clip, z, cutn, cs, T, facs, noise, prompts = _setup()
+    J, targets = _extras()
+    ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], T, cs, "reflection", 0.4, facs, noise,
+                    jitter=J, image_prompts=targets)
+    out = str(tmp_path / "sharded.pt")
+    mp.spawn(_sharded_grad, args=(2, _free_port(), out, True), nprocs=2, join=True)
     got = torch.load(out)
     err = (got["grad"] - ref["z_grad"]).abs().max().item()
     mag = ref["z_grad"].abs().max().item()
