@@ -41,6 +41,7 @@ class Session:
         self.cur_iteration = 0
         self.global_padding_mode = "reflection"
         self.global_fill_color = 0.0
+        self.last_embeds = {}  # clip_idx -> the tensor Perceptor.encode_image handed out this iteration
 
     def begin_iteration(self, cur_iteration, fill=None, rng=None):
         self.cur_iteration = cur_iteration
@@ -217,6 +218,62 @@ class VdiffDrawer(DrawingInterface):
         return self.x.clone()
 
 
+class FftDrawer(DrawingInterface):
+    """fftdrawer.py:13-109, `fft_use="fft"`: params = the rfft2 spectrum [1, 3, H, W/2+1, 2] ~ N(0, 0.01^2)
+    (aphantasia fft_image), synth = to_valid_rgb(fft_image)(contrast=0.9); the drawer owns its Adam (lr fft_lrate /
+    decay_divisor, fftdrawer.py:63-67), which `get_opts` reports as a learning rate for the engine's fused Adam."""
+
+    @staticmethod
+    def add_settings(parser):
+        parser.add_argument("--fft_use", type=str, help="use fft or dwt or pixel", default="fft", dest="fft_use")
+        parser.add_argument("--fft_decay", default=1.5, type=float, dest="fft_decay")
+        parser.add_argument("--fft_wave", default="coif2", help="wavelets: db[1..], coif[1..], haar, dmey", dest="fft_wave")
+        parser.add_argument("--fft_sharp", default=0.3, type=float, dest="fft_sharp")
+        parser.add_argument("--fft_colors", default=1.5, type=float, dest="fft_colors")
+        parser.add_argument("--fft_lrate", default=0.3, type=float, help="Learning rate", dest="fft_lrate")
+        return parser
+
+    def __init__(self, settings, session: Session):
+        super().__init__(settings)
+        self.session = session
+        if getattr(settings, "fft_use", "fft") != "fft":
+            raise NotImplementedError("fft_use: only 'fft' is on the hot-path scope (dwt / pixel need pytorch_wavelets)")
+        self.lrate = getattr(settings, "fft_lrate", 0.3)
+        self.params = None
+
+    def load_model(self, settings, device):
+        self.device = device
+
+    def get_opts(self, decay_divisor=1):
+        return [{"lr": self.lrate / decay_divisor}]
+
+    def get_num_resolutions(self):
+        return None
+
+    def init_from_tensor(self, init_tensor, seed=None):
+        if init_tensor is not None:
+            raise NotImplementedError("resuming the spectrum from an image (fft_image(resume=...)) is init-time and not built")
+        eng = self.session.engine
+        g = None if seed is None else torch.Generator(device=eng.device).manual_seed(seed)
+        self.params = (0.01 * torch.randn(eng.z_shape, device=eng.device, generator=g)).contiguous()  # fft_image(sd=0.01)
+
+    def synth(self, cur_iteration):
+        return self.session.engine.synth(self.params)
+
+    def clip_z(self):
+        pass
+
+    def get_z(self):
+        return self.params  # the reference returns None here and optimises self.params through its own Adam
+
+    def set_z(self, new_z):
+        with torch.no_grad():
+            return self.params.copy_(new_z)
+
+    def get_z_copy(self):
+        return self.params.clone()
+
+
 class MakeCutouts:
     """pixray.py:399-511.  `transforms` is the per-iteration cache of composed 3x3s (pixray.py:498); when it is None
     a fresh set is sampled (the distributions of the reference's augmentation stacks, pixray_b200/cutouts.py)."""
@@ -268,7 +325,9 @@ class Perceptor:
     def encode_image(self, imgs, input_range=None, apply_preprocess=True):
         if input_range is not None or not apply_preprocess:
             raise NotImplementedError("only the default preprocess path of the hot loop is implemented (pixray.py:1295)")
-        return self.session.engine.encode_image(self.clip_idx, imgs)
+        e = self.session.engine.encode_image(self.clip_idx, imgs)
+        self.session.last_embeds[self.clip_idx] = e
+        return e
 
     def encode_text(self, text):
         raise NotImplementedError("text towers are init-time (SURVEY.md row 10); pass prompt embeddings")
@@ -287,7 +346,8 @@ class Prompt:
     def register(session: Session, clip_idx, prompts):
         """pmsTable[clip_model] = [Prompt, ...] (pixray.py:859-915)."""
         if any(p.embed.shape[0] != 1 for p in prompts):
-            raise ValueError("one embedding row per Prompt (multi-row image prompts are out of scope, SURVEY.md 8f-2)")
+            raise ValueError("one embedding row per registered Prompt; image prompts ([cutn, D] rows, refreshed every "
+                             "iteration) go through engine.set_image_prompts")
         session.engine.set_prompts(clip_idx, torch.cat([p.embed for p in prompts]).numpy(),
                                    [float(p.weight) for p in prompts], [float(p.stop) for p in prompts])
         for i, p in enumerate(prompts):
@@ -299,7 +359,12 @@ class Prompt:
     def forward(self, input):
         if self._session is None:
             raise RuntimeError("Prompt.register(session, clip_idx, prompts) must be called first")
-        return self._session.engine.prompt_loss(self._clip_idx, input)[self._index]
+        # `input` is normally the tensor perceptor.encode_image just returned (possibly through .float()): the engine still
+        # holds those embeddings un-normalised, which its backward needs, so they are not passed back in.  Foreign
+        # embeddings are scored as given (their gradient then stops at the embedding).
+        own = self._session.last_embeds.get(self._clip_idx)
+        mine = own is not None and input.data_ptr() == own.data_ptr() and input.shape == own.shape
+        return self._session.engine.prompt_loss(self._clip_idx, None if mine else input)[self._index]
 
 
 def parse_prompt(prompt):

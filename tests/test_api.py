@@ -1,0 +1,233 @@
+"""The module-level entry points (pixray_b200/api.py = pixray.py:2005-2124) on the CPU: the settings pipeline against what
+the real reference resolves (tests/golden/api_settings.json, oracle/make_golden_api.py), and the do_init / do_run control flow
+(prompt order, learning-rate drops, auto-stop, vdiff re-noising) against a recording stand-in for the engine."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fake_engine import FakeEngine
+from pixray_b200 import api
+from pixray_b200 import engine as E
+from pixray_b200 import plugins as P
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "api_settings.json")))
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    monkeypatch.setattr(api, "_engine_factory", FakeEngine)
+    FakeEngine.loss_script = staticmethod(lambda it, n: np.full(n, 1.0 / (1 + it), dtype=np.float32))
+    api.reset_settings()
+    yield
+    api.reset_settings()
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_settings_resolve_like_the_reference(name):
+    case = GOLD[name]
+    api.reset_settings()
+    api.add_settings(outdir="", **case["settings"])
+    a = api.apply_settings()
+    for k, want in case["want"].items():
+        assert getattr(a, k) == want, (name, k, getattr(a, k), want)
+    assert api.get_settings()["outdir"] == ""
+
+
+def test_unknown_setting_and_unknown_plugins_raise():
+    api.reset_settings()
+    api.add_settings(prompts="x", bogus=1)
+    with pytest.raises(ValueError, match="Requested setting not found, aborting: bogus=1"):   # pixray.py:2093
+        api.apply_settings()
+    api.reset_settings()
+    api.add_settings(prompts="x", drawer="clipdraw")
+    with pytest.raises(ValueError):
+        api.apply_settings()
+    api.reset_settings()
+    api.add_settings(prompts="x", custom_loss="style")
+    with pytest.raises(ValueError, match="Requested loss not found"):
+        api.apply_settings()
+    api.reset_settings()
+
+
+@pytest.mark.parametrize("kw", [dict(spot_prompts="a"), dict(init_image="x.png"), dict(optimiser="AdamP"),
+                                dict(perceptors="slip"), dict(filters="wallpaper"), dict(make_video=True),
+                                dict(animation_dir="anim"), dict(overlay_image="o.png"), dict(transparent=True)])
+def test_options_off_the_hot_path_are_refused_not_ignored(kw):
+    api.reset_settings()
+    api.add_settings(prompts="x", **kw)
+    with pytest.raises(NotImplementedError):
+        api.apply_settings()
+    api.reset_settings()
+
+
+def test_drawer_and_loss_options_are_contributed_by_the_plugins():
+    api.reset_settings()
+    api.add_settings(prompts="x", drawer="fft", fft_decay=2.0, custom_loss="smoothness:0.5", smoothness_type="log")
+    a = api.apply_settings()
+    assert a.fft_decay == 2.0 and a.fft_lrate == 0.3 and a.smoothness_type == "log"
+    api.reset_settings()
+    api.add_settings(prompts="x", fft_decay=2.0)          # not a vqgan option
+    with pytest.raises(ValueError):
+        api.apply_settings()
+    api.reset_settings()
+
+
+def _init(tmp_path, **kw):
+    (tmp_path / "vectors").mkdir(exist_ok=True)
+    (tmp_path / "vectors" / "textoff.json").write_text(json.dumps({"ViT-B/16": [[0.1] * 512], "ViT-B/32": [[0.2] * 512]}))
+    os.environ["PIXRAY_ROOT"] = str(tmp_path)
+    base = dict(size=[64, 64], num_cuts=8, outdir="", seed="7", b200_allow_synthetic=True)
+    base.update(kw)
+    api.add_settings(**base)
+    args = api.apply_settings()
+    return api.do_init(args)
+
+
+def test_do_init_builds_the_session_in_the_reference_order(fake, tmp_path):
+    args = _init(tmp_path, prompts="a cat:2|a dog:-0.5:0.3", clip_models="ViT-B/32,ViT-B/16", iterations=20,
+                 noise_prompt_seeds=[3], noise_prompt_weights=[0.25])
+    eng = api._state.engine
+    assert eng.kw["image_hw"] == (64, 64) and eng.kw["cutn"] == 8 and len(eng.kw["clip"]) == 2
+    assert eng.names()[:4] == ["load_module", "load_module", "load_module", "finalize"]
+    # per perceptor: text prompts, then the vector prompt at 10 % weight; the noise prompt lands on the loop's last perceptor
+    for i, name in enumerate(args.clip_models):
+        emb, w, stops = eng.prompts[i]
+        want_w = [2.0, -0.5, 0.1] + ([0.25] if i == 1 else [])
+        assert w == pytest.approx(want_w)
+        assert stops[1] == pytest.approx(0.3) and stops[0] == float("-inf")
+        assert np.allclose(emb[2], 0.2 if name == "ViT-B/32" else 0.1)
+    assert isinstance(api._state.drawer, P.VqganDrawer) and tuple(api._state.drawer.get_z().shape) == (1, 256, 4, 4)
+    assert api._state.lr == pytest.approx(0.2) and eng.names().count("reset_optimizer") == 1
+    # same seed string -> same starting latent (sha512 seed, pixray.py:595-606)
+    z0 = api._state.drawer.get_z_copy()
+    api.reset_settings()
+    _init(tmp_path, prompts="a cat:2|a dog:-0.5:0.3", clip_models="ViT-B/32,ViT-B/16", iterations=20)
+    assert torch.equal(z0, api._state.drawer.get_z())
+
+
+def test_text_prompts_need_a_text_tower(fake, tmp_path):
+    with pytest.raises(ValueError, match="text tower"):
+        _init(tmp_path, prompts="a cat", clip_models="ViT-B/16", b200_allow_synthetic=False)
+    api.reset_settings()
+    seen = []
+
+    def enc(model, txt):
+        seen.append((model, txt))
+        return torch.ones(1, 512)
+    _init(tmp_path, prompts="a cat|a dog", clip_models="ViT-B/16", b200_allow_synthetic=False, b200_text_encoder=enc)
+    assert seen == [("ViT-B/16", "a cat"), ("ViT-B/16", "a dog")]
+
+
+def test_unbuilt_configurations_fail_loudly(fake, tmp_path):
+    for kw in (dict(clip_models="RN50"), dict(size=[128, 64]), dict(quality="best", clip_models="ViT-B/16")):
+        api.reset_settings()
+        with pytest.raises(NotImplementedError):
+            _init(tmp_path, prompts="x", **kw)
+
+
+def test_do_run_scheduled_learning_rate_drops(fake, tmp_path):
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", iterations=20, learning_rate_drops=[50, 25])
+    assert args.learning_rate_drops == [9, 4]                      # percent of iterations - 1 (pixray.py:1999-2003)
+    assert api.do_run(args) is True
+    eng = api._state.engine
+    its = [(c[1]["it"], round(c[1]["lr"], 6)) for c in eng.calls if c[0] == "iterate"]
+    assert [i for i, _ in its] == list(range(20))                  # iterations 0..19, the 20th call only checks in
+    # a drop takes effect AFTER the iteration that triggers it (rebuild_opts_when_done), each one divides by 10
+    assert [lr for _, lr in its] == [0.2] * 5 + [0.02] * 5 + [0.002] * 10
+    assert eng.names().count("reset_optimizer") == 3               # fresh Adam at init and at every drop
+    assert api._state.cur_iteration == 20 and api.get_image() is not None
+    assert eng.names()[-1] == "synth"                              # final checkin renders the image
+
+
+def test_do_run_auto_stop_on_plateau(fake, tmp_path):
+    # the loss stops improving at iteration 3: 12 iterations later (iter_drop_delay) checkdrop fires, auto_stop turns that
+    # into a drop, and with one scheduled drop the second plateau ends the run (num_loss_drop > max_loss_drops)
+    FakeEngine.loss_script = staticmethod(lambda it, n: np.full(n, max(1.0 - 0.1 * it, 0.7), dtype=np.float32))
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", iterations=200, learning_rate_drops=[99], auto_stop=True)
+    assert api.do_run(args) is True
+    its = [(c[1]["it"], round(c[1]["lr"], 6)) for c in api._state.engine.calls if c[0] == "iterate"]
+    # best at 3 -> drop after 15 (best_loss reset, pixray.py:1509-1510) -> new best at 16 -> second plateau ends the run at 28
+    assert its[-1][0] == 28 and len(its) == 29
+    assert [lr for _, lr in its] == [0.2] * 16 + [0.02] * 13
+
+
+def test_return_display_hands_control_back(fake, tmp_path):
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", iterations=50, display_every=20)
+    assert api.do_run(args, return_display=True) is False and api._state.cur_iteration == 20
+    assert api.do_run(args, return_display=True) is False and api._state.cur_iteration == 40
+    assert api.do_run(args, return_display=True) is True and api._state.cur_iteration == 50
+
+
+def test_runtime_errors_get_the_hint_and_propagate(fake, tmp_path, capsys):
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", iterations=5)
+
+    def boom(*a, **k):
+        raise RuntimeError("CUDA out of memory")
+    api._state.engine.iterate = boom
+    with pytest.raises(RuntimeError, match="out of memory"):
+        api.do_run(args)
+    assert "Try reducing --num-cuts" in capsys.readouterr().out     # pixray.py:1625-1628
+
+
+def test_vdiff_loop_renoises_and_restarts_adam(fake, tmp_path):
+    sd = {"dummy": torch.zeros(1)}
+    args = _init(tmp_path, prompts="x", drawer="vdiff", clip_models="ViT-B/16", iterations=6, learning_rate_drops=None,
+                 b200_weights={"vdiff": sd})
+    eng = api._state.engine
+    assert "vdiff_set_schedule" in eng.names() and "vdiff_set_clip_embed" in eng.names()
+    assert api.do_run(args) is True
+    renoise = [c[1]["i"] for c in eng.calls if c[0] == "vdiff_renoise"]
+    assert renoise == [1, 2, 3, 4, 5, 6]                              # every step from the second on (pixray.py:1489-1495)
+    lrs = [c[1]["lr"] for c in eng.calls if c[0] == "iterate"]
+    d = api._state.drawer
+    assert lrs[0] == pytest.approx(0.2)
+    for it in range(2, 6):                                            # lr of iteration it was set after iteration it-1
+        assert lrs[it] == pytest.approx(min(float(d.sigmas[it - 1] / d.alphas[it - 1]) * 0.001, 0.01))
+
+
+def test_custom_losses_and_image_prompts_reach_the_engine(fake, tmp_path):
+    target = torch.rand(1, 3, 32, 32)
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", iterations=3, custom_loss="smoothness:0.5,symmetry",
+                 image_prompts=[target], image_prompt_weight=0.7)
+    eng = api._state.engine
+    assert [a[0] for a in eng.aux] == [E.LOSS_SMOOTHNESS, E.LOSS_SYMMETRY] and eng.aux[0][1] == 0.5 and eng.aux[1][1] == 1
+    imgs, w = eng.image_prompts
+    assert tuple(imgs.shape) == (1, 3, 64, 64) and w == [0.7]
+    assert api._state.loss_buf.size == eng.num_losses() == 2 + 1 + 2  # text + vector, image prompt, two custom losses
+    assert api.do_run(args) is True
+
+
+def test_run_is_the_one_stop_call(fake, tmp_path):
+    (tmp_path / "vectors").mkdir(exist_ok=True)
+    (tmp_path / "vectors" / "textoff.json").write_text(json.dumps({"ViT-B/16": [[0.1] * 512]}))
+    os.environ["PIXRAY_ROOT"] = str(tmp_path)
+    api.run("a cat", "fast_pixel", size=[32, 32], pixel_size=[8, 8], clip_models="ViT-B/16", iterations=4, num_cuts=4,
+            outdir="", b200_allow_synthetic=True)
+    assert [c[1]["it"] for c in api._state.engine.calls if c[0] == "iterate"] == [0, 1, 2, 3]
+    assert isinstance(api._state.drawer, P.FastPixelDrawer) and tuple(api._state.drawer.get_z().shape) == (1, 3, 8, 8)
+
+
+def test_plugin_train_iteration_call_sequence(fake, tmp_path):
+    """The per-op plugin path (what a pixray loop written against the plugin objects executes): one iteration issues the
+    reference's sequence, and Prompt.forward does not hand the engine's own embeddings back in (the engine keeps them
+    un-normalised for its backward)."""
+    _init(tmp_path, prompts="a|b", clip_models="ViT-B/16", iterations=3)
+    st = api._state
+    eng = st.engine
+    eng.calls.clear()
+    opt = P.Optimizer(st.session, st.drawer, 0.05)
+    st.session.begin_iteration(0, fill=0.5)
+    losses = P.train_iteration(st.session, st.drawer, st.make_cutouts, st.perceptors, st.prompt_tables, opt)
+    assert len(losses) == 3
+    assert eng.names() == ["reset_optimizer", "synth", "make_cutouts", "encode_image", "prompt_loss", "prompt_loss",
+                           "prompt_loss", "backward", "step"]
+    assert not any(c[1]["passed_embeds"] for c in eng.calls if c[0] == "prompt_loss")
+    mc = [c for c in eng.calls if c[0] == "make_cutouts"][0][1]
+    assert mc["transforms"] == "ndarray" and mc["color_jitter"] == "ndarray" and mc["noise"] == "Tensor"
+    assert st.make_cutouts.transforms is None                        # per-iteration cache cleared (pixray.py:1339-1342)
+    assert torch.equal(st.drawer.get_z().grad, torch.ones(eng.z_shape))
+    step = [c for c in eng.calls if c[0] == "step"][0][1]
+    assert step["lr"] == 0.05 and step["it"] == 0
