@@ -231,3 +231,12 @@ def test_plugin_train_iteration_call_sequence(fake, tmp_path):
     assert torch.equal(st.drawer.get_z().grad, torch.ones(eng.z_shape))
     step = [c for c in eng.calls if c[0] == "step"][0][1]
     assert step["lr"] == 0.05 and step["it"] == 0
+
+
+def test_package_exposes_the_reference_entry_points():
+    import pixray_b200 as pixray
+    for name in ("run", "reset_settings", "add_settings", "get_settings", "apply_settings", "do_init", "do_run",
+                 "add_custom_loss"):
+        assert callable(getattr(pixray, name)), name
+    with pytest.raises(AttributeError):
+        pixray.no_such_thing
