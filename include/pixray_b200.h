@@ -76,8 +76,11 @@ typedef struct {
   const float* transforms; /* host, [cutn, 3, 3] */
   int zoom_padding;        /* PXR_PAD_REFLECTION on even iterations, PXR_PAD_BORDER on odd (pixray.py:1250-1253) */
   float fill;              /* wide-group fill grey = random.random() (pixray.py:1255-1258) */
-  const float* noise_facs; /* host, [cutn] ~ U(0, noise_fac) (pixray.py:509); NULL = engine Philox */
-  const float* noise;      /* DEVICE, [cutn,3,cs,cs] standard normal (pixray.py:510); NULL = engine Philox */
+  /* batch + facs * randn_like(batch) (pixray.py:508-510).  Given together: replayed as is.  Both NULL: with
+   * transforms == NULL the engine draws them (Philox keyed by seed, iteration and GLOBAL element index), with explicit
+   * transforms the call is a deterministic replay WITHOUT noise.  One without the other is an error (-61). */
+  const float* noise_facs; /* host, [cutn] ~ U(0, noise_fac) (pixray.py:509) */
+  const float* noise;      /* DEVICE, [cutn,3,cs,cs] standard normal (pixray.py:510) */
   /* K.ColorJitter(hue=0.1, saturation=0.1, p=0.8), the last stage of both stacks (pixray.py:416, 436): host
    * [cutn, 3] rows {code, saturation_factor, hue_factor}.  code 0 = this cutout missed the Bernoulli(p); else
    * 256 + o0 + 4*o1 + 16*o2 + 64*o3 with o_k the transform applied k-th (0 brightness, 1 contrast, 2 saturation,
