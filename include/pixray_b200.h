@@ -210,6 +210,9 @@ int pxr_test_conv(const pxr_test_gemm_desc* d, int batch, int H, int W, int c_in
 /* host-side evaluation of the ColorJitter pixel body and its vector-Jacobian product (no GPU needed) */
 int pxr_test_color_jitter_host(const float* rgb, int n, int code, float saturation, float hue, const float* g_out,
                                float* out, float* g_in);
+/* the same body on the device; all pointers are DEVICE [n, 3] (default stream, synchronous) */
+int pxr_test_color_jitter_device(const float* rgb, int n, int code, float saturation, float hue, const float* g_out,
+                                 float* out, float* g_in);
 
 /* fused ViT attention (attn_tc.cu): forward, and backward when d_o != NULL.  qkv [B*T, 3W], o / d_o [B*T, W],
  * gqkv [B*T, 3W] fp16 device tensors, lse [B*H*T] fp32; heads are 64 wide (W = 64 H), T <= 256 */

@@ -125,3 +125,31 @@ extern "C" int pxr_test_color_jitter_host(const float* rgb, int n, int code, flo
   }
   return 0;
 }
+
+// The same body on the device (what cutout_fwd / cutout_bwd execute per pixel), for a device-vs-host comparison of the
+// forward and of the vector-Jacobian product.  rgb / g_out / out / g_in are DEVICE [n, 3].
+namespace {
+__global__ void color_jitter_device_kernel(const float* rgb, int n, int code, float saturation, float hue,
+                                           const float* g_out, float* out, float* g_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float in[3] = {rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+  float c[3] = {in[0], in[1], in[2]};
+  pxr::cj_apply(c, code, saturation, hue);
+  for (int k = 0; k < 3; ++k) out[3 * i + k] = c[k];
+  if (g_out && g_in) {
+    const float go[3] = {g_out[3 * i], g_out[3 * i + 1], g_out[3 * i + 2]};
+    float gi[3];
+    pxr::cj_vjp(in, code, saturation, hue, go, gi);
+    for (int k = 0; k < 3; ++k) g_in[3 * i + k] = gi[k];
+  }
+}
+}  // namespace
+
+extern "C" int pxr_test_color_jitter_device(const float* rgb, int n, int code, float saturation, float hue,
+                                            const float* g_out, float* out, float* g_in) {
+  if (!rgb || !out || n < 0) return -1;
+  if (n == 0) return 0;
+  color_jitter_device_kernel<<<(n + 255) / 256, 256>>>(rgb, n, code, saturation, hue, g_out, out, g_in);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}

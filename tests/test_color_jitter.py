@@ -71,6 +71,27 @@ def test_pixel_body_matches_the_oracle_for_every_order():
     assert worst_g <= 1e-5, worst_g
 
 
+def test_pixel_body_at_exact_channel_ties():
+    """Clamped images are full of exact ties (white, black, grey, two saturated channels): there the Jacobian is one-sided
+    and must follow torch's choice (first arg-max / arg-min channel, zero hue gradient at delta == 0, closed clamp)."""
+    g = np.random.default_rng(0)
+    n = 1000
+    a, b = g.uniform(0, 1, n).astype(np.float32), g.uniform(0, 1, n).astype(np.float32)
+    hi, lo, one, zero = np.maximum(a, b), np.minimum(a, b), np.ones(n, np.float32), np.zeros(n, np.float32)
+    cases = {"grey": [a, a, a], "white": [one, one, one], "black": [zero, zero, zero], "max tie rg": [hi, hi, lo],
+             "max tie gb": [lo, hi, hi], "max tie rb": [hi, lo, hi], "min tie rg": [lo, lo, hi], "min tie gb": [hi, lo, lo],
+             "r=1": [one, a, b], "b=0": [a, b, zero], "r=g=1": [one, one, b], "g=b=0": [a, zero, zero]}
+    go = g.standard_normal((n, 3)).astype(np.float32)
+    for name, cols in cases.items():
+        rgb = np.stack(cols, 1)
+        for order in ([2, 3, 0, 1], [3, 2, 1, 0], [0, 2, 1, 3]):
+            code = cutouts.jitter_code(order)
+            out, g_in = _host_jitter(rgb, code, 1.07, -0.083, go)
+            ref, ref_g = _oracle_jitter(rgb, code, 1.07, -0.083, go)
+            assert np.abs(out - ref).max() <= 2e-6, (name, order)
+            assert np.abs(g_in - ref_g).max() <= 2e-5, (name, order, float(np.abs(g_in - ref_g).max()))
+
+
 def test_not_selected_cutouts_pass_through():
     rgb = _colours(256, 2)
     g = np.ones_like(rgb)
