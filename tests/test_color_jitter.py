@@ -92,6 +92,38 @@ def test_pixel_body_at_exact_channel_ties():
             assert np.abs(g_in - ref_g).max() <= 2e-5, (name, order, float(np.abs(g_in - ref_g).max()))
 
 
+def test_backward_algorithm_of_the_cutout_kernel_equals_autograd():
+    """What cutout_bwd does with the stage on -- recompute the warped colour, push the incoming gradient through the pixel
+    body's VJP, then through the warp's adjoint -- against autograd through the oracle's whole jittered make_cutouts."""
+    torch.manual_seed(0)
+    cutn, cs = 5, 40
+    img = torch.rand(1, 3, 16, 16)
+    img[:, :, :4] = 1.0                      # a saturated band: exact ties inside, kinks at its border
+    img[:, 1:, 12:] = 0.0
+    img.requires_grad_(True)
+    T = torch.eye(3).repeat(cutn, 1, 1)
+    T[:, 0, 0] = torch.tensor([1.3, 1.1, 1.5, 0.9, 0.8])
+    T[:, 1, 1] = torch.tensor([1.2, 1.4, 1.1, 0.9, 0.85])
+    T[:, 0, 2] = torch.tensor([-3.0, 1.5, -6.0, 1.0, 2.0])
+    J = torch.from_numpy(cutouts.sample_color_jitter(cutn, 3, p=1.0))
+    J[2, 0] = 0
+    facs, noise = torch.rand(cutn) * 0.1, torch.randn(cutn, 3, cs, cs)
+    full = R.make_cutouts(img, T, cs, "reflection", 0.4, facs, noise, jitter=J)
+    g_out = torch.randn_like(full)
+    want, = torch.autograd.grad(full, img, g_out, retain_graph=True)
+    pre = R.make_cutouts(img, T, cs, "reflection", 0.4)                      # the warp alone
+    g_pre = torch.zeros_like(pre)
+    for n in range(cutn):
+        rgb = pre[n].detach().reshape(3, -1).t().contiguous().numpy()
+        go = g_out[n].reshape(3, -1).t().contiguous().numpy()
+        out, gi = _host_jitter(rgb, int(J[n, 0]), float(J[n, 1]), float(J[n, 2]), go)
+        g_pre[n] = torch.from_numpy(gi).t().reshape(3, cs, cs)
+        got_fwd = torch.from_numpy(out).t().reshape(3, cs, cs) + facs[n] * noise[n]
+        assert (got_fwd - full[n].detach()).abs().max() <= 2e-6
+    got, = torch.autograd.grad(pre, img, g_pre)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+
+
 def test_not_selected_cutouts_pass_through():
     rgb = _colours(256, 2)
     g = np.ones_like(rgb)
