@@ -184,7 +184,8 @@ def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None,
 # kornia/enhance/adjust.py adjust_{brightness,contrast,saturation,hue}, kornia/augmentation ColorJitter.apply_transform
 # with random_color_jitter_generator's parameters).  Parity for this stage is therefore UNPINNED against kornia itself;
 # it is anchored on the reference's call site (which factors, which probability) and on the kernel matching this
-# restatement forward and backward.
+# restatement forward and backward; the rgb<->hsv maps themselves are cross-checked against OpenCV's float conversions and
+# the standard library's colorsys (tests/test_color_jitter.py::test_oracle_hsv_maps_agree_with_opencv_and_colorsys).
 
 
 def rgb_to_hsv(image, eps=1e-8):

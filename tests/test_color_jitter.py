@@ -124,6 +124,36 @@ def test_backward_algorithm_of_the_cutout_kernel_equals_autograd():
     assert (got - want).abs().max() <= 2e-5 * want.abs().max()
 
 
+def test_oracle_hsv_maps_agree_with_opencv_and_colorsys():
+    """kornia itself is not installable here, so the oracle's rgb<->hsv restatement cannot be pinned to it; it is
+    cross-checked against two independent implementations of the same published transform instead (OpenCV's float
+    RGB2HSV / HSV2RGB, H in degrees; the standard library's colorsys, h in turns)."""
+    import colorsys
+    import math
+    cv2 = pytest.importorskip("cv2")
+    rgb = _colours(4096, 5)
+    hsv = R.rgb_to_hsv(torch.from_numpy(rgb).t().reshape(1, 3, 1, -1)).reshape(3, -1).t().numpy()
+    ref = cv2.cvtColor(rgb.reshape(1, -1, 3), cv2.COLOR_RGB2HSV).reshape(-1, 3)
+    dh = np.abs(hsv[:, 0] - np.deg2rad(ref[:, 0]))
+    dh = np.minimum(dh, 2 * math.pi - dh)
+    sat = ref[:, 1] > 1e-3                                            # hue is arbitrary at zero saturation
+    assert dh[sat].max() < 2e-4 and np.abs(hsv[:, 1] - ref[:, 1]).max() < 1e-5 and np.abs(hsv[:, 2] - ref[:, 2]).max() < 1e-7
+    for i in range(0, 4096, 97):
+        h, s_, v = colorsys.rgb_to_hsv(*[float(c) for c in rgb[i]])
+        d = abs(hsv[i, 0] / (2 * math.pi) - h)
+        assert (min(d, 1 - d) < 1e-5 or s_ < 1e-3) and abs(hsv[i, 1] - s_) < 1e-5 and abs(hsv[i, 2] - v) < 1e-6
+    # and back: hue shifted by a fixed angle, saturation scaled, through the oracle vs through OpenCV
+    shifted = ref.copy()
+    shifted[:, 0] = np.mod(shifted[:, 0] + 25.0, 360.0)
+    shifted[:, 1] = np.clip(shifted[:, 1] * 1.07, 0, 1)
+    want = cv2.cvtColor(shifted.reshape(1, -1, 3), cv2.COLOR_HSV2RGB).reshape(-1, 3)
+    t = torch.from_numpy(hsv.copy())
+    t[:, 0] = torch.fmod(t[:, 0] + math.radians(25.0), 2 * math.pi)
+    t[:, 1] = torch.clamp(t[:, 1] * 1.07, 0, 1)
+    got = R.hsv_to_rgb(t.t().reshape(1, 3, 1, -1)).reshape(3, -1).t().numpy()
+    assert np.abs(got - want).max() < 2e-5
+
+
 def test_not_selected_cutouts_pass_through():
     rgb = _colours(256, 2)
     g = np.ones_like(rgb)
