@@ -214,6 +214,9 @@ int pxr_test_color_jitter_host(const float* rgb, int n, int code, float saturati
 int pxr_test_color_jitter_device(const float* rgb, int n, int code, float saturation, float hue, const float* g_out,
                                  float* out, float* g_in);
 
+/* adaptive-pool window bounds as the device computes them (pool_fwd / pool_bwd): DEVICE int [out_size] each */
+int pxr_test_pool_bounds(int in_size, int out_size, int* starts, int* ends);
+
 /* fused ViT attention (attn_tc.cu): forward, and backward when d_o != NULL.  qkv [B*T, 3W], o / d_o [B*T, W],
  * gqkv [B*T, 3W] fp16 device tensors, lse [B*H*T] fp32; heads are 64 wide (W = 64 H), T <= 256 */
 int pxr_test_attention(const void* qkv, void* o, float* lse, const void* d_o, void* gqkv, int B, int T, int H, int W,

@@ -791,7 +791,6 @@ void Engine::build_vqgan() {
   if (cfg.image_h % f || cfg.image_w % f)
     throw EngineError(-44, "image size must be a multiple of 2^(n_levels-1)");
   const int h = cfg.image_h / f, w = cfg.image_w / f, hw = h * w;
-  if (w % 8) throw EngineError(-45, "latent width must be a multiple of 8 for the implicit-GEMM conv tiles");
   z_numel = (int64_t)zc * hw;
   // GN scratch sized for the largest activation
   // (the cooperative kernels use up to one block per SM, the three-kernel path gn_num_partials blocks)
@@ -827,6 +826,7 @@ void Engine::build_vqgan() {
   float* zb = z_buf = dalloc<float>(z_numel);
   z_grad = dalloc<float>(z_numel);
   drawer_fwd.add(2, [=] { vq_nearest(zb, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq.p, cs); }, 0.0, "vq_nearest");
+  reg("vq_idx", idx, sizeof(int) * hw);  // argmin code per latent position (vqgan.py:62): integer bookkeeping
 
   // post_quant_conv + decoder
   ConvW pq = load_conv("post_quant_conv", zc, zc, 1);
@@ -1621,6 +1621,7 @@ void Engine::finalize() {
     reg("img_pre", img_pre, npx * 4);
     reg("g_img", g_img, npx * 4);
     reg("pooled", pooled, ncs * 4);
+    reg("pool_argmax", pool_argmax, ncs * 4);
     reg("g_pooled", g_pooled, ncs * 4);
     reg("batch", batch, ncs * n_local * 4);
     reg("g_batch", g_batch, ncs * n_local * 4);

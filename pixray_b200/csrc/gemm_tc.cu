@@ -1607,11 +1607,15 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
     set_err(err, errlen, "conv: c_in must be a multiple of 64 and ksize 1 or 3");
     return -30;
   }
-  int tile_w = W >= 16 ? 16 : 8;
-  if (W < 8 || (W % tile_w)) {
-    set_err(err, errlen, "conv: W must be a multiple of 8 (>= 8)");
+  if (W < 1 || H < 1) {
+    set_err(err, errlen, "conv: empty image");
     return -31;
   }
+  // M tile = tile_h x tile_w pixels (8 x 16 or 16 x 8).  Any W works: columns past the image are zero-filled by the
+  // TMA loads and clipped by the stores (tensor-map epilogue) / predicated off (generic epilogue); pick the width that
+  // wastes the fewest columns (pixray's presets give latents such as 9 x 9, 18 x 18, 12 x 6: pixray.py:1864-1878)
+  const int waste16 = (W + 15) / 16 * 16, waste8 = (W + 7) / 8 * 8;
+  int tile_w = (waste16 <= waste8) ? 16 : 8;
   int tile_h = GEMM_BLOCK_M / tile_w;
   p.M = H * W;
   p.N = n_out;
@@ -1625,7 +1629,7 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
   p.conv_W = W;
   p.tile_h = tile_h;
   p.tile_w = tile_w;
-  p.tiles_w = W / tile_w;
+  p.tiles_w = (W + tile_w - 1) / tile_w;
   p.tiles_m = p.tiles_w * ((H + tile_h - 1) / tile_h);
   p.tiles_n = (n_out + block_n - 1) / block_n;
   p.nb0 = batch;

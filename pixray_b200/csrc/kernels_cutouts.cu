@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 #include "color_jitter.cuh"
 #include "philox.cuh"
+#include "pool_bounds.cuh"
 #include <cfloat>
 
 namespace pxr {
@@ -16,11 +17,7 @@ namespace {
 __constant__ float c_clip_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
-// ATen adaptive pooling window: [floor(i*in/out), ceil((i+1)*in/out))
-__device__ __forceinline__ int pool_start(int i, int in, int out) { return (int)(((long long)i * in) / out); }
-__device__ __forceinline__ int pool_end(int i, int in, int out) {
-  return (int)((((long long)(i + 1)) * in + out - 1) / out);
-}
+// ATen adaptive pooling window [floor(i*in/out), ceil((i+1)*in/out)): pool_start / pool_end of pool_bounds.cuh
 
 __global__ void pool_fwd_kernel(const float* __restrict__ img, int H, int W, int cs, float* __restrict__ pooled,
                                 int* __restrict__ argmax) {

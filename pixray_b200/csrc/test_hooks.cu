@@ -4,6 +4,7 @@
 #include "gemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "color_jitter.cuh"
+#include "pool_bounds.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -151,5 +152,22 @@ extern "C" int pxr_test_color_jitter_device(const float* rgb, int n, int code, f
   if (!rgb || !out || n < 0) return -1;
   if (n == 0) return 0;
   color_jitter_device_kernel<<<(n + 255) / 256, 256>>>(rgb, n, code, saturation, hue, g_out, out, g_in);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+
+// The adaptive-pool window bounds as the DEVICE computes them (pool_bounds.cuh, the functions pool_fwd / pool_bwd call):
+// starts / ends are DEVICE int [out_size].  Integer bookkeeping: the test asserts equality with ATen's formula.
+namespace {
+__global__ void pool_bounds_kernel(int in_size, int out_size, int* starts, int* ends) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_size) return;
+  starts[i] = pxr::pool_start(i, in_size, out_size);
+  ends[i] = pxr::pool_end(i, in_size, out_size);
+}
+}  // namespace
+
+extern "C" int pxr_test_pool_bounds(int in_size, int out_size, int* starts, int* ends) {
+  if (in_size < 1 || out_size < 1 || !starts || !ends) return -1;
+  pool_bounds_kernel<<<(out_size + 255) / 256, 256>>>(in_size, out_size, starts, ends);
   return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
 }

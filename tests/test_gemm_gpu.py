@@ -162,7 +162,10 @@ def test_gemm_fused_softmax_forward_and_backward():
 
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("H,W,Cin,Cout,ks,bn", [(32, 32, 128, 128, 3, 128), (16, 16, 256, 512, 3, 128),
-                                                  (64, 64, 64, 3, 3, 16), (16, 16, 256, 256, 1, 64)])
+                                                  (64, 64, 64, 3, 3, 16), (16, 16, 256, 256, 1, 64),
+                                                  # ragged widths / heights (pixray's preset latents: 9x9, 18x18, 6x12 ...)
+                                                  (9, 9, 128, 128, 3, 128), (18, 26, 64, 128, 3, 64), (6, 12, 128, 64, 3, 64),
+                                                  (4, 4, 64, 64, 3, 64), (27, 27, 64, 64, 1, 64), (13, 24, 128, 3, 3, 16)])
 def test_conv_implicit_gemm(H, W, Cin, Cout, ks, bn, cg):
     torch.manual_seed(7)
     x = _rand(1, H, W, Cin, scale=0.5)
@@ -242,7 +245,8 @@ def test_gemm_tensor_map_epilogue_batched_ragged(te, cg):
 
 
 @pytest.mark.parametrize("te,cg", [(0, 1), (-1, 1), (0, 2)])
-@pytest.mark.parametrize("H,W,Cin,Cout,bn", [(32, 32, 128, 128, 128), (16, 16, 256, 512, 64), (24, 8, 64, 64, 64)])
+@pytest.mark.parametrize("H,W,Cin,Cout,bn", [(32, 32, 128, 128, 128), (16, 16, 256, 512, 64), (24, 8, 64, 64, 64),
+                                             (9, 9, 64, 64, 64), (18, 27, 128, 128, 128), (5, 36, 64, 128, 64)])
 def test_conv_tensor_map_epilogue(H, W, Cin, Cout, bn, te, cg):
     torch.manual_seed(23)
     x = _rand(1, H, W, Cin, scale=0.5)

@@ -1,18 +1,11 @@
 """GPU checks of the host-side paths above the C ABI: the plugin objects' per-op loop (plugins.train_iteration) against
-the fused pxr_iterate on the same inputs, and api.run() end to end on the real engine.
-
-Written after the round's GPU budget was spent: NOT yet executed on a B200.  Until someone runs them once
-(PXR_RUN_UNVALIDATED=1 python -m pytest tests/test_zz_host_paths_gpu.py -m gpu) they are skipped, so an untested test cannot
-stop the validated suite; the same host code is covered on the CPU against a recording engine in tests/test_api.py."""
-import os
-
+the fused pxr_iterate on the same inputs, api.run() end to end on the real engine, and the ColorJitter pixel body as
+compiled for the device against its host instantiation."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PXR_RUN_UNVALIDATED") != "1",
-                                 reason="not yet validated on a GPU (set PXR_RUN_UNVALIDATED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_plugin_loop_matches_the_fused_iteration():
@@ -33,6 +26,7 @@ def test_plugin_loop_matches_the_fused_iteration():
     eng.reset_optimizer()
     eng.iterate(z_fused, lr, 0, params=dict(transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.3, noise_facs=facs, noise=noise,
                                             color_jitter=J), losses_out=losses)
+    g_fused = eng.debug_read("z_grad", z.shape).clone()
     # plugin objects, one call per reference method
     session = P.Session(eng)
     drawer = P.VqganDrawer(None, session)
@@ -52,15 +46,28 @@ def test_plugin_loop_matches_the_fused_iteration():
     opt.step()
     drawer.clip_z()
     assert np.abs(got - losses).max() < 1e-5
-    assert (drawer.get_z() - z_fused).abs().max().item() < 1e-6
+    # Same kernels on the same inputs -- but cutout_bwd scatters with fp32 atomics, so z.grad differs in its last bits
+    # between two runs, and Adam's FIRST step is lr * g / (|g| + eps): an element whose gradient is rounding noise around
+    # zero can flip sign and move by 2 lr.  So: the gradients agree to rounding, and the updates agree wherever the
+    # gradient is above that noise.
+    g_plugin = drawer.get_z().grad
+    g_fused = g_fused.to(g_plugin.device)
+    gmax = g_fused.abs().max().item()
+    assert (g_plugin - g_fused).abs().max().item() <= 1e-4 * gmax
+    solid = g_fused.abs() > 1e-3 * gmax
+    assert solid.float().mean().item() > 0.5
+    assert ((drawer.get_z() - z_fused).abs() * solid).max().item() < 1e-5
 
 
-def test_api_run_end_to_end_small():
+@pytest.mark.parametrize("size", [[128, 128], [144, 144]])
+def test_api_run_end_to_end_small(size):
+    """pixray.run() (pixray.py:2119-2124) on the real engine.  144 x 144 is the reference's own aspect='square',
+    scale 1 canvas (pixray.py:1864-1878): a 9 x 9 latent, i.e. the ragged conv tiles."""
     from pixray_b200 import api
-    api.run("a cat", "vqgan", size=[64, 64], clip_models="ViT-B/16", iterations=6, num_cuts=8, outdir="",
+    api.run("a cat", "vqgan", size=size, clip_models="ViT-B/16", iterations=6, num_cuts=8, outdir="",
             vector_prompts="none", b200_allow_synthetic=True, seed="3", learning_rate_drops=[50])
     img = api.get_image()
-    assert img is not None and tuple(img.shape) == (1, 3, 64, 64) and torch.isfinite(img).all()
+    assert img is not None and tuple(img.shape) == (1, 3, size[1], size[0]) and torch.isfinite(img).all()
     assert 0.0 <= float(img.min()) and float(img.max()) <= 1.0
     assert np.isfinite(api._state.losses).all() and api._state.cur_iteration == 6
 

@@ -1,4 +1,9 @@
-"""Small-config pxr_iterate + per-op path for compute-sanitizer (memcheck / racecheck / initcheck)."""
+"""Small-config pxr_iterate + per-op path for compute-sanitizer (memcheck / racecheck / initcheck):
+
+    PXR_GN_COOP=0 compute-sanitizer --tool memcheck python tools/sanitize_small.py
+
+PXR_GN_COOP=0: the single-kernel GroupNorm synchronises its blocks through a device counter and needs them co-resident,
+which the sanitizer's serialised execution does not guarantee; the three-kernel variant computes the same thing."""
 import os
 import sys
 
@@ -35,21 +40,13 @@ img_op = eng.synth(z).cpu()
 eng.make_cutouts(None, transforms=T, zoom_padding=0, fill=0.5, noise_facs=facs, noise=noise, it=0)
 eng.encode_image(0)
 g_op = eng.backward().cpu()
-from oracle import ref_path as R  # diagnostic only
-vq = R.VQModel(n_embed=1024, embed_dim=128, ch=128, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(16,), resolution=32, z_channels=128)
-vq.load_state_dict(vq_sd)
-with torch.no_grad():
-    img_ref = R.vqgan_synth(vq.eval(), z)
-print("iterate image vs oracle", (img_it - img_ref).abs().max().item(), " per-op image vs oracle", (img_op - img_ref).abs().max().item())
-d = (img_it - img_ref).abs()[0]
-print("pixels off by > 0.05 in iterate image:", (d > 0.05).sum().item(), "of", d.numel(), "; first few:", (d > 0.05).nonzero()[:8].tolist())
 img_op2 = eng.synth(z).cpu()
 print("per-op again vs per-op", (img_op2 - img_op).abs().max().item())
 zc2 = z.clone().cuda()
 torch.cuda.synchronize()
 eng.iterate(zc2, 0.05, 1, params=dict(transforms=T, zoom_padding=1, fill=0.5, noise_facs=facs, noise=noise), losses_out=losses)
 img_it2 = eng.debug_read("img", (1, 3, 32, 32)).cpu()
-print("second iterate image vs oracle", (img_it2 - img_ref).abs().max().item())
+print("second iterate image vs first", (img_it2 - img_it).abs().max().item())
 zb = eng.debug_read("z", z.shape).cpu()
 print("engine z after iterate vs z (Adam moved it by ~lr):", (zb - z).abs().max().item())
 print("losses", losses)
