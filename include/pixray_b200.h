@@ -161,6 +161,32 @@ int pxr_vdiff_set_iteration(pxr_handle h, int i);
 int pxr_vdiff_renoise(pxr_handle h, float* z, int i, const float* noise);
 
 int pxr_reset_optimizer(pxr_handle h); /* rebuild_optimisers: fresh Adam state (pixray.py:520-555, 1511) */
+
+/* train()'s control decisions on the device (checkdrop pixray.py:1090-1109; scheduled learning-rate drops, auto-stop and
+ * rebuild_optimisers 1464-1512): the optimiser step of every pxr_iterate reads the iteration's loss vector, tracks the best
+ * loss, drops the learning rate (fresh Adam at base_lr / 10^drops) at the iterations in `drops` or -- with auto_stop --
+ * when the loss has not improved for iter_drop_delay iterations, and stops updating z once max_loss_drops is exceeded.
+ * No host synchronisation: pxr_iterate's `lr` is ignored afterwards and pxr_poll_status reads the last completed
+ * iteration's record from pinned memory. */
+typedef struct {
+  int iter;            /* the iteration this record describes */
+  float loss_sum;      /* sum(lossAll) of that iteration */
+  float best_loss;     /* after the iteration (1e20 right after a rebuild) */
+  int best_iter, num_loss_drop;
+  int stopped;         /* train() would have returned False: later iterations leave z untouched */
+  int rebuilt;         /* the iteration ended with rebuild_optimisers */
+  float lr;            /* learning rate the NEXT iteration uses */
+  int n_losses;
+  float losses[64];
+} pxr_status;
+int pxr_set_schedule(pxr_handle h, float base_lr, int iter_drop_delay, int max_loss_drops, int auto_stop, const int* drops,
+                     int n_drops);
+int pxr_poll_status(pxr_handle h, pxr_status* out); /* 0 ok, 1 no consistent record yet; never blocks */
+/* args.batches (pixray.py:1464-1482): every pxr_iterate runs this many ascend_txt + backward passes with fresh
+ * engine-drawn augmentations, accumulates z.grad over them and takes ONE optimiser step */
+int pxr_set_batches(pxr_handle h, int batches);
+/* hand pxr_step the gradient to apply (device [z_numel]); the per-op plugin loop accumulates several passes itself */
+int pxr_set_z_grad(pxr_handle h, const float* z_grad);
 int pxr_sync(pxr_handle h);
 
 /* Introspection used by tests and bench.py */
@@ -168,6 +194,9 @@ int pxr_num_kernel_launches(pxr_handle h, int64_t* out); /* launches issued sinc
 /* one iteration with CUDA events around every launch: out6 = {gemm ms, gemm launches, gemm algorithmic FLOPs,
  * other ms, other launches, whole-iteration ms}; feeds bench.py's roofline object */
 int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* out6);
+/* the same, plus the compulsory (algorithmic) bytes of the tensor-core launches: each operand read once, each epilogue
+ * tensor read / written once -- the denominator against which measured DRAM traffic shows wasted re-reads */
+int pxr_profile_iteration2(pxr_handle h, float* z, float lr, int iter, double* out6, double* tensor_bytes);
 int pxr_get_stream(pxr_handle h, void** out);
 int pxr_z_numel(pxr_handle h, int64_t* out);
 int pxr_z_bounds(pxr_handle h, float* zmin, float* zmax); /* device [z_channels]: codebook per-channel min/max */

@@ -38,6 +38,12 @@ class CutParams(C.Structure):
                 ("noise_facs", C.c_void_p), ("noise", C.c_void_p), ("color_jitter", C.c_void_p)]
 
 
+class Status(C.Structure):
+    _fields_ = [("iter", C.c_int), ("loss_sum", C.c_float), ("best_loss", C.c_float), ("best_iter", C.c_int),
+                ("num_loss_drop", C.c_int), ("stopped", C.c_int), ("rebuilt", C.c_int), ("lr", C.c_float),
+                ("n_losses", C.c_int), ("losses", C.c_float * 64)]
+
+
 class TestGemmDesc(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_mode", C.c_int),
@@ -61,9 +67,9 @@ EXPORTS = [
     "pxr_last_error", "pxr_version", "pxr_create", "pxr_destroy", "pxr_load_weight", "pxr_finalize",
     "pxr_set_prompts", "pxr_set_comm", "pxr_get_unique_id", "pxr_synth", "pxr_make_cutouts", "pxr_encode_image",
     "pxr_prompt_loss", "pxr_backward", "pxr_step", "pxr_iterate", "pxr_reset_optimizer", "pxr_sync",
-    "pxr_num_kernel_launches", "pxr_get_stream", "pxr_z_numel", "pxr_z_bounds", "pxr_test_gemm", "pxr_test_conv", "pxr_debug_read", "pxr_profile_iteration",
+    "pxr_num_kernel_launches", "pxr_get_stream", "pxr_z_numel", "pxr_z_bounds", "pxr_test_gemm", "pxr_test_conv", "pxr_debug_read", "pxr_profile_iteration", "pxr_profile_iteration2",
     "pxr_test_attention", "pxr_test_color_jitter_host", "pxr_test_color_jitter_device", "pxr_set_color_jitter", "pxr_set_image_prompts", "pxr_add_aux_loss", "pxr_clear_aux_losses", "pxr_num_losses", "pxr_read_losses",
-    "pxr_test_pool_bounds", "pxr_vdiff_set_schedule", "pxr_vdiff_set_clip_embed", "pxr_vdiff_set_iteration", "pxr_vdiff_renoise",
+    "pxr_test_pool_bounds", "pxr_set_schedule", "pxr_poll_status", "pxr_set_batches", "pxr_set_z_grad", "pxr_vdiff_set_schedule", "pxr_vdiff_set_clip_embed", "pxr_vdiff_set_iteration", "pxr_vdiff_renoise",
 ]
 
 _lib = None

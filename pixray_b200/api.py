@@ -93,7 +93,13 @@ _OPTIONS = [
     (("--output",), "output", str, "output.png"), (("--outdir",), "outdir", str, "outputs/%DATE%_%SEQ%"),
 ]
 _ENGINE_OPTIONS = [(("--b200_weights",), "b200_weights", None, None), (("--b200_text_encoder",), "b200_text_encoder", None, None),
-                   (("--b200_allow_synthetic",), "b200_allow_synthetic", str2bool, False)]
+                   (("--b200_allow_synthetic",), "b200_allow_synthetic", str2bool, False),
+                   # checkdrop / learning-rate drops / auto-stop decided on the device, no per-iteration host sync
+                   # (pxr_set_schedule); False keeps the reference's host-side control flow (one loss readback per iteration)
+                   (("--b200_device_checkdrop",), "b200_device_checkdrop", str2bool, True),
+                   # cutout-sharded multi-GPU run (one process per GPU, torch.distributed already initialised by the
+                   # launcher): this process is rank b200_rank of b200_world and drives cuda:<LOCAL_RANK>
+                   (("--b200_rank",), "b200_rank", int, 0), (("--b200_world",), "b200_world", int, 1)]
 
 # options that leave the hot path: dest -> the value(s) that keep them off
 _OFF_PATH = {
@@ -242,7 +248,7 @@ def process_args(vq_parser, namespace):
 # ------------------------------------------------------------------------------------------------ session state
 _state = SimpleNamespace(engine=None, session=None, drawer=None, perceptors=[], make_cutouts=None, lr=0.0,
                          cur_iteration=0, best_loss=1e20, best_iter=0, num_loss_drop=0, max_loss_drops=0,
-                         iter_drop_delay=12, losses=None, loss_buf=None, seed=None, custom=[])
+                         iter_drop_delay=12, losses=None, loss_buf=None, seed=None, custom=[], managed=False, stop_iter=None)
 
 
 def _seed_everything(args):
@@ -306,9 +312,6 @@ def _side(args, num_resolutions):
 def do_init(args):
     """pixray.py:569-1020 for the hot path: engine + drawer + perceptors + cutouts + prompts + losses + optimiser."""
     st = _state
-    if args.batches != 1:
-        raise NotImplementedError("batches > 1 (gradient accumulation over several cutout draws) is not built; "
-                                  "raise num_cuts instead -- the engine holds all cutouts of an iteration at once")
     for m in args.clip_models:
         if m not in E.CLIP_ARCH:
             raise NotImplementedError(f"perceptor '{m}': only the ViT image towers {sorted(E.CLIP_ARCH)} are built")
@@ -324,6 +327,9 @@ def do_init(args):
     device = int(str(args.cuda_device).split(":")[1]) if ":" in str(args.cuda_device) else 0
     clip_cfgs = [E.CLIP_ARCH[m] for m in args.clip_models]
     kw = dict(drawer=kind, image_hw=(sideY, sideX), cutn=args.num_cuts, clip=clip_cfgs, seed=st.seed, device=device)
+    world = int(getattr(args, "b200_world", 1) or 1)
+    if world > 1:
+        kw.update(rank=int(args.b200_rank), world=world)
     if kind == E.DRAWER_PIXEL:
         ps = getattr(args, "pixel_size", None)
         kw["grid"] = (ps[1], ps[0]) if ps else (sideY, sideX)
@@ -337,13 +343,18 @@ def do_init(args):
             vq_sd = _load_state_dict(weights[key])
         elif kind == E.DRAWER_VQGAN:
             vq_sd = S.vqgan_state_dict(E.VQGAN_F16_16384, 0)
+        elif args.b200_allow_synthetic:
+            vq_sd = S.vdiff_state_dict(0)
         else:
-            raise ValueError("the vdiff drawer needs b200_weights['vdiff'] (the cc12m_1 checkpoint's state_dict)")
+            raise ValueError("the vdiff drawer needs b200_weights['vdiff'] (the cc12m_1 checkpoint's state_dict), or "
+                             "b200_allow_synthetic=True for seeded random weights")
         eng.load_module(E.MOD_VQGAN, vq_sd)
     for i, m in enumerate(args.clip_models):
         sd = _load_state_dict(weights[m]) if m in weights else S.clip_state_dict(E.CLIP_ARCH[m], 1 + i)
         eng.load_module(E.MOD_CLIP0 + i, sd)
     eng.finalize()
+    if world > 1:
+        eng.init_comm()
     st.engine, st.session = eng, P.Session(eng)
     drawer = class_table[args.drawer](args, st.session)
     drawer.load_model(args, eng.device)
@@ -415,7 +426,15 @@ def do_init(args):
     st.max_loss_drops, st.iter_drop_delay = len(args.learning_rate_drops), 12
     st.loss_buf = np.zeros(eng.num_losses(), dtype=np.float32)
     st.losses = None
+    if args.batches != 1:
+        eng.set_batches(args.batches)  # pixray.py:1464-1482: gradient accumulation over several cutout draws
     rebuild_optimisers(args)
+    # train()'s control decisions move to the device when the engine can take them (everything but vdiff, whose loop
+    # rebuilds Adam with a scheduled rate every iteration on the host, pixray.py:1489-1495)
+    st.managed = bool(getattr(args, "b200_device_checkdrop", True)) and hasattr(eng, "set_schedule") and kind != E.DRAWER_VDIFF
+    if st.managed:
+        eng.set_schedule(st.lr, st.iter_drop_delay, st.max_loss_drops, bool(args.auto_stop), list(args.learning_rate_drops)[:16])
+        st.stop_iter = None
     return args
 
 
@@ -453,8 +472,14 @@ def checkdrop(args, it, losses):
 
 def train(args, cur_it):
     """pixray.py:1436-1512.  The whole iteration (synth -> cutouts -> encode -> losses -> backward -> Adam -> clip_z) is
-    ONE pxr_iterate call; the loss vector comes back every iteration because checkdrop consumes it (pixray.py:1466)."""
+    ONE pxr_iterate call.  Default: checkdrop, the scheduled learning-rate drops and auto-stop are decided inside that
+    call on the device (pxr_set_schedule) and the host only POLLS a pinned status record -- no synchronisation in the
+    loop; iterations enqueued after the device raised `stopped` leave z untouched, so the result equals the reference's
+    control flow.  With b200_device_checkdrop=False (and for vdiff) the reference's host-side flow runs as written, one
+    loss readback per iteration."""
     st = _state
+    if getattr(st, "managed", False):
+        return _train_managed(args, cur_it)
     rebuild = False
     if cur_it < args.iterations:
         if apply_overlay(args, cur_it):
@@ -486,6 +511,42 @@ def train(args, cur_it):
             return False
         st.best_iter, st.best_loss = cur_it, 1e20
         rebuild_optimisers(args)
+    return True
+
+
+def _absorb_status(rec):
+    st = _state
+    st.losses = rec["losses"]
+    st.best_loss, st.best_iter, st.num_loss_drop, st.lr = rec["best_loss"], rec["best_iter"], rec["num_loss_drop"], rec["lr"]
+    if rec["stopped"] and st.stop_iter is None:
+        st.stop_iter = rec["iter"]
+
+
+def _train_managed(args, cur_it):
+    st = _state
+    if cur_it < args.iterations:
+        if apply_overlay(args, cur_it):
+            raise NotImplementedError("overlays re-encode through the VQGAN encoder (pixray.py:1408-1420)")
+        st.session.begin_iteration(cur_it)
+        if cur_it in args.learning_rate_drops:
+            print("Dropping learning rate")
+        st.engine.iterate(st.drawer.get_z(), st.lr, cur_it, params=None, losses_out=None)
+        rec = st.engine.poll_status()  # the last COMPLETED iteration (lags the launch by the queue depth): no sync
+        if rec is not None:
+            _absorb_status(rec)
+            if st.stop_iter is not None:
+                # train() returned False at stop_iter; what was enqueued since did not move z.  Rewind the counter to
+                # that call (do_run then counts it like the reference does).
+                st.engine.sync()
+                st.cur_iteration = st.stop_iter
+                return False
+    if cur_it == args.iterations:
+        st.engine.sync()
+        rec = st.engine.poll_status()
+        if rec is not None:
+            _absorb_status(rec)
+        checkin(args, cur_it, st.losses)
+        return False
     return True
 
 

@@ -8,6 +8,7 @@
 // so Q, K, V and dO are each loaded once per (image, head) and serve every product.  P / dS are written by the
 // softmax threads straight into that layout (chunk index XOR row % 8), one 128 x 64 atom per 64 key columns.
 #include "attn_tc.cuh"
+#include "launch.cuh"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 #include <cstdio>
@@ -88,6 +89,7 @@ __device__ __forceinline__ uint32_t kv_slot_bytes(int n_pad) { return (static_ca
 // TMEM: S tile mt at columns [256 mt, 256 mt + n_pad); O tile mt re-uses the first 64 columns of its S tile.
 // The next pair's Q / K are fetched as soon as both S tiles are complete, its V once both PV products are.
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t s_base = smem_u32(smem);
+  pdl_wait();  // above: parameters, shared memory, TMEM only
 
   if (warp == 0) {
     if (lane == 0) {
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 constexpr uint32_t TM_DK = 256, TM_DV = 384;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
@@ -321,6 +325,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t s_base = smem_u32(smem);
+  pdl_wait();  // above: parameters, shared memory, TMEM only
 
   if (warp == 0) {
     if (lane == 0) {
@@ -522,8 +527,305 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, version 2
+// Key-tile-outer order with ONE threads<->tensor-pipe hand-off per 128 x 128 score block (the first version above makes
+// six serial MMA <-> softmax round trips per query tile and leaves the tensor pipe idle 86 % of the time,
+// profiles/r01_ncu_attn_full_summary.txt).  For key tile jt (outer) and query tile mt (inner):
+//     phase 1 (tensor):  S  = Q_mt K_jt^T          dP = dO_mt V_jt^T                       -> TMEM
+//     threads         :  P  = exp2(S sc - lse)     dS = scale P (dP - D)                   -> shared memory (fp16 operands)
+//     phase 2 (tensor):  dV_jt += P^T dO_mt        dK_jt += dS^T Q_mt      dQ_mt += dS K_jt
+// S and dP sit side by side in TMEM, so the threads produce P and dS in one pass over both.  The MMA thread issues
+// phase 1 of block n+1 BEFORE phase 2 of block n (the S / dP columns are free as soon as the threads have loaded block
+// n into registers), so while the threads work on block n+1 the tensor pipe runs phase 2 of block n: one hand-off each
+// way per block, software-pipelined inside an (image, head) item.
+// smem: Q 32 KiB | dO 32 KiB | K | V (n_pad rows each) | P 32 KiB | dS 32 KiB | barriers | D exchange.
+// TMEM: S [0,128) | dP [128,256) | dQ tile 0 / 1 [256,320) [320,384) | dK_jt [384,448) | dV_jt [448,512).
+constexpr uint32_t T2_S = 0, T2_DP = 128, T2_DQ = 256, T2_DK = 384, T2_DV = 448;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd2_kernel(const __grid_constant__ AttnParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
+  const int n_mt = p.n_mt, n_pad = p.n_pad, T = p.T;
+  const uint32_t kvb = kv_slot_bytes(n_pad);
+  const uint32_t B_Q = 0, B_DO = 32 * KiB, B_K = 64 * KiB, B_V = B_K + kvb, B_P = B_V + kvb, B_DS = B_P + 32 * KiB,
+                 B_BAR = B_DS + 32 * KiB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BAR);
+  uint64_t* bar_load = bars;      // per item: Q, dO, K, V landed
+  uint64_t* bar_p1 = bars + 1;    // per block: S and dP complete
+  uint64_t* bar_free = bars + 2;  // per block: every warp has loaded its S / dP columns (16 warps)
+  uint64_t* bar_pds = bars + 3;   // per block: P and dS written (16 warps)
+  uint64_t* bar_p2 = bars + 4;    // per block: dV / dK / dQ products complete (P / dS consumed, accumulators current)
+  uint64_t* bar_smem = bars + 5;  // per item: every product has consumed Q / dO / K / V
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xd = reinterpret_cast<float*>(smem + B_BAR + 256);  // [2 query tiles][4 channel quarters][128 rows] partial D
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tm_q);
+    prefetch_tmap(&p.tm_kv);
+    prefetch_tmap(&p.tm_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_p1, 1);
+    mbar_init(bar_free, ATT_EPI_WARPS);
+    mbar_init(bar_pds, ATT_EPI_WARPS);
+    mbar_init(bar_p2, 1);
+    mbar_init(bar_smem, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t s_base = smem_u32(smem);
+  pdl_wait();  // above: parameters, shared memory, TMEM only
+  const int n_blocks = n_mt * n_mt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = 2u * static_cast<uint32_t>(n_mt) * ATOM + 2u * static_cast<uint32_t>(n_pad) * 128u;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item % p.H;
+        if (it > 0) mbar_wait(bar_smem, (it - 1) & 1);
+        mbar_arrive_expect_tx(bar_load, bytes);
+        for (int mt = 0; mt < n_mt; ++mt) {
+          tma_load_4d(&p.tm_q, bar_load, smem + B_Q + mt * ATOM, h * 64, mt * 128, b, 0);
+          tma_load_4d(&p.tm_do, bar_load, smem + B_DO + mt * ATOM, h * 64, mt * 128, b, 0);
+        }
+        tma_load_4d(&p.tm_kv, bar_load, smem + B_K, p.W + h * 64, 0, b, 0);
+        tma_load_4d(&p.tm_kv, bar_load, smem + B_V, 2 * p.W + h * 64, 0, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_dq = make_idesc_f16(128, 64, 0, 0, 1);  // dQ = dS K: A K-major, B MN-major
+      const uint32_t id_t = make_idesc_f16(128, 64, 0, 1, 1);   // dV = P^T dO, dK = dS^T Q: both MN-major
+      constexpr uint64_t AT = ATOM >> 4;
+      const uint64_t dk_q = desc_k(s_base + B_Q), dk_k = desc_k(s_base + B_K), dk_v = desc_k(s_base + B_V),
+                     dk_do = desc_k(s_base + B_DO), dk_ds = desc_k(s_base + B_DS);
+      const uint64_t dm_p = desc_mn(s_base + B_P, ATOM), dm_ds = desc_mn(s_base + B_DS, ATOM),
+                     dm_do = desc_mn(s_base + B_DO, 8192), dm_q = desc_mn(s_base + B_Q, 8192),
+                     dm_k = desc_mn(s_base + B_K, 8192);
+      int it = 0, cnt = 0;  // cnt: blocks issued so far (all items) = parity source of the per-block barriers
+      auto phase2 = [&](int jt, int mt, int nk) {
+        const int rows_left = T - mt * 128;
+        const int ksi = rows_left >= 128 ? 8 : (rows_left + 15) / 16;  // 16-row reduction steps over this tile's queries
+#pragma unroll 4
+        for (int ks = 0; ks < ksi; ++ks)
+          umma_f16(tmem_base + T2_DV, dm_p + ks * 128, dm_do + mt * AT + ks * 128, id_t, (mt | ks) ? 1u : 0u);
+#pragma unroll 4
+        for (int ks = 0; ks < ksi; ++ks)
+          umma_f16(tmem_base + T2_DK, dm_ds + ks * 128, dm_q + mt * AT + ks * 128, id_t, (mt | ks) ? 1u : 0u);
+        const int n_k = nk / 16;
+#pragma unroll 4
+        for (int k = 0; k < n_k; ++k)
+          umma_f16(tmem_base + T2_DQ + mt * 64, dk_ds + (k >> 2) * AT + (k & 3) * 2, dm_k + (jt * 8 + k) * 128, id_dq,
+                   (jt | k) ? 1u : 0u);
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        mbar_wait(bar_load, it & 1);
+        tc_fence_after();
+        int pj = 0, pm = 0, pnk = 0;  // the block whose phase 2 is pending
+        for (int n = 0; n < n_blocks; ++n, ++cnt) {
+          const int jt = n / n_mt, mt = n % n_mt;
+          const int nk = min(128, n_pad - jt * 128);
+          if (cnt > 0) {  // S / dP columns: every warp has loaded the previous block into registers
+            mbar_wait(bar_free, (cnt - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t id_s = make_idesc_f16(128, nk, 0, 0, 0);  // S, dP: both operands K-major
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + T2_S, dk_q + mt * AT + 2 * k, dk_k + jt * AT + 2 * k, id_s, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + T2_DP, dk_do + mt * AT + 2 * k, dk_v + jt * AT + 2 * k, id_s, k ? 1u : 0u);
+          umma_commit(bar_p1);
+          if (n > 0) {
+            mbar_wait(bar_pds, (cnt - 1) & 1);
+            tc_fence_after();
+            phase2(pj, pm, pnk);
+            umma_commit(bar_p2);
+          }
+          pj = jt;
+          pm = mt;
+          pnk = nk;
+        }
+        // drain at the item boundary: the next item's operands can only be fetched once these products have run
+        mbar_wait(bar_pds, (cnt - 1) & 1);
+        tc_fence_after();
+        phase2(pj, pm, pnk);
+        umma_commit(bar_p2);
+        umma_commit(bar_smem);
+      }
+    }
+  } else {
+    const int q = warp & 3, cq = (warp - 2) >> 2;  // lane quarter; which of its four warps (32-column slice cq of a block)
+    const int row = q * 32 + lane;
+    const float sc = p.scale * LOG2E;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* pbuf = smem + B_P;
+    uint8_t* dsbuf = smem + B_DS;
+    int it = 0, cnt = 0;
+    int pb = 0, ph = 0;  // (image, head) of the previous item: its dQ leaves after its last block's phase 2
+    // dK / dV rows of key tile jt (this warp: dK for cq 0, 1 / dV for cq 2, 3; 32 of the 64 channels) and, after an
+    // item's last block, its dQ rows (16 of the 64 channels of both query tiles).  Call after bar_p2 of that block.
+    auto read_out = [&](int b, int h, int jt, bool item_done) {
+      tc_fence_after();
+      {
+        const int which = cq >> 1, half = cq & 1;
+        const int j = jt * 128 + row;
+        uint32_t a0[16], a1[16];
+        tmem_ld_x16(lane_addr + (which ? T2_DV : T2_DK) + half * 32, a0);
+        tmem_ld_x16(lane_addr + (which ? T2_DV : T2_DK) + half * 32 + 16, a1);
+        tmem_ld_wait();
+        if (j < T) {
+          uint4* dst = reinterpret_cast<uint4*>(p.gqkv + (static_cast<size_t>(b) * T + j) * 3 * p.W + (which + 1) * p.W + h * 64 + half * 32);
+          dst[0] = pack8h_acc(a0, 1.f);
+          dst[1] = pack8h_acc(a0 + 8, 1.f);
+          dst[2] = pack8h_acc(a1, 1.f);
+          dst[3] = pack8h_acc(a1 + 8, 1.f);
+        }
+      }
+      if (item_done) {
+        for (int mt = 0; mt < n_mt; ++mt) {
+          const int i = mt * 128 + row;
+          uint32_t u[16];
+          tmem_ld_x16(lane_addr + T2_DQ + mt * 64 + cq * 16, u);
+          tmem_ld_wait();
+          if (i < T) {
+            uint4* dst = reinterpret_cast<uint4*>(p.gqkv + (static_cast<size_t>(b) * T + i) * 3 * p.W + h * 64 + cq * 16);
+            dst[0] = pack8h_acc(u, 1.f);
+            dst[1] = pack8h_acc(u + 8, 1.f);
+          }
+        }
+      }
+      tc_fence_before();
+    };
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int b = item / p.H, h = item % p.H;
+      mbar_wait(bar_load, it & 1);
+      // D_i = dO_i . O_i and the row log-sum-exp for both query tiles (each of the quarter's four warps: 16 channels)
+      float Dv0 = 0.f, Dv1 = 0.f, lse2_0 = 3.0e38f, lse2_1 = 3.0e38f;  // invalid rows: exp2(x - huge) = 0
+      for (int mt = 0; mt < n_mt; ++mt) {
+        const int i = mt * 128 + row;
+        float dpart = 0.f;
+        if (i < T) {
+          const float l2 = p.lse[(static_cast<size_t>(b) * p.H + h) * T + i] * LOG2E;
+          if (mt == 0) lse2_0 = l2;
+          else lse2_1 = l2;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.o + (static_cast<size_t>(b) * T + i) * p.W + h * 64);
+          const uint8_t* drow = smem + B_DO + mt * ATOM;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float a[8], g[8];
+            unpack8h(__ldg(orow + 2 * cq + c), a);
+            unpack8h(*reinterpret_cast<const uint4*>(drow + op_off(row, 8 * (2 * cq + c))), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dpart += a[j] * g[j];
+          }
+        }
+        xd[(mt * 4 + cq) * 128 + row] = dpart;
+      }
+      named_bar_sync(1 + q, 128);
+      Dv0 = (xd[0 * 128 + row] + xd[1 * 128 + row]) + (xd[2 * 128 + row] + xd[3 * 128 + row]);
+      if (n_mt > 1) Dv1 = (xd[4 * 128 + row] + xd[5 * 128 + row]) + (xd[6 * 128 + row] + xd[7 * 128 + row]);
+      // the next item's partials overwrite xd: its writers are ordered behind these reads by the per-block mbarrier
+      // chain anyway, but a second barrier makes the exchange self-contained (and visible to compute-sanitizer)
+      named_bar_sync(1 + q, 128);
+      for (int n = 0; n < n_blocks; ++n, ++cnt) {
+        const int jt = n / n_mt, mt = n % n_mt;
+        const int nk = min(128, n_pad - jt * 128);
+        const int c_lo = cq * 32;
+        const int ncol = max(0, min(32, nk - c_lo));  // this warp's columns of the block: 32, 16 or 0
+        mbar_wait(bar_p1, cnt & 1);
+        tc_fence_after();
+        // Two steps keep the live registers under the 96 a 576-thread block gets: S -> P (packed fp16), then dP -> dS.
+        // Freeing the S / dP columns a little later costs nothing: the tensor pipe is still busy with the previous
+        // block's phase 2 when phase 1 of the next block is issued.
+        uint4 pv[4], dv[4];
+        const float lz = mt ? lse2_1 : lse2_0, Dm = mt ? Dv1 : Dv0;
+        const int key0 = jt * 128 + c_lo;
+        {
+          uint32_t s0[16], s1[16];
+          if (ncol > 0) tmem_ld_x16(lane_addr + T2_S + c_lo, s0);
+          if (ncol > 16) tmem_ld_x16(lane_addr + T2_S + c_lo + 16, s1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 8 * g + j;
+              float x = ex2_approx(fmaf(__uint_as_float(g < 2 ? s0[c & 15] : s1[c & 15]), sc, -lz));
+              if (key0 + c >= T || c >= ncol) x = 0.f;
+              e[j] = x;
+            }
+            pv[g] = pack8h(e);
+          }
+        }
+        {
+          uint32_t d0[16], d1[16];
+          if (ncol > 0) tmem_ld_x16(lane_addr + T2_DP + c_lo, d0);
+          if (ncol > 16) tmem_ld_x16(lane_addr + T2_DP + c_lo + 16, d1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8], f[8];
+            unpack8h(pv[g], e);  // dS from the fp16-rounded P: the value the dV product multiplies
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 8 * g + j;
+              const float dpv = __uint_as_float(g < 2 ? d0[c & 15] : d1[c & 15]);
+              f[j] = (c < ncol) ? p.scale * e[j] * (dpv - Dm) : 0.f;
+            }
+            dv[g] = pack8h(f);
+          }
+        }
+        // the previous block's products have consumed P / dS (and its accumulators are current)
+        if (cnt > 0) {
+          mbar_wait(bar_p2, (cnt - 1) & 1);
+          if (n == 0) read_out(pb, ph, n_mt - 1, true);            // previous item: last key tile + its dQ
+          else if (mt == 0) read_out(b, h, jt - 1, false);         // previous key tile of this item is complete
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (8 * g < ncol) {
+            *reinterpret_cast<uint4*>(pbuf + op_off(row, c_lo + 8 * g)) = pv[g];
+            *reinterpret_cast<uint4*>(dsbuf + op_off(row, c_lo + 8 * g)) = dv[g];
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pds);
+      }
+      pb = b;
+      ph = h;
+    }
+    if (cnt > 0) {  // the last item's last key tile and its dQ
+      mbar_wait(bar_p2, (cnt - 1) & 1);
+      read_out(pb, ph, n_mt - 1, true);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int fwd_smem_bytes(int n_pad) { return 32 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 128 * 1024 + 256 + 4096 + 1024; }
 int bwd_smem_bytes(int n_pad) { return 64 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 64 * 1024 + 256 + 2048 + 1024; }
+int bwd2_smem_bytes(int n_pad) { return 64 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 64 * 1024 + 256 + 4096 + 1024; }
 
 }  // namespace
 
@@ -564,22 +866,33 @@ int attn_plan_make(AttnPlan* plan, const __half* qkv, __half* o, const __half* d
   plan->grid = p.items < num_sms ? p.items : num_sms;
   plan->smem_fwd = fwd_smem_bytes(p.n_pad);
   plan->smem_bwd = bwd_smem_bytes(p.n_pad);
+  plan->smem_bwd2 = bwd2_smem_bytes(p.n_pad);
   const double tt = (double)T * T * 64 * 2 * p.items;
   plan->flops_fwd = 2 * tt;  // QK^T, PV
   plan->flops_bwd = 4 * tt;  // dP, dQ, dK, dV (the recomputed S is not algorithmic work)
+  const double mw = (double)B * T * W * 2.0;  // one [B*T, W] fp16 tensor
+  plan->bytes_fwd = 3 * mw + mw + 4.0 * B * H * T;
+  plan->bytes_bwd = 3 * mw + mw + mw + 3 * mw + 4.0 * B * H * T;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem_bytes(240));
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(240));
+    cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2_smem_bytes(240));
   });
   return 0;
 }
 
 void attn_forward_launch(const AttnPlan& plan, cudaStream_t st) {
-  attn_fwd_kernel<<<plan.grid, ATT_THREADS, plan.smem_fwd, st>>>(plan.p);
+  launch_pdl(attn_fwd_kernel, dim3(plan.grid), dim3(ATT_THREADS), plan.smem_fwd, st, plan.p);
 }
+// PXR_ATTN_BWD=1 selects the first backward kernel (six hand-offs per query tile) for A/B measurements
 void attn_backward_launch(const AttnPlan& plan, cudaStream_t st) {
-  attn_bwd_kernel<<<plan.grid, ATT_THREADS, plan.smem_bwd, st>>>(plan.p);
+  static const bool v1 = [] {
+    const char* e = getenv("PXR_ATTN_BWD");
+    return e && atoi(e) == 1;
+  }();
+  if (v1) launch_pdl(attn_bwd_kernel, dim3(plan.grid), dim3(ATT_THREADS), plan.smem_bwd, st, plan.p);
+  else launch_pdl(attn_bwd2_kernel, dim3(plan.grid), dim3(ATT_THREADS), plan.smem_bwd2, st, plan.p);
 }
 
 }  // namespace pxr

@@ -29,8 +29,9 @@ struct AttnParams {
 struct AttnPlan {
   AttnParams p;
   int grid = 0;
-  int smem_fwd = 0, smem_bwd = 0;
+  int smem_fwd = 0, smem_bwd = 0, smem_bwd2 = 0;
   double flops_fwd = 0, flops_bwd = 0;
+  double bytes_fwd = 0, bytes_bwd = 0;  // compulsory traffic: qkv in, o out (+ lse) / qkv, o, dO in, dqkv out
 };
 
 // true when the fused kernels cover this shape (head width 64, T <= 256, 16-byte aligned rows)

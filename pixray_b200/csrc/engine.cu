@@ -11,6 +11,7 @@
 #include "attn_tc.cuh"
 #include "transforms.h"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -49,6 +50,18 @@ class Engine {
   float* z_grad = nullptr;
   float *adam_m = nullptr, *adam_v = nullptr;
   int adam_t = 0;
+  // device-side checkdrop / learning-rate drops / auto-stop (kernels.cuh): off until pxr_set_schedule
+  bool managed = false;
+  DropConfig drop_cfg{};
+  DropState* drop_state = nullptr;        // [2], double-buffered on the device
+  DropStatus* drop_status = nullptr;      // pinned, mapped
+  DropStatus* drop_status_dev = nullptr;  // its device address
+  float* best_z = nullptr;
+  int drop_parity = 0;
+  // gradient accumulation over the `batches` passes of one iteration (pixray.py:1464-1482)
+  int batches = 1;
+  float* z_grad_acc = nullptr;
+  int rng_iter = 0;  // key of the engine-drawn cutout parameters: iteration, and pass within the iteration
   int64_t z_numel = 0;
   float *zmin = nullptr, *zmax = nullptr;  // [z_channels]
   float *img = nullptr, *img_pre = nullptr, *g_img = nullptr;  // [3,H,W]
@@ -105,6 +118,7 @@ class Engine {
   };
   Clip clip[2];
   float* losses_dev = nullptr;   // [total prompts]
+  float* losses_scratch = nullptr;  // loss vector of the passes b > 0 of an iteration (batches > 1)
   float* losses_host = nullptr;  // pinned
   int total_prompts = 0;
   // image prompts (pixray.py:1308-1336): target images, cut + encoded every iteration with the cached transforms
@@ -198,6 +212,7 @@ class Engine {
   struct ProfRec {
     cudaEvent_t a, b;
     double flops;
+    double bytes;
     int launches;
     std::string name;
   };
@@ -207,11 +222,19 @@ class Engine {
     PXR_CUDA(cudaEventCreate(&r.b));
     PXR_CUDA(cudaEventRecord(r.a, st));
   }
+  bool trace = false;  // PXR_TRACE=1: print every op before it runs and synchronise after it (localises a hanging kernel)
   void run(OpList& l) {
     for (size_t i = 0; i < l.ops.size(); ++i) {
-      if (profiling) {
+      if (trace) {
+        fprintf(stderr, "[pxr op] %s\n", l.names[i].empty() ? "(unnamed)" : l.names[i].c_str());
+        fflush(stderr);
+        l.ops[i]();
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) throw EngineError(-202, std::string("op '") + l.names[i] + "' failed: " + cudaGetErrorString(e));
+      } else if (profiling) {
         ProfRec r;
         r.flops = l.flops[i];
+        r.bytes = l.bytes[i];
         r.launches = l.launches[i];
         r.name = l.names[i];
         prof_begin(r);
@@ -285,7 +308,7 @@ class Engine {
     int rc = gemm_plan_make(plan.get(), A, B, M, N, K, e, bn, fmt, num_sms, buf, sizeof buf);
     if (rc) throw EngineError(rc, std::string("gemm plan: ") + buf);
     cudaStream_t s = st;
-    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label("gemm", *plan, A.mode, B.mode, e));
+    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label("gemm", *plan, A.mode, B.mode, e), plan->bytes);
   }
   static std::string gemm_label(const char* kind, const GemmPlan& p, int am, int bm, const GemmEpilogue& e) {
     char b[256];
@@ -340,13 +363,13 @@ class Engine {
       l.add(2, [=] {
         gemm_launch(*plan, s);
         splitk_reduce(ws, plan->p.k_splits, px, n_out, n_out, bias, res, out, ld_out, s);
-      }, plan->flops, label);
+      }, plan->flops, label, plan->bytes);
       return;
     }
     int rc = conv_plan_make(plan.get(), in, cin, 1, H, Wd, cin, wt, cout_pad, n_out, ks, e, bn, fmt, num_sms, buf,
                             sizeof buf);
     if (rc) throw EngineError(rc, std::string("conv plan: ") + buf);
-    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e));
+    l.add(1, [plan, s] { gemm_launch(*plan, s); }, plan->flops, gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e), plan->bytes);
   }
 
   // Split-K for a plain K-major GEMM with few output tiles and a long reduction (the vdiff U-Net's 4x4 ... 1x1 levels:
@@ -388,7 +411,7 @@ class Engine {
     l.add(2, [=] {
       gemm_launch(*plan, s);
       splitk_reduce(ws, plan->p.k_splits, M, N, N, bias, res, out, ld_out, s);
-    }, plan->flops, label);
+    }, plan->flops, label, plan->bytes);
   }
 
   // ------------------------------------------------------------------ build steps
@@ -463,6 +486,8 @@ class Engine {
   void loss_clip(int i);
   void backward_all();
   void step(float lr);
+  void step_managed(int iter);
+  void write_initial_drop_state();
 };
 
 Engine::~Engine() {
@@ -476,6 +501,7 @@ Engine::~Engine() {
     if (ring_ev[i]) cudaEventDestroy(ring_ev[i]);
   }
   if (losses_host) cudaFreeHost(losses_host);
+  if (drop_status) cudaFreeHost(const_cast<DropStatus*>(drop_status));
   if (st) cudaStreamDestroy(st);
 }
 
@@ -501,6 +527,7 @@ void Engine::create() {
   if (const char* fa = getenv("PXR_FUSED_ATTN")) fused_attn = atoi(fa) != 0;
   if (const char* gc = getenv("PXR_GN_COOP")) gn_coop = atoi(gc) != 0;
   if (const char* sk = getenv("PXR_CONV_SPLITK")) conv_splitk = atoi(sk) != 0;
+  if (const char* tr = getenv("PXR_TRACE")) trace = atoi(tr) != 0;
   if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
   if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
   if (cfg.adam_eps <= 0) cfg.adam_eps = 1e-8f;
@@ -1010,6 +1037,9 @@ void Engine::build_cutouts() {
 // kernel uses (kornia warp_perspective inverts the normalised homography; with align_corners=True the
 // normalisations cancel and src_pix = M^-1 dst_pix), stage them through pinned memory.
 void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
+  // engine-drawn parameters are keyed by (seed, rng_iter): pass b > 0 of an iteration (batches > 1) draws a fresh set,
+  // like a second ascend_txt call does, while the padding mode still follows the iteration's parity (pixray.py:1250)
+  const int key = rng_iter ? rng_iter : iter;
   const int slot = ring_pos;
   ring_pos = (ring_pos + 1) % RING;
   PXR_CUDA(cudaEventSynchronize(ring_ev[slot]));
@@ -1019,9 +1049,9 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
   float fill = p ? p->fill : 0.f;
   if (!T) {  // engine RNG, keyed by (seed, iter, global cutout index)
     gen.resize((size_t)cfg.cutn * 9);
-    sample_cutout_transforms(cfg.seed, iter, cfg.cutn, cfg.cut_size, gen.data());
+    sample_cutout_transforms(cfg.seed, key, cfg.cutn, cfg.cut_size, gen.data());
     T = gen.data();
-    if (!p) fill = sample_fill(cfg.seed, iter);
+    if (!p) fill = sample_fill(cfg.seed, key);
   }
   for (int n = 0; n < n_local; ++n) {
     double m[9], inv[9];
@@ -1034,7 +1064,7 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
   std::vector<float> genj;
   if (!J && !(p && p->transforms) && cj_p > 0.f) {
     genj.resize((size_t)cfg.cutn * 3);
-    sample_color_jitter(cfg.seed, iter, cfg.cutn, cj_p, cj_sat, cj_hue, genj.data());
+    sample_color_jitter(cfg.seed, key, cfg.cutn, cj_p, cj_sat, cj_hue, genj.data());
     J = genj.data();
   }
   float* jh = minv_host[slot] + (size_t)n_local * 9;
@@ -1044,7 +1074,7 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
   PXR_CUDA(cudaMemcpyAsync(minv_dev, minv_host[slot], sizeof(float) * n_local * (J ? 12 : 9), cudaMemcpyHostToDevice, st));
   cut_args.zoom_padding = zoom_padding;
   cut_args.fill = fill;
-  cut_args.iter = iter;
+  cut_args.iter = key;
   cut_args.noise = nullptr;
   cut_args.noise_facs = nullptr;
   if (cfg.noise_fac <= 0.f) {
@@ -1211,7 +1241,7 @@ void Engine::build_clip(int i) {
       std::shared_ptr<AttnPlan> ap = ly.attn;
       char lab[96];
       snprintf(lab, sizeof lab, "attn_fwd B=%d T=%d heads=%d", B, T, Hh);
-      C.fwd.add(1, [ap, cs] { attn_forward_launch(*ap, cs); }, ap->flops_fwd, lab);
+      C.fwd.add(1, [ap, cs] { attn_forward_launch(*ap, cs); }, ap->flops_fwd, lab, ap->bytes_fwd);
     } else {
     {  // S = scale * q k^T  (nn.MultiheadAttention scales q by d^-1/2)
       GemmEpilogue e;
@@ -1320,7 +1350,7 @@ void Engine::build_clip(int i) {
       std::shared_ptr<AttnPlan> ap = ly.attn;
       char lab[96];
       snprintf(lab, sizeof lab, "attn_bwd B=%d T=%d heads=%d", B, T, Hh);
-      C.bwd.add(1, [ap, cs] { attn_backward_launch(*ap, cs); }, ap->flops_bwd, lab);
+      C.bwd.add(1, [ap, cs] { attn_backward_launch(*ap, cs); }, ap->flops_bwd, lab, ap->bytes_bwd);
     } else {
     {  // dP = go v^T ; fused: dS = scale * P * (dP - <P, dP>)
       GemmEpilogue e;
@@ -1589,8 +1619,30 @@ void Engine::backward_all() {
 void Engine::step(float lr) {
   ++adam_t;
   const int per_channel = (cfg.drawer == PXR_DRAWER_VQGAN) ? (int)(z_numel / cfg.z_channels) : 1;
-  adam_clip_step(z_buf, adam_m, adam_v, z_grad, 1.f, (int)z_numel, per_channel, zmin, zmax,
+  adam_clip_step(z_buf, adam_m, adam_v, batches > 1 ? z_grad_acc : z_grad, 1.f, (int)z_numel, per_channel, zmin, zmax,
                  cfg.drawer == PXR_DRAWER_PIXEL, lr, cfg.beta1, cfg.beta2, cfg.adam_eps, adam_t, st);
+  launches += 1;
+}
+
+void Engine::write_initial_drop_state() {
+  DropState s0{};
+  s0.best_loss = 1e20f;
+  s0.lr = drop_cfg.base_lr;
+  PXR_CUDA(cudaMemcpyAsync(drop_state, &s0, sizeof s0, cudaMemcpyHostToDevice, st));
+  PXR_CUDA(cudaMemcpyAsync(drop_state + 1, &s0, sizeof s0, cudaMemcpyHostToDevice, st));
+  PXR_CUDA(cudaStreamSynchronize(st));  // s0 is a stack object
+  drop_parity = 0;
+  memset(const_cast<DropStatus*>(drop_status), 0, sizeof(DropStatus));
+}
+
+// opt.step() + clip_z + checkdrop + (scheduled | auto-stop) optimiser rebuild, all decided on the device
+void Engine::step_managed(int iter) {
+  const int per_channel = (cfg.drawer == PXR_DRAWER_VQGAN) ? (int)(z_numel / cfg.z_channels) : 1;
+  const float* g = batches > 1 ? z_grad_acc : z_grad;
+  adam_clip_managed(z_buf, adam_m, adam_v, g, best_z, 1.f, (int)z_numel, per_channel, zmin, zmax,
+                    cfg.drawer == PXR_DRAWER_PIXEL, cfg.beta1, cfg.beta2, cfg.adam_eps, losses_dev, num_losses(), iter,
+                    drop_cfg, drop_state + drop_parity, drop_state + (drop_parity ^ 1), drop_status_dev, st);
+  drop_parity ^= 1;
   launches += 1;
 }
 
@@ -1603,10 +1655,23 @@ void Engine::finalize() {
   else throw EngineError(-47, "unknown drawer kind");
   adam_m = dalloc<float>(z_numel);
   adam_v = dalloc<float>(z_numel);
+  z_grad_acc = dalloc<float>(z_numel);
+  best_z = dalloc<float>(z_numel);
+  drop_state = dalloc<DropState>(2);
+  {
+    void* hp = nullptr;
+    PXR_CUDA(cudaHostAlloc(&hp, sizeof(DropStatus), cudaHostAllocMapped));
+    memset(hp, 0, sizeof(DropStatus));
+    drop_status = static_cast<DropStatus*>(hp);
+    void* dp = nullptr;
+    PXR_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    drop_status_dev = static_cast<DropStatus*>(dp);
+  }
   build_cutouts();
   if (cfg.n_clip < 1 || cfg.n_clip > 2) throw EngineError(-53, "n_clip must be 1 or 2");
   for (int i = 0; i < cfg.n_clip; ++i) build_clip(i);
   losses_dev = dalloc<float>(64);
+  losses_scratch = dalloc<float>(64);
   aux_part = dalloc<double>(std::max(4 * AUX_MAX_BLOCKS, n_local) + 8);
   aux_sums = dalloc<double>(4);
   aux_A = dalloc<float>(((size_t)n_local * cfg.cut_size + 2) * cfg.cut_size);
@@ -1629,6 +1694,8 @@ void Engine::finalize() {
     reg("irange", irange, 16);
     reg("sums", sums, 16);
     reg("z_grad", z_grad, z_numel * 4);
+    reg("z_grad_acc", z_grad_acc, z_numel * 4);
+    reg("best_z", best_z, z_numel * 4);
     reg("z", z_buf, z_numel * 4);
     reg("losses", losses_dev, 64 * 4);
     if (vd_pred) {
@@ -1872,18 +1939,40 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
   PXR_TRY(h, {
     Engine* e = h->e;
     if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
-    e->prepare_cut_params(p, iter);
+    if (e->batches > 1 && p) throw EngineError(-63, "batches > 1 draws its cutout parameters in the engine: pass p = NULL");
     e->vd_iter_request = iter;
-    PXR_CUDA(cudaMemsetAsync(e->losses_dev, 0, 64 * sizeof(float), e->st));
-    e->encode_image_prompts();
-    e->forward_drawer();
-    e->forward_cutouts();
-    for (int i = 0; i < e->cfg.n_clip; ++i) {
-      e->forward_clip(i);
-      e->loss_clip(i);
+    for (int b = 0; b < e->batches; ++b) {
+      // every pass is one ascend_txt + backward (pixray.py:1464-1482): fresh augmentations, gradients accumulate in z.grad;
+      // checkdrop and the reported loss vector use the FIRST pass (`if i == 0`, pixray.py:1466)
+      e->rng_iter = b == 0 ? 0 : iter + b * (1 << 20);
+      e->prepare_cut_params(p, iter);
+      if (b == 0) PXR_CUDA(cudaMemsetAsync(e->losses_dev, 0, 64 * sizeof(float), e->st));
+      else PXR_CUDA(cudaMemsetAsync(e->losses_scratch, 0, 64 * sizeof(float), e->st));
+      float* keep = e->losses_dev;
+      if (b > 0) e->losses_dev = e->losses_scratch;  // later passes must not disturb the first pass's loss vector
+      try {
+        e->encode_image_prompts();
+        if (b == 0) e->forward_drawer();  // same z: the image of the later passes is the same image
+        e->forward_cutouts();
+        for (int i = 0; i < e->cfg.n_clip; ++i) {
+          e->forward_clip(i);
+          e->loss_clip(i);
+        }
+        e->backward_all();
+      } catch (...) {
+        e->losses_dev = keep;
+        e->rng_iter = 0;
+        throw;
+      }
+      e->losses_dev = keep;
+      if (e->batches > 1) {
+        pxr::accumulate_f32(e->z_grad, e->z_grad_acc, e->z_numel, b > 0, e->st);
+        e->launches += 1;
+      }
     }
-    e->backward_all();
-    e->step(lr);
+    e->rng_iter = 0;
+    if (e->managed) e->step_managed(iter);
+    else e->step(lr);
     if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
     if (out_losses_host) {
       PXR_CUDA(cudaMemcpyAsync(e->losses_host, e->losses_dev, 64 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
@@ -1893,10 +1982,78 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
   });
 }
 
+// train()'s control decisions on the device (checkdrop, scheduled learning-rate drops, auto-stop; pixray.py:1090-1109,
+// 1464-1512).  After this call pxr_iterate ignores its `lr` argument: the engine owns the learning rate, the Adam step
+// counter and the drop bookkeeping, and pxr_poll_status reports them without synchronising.  n_drops <= 16.
+int pxr_set_schedule(pxr_handle h, float base_lr, int iter_drop_delay, int max_loss_drops, int auto_stop, const int* drops,
+                     int n_drops) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (n_drops < 0 || n_drops > 16 || (n_drops > 0 && !drops)) throw EngineError(-64, "pxr_set_schedule: at most 16 scheduled drops");
+    if (!(base_lr > 0.f) || iter_drop_delay < 0 || max_loss_drops < 0) throw EngineError(-64, "pxr_set_schedule: bad arguments");
+    e->drop_cfg.base_lr = base_lr;
+    e->drop_cfg.iter_drop_delay = iter_drop_delay;
+    e->drop_cfg.max_loss_drops = max_loss_drops;
+    e->drop_cfg.auto_stop = auto_stop ? 1 : 0;
+    e->drop_cfg.n_sched = n_drops;
+    for (int i = 0; i < n_drops; ++i) e->drop_cfg.sched[i] = drops[i];
+    e->managed = true;
+    PXR_CUDA(cudaMemsetAsync(e->adam_m, 0, e->z_numel * sizeof(float), e->st));
+    PXR_CUDA(cudaMemsetAsync(e->adam_v, 0, e->z_numel * sizeof(float), e->st));
+    e->write_initial_drop_state();
+  });
+}
+
+// Non-blocking: the record the last COMPLETED iteration left in pinned memory.  Returns 1 when there is no consistent
+// record yet (no managed iteration has finished, or the kernel is mid-write: poll again), 0 on success.
+int pxr_poll_status(pxr_handle h, pxr_status* out) {
+  pxr::DropStatus* s = h->e->drop_status;
+  if (!s || !out) return -10;
+  const int e1 = s->seq_end;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  pxr_status r;
+  r.iter = s->iter;
+  r.loss_sum = s->loss_sum;
+  r.best_loss = s->best_loss;
+  r.best_iter = s->best_iter;
+  r.num_loss_drop = s->num_loss_drop;
+  r.stopped = s->stopped;
+  r.rebuilt = s->rebuilt;
+  r.lr = s->lr;
+  r.n_losses = s->n_losses;
+  for (int k = 0; k < 64; ++k) r.losses[k] = s->losses[k];
+  std::atomic_thread_fence(std::memory_order_acquire);
+  const int e0 = s->seq_begin;
+  if (e1 == 0 || e0 != e1) return 1;
+  *out = r;
+  return 0;
+}
+
+int pxr_set_batches(pxr_handle h, int batches) {
+  PXR_TRY(h, {
+    if (batches < 1 || batches > 64) throw EngineError(-65, "batches must be in [1, 64]");
+    h->e->batches = batches;
+  });
+}
+
+// z.grad for the next pxr_step from the caller (the plugin loop accumulates the gradients of several passes itself)
+int pxr_set_z_grad(pxr_handle h, const float* z_grad) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!z_grad) throw EngineError(-10, "pxr_set_z_grad: null gradient");
+    PXR_CUDA(cudaMemcpyAsync(e->z_grad, z_grad, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
 // One full iteration with a CUDA-event pair around every op (engine stream).  out[0] = ms in gemm_tc_kernel launches,
 // out[1] = number of those launches, out[2] = their algorithmic FLOPs, out[3] = ms in all other kernels,
 // out[4] = number of other launches, out[5] = ms of the whole iteration (first event -> last event).
 int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* out6) {
+  return pxr_profile_iteration2(h, z, lr, iter, out6, nullptr);
+}
+
+int pxr_profile_iteration2(pxr_handle h, float* z, float lr, int iter, double* out6, double* tensor_bytes) {
   PXR_TRY(h, {
     Engine* e = h->e;
     if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
@@ -1921,6 +2078,7 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
     e->profiling = false;
     PXR_CUDA(cudaStreamSynchronize(e->st));
     for (int i = 0; i < 6; ++i) out6[i] = 0;
+    double tb = 0;
     FILE* dump = nullptr;
     if (const char* path = getenv("PXR_PROFILE_DUMP")) dump = fopen(path, "w");
     if (dump) fprintf(dump, "op,ms,gflop,launches\n");
@@ -1932,6 +2090,7 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
         out6[0] += ms;
         out6[1] += r.launches;
         out6[2] += r.flops;
+        tb += r.bytes;
       } else {
         out6[3] += ms;
         out6[4] += r.launches;
@@ -1944,6 +2103,7 @@ int pxr_profile_iteration(pxr_handle h, float* z, float lr, int iter, double* ou
     float tot = 0;
     PXR_CUDA(cudaEventElapsedTime(&tot, t0, t1));
     out6[5] = tot;
+    if (tensor_bytes) *tensor_bytes = tb;
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);
     if (z) PXR_CUDA(cudaMemcpyAsync(z, e->z_buf, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
@@ -2067,6 +2227,7 @@ int pxr_reset_optimizer(pxr_handle h) {
     PXR_CUDA(cudaMemsetAsync(e->adam_m, 0, e->z_numel * sizeof(float), e->st));
     PXR_CUDA(cudaMemsetAsync(e->adam_v, 0, e->z_numel * sizeof(float), e->st));
     e->adam_t = 0;
+    if (e->managed) e->write_initial_drop_state();  // a fresh session: best-loss tracking and the drop count restart too
   });
 }
 

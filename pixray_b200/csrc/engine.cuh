@@ -60,17 +60,20 @@ struct OpList {
   std::vector<int> launches;
   std::vector<double> flops;  // > 0: a gemm_tc_kernel launch with this many algorithmic FLOPs
   std::vector<std::string> names;  // label for the per-op profile dump (PXR_PROFILE_DUMP)
-  void add(int n_launch, Op f, double fl = 0.0, std::string name = std::string()) {
+  std::vector<double> bytes;  // algorithmic (compulsory) operand + result bytes of a tensor-core launch, 0 otherwise
+  void add(int n_launch, Op f, double fl = 0.0, std::string name = std::string(), double by = 0.0) {
     ops.push_back(std::move(f));
     launches.push_back(n_launch);
     flops.push_back(fl);
     names.push_back(std::move(name));
+    bytes.push_back(by);
   }
   void append(const OpList& o) {
     ops.insert(ops.end(), o.ops.begin(), o.ops.end());
     launches.insert(launches.end(), o.launches.begin(), o.launches.end());
     flops.insert(flops.end(), o.flops.begin(), o.flops.end());
     names.insert(names.end(), o.names.begin(), o.names.end());
+    bytes.insert(bytes.end(), o.bytes.begin(), o.bytes.end());
   }
 };
 

@@ -1,5 +1,6 @@
 // See gemm_tc.cuh for the contract.  sm_100a only (tcgen05 + TMA + TMEM).
 #include "gemm_tc.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 #include <cstdio>
 #include <cstring>
@@ -551,6 +552,7 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, uint8_t* smem, uin
 // stays lean (the prefetch registers cost the plain GEMMs ~25 %).
 template <int EPI, bool HAS_IN>
 __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ symbol (offset arithmetic only) so smem accesses compile to LDS/STS
   const uint32_t smem_base_u32 = smem_u32(smem_raw);
@@ -586,6 +588,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above touched only parameters, shared memory and TMEM
 
   if (warp == 0) {
     if (lane == 0) producer_loop(p, smem, full_bar, empty_bar, stage_bytes);
@@ -888,6 +891,7 @@ __device__ __forceinline__ void tma_epilogue_loop(const GemmParams& p, uint8_t* 
 
 template <int MODE>
 __device__ __forceinline__ void gemm_tce_body(const GemmParams& p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
@@ -926,6 +930,7 @@ __device__ __forceinline__ void gemm_tce_body(const GemmParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above touched only parameters, shared memory and TMEM
 
   if (warp == 0) {
     if (lane == 0) producer_loop(p, smem, full_bar, empty_bar, stage_bytes);
@@ -1079,6 +1084,7 @@ __device__ __forceinline__ void mma2_loop(const GemmParams& p, const PairInfo& p
 
 template <bool HAS_IN>
 __device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
@@ -1116,6 +1122,7 @@ __device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
   cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   const PairInfo pinfo = pair_info(p);
   const int cluster_id = pinfo.cluster_id, num_clusters = pinfo.num_clusters, pairs_m = pinfo.pairs_m,
@@ -1190,6 +1197,7 @@ __device__ __forceinline__ void gemm_tc2_body(const GemmParams& p) {
 // tile is capped near 45 % of tensor peak by the ~43 B/clk/SM the L2 delivers), the epilogue keeps out of its way.
 template <int MODE>
 __device__ __forceinline__ void gemm_tce2_body(const GemmParams& p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((smem_base_u32 + 1023u) & ~1023u) - smem_base_u32);
@@ -1229,6 +1237,7 @@ __device__ __forceinline__ void gemm_tce2_body(const GemmParams& p) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) producer2_loop(p, pinfo, smem, full_bar, empty_bar, stage_bytes);
@@ -1461,6 +1470,18 @@ int encode_epilogue_map(CUtensorMap* out, const void* ptr, bool f32, const GemmP
   return encode_tmap4(out, ptr, f32 ? 2 : 0, dims, strides, box, err, errlen, true);
 }
 
+// bytes the epilogue must move for `mn` output elements: every output written once, every input tensor read once
+double epilogue_bytes(const GemmEpilogue& e, double mn) {
+  double b = 0;
+  if (e.out_f16) b += 2 * mn;
+  if (e.out_f32) b += 4 * mn;
+  if (e.aux_out) b += 2 * mn;
+  if (e.aux_in) b += 2 * mn;
+  if (e.res_f16) b += 2 * mn;
+  if (e.res_f32) b += 4 * mn;
+  return b;
+}
+
 int finish_plan(GemmPlan* plan, const GemmEpilogue& epi, int block_n, int num_sms, char* err, int errlen) {
   GemmParams& p = plan->p;
   if (block_n < 16 || block_n > 256 || block_n % 16) {
@@ -1595,6 +1616,10 @@ int gemm_plan_make(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
   rc = encode_operand(&p.tma_b, B, p.cta_group == 2 ? block_n / 2 : block_n, fmt, err, errlen);
   if (rc) return rc;
   plan->flops = 2.0 * M * N * K * nb0 * nb1;
+  {
+    const double nb = (double)nb0 * nb1, mn = (double)M * N * nb;
+    plan->bytes = 2.0 * M * K * nb + 2.0 * N * K * (p.b_batched ? nb : 1.0) + epilogue_bytes(epi, mn);
+  }
   return finish_plan(plan, epi_s, block_n, num_sms, err, errlen);
 }
 
@@ -1667,6 +1692,8 @@ int conv_plan_make(GemmPlan* plan, const void* in, long long in_ld, int batch, i
     if (rc) return rc;
   }
   plan->flops = 2.0 * H * W * (double)n_out * c_in * p.num_taps * batch;
+  plan->bytes = 2.0 * H * W * (double)c_in * batch + 2.0 * (double)n_out * c_in * p.num_taps +
+                epilogue_bytes(epi, (double)H * W * n_out * batch * (epi.k_splits > 1 ? epi.k_splits : 1));
   GemmEpilogue e = epi;
   return finish_plan(plan, e, block_n, num_sms, err, errlen);
 }
@@ -1676,6 +1703,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             int N, int ld_ws, const float* __restrict__ bias,
                                                             const __half* __restrict__ res, __half* __restrict__ out,
                                                             int ld_out) {
+  pdl_prologue();
   const int vecs = N / 8;
   const long long n = pixels * vecs;
   const size_t slab = static_cast<size_t>(pixels) * ld_ws;
@@ -1686,8 +1714,32 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
     const float* src = ws + static_cast<size_t>(px) * ld_ws + c0;
-    for (int s = 0; s < splits; ++s) {  // fixed order: deterministic
-      const float4 a = *reinterpret_cast<const float4*>(src + s * slab), b = *reinterpret_cast<const float4*>(src + s * slab + 4);
+    uint4 r16 = make_uint4(0, 0, 0, 0);
+    if (res) r16 = *reinterpret_cast<const uint4*>(res + static_cast<size_t>(px) * ld_out + c0);
+    // the partial sums are independent loads: issue four splits' worth before the (fixed-order) adds, so the loop pays
+    // one L2 round trip per four splits instead of one per split
+    int s0 = 0;
+    for (; s0 + 4 <= splits; s0 += 4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = __ldcg(reinterpret_cast<const float4*>(src + (s0 + u) * slab));
+        b[u] = __ldcg(reinterpret_cast<const float4*>(src + (s0 + u) * slab + 4));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // fixed order: deterministic
+        acc[0] += a[u].x;
+        acc[1] += a[u].y;
+        acc[2] += a[u].z;
+        acc[3] += a[u].w;
+        acc[4] += b[u].x;
+        acc[5] += b[u].y;
+        acc[6] += b[u].z;
+        acc[7] += b[u].w;
+      }
+    }
+    for (; s0 < splits; ++s0) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(src + s0 * slab)), b = __ldcg(reinterpret_cast<const float4*>(src + s0 * slab + 4));
       acc[0] += a.x;
       acc[1] += a.y;
       acc[2] += a.z;
@@ -1699,7 +1751,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
     if (res) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + static_cast<size_t>(px) * ld_out + c0), r);
+      unpack8(r16, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += r[j];
     }
@@ -1713,11 +1765,11 @@ void splitk_reduce(const float* ws, int splits, long long pixels, int N, int ld_
   const long long n = pixels * (N / 8);
   long long g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  splitk_reduce_kernel<<<static_cast<int>(g), 256, 0, stream>>>(ws, splits, pixels, N, ld_ws, bias, res, out, ld_out);
+  launch_pdl(splitk_reduce_kernel, dim3(static_cast<int>(g)), dim3(256), 0, stream, ws, splits, pixels, N, ld_ws, bias, res, out, ld_out);
 }
 
 #define PXR_LAUNCH_TCE2(MODE) \
-  gemm_tce2_kernel<MODE><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p)
+  launch_pdl(gemm_tce2_kernel<MODE>, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p)
 
 void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.p.tma_epi != TE_NONE && plan.p.cta_group == 2) {
@@ -1731,27 +1783,27 @@ void gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     return;
   }
   if (plan.p.tma_epi == TE_F16)
-    gemm_tce_kernel<TE_F16><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tce_kernel<TE_F16>, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.tma_epi == TE_GELU)
-    gemm_tce_kernel<TE_GELU><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tce_kernel<TE_GELU>, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.tma_epi == TE_GELU_BWD)
-    gemm_tce_kernel<TE_GELU_BWD><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tce_kernel<TE_GELU_BWD>, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.tma_epi == TE_RES32)
-    gemm_tce_kernel<TE_RES32><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tce_kernel<TE_RES32>, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.tma_epi == TE_RES16)
-    gemm_tce_kernel<TE_RES16><<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tce_kernel<TE_RES16>, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.act == ACT_SOFTMAX)
-    gemm_tc_softmax_fwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc_softmax_fwd_kernel, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.act == ACT_SOFTMAX_BWD)
-    gemm_tc_softmax_bwd_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc_softmax_bwd_kernel, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.cta_group == 2 && (plan.p.res_f32 || plan.p.res_f16 || plan.p.act == ACT_QUICKGELU_BWD))
-    gemm_tc2_in_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc2_in_kernel, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.cta_group == 2)
-    gemm_tc2_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc2_kernel, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else if (plan.p.res_f32 || plan.p.res_f16 || plan.p.act == ACT_QUICKGELU_BWD)
-    gemm_tc_in_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc_in_kernel, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
   else
-    gemm_tc_kernel<<<plan.grid, GEMM_THREADS, plan.smem_bytes, stream>>>(plan.p);
+    launch_pdl(gemm_tc_kernel, dim3(plan.grid), dim3(GEMM_THREADS), plan.smem_bytes, stream, plan.p);
 }
 
 }  // namespace pxr

@@ -108,6 +108,7 @@ struct GemmPlan {
   int grid = 0;
   int smem_bytes = 0;
   double flops = 0;   // 2*M*N*K*batches (algorithmic)
+  double bytes = 0;   // compulsory traffic: each operand read once, each epilogue tensor read / written once
 };
 
 // Plain (possibly batched) GEMM.  K is the reduction length; M, N output extents per batch.

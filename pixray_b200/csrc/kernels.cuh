@@ -147,6 +147,49 @@ void adam_clip_step(float* z, float* m, float* v, const float* g, float inv_scal
                     const float* zmin, const float* zmax, int clip01, float lr, float b1, float b2, float eps, int t,
                     cudaStream_t st);
 
+// ------------------------------------------------------------------ device-side checkdrop + Adam (pixray.py:1090-1109, 1464-1512)
+// train()'s per-iteration control decisions without a host round trip.  The optimiser step of iteration `it` reads the
+// iteration's loss vector, decides like checkdrop / the scheduled learning-rate drops / auto_stop do, applies Adam + clip_z
+// with the CURRENT learning rate and Adam state, and -- when the decision is "rebuild the optimisers" -- leaves a fresh
+// Adam (m = v = 0, t = 0) at learning_rate / 10^num_loss_drop behind for the next iteration, or raises `stopped` when
+// the drops are used up (after which further iterations leave z untouched).  State is double-buffered (read cur, write
+// next) so every block of the kernel sees the same decision inputs.
+struct DropState {
+  float best_loss;     // 1e20 after a rebuild (pixray.py:1509)
+  int best_iter;
+  int num_loss_drop;
+  int stopped;
+  float lr;
+  int adam_t;          // steps taken by the current Adam instance
+  int pad[2];
+};
+struct DropConfig {
+  float base_lr;       // args.learning_rate, or the drawer's own rate (fftdrawer.py:63-67)
+  int iter_drop_delay; // 12 (pixray.py:1987)
+  int max_loss_drops;  // len(args.learning_rate_drops)
+  int auto_stop;
+  int n_sched;
+  int sched[16];       // args.learning_rate_drops: iterations at which the rate drops regardless of the losses
+};
+// What the host may poll without synchronising (pinned, mapped memory; seq_begin == seq_end == iteration + 1 when the
+// record is consistent).
+struct DropStatus {
+  volatile int seq_begin;
+  int iter;
+  float loss_sum, best_loss;
+  int best_iter, num_loss_drop, stopped, rebuilt;
+  float lr;
+  int n_losses;
+  float losses[64];
+  volatile int seq_end;
+};
+void adam_clip_managed(float* z, float* m, float* v, const float* g, float* best_z, float inv_scale, int n,
+                       int per_channel, const float* zmin, const float* zmax, int clip01, float b1, float b2,
+                       float eps, const float* losses, int n_losses, int iter, const DropConfig& cfg,
+                       const DropState* cur, DropState* next, DropStatus* status_mapped, cudaStream_t st);
+// acc (=|+=) g: gradient accumulation over the `batches` passes of one iteration (pixray.py:1464-1482)
+void accumulate_f32(const float* g, float* acc, long long n, int accumulate, cudaStream_t st);
+
 // ------------------------------------------------------------------ auxiliary losses (Losses/*.py), kernels_losses.cu
 // Every launcher adds grad_scale * weight * dL/dx into the fp32 gradient buffer of the tensor the reference loss reads
 // and writes (image losses) or accumulates (cutout / embedding losses: per-rank partial sums) the weighted loss value.

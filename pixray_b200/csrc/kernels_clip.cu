@@ -1,6 +1,7 @@
 // CLIP-side row kernels: LayerNorm fwd/bwd on the fp32 residual stream, attention softmax fwd/bwd, the
 // class-token head (ln_post + proj), the Prompt / spherical-distance loss with its gradient, Adam + clip_z.
 #include "kernels.cuh"
+#include "launch.cuh"
 #include <cfloat>
 #include <cmath>
 
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, int rows, int W, float eps,
                                                             act_t* __restrict__ y16, float* __restrict__ y32,
                                                             float* __restrict__ stats) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
                                                             const float* __restrict__ gamma, int rows, int W,
                                                             int accumulate, float* __restrict__ gx,
                                                             act_t* __restrict__ gx16) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
 // one warp per row; lane owns NV 16-byte vectors (8 halfs) of the row: ld % 8 == 0, ld <= 256 * NV
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(act_t* __restrict__ s, long long rows, int cols, int ld) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(act_t* __restrict__ s,
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const act_t* __restrict__ p, act_t* __restrict__ dp,
                                                           long long rows, int cols, int ld) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(128) prompt_loss_kernel(const float* __restric
                                                           float grad_scale, float* __restrict__ e_unit,
                                                           float* __restrict__ losses, float* __restrict__ de,
                                                           act_t* __restrict__ de16) {
+  pdl_prologue();
   extern __shared__ float sh[];  // en [D], gen [D]
   float* en = sh;
   float* gen = sh + D;
@@ -324,6 +330,7 @@ __global__ void adam_clip_kernel(float* __restrict__ z, float* __restrict__ m, f
                                  const float* __restrict__ g, float inv_scale, int n, int per_channel,
                                  const float* __restrict__ zmin, const float* __restrict__ zmax, int clip01,
                                  float step_size, float b1, float b2, float eps, float inv_sqrt_bc2) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float gi = g[i] * inv_scale;
@@ -342,11 +349,106 @@ __global__ void adam_clip_kernel(float* __restrict__ z, float* __restrict__ m, f
   z[i] = zi;
 }
 
+// see kernels.cuh "device-side checkdrop + Adam"
+__global__ void adam_clip_managed_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
+                                         const float* __restrict__ g, float* __restrict__ best_z, float inv_scale, int n,
+                                         int per_channel, const float* __restrict__ zmin, const float* __restrict__ zmax,
+                                         int clip01, float b1, float b2, float eps, const float* __restrict__ losses,
+                                         int n_losses, int iter, DropConfig cfg, const DropState* __restrict__ cur,
+                                         DropState* __restrict__ next, DropStatus* status) {
+  pdl_prologue();
+  const DropState s = *cur;
+  const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+  float loss_sum = 0.f;
+  for (int k = 0; k < n_losses; ++k) loss_sum += losses[k];  // sum(lossAll): left to right in fp32 like Python's sum()
+  DropState nx = s;
+  bool rebuild = false, new_best = false;
+  if (!s.stopped) {
+    bool scheduled = false;
+    for (int k = 0; k < cfg.n_sched; ++k) scheduled |= (cfg.sched[k] == iter);
+    if (scheduled) {
+      rebuild = true;  // "Dropping learning rate" (pixray.py:1468-1470): checkdrop is not consulted on these iterations
+    } else {
+      bool drop = false;
+      if (loss_sum < s.best_loss) {
+        new_best = true;
+        nx.best_loss = loss_sum;
+        nx.best_iter = iter;
+      } else if (iter - s.best_iter >= cfg.iter_drop_delay) {
+        drop = true;
+      }
+      if (cfg.auto_stop) rebuild = drop;
+    }
+    const int t = s.adam_t + 1;
+    nx.adam_t = t;
+    // torch.optim.Adam: step_size = lr / (1 - b1^t); denom = sqrt(v) / sqrt(1 - b2^t) + eps
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)s.lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    if (rebuild) {
+      nx.num_loss_drop = s.num_loss_drop + 1;
+      if (nx.num_loss_drop > cfg.max_loss_drops) {
+        nx.stopped = 1;  // train() returns False (pixray.py:1505-1506); this iteration's step still happened
+      } else {
+        nx.best_iter = iter;
+        nx.best_loss = 1e20f;
+        nx.adam_t = 0;
+        nx.lr = (float)((double)cfg.base_lr / pow(10.0, (double)nx.num_loss_drop));  // learning_rate / 10^drops (pixray.py:522-539)
+      }
+    }
+    const bool fresh = rebuild && !nx.stopped;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const float z0 = z[i];
+      if (new_best && best_z) best_z[i] = z0;  // best_z = drawer.get_z_copy() (pixray.py:1104): z BEFORE this step
+      const float gi = g[i] * inv_scale;
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = fresh ? 0.f : mi;
+      v[i] = fresh ? 0.f : vi;
+      const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+      float zi = z0 - step_size * mi / denom;
+      if (zmin) {
+        const int c = i / per_channel;
+        zi = fminf(fmaxf(zi, zmin[c]), zmax[c]);
+      } else if (clip01) {
+        zi = fminf(fmaxf(zi, 0.f), 1.f);
+      }
+      z[i] = zi;
+    }
+  }
+  if (writer) {
+    *next = nx;
+    if (status) {
+      status->seq_begin = iter + 1;
+      __threadfence_system();
+      status->iter = iter;
+      status->loss_sum = loss_sum;
+      status->best_loss = nx.best_loss;
+      status->best_iter = nx.best_iter;
+      status->num_loss_drop = nx.num_loss_drop;
+      status->stopped = nx.stopped;
+      status->rebuilt = rebuild ? 1 : 0;
+      status->lr = nx.lr;
+      status->n_losses = n_losses;
+      for (int k = 0; k < n_losses && k < 64; ++k) status->losses[k] = losses[k];
+      __threadfence_system();
+      status->seq_end = iter + 1;
+    }
+  }
+}
+
+__global__ void accumulate_kernel(const float* __restrict__ g, float* __restrict__ acc, long long n, int accumulate) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] = accumulate ? acc[i] + g[i] : g[i];
+}
+
 __global__ void fill_kernel(float* p, float v, long long n) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = v;
 }
 __global__ void cast_kernel(const float* x, act_t* y, long long n, float scale) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2half_rn(x[i] * scale);
 }
@@ -355,11 +457,11 @@ __global__ void cast_kernel(const float* x, act_t* y, long long n, float scale) 
 
 #define LN_DISPATCH(KERNEL, ...)                                                   \
   switch (W / 128) {                                                              \
-    case 1: KERNEL<1><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
-    case 2: KERNEL<2><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
-    case 4: KERNEL<4><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
-    case 6: KERNEL<6><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
-    case 8: KERNEL<8><<<(rows + 7) / 8, 256, 0, st>>>(__VA_ARGS__); break;        \
+    case 1: launch_pdl(KERNEL<1>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 2: launch_pdl(KERNEL<2>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 4: launch_pdl(KERNEL<4>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 6: launch_pdl(KERNEL<6>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 8: launch_pdl(KERNEL<8>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
     default: break;                                                               \
   }
 
@@ -376,22 +478,22 @@ void layernorm_backward(const act_t* dy, const float* x, long long x_stride, con
 void softmax_forward(act_t* s, int rows, int cols, int ld, cudaStream_t st) {
   const int nv = (ld / 8 + 31) / 32;
   const int grid = (rows + 7) / 8;
-  if (nv <= 1) softmax_fwd_kernel<1><<<grid, 256, 0, st>>>(s, rows, cols, ld);
-  else if (nv == 2) softmax_fwd_kernel<2><<<grid, 256, 0, st>>>(s, rows, cols, ld);
-  else softmax_fwd_kernel<4><<<grid, 256, 0, st>>>(s, rows, cols, ld);
+  if (nv <= 1) launch_pdl(softmax_fwd_kernel<1>, dim3(grid), dim3(256), 0, st, s, rows, cols, ld);
+  else if (nv == 2) launch_pdl(softmax_fwd_kernel<2>, dim3(grid), dim3(256), 0, st, s, rows, cols, ld);
+  else launch_pdl(softmax_fwd_kernel<4>, dim3(grid), dim3(256), 0, st, s, rows, cols, ld);
 }
 void softmax_backward(const act_t* p, act_t* dp_to_ds, int rows, int cols, int ld, cudaStream_t st) {
   const int nv = (ld / 8 + 31) / 32;
   const int grid = (rows + 7) / 8;
-  if (nv <= 1) softmax_bwd_kernel<1><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
-  else if (nv == 2) softmax_bwd_kernel<2><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
-  else softmax_bwd_kernel<4><<<grid, 256, 0, st>>>(p, dp_to_ds, rows, cols, ld);
+  if (nv <= 1) launch_pdl(softmax_bwd_kernel<1>, dim3(grid), dim3(256), 0, st, p, dp_to_ds, rows, cols, ld);
+  else if (nv == 2) launch_pdl(softmax_bwd_kernel<2>, dim3(grid), dim3(256), 0, st, p, dp_to_ds, rows, cols, ld);
+  else launch_pdl(softmax_bwd_kernel<4>, dim3(grid), dim3(256), 0, st, p, dp_to_ds, rows, cols, ld);
 }
 void prompt_loss(const float* e, int B, int D, const float* prompts, const float* weights, const float* stops,
                  const int* slots, const float* inv_rows, int n, int cutn_global, float grad_scale, float* e_unit,
                  float* losses, float* de, act_t* de16, cudaStream_t st) {
   // Prompt.forward means over [cutn, n_embed] per prompt (pixray.py:280)
-  prompt_loss_kernel<<<B, 128, 2 * D * sizeof(float), st>>>(e, D, prompts, weights, stops, slots, inv_rows, n,
+  launch_pdl(prompt_loss_kernel, dim3(B), dim3(128), 2 * D * sizeof(float), st, e, D, prompts, weights, stops, slots, inv_rows, n,
                                                            1.f / cutn_global, grad_scale, e_unit, losses, de, de16);
 }
 
@@ -400,19 +502,35 @@ void adam_clip_step(float* z, float* m, float* v, const float* g, float inv_scal
                     cudaStream_t st) {
   // torch.optim.Adam: step_size = lr / (1 - b1^t); denom = sqrt(v) / sqrt(1 - b2^t) + eps
   const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
-  adam_clip_kernel<<<(n + 255) / 256, 256, 0, st>>>(z, m, v, g, inv_scale, n, per_channel, zmin, zmax, clip01,
+  launch_pdl(adam_clip_kernel, dim3((n + 255) / 256), dim3(256), 0, st, z, m, v, g, inv_scale, n, per_channel, zmin, zmax, clip01,
                                                     (float)(lr / bc1), b1, b2, eps, (float)(1.0 / sqrt(bc2)));
+}
+
+void adam_clip_managed(float* z, float* m, float* v, const float* g, float* best_z, float inv_scale, int n,
+                       int per_channel, const float* zmin, const float* zmax, int clip01, float b1, float b2,
+                       float eps, const float* losses, int n_losses, int iter, const DropConfig& cfg,
+                       const DropState* cur, DropState* next, DropStatus* status_mapped, cudaStream_t st) {
+  int grid = (n + 255) / 256;
+  if (grid > 148 * 4) grid = 148 * 4;
+  launch_pdl(adam_clip_managed_kernel, dim3(grid), dim3(256), 0, st, z, m, v, g, best_z, inv_scale, n, per_channel, zmin,
+             zmax, clip01, b1, b2, eps, losses, n_losses, iter, cfg, cur, next, status_mapped);
+}
+
+void accumulate_f32(const float* g, float* acc, long long n, int accumulate, cudaStream_t st) {
+  long long gr = (n + 255) / 256;
+  if (gr > 148 * 8) gr = 148 * 8;
+  launch_pdl(accumulate_kernel, dim3((int)gr), dim3(256), 0, st, g, acc, n, accumulate);
 }
 
 void fill_f32(float* p, float v, long long n, cudaStream_t st) {
   long long g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  fill_kernel<<<(int)g, 256, 0, st>>>(p, v, n);
+  launch_pdl(fill_kernel, dim3((int)g), dim3(256), 0, st, p, v, n);
 }
 void cast_f32_to_f16(const float* x, act_t* y, long long n, float scale, cudaStream_t st) {
   long long g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  cast_kernel<<<(int)g, 256, 0, st>>>(x, y, n, scale);
+  launch_pdl(cast_kernel, dim3((int)g), dim3(256), 0, st, x, y, n, scale);
 }
 
 }  // namespace pxr

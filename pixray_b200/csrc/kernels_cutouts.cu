@@ -6,6 +6,7 @@
 //                     im2col of the ViT patch embedding, and its adjoint
 //   cutout_backward : adjoint of the resample (scatter-add through the bilinear taps) incl. the d/dmin, d/dmax terms
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "color_jitter.cuh"
 #include "philox.cuh"
 #include "pool_bounds.cuh"
@@ -21,6 +22,7 @@ __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
 __global__ void pool_fwd_kernel(const float* __restrict__ img, int H, int W, int cs, float* __restrict__ pooled,
                                 int* __restrict__ argmax) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * cs * cs) return;
   int ox = i % cs, oy = (i / cs) % cs, c = i / (cs * cs);
@@ -45,6 +47,7 @@ __global__ void pool_fwd_kernel(const float* __restrict__ img, int H, int W, int
 
 __global__ void pool_bwd_kernel(const float* __restrict__ g_pooled, const int* __restrict__ argmax, int H, int W,
                                 int cs, float* __restrict__ g_img) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * H * W) return;
   int x = i % W, y = (i / W) % H, c = i / (W * H);
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_fwd_kernel(CutoutArgs a, f
                                                                  float* __restrict__ part_max,
                                                                  int* __restrict__ part_imin,
                                                                  int* __restrict__ part_imax) {
+  pdl_prologue();
   const int n = blockIdx.y;
   const int n_global = a.first_global + n;
   const int cs = a.cs;
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __rest
                                                              float* __restrict__ part_max,
                                                              int* __restrict__ part_imin,
                                                              int* __restrict__ part_imax) {
+  pdl_prologue();
   float tmin = FLT_MAX, tmax = -FLT_MAX;
   int imin = 0x7fffffff, imax = 0x7fffffff;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restr
                                                             const int* __restrict__ part_imin,
                                                             const int* __restrict__ part_imax, int nparts,
                                                             float* __restrict__ range, int* __restrict__ irange) {
+  pdl_prologue();
   __shared__ float smin[256], smax[256];
   __shared__ int simin[256], simax[256];
   float tmin = FLT_MAX, tmax = -FLT_MAX;
@@ -360,11 +366,13 @@ __global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restr
 // Cutout-sharded ranks: exchange buffer {min, -max} goes through one allreduce(min); afterwards every rank holds the
 // global range, and only the rank that owns the extreme element keeps its index (others get -1).
 __global__ void range_pack_kernel(const float* __restrict__ range, float* __restrict__ xbuf) {
+  pdl_prologue();
   xbuf[0] = range[0];
   xbuf[1] = -range[2];
 }
 __global__ void range_unpack_kernel(const float* __restrict__ xbuf, float* __restrict__ range,
                                     int* __restrict__ irange) {
+  pdl_prologue();
   const float gmin = xbuf[0], gmax = -xbuf[1];
   if (range[0] != gmin) irange[0] = -1;
   if (range[2] != gmax) irange[1] = -1;
@@ -379,6 +387,7 @@ __global__ void range_unpack_kernel(const float* __restrict__ xbuf, float* __res
 __global__ void __launch_bounds__(256) patchify_fwd_kernel(const float* __restrict__ batch,
                                                            const float* __restrict__ range, int n, int cs, int P,
                                                            int ld, act_t* __restrict__ patches) {
+  pdl_prologue();
   const int gp = cs / P;
   const int vec_per_row = 3 * P * P / 8;
   const long long total = (long long)n * gp * gp * vec_per_row;
@@ -411,6 +420,7 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
                                                            const float* __restrict__ range, int n, int cs, int P,
                                                            int ld, int accumulate, float* __restrict__ g_batch,
                                                            float* __restrict__ sums) {
+  pdl_prologue();
   const int gp = cs / P;
   const int vec_per_row = 3 * P * P / 8;
   const long long total = (long long)n * gp * gp * vec_per_row;
@@ -477,6 +487,7 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
 __global__ void __launch_bounds__(256) patchify_fwd_generic_kernel(const float* __restrict__ batch,
                                                                    const float* __restrict__ range, int n, int cs,
                                                                    int P, int ld, act_t* __restrict__ patches) {
+  pdl_prologue();
   const int gp = cs / P, K = 3 * P * P;
   const long long total = (long long)n * gp * gp * K;
   const float mn = range[0], R = range[1];
@@ -498,6 +509,7 @@ __global__ void __launch_bounds__(256) patchify_bwd_generic_kernel(const act_t* 
                                                                    int P, int ld, int accumulate,
                                                                    float* __restrict__ g_batch,
                                                                    float* __restrict__ sums) {
+  pdl_prologue();
   const int gp = cs / P;
   const long long total = (long long)n * 3 * cs * cs;
   const float mn = range[0], R = range[1];
@@ -543,6 +555,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
                                                                  const int* __restrict__ irange,
                                                                  const float* __restrict__ sums,
                                                                  float* __restrict__ g_pooled) {
+  pdl_prologue();
   const int n = blockIdx.y;
   const int n_global = a.first_global + n;
   const int cs = a.cs;
@@ -609,10 +622,10 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
 }  // namespace
 
 void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* argmax, cudaStream_t st) {
-  pool_fwd_kernel<<<(3 * cs * cs + 255) / 256, 256, 0, st>>>(img, H, W, cs, pooled, argmax);
+  launch_pdl(pool_fwd_kernel, dim3((3 * cs * cs + 255) / 256), dim3(256), 0, st, img, H, W, cs, pooled, argmax);
 }
 void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st) {
-  pool_bwd_kernel<<<(3 * H * W + 255) / 256, 256, 0, st>>>(g_pooled, argmax, H, W, cs, g_img);
+  launch_pdl(pool_bwd_kernel, dim3((3 * H * W + 255) / 256), dim3(256), 0, st, g_pooled, argmax, H, W, cs, g_img);
 }
 
 int cutout_num_blocks(int n_local, int cs) { return n_local * ((cs * cs / 4 + CUT_THREADS - 1) / CUT_THREADS); }
@@ -620,22 +633,22 @@ int cutout_num_blocks(int n_local, int cs) { return n_local * ((cs * cs / 4 + CU
 void cutout_forward(const CutoutArgs& a, float* batch, float* part_min, float* part_max, int* part_imin,
                     int* part_imax, cudaStream_t st) {
   dim3 grid((a.cs * a.cs / 4 + CUT_THREADS - 1) / CUT_THREADS, a.n_local);
-  cutout_fwd_kernel<<<grid, CUT_THREADS, 0, st>>>(a, batch, part_min, part_max, part_imin, part_imax);
+  launch_pdl(cutout_fwd_kernel, dim3(grid), dim3(CUT_THREADS), 0, st, a, batch, part_min, part_max, part_imin, part_imax);
 }
 
-void range_pack(const float* range, float* xbuf, cudaStream_t st) { range_pack_kernel<<<1, 1, 0, st>>>(range, xbuf); }
+void range_pack(const float* range, float* xbuf, cudaStream_t st) { launch_pdl(range_pack_kernel, dim3(1), dim3(1), 0, st, range, xbuf); }
 void range_unpack(const float* xbuf, float* range, int* irange, cudaStream_t st) {
-  range_unpack_kernel<<<1, 1, 0, st>>>(xbuf, range, irange);
+  launch_pdl(range_unpack_kernel, dim3(1), dim3(1), 0, st, xbuf, range, irange);
 }
 
 void minmax_partials(const float* x, long long n, int nparts, float* part_min, float* part_max, int* part_imin,
                      int* part_imax, cudaStream_t st) {
-  minmax_partial_kernel<<<nparts, 256, 0, st>>>(x, n, part_min, part_max, part_imin, part_imax);
+  launch_pdl(minmax_partial_kernel, dim3(nparts), dim3(256), 0, st, x, n, part_min, part_max, part_imin, part_imax);
 }
 
 void minmax_reduce(const float*, const float* part_min, const float* part_max, const int* part_imin,
                    const int* part_imax, int nparts, float* range, int* irange, cudaStream_t st) {
-  minmax_reduce_kernel<<<1, 256, 0, st>>>(part_min, part_max, part_imin, part_imax, nparts, range, irange);
+  launch_pdl(minmax_reduce_kernel, dim3(1), dim3(256), 0, st, part_min, part_max, part_imin, part_imax, nparts, range, irange);
 }
 
 static int patch_grid(long long total) {
@@ -648,28 +661,28 @@ void patchify_forward(const float* batch, const float* range, int n, int cs, int
                       cudaStream_t st) {
   if (P % 8) {
     const long long tot = (long long)n * (cs / P) * (cs / P) * 3 * P * P;
-    patchify_fwd_generic_kernel<<<patch_grid(tot), 256, 0, st>>>(batch, range, n, cs, P, ld, patches);
+    launch_pdl(patchify_fwd_generic_kernel, dim3(patch_grid(tot)), dim3(256), 0, st, batch, range, n, cs, P, ld, patches);
     return;
   }
   const long long total = (long long)n * (cs / P) * (cs / P) * (3 * P * P / 8);
-  patchify_fwd_kernel<<<patch_grid(total), 256, 0, st>>>(batch, range, n, cs, P, ld, patches);
+  launch_pdl(patchify_fwd_kernel, dim3(patch_grid(total)), dim3(256), 0, st, batch, range, n, cs, P, ld, patches);
 }
 void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
                        int accumulate, float* g_batch, float* sums, cudaStream_t st) {
   if (P % 8) {
     const long long tot = (long long)n * 3 * cs * cs;
-    patchify_bwd_generic_kernel<<<patch_grid(tot), 256, 0, st>>>(g_patches, batch, range, n, cs, P, ld, accumulate,
+    launch_pdl(patchify_bwd_generic_kernel, dim3(patch_grid(tot)), dim3(256), 0, st, g_patches, batch, range, n, cs, P, ld, accumulate,
                                                                  g_batch, sums);
     return;
   }
   const long long total = (long long)n * (cs / P) * (cs / P) * (3 * P * P / 8);
-  patchify_bwd_kernel<<<patch_grid(total), 256, 0, st>>>(g_patches, batch, range, n, cs, P, ld, accumulate, g_batch,
+  launch_pdl(patchify_bwd_kernel, dim3(patch_grid(total)), dim3(256), 0, st, g_patches, batch, range, n, cs, P, ld, accumulate, g_batch,
                                                          sums);
 }
 void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* range, const int* irange,
                      const float* sums, float* g_pooled, cudaStream_t st) {
   dim3 grid((a.cs * a.cs / 4 + CUT_THREADS - 1) / CUT_THREADS, a.n_local);
-  cutout_bwd_kernel<<<grid, CUT_THREADS, 0, st>>>(a, g_batch, range, irange, sums, g_pooled);
+  launch_pdl(cutout_bwd_kernel, dim3(grid), dim3(CUT_THREADS), 0, st, a, g_batch, range, irange, sums, g_pooled);
 }
 
 }  // namespace pxr

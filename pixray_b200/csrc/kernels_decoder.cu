@@ -1,6 +1,7 @@
 // VQGAN-drawer side kernels: nearest-code search, GroupNorm(+swish) fwd/bwd, nearest upsample and its adjoint,
 // image finish (clamp_with_grad) and the pixel drawer.  All HBM/L2-bound; vectorised 16-byte accesses on NHWC fp16.
 #include "kernels.cuh"
+#include "launch.cuh"
 #include <cooperative_groups.h>
 #include <cfloat>
 
@@ -16,6 +17,7 @@ __global__ void __launch_bounds__(256) vq_partial_kernel(const float* __restrict
                                                          const float* __restrict__ c2, int C, int hw, int n_e,
                                                          int n_chunks, float* __restrict__ part_d,
                                                          int* __restrict__ part_i) {
+  pdl_prologue();
   extern __shared__ float xs[];  // [C][VQ_POS]
   __shared__ float x2[VQ_POS];
   __shared__ float red_d[8][VQ_POS];
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(256) vq_partial_kernel(const float* __restrict
 // one block per position: final argmin over chunks, gather the code row as fp16
 __global__ void vq_final_kernel(const float* __restrict__ part_d, const int* __restrict__ part_i, int n_chunks,
                                 const float* __restrict__ cb, int C, int* __restrict__ idx, act_t* __restrict__ zq) {
+  pdl_prologue();
   const int p = blockIdx.x;
   __shared__ int s_idx;
   if (threadIdx.x == 0) {
@@ -133,6 +136,7 @@ __global__ void vq_final_kernel(const float* __restrict__ part_d, const int* __r
 
 __global__ void vq_backward_kernel(const act_t* __restrict__ dzq, float inv_scale, int C, int hw,
                                    float* __restrict__ z_grad) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [C, hw]
   if (i >= C * hw) return;
   int k = i / hw, p = i % hw;
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int pixels, int C, int swish,
                                                          float* __restrict__ part) {
+  pdl_prologue();
   __shared__ float acc[GN_G][2];
   const int vecs = C / 8, cpg = C / GN_G;
   const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = 256 / vecs;
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const act_t* __restrict
 template <int MODE>
 __global__ void gn_final_kernel(const float* __restrict__ part, int nblk, double count, float eps,
                                 float* __restrict__ out) {
+  pdl_prologue();
   const int t = threadIdx.x & 63, q = threadIdx.x >> 6;  // 256 threads: slot (group, which) x quarter of the partials
   double s = 0.0;
   for (int b = q; b < nblk; b += 4) s += (double)part[(size_t)b * GN_G * 2 + t];
@@ -282,6 +288,7 @@ __global__ void gn_final_kernel(const float* __restrict__ part, int nblk, double
 __global__ void __launch_bounds__(256) gn_apply_kernel(const act_t* __restrict__ x, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        long long nvec, int C, int swish, act_t* __restrict__ y) {
+  pdl_prologue();
   const int cpg = C / GN_G, vecs = C / 8;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
        v += (long long)gridDim.x * blockDim.x) {
@@ -305,6 +312,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const act_t* __restri
                                                            const float* __restrict__ beta, long long nvec, int C,
                                                            int swish, const act_t* __restrict__ dres,
                                                            act_t* __restrict__ dx) {
+  pdl_prologue();
   const int cpg = C / GN_G, vecs = C / 8;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
        v += (long long)gridDim.x * blockDim.x) {
@@ -358,7 +366,10 @@ __device__ __forceinline__ void gnc_grid_barrier(unsigned long long* counter, un
   __syncthreads();
 }
 
-// per-block fixed-order reduction of the thread partials s[half][a/b] to part_out[32 groups][2]
+// per-block fixed-order reduction of the thread partials s[half][a/b] to part_out[32 groups][2].
+// Threads (vc, pl) hold the sums of vector column vc over the pixels of plane pl: a fixed-shape binary tree over the
+// planes (plane = GNC_THREADS / vecs is a power of two for every supported C) -- log2(plane) barriers instead of a
+// serial walk over up to 64 planes by `vecs` threads (which was ~3 us of dependent shared-memory loads per call).
 __device__ __forceinline__ void gnc_block_partials(const float (&s)[2][2], float* red, int vecs, int cpg,
                                                    float* __restrict__ part_out) {
   const int tid = threadIdx.x, vc = tid % vecs, pl = tid / vecs, plane = GNC_THREADS / vecs;
@@ -366,14 +377,12 @@ __device__ __forceinline__ void gnc_block_partials(const float (&s)[2][2], float
   red[1 * GNC_THREADS + tid] = s[0][1];
   red[2 * GNC_THREADS + tid] = s[1][0];
   red[3 * GNC_THREADS + tid] = s[1][1];
-  __syncthreads();
-  if (pl == 0) {
-    float t[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int l = 0; l < plane; ++l)
+  for (int stride = plane >> 1; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if (pl < stride) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t[k] += red[k * GNC_THREADS + l * vecs + vc];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) red[k * GNC_THREADS + vc] = t[k];
+      for (int k = 0; k < 4; ++k) red[k * GNC_THREADS + tid] += red[k * GNC_THREADS + tid + stride * vecs];
+    }
   }
   __syncthreads();
   if (tid < GN_G * 2) {
@@ -408,17 +417,33 @@ __device__ __forceinline__ void gnc_cluster_fold(float* cpart, int nblk, double 
   cluster.sync();  // nobody leaves (or rewrites cpart) while a peer still reads it
 }
 
-// every block: fold the nblk block partials (fixed order, double) -> sh[64] = per-(group, which) mean
-__device__ __forceinline__ void gnc_fold(const float* part, int nblk, double count, double* acc4, double* sh) {
+// every block: fold the nblk (<= GNC_FOLD_MAX) block partials -> sh[64] = per-(group, which) mean.  All 1024 threads
+// take part: thread (slot, lane16) loads partials lane16, lane16 + 16, ... with every load issued before the first add
+// (ONE L2 round trip after the grid barrier, where the previous 256-thread version paid ~37 dependent ones), then the 16
+// lane sums are added in a fixed order in double.
+constexpr int GNC_FOLD_LANES = GNC_THREADS / 64;                        // 16
+constexpr int GNC_FOLD_MAX = 160;                                       // >= blocks per grid (<= num_sms)
+constexpr int GNC_FOLD_PER = (GNC_FOLD_MAX + GNC_FOLD_LANES - 1) / GNC_FOLD_LANES;  // 10
+__device__ __forceinline__ void gnc_fold(const float* part, int nblk, double count, double* acc16, double* sh) {
   const int tid = threadIdx.x;
-  if (tid < 256) {
-    const int slot = tid & 63, qd = tid >> 6;
-    double a = 0.0;
-    for (int b = qd; b < nblk; b += 4) a += (double)__ldcg(part + (size_t)b * GN_G * 2 + slot);
-    acc4[qd * 64 + slot] = a;
+  const int slot = tid & 63, ln = tid >> 6;
+  float v[GNC_FOLD_PER];
+#pragma unroll
+  for (int u = 0; u < GNC_FOLD_PER; ++u) {
+    const int b = ln + u * GNC_FOLD_LANES;
+    v[u] = b < nblk ? __ldcg(part + (size_t)b * GN_G * 2 + slot) : 0.f;
   }
+  double a = 0.0;
+#pragma unroll
+  for (int u = 0; u < GNC_FOLD_PER; ++u) a += (double)v[u];
+  acc16[ln * 64 + slot] = a;
   __syncthreads();
-  if (tid < 64) sh[tid] = (acc4[tid] + acc4[64 + tid] + acc4[128 + tid] + acc4[192 + tid]) / count;
+  if (tid < 64) {
+    double t = 0.0;
+#pragma unroll
+    for (int l = 0; l < GNC_FOLD_LANES; ++l) t += acc16[l * 64 + tid];
+    sh[tid] = t / count;
+  }
   __syncthreads();
 }
 
@@ -445,10 +470,11 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
     gn_coop_fwd_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                        int pixels, int C, int swish, float eps, int rpb, float* part, float* __restrict__ stats_out,
                        act_t* y, unsigned long long* bar, unsigned long long bar_target, GnOpts o) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t gnc_smem[];
   float* red = reinterpret_cast<float*>(gnc_smem);                       // [4][1024]
   act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);  // slab of x
-  __shared__ double acc4[256];
+  __shared__ double acc4[GNC_THREADS];  // gnc_fold: [16 lanes][64 slots]
   __shared__ double sh[64];
   __shared__ float st[64];
   const int vecs = C / 8, cpg = C / GN_G;
@@ -525,11 +551,12 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
                        const float* __restrict__ gamma, const float* __restrict__ beta, int pixels, int C, int swish,
                        const act_t* dres, int rpb, int cache_dy, float* part, act_t* dx, unsigned long long* bar,
                        unsigned long long bar_target, GnOpts o) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t gnc_smem[];
   float* red = reinterpret_cast<float*>(gnc_smem);
   act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);
   act_t* cd = cx + (size_t)rpb * C;  // only touched when cache_dy
-  __shared__ double acc4[256];
+  __shared__ double acc4[GNC_THREADS];  // gnc_fold: [16 lanes][64 slots]
   __shared__ double sh[64];
   const int vecs = C / 8, cpg = C / GN_G;
   const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs, plane = GNC_THREADS / vecs;
@@ -622,6 +649,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const act_t* __restrict__ x, int H, int W, int C,
                                                          act_t* __restrict__ y) {
+  pdl_prologue();
   const int vecs = C / 8;
   const long long n = (long long)4 * H * W * vecs;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
@@ -635,6 +663,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const act_t* __restrict
 
 __global__ void __launch_bounds__(256) downsum2x_kernel(const act_t* __restrict__ gy, int H, int W, int C,
                                                         act_t* __restrict__ gx) {
+  pdl_prologue();
   const int vecs = C / 8;
   const long long n = (long long)H * W * vecs;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
@@ -657,6 +686,7 @@ __global__ void __launch_bounds__(256) downsum2x_kernel(const act_t* __restrict_
 
 __global__ void image_finish_kernel(const float* __restrict__ conv_out, int ld, int pixels, float* __restrict__ pre,
                                     float* __restrict__ img) {
+  pdl_prologue();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pixels) return;
 #pragma unroll
@@ -669,6 +699,7 @@ __global__ void image_finish_kernel(const float* __restrict__ conv_out, int ld, 
 
 __global__ void image_finish_bwd_kernel(const float* __restrict__ g_img, const float* __restrict__ pre, int pixels,
                                         int ld, act_t* __restrict__ g_out) {
+  pdl_prologue();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pixels) return;
 #pragma unroll
@@ -683,6 +714,7 @@ __global__ void image_finish_bwd_kernel(const float* __restrict__ g_img, const f
 
 __global__ void pixel_synth_kernel(const float* __restrict__ z, int rows, int cols, int H, int W,
                                    float* __restrict__ pre, float* __restrict__ img) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * H * W) return;
   int x = i % W, y = (i / W) % H, c = i / (W * H);
@@ -696,6 +728,7 @@ __global__ void pixel_synth_kernel(const float* __restrict__ z, int rows, int co
 
 __global__ void pixel_synth_bwd_kernel(const float* __restrict__ g_img, const float* __restrict__ pre, int rows,
                                        int cols, int H, int W, float inv_scale, float* __restrict__ z_grad) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [3, rows, cols]
   if (i >= 3 * rows * cols) return;
   int sx = i % cols, sy = (i / cols) % rows, c = i / (cols * rows);
@@ -729,12 +762,12 @@ void vq_nearest(const float* z, const float* cbT, const float* c2, const float* 
                 float* part_d, int* part_i, int* idx, act_t* zq, cudaStream_t st) {
   const int n_chunks = (n_e + VQ_CODES - 1) / VQ_CODES;
   dim3 grid(n_chunks, (hw + VQ_POS - 1) / VQ_POS);
-  vq_partial_kernel<<<grid, 256, C * VQ_POS * sizeof(float), st>>>(z, cbT, c2, C, hw, n_e, n_chunks, part_d, part_i);
-  vq_final_kernel<<<hw, 128, 0, st>>>(part_d, part_i, n_chunks, cb, C, idx, zq);
+  launch_pdl(vq_partial_kernel, dim3(grid), dim3(256), C * VQ_POS * sizeof(float), st, z, cbT, c2, C, hw, n_e, n_chunks, part_d, part_i);
+  launch_pdl(vq_final_kernel, dim3(hw), dim3(128), 0, st, part_d, part_i, n_chunks, cb, C, idx, zq);
 }
 
 void vq_backward(const act_t* dzq, float inv_scale, int C, int hw, float* z_grad, cudaStream_t st) {
-  vq_backward_kernel<<<(C * hw + 255) / 256, 256, 0, st>>>(dzq, inv_scale, C, hw, z_grad);
+  launch_pdl(vq_backward_kernel, dim3((C * hw + 255) / 256), dim3(256), 0, st, dzq, inv_scale, C, hw, z_grad);
 }
 
 int gn_num_partials(int pixels, int C) {
@@ -744,24 +777,24 @@ int gn_num_partials(int pixels, int C) {
 
 void gn_stats(const act_t* x, int pixels, int C, float eps, float* part, float* stats, cudaStream_t st) {
   const int nblk = gn_num_partials(pixels, C);
-  gn_partial_kernel<0><<<nblk, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, part);
-  gn_final_kernel<0><<<1, 256, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), eps, stats);
+  launch_pdl(gn_partial_kernel<0>, dim3(nblk), dim3(256), 0, st, x, nullptr, nullptr, nullptr, nullptr, pixels, C, 0, part);
+  launch_pdl(gn_final_kernel<0>, dim3(1), dim3(256), 0, st, part, nblk, (double)pixels * (C / GN_G), eps, stats);
 }
 
 void gn_apply(const act_t* x, const float* stats, const float* gamma, const float* beta, int pixels, int C, int swish,
               act_t* y, cudaStream_t st) {
   const long long nvec = (long long)pixels * C / 8;
-  gn_apply_kernel<<<grid_for(nvec, 256), 256, 0, st>>>(x, stats, gamma, beta, nvec, C, swish, y);
+  launch_pdl(gn_apply_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, st, x, stats, gamma, beta, nvec, C, swish, y);
 }
 
 void gn_backward(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
                  int pixels, int C, int swish, const act_t* dres, float* part, float* gstats, act_t* dx,
                  cudaStream_t st) {
   const int nblk = gn_num_partials(pixels, C);
-  gn_partial_kernel<1><<<nblk, 256, 0, st>>>(x, dy, stats, gamma, beta, pixels, C, swish, part);
-  gn_final_kernel<1><<<1, 256, 0, st>>>(part, nblk, (double)pixels * (C / GN_G), 0.f, gstats);
+  launch_pdl(gn_partial_kernel<1>, dim3(nblk), dim3(256), 0, st, x, dy, stats, gamma, beta, pixels, C, swish, part);
+  launch_pdl(gn_final_kernel<1>, dim3(1), dim3(256), 0, st, part, nblk, (double)pixels * (C / GN_G), 0.f, gstats);
   const long long nvec = (long long)pixels * C / 8;
-  gn_bwd_apply_kernel<<<grid_for(nvec, 256), 256, 0, st>>>(dy, x, stats, gstats, gamma, beta, nvec, C, swish, dres,
+  launch_pdl(gn_bwd_apply_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, st, dy, x, stats, gstats, gamma, beta, nvec, C, swish, dres,
                                                            dx);
 }
 
@@ -813,6 +846,7 @@ void gnc_launch_cluster(K kernel, int nb, size_t smem, cudaStream_t st, Args... 
 
 bool gn_coop_supported(int pixels, int C, int num_sms) {
   if (C % 8 || (C / 8) > GNC_THREADS || GNC_THREADS % (C / 8) || (C % GN_G) || (C / GN_G != 4 && (C / GN_G) % 8)) return false;
+  if (num_sms > GNC_FOLD_MAX) return false;  // gnc_fold's register array covers grids of <= GNC_FOLD_MAX blocks
   const int rpb = gnc_rows_per_block(pixels, num_sms);
   return 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2 <= (size_t)GNC_SMEM_MAX;
 }
@@ -829,7 +863,7 @@ void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int 
   int rpb = gnc_rows_per_block(pixels, num_sms);
   const int grid = (pixels + rpb - 1) / rpb;
   const size_t smem = 4 * GNC_THREADS * 4 + (size_t)rpb * C * 2;
-  gn_coop_fwd_kernel<false><<<grid, GNC_THREADS, smem, st>>>(x, gamma, beta, pixels, C, swish, eps, rpb, part, stats, y,
+  launch_pdl(gn_coop_fwd_kernel<false>, dim3(grid), dim3(GNC_THREADS), smem, st, x, gamma, beta, pixels, C, swish, eps, rpb, part, stats, y,
                                                              gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;  // a rejected launch must not move the target
 }
@@ -849,31 +883,31 @@ void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const
   const size_t slab = (size_t)rpb * C * 2;
   int cache_dy = (4 * GNC_THREADS * 4 + 2 * slab <= (size_t)GNC_SMEM_MAX) ? 1 : 0;
   const size_t smem = 4 * GNC_THREADS * 4 + (cache_dy ? 2 : 1) * slab;
-  gn_coop_bwd_kernel<false><<<grid, GNC_THREADS, smem, st>>>(dy, x, stats, gamma, beta, pixels, C, swish, dres, rpb,
+  launch_pdl(gn_coop_bwd_kernel<false>, dim3(grid), dim3(GNC_THREADS), smem, st, dy, x, stats, gamma, beta, pixels, C, swish, dres, rpb,
                                                              cache_dy, part, dx, gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;
 }
 
 void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st) {
-  upsample2x_kernel<<<grid_for((long long)4 * H * W * C / 8, 256), 256, 0, st>>>(x, H, W, C, y);
+  launch_pdl(upsample2x_kernel, dim3(grid_for((long long)4 * H * W * C / 8, 256)), dim3(256), 0, st, x, H, W, C, y);
 }
 void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st) {
-  downsum2x_kernel<<<grid_for((long long)H * W * C / 8, 256), 256, 0, st>>>(gy, H, W, C, gx);
+  launch_pdl(downsum2x_kernel, dim3(grid_for((long long)H * W * C / 8, 256)), dim3(256), 0, st, gy, H, W, C, gx);
 }
 
 void image_finish(const float* conv_out, int ld, int pixels, float* pre, float* img, cudaStream_t st) {
-  image_finish_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(conv_out, ld, pixels, pre, img);
+  launch_pdl(image_finish_kernel, dim3((pixels + 255) / 256), dim3(256), 0, st, conv_out, ld, pixels, pre, img);
 }
 void image_finish_backward(const float* g_img, const float* pre, int pixels, int ld, act_t* g_out, cudaStream_t st) {
-  image_finish_bwd_kernel<<<(pixels + 255) / 256, 256, 0, st>>>(g_img, pre, pixels, ld, g_out);
+  launch_pdl(image_finish_bwd_kernel, dim3((pixels + 255) / 256), dim3(256), 0, st, g_img, pre, pixels, ld, g_out);
 }
 
 void pixel_synth(const float* z, int rows, int cols, int H, int W, float* pre, float* img, cudaStream_t st) {
-  pixel_synth_kernel<<<(3 * H * W + 255) / 256, 256, 0, st>>>(z, rows, cols, H, W, pre, img);
+  launch_pdl(pixel_synth_kernel, dim3((3 * H * W + 255) / 256), dim3(256), 0, st, z, rows, cols, H, W, pre, img);
 }
 void pixel_synth_backward(const float* g_img, const float* pre, int rows, int cols, int H, int W, float inv_scale,
                           float* z_grad, cudaStream_t st) {
-  pixel_synth_bwd_kernel<<<(3 * rows * cols + 255) / 256, 256, 0, st>>>(g_img, pre, rows, cols, H, W, inv_scale,
+  launch_pdl(pixel_synth_bwd_kernel, dim3((3 * rows * cols + 255) / 256), dim3(256), 0, st, g_img, pre, rows, cols, H, W, inv_scale,
                                                                         z_grad);
 }
 

@@ -324,6 +324,32 @@ class B200Engine:
     def reset_optimizer(self):
         self._check(self.lib.pxr_reset_optimizer(self.h), "pxr_reset_optimizer")
 
+    def set_z_grad(self, g):
+        """The gradient the next step() applies (the plugin loop accumulates z.grad over several passes itself)."""
+        self._check(self.lib.pxr_set_z_grad(self.h, self._p_inplace(g, "z.grad")), "pxr_set_z_grad")
+
+    def set_batches(self, batches):
+        """args.batches (pixray.py:1464-1482): passes per iterate(), gradients accumulated, one optimiser step."""
+        self._check(self.lib.pxr_set_batches(self.h, int(batches)), "pxr_set_batches")
+
+    def set_schedule(self, base_lr, iter_drop_delay=12, max_loss_drops=0, auto_stop=False, drops=()):
+        """checkdrop / learning-rate drops / auto-stop on the device (pxr_set_schedule): iterate() then ignores `lr`."""
+        d = np.ascontiguousarray(np.asarray(list(drops), dtype=np.int32).reshape(-1))
+        self._check(self.lib.pxr_set_schedule(self.h, C.c_float(float(base_lr)), int(iter_drop_delay), int(max_loss_drops),
+                                              int(bool(auto_stop)), d.ctypes.data_as(C.c_void_p), int(d.size)),
+                    "pxr_set_schedule")
+
+    def poll_status(self):
+        """The last completed managed iteration's record, read from pinned memory WITHOUT synchronising; None when no
+        consistent record is available yet."""
+        st = _lib.Status()
+        rc = self.lib.pxr_poll_status(self.h, C.byref(st))
+        if rc != 0:
+            return None
+        return dict(iter=st.iter, loss_sum=st.loss_sum, best_loss=st.best_loss, best_iter=st.best_iter,
+                    num_loss_drop=st.num_loss_drop, stopped=bool(st.stopped), rebuilt=bool(st.rebuilt), lr=st.lr,
+                    losses=np.array(st.losses[:st.n_losses], dtype=np.float32))
+
     # ------------------------------------------------------------------ the fast path (what bench.py times)
     def iterate(self, z, lr, it, *, params=None, losses_out=None):
         """One train() iteration entirely inside the library.  params: dict(transforms, zoom_padding, fill,
@@ -351,10 +377,11 @@ class B200Engine:
 
     def profile_iteration(self, z, lr, it):
         out = (C.c_double * 6)()
-        self._check(self.lib.pxr_profile_iteration(self.h, self._p_inplace(z, "z"), C.c_float(lr), it, out),
-                    "pxr_profile_iteration")
+        tb = C.c_double(0.0)
+        self._check(self.lib.pxr_profile_iteration2(self.h, self._p_inplace(z, "z"), C.c_float(lr), it, out, C.byref(tb)),
+                    "pxr_profile_iteration2")
         return dict(gemm_ms=out[0], gemm_launches=int(out[1]), gemm_flops=out[2], other_ms=out[3],
-                    other_launches=int(out[4]), total_ms=out[5])
+                    other_launches=int(out[4]), total_ms=out[5], gemm_bytes=tb.value)
 
     def stream_ptr(self):
         p = C.c_void_p()

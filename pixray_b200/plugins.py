@@ -408,7 +408,10 @@ class Optimizer:
         z.grad = None
 
     def step(self):
-        self.session.engine.step(self.drawer.get_z(), self.lr, self.session.cur_iteration)
+        z = self.drawer.get_z()
+        if getattr(z, "grad", None) is not None:  # the gradient the loop accumulated (several passes when batches > 1)
+            self.session.engine.set_z_grad(z.grad.contiguous())
+        self.session.engine.step(z, self.lr, self.session.cur_iteration)
 
 
 def train_iteration(session: Session, drawer, make_cutouts, perceptors, prompt_table, opt):

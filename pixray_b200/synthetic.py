@@ -155,3 +155,84 @@ def vqgan_decoder_fwd_flops(v, image_hw):
             curr *= 2
     fl += conv(block_in, 3, 3, px)
     return fl
+
+
+def vdiff_state_dict(seed=0, c=128):
+    """cc12m_1's tensors under the checkpoint's own keys (diffusion/models/cc12m_1.py:115-241), seeded random with the
+    module defaults' scale (uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)), then * sqrt(1/2) as cc12m_1.py:239-241 does)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def uni(*shape, fan_in):
+        b = (1.0 / fan_in) ** 0.5 * 0.5 ** 0.5
+        return (torch.rand(*shape, generator=g) * 2 - 1) * b
+
+    def linear(key, cin, cout, bias=True):
+        sd[key + ".weight"] = uni(cout, cin, fan_in=cin)
+        if bias:
+            sd[key + ".bias"] = uni(cout, fan_in=cin)
+
+    def conv(key, cin, cout, k, bias=True):
+        sd[key + ".weight"] = uni(cout, cin, k, k, fan_in=cin * k * k)
+        if bias:
+            sd[key + ".bias"] = uni(cout, fan_in=cin * k * k)
+
+    sd["mapping_timestep_embed.weight"] = torch.randn(64, 1, generator=g)
+    sd["timestep_embed.weight"] = torch.randn(8, 1, generator=g)
+    linear("mapping.0.skip", 640, 1024, bias=False)
+    linear("mapping.0.main.0", 640, 1024)
+    linear("mapping.0.main.2", 1024, 1024)
+    linear("mapping.1.main.0", 1024, 1024)
+    linear("mapping.1.main.2", 1024, 1024)
+    cs = [c, c * 2, c * 2, c * 4, c * 4, c * 8, c * 8]
+
+    def block(key, cin, cmid, cout, last=False):
+        if cin != cout:
+            conv(key + ".skip", cin, cout, 1, bias=False)
+        conv(key + ".main.0", cin, cmid, 3)
+        linear(key + ".main.2.layer", 1024, cmid * 2, bias=False)
+        conv(key + ".main.4", cmid, cout, 3)
+        if not last:
+            linear(key + ".main.6.layer", 1024, cout * 2, bias=False)
+
+    def attn(key, ch):
+        sd[key + ".norm.weight"] = torch.ones(ch)
+        sd[key + ".norm.bias"] = torch.zeros(ch)
+        conv(key + ".qkv_proj", ch, ch * 3, 1)
+        conv(key + ".out_proj", ch, ch, 1)
+
+    def stage(prefix, lv):
+        # SkipBlock: main = [AvgPool2d, blocks (+ attention from level 4 on), nested SkipBlock, blocks, Upsample]
+        cin, cc = cs[lv - 1], cs[lv]
+        i = 1  # index 0 is the AvgPool2d
+        if lv < 6:
+            for (a, m, o) in [(cin, cc, cc), (cc, cc, cc), (cc, cc, cc), (cc, cc, cc)]:
+                block(f"{prefix}.{i}", a, m, o)
+                i += 1
+                if lv >= 4:
+                    attn(f"{prefix}.{i}", o)
+                    i += 1
+            stage(f"{prefix}.{i}.main", lv + 1)
+            i += 1
+            for (a, m, o) in [(cc * 2, cc, cc), (cc, cc, cc), (cc, cc, cc), (cc, cc, cin)]:
+                block(f"{prefix}.{i}", a, m, o)
+                i += 1
+                if lv >= 4:
+                    attn(f"{prefix}.{i}", o)
+                    i += 1
+        else:
+            for (a, m, o) in [(cin, cc, cc)] + [(cc, cc, cc)] * 6 + [(cc, cc, cin)]:
+                block(f"{prefix}.{i}", a, m, o)
+                i += 1
+                attn(f"{prefix}.{i}", o)
+                i += 1
+
+    block("net.0", 3 + 16, cs[0], cs[0])
+    for k in (1, 2, 3):
+        block(f"net.{k}", cs[0], cs[0], cs[0])
+    stage("net.4.main", 1)
+    block("net.5", cs[0] * 2, cs[0], cs[0])
+    block("net.6", cs[0], cs[0], cs[0])
+    block("net.7", cs[0], cs[0], cs[0])
+    block("net.8", cs[0], cs[0], 3, last=True)
+    return sd

@@ -96,6 +96,12 @@ class FakeEngine:
         self._log("backward")
         return torch.ones(self.z_shape)
 
+    def set_z_grad(self, g):
+        self._log("set_z_grad", shape=tuple(g.shape))
+
+    def set_batches(self, batches):
+        self._log("set_batches", batches=batches)
+
     def step(self, z, lr, it=0):
         self._log("step", lr=lr, it=it)
         return z

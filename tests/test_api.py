@@ -122,10 +122,17 @@ def test_text_prompts_need_a_text_tower(fake, tmp_path):
 
 
 def test_unbuilt_configurations_fail_loudly(fake, tmp_path):
-    for kw in (dict(clip_models="RN50"), dict(size=[128, 64]), dict(quality="best", clip_models="ViT-B/16")):
+    for kw in (dict(clip_models="RN50"), dict(size=[128, 64])):
         api.reset_settings()
         with pytest.raises(NotImplementedError):
             _init(tmp_path, prompts="x", **kw)
+
+
+def test_batches_preset_reaches_the_engine(fake, tmp_path):
+    """quality='best' means batches = 2 (pixray.py:1864-1878): two ascend_txt + backward passes per optimiser step."""
+    args = _init(tmp_path, prompts="x", quality="best", clip_models="ViT-B/16", size=[128, 128])
+    assert args.batches == 2
+    assert ("set_batches", {"batches": 2}) in api._state.engine.calls
 
 
 def test_do_run_scheduled_learning_rate_drops(fake, tmp_path):
@@ -223,7 +230,7 @@ def test_plugin_train_iteration_call_sequence(fake, tmp_path):
     losses = P.train_iteration(st.session, st.drawer, st.make_cutouts, st.perceptors, st.prompt_tables, opt)
     assert len(losses) == 3
     assert eng.names() == ["reset_optimizer", "synth", "make_cutouts", "encode_image", "prompt_loss", "prompt_loss",
-                           "prompt_loss", "backward", "step"]
+                           "prompt_loss", "backward", "set_z_grad", "step"]
     assert not any(c[1]["passed_embeds"] for c in eng.calls if c[0] == "prompt_loss")
     mc = [c for c in eng.calls if c[0] == "make_cutouts"][0][1]
     assert mc["transforms"] == "ndarray" and mc["color_jitter"] == "ndarray" and mc["noise"] == "Tensor"

@@ -46,16 +46,17 @@ def test_plugin_loop_matches_the_fused_iteration():
     opt.step()
     drawer.clip_z()
     assert np.abs(got - losses).max() < 1e-5
-    # Same kernels on the same inputs -- but cutout_bwd scatters with fp32 atomics, so z.grad differs in its last bits
-    # between two runs, and Adam's FIRST step is lr * g / (|g| + eps): an element whose gradient is rounding noise around
-    # zero can flip sign and move by 2 lr.  So: the gradients agree to rounding, and the updates agree wherever the
-    # gradient is above that noise.
+    # Same kernels on the same inputs -- but cutout_bwd scatters with fp32 atomics, so d loss / d image differs in its last
+    # bits between two runs; the fp16 decoder backward re-quantises that (one fp16 ulp = 5e-4 relative), so z.grad agrees to
+    # ~1e-3 of its maximum, not bit for bit.  Adam's FIRST step is lr * g / (|g| + eps): an element whose gradient is at
+    # that noise level can flip sign and move by 2 lr.  So: the gradients agree to the fp16 noise, and the updates agree
+    # wherever the gradient is well above it.
     g_plugin = drawer.get_z().grad
     g_fused = g_fused.to(g_plugin.device)
     gmax = g_fused.abs().max().item()
-    assert (g_plugin - g_fused).abs().max().item() <= 1e-4 * gmax
-    solid = g_fused.abs() > 1e-3 * gmax
-    assert solid.float().mean().item() > 0.5
+    assert (g_plugin - g_fused).abs().max().item() <= 5e-3 * gmax
+    solid = g_fused.abs() > 5e-2 * gmax
+    assert solid.float().mean().item() > 0.2
     assert ((drawer.get_z() - z_fused).abs() * solid).max().item() < 1e-5
 
 
@@ -104,4 +105,6 @@ def test_color_jitter_device_body_matches_the_host_body():
         tol = 2e-3 * (1.0 + np.abs(h_gin).max(axis=1))
         print(f"[parity] device vs host jitter body, order {order}: fwd {e_f:.2e}, vjp median {np.median(err):.2e}, "
               f"frac off-piece {float((err > tol).mean()):.2e}")
-        assert e_f <= 2e-4 and np.median(err) <= 1e-4 and (err > tol).mean() < 1e-3
+        # values go through exactly rounded operations on both sides (color_jitter.cuh): bit-identical forward, and so the
+        # same Jacobian piece for EVERY colour, the exact channel ties and sector boundaries of clamped images included
+        assert e_f == 0.0 and np.median(err) <= 1e-5 and (err > tol).mean() == 0.0

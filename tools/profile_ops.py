@@ -1,7 +1,10 @@
 """Per-op CUDA-event profile of one full-size (BASELINE config 2) iteration: sets PXR_PROFILE_DUMP so that
 pxr_profile_iteration writes one CSV row per op, then prints the rows grouped by label (sum of 3 profiled iterations / 3).
 
-    python tools/profile_ops.py [out.csv]
+    python tools/profile_ops.py [out.csv] [cutn]
+
+cutn = 8 reproduces, on ONE GPU, the per-rank shapes of the 8-way cutout-sharded run (M = 8 x 197 tokens per GEMM) without
+the collectives: where the small-M regime loses time.
 """
 import collections
 import csv
@@ -12,6 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/ops.csv"
+cutn = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
 os.environ["PXR_PROFILE_DUMP"] = out + ".tmp"
 from pixray_b200 import engine as E  # noqa: E402
@@ -21,7 +25,7 @@ vq_sd = S.vqgan_state_dict(E.VQGAN_F16_16384, 0)
 clip_sd = S.clip_state_dict(E.CLIP_ARCH["ViT-B/16"], 1)
 prompts = S.prompts(512, (1.0, 0.1), 2)
 z = S.z0_vqgan(vq_sd["quantize.embedding.weight"], (16, 16), 3).cuda()
-eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=(256, 256), cutn=64, clip=[E.CLIP_ARCH["ViT-B/16"]], seed=0)
+eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=(256, 256), cutn=cutn, clip=[E.CLIP_ARCH["ViT-B/16"]], seed=0)
 eng.load_module(E.MOD_VQGAN, vq_sd)
 eng.load_module(E.MOD_CLIP0, clip_sd)
 eng.finalize()
