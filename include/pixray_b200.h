@@ -113,6 +113,10 @@ int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int 
  * perceptor's text prompts in the loss vector.  Cutout-sharded ranks exchange the [cutn, D] rows (one allreduce).
  * n = 0 clears. */
 int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* weights);
+/* the same with every target at its own size: imgs[k] fp32 [3, hs[k], ws[k]] (resize_image keeps the source aspect and never
+ * upsamples, pixray.py:514-518; MakeCutouts pools any size to cut_size x cut_size, pixray.py:463) */
+int pxr_set_image_prompts_sized(pxr_handle h, const float* const* imgs, const int* hs, const int* ws, int n,
+                                const float* weights);
 
 /* Multi-GPU: 128-byte ncclUniqueId from rank 0; the engine owns the communicator. */
 int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world);

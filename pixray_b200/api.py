@@ -330,9 +330,9 @@ def do_init(args):
     world = int(getattr(args, "b200_world", 1) or 1)
     if world > 1:
         kw.update(rank=int(args.b200_rank), world=world)
-    if kind == E.DRAWER_PIXEL:
-        ps = getattr(args, "pixel_size", None)
-        kw["grid"] = (ps[1], ps[0]) if ps else (sideY, sideX)
+    if kind == E.DRAWER_PIXEL:  # fast_pixeldrawer.py:37-63: 40x40 / 40x50 / 80x45 default grid, pixel_scale, clamp to canvas
+        kw["grid"] = P.FastPixelDrawer.grid_for((sideX, sideY), getattr(args, "pixel_size", None), getattr(args, "pixel_scale", None))
+        print(f"Running fast pixeldrawer with {kw['grid'][1]}x{kw['grid'][0]} grid")
     if kind == E.DRAWER_FFT:
         kw.update(fft_decay=args.fft_decay, fft_colors=args.fft_colors)
     eng = _engine_factory(**kw)
@@ -407,7 +407,7 @@ def do_init(args):
     if args.image_prompts:
         imgs = [_load_image(p, sideX, sideY) for p in args.image_prompts]
         w = None if args.image_prompt_weight is None else [args.image_prompt_weight] * len(imgs)
-        eng.set_image_prompts(torch.cat(imgs), w)
+        eng.set_image_prompts(imgs, w)  # each at its own (aspect-preserving) size
 
     # ---- custom losses: "name:weight,name2->arg" (pixray.py:961-990)
     st.custom = []
@@ -439,15 +439,18 @@ def do_init(args):
 
 
 def _load_image(src, sideX, sideY):
+    """Image.open(path).convert('RGB') -> resize_image(img, (sideX, sideY)) -> to_tensor (pixray.py:949-953, 514-518): the
+    source aspect ratio is kept and the image is never upsampled beyond the canvas AREA; MakeCutouts pools whatever size
+    comes out.  Tensors ([1|-, 3, h, w] in [0, 1]) are taken as they are."""
     if torch.is_tensor(src):
-        t = src.to(torch.float32).reshape(1, 3, *src.shape[-2:])
-    else:
-        from PIL import Image  # only needed for file image prompts
-        img = Image.open(src).convert("RGB").resize((sideX, sideY), Image.LANCZOS)  # resize_image, pixray.py:514-518
-        t = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
-    if tuple(t.shape[-2:]) != (sideY, sideX):
-        t = torch.nn.functional.interpolate(t, size=(sideY, sideX), mode="bilinear", align_corners=False)
-    return t.contiguous()
+        return src.to(torch.float32).reshape(1, 3, *src.shape[-2:]).contiguous()
+    from PIL import Image  # only needed for file image prompts
+    img = Image.open(src).convert("RGB")
+    ratio = img.size[0] / img.size[1]
+    area = min(img.size[0] * img.size[1], sideX * sideY)
+    size = round((area * ratio) ** 0.5), round((area / ratio) ** 0.5)
+    img = img.resize(size, Image.LANCZOS)
+    return torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0).contiguous()
 
 
 def rebuild_optimisers(args):

@@ -122,7 +122,8 @@ class Engine {
   float* losses_host = nullptr;  // pinned
   int total_prompts = 0;
   // image prompts (pixray.py:1308-1336): target images, cut + encoded every iteration with the cached transforms
-  float* img_prompts = nullptr;  // [n_img, 3, H, W]
+  float* img_prompts = nullptr;  // [n_img, 3, cs, cs]: the POOLED targets ((avg + max) / 2 of each image at its own size,
+                                 // pixray.py:463): constants, pooled once when they are set, not every iteration
   int n_img = 0;
   std::vector<float> img_w;
   void rebuild_prompt_rows();
@@ -1477,15 +1478,15 @@ void Engine::rebuild_prompt_rows() {
 // the main pass, which then overwrites every buffer used here.
 void Engine::encode_image_prompts() {
   if (n_img == 0) return;
-  const size_t npx = (size_t)3 * cfg.image_h * cfg.image_w;
+  const size_t ncs = (size_t)3 * cfg.cut_size * cfg.cut_size;
   for (int k = 0; k < n_img; ++k) {
     CutoutArgs a = cut_args;
     a.jitter = nullptr;
     a.iter = cut_args.iter + (k + 1) * (1 << 24);  // engine-drawn noise: an independent Philox stream per call
-    pool_forward(img_prompts + k * npx, cfg.image_h, cfg.image_w, cfg.cut_size, pooled, pool_argmax, st);
+    a.pooled = img_prompts + k * ncs;
     cutout_forward(a, batch, part_min, part_max, part_imin, part_imax, st);
     minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
-    launches += 3;
+    launches += 2;
     if (comm) {
       range_pack(range, xbuf, st);
       nccl_check(Comm::api().all_reduce(xbuf, xbuf, 2, Comm::kFloat32, Comm::kMin, comm, st), "allreduce(min,max)");
@@ -1817,24 +1818,48 @@ int pxr_set_prompts(pxr_handle h, int clip_idx, const float* embeds, int n, int 
   });
 }
 
-int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* weights) {
+// Image prompts at their own sizes (the reference keeps each target at its aspect-preserving size, resize_image
+// pixray.py:514-518, and MakeCutouts pools whatever it is given to cut_size x cut_size, pixray.py:463): imgs[k] is host or
+// device fp32 [3, hs[k], ws[k]] in [0, 1].  Pooled here, once.
+int pxr_set_image_prompts_sized(pxr_handle h, const float* const* imgs, const int* hs, const int* ws, int n,
+                                const float* weights) {
   PXR_TRY(h, {
     Engine* e = h->e;
     if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
-    if (n < 0 || (n > 0 && !imgs)) throw EngineError(-17, "pxr_set_image_prompts: bad arguments");
-    const size_t npx = (size_t)3 * e->cfg.image_h * e->cfg.image_w;
+    if (n < 0 || (n > 0 && (!imgs || !hs || !ws))) throw EngineError(-17, "pxr_set_image_prompts: bad arguments");
+    const size_t ncs = (size_t)3 * e->cfg.cut_size * e->cfg.cut_size;
     e->n_img = n;
     e->img_w.assign(n, 1.f);
     if (weights)
       for (int k = 0; k < n; ++k) e->img_w[k] = weights[k];
     e->dfree(e->img_prompts);
     if (n > 0) {
-      e->img_prompts = e->dalloc<float>(npx * n);
-      PXR_CUDA(cudaMemcpyAsync(e->img_prompts, imgs, sizeof(float) * npx * n, cudaMemcpyDefault, e->st));
-      PXR_CUDA(cudaStreamSynchronize(e->st));
+      e->img_prompts = e->dalloc<float>(ncs * n);
+      for (int k = 0; k < n; ++k) {
+        if (hs[k] < 1 || ws[k] < 1 || !imgs[k]) throw EngineError(-17, "pxr_set_image_prompts: empty image");
+        float* tmp = nullptr;
+        const size_t bytes = sizeof(float) * 3 * hs[k] * ws[k];
+        PXR_CUDA(cudaMalloc(&tmp, bytes));
+        cudaError_t ce = cudaMemcpyAsync(tmp, imgs[k], bytes, cudaMemcpyDefault, e->st);
+        if (ce == cudaSuccess) {
+          pxr::pool_forward(tmp, hs[k], ws[k], e->cfg.cut_size, e->img_prompts + k * ncs, e->pool_argmax, e->st);
+          ce = cudaStreamSynchronize(e->st);
+        }
+        cudaFree(tmp);
+        if (ce != cudaSuccess) throw EngineError(-200, std::string("image prompt upload failed: ") + cudaGetErrorString(ce));
+      }
     }
     e->rebuild_prompt_rows();
   });
+}
+
+int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* weights) {
+  if (!h) return -10;
+  const int H = h->e->cfg.image_h, W = h->e->cfg.image_w;
+  std::vector<const float*> ptrs(n > 0 ? n : 0);
+  std::vector<int> hs(ptrs.size(), H), ws(ptrs.size(), W);
+  for (size_t k = 0; k < ptrs.size(); ++k) ptrs[k] = imgs ? imgs + k * (size_t)3 * H * W : nullptr;
+  return pxr_set_image_prompts_sized(h, ptrs.data(), hs.data(), ws.data(), n, weights);
 }
 
 int pxr_synth(pxr_handle h, const float* z, float* out_img) {

@@ -147,17 +147,26 @@ class B200Engine:
         self.n_prompts[clip_idx] = n + self._n_img
 
     def set_image_prompts(self, imgs, weights=None):
-        """Image prompts (pixray.py:1308-1336): target images [n, 3, H, W] in [0, 1] at the output size.  Every iteration
-        each is cut with that iteration's cached transforms, encoded by every perceptor and scored as a throwaway
-        Prompt(embed [cutn, D], weight) appended after the perceptor's text prompts.  n = 0 clears them."""
+        """Image prompts (pixray.py:1308-1336): target images in [0, 1], each [1|-, 3, h, w] at ITS OWN size (a list), or one
+        [n, 3, H, W] tensor.  Every iteration each is cut with that iteration's cached transforms, encoded by every
+        perceptor and scored as a throwaway Prompt(embed [cutn, D], weight) appended after the perceptor's text prompts.
+        n = 0 clears them."""
         if imgs is None or len(imgs) == 0:
-            n, ptr, wp = 0, None, None
+            items = []
+        elif torch.is_tensor(imgs):
+            items = [t for t in torch.as_tensor(imgs, dtype=torch.float32).reshape(-1, 3, *imgs.shape[-2:])]
         else:
-            t = torch.as_tensor(imgs, dtype=torch.float32).reshape(-1, 3, *self.image_hw).contiguous().cpu()
-            n, ptr = t.shape[0], C.c_void_p(t.data_ptr())
-            w = np.ascontiguousarray(np.asarray([1.0] * n if weights is None else weights, dtype=np.float32).reshape(n))
+            items = [torch.as_tensor(t, dtype=torch.float32).reshape(3, *t.shape[-2:]) for t in imgs]
+        items = [t.contiguous().cpu() for t in items]
+        n = len(items)
+        ptrs = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in items])
+        hs = (C.c_int * max(n, 1))(*[t.shape[1] for t in items])
+        ws = (C.c_int * max(n, 1))(*[t.shape[2] for t in items])
+        wp = None
+        if n and weights is not None:
+            w = np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(n))
             wp = w.ctypes.data_as(C.c_void_p)
-        self._check(self.lib.pxr_set_image_prompts(self.h, ptr, n, wp), "pxr_set_image_prompts")
+        self._check(self.lib.pxr_set_image_prompts_sized(self.h, ptrs, hs, ws, n, wp), "pxr_set_image_prompts_sized")
         self._n_img = n
         self.n_prompts = [t_ + n for t_ in self._n_text]
 

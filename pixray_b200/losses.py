@@ -184,14 +184,33 @@ class GaussianLoss(LossInterface):
 
 
 class AestheticLoss(LossInterface):
-    """Losses/AestheticLoss.py; the linear AVA head is passed in (`args.aesthetic_head = {"weight": [1, D], "bias": [1]}`)
-    instead of being downloaded (AestheticLoss.py:18-20)."""
+    """Losses/AestheticLoss.py.  The reference downloads the linear AVA head to models/ava_vit_b_16_linear.pth
+    (AestheticLoss.py:15-20); there is no network here, so the head comes in through the extra setting `aesthetic_head`:
+    the path of that .pth file, or the dict it holds ({"weight": [1, D], "bias": [1]}); default = the reference's path."""
     kind = E.LOSS_AESTHETIC
+    default_path = "models/ava_vit_b_16_linear.pth"
 
     @staticmethod
     def add_settings(parser):
         parser.add_argument("--aesthetic_target", type=float, help="0-10", default=10, dest="aesthetic_target")
+        parser.add_argument("--aesthetic_head", help="path of ava_vit_b_16_linear.pth, or its {'weight','bias'} dict",
+                            default=None, dest="aesthetic_head")
         return parser
+
+    def parse_settings(self, args):
+        head = getattr(args, "aesthetic_head", None)
+        if head is None:
+            head = self.default_path
+        if isinstance(head, (str, bytes)) or hasattr(head, "__fspath__"):
+            import os
+            if not os.path.exists(head):
+                raise FileNotFoundError(f"aesthetic loss: linear head '{head}' not found (the reference downloads it from "
+                                        "https://dazhi.art/f/ava_vit_b_16_linear.pth; pass aesthetic_head=<path or dict>)")
+            head = torch.load(head, map_location="cpu", weights_only=False)  # layer_weights, AestheticLoss.py:23
+        if not (isinstance(head, dict) and "weight" in head and "bias" in head):
+            raise ValueError("aesthetic_head must hold 'weight' [1, D] and 'bias' [1]")
+        args.aesthetic_head = head
+        return args
 
     def engine_params(self, args, session):
         head = args.aesthetic_head

@@ -114,11 +114,37 @@ class FastPixelDrawer(DrawingInterface):
         parser.add_argument("--pixel_scale", type=float, help="Pixel scale", default=None, dest="pixel_scale")
         return parser
 
+    @staticmethod
+    def grid_for(size, pixel_size=None, pixel_scale=None, verbose=True):
+        """(num_rows, num_cols) as FastPixelDrawer.__init__ derives them (fast_pixeldrawer.py:37-63): an explicit
+        pixel_size (width, height), else 40x40 on a square canvas, 40x50 on a portrait one, 80x45 on a landscape one; divided
+        by pixel_scale; never larger than the canvas."""
+        canvas_width, canvas_height = size
+        if pixel_size is not None:
+            num_cols, num_rows = pixel_size
+        elif canvas_width == canvas_height:
+            num_cols, num_rows = 40, 40
+        elif canvas_width < canvas_height:
+            num_cols, num_rows = 40, 50
+        else:
+            num_cols, num_rows = 80, 45
+        if pixel_scale is not None and pixel_scale > 0:
+            num_cols, num_rows = int(num_cols / pixel_scale), int(num_rows / pixel_scale)
+        shrink = False
+        if num_cols > canvas_width:
+            shrink, num_cols = True, canvas_width
+        if num_rows > canvas_height:
+            shrink, num_rows = True, canvas_height
+        if shrink and verbose:
+            print("pixel grid size should not be larger than output pixel size: reducing pixel grid")
+        return num_rows, num_cols
+
     def __init__(self, settings, session: Session):
         super().__init__(settings)
         self.session = session
         self.pixel_size = (session.engine.z_shape[2], session.engine.z_shape[3])
         self.output_size = session.engine.image_hw
+        self.num_rows, self.num_cols = self.pixel_size
         self.z = None
 
     def get_opts(self, decay_divisor):

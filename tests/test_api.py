@@ -202,7 +202,8 @@ def test_custom_losses_and_image_prompts_reach_the_engine(fake, tmp_path):
     eng = api._state.engine
     assert [a[0] for a in eng.aux] == [E.LOSS_SMOOTHNESS, E.LOSS_SYMMETRY] and eng.aux[0][1] == 0.5 and eng.aux[1][1] == 1
     imgs, w = eng.image_prompts
-    assert tuple(imgs.shape) == (1, 3, 64, 64) and w == [0.7]
+    # the target keeps ITS size (resize_image never forces the canvas size, pixray.py:514-518; MakeCutouts pools any size)
+    assert len(imgs) == 1 and tuple(imgs[0].shape) == (1, 3, 32, 32) and w == [0.7]
     assert api._state.loss_buf.size == eng.num_losses() == 2 + 1 + 2  # text + vector, image prompt, two custom losses
     assert api.do_run(args) is True
 
@@ -247,3 +248,50 @@ def test_package_exposes_the_reference_entry_points():
         assert callable(getattr(pixray, name)), name
     with pytest.raises(AttributeError):
         pixray.no_such_thing
+
+
+def test_pixel_drawer_grid_follows_the_reference_defaults(fake, tmp_path):
+    """fast_pixeldrawer.py:37-63: 40x40 on a square canvas when no pixel_size is given, pixel_scale divides the grid, and the
+    grid never exceeds the canvas."""
+    assert P.FastPixelDrawer.grid_for((256, 256)) == (40, 40)
+    assert P.FastPixelDrawer.grid_for((192, 108)) == (45, 80)
+    assert P.FastPixelDrawer.grid_for((128, 160)) == (50, 40)
+    assert P.FastPixelDrawer.grid_for((256, 256), pixel_scale=2.0) == (20, 20)
+    assert P.FastPixelDrawer.grid_for((256, 256), pixel_size=[64, 32]) == (32, 64)
+    assert P.FastPixelDrawer.grid_for((32, 32), verbose=False) == (32, 32)
+    args = _init(tmp_path, prompts="x", drawer="fast_pixel", clip_models="ViT-B/32", size=[256, 256])
+    assert api._state.engine.kw["grid"] == (40, 40) and tuple(api._state.drawer.get_z().shape) == (1, 3, 40, 40)
+    api.reset_settings()
+    args = _init(tmp_path, prompts="x", drawer="fast_pixel", clip_models="ViT-B/32", size=[256, 256], pixel_scale=0.5)
+    assert api._state.engine.kw["grid"] == (80, 80)
+
+
+def test_aesthetic_loss_is_usable_through_the_settings(fake, tmp_path):
+    """custom_loss='aesthetic' (pixray.py:131-140, Losses/AestheticLoss.py): the linear AVA head the reference downloads comes
+    in through `aesthetic_head` (dict or .pth path); without it the error names the missing file."""
+    head = {"weight": torch.linspace(-1, 1, 512).reshape(1, 512), "bias": torch.tensor([0.25])}
+    path = tmp_path / "ava_head.pth"
+    torch.save(head, path)
+    for spec in (head, str(path)):
+        api.reset_settings()
+        _init(tmp_path, prompts="x", clip_models="ViT-B/16", custom_loss="aesthetic:0.5", aesthetic_target=7, aesthetic_head=spec)
+        kind, weight, params = api._state.engine.aux[-1]
+        assert kind == E.LOSS_AESTHETIC and weight == 0.5
+        assert params[0] == 7 and abs(params[1] - 0.25) < 1e-7 and len(params) == 2 + 512 and abs(params[2] + 1.0) < 1e-6
+    api.reset_settings()
+    with pytest.raises(FileNotFoundError):
+        _init(tmp_path, prompts="x", clip_models="ViT-B/16", custom_loss="aesthetic")
+
+
+def test_file_image_prompts_keep_their_aspect_ratio(fake, tmp_path):
+    """resize_image (pixray.py:514-518): area = min(source area, canvas area), the source's aspect ratio is kept."""
+    from PIL import Image
+    wide = tmp_path / "wide.png"
+    Image.fromarray((np.random.default_rng(0).random((40, 160, 3)) * 255).astype(np.uint8)).save(wide)
+    big = tmp_path / "big.png"
+    Image.fromarray((np.random.default_rng(1).random((300, 200, 3)) * 255).astype(np.uint8)).save(big)
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16", size=[64, 64], image_prompts=[str(wide), str(big)])
+    imgs, _ = api._state.engine.image_prompts
+    # 160x40 (area 6400 > 64*64 = 4096): ratio 4 -> 128 x 32;  200x300: ratio 2/3 -> 52 x 78
+    assert tuple(imgs[0].shape[-2:]) == (32, 128) and tuple(imgs[1].shape[-2:]) == (78, 52)
+    assert 0.0 <= float(imgs[0].min()) and float(imgs[0].max()) <= 1.0

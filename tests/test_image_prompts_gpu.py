@@ -19,12 +19,14 @@ def test_image_prompt_losses_and_gradient():
     J = cutouts.sample_color_jitter(cutn, 23)
     g = torch.Generator().manual_seed(29)
     facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
-    targets = [torch.rand(1, 3, 32, 32, generator=g), torch.rand(1, 3, 32, 32, generator=g) * 0.5 + 0.25]
+    # the second target has its OWN size (resize_image keeps the source aspect, pixray.py:514-518; MakeCutouts pools any
+    # size to cut_size x cut_size, pixray.py:463), larger than the canvas in one direction: ragged pooling windows
+    targets = [torch.rand(1, 3, 32, 32, generator=g), torch.rand(1, 3, 300, 100, generator=g) * 0.5 + 0.25]
     weights = [0.8, -0.4]
     tp = list(zip(targets, weights))
     synth = lambda zz: R.vqgan_synth(vq, zz)  # noqa: E731
     ref_text_only = R.iterate(synth, z, [clip], [prompts], torch.from_numpy(T), cs, "reflection", 0.45, facs, noise)
-    eng.set_image_prompts(torch.cat(targets), weights)
+    eng.set_image_prompts(targets, weights)
     assert eng.num_losses() == len(prompts) + 2
     losses = None
     # with the main pass jittered (the targets' cutouts are not, pixray.py:480-486): loss vector; without: z.grad at the
