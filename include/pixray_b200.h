@@ -66,12 +66,16 @@ typedef struct {
   float beta1, beta2, adam_eps; /* optim.Adam defaults 0.9 / 0.999 / 1e-8 when 0 */
   /* fft drawer (fftdrawer.py:16-22, 57-61): fft_image(decay_power) / to_valid_rgb(colors) / image_f(contrast) */
   float fft_decay, fft_colors, fft_contrast; /* 0 -> 1.5 / 1.5 / 0.9 */
-  int reserved[5];
+  /* global_aspect_width = args.size[0] / args.size[1] (pixray.py:1931): != 1 stretches the pooled cut_size x cut_size image
+   * to [cut_size, int(cut_size * a)] (a > 1) or [int(cut_size / a), cut_size] (a < 1) before the warps (pixray.py:468-472)
+   * and changes the wide stack's affine (pixray.py:420-432).  0 = 1 (square). */
+  float cut_aspect;
+  int reserved[4];
 } pxr_config;
 
 /* Per-iteration cutout parameters: what kornia's augmentations sample per cutout, made explicit.
  * transforms[cutn*9]: row-major 3x3 "dst_pix <- src_pix" homographies exactly as MakeCutouts.transforms caches them
- * (pixray.py:498); indices [0, int(0.6*cutn)) form the zoom group, the rest the wide group (pixray.py:407, 493-494). */
+ * (pixray.py:498; src = the pooled image, stretched when cut_aspect != 1); indices [0, int(0.6*cutn)) form the zoom group, the rest the wide group (pixray.py:407, 493-494). */
 typedef struct {
   const float* transforms; /* host, [cutn, 3, 3] */
   int zoom_padding;        /* PXR_PAD_REFLECTION on even iterations, PXR_PAD_BORDER on odd (pixray.py:1250-1253) */

@@ -150,8 +150,19 @@ def warp_perspective(src, M, dsize, padding_mode="zeros", fill_value=None, align
     return F.grid_sample(src, grid, align_corners=align_corners, mode="bilinear", padding_mode=padding_mode)
 
 
+def rescale_for_aspect(pooled, aspect):
+    """pixray.py:468-472: kornia.geometry.transform.rescale(cutout, (1, aspect)) / ((1 / aspect, 1)) -- kornia 0.6.2 rescale
+    is resize(input, (int(h * fv), int(w * fh)), 'bilinear', align_corners=None), i.e. F.interpolate(..., align_corners=False)
+    [UPSTREAM, un-vendored]."""
+    if aspect == 1.0:
+        return pooled
+    h, w = pooled.shape[-2:]
+    size = (int(h * 1), int(w * aspect)) if aspect > 1.0 else (int(h * (1.0 / aspect)), int(w * 1))
+    return F.interpolate(pooled, size=size, mode="bilinear", align_corners=False)
+
+
 def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None, noise=None, cutn_zoom=None,
-                 jitter=None):
+                 jitter=None, aspect=1.0):
     """MakeCutouts.forward on explicit (cached) transforms, pixray.py:445-511.
 
     img [1, 3, H, W]; transforms [cutn, 3, 3]; zoom group = first int(0.6 * cutn) (pixray.py:407) warped with
@@ -162,6 +173,7 @@ def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None,
     if cutn_zoom is None:
         cutn_zoom = int(0.6 * cutn)
     pooled = pool_avg_max(img, cut_size)  # identical for every cutout (pixray.py:461-478)
+    pooled = rescale_for_aspect(pooled, aspect)  # global_aspect_width != 1 (pixray.py:468-472)
     src = pooled.expand(cutn, -1, -1, -1)
     parts = []
     if cutn_zoom > 0:
@@ -933,7 +945,7 @@ class AdamState:
 
 
 def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=(),
-            jitter=None, image_prompts=()):
+            jitter=None, image_prompts=(), aspect=1.0):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
@@ -943,7 +955,7 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
     out.retain_grad()
-    batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise, jitter=jitter)
+    batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise, jitter=jitter, aspect=aspect)
     batch.retain_grad()
     losses, embeds = [], []
     for model, pms in zip(clip_models, prompts):
@@ -955,7 +967,7 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
         # no ColorJitter (pixray.py:480-486) -- and the [cutn, D] embedding becomes a throwaway Prompt(embed, weight)
         for (timg, weight) in image_prompts:
             with torch.no_grad():
-                tb = make_cutouts(timg, transforms, cut_size, zoom_padding, fill, noise_facs, noise)
+                tb = make_cutouts(timg, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aspect=aspect)
                 te = encode_image(model, tb).float()
             losses.append(prompt_loss(iii, te, weight, float("-inf")))
     for (lossweight, fn) in aux:

@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("op_dtype", C.c_int), ("grad_scale", C.c_float),
         ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
         ("fft_decay", C.c_float), ("fft_colors", C.c_float), ("fft_contrast", C.c_float),
-        ("reserved", C.c_int * 5),
+        ("cut_aspect", C.c_float), ("reserved", C.c_int * 4),
     ]
 
 

@@ -321,12 +321,14 @@ def do_init(args):
     kind = _DRAWER_KIND[args.drawer]
     n_levels = len(E.VQGAN_F16_16384["ch_mult"]) if kind == E.DRAWER_VQGAN else None
     sideX, sideY = _side(args, n_levels)
-    if sideX != sideY:
-        raise NotImplementedError(f"non-square canvases ({sideX}x{sideY}: global_aspect_width != 1 rescales the cutouts, "
-                                  "pixray.py:470-476) are not built; pass aspect='square' or size=[n, n]")
+    # global_aspect_width = args.size[0] / args.size[1] (pixray.py:1931: the REQUESTED size, before the drawer rounds it):
+    # != 1 stretches the pooled image before the warps and changes the wide augmentation stack (pixray.py:420-432, 468-472)
+    aspect = float(args.size[0]) / float(args.size[1])
     device = int(str(args.cuda_device).split(":")[1]) if ":" in str(args.cuda_device) else 0
     clip_cfgs = [E.CLIP_ARCH[m] for m in args.clip_models]
     kw = dict(drawer=kind, image_hw=(sideY, sideX), cutn=args.num_cuts, clip=clip_cfgs, seed=st.seed, device=device)
+    if aspect != 1.0:
+        kw["cut_aspect"] = aspect
     world = int(getattr(args, "b200_world", 1) or 1)
     if world > 1:
         kw.update(rank=int(args.b200_rank), world=world)
@@ -370,7 +372,8 @@ def do_init(args):
         drawer.init_from_tensor(None)
     st.drawer = drawer
     st.perceptors = [P.Perceptor(st.session, i) for i in range(len(args.clip_models))]
-    st.make_cutouts = P.MakeCutouts(clip_cfgs[0]["image_res"], args.num_cuts, st.session, cut_pow=args.cut_pow, seed=st.seed)
+    st.make_cutouts = P.MakeCutouts(clip_cfgs[0]["image_res"], args.num_cuts, st.session, cut_pow=args.cut_pow, seed=st.seed,
+                                    aspect=aspect)
 
     # ---- prompts, in the order ascend_txt scores them (pixray.py:859-958): text, vector, noise; then image prompts
     tables = [[] for _ in args.clip_models]

@@ -69,6 +69,10 @@ class Engine {
 
   // ---- cutouts
   float *pooled = nullptr, *g_pooled = nullptr, *batch = nullptr, *g_batch = nullptr;
+  // non-square canvas (cfg.cut_aspect != 1): the warps sample from a stretch of the pooled image (pixray.py:468-472)
+  double aspect = 1.0;
+  int src_h = 0, src_w = 0;
+  float *cut_src = nullptr, *g_cut_src = nullptr;  // [3, src_h, src_w]; == pooled / g_pooled when square
   int* pool_argmax = nullptr;
   float *part_min = nullptr, *part_max = nullptr, *range = nullptr, *sums = nullptr;
   int *part_imin = nullptr, *part_imax = nullptr, *irange = nullptr;
@@ -114,6 +118,7 @@ class Engine {
     int n_text = 0, n_rows = 0;
     int* pslot = nullptr;
     float* pinv = nullptr;
+    float* scratch = nullptr;  // pxr_prompt_loss on caller-provided embeddings
     OpList fwd, bwd;
   };
   Clip clip[2];
@@ -1004,6 +1009,16 @@ void Engine::build_cutouts() {
   const int cs_ = cfg.cut_size;
   pooled = dalloc<float>((size_t)3 * cs_ * cs_);
   g_pooled = dalloc<float>((size_t)3 * cs_ * cs_);
+  aspect = (cfg.cut_aspect > 0.f && cfg.cut_aspect != 1.f) ? (double)cfg.cut_aspect : 1.0;
+  if (aspect > 8.0 || aspect < 0.125) throw EngineError(-66, "cut_aspect (canvas width / height) must be within [1/8, 8]");
+  source_size(cs_, aspect, src_h, src_w);
+  if (aspect != 1.0) {
+    cut_src = dalloc<float>((size_t)3 * src_h * src_w);
+    g_cut_src = dalloc<float>((size_t)3 * src_h * src_w);
+  } else {
+    cut_src = pooled;
+    g_cut_src = g_pooled;
+  }
   pool_argmax = dalloc<int>((size_t)3 * cs_ * cs_);
   batch = dalloc<float>((size_t)n_local * 3 * cs_ * cs_);
   g_batch = dalloc<float>((size_t)n_local * 3 * cs_ * cs_);
@@ -1024,7 +1039,9 @@ void Engine::build_cutouts() {
     PXR_CUDA(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming));
   }
   memset(&cut_args, 0, sizeof cut_args);
-  cut_args.pooled = pooled;
+  cut_args.pooled = cut_src;
+  cut_args.src_h = src_h;
+  cut_args.src_w = src_w;
   cut_args.minv = minv_dev;
   cut_args.cs = cs_;
   cut_args.n_local = n_local;
@@ -1050,7 +1067,7 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
   float fill = p ? p->fill : 0.f;
   if (!T) {  // engine RNG, keyed by (seed, iter, global cutout index)
     gen.resize((size_t)cfg.cutn * 9);
-    sample_cutout_transforms(cfg.seed, key, cfg.cutn, cfg.cut_size, gen.data());
+    sample_cutout_transforms(cfg.seed, key, cfg.cutn, cfg.cut_size, gen.data(), aspect);
     T = gen.data();
     if (!p) fill = sample_fill(cfg.seed, key);
   }
@@ -1100,6 +1117,10 @@ void Engine::forward_cutouts() {
   if (!aux.empty())  // the cutout / embedding losses accumulate per-rank partial sums into their slots
     PXR_CUDA(cudaMemsetAsync(losses_dev + total_prompts, 0, sizeof(float) * aux.size(), st));
   pool_forward(img, cfg.image_h, cfg.image_w, cfg.cut_size, pooled, pool_argmax, st);
+  if (aspect != 1.0) {
+    rescale_bilinear(pooled, cfg.cut_size, cfg.cut_size, src_h, src_w, cut_src, st);
+    launches += 1;
+  }
   cutout_forward(cut_args, batch, part_min, part_max, part_imin, part_imax, st);
   minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
   launches += 3;
@@ -1478,7 +1499,7 @@ void Engine::rebuild_prompt_rows() {
 // the main pass, which then overwrites every buffer used here.
 void Engine::encode_image_prompts() {
   if (n_img == 0) return;
-  const size_t ncs = (size_t)3 * cfg.cut_size * cfg.cut_size;
+  const size_t ncs = (size_t)3 * src_h * src_w;
   for (int k = 0; k < n_img; ++k) {
     CutoutArgs a = cut_args;
     a.jitter = nullptr;
@@ -1594,8 +1615,13 @@ void Engine::backward_all() {
   if (!aux.empty()) aux_on_cutouts();
   if (comm)  // d/dmin, d/dmax terms need the sums over ALL cutouts
     nccl_check(Comm::api().all_reduce(sums, sums, 2, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(sums)");
-  PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * 3 * cfg.cut_size * cfg.cut_size, st));
-  cutout_backward(cut_args, g_batch, range, irange, sums, g_pooled, st);
+  PXR_CUDA(cudaMemsetAsync(g_cut_src, 0, sizeof(float) * 3 * src_h * src_w, st));
+  cutout_backward(cut_args, g_batch, range, irange, sums, g_cut_src, st);
+  if (aspect != 1.0) {
+    PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * 3 * cfg.cut_size * cfg.cut_size, st));
+    rescale_bilinear_backward(g_cut_src, cfg.cut_size, cfg.cut_size, src_h, src_w, g_pooled, st);
+    launches += 1;
+  }
   pool_backward(g_pooled, pool_argmax, cfg.image_h, cfg.image_w, cfg.cut_size, g_img, st);
   launches += 2;
   if (comm) {
@@ -1687,6 +1713,7 @@ void Engine::finalize() {
     reg("img_pre", img_pre, npx * 4);
     reg("g_img", g_img, npx * 4);
     reg("pooled", pooled, ncs * 4);
+    reg("cut_src", cut_src, (size_t)3 * src_h * src_w * 4);
     reg("pool_argmax", pool_argmax, ncs * 4);
     reg("g_pooled", g_pooled, ncs * 4);
     reg("batch", batch, ncs * n_local * 4);
@@ -1827,7 +1854,7 @@ int pxr_set_image_prompts_sized(pxr_handle h, const float* const* imgs, const in
     Engine* e = h->e;
     if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
     if (n < 0 || (n > 0 && (!imgs || !hs || !ws))) throw EngineError(-17, "pxr_set_image_prompts: bad arguments");
-    const size_t ncs = (size_t)3 * e->cfg.cut_size * e->cfg.cut_size;
+    const size_t ncs = (size_t)3 * e->src_h * e->src_w;
     e->n_img = n;
     e->img_w.assign(n, 1.f);
     if (weights)
@@ -1842,7 +1869,12 @@ int pxr_set_image_prompts_sized(pxr_handle h, const float* const* imgs, const in
         PXR_CUDA(cudaMalloc(&tmp, bytes));
         cudaError_t ce = cudaMemcpyAsync(tmp, imgs[k], bytes, cudaMemcpyDefault, e->st);
         if (ce == cudaSuccess) {
-          pxr::pool_forward(tmp, hs[k], ws[k], e->cfg.cut_size, e->img_prompts + k * ncs, e->pool_argmax, e->st);
+          if (e->aspect != 1.0) {  // pooled like the canvas, then stretched like the canvas (pixray.py:463-472)
+            pxr::pool_forward(tmp, hs[k], ws[k], e->cfg.cut_size, e->pooled, e->pool_argmax, e->st);
+            pxr::rescale_bilinear(e->pooled, e->cfg.cut_size, e->cfg.cut_size, e->src_h, e->src_w, e->img_prompts + k * ncs, e->st);
+          } else {
+            pxr::pool_forward(tmp, hs[k], ws[k], e->cfg.cut_size, e->img_prompts + k * ncs, e->pool_argmax, e->st);
+          }
           ce = cudaStreamSynchronize(e->st);
         }
         cudaFree(tmp);
@@ -1932,8 +1964,25 @@ int pxr_prompt_loss(pxr_handle h, int clip_idx, const float* embeds, float* out_
     Engine* e = h->e;
     if (clip_idx < 0 || clip_idx >= e->cfg.n_clip) throw EngineError(-14, "bad clip index");
     auto& C = e->clip[clip_idx];
-    if (embeds)
-      PXR_CUDA(cudaMemcpyAsync(C.e, embeds, sizeof(float) * C.B * C.c.out_dim, cudaMemcpyDeviceToDevice, e->st));
+    if (embeds) {
+      // Foreign embeddings (not the ones this engine's encode_image produced): scored as given into SCRATCH buffers --
+      // the perceptor's own un-normalised embeddings and their gradient (C.e / C.de, which pxr_backward consumes together
+      // with the saved ViT activations) stay what the last encode_image / prompt_loss pair left there.
+      if (C.n_prompts == 0) throw EngineError(-70, "no prompts set for perceptor " + std::to_string(clip_idx));
+      const size_t n = (size_t)C.B * C.c.out_dim;
+      if (!C.scratch) C.scratch = e->dalloc<float>(3 * n + n);  // e | e_unit | de | de16 (fp16 in the last n floats' space)
+      float *se = C.scratch, *su = C.scratch + n, *sd = C.scratch + 2 * n;
+      pxr::act_t* sd16 = reinterpret_cast<pxr::act_t*>(C.scratch + 3 * n);
+      float* sl = e->losses_scratch;
+      PXR_CUDA(cudaMemcpyAsync(se, embeds, sizeof(float) * n, cudaMemcpyDeviceToDevice, e->st));
+      PXR_CUDA(cudaMemsetAsync(sl, 0, 64 * sizeof(float), e->st));
+      pxr::prompt_loss(se, C.B, C.c.out_dim, C.prompts, C.pweights, C.pstops, C.pslot, C.pinv, C.n_rows, e->cfg.cutn, e->S, su,
+                       sl, sd, sd16, e->st);
+      e->launches += 1;
+      if (out_losses)
+        PXR_CUDA(cudaMemcpyAsync(out_losses, sl, sizeof(float) * C.n_prompts, cudaMemcpyDeviceToDevice, e->st));
+      return 0;
+    }
     PXR_CUDA(cudaMemsetAsync(e->losses_dev + C.loss_offset, 0, sizeof(float) * C.n_prompts, e->st));
     e->loss_clip(clip_idx);
     if (out_losses)

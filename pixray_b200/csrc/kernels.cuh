@@ -83,8 +83,13 @@ void fft_synth_backward(FftPlans* pl, const float* g_img, const float* img, cons
 void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* argmax, cudaStream_t st);
 void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st);
 
+// kornia.geometry.transform.rescale of the pooled image for non-square canvases (pixray.py:468-472): bilinear,
+// align_corners=False ([3, in_h, in_w] -> [3, out_h, out_w]), and its adjoint (g_in must be zeroed by the caller)
+void rescale_bilinear(const float* x, int in_h, int in_w, int out_h, int out_w, float* y, cudaStream_t st);
+void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, float* gx, cudaStream_t st);
+
 struct CutoutArgs {
-  const float* pooled;     // [3, cs, cs]
+  const float* pooled;     // [3, src_h, src_w]: the pooled image (cs x cs), stretched when the canvas is not square
   const float* minv;       // [n_local, 9] src_pix <- dst_pix homographies (device)
   const float* noise_facs; // [n_local]            (noise_mode 1)
   const float* noise;      // [n_local, 3, cs, cs] (noise_mode 1)
@@ -92,6 +97,7 @@ struct CutoutArgs {
   int noise_mode;          // 0 none, 1 explicit facs + noise, 2 engine Philox (seed, iter)
   float noise_fac;         // U(0, noise_fac) upper bound for mode 2 (pixray.py:439)
   int cs, n_local, first_global, cutn_zoom, zoom_padding;
+  int src_h, src_w;        // size of `pooled` (== cs, cs on a square canvas)
   float fill;
   uint64_t seed;
   int iter;
@@ -116,6 +122,7 @@ void patchify_forward(const float* batch, const float* range, int n, int cs, int
 void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
                        int accumulate, float* g_batch, float* sums, cudaStream_t st);
 // adds the argmin / argmax terms of the global range normalise, then scatters through the bilinear taps
+// g_pooled: [3, src_h, src_w], zeroed by the caller
 void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* range, const int* irange,
                      const float* sums, float* g_pooled, cudaStream_t st);
 

@@ -93,7 +93,7 @@ struct Taps {
   float w[4];     // nw, ne, sw, se
   bool in[4];
 };
-__device__ __forceinline__ Taps make_taps(float xs, float ys, int cs) {
+__device__ __forceinline__ Taps make_taps(float xs, float ys, int sw, int sh) {
   Taps t;
   float fx = floorf(xs), fy = floorf(ys);
   t.x0 = (int)fx;
@@ -103,8 +103,8 @@ __device__ __forceinline__ Taps make_taps(float xs, float ys, int cs) {
   t.w[1] = ax * (1.f - ay);
   t.w[2] = (1.f - ax) * ay;
   t.w[3] = ax * ay;
-  bool xin0 = t.x0 >= 0 && t.x0 < cs, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < cs;
-  bool yin0 = t.y0 >= 0 && t.y0 < cs, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < cs;
+  bool xin0 = t.x0 >= 0 && t.x0 < sw, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < sw;
+  bool yin0 = t.y0 >= 0 && t.y0 < sh, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < sh;
   t.in[0] = xin0 && yin0;
   t.in[1] = xin1 && yin0;
   t.in[2] = xin0 && yin1;
@@ -121,22 +121,69 @@ __device__ __forceinline__ void src_coord(const float* m, int u, int v, float& x
 }
 
 // one warped pixel, all three channels: bilinear taps (+ the wide group's fill under the uncovered weight)
-__device__ __forceinline__ void warp_sample(const float* __restrict__ pooled, const Taps& t, int cs, bool zoom,
+__device__ __forceinline__ void warp_sample(const float* __restrict__ pooled, const Taps& t, int sw, int sh, bool zoom,
                                             float fill, float rgb[3]) {
   float cover = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) cover += t.in[k] ? t.w[k] : 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* p = pooled + (size_t)c * cs * cs;
+    const float* p = pooled + (size_t)c * sh * sw;
     float val = 0.f;
-    if (t.in[0]) val += t.w[0] * p[t.y0 * cs + t.x0];
-    if (t.in[1]) val += t.w[1] * p[t.y0 * cs + t.x0 + 1];
-    if (t.in[2]) val += t.w[2] * p[(t.y0 + 1) * cs + t.x0];
-    if (t.in[3]) val += t.w[3] * p[(t.y0 + 1) * cs + t.x0 + 1];
+    if (t.in[0]) val += t.w[0] * p[t.y0 * sw + t.x0];
+    if (t.in[1]) val += t.w[1] * p[t.y0 * sw + t.x0 + 1];
+    if (t.in[2]) val += t.w[2] * p[(t.y0 + 1) * sw + t.x0];
+    if (t.in[3]) val += t.w[3] * p[(t.y0 + 1) * sw + t.x0 + 1];
     if (!zoom) val += (1.f - cover) * fill;  // kornia _fill_and_warp
     rgb[c] = val;
   }
+}
+
+// F.interpolate(mode='bilinear', align_corners=False) source coordinate and taps along one axis (ATen
+// area_pixel_compute_source_index: scale * (dst + 0.5) - 0.5, clamped at 0; the high tap clamps at in - 1)
+__device__ __forceinline__ void lin_taps(int o, int in, int out, int& i0, int& i1, float& l1) {
+  const float scale = (float)in / (float)out;
+  float src = scale * ((float)o + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+__global__ void rescale_fwd_kernel(const float* __restrict__ x, int in_h, int in_w, int out_h, int out_w,
+                                   float* __restrict__ y) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * out_h * out_w) return;
+  const int ox = i % out_w, oy = (i / out_w) % out_h, c = i / (out_w * out_h);
+  int x0, x1, y0, y1;
+  float lx, ly;
+  lin_taps(ox, in_w, out_w, x0, x1, lx);
+  lin_taps(oy, in_h, out_h, y0, y1, ly);
+  const float* p = x + (size_t)c * in_h * in_w;
+  // ATen: h0lambda * (w0lambda * a + w1lambda * b) + h1lambda * (w0lambda * c + w1lambda * d)
+  const float top = (1.f - lx) * p[y0 * in_w + x0] + lx * p[y0 * in_w + x1];
+  const float bot = (1.f - lx) * p[y1 * in_w + x0] + lx * p[y1 * in_w + x1];
+  y[i] = (1.f - ly) * top + ly * bot;
+}
+
+__global__ void rescale_bwd_kernel(const float* __restrict__ gy, int in_h, int in_w, int out_h, int out_w,
+                                   float* __restrict__ gx) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * out_h * out_w) return;
+  const int ox = i % out_w, oy = (i / out_w) % out_h, c = i / (out_w * out_h);
+  int x0, x1, y0, y1;
+  float lx, ly;
+  lin_taps(ox, in_w, out_w, x0, x1, lx);
+  lin_taps(oy, in_h, out_h, y0, y1, ly);
+  float* p = gx + (size_t)c * in_h * in_w;
+  const float g = gy[i];
+  atomicAdd(p + y0 * in_w + x0, (1.f - ly) * (1.f - lx) * g);
+  atomicAdd(p + y0 * in_w + x1, (1.f - ly) * lx * g);
+  atomicAdd(p + y1 * in_w + x0, ly * (1.f - lx) * g);
+  atomicAdd(p + y1 * in_w + x1, ly * lx * g);
 }
 
 constexpr int CUT_THREADS = 256;
@@ -197,11 +244,11 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_fwd_kernel(CutoutArgs a, f
     for (int j = 0; j < 4; ++j) {
       float xs, ys;
       src_coord(m, u0 + j, v, xs, ys);
-      xs = pad_coord(xs, cs, padding);
-      ys = pad_coord(ys, cs, padding);
-      Taps t = make_taps(xs, ys, cs);
+      xs = pad_coord(xs, a.src_w, padding);
+      ys = pad_coord(ys, a.src_h, padding);
+      Taps t = make_taps(xs, ys, a.src_w, a.src_h);
       float rgb[3];
-      warp_sample(a.pooled, t, cs, zoom, a.fill, rgb);
+      warp_sample(a.pooled, t, a.src_w, a.src_h, zoom, a.fill, rgb);
       cj_apply(rgb, cj_code, cj_sat, cj_hue);
 #pragma unroll
       for (int c = 0; c < 3; ++c) out[c][j] = have_noise ? rgb[c] + fac * nz[c][j] : rgb[c];  // pixray.py:508-510
@@ -597,24 +644,25 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
   for (int j = 0; j < 4; ++j) {
     float xs, ys;
     src_coord(m, u0 + j, v, xs, ys);
-    xs = pad_coord(xs, cs, padding);
-    ys = pad_coord(ys, cs, padding);
-    Taps t = make_taps(xs, ys, cs);
+    xs = pad_coord(xs, a.src_w, padding);
+    ys = pad_coord(ys, a.src_h, padding);
+    Taps t = make_taps(xs, ys, a.src_w, a.src_h);
     float gpre[3] = {g[0][j], g[1][j], g[2][j]};
     if (cj_code) {  // through the ColorJitter Jacobian at the recomputed pre-jitter colour
       float rgb[3];
-      warp_sample(a.pooled, t, cs, zoom, a.fill, rgb);
+      warp_sample(a.pooled, t, a.src_w, a.src_h, zoom, a.fill, rgb);
       const float gout[3] = {gpre[0], gpre[1], gpre[2]};
       cj_vjp(rgb, cj_code, cj_sat, cj_hue, gout, gpre);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float* p = g_pooled + (size_t)c * cs * cs;
+      float* p = g_pooled + (size_t)c * a.src_h * a.src_w;
+      const int sw = a.src_w;
       float gv = gpre[c];
-      if (t.in[0]) atomicAdd(p + t.y0 * cs + t.x0, t.w[0] * gv);
-      if (t.in[1]) atomicAdd(p + t.y0 * cs + t.x0 + 1, t.w[1] * gv);
-      if (t.in[2]) atomicAdd(p + (t.y0 + 1) * cs + t.x0, t.w[2] * gv);
-      if (t.in[3]) atomicAdd(p + (t.y0 + 1) * cs + t.x0 + 1, t.w[3] * gv);
+      if (t.in[0]) atomicAdd(p + t.y0 * sw + t.x0, t.w[0] * gv);
+      if (t.in[1]) atomicAdd(p + t.y0 * sw + t.x0 + 1, t.w[1] * gv);
+      if (t.in[2]) atomicAdd(p + (t.y0 + 1) * sw + t.x0, t.w[2] * gv);
+      if (t.in[3]) atomicAdd(p + (t.y0 + 1) * sw + t.x0 + 1, t.w[3] * gv);
     }
   }
 }
@@ -626,6 +674,13 @@ void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* ar
 }
 void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st) {
   launch_pdl(pool_bwd_kernel, dim3((3 * H * W + 255) / 256), dim3(256), 0, st, g_pooled, argmax, H, W, cs, g_img);
+}
+
+void rescale_bilinear(const float* x, int in_h, int in_w, int out_h, int out_w, float* y, cudaStream_t st) {
+  launch_pdl(rescale_fwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, x, in_h, in_w, out_h, out_w, y);
+}
+void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, float* gx, cudaStream_t st) {
+  launch_pdl(rescale_bwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, gy, in_h, in_w, out_h, out_w, gx);
 }
 
 int cutout_num_blocks(int n_local, int cs) { return n_local * ((cs * cs / 4 + CUT_THREADS - 1) / CUT_THREADS); }

@@ -116,12 +116,94 @@ inline void sample_affine(CutRng& r, int size, double n_s, double n_t, double H[
   for (int i = 0; i < 9; ++i) H[i] = M[i];
 }
 
+// ---- non-square canvases (global_aspect_width != 1): the warps sample from an h x w stretch of the pooled image
+inline void source_size(int cut_size, double aspect, int& h, int& w) {  // kornia rescale truncates: int(size * factor)
+  h = w = cut_size;
+  if (aspect > 1.0) w = (int)(cut_size * aspect);
+  else if (aspect < 1.0) h = (int)(cut_size * (1.0 / aspect));
+}
+inline void identity3(double H[9]) {
+  for (int i = 0; i < 9; ++i) H[i] = (i % 4 == 0) ? 1.0 : 0.0;
+}
+inline void sample_perspective_hw(CutRng& r, int h, int w, double distortion, double p, double H[9]) {
+  const bool apply = r.uni() <= p;
+  const double fx = distortion * w / 2.0, fy = distortion * h / 2.0;
+  const double start[4][2] = {{0, 0}, {w - 1.0, 0}, {w - 1.0, h - 1.0}, {0, h - 1.0}};
+  const double sgn[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  double end[4][2];
+  for (int k = 0; k < 4; ++k) {
+    end[k][0] = start[k][0] + fx * r.uni() * sgn[k][0];
+    end[k][1] = start[k][1] + fy * r.uni() * sgn[k][1];
+  }
+  if (!apply || !perspective_from_points(start, end, H)) identity3(H);
+}
+inline void sample_resized_crop_hw(CutRng& r, int h, int w, int out, double H[9]) {
+  double cw = -1, ch = -1;
+  for (int attempt = 0; attempt < 10; ++attempt) {
+    const double area = r.uni(0.25, 0.95) * h * w;
+    const double ratio = std::exp(r.uni(std::log(0.85), std::log(1.2)));
+    const double tw = std::round(std::sqrt(area * ratio)), th = std::round(std::sqrt(area / ratio));
+    if (tw > 0 && tw <= w && th > 0 && th <= h) {
+      cw = tw;
+      ch = th;
+      break;
+    }
+  }
+  if (cw < 0) {  // the fallback of the ten-tries loop: whole height or width with the ratio clamped
+    const double in_ratio = (double)w / h;
+    if (in_ratio < 0.85) {
+      cw = w;
+      ch = std::round(w / 0.85);
+    } else if (in_ratio > 1.2) {
+      ch = h;
+      cw = std::round(h * 1.2);
+    } else {
+      cw = w;
+      ch = h;
+    }
+  }
+  const double x0 = std::floor(r.uni() * (w - cw + 1) * 0.999999), y0 = std::floor(r.uni() * (h - ch + 1) * 0.999999);
+  const double src[4][2] = {{x0, y0}, {x0 + cw - 1, y0}, {x0 + cw - 1, y0 + ch - 1}, {x0, y0 + ch - 1}};
+  const double s1 = out - 1.0;
+  const double dst[4][2] = {{0, 0}, {s1, 0}, {s1, s1}, {0, s1}};
+  if (!perspective_from_points(src, dst, H)) identity3(H);
+}
+// MyRandomAffine(degrees=0, translate=(tfx, tfy), scale=(lo, hi)) about the centre of an h x w image (pixray.py:424-431)
+inline void sample_affine_hw(CutRng& r, int h, int w, double lo, double hi, double tfx, double tfy, double H[9]) {
+  const double s = r.uni(lo, hi);
+  const double cx = w / 2.0 - 0.5, cy = h / 2.0 - 0.5;
+  const double tx = tfx > 0 ? r.uni(-tfx * w, tfx * w) : 0.0, ty = tfy > 0 ? r.uni(-tfy * h, tfy * h) : 0.0;
+  const double M[9] = {s, 0, (1 - s) * cx + tx, 0, s, (1 - s) * cy + ty, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) H[i] = M[i];
+}
+
 // out: [cutn, 9] row-major dst<-src homographies; zoom group first (global index < int(0.6 * cutn), pixray.py:407)
-inline void sample_cutout_transforms(uint64_t seed, int iter, int cutn, int cut_size, float* out) {
+inline void sample_cutout_transforms(uint64_t seed, int iter, int cutn, int cut_size, float* out, double aspect = 1.0) {
   const int cutn_zoom = (int)(0.6 * cutn);
+  int sh, sw;
+  source_size(cut_size, aspect, sh, sw);
   for (int n = 0; n < cutn; ++n) {
     CutRng r{seed, (uint32_t)iter, (uint64_t)n * 64};
     double A[9], B[9], H[9];
+    if (aspect != 1.0) {
+      if (n < cutn_zoom) {
+        sample_perspective_hw(r, sh, sw, 0.40, 0.7, A);
+        sample_resized_crop_hw(r, sh, sw, cut_size, B);
+        matmul3(B, A, H);
+      } else {
+        const double n_s = aspect > 1.0 ? 1.0 / aspect : aspect, n_t = (1 - n_s) / 2;
+        if (aspect > 1.0) sample_affine_hw(r, sh, sw, 0.9 * n_s, n_s, 0.0, n_t, A);
+        else sample_affine_hw(r, sh, sw, 0.9 * n_s, n_s, n_t, 0.0, A);
+        // K.CenterCrop(size=cut_size): the central box, a translation
+        const double Cc[9] = {1, 0, -(double)((sw - cut_size) / 2), 0, 1, -(double)((sh - cut_size) / 2), 0, 0, 1};
+        double CA[9];
+        matmul3(Cc, A, CA);
+        sample_perspective(r, cut_size, 0.20, 0.7, B);
+        matmul3(B, CA, H);
+      }
+      for (int i = 0; i < 9; ++i) out[(size_t)n * 9 + i] = (float)H[i];
+      continue;
+    }
     if (n < cutn_zoom) {
       sample_perspective(r, cut_size, 0.40, 0.7, A);  // pixray.py:414
       sample_resized_crop(r, cut_size, B);            // pixray.py:415

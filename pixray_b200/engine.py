@@ -31,7 +31,7 @@ class EngineError(RuntimeError):
 class B200Engine:
     def __init__(self, *, drawer=DRAWER_VQGAN, image_hw=(256, 256), vqgan=None, grid=None, cutn=64, cut_size=224,
                  clip=(), noise_fac=0.1, seed=0, device=0, rank=0, world=1, grad_scale=0.0, lr_betas=(0.9, 0.999),
-                 adam_eps=1e-8, fft_decay=0.0, fft_colors=0.0, fft_contrast=0.0):
+                 adam_eps=1e-8, fft_decay=0.0, fft_colors=0.0, fft_contrast=0.0, cut_aspect=1.0):
         if not torch.cuda.is_available():
             raise EngineError("pixray_b200 needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -66,6 +66,8 @@ class B200Engine:
         cfg.op_dtype, cfg.grad_scale = 0, grad_scale
         cfg.beta1, cfg.beta2, cfg.adam_eps = lr_betas[0], lr_betas[1], adam_eps
         cfg.fft_decay, cfg.fft_colors, cfg.fft_contrast = fft_decay, fft_colors, fft_contrast  # 0 -> 1.5 / 1.5 / 0.9
+        cfg.cut_aspect = float(cut_aspect)  # global_aspect_width (pixray.py:1931); 1 = square canvas
+        self.cut_aspect = float(cut_aspect)
         self.cfg = cfg
         self.device = torch.device("cuda", device)
         self.cutn, self.cut_size, self.world, self.rank = cutn, cut_size, world, rank

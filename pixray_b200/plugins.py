@@ -304,8 +304,9 @@ class MakeCutouts:
     """pixray.py:399-511.  `transforms` is the per-iteration cache of composed 3x3s (pixray.py:498); when it is None
     a fresh set is sampled (the distributions of the reference's augmentation stacks, pixray_b200/cutouts.py)."""
 
-    def __init__(self, cut_size, cutn, session: Session, cut_pow=1.0, seed=0):
+    def __init__(self, cut_size, cutn, session: Session, cut_pow=1.0, seed=0, aspect=1.0):
         self.cut_size, self.cutn, self.cut_pow = cut_size, cutn, cut_pow
+        self.aspect = aspect  # global_aspect_width (pixray.py:402, 1931)
         self.cutn_zoom = int(0.6 * cutn)
         self.noise_fac = 0.1
         self.transforms = None
@@ -322,7 +323,7 @@ class MakeCutouts:
         s = self.session
         if self.transforms is None:
             self.transforms = torch.from_numpy(
-                cut_sampler.sample_transforms(self.cutn, self.cut_size, int(self._rng.integers(1 << 31))))
+                cut_sampler.sample_transforms(self.cutn, self.cut_size, int(self._rng.integers(1 << 31)), aspect=self.aspect))
             # the live stacks end in K.ColorJitter (pixray.py:416, 436); replays of the cached transforms within the
             # same iteration (pixray.py:480-486) do not repeat it
             jitter = cut_sampler.sample_color_jitter(self.cutn, int(self._rng.integers(1 << 31)))
@@ -387,7 +388,8 @@ class Prompt:
             raise RuntimeError("Prompt.register(session, clip_idx, prompts) must be called first")
         # `input` is normally the tensor perceptor.encode_image just returned (possibly through .float()): the engine still
         # holds those embeddings un-normalised, which its backward needs, so they are not passed back in.  Foreign
-        # embeddings are scored as given (their gradient then stops at the embedding).
+        # embeddings are scored as given into scratch buffers: they have no graph behind them, and the engine's own
+        # embeddings / gradient (what Session.backward() propagates) are left untouched.
         own = self._session.last_embeds.get(self._clip_idx)
         mine = own is not None and input.data_ptr() == own.data_ptr() and input.shape == own.shape
         return self._session.engine.prompt_loss(self._clip_idx, None if mine else input)[self._index]

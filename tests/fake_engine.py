@@ -17,6 +17,7 @@ class FakeEngine:
                  clip=(), noise_fac=0.1, seed=0, device=0, rank=0, world=1, **extra):
         self.calls = []
         self.kw = dict(drawer=drawer, image_hw=tuple(image_hw), cutn=cutn, clip=list(clip), seed=seed, grid=grid, **extra)
+        self.cut_aspect = extra.get('cut_aspect', 1.0)
         self.device = torch.device("cpu")
         self.cutn, self.cut_size, self.image_hw = cutn, cut_size, tuple(image_hw)
         self.n_local = cutn

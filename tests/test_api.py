@@ -122,10 +122,23 @@ def test_text_prompts_need_a_text_tower(fake, tmp_path):
 
 
 def test_unbuilt_configurations_fail_loudly(fake, tmp_path):
-    for kw in (dict(clip_models="RN50"), dict(size=[128, 64])):
+    for kw in (dict(clip_models="RN50"),):
         api.reset_settings()
         with pytest.raises(NotImplementedError):
             _init(tmp_path, prompts="x", **kw)
+
+
+def test_default_widescreen_aspect_reaches_the_engine(fake, tmp_path):
+    """The reference's DEFAULT canvas is widescreen (aspect='widescreen', quality 'normal': 384 x 216, pixray.py:1753,
+    1864-1878): global_aspect_width = 384 / 216 from the requested size, the VQGAN canvas rounds to 384 x 208."""
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", size=None)
+    assert args.size == [384, 216]
+    eng = api._state.engine
+    assert eng.kw["image_hw"] == (208, 384) and abs(eng.kw["cut_aspect"] - 384 / 216) < 1e-12
+    assert abs(api._state.make_cutouts.aspect - 384 / 216) < 1e-12
+    api.reset_settings()
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16", aspect="square", size=None)
+    assert "cut_aspect" not in api._state.engine.kw and api._state.engine.kw["image_hw"] == (288, 288)
 
 
 def test_batches_preset_reaches_the_engine(fake, tmp_path):

@@ -1,0 +1,63 @@
+"""Non-square canvases (global_aspect_width = size[0] / size[1] != 1, pixray.py:1931): the pooled cut_size x cut_size image is
+stretched by kornia's rescale before the warps (pixray.py:468-472) and the cached transforms map from that stretched source
+(pixray.py:480-486).  The reference's default canvas is widescreen (pixray.py:1753).  Engine vs oracle on explicit
+transforms drawn from the aspect-aware sampler: cutouts, losses, z.grad -- wide and tall."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_path as R
+from pixray_b200 import cutouts
+from pixray_b200 import engine as E
+from test_pipeline_gpu import SMALL_CLIP, SMALL_VQ, plant_extremes, report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("hw", [(32, 48), (48, 32), (18, 32)])
+def test_non_square_canvas_matches_the_oracle(hw):
+    H, W = hw
+    aspect = W / H
+    cutn, cs, seed = 8, 224, 3
+    torch.manual_seed(seed)
+    vq = R.init_vqgan_weights(R.VQModel(n_embed=1024, embed_dim=128, ch=128, ch_mult=(1, 2), num_res_blocks=1,
+                                        attn_resolutions=(16,), resolution=32, z_channels=128), seed)
+    clip = R.init_clip_weights(R.ClipVisual(224, 32, 128, 2, 2, 64), seed + 1)
+    eng = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=(H, W), vqgan=SMALL_VQ, cutn=cutn, clip=[SMALL_CLIP], noise_fac=0.1,
+                       seed=seed, cut_aspect=aspect)
+    eng.load_module(E.MOD_VQGAN, vq.state_dict())
+    eng.load_module(E.MOD_CLIP0, clip.state_dict())
+    eng.finalize()
+    g = torch.Generator().manual_seed(seed + 2)
+    prompts = [(torch.randn(1, 64, generator=g), 1.0, float("-inf")), (torch.randn(1, 64, generator=g), -0.3, float("-inf"))]
+    eng.set_prompts(0, torch.cat([p[0] for p in prompts]).numpy(), [1.0, -0.3], [float("-inf")] * 2)
+    h, w = H // 2, W // 2
+    idx = torch.randint(1024, (h * w,), generator=g)
+    z = (vq.quantize.embedding.weight[idx].T.reshape(1, 128, h, w) + 0.05 * torch.randn(1, 128, h, w, generator=g)).contiguous()
+    T = cutouts.sample_transforms(cutn, cs, 11, aspect=aspect)
+    sh, sw = cutouts.source_size(cs, aspect)
+    facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
+    ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), cs, "reflection", 0.4,
+                    facs, noise, aspect=aspect)
+    img = eng.synth(z)
+    e_img, _ = report(f"image {H}x{W}", img, ref["image"])
+    batch = eng.make_cutouts(ref["image"], transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.4, noise_facs=facs.numpy(),
+                             noise=noise)
+    src = eng.debug_read("cut_src", (1, 3, sh, sw))
+    e_src, _ = report(f"stretched source {sh}x{sw}", src, R.rescale_for_aspect(R.pool_avg_max(ref["image"], cs), aspect))
+    e_b, _ = report("cutouts (oracle image in)", batch, ref["batch"])
+    ref_b = R.make_cutouts(ref["image"], torch.from_numpy(T), cs, "border", 0.4, facs, noise, aspect=aspect)
+    batch_b = eng.make_cutouts(ref["image"], transforms=T, zoom_padding=E.PAD_BORDER, fill=0.4, noise_facs=facs.numpy(), noise=noise)
+    e_bb, _ = report("cutouts, border padding", batch_b, ref_b)
+    zc = z.clone().cuda()
+    losses = np.zeros(2, dtype=np.float32)
+    eng.iterate(zc, 0.05, 0, params=dict(transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.4, noise_facs=facs.numpy(),
+                                         noise=noise), losses_out=losses)
+    ref_l = np.array([float(l) for l in ref["losses"]], dtype=np.float32)
+    e_g, m_g = report("z.grad", eng.debug_read("z_grad", z.shape), ref["z_grad"])
+    assert e_img < 5e-3 and e_src < 1e-5 and e_b < 1e-4 and e_bb < 1e-4
+    assert np.abs(losses - ref_l).max() < 5e-3
+    assert e_g <= 3e-2 * m_g
+    # the engine's own draws (Philox sampler of csrc/transforms.h) stay finite and inside the stretched source
+    eng.iterate(zc, 0.05, 1, losses_out=losses)
+    assert np.isfinite(losses).all() and torch.isfinite(zc).all()
