@@ -122,6 +122,16 @@ int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* w
 int pxr_set_image_prompts_sized(pxr_handle h, const float* const* imgs, const int* hs, const int* ws, int n,
                                 const float* weights);
 
+/* Spot prompts (args.spot_prompts / spot_prompts_off: pixray.py:917-931, 1262-1293; mask from fetch_spot_indexes 370-394,
+ * applied to the pooled image at 453-459).  which = 1: `embeds` are scored on cutouts of the image with the SPOT zeroed
+ * (make_cutouts(out, spot=1) zeroes mask >= 0.5), which = 0: with everything but the spot zeroed.  Every pxr_iterate then
+ * runs one more cutout + encode + backward pass per kind (cached transforms of the iteration, no ColorJitter, fresh noise);
+ * their losses come FIRST in the perceptor's part of the loss vector (spot, spot off, prompts, image prompts).
+ * mask: host bytes [3, cut_size, cut_size], != 0 where the resized RGB mask image is >= 0.5. */
+int pxr_set_spot_prompts(pxr_handle h, int clip_idx, int which, const float* embeds, int n, int D, const float* weights,
+                         const float* stops);
+int pxr_set_spot_mask(pxr_handle h, const unsigned char* mask);
+
 /* Multi-GPU: 128-byte ncclUniqueId from rank 0; the engine owns the communicator. */
 int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world);
 int pxr_get_unique_id(void* out128);

@@ -162,7 +162,7 @@ def rescale_for_aspect(pooled, aspect):
 
 
 def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None, noise=None, cutn_zoom=None,
-                 jitter=None, aspect=1.0):
+                 jitter=None, aspect=1.0, spot=None, spot_mask=None):
     """MakeCutouts.forward on explicit (cached) transforms, pixray.py:445-511.
 
     img [1, 3, H, W]; transforms [cutn, 3, 3]; zoom group = first int(0.6 * cutn) (pixray.py:407) warped with
@@ -173,6 +173,11 @@ def make_cutouts(img, transforms, cut_size, zoom_padding, fill, noise_facs=None,
     if cutn_zoom is None:
         cutn_zoom = int(0.6 * cutn)
     pooled = pool_avg_max(img, cut_size)  # identical for every cutout (pixray.py:461-478)
+    if spot is not None:
+        # pixray.py:453-466: spot == 0 zeroes mask_indexes_off (mask < 0.5), anything else zeroes mask_indexes (mask >= 0.5);
+        # spot_mask: bool [3, cs, cs] = mask_image_tensor.ge(0.5) of fetch_spot_indexes (pixray.py:370-394)
+        sel = ~spot_mask if spot == 0 else spot_mask
+        pooled = pooled.masked_fill(sel[None], 0.0)
     pooled = rescale_for_aspect(pooled, aspect)  # global_aspect_width != 1 (pixray.py:468-472)
     src = pooled.expand(cutn, -1, -1, -1)
     parts = []
@@ -945,7 +950,7 @@ class AdamState:
 
 
 def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=(),
-            jitter=None, image_prompts=(), aspect=1.0):
+            jitter=None, image_prompts=(), aspect=1.0, spot_mask=None, spot_prompts=None, spot_prompts_off=None):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
@@ -958,7 +963,19 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
     batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise, jitter=jitter, aspect=aspect)
     batch.retain_grad()
     losses, embeds = [], []
-    for model, pms in zip(clip_models, prompts):
+    # spot prompts (pixray.py:1262-1293): per kind ONE more make_cutouts on the cached transforms (no ColorJitter; the
+    # explicit noise is replayed), encoded by every perceptor that has such prompts, scored before the regular prompts
+    spot_batches = {}
+    for which, table in ((1, spot_prompts), (0, spot_prompts_off)):
+        if table is not None and any(len(t) for t in table):
+            spot_batches[which] = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aspect=aspect,
+                                               spot=which, spot_mask=spot_mask)
+    for mi, (model, pms) in enumerate(zip(clip_models, prompts)):
+        for which, table in ((1, spot_prompts), (0, spot_prompts_off)):
+            if which in spot_batches and len(table[mi]):
+                iii_s = encode_image(model, spot_batches[which]).float()
+                for (embed, weight, stop) in table[mi]:
+                    losses.append(prompt_loss(iii_s, embed, weight, stop))
         iii = encode_image(model, batch).float()
         embeds.append(iii)
         for (embed, weight, stop) in pms:

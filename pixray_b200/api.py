@@ -103,7 +103,7 @@ _ENGINE_OPTIONS = [(("--b200_weights",), "b200_weights", None, None), (("--b200_
 
 # options that leave the hot path: dest -> the value(s) that keep them off
 _OFF_PATH = {
-    "spot_prompts": ([],), "spot_prompts_off": ([],), "spot_file": (None,), "labels": ([],), "image_labels": (None,),
+    "labels": ([],), "image_labels": (None,),
     "overlay_image": (None,), "init_image": (None,), "target_images": (None, []), "animation_dir": (None,),
     "init_weight": (None, 0, 0.0), "init_weight_dist": (0, 0.0), "init_weight_cos": (0, 0.0), "init_weight_pix": (0, 0.0),
     "perceptors": ("clip",), "optimiser": ("Adam",), "make_video": (False,), "transparent": (False,), "filters": (None,),
@@ -407,6 +407,16 @@ def do_init(args):
             raise ValueError(f"no prompts for perceptor {args.clip_models[i]}")
         P.Prompt.register(st.session, i, t)
     st.prompt_tables = tables
+    # spot prompts (pixray.py:917-931): text Prompts scored on the cutouts of the masked image (fetch_spot_indexes, 370-394)
+    spot_on, spot_off = split_pipes(args.spot_prompts) or [], split_pipes(args.spot_prompts_off) or []
+    if spot_on or spot_off:
+        eng.set_spot_mask(_spot_mask(args, clip_cfgs[0]["image_res"], aspect))
+        for i, m in enumerate(args.clip_models):
+            for which, plist in ((1, spot_on), (0, spot_off)):
+                parsed = [P.parse_prompt(p) for p in plist]
+                embeds = [_text_embed(args, m, txt, clip_cfgs[i]["out_dim"]) for (txt, _, _) in parsed]
+                eng.set_spot_prompts(i, which, torch.cat(embeds).numpy() if embeds else [], [w for (_, w, _) in parsed],
+                                     [s_ for (_, _, s_) in parsed])
     if args.image_prompts:
         imgs = [_load_image(p, sideX, sideY) for p in args.image_prompts]
         w = None if args.image_prompt_weight is None else [args.image_prompt_weight] * len(imgs)
@@ -439,6 +449,27 @@ def do_init(args):
         eng.set_schedule(st.lr, st.iter_drop_delay, st.max_loss_drops, bool(args.auto_stop), list(args.learning_rate_drops)[:16])
         st.stop_iter = None
     return args
+
+
+def _spot_mask(args, cut_size, aspect):
+    """fetch_spot_indexes (pixray.py:370-394): args.spot_file, else the reference's inputs/spot_wide.png (non-square canvas) /
+    inputs/spot_square.png, as RGB, LANCZOS-resized to cut_size x cut_size, >= 0.5.  Arrays / tensors ([cs, cs] or
+    [3, cs, cs], truthy inside the spot) are taken as they are."""
+    src = getattr(args, "spot_file", None)
+    if src is not None and not isinstance(src, (str, os.PathLike)):
+        return np.asarray(src.cpu() if torch.is_tensor(src) else src) != 0
+    if src is None:
+        name = "spot_wide.png" if aspect != 1.0 else "spot_square.png"
+        cands = [os.path.join("inputs", name)]
+        if os.environ.get("PIXRAY_ROOT"):
+            cands.append(os.path.join(os.environ["PIXRAY_ROOT"], "inputs", name))
+        src = next((c for c in cands if os.path.exists(c)), None)
+        if src is None:
+            raise FileNotFoundError(f"spot prompts need a mask image: pass spot_file, or set PIXRAY_ROOT (tried {cands})")
+    from PIL import Image
+    img = Image.open(src).convert("RGB").resize((cut_size, cut_size), Image.LANCZOS)
+    t = np.asarray(img, dtype=np.float32) / 255.0  # TF.to_tensor
+    return np.ascontiguousarray(np.transpose(t, (2, 0, 1)) >= 0.5)
 
 
 def _load_image(src, sideX, sideY):

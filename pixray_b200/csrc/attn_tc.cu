@@ -194,9 +194,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     int it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int b = item / p.H, h = item % p.H;
+      // EVERY warp paces itself on the item's S barrier, also the eight that own the second query tile when there is
+      // none (T <= 128): without it they would run through all their items at once and arrive on bar_free ahead of
+      // the phases those arrivals belong to (a CTA with more than one item then deadlocks: B x heads > #SMs at T <= 128,
+      // e.g. ViT-B/32 with cutn = 128)
+      mbar_wait(bar_s, it & 1);
       if (mt < n_mt) {
         const int i = mt * 128 + row;
-        mbar_wait(bar_s, it & 1);
         tc_fence_after();
         // ---- row maximum (columns split between the two warps of the pair)
         float m4[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
@@ -885,11 +889,12 @@ int attn_plan_make(AttnPlan* plan, const __half* qkv, __half* o, const __half* d
 void attn_forward_launch(const AttnPlan& plan, cudaStream_t st) {
   launch_pdl(attn_fwd_kernel, dim3(plan.grid), dim3(ATT_THREADS), plan.smem_fwd, st, plan.p);
 }
-// PXR_ATTN_BWD=1 selects the first backward kernel (six hand-offs per query tile) for A/B measurements
+// Measured in the config-2 iteration (profiles/README.md, round 2): the first backward kernel 106 us per layer, the
+// key-tile-outer one 151 us -- so the first one stays the default; PXR_ATTN_BWD=2 selects the second for A/B runs.
 void attn_backward_launch(const AttnPlan& plan, cudaStream_t st) {
   static const bool v1 = [] {
     const char* e = getenv("PXR_ATTN_BWD");
-    return e && atoi(e) == 1;
+    return !(e && atoi(e) == 2);
   }();
   if (v1) launch_pdl(attn_bwd_kernel, dim3(plan.grid), dim3(ATT_THREADS), plan.smem_bwd, st, plan.p);
   else launch_pdl(attn_bwd2_kernel, dim3(plan.grid), dim3(ATT_THREADS), plan.smem_bwd2, st, plan.p);

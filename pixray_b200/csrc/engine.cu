@@ -119,6 +119,14 @@ class Engine {
     int* pslot = nullptr;
     float* pinv = nullptr;
     float* scratch = nullptr;  // pxr_prompt_loss on caller-provided embeddings
+    // spot prompts (pixray.py:1283-1293): text Prompts scored on the embeddings of the masked cutouts.
+    // [1] = args.spot_prompts (make_cutouts(out, spot=1)), [0] = args.spot_prompts_off (spot=0)
+    struct Spot {
+      std::vector<float> rows, w, stop;
+      int n = 0, loss_offset = 0;
+      float *d_rows = nullptr, *d_w = nullptr, *d_stop = nullptr, *d_inv = nullptr;
+      int* d_slot = nullptr;
+    } spot[2];
     OpList fwd, bwd;
   };
   Clip clip[2];
@@ -133,6 +141,18 @@ class Engine {
   std::vector<float> img_w;
   void rebuild_prompt_rows();
   void encode_image_prompts();
+  // spot passes: the mask (device [3, cs, cs], != 0 where the mask image is >= 0.5) and the masked pooled image
+  unsigned char* spot_mask = nullptr;
+  float* pooled_masked = nullptr;
+  bool any_spot(int which) const {
+    for (int i = 0; i < cfg.n_clip; ++i)
+      if (clip[i].spot[which].n > 0) return true;
+    return false;
+  }
+  bool spot_accumulated = false;  // a spot pass of this iteration already wrote d loss / d image: the main pass adds to it
+  bool spot_pass(int which, bool accumulate_img);
+  void backward_to_image(const CutoutArgs& a, int mask_which, bool accumulate_img, bool main_pass);
+  void backward_drawer();
 
   // ---- auxiliary losses (Losses/*.py; pixray.py:1384-1393): extra loss-vector entries after the prompts
   struct AuxLoss {
@@ -1009,6 +1029,7 @@ void Engine::build_cutouts() {
   const int cs_ = cfg.cut_size;
   pooled = dalloc<float>((size_t)3 * cs_ * cs_);
   g_pooled = dalloc<float>((size_t)3 * cs_ * cs_);
+  pooled_masked = dalloc<float>((size_t)3 * cs_ * cs_);
   aspect = (cfg.cut_aspect > 0.f && cfg.cut_aspect != 1.f) ? (double)cfg.cut_aspect : 1.0;
   if (aspect > 8.0 || aspect < 0.125) throw EngineError(-66, "cut_aspect (canvas width / height) must be within [1/8, 8]");
   source_size(cs_, aspect, src_h, src_w);
@@ -1452,6 +1473,26 @@ void Engine::rebuild_prompt_rows() {
   int off = 0;
   for (int i = 0; i < cfg.n_clip; ++i) {
     Clip& C = clip[i];
+    // the reference's result order per perceptor: spot prompts, spot-off prompts, prompts, image prompts (pixray.py:1283-1336)
+    for (int which : {1, 0}) {
+      Clip::Spot& sp = C.spot[which];
+      dfree(sp.d_rows);
+      dfree(sp.d_w);
+      dfree(sp.d_stop);
+      dfree(sp.d_inv);
+      dfree(sp.d_slot);
+      sp.loss_offset = off;
+      if (sp.n > 0) {
+        sp.d_rows = upload(sp.rows);
+        sp.d_w = upload(sp.w);
+        sp.d_stop = upload(sp.stop);
+        sp.d_inv = upload(std::vector<float>(sp.n, 1.f));
+        std::vector<int> slot(sp.n);
+        for (int j = 0; j < sp.n; ++j) slot[j] = j;
+        sp.d_slot = upload(slot);
+        off += sp.n;
+      }
+    }
     const int D = C.c.out_dim, rows = C.n_text + n_img * cfg.cutn;
     std::vector<float> pr((size_t)rows * D, 0.f), w(rows), stp(rows), inv(rows);
     std::vector<int> slot(rows);
@@ -1604,26 +1645,40 @@ void Engine::aux_on_image() {
   }
 }
 
-void Engine::backward_all() {
+// CLIP backward of every participating perceptor -> d loss / d cutouts -> (range terms, ColorJitter, warp adjoint) ->
+// d loss / d pooled [-> un-stretch] [-> spot mask] -> d loss / d image (= or +=).  `a` = the cutout parameters of the pass
+// whose activations are live; mask_which >= 0: a spot pass (only the perceptors with spot prompts of that kind ran).
+void Engine::backward_to_image(const CutoutArgs& a, int mask_which, bool accumulate_img, bool main_pass) {
   PXR_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), st));
+  bool first = true;
   for (int i = 0; i < cfg.n_clip; ++i) {
     Clip& C = clip[i];
+    if (mask_which >= 0 && C.spot[mask_which].n == 0) continue;
     run(C.bwd);
-    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, i > 0, g_batch, sums, st);
+    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, !first, g_batch, sums, st);
+    first = false;
     launches += 1;
   }
-  if (!aux.empty()) aux_on_cutouts();
+  if (main_pass && !aux.empty()) aux_on_cutouts();
   if (comm)  // d/dmin, d/dmax terms need the sums over ALL cutouts
     nccl_check(Comm::api().all_reduce(sums, sums, 2, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(sums)");
   PXR_CUDA(cudaMemsetAsync(g_cut_src, 0, sizeof(float) * 3 * src_h * src_w, st));
-  cutout_backward(cut_args, g_batch, range, irange, sums, g_cut_src, st);
+  cutout_backward(a, g_batch, range, irange, sums, g_cut_src, st);
+  const int ncs = 3 * cfg.cut_size * cfg.cut_size;
   if (aspect != 1.0) {
-    PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * 3 * cfg.cut_size * cfg.cut_size, st));
+    PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * ncs, st));
     rescale_bilinear_backward(g_cut_src, cfg.cut_size, cfg.cut_size, src_h, src_w, g_pooled, st);
     launches += 1;
   }
-  pool_backward(g_pooled, pool_argmax, cfg.image_h, cfg.image_w, cfg.cut_size, g_img, st);
+  if (mask_which >= 0) {  // cutout[0][mask_indexes] = 0 (pixray.py:466): no gradient through the zeroed pixels
+    spot_mask_apply(g_pooled, spot_mask, mask_which == 1, ncs, g_pooled, st);
+    launches += 1;
+  }
+  pool_backward(g_pooled, pool_argmax, cfg.image_h, cfg.image_w, cfg.cut_size, g_img, st, accumulate_img ? 1 : 0);
   launches += 2;
+}
+
+void Engine::backward_drawer() {
   if (comm) {
     // The path's one exchange step.  It sits on the IMAGE gradient, not on z.grad: ClampWithGrad's backward
     // (vqgan.py:76-79) masks by the sign of the incoming gradient, so the drawer backward is not linear in it and
@@ -1641,6 +1696,54 @@ void Engine::backward_all() {
   if (cfg.drawer == PXR_DRAWER_VDIFF) vdiff_backward();
   else run(drawer_bwd);
   check_launch("backward");
+}
+
+void Engine::backward_all() {
+  backward_to_image(cut_args, -1, spot_accumulated, true);
+  spot_accumulated = false;
+  backward_drawer();
+}
+
+// One spot pass (pixray.py:1262-1293): the pooled image with the spot (which = 1) or everything but the spot (which = 0)
+// zeroed, cut with THIS iteration's cached transforms (the cached path: no ColorJitter, fresh noise, pixray.py:480-486),
+// encoded by every perceptor that has spot prompts of this kind, scored, and taken back to the image gradient right away
+// (the activations are single-buffered; the drawer backward runs once, on the sum, in backward_drawer).
+// `pooled` must hold the current image's pooling.  Returns false when no perceptor has such prompts.
+bool Engine::spot_pass(int which, bool accumulate_img) {
+  if (!any_spot(which)) return false;
+  if (!spot_mask) throw EngineError(-71, "spot prompts need a spot mask (pxr_set_spot_mask)");
+  const int ncs = 3 * cfg.cut_size * cfg.cut_size;
+  spot_mask_apply(pooled, spot_mask, which == 1, ncs, pooled_masked, st);
+  CutoutArgs a = cut_args;
+  a.jitter = nullptr;
+  a.iter = cut_args.iter + (9 + which) * (1 << 24);  // engine-drawn noise: its own Philox stream
+  if (aspect != 1.0) {
+    rescale_bilinear(pooled_masked, cfg.cut_size, cfg.cut_size, src_h, src_w, cut_src, st);
+    a.pooled = cut_src;
+    launches += 1;
+  } else {
+    a.pooled = pooled_masked;
+  }
+  cutout_forward(a, batch, part_min, part_max, part_imin, part_imax, st);
+  minmax_reduce(nullptr, part_min, part_max, part_imin, part_imax, n_parts, range, irange, st);
+  launches += 3;
+  if (comm) {
+    range_pack(range, xbuf, st);
+    nccl_check(Comm::api().all_reduce(xbuf, xbuf, 2, Comm::kFloat32, Comm::kMin, comm, st), "allreduce(min,max)");
+    range_unpack(xbuf, range, irange, st);
+    launches += 3;
+  }
+  for (int i = 0; i < cfg.n_clip; ++i) {
+    Clip& C = clip[i];
+    Clip::Spot& sp = C.spot[which];
+    if (sp.n == 0) continue;
+    forward_clip(i);
+    prompt_loss(C.e, C.B, C.c.out_dim, sp.d_rows, sp.d_w, sp.d_stop, sp.d_slot, sp.d_inv, sp.n, cfg.cutn, S, C.e_unit,
+                losses_dev + sp.loss_offset, C.de, C.de16, st);
+    launches += 1;
+  }
+  backward_to_image(a, which, accumulate_img, false);
+  return true;
 }
 
 void Engine::step(float lr) {
@@ -1885,6 +1988,47 @@ int pxr_set_image_prompts_sized(pxr_handle h, const float* const* imgs, const in
   });
 }
 
+// Spot prompts (args.spot_prompts / args.spot_prompts_off, pixray.py:917-931, 1262-1293): which = 1 scores `embeds` on the
+// cutouts of the image with the spot region zeroed (make_cutouts(out, spot=1)), which = 0 on the cutouts with everything
+// BUT the spot zeroed.  n = 0 clears.  Needs pxr_set_spot_mask.  Fused path (pxr_iterate) only.
+int pxr_set_spot_prompts(pxr_handle h, int clip_idx, int which, const float* embeds, int n, int D, const float* weights,
+                         const float* stops) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (clip_idx < 0 || clip_idx >= e->cfg.n_clip) throw EngineError(-14, "bad clip index");
+    if (which != 0 && which != 1) throw EngineError(-72, "pxr_set_spot_prompts: which = 1 (spot) or 0 (spot off)");
+    auto& C = e->clip[clip_idx];
+    if (n > 0 && D != C.c.out_dim) throw EngineError(-15, "prompt embedding width does not match the perceptor");
+    auto& sp = C.spot[which];
+    sp.rows.assign((size_t)n * (n > 0 ? D : 0), 0.f);
+    for (int j = 0; j < n; ++j) {  // F.normalize(self.embed), pixray.py:277
+      double s2 = 0;
+      for (int k = 0; k < D; ++k) s2 += (double)embeds[(size_t)j * D + k] * embeds[(size_t)j * D + k];
+      const double nrm = std::max(std::sqrt(s2), 1e-12);
+      for (int k = 0; k < D; ++k) sp.rows[(size_t)j * D + k] = (float)(embeds[(size_t)j * D + k] / nrm);
+    }
+    sp.w.assign(weights, weights + (n > 0 ? n : 0));
+    sp.stop.assign(stops, stops + (n > 0 ? n : 0));
+    sp.n = n > 0 ? n : 0;
+    e->rebuild_prompt_rows();
+  });
+}
+
+// mask: host bytes [3, cut_size, cut_size], != 0 where the (resized, RGB) mask image is >= 0.5 (fetch_spot_indexes,
+// pixray.py:370-394)
+int pxr_set_spot_mask(pxr_handle h, const unsigned char* mask) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (!mask) throw EngineError(-10, "pxr_set_spot_mask: null mask");
+    const size_t n = (size_t)3 * e->cfg.cut_size * e->cfg.cut_size;
+    if (!e->spot_mask) e->spot_mask = e->dalloc<unsigned char>(n);
+    PXR_CUDA(cudaMemcpyAsync(e->spot_mask, mask, n, cudaMemcpyHostToDevice, e->st));
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+  });
+}
+
 int pxr_set_image_prompts(pxr_handle h, const float* imgs, int n, const float* weights) {
   if (!h) return -10;
   const int H = h->e->cfg.image_h, W = h->e->cfg.image_w;
@@ -2027,6 +2171,14 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
       try {
         e->encode_image_prompts();
         if (b == 0) e->forward_drawer();  // same z: the image of the later passes is the same image
+        if (e->any_spot(1) || e->any_spot(0)) {  // spot / spot-off prompts: their own masked cutout batches (pixray.py:1262-1293)
+          pxr::pool_forward(e->img, e->cfg.image_h, e->cfg.image_w, e->cfg.cut_size, e->pooled, e->pool_argmax, e->st);
+          e->launches += 1;
+          bool acc = false;
+          acc |= e->spot_pass(1, acc);
+          acc |= e->spot_pass(0, acc);
+          e->spot_accumulated = acc;
+        }
         e->forward_cutouts();
         for (int i = 0; i < e->cfg.n_clip; ++i) {
           e->forward_clip(i);

@@ -81,7 +81,11 @@ void fft_synth_backward(FftPlans* pl, const float* g_img, const float* img, cons
 // ------------------------------------------------------------------ MakeCutouts (pixray.py:445-511)
 // (AdaptiveAvgPool2d + AdaptiveMaxPool2d) / 2 of the whole image, once (pixray.py:463); argmax kept for backward.
 void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* argmax, cudaStream_t st);
-void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st);
+void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st,
+                   int accumulate = 0);
+// Spot prompts (pixray.py:453-459): cutout[0][mask_indexes] = 0 on the pooled image -- y = keep ? x : 0 with
+// keep = (mask[i] != 0) XOR zero_where_set; the same call masks the gradient on the way back (in place when y == x)
+void spot_mask_apply(const float* x, const unsigned char* mask, int zero_where_set, int n, float* y, cudaStream_t st);
 
 // kornia.geometry.transform.rescale of the pooled image for non-square canvases (pixray.py:468-472): bilinear,
 // align_corners=False ([3, in_h, in_w] -> [3, out_h, out_w]), and its adjoint (g_in must be zeroed by the caller)

@@ -45,8 +45,17 @@ __global__ void pool_fwd_kernel(const float* __restrict__ img, int H, int W, int
   argmax[i] = mi;
 }
 
+__global__ void spot_mask_kernel(const float* __restrict__ x, const unsigned char* __restrict__ mask, int zero_where_set,
+                                 int n, float* __restrict__ y) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool set = mask[i] != 0;
+  y[i] = (set != (zero_where_set != 0)) ? x[i] : 0.f;
+}
+
 __global__ void pool_bwd_kernel(const float* __restrict__ g_pooled, const int* __restrict__ argmax, int H, int W,
-                                int cs, float* __restrict__ g_img) {
+                                int cs, float* __restrict__ g_img, int accumulate) {
   pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * H * W) return;
@@ -67,7 +76,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ g_pooled, const int* _
       if (argmax[o] == y * W + x) s += g;
     }
   }
-  g_img[i] = s;
+  g_img[i] = accumulate ? g_img[i] + s : s;
 }
 
 // ------------------------------------------------------------------ coordinate helpers (ATen grid_sampler semantics)
@@ -672,8 +681,12 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
 void pool_forward(const float* img, int H, int W, int cs, float* pooled, int* argmax, cudaStream_t st) {
   launch_pdl(pool_fwd_kernel, dim3((3 * cs * cs + 255) / 256), dim3(256), 0, st, img, H, W, cs, pooled, argmax);
 }
-void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st) {
-  launch_pdl(pool_bwd_kernel, dim3((3 * H * W + 255) / 256), dim3(256), 0, st, g_pooled, argmax, H, W, cs, g_img);
+void pool_backward(const float* g_pooled, const int* argmax, int H, int W, int cs, float* g_img, cudaStream_t st,
+                   int accumulate) {
+  launch_pdl(pool_bwd_kernel, dim3((3 * H * W + 255) / 256), dim3(256), 0, st, g_pooled, argmax, H, W, cs, g_img, accumulate);
+}
+void spot_mask_apply(const float* x, const unsigned char* mask, int zero_where_set, int n, float* y, cudaStream_t st) {
+  launch_pdl(spot_mask_kernel, dim3((n + 255) / 256), dim3(256), 0, st, x, mask, zero_where_set, n, y);
 }
 
 void rescale_bilinear(const float* x, int in_h, int in_w, int out_h, int out_w, float* y, cudaStream_t st) {

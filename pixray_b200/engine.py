@@ -76,6 +76,7 @@ class B200Engine:
         self.clip_dims = [c["out_dim"] for c in clip]
         self.n_prompts = [0 for _ in clip]  # loss slots per perceptor: text prompts + image prompts
         self._n_text = [0 for _ in clip]
+        self._n_spot = [[0, 0] for _ in clip]  # [spot off, spot] prompts per perceptor (scored in the fused path only)
         self._n_img = 0
         h = C.c_void_p()
         rc = self.lib.pxr_create(C.byref(cfg), C.byref(h))
@@ -171,6 +172,28 @@ class B200Engine:
         self._check(self.lib.pxr_set_image_prompts_sized(self.h, ptrs, hs, ws, n, wp), "pxr_set_image_prompts_sized")
         self._n_img = n
         self.n_prompts = [t_ + n for t_ in self._n_text]
+
+    def set_spot_mask(self, mask):
+        """fetch_spot_indexes (pixray.py:370-394): bool / 0-1 array [3, cut_size, cut_size] (or [cut_size, cut_size]), True
+        where the resized mask image is >= 0.5."""
+        m = np.asarray(mask.cpu() if torch.is_tensor(mask) else mask)
+        if m.ndim == 2:
+            m = np.broadcast_to(m[None], (3,) + m.shape)
+        m = np.ascontiguousarray((m != 0).astype(np.uint8).reshape(3, self.cut_size, self.cut_size))
+        self._check(self.lib.pxr_set_spot_mask(self.h, m.ctypes.data_as(C.c_void_p)), "pxr_set_spot_mask")
+
+    def set_spot_prompts(self, clip_idx, which, embeds, weights, stops):
+        """args.spot_prompts (which = 1) / args.spot_prompts_off (which = 0) of one perceptor (pixray.py:917-931): scored on
+        the cutouts of the masked image, ahead of the regular prompts in the loss vector.  Empty list clears."""
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(-1))
+        n = int(w.size)
+        s = np.maximum(np.ascontiguousarray(np.asarray(stops, dtype=np.float32).reshape(-1)), np.float32(-3.0e38))
+        D = self.clip_dims[clip_idx]
+        e = np.ascontiguousarray(np.asarray(embeds, dtype=np.float32).reshape(n, D)) if n else np.zeros((1, D), np.float32)
+        rc = self.lib.pxr_set_spot_prompts(self.h, clip_idx, int(which), e.ctypes.data_as(C.c_void_p), n, D,
+                                           w.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p))
+        self._check(rc, "pxr_set_spot_prompts")
+        self._n_spot[clip_idx][int(which)] = n
 
     def add_aux_loss(self, kind, weight, params):
         """One more entry of the loss vector / term of the gradient (pxr_add_aux_loss; Losses/*.py).  Returns the

@@ -97,6 +97,13 @@ class FakeEngine:
         self._log("backward")
         return torch.ones(self.z_shape)
 
+    def set_spot_mask(self, mask):
+        self.spot_mask = np.asarray(mask)
+        self._log("set_spot_mask", shape=tuple(self.spot_mask.shape), frac=float(self.spot_mask.mean()))
+
+    def set_spot_prompts(self, clip_idx, which, embeds, weights, stops):
+        self._log("set_spot_prompts", clip=clip_idx, which=which, n=len(weights))
+
     def set_z_grad(self, g):
         self._log("set_z_grad", shape=tuple(g.shape))
 

@@ -52,7 +52,7 @@ def test_unknown_setting_and_unknown_plugins_raise():
     api.reset_settings()
 
 
-@pytest.mark.parametrize("kw", [dict(spot_prompts="a"), dict(init_image="x.png"), dict(optimiser="AdamP"),
+@pytest.mark.parametrize("kw", [dict(target_images="t.png"), dict(init_image="x.png"), dict(optimiser="AdamP"),
                                 dict(perceptors="slip"), dict(filters="wallpaper"), dict(make_video=True),
                                 dict(animation_dir="anim"), dict(overlay_image="o.png"), dict(transparent=True)])
 def test_options_off_the_hot_path_are_refused_not_ignored(kw):
@@ -308,3 +308,31 @@ def test_file_image_prompts_keep_their_aspect_ratio(fake, tmp_path):
     # 160x40 (area 6400 > 64*64 = 4096): ratio 4 -> 128 x 32;  200x300: ratio 2/3 -> 52 x 78
     assert tuple(imgs[0].shape[-2:]) == (32, 128) and tuple(imgs[1].shape[-2:]) == (78, 52)
     assert 0.0 <= float(imgs[0].min()) and float(imgs[0].max()) <= 1.0
+
+
+def test_spot_prompts_reach_the_engine(fake, tmp_path):
+    """args.spot_prompts / spot_prompts_off (pixray.py:917-931) with the reference's own mask image (inputs/spot_square.png,
+    fetch_spot_indexes pixray.py:370-394) resized to the cut size."""
+    ref_inputs = "/root/reference/inputs/spot_square.png"
+    if not os.path.exists(ref_inputs):
+        pytest.skip("reference checkout not present")
+    (tmp_path / "inputs").mkdir(exist_ok=True)
+    import shutil
+    shutil.copy(ref_inputs, tmp_path / "inputs" / "spot_square.png")
+    _init(tmp_path, prompts="x", clip_models="ViT-B/32,ViT-B/16", spot_prompts="a red circle:2|a dot", spot_prompts_off="the sky")
+    eng = api._state.engine
+    calls = [c for c in eng.calls if c[0] == "set_spot_prompts"]
+    assert [(c[1]["clip"], c[1]["which"], c[1]["n"]) for c in calls] == [(0, 1, 2), (0, 0, 1), (1, 1, 2), (1, 0, 1)]
+    assert eng.spot_mask.shape == (3, 224, 224) and 0.05 < eng.spot_mask.mean() < 0.95
+    api.reset_settings()
+    with pytest.raises(FileNotFoundError):
+        os.environ["PIXRAY_ROOT"] = str(tmp_path / "nowhere")
+        _init2 = dict(size=[64, 64], num_cuts=8, outdir="", seed="7", b200_allow_synthetic=True, prompts="x", clip_models="ViT-B/16",
+                      spot_prompts="a dot", vector_prompts="none")
+        api.add_settings(**_init2)
+        cwd = os.getcwd()
+        os.chdir(tmp_path / "vectors")
+        try:
+            api.do_init(api.apply_settings())
+        finally:
+            os.chdir(cwd)

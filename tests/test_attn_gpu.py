@@ -55,7 +55,9 @@ def _report(name, got, ref, log):
     return err.max().item(), m
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 197, 12), (3, 50, 4), (1, 240, 2), (2, 130, 3), (5, 64, 2), (1, 16, 1), (150, 197, 1)])
+@pytest.mark.parametrize("B,T,H", [(2, 197, 12), (3, 50, 4), (1, 240, 2), (2, 130, 3), (5, 64, 2), (1, 16, 1), (150, 197, 1),
+                                   # several (image, head) items per CTA at T <= 128 (ViT-B/32 with many cutouts)
+                                   (40, 50, 12), (13, 128, 12)])
 def test_attention_matches_torch(B, T, H):
     torch.manual_seed(B * 1000 + T)
     W = 64 * H
