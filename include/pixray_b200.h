@@ -70,7 +70,10 @@ typedef struct {
    * to [cut_size, int(cut_size * a)] (a > 1) or [int(cut_size / a), cut_size] (a < 1) before the warps (pixray.py:468-472)
    * and changes the wide stack's affine (pixray.py:420-432).  0 = 1 (square). */
   float cut_aspect;
-  int reserved[4];
+  /* the stretched size itself, int(cut_size * a) resp. int(cut_size * (1 / a)) as the reference's Python floats give it
+   * (kornia rescale truncates); 0 = derive from cut_aspect (which, being a C float, can round across an integer) */
+  int cut_src_h, cut_src_w;
+  int reserved[2];
 } pxr_config;
 
 /* Per-iteration cutout parameters: what kornia's augmentations sample per cutout, made explicit.
@@ -137,6 +140,10 @@ int pxr_set_comm(pxr_handle h, const void* nccl_unique_id, int rank, int world);
 int pxr_get_unique_id(void* out128);
 
 int pxr_synth(pxr_handle h, const float* z, float* out_img /* [3,H,W] */);
+/* z = model.encode(img)[0]: VqganDrawer.init_from_tensor / reapply_from_tensor / get_z_from_tensor (vqgan.py:174-185) --
+ * taming Encoder + quant_conv + nearest codebook row.  img device [3,H,W] in [-1,1]; z_out device [z_channels,h,w].
+ * Available when the weights loaded before pxr_finalize include the checkpoint's encoder.* and quant_conv.* tensors. */
+int pxr_vqgan_encode(pxr_handle h, const float* img, float* z_out);
 /* Distribution of the engine-drawn ColorJitter: Bernoulli(p) per cutout, saturation_factor ~ U(1-s, 1+s),
  * hue_factor ~ U(-hue, hue), one random order per group and iteration.  Defaults = the reference's call sites
  * (0.8, 0.1, 0.1); p = 0 turns the stage off. */
@@ -206,6 +213,14 @@ int pxr_set_batches(pxr_handle h, int batches);
 /* hand pxr_step the gradient to apply (device [z_numel]); the per-op plugin loop accumulates several passes itself */
 int pxr_set_z_grad(pxr_handle h, const float* z_grad);
 int pxr_sync(pxr_handle h);
+
+/* Checkpoint of the optimisation state for resume: {z, Adam m, v, step count, learning-rate / best-loss /
+ * drop bookkeeping} as one host blob of pxr_state_size bytes.  Load into an engine of the same configuration (after
+ * pxr_set_schedule when the saved session was device-managed) and keep calling pxr_iterate with the next iteration number:
+ * the engine-drawn augmentations are keyed by (seed, iteration), so the continuation follows the uninterrupted run. */
+int pxr_state_size(pxr_handle h, int64_t* nbytes);
+int pxr_save_state(pxr_handle h, void* host_buf);
+int pxr_load_state(pxr_handle h, const void* host_buf);
 
 /* Introspection used by tests and bench.py */
 int pxr_num_kernel_launches(pxr_handle h, int64_t* out); /* launches issued since create */

@@ -520,18 +520,95 @@ class Decoder(nn.Module):
         return self.conv_out(_swish(self.norm_out(h)))
 
 
-class VQModel(nn.Module):
-    """The slice of taming VQModel pixray uses (vqgan.py:122-142, 190-195): codebook, post_quant_conv, decoder."""
+class _Downsample(nn.Module):
+    """taming Downsample(with_conv=True): F.pad(x, (0, 1, 0, 1)) then Conv2d(k=3, stride=2, padding=0) [UPSTREAM]."""
 
-    def __init__(self, n_embed=16384, embed_dim=256, **dd):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class Encoder(nn.Module):
+    """taming Encoder (VQModel.encode, used by VqganDrawer.init_from_tensor / reapply_from_tensor / get_z_from_tensor,
+    vqgan.py:174-185) [UPSTREAM taming/modules/diffusionmodules/model.py, un-vendored: parity unpinned for the leaf; module
+    names mirror the checkpoint keys].  double_z = False (the VQ models)."""
+
+    def __init__(self, ch=128, in_channels=3, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, attn_resolutions=(16,),
+                 resolution=256, z_channels=256, **ignore):
+        super().__init__()
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            down = _Up()
+            down.block, down.attn = nn.ModuleList(), nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                down.block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    down.attn.append(AttnBlock(block_in))
+            if i_level != self.num_resolutions - 1:
+                down.downsample = _Downsample(block_in)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.norm_out = _gn(block_in)
+        self.conv_out = nn.Conv2d(block_in, z_channels, 3, 1, 1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for i_level in range(self.num_resolutions):
+            down = self.down[i_level]
+            for i_block in range(self.num_res_blocks):
+                h = down.block[i_block](h)
+                if len(down.attn) > 0:
+                    h = down.attn[i_block](h)
+            if i_level != self.num_resolutions - 1:
+                h = down.downsample(h)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        return self.conv_out(_swish(self.norm_out(h)))
+
+
+class VQModel(nn.Module):
+    """The slice of taming VQModel pixray uses (vqgan.py:122-142, 174-195): codebook, post_quant_conv, decoder and -- with
+    with_encoder -- the encoder + quant_conv behind model.encode."""
+
+    def __init__(self, n_embed=16384, embed_dim=256, with_encoder=False, **dd):
         super().__init__()
         self.quantize = nn.Module()
         self.quantize.embedding = nn.Embedding(n_embed, embed_dim)
         self.post_quant_conv = nn.Conv2d(embed_dim, dd.get("z_channels", 256), 1)
         self.decoder = Decoder(**dd)
+        if with_encoder:
+            self.encoder = Encoder(**dd)
+            self.quant_conv = nn.Conv2d(dd.get("z_channels", 256), embed_dim, 1)
 
     def decode(self, zq):
         return self.decoder(self.post_quant_conv(zq))
+
+    def encode(self, x):
+        """taming VQModel.encode: quantize(quant_conv(encoder(x))) -> (quant [B, C, h, w], indices, pre-quantisation h);
+        VectorQuantizer: nearest code by squared L2, value = the codebook row."""
+        h = self.quant_conv(self.encoder(x))
+        b, c, hh, ww = h.shape
+        flat = h.permute(0, 2, 3, 1).reshape(-1, c)
+        cb = self.quantize.embedding.weight
+        d = flat.pow(2).sum(dim=1, keepdim=True) + cb.pow(2).sum(dim=1) - 2 * flat @ cb.T
+        idx = d.argmin(dim=1)
+        quant = cb[idx].reshape(b, hh, ww, c).permute(0, 3, 1, 2).contiguous()
+        return quant, idx, h
 
 
 def init_vqgan_weights(model, seed=0):

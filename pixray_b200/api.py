@@ -104,7 +104,7 @@ _ENGINE_OPTIONS = [(("--b200_weights",), "b200_weights", None, None), (("--b200_
 # options that leave the hot path: dest -> the value(s) that keep them off
 _OFF_PATH = {
     "labels": ([],), "image_labels": (None,),
-    "overlay_image": (None,), "init_image": (None,), "target_images": (None, []), "animation_dir": (None,),
+    "target_images": (None, []), "animation_dir": (None,),
     "init_weight": (None, 0, 0.0), "init_weight_dist": (0, 0.0), "init_weight_cos": (0, 0.0), "init_weight_pix": (0, 0.0),
     "perceptors": ("clip",), "optimiser": ("Adam",), "make_video": (False,), "transparent": (False,), "filters": (None,),
     "image_prompt_shuffle": (False,),
@@ -344,7 +344,7 @@ def do_init(args):
         if key in weights:
             vq_sd = _load_state_dict(weights[key])
         elif kind == E.DRAWER_VQGAN:
-            vq_sd = S.vqgan_state_dict(E.VQGAN_F16_16384, 0)
+            vq_sd = S.vqgan_state_dict(E.VQGAN_F16_16384, 0, with_encoder=True)
         elif args.b200_allow_synthetic:
             vq_sd = S.vdiff_state_dict(0)
         else:
@@ -360,16 +360,48 @@ def do_init(args):
     st.engine, st.session = eng, P.Session(eng)
     drawer = class_table[args.drawer](args, st.session)
     drawer.load_model(args, eng.device)
-    if kind == E.DRAWER_VQGAN:
-        # VqganDrawer.rand_init (vqgan.py:162-171): random codebook rows.  The reference's default start (a noise image
-        # through the VQGAN encoder) is init-time work outside the hot path.
+    # ---- image initialisation (pixray.py:674-727): a noise / gradient / blank start image, optionally an init image, into
+    # drawer.init_from_tensor(t * 2 - 1) -- for the VQGAN drawer that is model.encode on the engine (pxr_vqgan_encode)
+    st.init_image_tensor = None
+    if kind in (E.DRAWER_VQGAN, E.DRAWER_PIXEL) and (args.init_image or args.init_noise):
+        from PIL import Image
+        from .util import random_gradient_image, random_noise_image
+        rng = np.random.default_rng(st.seed)
+        w0, h0 = args.size[0], args.size[1]
+        if args.init_noise == "pixels":
+            img = Image.fromarray(random_noise_image(w0, h0, rng))
+        elif args.init_noise == "gradient":
+            img = Image.fromarray(random_gradient_image(w0, h0, rng))
+        elif args.init_noise == "snow":
+            img = Image.fromarray(rng.integers(0, 255, (w0, h0, 3), dtype=np.uint8))  # old_random_noise_image: (w, h, 3)
+        else:
+            img = Image.new(mode="RGB", size=(w0, h0), color=(255, 255, 255))
+        starting_image = img.convert("RGB").resize((sideX, sideY), Image.LANCZOS)
+        to_t = lambda im: torch.from_numpy(np.asarray(im, dtype=np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)  # noqa: E731
+        if args.init_image:
+            init_rgb = Image.open(args.init_image).convert("RGB").resize((sideX, sideY), Image.LANCZOS)
+            st.init_image_tensor = to_t(init_rgb)
+            drawer.init_from_tensor(st.init_image_tensor * 2 - 1)  # the init image itself, not the alpha paste (pixray.py:715-716)
+        else:
+            drawer.init_from_tensor(to_t(starting_image) * 2 - 1)
+    elif kind == E.DRAWER_VQGAN:
+        # init_image and init_noise both off: the legacy start (VqganDrawer.rand_init, vqgan.py:162-171): random codebook rows
         code = torch.as_tensor(vq_sd["quantize.embedding.weight"], dtype=torch.float32)
         idx = torch.randint(code.shape[0], (eng.z_shape[2] * eng.z_shape[3],))
         drawer.set_z(code[idx].T.reshape(eng.z_shape))
     elif kind == E.DRAWER_PIXEL:
-        drawer.init_from_tensor(torch.rand(1, 3, sideY, sideX) * 2 - 1)  # random_noise_image (pixray.py:194-205) in [-1, 1]
+        drawer.init_from_tensor(torch.rand(1, 3, sideY, sideX) * 2 - 1)
     else:
         drawer.init_from_tensor(None)
+    # overlays (pixray.py:729-745, 1408-1420): one RGBA image pasted over the current image every overlay_every iterations
+    st.overlay_rgba = None
+    if args.overlay_image is not None:
+        from PIL import Image
+        ov = Image.open(args.overlay_image).convert("RGBA").resize((sideX, sideY), Image.LANCZOS)
+        if args.overlay_alpha:
+            ov.putalpha(args.overlay_alpha)
+        st.overlay_rgba = ov
+    st.side = (sideX, sideY)
     st.drawer = drawer
     st.perceptors = [P.Perceptor(st.session, i) for i in range(len(args.clip_models))]
     st.make_cutouts = P.MakeCutouts(clip_cfgs[0]["image_res"], args.num_cuts, st.session, cut_pow=args.cut_pow, seed=st.seed,
@@ -487,6 +519,18 @@ def _load_image(src, sideX, sideY):
     return torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0).contiguous()
 
 
+def re_average_z(args):
+    """pixray.py:1408-1420: render, paste the overlay, re-encode (drawer.reapply_from_tensor)."""
+    from PIL import Image
+    st = _state
+    cur = st.drawer.to_image().convert("RGB")
+    if st.overlay_rgba is not None:
+        cur.paste(st.overlay_rgba, (0, 0), mask=st.overlay_rgba)
+    cur = cur.resize(st.side, Image.LANCZOS)
+    t = torch.from_numpy(np.asarray(cur, dtype=np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
+    st.drawer.reapply_from_tensor(t * 2 - 1)
+
+
 def rebuild_optimisers(args):
     """pixray.py:520-555: a FRESH Adam at learning_rate / 10^drops (or the drawer's own rate, fftdrawer.py:63-67)."""
     st = _state
@@ -520,7 +564,7 @@ def train(args, cur_it):
     rebuild = False
     if cur_it < args.iterations:
         if apply_overlay(args, cur_it):
-            raise NotImplementedError("overlays re-encode through the VQGAN encoder (pixray.py:1408-1420)")
+            re_average_z(args)
         st.session.begin_iteration(cur_it)
         drawer, eng = st.drawer, st.engine
         if isinstance(drawer, P.VdiffDrawer):
@@ -563,7 +607,7 @@ def _train_managed(args, cur_it):
     st = _state
     if cur_it < args.iterations:
         if apply_overlay(args, cur_it):
-            raise NotImplementedError("overlays re-encode through the VQGAN encoder (pixray.py:1408-1420)")
+            re_average_z(args)
         st.session.begin_iteration(cur_it)
         if cur_it in args.learning_rate_drops:
             print("Dropping learning rate")
@@ -623,6 +667,32 @@ def do_run(args, return_display=False):
     except KeyboardInterrupt:
         pass
     return True
+
+
+def save_checkpoint(path):
+    """z, Adam state, learning-rate / drop bookkeeping and the iteration counter of the running session, for resume."""
+    st = _state
+    st.engine.sync()
+    with open(path, "wb") as f:
+        blob = st.engine.save_state()
+        f.write(int(st.cur_iteration).to_bytes(8, "little"))
+        f.write(int(st.num_loss_drop).to_bytes(8, "little"))
+        f.write(np.float64(st.lr).tobytes())
+        f.write(blob)
+
+
+def load_checkpoint(path):
+    """Into a session built by do_init with the same settings: restores z / Adam / bookkeeping; do_run then continues from the
+    saved iteration."""
+    st = _state
+    with open(path, "rb") as f:
+        raw = f.read()
+    st.cur_iteration = int.from_bytes(raw[:8], "little")
+    st.num_loss_drop = int.from_bytes(raw[8:16], "little")
+    st.lr = float(np.frombuffer(raw[16:24], dtype=np.float64)[0])
+    st.engine.load_state(raw[24:])
+    st.drawer.set_z(st.engine.read_z())
+    return st.cur_iteration
 
 
 def get_image():

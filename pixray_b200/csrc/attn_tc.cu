@@ -747,49 +747,52 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd2_kernel(const __grid_
         const int ncol = max(0, min(32, nk - c_lo));  // this warp's columns of the block: 32, 16 or 0
         mbar_wait(bar_p1, cnt & 1);
         tc_fence_after();
-        // Two steps keep the live registers under the 96 a 576-thread block gets: S -> P (packed fp16), then dP -> dS.
-        // Freeing the S / dP columns a little later costs nothing: the tensor pipe is still busy with the previous
-        // block's phase 2 when phase 1 of the next block is issued.
+        // Sixteen columns at a time (S and dP of the same columns side by side: 32 live accumulator registers + the packed
+        // results; the 96-register budget of a 576-thread block has no room for all 64 at once).  ~7 instructions per score:
+        // FFMA + EX2 for p, FADD + 2 FMUL for dS, half a cvt.pack each -- the threads, not the tensor pipe, pace this kernel
+        // (ncu: 830 instructions per thread and block before this rewrite, profiles/r02_ncu_attn_summary.txt), so the
+        // key-padding mask is only evaluated in the one slice that straddles T.
         uint4 pv[4], dv[4];
         const float lz = mt ? lse2_1 : lse2_0, Dm = mt ? Dv1 : Dv0;
         const int key0 = jt * 128 + c_lo;
-        {
-          uint32_t s0[16], s1[16];
-          if (ncol > 0) tmem_ld_x16(lane_addr + T2_S + c_lo, s0);
-          if (ncol > 16) tmem_ld_x16(lane_addr + T2_S + c_lo + 16, s1);
-          tmem_ld_wait();
+        const bool all_keys_valid = key0 + 32 <= T;
+        const float ps = p.scale;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float e[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = 8 * g + j;
-              float x = ex2_approx(fmaf(__uint_as_float(g < 2 ? s0[c & 15] : s1[c & 15]), sc, -lz));
-              if (key0 + c >= T || c >= ncol) x = 0.f;
-              e[j] = x;
-            }
-            pv[g] = pack8h(e);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t sr[16], dr[16];
+          const bool live = ncol > 16 * hf;
+          if (live) {
+            tmem_ld_x16(lane_addr + T2_S + c_lo + 16 * hf, sr);
+            tmem_ld_x16(lane_addr + T2_DP + c_lo + 16 * hf, dr);
           }
-        }
-        {
-          uint32_t d0[16], d1[16];
-          if (ncol > 0) tmem_ld_x16(lane_addr + T2_DP + c_lo, d0);
-          if (ncol > 16) tmem_ld_x16(lane_addr + T2_DP + c_lo + 16, d1);
           tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free);
+          if (hf == 1) {  // both halves are in registers: phase 1 of the next block may overwrite S / dP
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free);
+          }
+          if (!live) continue;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             float e[8], f[8];
-            unpack8h(pv[g], e);  // dS from the fp16-rounded P: the value the dV product multiplies
+            if (all_keys_valid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = 8 * g + j;
-              const float dpv = __uint_as_float(g < 2 ? d0[c & 15] : d1[c & 15]);
-              f[j] = (c < ncol) ? p.scale * e[j] * (dpv - Dm) : 0.f;
+              for (int j = 0; j < 8; ++j) {
+                const float x = ex2_approx(fmaf(__uint_as_float(sr[8 * g + j]), sc, -lz));
+                e[j] = x;
+                f[j] = ps * x * (__uint_as_float(dr[8 * g + j]) - Dm);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x = ex2_approx(fmaf(__uint_as_float(sr[8 * g + j]), sc, -lz));
+                if (key0 + 16 * hf + 8 * g + j >= T) x = 0.f;  // keys past the sequence: P = 0, and so dS = 0
+                e[j] = x;
+                f[j] = ps * x * (__uint_as_float(dr[8 * g + j]) - Dm);
+              }
             }
-            dv[g] = pack8h(f);
+            pv[2 * hf + g] = pack8h(e);
+            dv[2 * hf + g] = pack8h(f);
           }
         }
         // the previous block's products have consumed P / dS (and its accumulators are current)

@@ -449,7 +449,14 @@ class Engine {
   FftPlans* fft = nullptr;
   void build_cutouts();
   void build_clip(int i);
-  ConvW load_conv(const std::string& prefix, int cin, int cout, int ks);
+  ConvW load_conv(const std::string& prefix, int cin, int cout, int ks, int cin_real = 0);
+  // VQGAN encoder (taming Encoder + quant_conv + nearest code): VqganDrawer.init_from_tensor / reapply_from_tensor /
+  // get_z_from_tensor (vqgan.py:174-185).  Forward only; built at finalize when the checkpoint carries encoder.* tensors.
+  OpList enc_fwd;
+  bool have_encoder = false;
+  float* enc_img = nullptr;   // [3, H, W] input in [-1, 1]
+  float* enc_z = nullptr;     // [C, hw] result
+  void build_vqgan_encoder();
   NormW load_norm(int mod, const std::string& prefix, int c);
   Act new_act(int H, int Wd, int C) {
     Act a;
@@ -568,8 +575,10 @@ NormW Engine::load_norm(int mod, const std::string& prefix, int c) {
   return n;
 }
 
-ConvW Engine::load_conv(const std::string& prefix, int cin, int cout, int ks) {
-  const HostWeight& w = W(PXR_MOD_VQGAN, prefix + ".weight", {cout, cin, ks, ks});
+// cin_real < cin: the stored tensor has cin_real input channels and the activation is zero-padded to cin (conv_in: 3 -> 64)
+ConvW Engine::load_conv(const std::string& prefix, int cin, int cout, int ks, int cin_real) {
+  if (cin_real <= 0) cin_real = cin;
+  const HostWeight& w = W(PXR_MOD_VQGAN, prefix + ".weight", {cout, cin_real, ks, ks});
   const HostWeight& b = W(PXR_MOD_VQGAN, prefix + ".bias", {cout});
   ConvW c;
   c.cin = cin;
@@ -582,10 +591,10 @@ ConvW Engine::load_conv(const std::string& prefix, int cin, int cout, int ks) {
   if (cin % 64) throw EngineError(-42, "conv '" + prefix + "': input channels must be a multiple of 64");
   std::vector<float> f((size_t)taps * c.cout_pad * cin, 0.f), d((size_t)taps * c.cin_rows * c.cout_k, 0.f);
   for (int co = 0; co < cout; ++co)
-    for (int ci = 0; ci < cin; ++ci)
+    for (int ci = 0; ci < cin_real; ++ci)
       for (int ty = 0; ty < ks; ++ty)
         for (int tx = 0; tx < ks; ++tx) {
-          float v = w.data[(((size_t)co * cin + ci) * ks + ty) * ks + tx];
+          float v = w.data[(((size_t)co * cin_real + ci) * ks + ty) * ks + tx];
           int t = ty * ks + tx;
           f[((size_t)t * c.cout_pad + co) * cin + ci] = v;
           // dgrad: dx[p] = sum_t dy[p + off(t)] * W[.., flipped t]
@@ -956,6 +965,158 @@ void Engine::build_vqgan() {
   // flatten backward stack in reverse block order
   for (int i = (int)bwd_stack.size() - 1; i >= 0; --i) drawer_bwd.append(bwd_stack[i]);
   bwd_stack.clear();
+  if (weights[PXR_MOD_VQGAN].count("encoder.conv_in.weight")) build_vqgan_encoder();
+}
+
+// taming Encoder (un-vendored: taming/modules/diffusionmodules/model.py, restated in oracle/ref_path.py): conv_in, per level
+// num_res_blocks x ResnetBlock (+ AttnBlock at attn_resolution) and a strided Downsample, mid block_1 / attn_1 / block_2,
+// norm_out + swish + conv_out; then VQModel.encode's quant_conv and the quantiser's nearest code.  Same kernels as the
+// decoder's forward; no backward (the encoder only runs at init / overlay time, never inside the gradient path).
+void Engine::build_vqgan_encoder() {
+  const int zc = cfg.z_channels, ne = cfg.n_embed, L = cfg.n_levels, H = cfg.image_h, Wd = cfg.image_w;
+  cudaStream_t cs = st;
+  auto act = [&](int h, int w, int c) {
+    Act a;
+    a.H = h;
+    a.W = w;
+    a.C = c;
+    a.p = dalloc<act_t>((size_t)h * w * c);
+    return a;
+  };
+  auto conv = [&](const Act& x, const ConvW& w, const act_t* res) {
+    Act y = act(x.H, x.W, w.cout);
+    GemmEpilogue e;
+    e.bias = w.bias;
+    e.res_f16 = res;
+    e.out_f16 = y.p;
+    e.ldc = y.C;
+    add_conv(enc_fwd, x.p, x.H, x.W, x.C, w.w, w.cout_pad, w.cout, w.ks, e);
+    return y;
+  };
+  auto resblock_fwd = [&](const Act& x, const std::string& prefix, int cin, int cout) {
+    NormW n1 = load_norm(PXR_MOD_VQGAN, prefix + ".norm1", cin), n2 = load_norm(PXR_MOD_VQGAN, prefix + ".norm2", cout);
+    ConvW c1 = load_conv(prefix + ".conv1", cin, cout, 3), c2 = load_conv(prefix + ".conv2", cout, cout, 3);
+    Act a1 = act(x.H, x.W, cin), a2 = act(x.H, x.W, cout);
+    add_gn(enc_fwd, x, n1, 1, a1.p);
+    Act h1 = conv(a1, c1, nullptr);
+    add_gn(enc_fwd, h1, n2, 1, a2.p);
+    const act_t* shortcut = x.p;
+    if (cin != cout) {
+      ConvW sc = load_conv(prefix + ".nin_shortcut", cin, cout, 1);
+      shortcut = conv(x, sc, nullptr).p;
+    }
+    return conv(a2, c2, shortcut);
+  };
+  auto attn_fwd = [&](const Act& x, const std::string& prefix, int c) {
+    NormW n = load_norm(PXR_MOD_VQGAN, prefix + ".norm", c);
+    std::vector<float> wq, bq;
+    for (const char* nm : {".q", ".k", ".v"}) {
+      const HostWeight& w = W(PXR_MOD_VQGAN, prefix + nm + ".weight", {c, c, 1, 1});
+      const HostWeight& b = W(PXR_MOD_VQGAN, prefix + nm + ".bias", {c});
+      wq.insert(wq.end(), w.data.begin(), w.data.end());
+      bq.insert(bq.end(), b.data.begin(), b.data.end());
+    }
+    act_t* wqkv = upload_f16(wq);
+    float* bqkv = upload(bq);
+    ConvW po = load_conv(prefix + ".proj_out", c, c, 1);
+    const int T = x.pixels(), ldT = round_up(T, 8);
+    Act a = act(x.H, x.W, c), O = act(x.H, x.W, c);
+    act_t* qkv = dalloc<act_t>((size_t)T * 3 * c);
+    act_t* P = dalloc<act_t>((size_t)T * ldT);
+    add_gn(enc_fwd, x, n, 0, a.p);
+    {
+      GemmEpilogue e;
+      e.bias = bqkv;
+      e.out_f16 = qkv;
+      e.ldc = 3 * c;
+      add_gemm(enc_fwd, opK(a.p, c, T, c), opK(wqkv, c, 3 * c, c), T, 3 * c, c, e);
+    }
+    {
+      GemmEpilogue e;
+      e.alpha = 1.f / std::sqrt((float)c);
+      e.out_f16 = P;
+      e.ldc = ldT;
+      add_gemm(enc_fwd, opK(qkv, 3 * c, T, c), opK(qkv + c, 3 * c, T, c), T, T, c, e);
+    }
+    enc_fwd.add(1, [=] { softmax_forward(P, T, T, ldT, cs); }, 0.0, "softmax_forward");
+    {
+      GemmEpilogue e;
+      e.out_f16 = O.p;
+      e.ldc = c;
+      add_gemm(enc_fwd, opK(P, ldT, T, ldT), opMN(qkv + 2 * c, 3 * c, c, T), T, c, T, e);
+    }
+    return conv(O, po, x.p);
+  };
+  enc_img = dalloc<float>((size_t)3 * H * Wd);
+  Act x0 = act(H, Wd, 64);
+  {
+    float* im = enc_img;
+    const int px = H * Wd;
+    enc_fwd.add(1, [=] { image_to_nhwc64(im, px, x0.p, cs); }, 0.0, "image_to_nhwc64");
+  }
+  ConvW cin_w = load_conv("encoder.conv_in", 64, cfg.ch, 3, 3);
+  Act hcur = conv(x0, cin_w, nullptr);
+  int curr_res = cfg.resolution, block_in = cfg.ch;
+  for (int lv = 0; lv < L; ++lv) {
+    const int block_out = cfg.ch * cfg.ch_mult[lv];
+    for (int ib = 0; ib < cfg.num_res_blocks; ++ib) {
+      const std::string p = "encoder.down." + std::to_string(lv) + ".block." + std::to_string(ib);
+      hcur = resblock_fwd(hcur, p, block_in, block_out);
+      block_in = block_out;
+      if (curr_res == cfg.attn_resolution)
+        hcur = attn_fwd(hcur, "encoder.down." + std::to_string(lv) + ".attn." + std::to_string(ib), block_in);
+    }
+    if (lv != L - 1) {
+      ConvW dw = load_conv("encoder.down." + std::to_string(lv) + ".downsample.conv", block_in, block_in, 3);
+      Act full = conv(hcur, dw, nullptr);
+      Act half = act(hcur.H / 2, hcur.W / 2, block_in);
+      const int fh = hcur.H, fw = hcur.W, fc = block_in;
+      enc_fwd.add(1, [=] { subsample_odd(full.p, fh, fw, fc, half.p, cs); }, 0.0, "subsample_odd");
+      hcur = half;
+      curr_res /= 2;
+    }
+  }
+  hcur = resblock_fwd(hcur, "encoder.mid.block_1", block_in, block_in);
+  hcur = attn_fwd(hcur, "encoder.mid.attn_1", block_in);
+  hcur = resblock_fwd(hcur, "encoder.mid.block_2", block_in, block_in);
+  NormW no = load_norm(PXR_MOD_VQGAN, "encoder.norm_out", block_in);
+  Act a = act(hcur.H, hcur.W, block_in);
+  add_gn(enc_fwd, hcur, no, 1, a.p);
+  ConvW co = load_conv("encoder.conv_out", block_in, zc, 3);  // double_z = False for the VQ models
+  Act hz = conv(a, co, nullptr);
+  ConvW qc = load_conv("quant_conv", zc, zc, 1);
+  Act hq = conv(hz, qc, nullptr);
+  const int hw = hq.pixels();
+  if ((int64_t)zc * hw != z_numel) throw EngineError(-44, "encoder output does not match the latent size");
+  // quantise: the same exact fp32 nearest-code search as synth (the codebook copies are the decoder's)
+  const HostWeight& cb = W(PXR_MOD_VQGAN, "quantize.embedding.weight", {ne, zc});
+  std::vector<float> cbT((size_t)zc * ne), c2(ne);
+  for (int j = 0; j < ne; ++j) {
+    float s2 = 0.f;
+    for (int k = 0; k < zc; ++k) {
+      const float v = cb.data[(size_t)j * zc + k];
+      cbT[(size_t)k * ne + j] = v;
+      s2 += v * v;
+    }
+    c2[j] = s2;
+  }
+  float *d_cb = upload(cb.data), *d_cbT = upload(cbT), *d_c2 = upload(c2);
+  const int n_chunks = (ne + 1023) / 1024;
+  float* part_d = dalloc<float>((size_t)hw * n_chunks);
+  int* part_i = dalloc<int>((size_t)hw * n_chunks);
+  int* idx = dalloc<int>(hw);
+  float* z32 = dalloc<float>((size_t)zc * hw);
+  act_t* zq16 = dalloc<act_t>((size_t)hw * zc);
+  enc_z = dalloc<float>((size_t)zc * hw);
+  float* ez = enc_z;
+  enc_fwd.add(4, [=] {
+    vq_backward(hq.p, 1.f, zc, hw, z32, cs);  // NHWC fp16 -> [C, hw] fp32 (the same transpose kernel the decoder's backward ends with)
+    vq_nearest(z32, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq16, cs);
+    gather_codes(d_cb, idx, zc, hw, ez, cs);
+  }, 0.0, "encoder quantise");
+  reg("enc_idx", idx, sizeof(int) * hw);
+  reg("enc_h", z32, sizeof(float) * zc * hw);
+  have_encoder = true;
 }
 
 void Engine::build_pixel() {
@@ -1033,6 +1194,12 @@ void Engine::build_cutouts() {
   aspect = (cfg.cut_aspect > 0.f && cfg.cut_aspect != 1.f) ? (double)cfg.cut_aspect : 1.0;
   if (aspect > 8.0 || aspect < 0.125) throw EngineError(-66, "cut_aspect (canvas width / height) must be within [1/8, 8]");
   source_size(cs_, aspect, src_h, src_w);
+  if (aspect != 1.0 && cfg.cut_src_h > 0 && cfg.cut_src_w > 0) {  // the caller's (double-precision) truncation wins
+    if (std::abs(cfg.cut_src_h - src_h) > 1 || std::abs(cfg.cut_src_w - src_w) > 1)
+      throw EngineError(-66, "cut_src_h / cut_src_w do not match cut_aspect");
+    src_h = cfg.cut_src_h;
+    src_w = cfg.cut_src_w;
+  }
   if (aspect != 1.0) {
     cut_src = dalloc<float>((size_t)3 * src_h * src_w);
     g_cut_src = dalloc<float>((size_t)3 * src_h * src_w);
@@ -1088,7 +1255,7 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
   float fill = p ? p->fill : 0.f;
   if (!T) {  // engine RNG, keyed by (seed, iter, global cutout index)
     gen.resize((size_t)cfg.cutn * 9);
-    sample_cutout_transforms(cfg.seed, key, cfg.cutn, cfg.cut_size, gen.data(), aspect);
+    sample_cutout_transforms(cfg.seed, key, cfg.cutn, cfg.cut_size, gen.data(), aspect, src_h, src_w);
     T = gen.data();
     if (!p) fill = sample_fill(cfg.seed, key);
   }
@@ -2050,6 +2217,22 @@ int pxr_synth(pxr_handle h, const float* z, float* out_img) {
   });
 }
 
+// model.encode(init_tensor)[0] (VqganDrawer.init_from_tensor / reapply_from_tensor / get_z_from_tensor, vqgan.py:174-185):
+// img device fp32 [3, H, W] in [-1, 1] -> z_out device fp32 [z_channels, h, w] = the codebook rows nearest to
+// quant_conv(encoder(img)).  Needs the checkpoint's encoder.* / quant_conv.* tensors (loaded before pxr_finalize).
+int pxr_vqgan_encode(pxr_handle h, const float* img, float* z_out) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (e->cfg.drawer != PXR_DRAWER_VQGAN) throw EngineError(-67, "pxr_vqgan_encode: not a VQGAN engine");
+    if (!e->have_encoder) throw EngineError(-67, "pxr_vqgan_encode: the loaded VQGAN weights carry no encoder.* tensors");
+    if (!img || !z_out) throw EngineError(-10, "pxr_vqgan_encode: null pointer");
+    PXR_CUDA(cudaMemcpyAsync(e->enc_img, img, sizeof(float) * 3 * e->cfg.image_h * e->cfg.image_w, cudaMemcpyDeviceToDevice, e->st));
+    e->run(e->enc_fwd);
+    e->check_launch("vqgan encode");
+    PXR_CUDA(cudaMemcpyAsync(z_out, e->enc_z, sizeof(float) * e->z_numel, cudaMemcpyDeviceToDevice, e->st));
+  });
+}
+
 int pxr_set_color_jitter(pxr_handle h, float p, float saturation, float hue) {
   PXR_TRY(h, {
     if (!(p >= 0.f && p <= 1.f) || saturation < 0.f || saturation > 1.f || hue < 0.f || hue > 0.5f)
@@ -2454,6 +2637,69 @@ int pxr_reset_optimizer(pxr_handle h) {
     PXR_CUDA(cudaMemsetAsync(e->adam_v, 0, e->z_numel * sizeof(float), e->st));
     e->adam_t = 0;
     if (e->managed) e->write_initial_drop_state();  // a fresh session: best-loss tracking and the drop count restart too
+  });
+}
+
+// ---- checkpoint of the optimisation state (z, Adam m / v / step, the drop bookkeeping): resume = load + keep iterating
+namespace {
+struct StateHeader {
+  uint32_t magic, version;
+  int64_t z_numel;
+  int32_t adam_t, managed, drop_parity, pad;
+  pxr::DropState drop;
+};
+constexpr uint32_t kStateMagic = 0x50585253u;  // "PXRS"
+}  // namespace
+
+int pxr_state_size(pxr_handle h, int64_t* nbytes) {
+  *nbytes = (int64_t)sizeof(StateHeader) + 3 * h->e->z_numel * (int64_t)sizeof(float);
+  return 0;
+}
+
+// host buffer of pxr_state_size bytes <- {header, z, m, v}.  Blocking.
+int pxr_save_state(pxr_handle h, void* host_buf) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!host_buf) throw EngineError(-10, "pxr_save_state: null buffer");
+    StateHeader hd{};
+    hd.magic = kStateMagic;
+    hd.version = 1;
+    hd.z_numel = e->z_numel;
+    hd.adam_t = e->adam_t;
+    hd.managed = e->managed ? 1 : 0;
+    hd.drop_parity = e->drop_parity;
+    if (e->managed)
+      PXR_CUDA(cudaMemcpyAsync(&hd.drop, e->drop_state + e->drop_parity, sizeof(pxr::DropState), cudaMemcpyDeviceToHost, e->st));
+    char* out = static_cast<char*>(host_buf);
+    const size_t zb = (size_t)e->z_numel * sizeof(float);
+    PXR_CUDA(cudaMemcpyAsync(out + sizeof hd, e->z_buf, zb, cudaMemcpyDeviceToHost, e->st));
+    PXR_CUDA(cudaMemcpyAsync(out + sizeof hd + zb, e->adam_m, zb, cudaMemcpyDeviceToHost, e->st));
+    PXR_CUDA(cudaMemcpyAsync(out + sizeof hd + 2 * zb, e->adam_v, zb, cudaMemcpyDeviceToHost, e->st));
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+    memcpy(out, &hd, sizeof hd);
+  });
+}
+
+// The inverse: the engine's z, Adam state and (when it was saved in managed mode and pxr_set_schedule was called here
+// too) the learning-rate / best-loss / drop-count bookkeeping.  Blocking.
+int pxr_load_state(pxr_handle h, const void* host_buf) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!host_buf) throw EngineError(-10, "pxr_load_state: null buffer");
+    StateHeader hd;
+    memcpy(&hd, host_buf, sizeof hd);
+    if (hd.magic != kStateMagic || hd.version != 1) throw EngineError(-68, "pxr_load_state: not a pixray_b200 state blob");
+    if (hd.z_numel != e->z_numel) throw EngineError(-68, "pxr_load_state: the blob belongs to a different latent shape");
+    const char* in = static_cast<const char*>(host_buf);
+    const size_t zb = (size_t)e->z_numel * sizeof(float);
+    PXR_CUDA(cudaMemcpyAsync(e->z_buf, in + sizeof hd, zb, cudaMemcpyHostToDevice, e->st));
+    PXR_CUDA(cudaMemcpyAsync(e->adam_m, in + sizeof hd + zb, zb, cudaMemcpyHostToDevice, e->st));
+    PXR_CUDA(cudaMemcpyAsync(e->adam_v, in + sizeof hd + 2 * zb, zb, cudaMemcpyHostToDevice, e->st));
+    e->adam_t = hd.adam_t;
+    if (hd.managed && e->managed) {
+      PXR_CUDA(cudaMemcpyAsync(e->drop_state + e->drop_parity, &hd.drop, sizeof(pxr::DropState), cudaMemcpyHostToDevice, e->st));
+    }
+    PXR_CUDA(cudaStreamSynchronize(e->st));
   });
 }
 

@@ -54,6 +54,15 @@ void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const
                       int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
                       GridBarrier* gb, cudaStream_t st, GnOpts o = GnOpts());
 
+// ---- VQGAN encoder side (taming Encoder; VqganDrawer.init_from_tensor, vqgan.py:174-185): forward only, init time
+// image [3, H, W] fp32 in [-1, 1] -> NHWC fp16 [pixels, 64] (channels 3..63 zero: conv_in's padded reduction)
+void image_to_nhwc64(const float* img, int pixels, act_t* out, cudaStream_t st);
+// taming Downsample: F.pad(x, (0,1,0,1)) + Conv2d(k=3, stride=2, padding=0) == the odd positions of the stride-1 "same"
+// convolution: y[i, j] = full[2 i + 1, 2 j + 1], [H, W, C] -> [H/2, W/2, C]
+void subsample_odd(const act_t* full, int H, int W, int C, act_t* y, cudaStream_t st);
+// z[c, p] = codebook[idx[p], c] (fp32): the quantised latent model.encode returns
+void gather_codes(const float* cb, const int* idx, int C, int hw, float* z, cudaStream_t st);
+
 void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st);        // nearest, [H,W,C]->[2H,2W,C]
 void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st);       // adjoint: [2H,2W,C]->[H,W,C]
 

@@ -684,6 +684,42 @@ __global__ void __launch_bounds__(256) downsum2x_kernel(const act_t* __restrict_
   }
 }
 
+__global__ void image_to_nhwc64_kernel(const float* __restrict__ img, int pixels, act_t* __restrict__ out) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 channels) per thread
+  if (i >= pixels * 8) return;
+  const int p = i >> 3, ch = i & 7;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ch == 0) {
+    v[0] = img[p];
+    v[1] = img[(size_t)pixels + p];
+    v[2] = img[(size_t)2 * pixels + p];
+  }
+  store8(out + (size_t)p * 64 + ch * 8, v);
+}
+
+__global__ void subsample_odd_kernel(const act_t* __restrict__ full, int H, int W, int C, act_t* __restrict__ y) {
+  pdl_prologue();
+  const int Ho = H / 2, Wo = W / 2, vecs = C / 8;
+  const long long n = (long long)Ho * Wo * vecs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    const long long px = i / vecs;
+    const int ox = (int)(px % Wo), oy = (int)(px / Wo);
+    const uint4 u = *reinterpret_cast<const uint4*>(full + ((size_t)(2 * oy + 1) * W + 2 * ox + 1) * C + v * 8);
+    *reinterpret_cast<uint4*>(y + (size_t)px * C + v * 8) = u;
+  }
+}
+
+__global__ void gather_codes_kernel(const float* __restrict__ cb, const int* __restrict__ idx, int C, int hw,
+                                    float* __restrict__ z) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [C, hw]
+  if (i >= C * hw) return;
+  const int k = i / hw, p = i % hw;
+  z[i] = cb[(size_t)idx[p] * C + k];
+}
+
 __global__ void image_finish_kernel(const float* __restrict__ conv_out, int ld, int pixels, float* __restrict__ pre,
                                     float* __restrict__ img) {
   pdl_prologue();
@@ -893,6 +929,16 @@ void upsample2x(const act_t* x, int H, int W, int C, act_t* y, cudaStream_t st) 
 }
 void downsum2x(const act_t* gy, int H, int W, int C, act_t* gx, cudaStream_t st) {
   launch_pdl(downsum2x_kernel, dim3(grid_for((long long)H * W * C / 8, 256)), dim3(256), 0, st, gy, H, W, C, gx);
+}
+
+void image_to_nhwc64(const float* img, int pixels, act_t* out, cudaStream_t st) {
+  launch_pdl(image_to_nhwc64_kernel, dim3((pixels * 8 + 255) / 256), dim3(256), 0, st, img, pixels, out);
+}
+void subsample_odd(const act_t* full, int H, int W, int C, act_t* y, cudaStream_t st) {
+  launch_pdl(subsample_odd_kernel, dim3(grid_for((long long)(H / 2) * (W / 2) * C / 8, 256)), dim3(256), 0, st, full, H, W, C, y);
+}
+void gather_codes(const float* cb, const int* idx, int C, int hw, float* z, cudaStream_t st) {
+  launch_pdl(gather_codes_kernel, dim3((C * hw + 255) / 256), dim3(256), 0, st, cb, idx, C, hw, z);
 }
 
 void image_finish(const float* conv_out, int ld, int pixels, float* pre, float* img, cudaStream_t st) {

@@ -178,10 +178,15 @@ inline void sample_affine_hw(CutRng& r, int h, int w, double lo, double hi, doub
 }
 
 // out: [cutn, 9] row-major dst<-src homographies; zoom group first (global index < int(0.6 * cutn), pixray.py:407)
-inline void sample_cutout_transforms(uint64_t seed, int iter, int cutn, int cut_size, float* out, double aspect = 1.0) {
+inline void sample_cutout_transforms(uint64_t seed, int iter, int cutn, int cut_size, float* out, double aspect = 1.0,
+                                     int src_h = 0, int src_w = 0) {
   const int cutn_zoom = (int)(0.6 * cutn);
   int sh, sw;
   source_size(cut_size, aspect, sh, sw);
+  if (src_h > 0 && src_w > 0) {
+    sh = src_h;
+    sw = src_w;
+  }
   for (int n = 0; n < cutn; ++n) {
     CutRng r{seed, (uint32_t)iter, (uint64_t)n * 64};
     double A[9], B[9], H[9];

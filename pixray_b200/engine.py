@@ -68,6 +68,9 @@ class B200Engine:
         cfg.fft_decay, cfg.fft_colors, cfg.fft_contrast = fft_decay, fft_colors, fft_contrast  # 0 -> 1.5 / 1.5 / 0.9
         cfg.cut_aspect = float(cut_aspect)  # global_aspect_width (pixray.py:1931); 1 = square canvas
         self.cut_aspect = float(cut_aspect)
+        if self.cut_aspect != 1.0:  # the stretched source size in Python double arithmetic, like the reference computes it
+            from .cutouts import source_size
+            cfg.cut_src_h, cfg.cut_src_w = source_size(cut_size, self.cut_aspect)
         self.cfg = cfg
         self.device = torch.device("cuda", device)
         self.cutn, self.cut_size, self.world, self.rank = cutn, cut_size, world, rank
@@ -312,6 +315,15 @@ class B200Engine:
         self.sync()
         return out
 
+    def vqgan_encode(self, img):
+        """z = model.encode(img)[0] (vqgan.py:174-185): img [1, 3, H, W] in [-1, 1] -> z [1, C, h, w] (codebook rows)."""
+        img = img.to(self.device, torch.float32).reshape(1, 3, *self.image_hw).contiguous()
+        out = self._new(*self.z_shape)
+        torch.cuda.current_stream().synchronize()
+        self._check(self.lib.pxr_vqgan_encode(self.h, self._p(img), self._p(out)), "pxr_vqgan_encode")
+        self.sync()
+        return out
+
     def make_cutouts(self, img=None, *, transforms=None, zoom_padding=PAD_REFLECTION, fill=0.0, noise_facs=None,
                      noise=None, it=0, use_engine_rng=False, color_jitter=None):
         if img is not None:
@@ -357,6 +369,22 @@ class B200Engine:
 
     def reset_optimizer(self):
         self._check(self.lib.pxr_reset_optimizer(self.h), "pxr_reset_optimizer")
+
+    def save_state(self):
+        """bytes: z, Adam m / v / step and the drop bookkeeping (pxr_save_state)."""
+        n = C.c_int64()
+        self.lib.pxr_state_size(self.h, C.byref(n))
+        buf = (C.c_ubyte * n.value)()
+        self._check(self.lib.pxr_save_state(self.h, buf), "pxr_save_state")
+        return bytes(buf)
+
+    def load_state(self, blob):
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.pxr_load_state(self.h, buf), "pxr_load_state")
+
+    def read_z(self):
+        """The engine's current latent (a copy)."""
+        return self.debug_read("z", self.z_shape)
 
     def set_z_grad(self, g):
         """The gradient the next step() applies (the plugin loop accumulates z.grad over several passes itself)."""

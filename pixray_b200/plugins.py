@@ -31,6 +31,13 @@ class DrawingInterface:
     def load_model(self, settings, device):
         pass
 
+    @torch.no_grad()
+    def to_image(self):
+        """TF.to_pil_image(self.synth(None)[0].cpu()) (vqgan.py:197-200 and the other drawers): float -> mul(255).byte()."""
+        from PIL import Image
+        out = self.synth(None)
+        return Image.fromarray(out[0].detach().cpu().mul(255).byte().permute(1, 2, 0).numpy(), mode="RGB")
+
 
 class Session:
     """The shared engine + the per-iteration state the reference keeps in globals (cur_iteration,
@@ -81,8 +88,18 @@ class VqganDrawer(DrawingInterface):
         return self.session.engine.cfg.n_levels
 
     def init_from_tensor(self, init_tensor):
-        raise NotImplementedError("the VQGAN encoder is init-time only and out of the hot-path scope (SURVEY.md 8f-3); "
-                                  "use set_z() with a latent")
+        """self.z, *_ = self.model.encode(init_tensor) (vqgan.py:174-176): taming Encoder + quant_conv + nearest code on the
+        engine (pxr_vqgan_encode)."""
+        self.z = self.get_z_from_tensor(init_tensor).clone()
+        return self.z
+
+    def reapply_from_tensor(self, new_tensor):
+        new_z = self.get_z_from_tensor(new_tensor)
+        with torch.no_grad():
+            self.z.copy_(new_z)
+
+    def get_z_from_tensor(self, ref_tensor):
+        return self.session.engine.vqgan_encode(ref_tensor)
 
     def synth(self, cur_iteration):
         return self.session.engine.synth(self.z)

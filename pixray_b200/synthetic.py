@@ -43,8 +43,9 @@ def clip_state_dict(arch, seed=0):
     return sd
 
 
-def vqgan_state_dict(v, seed=0):
-    """taming VQModel tensors pixray uses: quantize.embedding, post_quant_conv, decoder.* (vqgan.py:122-142)."""
+def vqgan_state_dict(v, seed=0, with_encoder=False):
+    """taming VQModel tensors pixray uses: quantize.embedding, post_quant_conv, decoder.* (vqgan.py:122-142) and, with
+    with_encoder, encoder.* + quant_conv (model.encode: VqganDrawer.init_from_tensor, vqgan.py:174-185)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -91,6 +92,27 @@ def vqgan_state_dict(v, seed=0):
             curr *= 2
     norm("decoder.norm_out", block_in)
     conv("decoder.conv_out", block_in, 3, 3)
+    if with_encoder:  # a separate generator: the decoder tensors above do not depend on this flag
+        g = torch.Generator().manual_seed(seed + 7919)
+        conv("encoder.conv_in", 3, ch, 3)
+        curr, block_in = v["resolution"], ch
+        in_mult = (1,) + tuple(mult)
+        for lv in range(L):
+            block_in, block_out = ch * in_mult[lv], ch * mult[lv]
+            for ib in range(nrb):
+                res(f"encoder.down.{lv}.block.{ib}", block_in, block_out)
+                block_in = block_out
+                if curr == v["attn_resolution"]:
+                    attn(f"encoder.down.{lv}.attn.{ib}", block_in)
+            if lv != L - 1:
+                conv(f"encoder.down.{lv}.downsample.conv", block_in, block_in, 3)
+                curr //= 2
+        res("encoder.mid.block_1", block_in, block_in)
+        attn("encoder.mid.attn_1", block_in)
+        res("encoder.mid.block_2", block_in, block_in)
+        norm("encoder.norm_out", block_in)
+        conv("encoder.conv_out", block_in, zc, 3)
+        conv("quant_conv", zc, zc, 1)
     return sd
 
 

@@ -72,3 +72,73 @@ def vdiff_schedule(iterations, vdiff_skip=0.0):
     steps = np.where(big_t < cosine_crossover, big_t, ddpm_part)
     return (steps.astype(np.float32), np.cos(steps * np.pi / 2).astype(np.float32),
             np.sin(steps * np.pi / 2).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ init images (host, init time)
+def _perlin_2d(rng, shape, res):
+    """perlin_numpy.generate_perlin_noise_2d [UPSTREAM pvigier/perlin-numpy, un-vendored; requirements.txt]: gradient noise
+    on a res[0] x res[1] lattice, quintic interpolant, scaled by sqrt(2)."""
+    import numpy as np
+    delta = (res[0] / shape[0], res[1] / shape[1])
+    d = (shape[0] // res[0], shape[1] // res[1])
+    grid = np.mgrid[0:res[0]:delta[0], 0:res[1]:delta[1]].transpose(1, 2, 0) % 1
+    angles = 2 * np.pi * rng.random((res[0] + 1, res[1] + 1))
+    gradients = np.dstack((np.cos(angles), np.sin(angles))).repeat(d[0], 0).repeat(d[1], 1)
+    g00, g10 = gradients[:-d[0], :-d[1]], gradients[d[0]:, :-d[1]]
+    g01, g11 = gradients[:-d[0], d[1]:], gradients[d[0]:, d[1]:]
+    n00 = np.sum(np.dstack((grid[:, :, 0], grid[:, :, 1])) * g00, 2)
+    n10 = np.sum(np.dstack((grid[:, :, 0] - 1, grid[:, :, 1])) * g10, 2)
+    n01 = np.sum(np.dstack((grid[:, :, 0], grid[:, :, 1] - 1)) * g01, 2)
+    n11 = np.sum(np.dstack((grid[:, :, 0] - 1, grid[:, :, 1] - 1)) * g11, 2)
+    t = grid * grid * grid * (grid * (grid * 6 - 15) + 10)
+    n0 = n00 * (1 - t[:, :, 0]) + t[:, :, 0] * n10
+    n1 = n01 * (1 - t[:, :, 0]) + t[:, :, 0] * n11
+    return np.sqrt(2) * ((1 - t[:, :, 1]) * n0 + t[:, :, 1] * n1)
+
+
+def fractal_noise_2d(rng, shape, res, octaves):
+    """perlin_numpy.generate_fractal_noise_2d (persistence 0.5, lacunarity 2)."""
+    import numpy as np
+    noise, frequency, amplitude = np.zeros(shape), 1, 1.0
+    for _ in range(octaves):
+        noise += amplitude * _perlin_2d(rng, shape, (frequency * res[0], frequency * res[1]))
+        frequency *= 2
+        amplitude *= 0.5
+    return noise
+
+
+def random_noise_image(w, h, rng=None):
+    """pixray.py:207-224 (`init_noise='pixels'`, the reference's DEFAULT start image): three fractal-noise channels,
+    normalised, pushed through contrast_noise.  Returns uint8 [h, w, 3]."""
+    import numpy as np
+    rng = rng or np.random.default_rng()
+    if w > 1024 or h > 1024:
+        side, octp = 2048, 6
+    elif w > 512 or h > 512:
+        side, octp = 1024, 5
+    elif w > 256 or h > 256:
+        side, octp = 512, 4
+    else:
+        side, octp = 256, 3
+
+    def chan():
+        n = fractal_noise_2d(rng, (side, side), (32, 32), octp)
+        n = (n - n.min()) / (n.max() - n.min())                 # NormalizeData
+        n = 0.9998 * n + 0.0001                                 # contrast_noise
+        return 1 / (1 + np.power(n / (1 - n), -2))
+
+    stack = np.dstack((chan(), chan(), chan()))
+    return (255.999 * stack[:h, :w, :]).astype("uint8")
+
+
+def random_gradient_image(w, h, rng=None):
+    """pixray.py:239-242 (`init_noise='gradient'`).  Returns uint8 [h, w, 3]."""
+    import numpy as np
+    rng = rng or np.random.default_rng()
+    start = (0, 0, int(rng.integers(0, 255)))
+    stop = (int(rng.integers(1, 255)), int(rng.integers(2, 255)), int(rng.integers(3, 128)))
+    horizontal = (True, False, False)
+    out = np.zeros((h, w, 3), dtype=float)
+    for i, (a, b, hz) in enumerate(zip(start, stop, horizontal)):
+        out[:, :, i] = np.tile(np.linspace(a, b, w), (h, 1)) if hz else np.tile(np.linspace(a, b, h), (w, 1)).T
+    return np.uint8(out)

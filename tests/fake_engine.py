@@ -81,6 +81,10 @@ class FakeEngine:
         self._log("synth", shape=tuple(z.shape))
         return torch.full((1, 3, *self.image_hw), 0.5)
 
+    def vqgan_encode(self, img):
+        self._log("vqgan_encode", shape=tuple(img.shape), lo=float(img.min()), hi=float(img.max()))
+        return torch.zeros(self.z_shape)
+
     def make_cutouts(self, img=None, **kw):
         self._log("make_cutouts", **{k: (None if v is None else type(v).__name__) for k, v in kw.items()})
         return torch.zeros(self.cutn, 3, self.cut_size, self.cut_size)

@@ -52,9 +52,9 @@ def test_unknown_setting_and_unknown_plugins_raise():
     api.reset_settings()
 
 
-@pytest.mark.parametrize("kw", [dict(target_images="t.png"), dict(init_image="x.png"), dict(optimiser="AdamP"),
+@pytest.mark.parametrize("kw", [dict(target_images="t.png"), dict(optimiser="AdamP"),
                                 dict(perceptors="slip"), dict(filters="wallpaper"), dict(make_video=True),
-                                dict(animation_dir="anim"), dict(overlay_image="o.png"), dict(transparent=True)])
+                                dict(animation_dir="anim"), dict(transparent=True)])
 def test_options_off_the_hot_path_are_refused_not_ignored(kw):
     api.reset_settings()
     api.add_settings(prompts="x", **kw)
@@ -336,3 +336,31 @@ def test_spot_prompts_reach_the_engine(fake, tmp_path):
             api.do_init(api.apply_settings())
         finally:
             os.chdir(cwd)
+
+
+def test_default_start_is_an_encoded_noise_image_and_overlays_re_encode(fake, tmp_path):
+    """pixray.py:674-727: init_noise='pixels' (default) -> a fractal-noise image in [-1, 1] through drawer.init_from_tensor
+    (model.encode on the engine); init_image replaces it; overlays paste + re-encode every overlay_every iterations
+    (re_average_z, pixray.py:1408-1420)."""
+    from PIL import Image
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16")
+    enc = [c for c in api._state.engine.calls if c[0] == "vqgan_encode"]
+    assert len(enc) == 1 and enc[0][1]["shape"] == (1, 3, 64, 64) and -1.0 <= enc[0][1]["lo"] < -0.5 and 0.5 < enc[0][1]["hi"] <= 1.0
+    api.reset_settings()
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16", init_noise="none")
+    assert not [c for c in api._state.engine.calls if c[0] == "vqgan_encode"]      # legacy start: random codebook rows
+    init = tmp_path / "init.png"
+    Image.fromarray(np.full((40, 50, 3), 200, np.uint8)).save(init)
+    ov = tmp_path / "ov.png"
+    Image.fromarray(np.dstack([np.zeros((64, 64, 3), np.uint8), np.full((64, 64), 255, np.uint8)]), mode="RGBA").save(ov)
+    api.reset_settings()
+    args = _init(tmp_path, prompts="x", clip_models="ViT-B/16", init_image=str(init), overlay_image=str(ov), overlay_every=3,
+                 overlay_alpha=128, iterations=7)
+    enc = [c for c in api._state.engine.calls if c[0] == "vqgan_encode"]
+    assert len(enc) == 1 and abs(enc[0][1]["lo"] - (200 / 255 * 2 - 1)) < 1e-6 and enc[0][1]["lo"] == enc[0][1]["hi"]
+    assert api.do_run(args) is True
+    names = api._state.engine.names()
+    # iterations 0, 3 and 6 render (synth), paste the overlay and re-encode before their step
+    assert names.count("vqgan_encode") == 1 + 3
+    first = names.index("iterate")
+    assert names[first - 2:first] == ["synth", "vqgan_encode"]
