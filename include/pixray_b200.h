@@ -170,7 +170,19 @@ enum { PXR_LOSS_SYMMETRY = 0, PXR_LOSS_SATURATION = 1, PXR_LOSS_PALETTE = 2, PXR
        PXR_LOSS_GAUSSIAN = 5, PXR_LOSS_AESTHETIC = 6 };
 int pxr_add_aux_loss(pxr_handle h, int kind, float weight, const float* params, int n_params);
 int pxr_clear_aux_losses(pxr_handle h);
-int pxr_num_losses(pxr_handle h, int* out); /* prompts of every perceptor + auxiliary losses */
+int pxr_num_losses(pxr_handle h, int* out); /* filters + prompts of every perceptor + auxiliary losses */
+
+/* Filters (args.filters "name:weight,..."; FilterInterface.forward(img) -> (img, loss), pixray.py:651-668, applied to the
+ * drawer's output before MakeCutouts in do_synth_and_filter, pixray.py:1203-1222).  Inside pxr_iterate only.  params:
+ *   TILER     {}                                               filters/tiler.py: torch.roll by random (h, w) shifts
+ *   WALLPAPER {type (0 none, 1 shift, 2 horizontal, 3 vertical), wallpaper_edge_match}   filters/wallpaper.py
+ *   LOOKUP    {lookup_beta, r0,g0,b0, ...} palette in [0,1]     filters/colorlookup.py (nearest colour, straight-through)
+ * Each filter owns one entry at the FRONT of the loss vector (its weighted loss; 0 for the loss-free ones).  The random
+ * shifts are engine-drawn per iteration (Philox by seed / iteration) or fixed through pxr_set_filter_shifts. */
+enum { PXR_FILTER_TILER = 0, PXR_FILTER_WALLPAPER = 1, PXR_FILTER_LOOKUP = 2 };
+int pxr_add_filter(pxr_handle h, int kind, float weight, const float* params, int n_params);
+int pxr_clear_filters(pxr_handle h);
+int pxr_set_filter_shifts(pxr_handle h, int filter_idx, int rand_h, int rand_w);
 int pxr_read_losses(pxr_handle h, float* out_host); /* blocking: the loss vector of the last forward / backward */
 
 /* vdiff drawer (PXR_DRAWER_VDIFF; VdiffDrawer, vdiff.py:58-190, over diffusion/models/cc12m_1.py).  z = x [1,3,H,W];

@@ -279,6 +279,62 @@ def color_jitter(batch, jitter):
     return torch.cat(out)
 
 
+# ------------------------------------------------------------------------------------------------ filters (filters/*.py)
+# FilterInterface.forward(img) -> (img, loss), applied to the drawer's output before MakeCutouts (do_synth_and_filter,
+# pixray.py:1203-1222).  The reference draws rand_w = randint(0, W) and rand_h = randint(0, H) inside forward; here they are
+# arguments so that both sides of a parity test use the same draws.
+
+
+def filter_tiler(img, rand_h, rand_w):
+    """filters/tiler.py:16-23."""
+    return torch.roll(img, shifts=(rand_h, rand_w), dims=(2, 3)), torch.zeros(())
+
+
+def filter_wallpaper(img, wallpaper_type, edge_match, rand_h, rand_w):
+    """filters/wallpaper.py:27-93."""
+    loss = torch.zeros(())
+    B, C, H, W = img.shape
+    em, em2 = edge_match, int(edge_match / 2)
+    if wallpaper_type == "shift":
+        row2 = torch.roll(img, shifts=(int(W / 2),), dims=(3,))
+        return torch.roll(torch.cat([img, row2], dim=2), shifts=(rand_h, rand_w), dims=(2, 3)), loss
+    if wallpaper_type == "horizontal":
+        if em != 0:
+            loss = F.mse_loss(img[:, :, :, :em], img[:, :, :, -em:]) / em
+            img = img[:, :, :, em2:-em2]
+        return torch.roll(img, shifts=(rand_w,), dims=(3,)), loss
+    if wallpaper_type == "vertical":
+        if em != 0:
+            loss = F.mse_loss(img[:, :, :em, :], img[:, :, -em:, :]) / em
+            img = img[:, :, em2:-em2, :]
+        return torch.roll(img, shifts=(rand_h,), dims=(2,)), loss
+    if em != 0:
+        loss1 = F.mse_loss(img[:, :, :, :em], img[:, :, :, -em:]) / em
+        img = img[:, :, :, em2:-em2]
+        loss2 = F.mse_loss(img[:, :, :em, :], img[:, :, -em:, :]) / em
+        img = img[:, :, em2:-em2, :]
+        loss = loss1 + loss2
+    return torch.roll(img, shifts=(rand_h, rand_w), dims=(2, 3)), loss
+
+
+COLORLOOKUP_DEFAULT_TABLE = [[0, 0, 0], [255, 255, 255], [63, 40, 50], [38, 43, 68], [90, 105, 136], [139, 155, 180],
+                             [25, 60, 62], [38, 92, 66], [62, 137, 72], [99, 199, 77], [254, 231, 97], [254, 174, 52],
+                             [254, 174, 52], [247, 118, 34], [184, 111, 80], [116, 63, 57]]  # colorlookup.py:10-26
+
+
+def filter_colorlookup(img, color_table=None, beta=10.0):
+    """filters/colorlookup.py:51-86 (3-channel path): nearest table colour, straight-through value, VQ-style loss."""
+    if color_table is None:
+        color_table = [[c / 255.0 for c in rgb] for rgb in COLORLOOKUP_DEFAULT_TABLE]
+    table = torch.as_tensor(color_table, dtype=torch.float32)
+    z3 = img.permute(0, 2, 3, 1).contiguous()
+    ind = torch.cdist(z3, table).argmin(dim=-1)
+    z_q = torch.index_select(table, 0, ind.flatten()).view(z3.shape)
+    loss = beta * torch.mean((z_q.detach() - z3) ** 2) + torch.mean((z_q - z3.detach()) ** 2)
+    z_q = z3 + (z_q - z3).detach()
+    return z_q.permute(0, 3, 1, 2).contiguous(), loss
+
+
 # ------------------------------------------------------------------------------------------------ perceptor
 
 
@@ -1027,7 +1083,8 @@ class AdamState:
 
 
 def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=(),
-            jitter=None, image_prompts=(), aspect=1.0, spot_mask=None, spot_prompts=None, spot_prompts_off=None):
+            jitter=None, image_prompts=(), aspect=1.0, spot_mask=None, spot_prompts=None, spot_prompts_off=None,
+            filters=()):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
@@ -1036,10 +1093,14 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
     after its text prompts (the explicit noise is replayed for their cutouts).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
+    filter_losses = []
+    for (weight, fn) in filters:  # do_synth_and_filter (pixray.py:1212-1222): fn(img) -> (img, loss); losses lead the list
+        out, fl = fn(out)
+        filter_losses.append(weight * fl)
     out.retain_grad()
     batch = make_cutouts(out, transforms, cut_size, zoom_padding, fill, noise_facs, noise, jitter=jitter, aspect=aspect)
     batch.retain_grad()
-    losses, embeds = [], []
+    losses, embeds = list(filter_losses), []
     # spot prompts (pixray.py:1262-1293): per kind ONE more make_cutouts on the cached transforms (no ColorJitter; the
     # explicit noise is replayed), encoded by every perceptor that has such prompts, scored before the regular prompts
     spot_batches = {}

@@ -28,6 +28,7 @@ import numpy as np
 import torch
 
 from . import engine as E
+from . import filters as FL
 from . import losses as L
 from . import plugins as P
 from . import synthetic as S
@@ -40,6 +41,7 @@ class_table = {"vqgan": P.VqganDrawer, "fast_pixel": P.FastPixelDrawer, "pixel":
 _DRAWER_KIND = {"vqgan": E.DRAWER_VQGAN, "fast_pixel": E.DRAWER_PIXEL, "pixel": E.DRAWER_PIXEL, "fft": E.DRAWER_FFT,
                 "vdiff": E.DRAWER_VDIFF}
 loss_class_table = L.loss_class_table
+filters_class_table = FL.filters_class_table
 
 global_pixray_settings = {}
 _engine_factory = E.B200Engine  # tests substitute a recording stand-in; the product has no other implementation
@@ -106,7 +108,7 @@ _OFF_PATH = {
     "labels": ([],), "image_labels": (None,),
     "target_images": (None, []), "animation_dir": (None,),
     "init_weight": (None, 0, 0.0), "init_weight_dist": (0, 0.0), "init_weight_cos": (0, 0.0), "init_weight_pix": (0, 0.0),
-    "perceptors": ("clip",), "optimiser": ("Adam",), "make_video": (False,), "transparent": (False,), "filters": (None,),
+    "perceptors": ("clip",), "optimiser": ("Adam",), "make_video": (False,), "transparent": (False,),
     "image_prompt_shuffle": (False,),
 }
 
@@ -169,6 +171,11 @@ def apply_settings():
         raise ValueError(f"drawer '{core.drawer}' is not on the hot-path scope; available: {sorted(class_table)}")
     vq_parser = setup_parser(first)
     class_table[core.drawer].add_settings(vq_parser)
+    if core.filters is not None:  # pixray.py:2072-2078
+        for name in _spec_names(core.filters):
+            if name not in filters_class_table:
+                raise ValueError(f"Requested filter not found, aborting: {name}")
+            filters_class_table[name].add_settings(vq_parser)
     if core.custom_loss is not None:
         for name in _spec_names(core.custom_loss):
             if name not in loss_class_table:
@@ -453,6 +460,19 @@ def do_init(args):
         imgs = [_load_image(p, sideX, sideY) for p in args.image_prompts]
         w = None if args.image_prompt_weight is None else [args.image_prompt_weight] * len(imgs)
         eng.set_image_prompts(imgs, w)  # each at its own (aspect-preserving) size
+
+    # ---- filters: "name:weight,..." (pixray.py:651-668); they run inside the fused iteration, between synth and the cutouts
+    st.filters = []
+    if args.filters is not None:
+        if kind == E.DRAWER_VDIFF:
+            raise NotImplementedError("filters on the vdiff drawer are not built")
+        for chunk in [c.strip() for c in args.filters.split(",")]:
+            filt_name, weight, _ = P.parse_prompt(chunk)
+            if filt_name not in filters_class_table:
+                raise ValueError(f"Requested filter not found, aborting: {filt_name}")
+            inst = filters_class_table[filt_name](args, device=eng.device)
+            inst.attach(st.session, args, weight)
+            st.filters.append({"filter": inst, "weight": weight})
 
     # ---- custom losses: "name:weight,name2->arg" (pixray.py:961-990)
     st.custom = []

@@ -67,6 +67,47 @@ class Engine {
   float *img = nullptr, *img_pre = nullptr, *g_img = nullptr;  // [3,H,W]
   OpList drawer_fwd, drawer_bwd;  // bwd stored in execution order
 
+  // ---- filters between synth and cutouts (do_synth_and_filter, pixray.py:1203-1222; filters/*.py), fused path only.
+  // A filter is a short chain of primitives; `cut_img` / `g_cut_img` [3, cut_h, cut_w] are what MakeCutouts and the image
+  // losses see (== img / g_img without filters; wallpaper "shift" doubles the height, edge_match trims).
+  enum { FP_ROLL = 0, FP_WSHIFT = 1, FP_CROP = 2, FP_EDGE = 3, FP_LOOKUP = 4 };
+  struct FilterPrim {
+    int kind, filter;       // primitive kind, index of the filter it belongs to (= its loss slot)
+    int Hin, Win, Hout, Wout;
+    int use_h = 0, use_w = 0;            // ROLL: which shifts apply
+    int top = 0, left = 0;               // CROP
+    int em = 0, axis = 0, accumulate = 0;  // EDGE
+    float beta = 0.f;                    // LOOKUP
+    const float* in = nullptr;           // input tensor (forward)
+    float* g_in = nullptr;               // gradient buffer of the input tensor
+    float *out = nullptr, *g_out = nullptr;
+  };
+  struct Filter {
+    int kind;               // PXR_FILTER_*
+    float weight;
+    int wp_type = 0, em = 0;
+    float beta = 10.f;
+    float* pal = nullptr;
+    int n_col = 0;
+    int H = 0, W = 0;       // input size of the filter (the shifts are drawn in [0, H) x [0, W), like the reference)
+    int sh = 0, sw = 0;     // this iteration's shifts
+    int fixed_h = -1, fixed_w = -1;  // explicit shifts for replays (pxr_set_filter_shifts)
+  };
+  std::vector<Filter> filters;
+  std::vector<FilterPrim> fprims;
+  float *cut_img = nullptr, *g_cut_img = nullptr;
+  int cut_h = 0, cut_w = 0;
+  bool filtered_valid = false;  // cut_img holds the filtered image of the current z (fused path); else use img
+  float* filter_dummy = nullptr;
+  int* lookup_best = nullptr;
+  void rebuild_filters();
+  void filters_forward(int iter);
+  void filters_backward();
+  const float* cur_cut_img() const { return filtered_valid ? cut_img : img; }
+  float* cur_g_cut_img() const { return filtered_valid ? g_cut_img : g_img; }
+  int cur_cut_h() const { return filtered_valid ? cut_h : cfg.image_h; }
+  int cur_cut_w() const { return filtered_valid ? cut_w : cfg.image_w; }
+
   // ---- cutouts
   float *pooled = nullptr, *g_pooled = nullptr, *batch = nullptr, *g_batch = nullptr;
   // non-square canvas (cfg.cut_aspect != 1): the warps sample from a stretch of the pooled image (pixray.py:468-472)
@@ -169,7 +210,7 @@ class Engine {
   float* aux_halo = nullptr;    // smoothness rows of the neighbouring ranks
   float* aux_xbuf = nullptr;    // smoothness halo exchange buffer
   int* aux_best = nullptr;      // palette argmin per pixel (bookkeeping, also a debug buffer)
-  int num_losses() const { return total_prompts + (int)aux.size(); }
+  int num_losses() const { return total_prompts + (int)aux.size(); }  // total_prompts includes the filter slots in front
   void aux_after_embed();   // aesthetic: needs de of the last perceptor (after its prompt_loss)
   void aux_on_cutouts();    // saturation / palette / smoothness: add into g_batch
   void aux_on_image();      // symmetry / edge / gaussian: add into g_img
@@ -1304,7 +1345,7 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
 void Engine::forward_cutouts() {
   if (!aux.empty())  // the cutout / embedding losses accumulate per-rank partial sums into their slots
     PXR_CUDA(cudaMemsetAsync(losses_dev + total_prompts, 0, sizeof(float) * aux.size(), st));
-  pool_forward(img, cfg.image_h, cfg.image_w, cfg.cut_size, pooled, pool_argmax, st);
+  pool_forward(cur_cut_img(), cur_cut_h(), cur_cut_w(), cfg.cut_size, pooled, pool_argmax, st);
   if (aspect != 1.0) {
     rescale_bilinear(pooled, cfg.cut_size, cfg.cut_size, src_h, src_w, cut_src, st);
     launches += 1;
@@ -1637,7 +1678,7 @@ void Engine::forward_clip(int i) {
 // Prompt rows of every perceptor: its text prompts (one row each), then cutn rows per image prompt.  Row j carries its
 // Prompt's weight / stop, the loss slot it sums into and 1 / (rows of that Prompt).
 void Engine::rebuild_prompt_rows() {
-  int off = 0;
+  int off = (int)filters.size();  // filter losses come first in the reference's result list (pixray.py:1203-1222)
   for (int i = 0; i < cfg.n_clip; ++i) {
     Clip& C = clip[i];
     // the reference's result order per perceptor: spot prompts, spot-off prompts, prompts, image prompts (pixray.py:1283-1336)
@@ -1794,7 +1835,9 @@ void Engine::aux_on_cutouts() {
 }
 
 void Engine::aux_on_image() {
-  const int H = cfg.image_h, Wd = cfg.image_w;
+  const int H = cur_cut_h(), Wd = cur_cut_w();
+  const float* img = cur_cut_img();   // `out` of do_synth_and_filter: the FILTERED image (pixray.py:1384-1393)
+  float* g_img = cur_g_cut_img();
   for (size_t k = 0; k < aux.size(); ++k) {
     AuxLoss& a = aux[k];
     float* slot = losses_dev + total_prompts + k;
@@ -1841,7 +1884,7 @@ void Engine::backward_to_image(const CutoutArgs& a, int mask_which, bool accumul
     spot_mask_apply(g_pooled, spot_mask, mask_which == 1, ncs, g_pooled, st);
     launches += 1;
   }
-  pool_backward(g_pooled, pool_argmax, cfg.image_h, cfg.image_w, cfg.cut_size, g_img, st, accumulate_img ? 1 : 0);
+  pool_backward(g_pooled, pool_argmax, cur_cut_h(), cur_cut_w(), cfg.cut_size, cur_g_cut_img(), st, accumulate_img ? 1 : 0);
   launches += 2;
 }
 
@@ -1852,7 +1895,8 @@ void Engine::backward_drawer() {
     // must see the gradient of ALL cutouts.  Every rank then runs the (replicated) drawer backward on identical bits.
     Comm& c = Comm::api();
     nccl_check(c.group_start(), "group start");
-    nccl_check(c.all_reduce(g_img, g_img, (size_t)3 * cfg.image_h * cfg.image_w, Comm::kFloat32, Comm::kSum, comm, st),
+    nccl_check(c.all_reduce(cur_g_cut_img(), cur_g_cut_img(), (size_t)3 * cur_cut_h() * cur_cut_w(), Comm::kFloat32, Comm::kSum,
+                            comm, st),
                "allreduce(d loss / d image)");
     nccl_check(c.all_reduce(losses_dev, losses_dev, 64, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(losses)");
     nccl_check(c.group_end(), "group end");
@@ -1860,6 +1904,7 @@ void Engine::backward_drawer() {
   }
   // image losses are replicated (every rank holds the same `out`): added after the exchange, values written, not summed
   if (!aux.empty()) aux_on_image();
+  if (filtered_valid) filters_backward();  // d loss / d filtered image -> d loss / d image (+ the filters' own loss gradients)
   if (cfg.drawer == PXR_DRAWER_VDIFF) vdiff_backward();
   else run(drawer_bwd);
   check_launch("backward");
@@ -1919,6 +1964,150 @@ void Engine::step(float lr) {
   adam_clip_step(z_buf, adam_m, adam_v, batches > 1 ? z_grad_acc : z_grad, 1.f, (int)z_numel, per_channel, zmin, zmax,
                  cfg.drawer == PXR_DRAWER_PIXEL, lr, cfg.beta1, cfg.beta2, cfg.adam_eps, adam_t, st);
   launches += 1;
+}
+
+// ---- filters (kernels_filters.cu).  Every filter becomes primitives over planar [3, H, W] buffers; EDGE primitives are taps
+// (loss + gradient on the tensor they look at), the others produce a new tensor.
+void Engine::rebuild_filters() {
+  fprims.clear();
+  int H = cfg.image_h, Wd = cfg.image_w;
+  const float* cur = img;
+  float* cur_g = g_img;
+  auto produce = [&](FilterPrim pr, int Ho, int Wo) {
+    pr.Hin = H;
+    pr.Win = Wd;
+    pr.Hout = Ho;
+    pr.Wout = Wo;
+    pr.in = cur;
+    pr.g_in = cur_g;
+    pr.out = dalloc<float>((size_t)3 * Ho * Wo);
+    pr.g_out = dalloc<float>((size_t)3 * Ho * Wo);
+    fprims.push_back(pr);
+    cur = pr.out;
+    cur_g = pr.g_out;
+    H = Ho;
+    Wd = Wo;
+  };
+  auto tap = [&](FilterPrim pr) {
+    pr.Hin = pr.Hout = H;
+    pr.Win = pr.Wout = Wd;
+    pr.in = cur;
+    pr.g_in = cur_g;
+    fprims.push_back(pr);
+  };
+  for (size_t f = 0; f < filters.size(); ++f) {
+    Filter& F = filters[f];
+    F.H = H;
+    F.W = Wd;
+    FilterPrim pr{};
+    pr.filter = (int)f;
+    if (F.kind == PXR_FILTER_TILER) {
+      pr.kind = FP_ROLL;
+      pr.use_h = pr.use_w = 1;
+      produce(pr, H, Wd);
+    } else if (F.kind == PXR_FILTER_LOOKUP) {
+      pr.kind = FP_LOOKUP;
+      pr.beta = F.beta;
+      produce(pr, H, Wd);
+    } else {  // wallpaper.py:27-93
+      const int em = F.em, em2 = em / 2;
+      if (F.wp_type == 1) {  // "shift"
+        pr.kind = FP_WSHIFT;
+        produce(pr, 2 * H, Wd);
+        continue;
+      }
+      const bool horiz = F.wp_type == 2 || F.wp_type == 0, vert = F.wp_type == 3 || F.wp_type == 0;
+      int n_edge = 0;
+      if (horiz && em != 0) {
+        if (em > Wd || Wd - 2 * em2 < 1 || em2 < 1) throw EngineError(-73, "wallpaper_edge_match does not fit the image width");
+        FilterPrim e = pr;
+        e.kind = FP_EDGE;
+        e.em = em;
+        e.axis = 0;
+        e.accumulate = n_edge++;
+        tap(e);
+        FilterPrim c = pr;
+        c.kind = FP_CROP;
+        c.left = em2;
+        produce(c, H, Wd - 2 * em2);
+      }
+      if (vert && em != 0) {
+        if (em > H || H - 2 * em2 < 1 || em2 < 1) throw EngineError(-73, "wallpaper_edge_match does not fit the image height");
+        FilterPrim e = pr;
+        e.kind = FP_EDGE;
+        e.em = em;
+        e.axis = 1;
+        e.accumulate = n_edge++;
+        tap(e);
+        FilterPrim c = pr;
+        c.kind = FP_CROP;
+        c.top = em2;
+        produce(c, H - 2 * em2, Wd);
+      }
+      pr.kind = FP_ROLL;
+      pr.use_h = vert ? 1 : 0;
+      pr.use_w = horiz ? 1 : 0;
+      produce(pr, H, Wd);
+    }
+  }
+  cut_img = const_cast<float*>(cur);
+  g_cut_img = cur_g;
+  cut_h = H;
+  cut_w = Wd;
+  if (!filter_dummy) filter_dummy = dalloc<float>(4);
+  if (!lookup_best) lookup_best = dalloc<int>((size_t)4 * cfg.image_h * cfg.image_w);
+  rebuild_prompt_rows();
+}
+
+void Engine::filters_forward(int iter) {
+  for (size_t f = 0; f < filters.size(); ++f) {
+    Filter& F = filters[f];  // rand_w = torch.randint(0, W), rand_h = torch.randint(0, H), drawn by every filter call
+    F.sh = F.fixed_h >= 0 ? F.fixed_h % F.H : (int)(philox_uniform(cfg.seed, (uint32_t)iter, 6u, 2 * f) * 0.999999f * F.H);
+    F.sw = F.fixed_w >= 0 ? F.fixed_w % F.W : (int)(philox_uniform(cfg.seed, (uint32_t)iter, 6u, 2 * f + 1) * 0.999999f * F.W);
+  }
+  const float value_w = cfg.rank == 0 ? 1.f : 0.f;  // the loss vector is summed over ranks: one rank reports the replicated value
+  for (FilterPrim& pr : fprims) {
+    Filter& F = filters[pr.filter];
+    float* slot = losses_dev + pr.filter;
+    switch (pr.kind) {
+      case FP_ROLL:
+        filter_roll(pr.in, pr.Hin, pr.Win, pr.use_h ? F.sh % pr.Hin : 0, pr.use_w ? F.sw % pr.Win : 0, pr.out, st);
+        break;
+      case FP_WSHIFT: filter_wallpaper_shift(pr.in, pr.Hin, pr.Win, F.sh, F.sw, pr.out, st); break;
+      case FP_CROP: filter_crop(pr.in, pr.Hin, pr.Win, pr.top, pr.left, pr.Hout, pr.Wout, pr.out, st); break;
+      case FP_EDGE:
+        filter_edge_match(pr.in, pr.Hin, pr.Win, pr.em, pr.axis, F.weight * value_w, 0.f, pr.accumulate, nullptr, slot, st);
+        break;
+      case FP_LOOKUP:
+        filter_colorlookup(pr.in, pr.Hin * pr.Win, F.pal, F.n_col, pr.beta, F.weight * value_w, pr.out, lookup_best, aux_part, slot, st);
+        launches += 1;
+        break;
+    }
+    launches += 1;
+  }
+  filtered_valid = true;
+  check_launch("filters forward");
+}
+
+void Engine::filters_backward() {
+  for (int i = (int)fprims.size() - 1; i >= 0; --i) {
+    FilterPrim& pr = fprims[i];
+    Filter& F = filters[pr.filter];
+    switch (pr.kind) {
+      case FP_ROLL:
+        filter_roll_backward(pr.g_out, pr.Hin, pr.Win, pr.use_h ? F.sh % pr.Hin : 0, pr.use_w ? F.sw % pr.Win : 0, 0, pr.g_in, st);
+        break;
+      case FP_WSHIFT: filter_wallpaper_shift_backward(pr.g_out, pr.Hin, pr.Win, F.sh, F.sw, 0, pr.g_in, st); break;
+      case FP_CROP: filter_crop_backward(pr.g_out, pr.Hin, pr.Win, pr.top, pr.left, pr.Hout, pr.Wout, pr.g_in, st); break;
+      case FP_EDGE:  // a tap: adds its loss gradient to the gradient of the tensor it looks at
+        filter_edge_match(pr.in, pr.Hin, pr.Win, pr.em, pr.axis, F.weight, S, 0, pr.g_in, filter_dummy, st);
+        break;
+      case FP_LOOKUP:
+        filter_colorlookup_backward(pr.g_out, pr.in, pr.out, pr.Hin * pr.Win, pr.beta, F.weight, S, 0, pr.g_in, st);
+        break;
+    }
+    launches += 1;
+  }
 }
 
 void Engine::write_initial_drop_state() {
@@ -2209,6 +2398,7 @@ int pxr_synth(pxr_handle h, const float* z, float* out_img) {
   PXR_TRY(h, {
     Engine* e = h->e;
     if (z) PXR_CUDA(cudaMemcpyAsync(e->z_buf, z, e->z_numel * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+    e->filtered_valid = false;  // the per-op path sees the drawer's image; filters live in the fused iteration
     e->forward_drawer();
     e->check_launch("synth");
     if (out_img)
@@ -2246,9 +2436,11 @@ int pxr_set_color_jitter(pxr_handle h, float p, float saturation, float hue) {
 int pxr_make_cutouts(pxr_handle h, const float* img, const pxr_cut_params* p, int iter, float* out_batch) {
   PXR_TRY(h, {
     Engine* e = h->e;
-    if (img)
+    if (img) {
       PXR_CUDA(cudaMemcpyAsync(e->img, img, sizeof(float) * 3 * e->cfg.image_h * e->cfg.image_w,
                                cudaMemcpyDeviceToDevice, e->st));
+      e->filtered_valid = false;
+    }
     e->prepare_cut_params(p, iter);
     e->encode_image_prompts();
     e->forward_cutouts();
@@ -2353,9 +2545,12 @@ int pxr_iterate(pxr_handle h, float* z, float lr, int iter, const pxr_cut_params
       if (b > 0) e->losses_dev = e->losses_scratch;  // later passes must not disturb the first pass's loss vector
       try {
         e->encode_image_prompts();
-        if (b == 0) e->forward_drawer();  // same z: the image of the later passes is the same image
+        if (b == 0) {
+          e->forward_drawer();  // same z: the image of the later passes is the same image
+          if (!e->filters.empty()) e->filters_forward(iter);
+        }
         if (e->any_spot(1) || e->any_spot(0)) {  // spot / spot-off prompts: their own masked cutout batches (pixray.py:1262-1293)
-          pxr::pool_forward(e->img, e->cfg.image_h, e->cfg.image_w, e->cfg.cut_size, e->pooled, e->pool_argmax, e->st);
+          pxr::pool_forward(e->cur_cut_img(), e->cur_cut_h(), e->cur_cut_w(), e->cfg.cut_size, e->pooled, e->pool_argmax, e->st);
           e->launches += 1;
           bool acc = false;
           acc |= e->spot_pass(1, acc);
@@ -2609,6 +2804,63 @@ int pxr_add_aux_loss(pxr_handle h, int kind, float weight, const float* params, 
       default: throw EngineError(-80, "pxr_add_aux_loss: unknown loss kind");
     }
     e->aux.push_back(std::move(a));
+  });
+}
+
+// Filters (args.filters = "name:weight,...", pixray.py:651-668; applied to drawer.synth's output before MakeCutouts,
+// pixray.py:1203-1222).  params (host floats) by kind:
+//   TILER     {}                                                       filters/tiler.py: torch.roll by random (h, w) shifts
+//   WALLPAPER {type (0 none, 1 shift, 2 horizontal, 3 vertical), edge_match}   filters/wallpaper.py
+//   LOOKUP    {lookup_beta, r0,g0,b0, r1,g1,b1, ...} palette in [0,1]   filters/colorlookup.py
+// Each filter owns one entry at the FRONT of the loss vector (0 for the loss-free ones), in the order added.
+int pxr_add_filter(pxr_handle h, int kind, float weight, const float* params, int n_params) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (e->num_losses() >= 64) throw EngineError(-16, "at most 64 losses (filters + prompts + auxiliary) in total");
+    Engine::Filter F{};
+    F.kind = kind;
+    F.weight = weight;
+    if (kind == PXR_FILTER_TILER) {
+    } else if (kind == PXR_FILTER_WALLPAPER) {
+      if (n_params < 2 || !params) throw EngineError(-74, "wallpaper needs {type, edge_match}");
+      F.wp_type = (int)params[0];
+      F.em = (int)params[1];
+      if (F.wp_type < 0 || F.wp_type > 3 || F.em < 0) throw EngineError(-74, "wallpaper: type in 0..3, edge_match >= 0");
+    } else if (kind == PXR_FILTER_LOOKUP) {
+      if (n_params < 4 || !params || (n_params - 1) % 3) throw EngineError(-74, "lookup needs {lookup_beta, r,g,b, ...}");
+      F.beta = params[0];
+      F.pal = e->upload(std::vector<float>(params + 1, params + n_params));
+      F.n_col = (n_params - 1) / 3;
+    } else {
+      throw EngineError(-74, "pxr_add_filter: unknown filter kind");
+    }
+    e->filters.push_back(F);
+    try {
+      e->rebuild_filters();
+    } catch (...) {
+      e->filters.pop_back();
+      e->rebuild_filters();
+      throw;
+    }
+  });
+}
+
+int pxr_clear_filters(pxr_handle h) {
+  PXR_TRY(h, {
+    h->e->filters.clear();
+    h->e->filtered_valid = false;
+    h->e->rebuild_filters();
+  });
+}
+
+// Explicit (rand_h, rand_w) of one filter for replays / parity tests; negative = engine-drawn again.
+int pxr_set_filter_shifts(pxr_handle h, int filter_idx, int rand_h, int rand_w) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (filter_idx < 0 || filter_idx >= (int)e->filters.size()) throw EngineError(-74, "pxr_set_filter_shifts: bad filter index");
+    e->filters[filter_idx].fixed_h = rand_h;
+    e->filters[filter_idx].fixed_w = rand_w;
   });
 }
 

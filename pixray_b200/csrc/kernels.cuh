@@ -242,6 +242,24 @@ void aux_aesthetic(const float* e, int n_local, int D, int cutn_global, const fl
                    float weight, float grad_scale, float* de, __half* de16, double* part, float* loss_out,
                    cudaStream_t st);
 
+// ------------------------------------------------------------------ filters (kernels_filters.cu; filters/*.py, pixray.py:1203-1222)
+// planar fp32 [3, H, W]; roll = torch.roll(x, (sh, sw), (2, 3)); *_backward: gx (=|+=) adjoint(gy)
+void filter_roll(const float* x, int H, int W, int sh, int sw, float* y, cudaStream_t st);
+void filter_roll_backward(const float* gy, int H, int W, int sh, int sw, int accumulate, float* gx, cudaStream_t st);
+// wallpaper "shift": [3,H,W] -> [3,2H,W] (second row of tiles offset by W/2), rolled by (sh, sw)
+void filter_wallpaper_shift(const float* x, int H, int W, int sh, int sw, float* y, cudaStream_t st);
+void filter_wallpaper_shift_backward(const float* gy, int H, int W, int sh, int sw, int accumulate, float* gx, cudaStream_t st);
+void filter_crop(const float* x, int H, int W, int top, int left, int Hc, int Wc, float* y, cudaStream_t st);
+void filter_crop_backward(const float* gy, int H, int W, int top, int left, int Hc, int Wc, float* gx, cudaStream_t st);
+// loss = weight * mse(first em, last em) / em along axis (0: columns, 1: rows); g (nullable) += grad_scale * dloss/dx
+void filter_edge_match(const float* x, int H, int W, int em, int axis, float weight, float grad_scale, int accumulate_loss,
+                       float* g, float* loss_out, cudaStream_t st);
+// nearest palette colour (first minimum), loss = weight * (beta + 1) * mean((z_q - z)^2); part: AUX_MAX_BLOCKS doubles
+void filter_colorlookup(const float* x, int pixels, const float* pal, int n_col, float beta, float weight, float* y,
+                        int* best_out, double* part, float* loss_out, cudaStream_t st);
+void filter_colorlookup_backward(const float* gy, const float* x, const float* y, int pixels, float beta, float weight,
+                                 float grad_scale, int accumulate, float* gx, cudaStream_t st);
+
 // ------------------------------------------------------------------ vdiff drawer (kernels_vdiff.cu; cc12m_1.py, sampling.py)
 struct VdFeatures {
   float v[144];  // [cos, sin] Fourier features of t: 128 for the mapping network, 16 timestep planes

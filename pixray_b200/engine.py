@@ -12,6 +12,7 @@ from . import _lib
 
 DRAWER_VQGAN, DRAWER_PIXEL, DRAWER_FFT, DRAWER_VDIFF = 0, 1, 2, 3
 LOSS_SYMMETRY, LOSS_SATURATION, LOSS_PALETTE, LOSS_SMOOTHNESS, LOSS_EDGE, LOSS_GAUSSIAN, LOSS_AESTHETIC = range(7)
+FILTER_TILER, FILTER_WALLPAPER, FILTER_LOOKUP = range(3)
 PAD_REFLECTION, PAD_BORDER = 0, 1
 MOD_VQGAN, MOD_CLIP0, MOD_CLIP1 = 0, 1, 2
 
@@ -205,6 +206,23 @@ class B200Engine:
         rc = self.lib.pxr_add_aux_loss(self.h, int(kind), C.c_float(float(weight)), a.ctypes.data_as(C.c_void_p), int(a.size))
         self._check(rc, "pxr_add_aux_loss")
         return self.num_losses() - 1
+
+    def add_filter(self, kind, weight, params):
+        """One more filter between synth and the cutouts (pxr_add_filter; filters/*.py).  Its loss takes the next entry at the
+        FRONT of the loss vector.  Returns the filter's index."""
+        a = np.ascontiguousarray(np.asarray(params, dtype=np.float32).reshape(-1))
+        rc = self.lib.pxr_add_filter(self.h, int(kind), C.c_float(float(weight)), a.ctypes.data_as(C.c_void_p), int(a.size))
+        self._check(rc, "pxr_add_filter")
+        self._n_filters = getattr(self, "_n_filters", 0) + 1
+        return self._n_filters - 1
+
+    def clear_filters(self):
+        self._check(self.lib.pxr_clear_filters(self.h), "pxr_clear_filters")
+        self._n_filters = 0
+
+    def set_filter_shifts(self, filter_idx, rand_h, rand_w):
+        """Fix one filter's (rand_h, rand_w) draws (replays / parity tests); negative values hand them back to the engine."""
+        self._check(self.lib.pxr_set_filter_shifts(self.h, int(filter_idx), int(rand_h), int(rand_w)), "pxr_set_filter_shifts")
 
     def clear_aux_losses(self):
         self._check(self.lib.pxr_clear_aux_losses(self.h), "pxr_clear_aux_losses")

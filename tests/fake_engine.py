@@ -60,6 +60,12 @@ class FakeEngine:
         self.image_prompts = (imgs, weights)
         self._log("set_image_prompts", n=0 if imgs is None else len(imgs))
 
+    def add_filter(self, kind, weight, params):
+        self.filters = getattr(self, "filters", [])
+        self.filters.append((kind, weight, list(params)))
+        self._log("add_filter", kind=kind, weight=weight)
+        return len(self.filters) - 1
+
     def add_aux_loss(self, kind, weight, params):
         self.aux.append((kind, weight, list(params)))
         self._log("add_aux_loss", kind=kind, weight=weight)
@@ -67,7 +73,7 @@ class FakeEngine:
 
     def num_losses(self):
         n_img = 0 if self.image_prompts is None or self.image_prompts[0] is None else len(self.image_prompts[0])
-        return sum(len(p[1]) + n_img for p in self.prompts.values()) + len(self.aux)
+        return sum(len(p[1]) + n_img for p in self.prompts.values()) + len(self.aux) + len(getattr(self, "filters", []))
 
     def z_bounds(self):
         c = self.z_shape[1]

@@ -53,7 +53,7 @@ def test_unknown_setting_and_unknown_plugins_raise():
 
 
 @pytest.mark.parametrize("kw", [dict(target_images="t.png"), dict(optimiser="AdamP"),
-                                dict(perceptors="slip"), dict(filters="wallpaper"), dict(make_video=True),
+                                dict(perceptors="slip"), dict(make_video=True),
                                 dict(animation_dir="anim"), dict(transparent=True)])
 def test_options_off_the_hot_path_are_refused_not_ignored(kw):
     api.reset_settings()
@@ -364,3 +364,21 @@ def test_default_start_is_an_encoded_noise_image_and_overlays_re_encode(fake, tm
     assert names.count("vqgan_encode") == 1 + 3
     first = names.index("iterate")
     assert names[first - 2:first] == ["synth", "vqgan_encode"]
+
+
+def test_filters_reach_the_engine(fake, tmp_path):
+    """args.filters = "name:weight,..." (pixray.py:651-668) with the filters' own settings (filters/wallpaper.py:17-20,
+    filters/colorlookup.py:32-35); unknown names raise like the reference."""
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16", filters="wallpaper:0.5,lookup,tiler", wallpaper_type="horizontal",
+          wallpaper_edge_match=8, lookup_beta=4.0, palette="#ff0000;#00ff00")
+    f = api._state.engine.filters
+    assert [(k, w) for k, w, _ in f] == [(E.FILTER_WALLPAPER, 0.5), (E.FILTER_LOOKUP, 1), (E.FILTER_TILER, 1)]
+    assert f[0][2] == [2, 8] and f[1][2] == [4.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0] and f[2][2] == []
+    assert api._state.loss_buf.size == 3 + 2
+    api.reset_settings()
+    api.add_settings(prompts="x", filters="sepia")
+    with pytest.raises(ValueError):
+        api.apply_settings()
+    api.reset_settings()
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16", filters="lookup")          # built-in 16-colour table
+    assert len(api._state.engine.filters[0][2]) == 1 + 16 * 3

@@ -1,0 +1,64 @@
+"""Filters between synth and the cutouts (filters/{tiler,wallpaper,colorlookup}.py through do_synth_and_filter,
+pixray.py:1203-1222) inside the fused iteration: loss vector (filter losses lead it) and z.grad against the oracle, whose
+filter restatements are pinned to the real reference classes (tests/golden/filter_vectors.npz), on identical shifts."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_path as R
+from pixray_b200 import cutouts
+from pixray_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+PAL = [[0.9, 0.1, 0.1], [0.1, 0.8, 0.2], [0.2, 0.2, 0.9], [0.95, 0.95, 0.9], [0.05, 0.05, 0.05]]
+CASES = {
+    "tiler": ([(E.FILTER_TILER, 1.0, [])], lambda rh, rw: [(1.0, lambda im: R.filter_tiler(im, rh, rw))]),
+    "wallpaper shift": ([(E.FILTER_WALLPAPER, 1.0, [1, 0])], lambda rh, rw: [(1.0, lambda im: R.filter_wallpaper(im, "shift", 0, rh, rw))]),
+    "wallpaper horizontal em=6": ([(E.FILTER_WALLPAPER, 2.0, [2, 6])],
+                                  lambda rh, rw: [(2.0, lambda im: R.filter_wallpaper(im, "horizontal", 6, rh, rw))]),
+    "wallpaper vertical em=4": ([(E.FILTER_WALLPAPER, 1.0, [3, 4])],
+                                lambda rh, rw: [(1.0, lambda im: R.filter_wallpaper(im, "vertical", 4, rh, rw))]),
+    "wallpaper both em=6": ([(E.FILTER_WALLPAPER, 0.5, [0, 6])],
+                            lambda rh, rw: [(0.5, lambda im: R.filter_wallpaper(im, None, 6, rh, rw))]),
+    "lookup": ([(E.FILTER_LOOKUP, 0.7, [3.0] + [v for c in PAL for v in c])],
+               lambda rh, rw: [(0.7, lambda im: R.filter_colorlookup(im, PAL, 3.0))]),
+    "lookup + tiler": ([(E.FILTER_LOOKUP, 1.0, [3.0] + [v for c in PAL for v in c]), (E.FILTER_TILER, 1.0, [])],
+                       lambda rh, rw: [(1.0, lambda im: R.filter_colorlookup(im, PAL, 3.0)), (1.0, lambda im: R.filter_tiler(im, rh, rw))]),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_filter_matches_the_oracle(name):
+    from test_pipeline_gpu import build, plant_extremes, report
+    specs, make_ref = CASES[name]
+    cutn, cs = 8, 224
+    vq, clip, eng, prompts, z = build(cutn=cutn, seed=9)
+    rh, rw = 11, 21
+    for i, (kind, weight, params) in enumerate(specs):
+        assert eng.add_filter(kind, weight, params) == i
+        eng.set_filter_shifts(i, rh, rw)
+    n_loss = len(specs) + len(prompts)
+    assert eng.num_losses() == n_loss
+    T = cutouts.sample_transforms(cutn, cs, 31)
+    g = torch.Generator().manual_seed(33)
+    facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
+    ref = R.iterate(lambda zz: R.vqgan_synth(vq, zz), z, [clip], [prompts], torch.from_numpy(T), cs, "reflection", 0.4, facs,
+                    noise, filters=make_ref(rh, rw))
+    zc = z.clone().cuda()
+    losses = np.zeros(n_loss, dtype=np.float32)
+    eng.iterate(zc, 0.05, 0, params=dict(transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.4, noise_facs=facs.numpy(),
+                                         noise=noise), losses_out=losses)
+    ref_l = np.array([float(l) for l in ref["losses"]], dtype=np.float32)
+    print(f"[parity] {name}: losses engine {losses} oracle {ref_l}")
+    assert np.abs(losses - ref_l).max() < 5e-3
+    e_g, m_g = report(f"z.grad through {name}", eng.debug_read("z_grad", z.shape), ref["z_grad"])
+    # the colour lookup's arg-min is one more discontinuity next to the VQ one: a 1e-3 image difference moves a few pixels to
+    # another palette colour, which changes the lookup loss gradient there (beta * (z - z_q)) -- hence the looser bound
+    assert e_g <= (8e-2 if "lookup" in name else 3e-2) * m_g
+    # engine-drawn shifts: finite, and clearing restores the plain iteration's loss count
+    eng.set_filter_shifts(0, -1, -1)
+    eng.iterate(zc, 0.05, 1, losses_out=losses)
+    assert np.isfinite(losses).all() and torch.isfinite(zc).all()
+    eng.clear_filters()
+    assert eng.num_losses() == len(prompts)

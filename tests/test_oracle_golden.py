@@ -243,3 +243,27 @@ def test_vdiff_schedule_and_renoise():
         torch.manual_seed(123)
         noise = torch.randn_like(x)
         close(R.vdiff_renoise(x, pred, v, alphas, sigmas, i, noise), torch.from_numpy(GV[f"renoise_{i}"]), 1e-6)
+
+
+def test_filters_reproduce_the_reference_classes():
+    """oracle.filter_* against filters/{tiler,wallpaper,colorlookup}.py run for real (oracle/make_golden_filters.py): output
+    image, loss and the gradient of sum(out * up) + loss, on the (rand_h, rand_w) the reference class itself drew."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "filter_vectors.npz"))
+    img = torch.from_numpy(G["img"])
+
+    def check(tag, fn):
+        rh, rw = (int(v) for v in G[tag + "_rand"])
+        x = img.clone().requires_grad_(True)
+        out, loss = fn(x, rh, rw)
+        ((out * torch.from_numpy(G[tag + "_up"])).sum() + loss).backward()
+        assert tuple(out.shape) == tuple(G[tag + "_out"].shape), tag
+        assert np.abs(out.detach().numpy() - G[tag + "_out"]).max() <= 1e-6, tag
+        assert abs(float(loss) - float(G[tag + "_loss"])) <= 1e-6 * max(1.0, abs(float(G[tag + "_loss"]))), tag
+        assert np.abs(x.grad.numpy() - G[tag + "_grad"]).max() <= 1e-6, tag
+
+    check("tiler", lambda x, rh, rw: R.filter_tiler(x, rh, rw))
+    for wt, em in (("shift", 0), ("horizontal", 0), ("horizontal", 6), ("vertical", 4), (None, 0), (None, 6)):
+        check(f"wallpaper_{wt}_{em}", lambda x, rh, rw, wt=wt, em=em: R.filter_wallpaper(x, wt, em, rh, rw))
+    pal = G["palette"].tolist()
+    check("lookup", lambda x, rh, rw: R.filter_colorlookup(x, pal, 3.0))
+    check("lookup_default", lambda x, rh, rw: R.filter_colorlookup(x, None, 10.0))
