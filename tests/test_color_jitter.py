@@ -211,13 +211,16 @@ def test_cutout_kernels_apply_color_jitter_like_the_oracle():
 @pytest.mark.gpu
 def test_iteration_gradient_with_color_jitter():
     """The backward through the stage.  rgb->hsv->rgb is continuous but its Jacobian is piecewise (arg-max / arg-min
-    channel, hue sector, the saturation clamp): where two channels are within the forward rounding of each other the two
-    sides may sit on different pieces, exactly like the reference's own fp16 CUDA path against its fp32 CPU path.  The CPU
-    oracle's z.grad moves by 2.7e-2..3.3e-2 of its maximum when its decoder output is perturbed by 3e-4..1e-3 before the
-    clamp (0.1e-2..1.2e-2 without the stage), so:
+    channel, hue sector, the saturation clamp).  The device body uses exactly-rounded fp32 operations, so it lands on the
+    same piece as the oracle whenever it sees the same colour (test_zz_host_paths: device vs host body, 0 pixels off-piece;
+    round 1's 2.5e-2 gap was __fdividef / FMA contraction flipping the sector at saturated-channel ties, see
+    profiles/r02_jitter_gap_diagnosis.log).
       (a) decisive: the ORACLE's image goes into the engine's cutouts -> the jittered batch matches to 2e-4 and d loss / d
-          image to 5e-2 of max (measured 2.5e-2; the stage's own Jacobian is exact, see the CPU test above);
-      (b) whole chain from z (engine decoder, 1e-3 image error): stated bound 8e-2 of max|z.grad|, cosine >= 0.995."""
+          image to 5e-3 of max (measured 1.6e-3, the level of the un-jittered path);
+      (b) whole chain from z: the engine's fp16 decoder image differs from the oracle's by ~1e-3 before the clamp, which
+          moves a few pixels across a piece boundary on either side.  The CPU oracle's own z.grad moves by 2.7e-2..3.3e-2 of
+          its maximum under a perturbation of that size (0.1e-2..1.2e-2 without the stage), so the bound is 4e-2 of
+          max|z.grad| (measured 2.96e-2) with cosine >= 0.995."""
     import test_pipeline_gpu as P
     cutn, cs = 8, 224
     vq, clip, eng, prompts, z = P.build(cutn=cutn, seed=3)
@@ -249,7 +252,7 @@ def test_iteration_gradient_with_color_jitter():
     g_img = eng.debug_read("g_img", (1, 3, 32, 32)) / S
     e_gi, m_gi = P.report("d/d image through ColorJitter (oracle image in)", g_img, img_r.grad)
     assert e_b <= 2e-4
-    assert e_gi <= 5e-2 * m_gi  # measured 2.5e-2 (the 1/(max-min)-scaled hue terms amplify the fp16 encoder's gradient rounding)
+    assert e_gi <= 5e-3 * m_gi  # measured 1.6e-3
 
     # (b) the engine's own chain
     eng.synth(z)
@@ -264,4 +267,4 @@ def test_iteration_gradient_with_color_jitter():
     cos = torch.nn.functional.cosine_similarity(zg.cpu().reshape(-1), ref["z_grad"].reshape(-1), dim=0).item()
     print(f"[parity] z.grad cosine {cos:.5f}")
     assert e_l < 2e-3
-    assert e_g <= 8e-2 * m_g and cos >= 0.995
+    assert e_g <= 4e-2 * m_g and cos >= 0.995

@@ -49,7 +49,7 @@ def test_image_prompt_losses_and_gradient():
             assert (ref["z_grad"] - ref_text_only["z_grad"]).abs().max() > 0.05 * ref["z_grad"].abs().max()
             assert e_g <= 3e-2 * m_g
         else:
-            assert e_g <= 8e-2 * m_g
+            assert e_g <= 4e-2 * m_g   # measured 2.85e-2; bound explained in tests/test_color_jitter.py (b)
 
     # the fused iteration takes the same path: loss vector of pxr_iterate == the stage-wise one
     out = np.zeros(eng.num_losses(), dtype=np.float32)
