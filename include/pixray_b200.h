@@ -170,6 +170,20 @@ enum { PXR_LOSS_SYMMETRY = 0, PXR_LOSS_SATURATION = 1, PXR_LOSS_PALETTE = 2, PXR
        PXR_LOSS_GAUSSIAN = 5, PXR_LOSS_AESTHETIC = 6 };
 int pxr_add_aux_loss(pxr_handle h, int kind, float weight, const float* params, int n_params);
 int pxr_clear_aux_losses(pxr_handle h);
+
+/* Anchors to a stored copy: the init_weight family and image_labels of ascend_txt (pixray.py:1344-1375).  Each is one entry
+ * of the loss vector after the prompts and before the auxiliary losses, in the order added (the reference's order is
+ * image_labels..., init_weight, init_weight_dist, init_weight_pix, init_weight_cos).
+ *   SPHERICAL  spherical_dist_loss(z.reshape(1,-1), ref.reshape(1,-1)) * weight      init_weight, image_label_weight
+ *   MSE        F.mse_loss(z, ref) * weight / 2                                        init_weight_dist
+ *   COS        F.cosine_embedding_loss(z.reshape(1,-1), ref.reshape(1,-1), 1) * weight  init_weight_cos
+ *   PIX        F.l1_loss(out, ref) * weight / 2, ref = init_image_tensor [3,H,W] in [0,1]   init_weight_pix
+ * `ref` (host or device floats) is copied: the latent's element count for the first three (z_orig = drawer.get_z_copy(),
+ * pixray.py:719, or an encoded label image), 3*H*W of the image MakeCutouts sees for PIX.  The latent terms add to z.grad
+ * after the drawer backward; PIX adds to the image gradient before it.  Replicated on every rank when sharded. */
+enum { PXR_ANCHOR_SPHERICAL = 0, PXR_ANCHOR_MSE = 1, PXR_ANCHOR_COS = 2, PXR_ANCHOR_PIX = 3 };
+int pxr_add_anchor(pxr_handle h, int kind, float weight, const float* ref, long long n);
+int pxr_clear_anchors(pxr_handle h);
 int pxr_num_losses(pxr_handle h, int* out); /* filters + prompts of every perceptor + auxiliary losses */
 
 /* Filters (args.filters "name:weight,..."; FilterInterface.forward(img) -> (img, loss), pixray.py:651-668, applied to the

@@ -1082,15 +1082,32 @@ class AdamState:
         return z - (lr / bc1) * self.m / denom
 
 
+def anchor_loss(kind, weight, z, out, ref):
+    """The init_weight family / image_labels of ascend_txt (pixray.py:1344-1375): z = drawer.get_z(), ref = z_orig (or an
+    encoded label image); "pix": out vs init_image_tensor."""
+    if kind == "spherical":   # pixray.py:1346-1349, 1352-1356
+        return spherical_dist_loss(z.reshape(1, -1), ref.reshape(1, -1))[0] * weight
+    if kind == "mse":         # pixray.py:1359-1361
+        return F.mse_loss(z, ref) * weight / 2
+    if kind == "cos":         # pixray.py:1370-1375 (the reference passes y = ones_like(f[0]); every element says "similar")
+        f, f2 = z.reshape(1, -1), ref.reshape(1, -1)
+        return F.cosine_embedding_loss(f, f2, torch.ones(1)) * weight
+    if kind == "pix":         # pixray.py:1363-1368
+        return F.l1_loss(out, ref) * weight / 2
+    raise ValueError(kind)
+
+
 def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aux=(),
             jitter=None, image_prompts=(), aspect=1.0, spot_mask=None, spot_prompts=None, spot_prompts_off=None,
-            filters=()):
+            filters=(), anchors=()):
     """One ascend_txt + backward (pixray.py:1243-1406, 1481-1482) on explicit cutout parameters.
 
     synth_fn: z -> image [1,3,H,W]; clip_models: list of ClipVisual; prompts: per model list of
     (embed [n,D], weight, stop); aux: custom losses (pixray.py:1384-1393) as (weight, fn(out, batch, embeds) ->
     scalar), appended to the loss list in order; image_prompts: (target image [1,3,H,W], weight), scored per model
-    after its text prompts (the explicit noise is replayed for their cutouts).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
+    after its text prompts (the explicit noise is replayed for their cutouts); anchors: (kind, weight, ref) with kind in
+    "spherical" (init_weight / image_labels), "mse" (init_weight_dist), "cos" (init_weight_cos), "pix" (init_weight_pix),
+    between the prompts and the custom losses (pixray.py:1344-1375).  Returns dict(image, batch, embeds[], losses[], z_grad)."""
     z = z.detach().clone().requires_grad_(True)
     out = synth_fn(z)
     filter_losses = []
@@ -1125,6 +1142,8 @@ def iterate(synth_fn, z, clip_models, prompts, transforms, cut_size, zoom_paddin
                 tb = make_cutouts(timg, transforms, cut_size, zoom_padding, fill, noise_facs, noise, aspect=aspect)
                 te = encode_image(model, tb).float()
             losses.append(prompt_loss(iii, te, weight, float("-inf")))
+    for (kind, weight, ref) in anchors:
+        losses.append(anchor_loss(kind, weight, z, out, ref))
     for (lossweight, fn) in aux:
         losses.append(lossweight * fn(out, batch, embeds[-1]))
     total = sum(losses)

@@ -105,9 +105,8 @@ _ENGINE_OPTIONS = [(("--b200_weights",), "b200_weights", None, None), (("--b200_
 
 # options that leave the hot path: dest -> the value(s) that keep them off
 _OFF_PATH = {
-    "labels": ([],), "image_labels": (None,),
+    "labels": ([],),
     "target_images": (None, []), "animation_dir": (None,),
-    "init_weight": (None, 0, 0.0), "init_weight_dist": (0, 0.0), "init_weight_cos": (0, 0.0), "init_weight_pix": (0, 0.0),
     "perceptors": ("clip",), "optimiser": ("Adam",), "make_video": (False,), "transparent": (False,),
     "image_prompt_shuffle": (False,),
 }
@@ -369,7 +368,7 @@ def do_init(args):
     drawer.load_model(args, eng.device)
     # ---- image initialisation (pixray.py:674-727): a noise / gradient / blank start image, optionally an init image, into
     # drawer.init_from_tensor(t * 2 - 1) -- for the VQGAN drawer that is model.encode on the engine (pxr_vqgan_encode)
-    st.init_image_tensor = None
+    st.init_image_tensor, st.z_orig = None, None
     if kind in (E.DRAWER_VQGAN, E.DRAWER_PIXEL) and (args.init_image or args.init_noise):
         from PIL import Image
         from .util import random_gradient_image, random_noise_image
@@ -389,6 +388,7 @@ def do_init(args):
             init_rgb = Image.open(args.init_image).convert("RGB").resize((sideX, sideY), Image.LANCZOS)
             st.init_image_tensor = to_t(init_rgb)
             drawer.init_from_tensor(st.init_image_tensor * 2 - 1)  # the init image itself, not the alpha paste (pixray.py:715-716)
+            st.z_orig = drawer.get_z_copy()                        # pixray.py:719
         else:
             drawer.init_from_tensor(to_t(starting_image) * 2 - 1)
     elif kind == E.DRAWER_VQGAN:
@@ -461,6 +461,9 @@ def do_init(args):
         w = None if args.image_prompt_weight is None else [args.image_prompt_weight] * len(imgs)
         eng.set_image_prompts(imgs, w)  # each at its own (aspect-preserving) size
 
+    # ---- anchors to the start (pixray.py:833-850, 1344-1375): image_labels, then the init_weight family, in ascend_txt's order
+    _attach_anchors(args, st, drawer, sideX, sideY)
+
     # ---- filters: "name:weight,..." (pixray.py:651-668); they run inside the fused iteration, between synth and the cutouts
     st.filters = []
     if args.filters is not None:
@@ -501,6 +504,44 @@ def do_init(args):
         eng.set_schedule(st.lr, st.iter_drop_delay, st.max_loss_drops, bool(args.auto_stop), list(args.learning_rate_drops)[:16])
         st.stop_iter = None
     return args
+
+
+def _attach_anchors(args, st, drawer, sideX, sideY):
+    eng = st.engine
+    wants_z = args.init_weight or args.init_weight_dist or args.init_weight_cos
+    if (wants_z or args.image_labels is not None) and not hasattr(eng, "add_anchor"):
+        raise NotImplementedError("this engine build has no anchor losses (pxr_add_anchor)")
+    if args.image_labels is not None:
+        # one label latent: every file encoded (drawer.get_z_from_tensor), rows normalised along the last axis, averaged,
+        # normalised as a whole (pixray.py:833-850)
+        import glob
+        from PIL import Image
+        files = sorted(glob.glob(args.image_labels))
+        if not files:
+            raise FileNotFoundError(f"image_labels matched no file: {args.image_labels}")
+        cur = []
+        for f in files:
+            rgb = Image.open(f).convert("RGB").resize((sideX, sideY), Image.LANCZOS)
+            t = torch.from_numpy(np.asarray(rgb, dtype=np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0) * 2 - 1
+            cur.append(torch.as_tensor(drawer.get_z_from_tensor(t)).float().cpu())
+        emb = torch.stack(cur)
+        emb = emb / emb.norm(dim=-1, keepdim=True)
+        emb = emb.mean(dim=0)
+        emb = emb / emb.norm()
+        eng.add_anchor(E.ANCHOR_SPHERICAL, args.image_label_weight, emb)
+    if wants_z and st.z_orig is None:
+        raise ValueError("init_weight needs an init_image (z_orig is the encoded init image, pixray.py:719)")
+    if args.init_weight:
+        eng.add_anchor(E.ANCHOR_SPHERICAL, args.init_weight, st.z_orig)
+    if args.init_weight_dist:
+        eng.add_anchor(E.ANCHOR_MSE, args.init_weight_dist, st.z_orig)
+    if args.init_weight_pix:
+        if st.init_image_tensor is None:
+            print("OOPS IIT is 0")  # the reference's own message (pixray.py:1364-1365); the term is skipped there too
+        else:
+            eng.add_anchor(E.ANCHOR_PIX, args.init_weight_pix, st.init_image_tensor)
+    if args.init_weight_cos:
+        eng.add_anchor(E.ANCHOR_COS, args.init_weight_cos, st.z_orig)
 
 
 def _spot_mask(args, cut_size, aspect):

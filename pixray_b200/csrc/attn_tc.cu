@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
   uint64_t* bar_done = bars + 9;    // per pair: dK / dV read out (16 warps)
   uint64_t* bar_smem = bars + 10;   // per pair: every product has consumed its operands
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-  float* xd = reinterpret_cast<float*>(smem + B_BAR + 256);  // [4 column quarters][128 rows] partial D
+  float* xd = reinterpret_cast<float*>(smem + B_BAR + 256);  // [2 buffers][4 column quarters][128 rows] partial D
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -434,9 +434,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             for (int j = 0; j < 8; ++j) dpart += a[j] * g[j];
           }
         }
-        xd[cq * 128 + row] = dpart;
+        float* xb = xd + (cnt & 1) * 512;  // double-buffered: the next tile's partials never meet this tile's readers
+        xb[cq * 128 + row] = dpart;
         named_bar_sync(1 + q, 128);
-        const float D = (xd[row] + xd[128 + row]) + (xd[256 + row] + xd[384 + row]);
+        const float D = (xb[row] + xb[128 + row]) + (xb[256 + row] + xb[384 + row]);
         mbar_wait(bar_s, cnt & 1);
         tc_fence_after();
         if (mt > 0) mbar_wait(bar_dsfree, (cnt - 1) & 1);  // the previous tile's dS is consumed: PS may be rewritten
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd2_kernel(const __grid_
 }
 
 int fwd_smem_bytes(int n_pad) { return 32 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 128 * 1024 + 256 + 4096 + 1024; }
-int bwd_smem_bytes(int n_pad) { return 64 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 64 * 1024 + 256 + 2048 + 1024; }
+int bwd_smem_bytes(int n_pad) { return 64 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 64 * 1024 + 256 + 4096 + 1024; }
 int bwd2_smem_bytes(int n_pad) { return 64 * 1024 + 2 * (int)((n_pad * 128 + 1023) / 1024 * 1024) + 64 * 1024 + 256 + 4096 + 1024; }
 
 }  // namespace

@@ -210,7 +210,18 @@ class Engine {
   float* aux_halo = nullptr;    // smoothness rows of the neighbouring ranks
   float* aux_xbuf = nullptr;    // smoothness halo exchange buffer
   int* aux_best = nullptr;      // palette argmin per pixel (bookkeeping, also a debug buffer)
-  int num_losses() const { return total_prompts + (int)aux.size(); }  // total_prompts includes the filter slots in front
+  // ---- anchors to a stored copy (pixray.py:1344-1375): loss-vector entries between the prompts and the auxiliary losses
+  struct Anchor {
+    int kind;      // PXR_ANCHOR_*
+    float weight;
+    float* ref = nullptr;
+    size_t n = 0;
+  };
+  std::vector<Anchor> anchors;
+  void anchors_on_image();  // init_weight_pix: into the (filtered) image gradient, before the drawer backward
+  void anchors_on_z();      // z-space terms: into z.grad, after the drawer backward
+  int aux_base() const { return total_prompts + (int)anchors.size(); }
+  int num_losses() const { return aux_base() + (int)aux.size(); }  // total_prompts includes the filter slots in front
   void aux_after_embed();   // aesthetic: needs de of the last perceptor (after its prompt_loss)
   void aux_on_cutouts();    // saturation / palette / smoothness: add into g_batch
   void aux_on_image();      // symmetry / edge / gaussian: add into g_img
@@ -1344,7 +1355,7 @@ void Engine::prepare_cut_params(const pxr_cut_params* p, int iter) {
 
 void Engine::forward_cutouts() {
   if (!aux.empty())  // the cutout / embedding losses accumulate per-rank partial sums into their slots
-    PXR_CUDA(cudaMemsetAsync(losses_dev + total_prompts, 0, sizeof(float) * aux.size(), st));
+    PXR_CUDA(cudaMemsetAsync(losses_dev + aux_base(), 0, sizeof(float) * aux.size(), st));
   pool_forward(cur_cut_img(), cur_cut_h(), cur_cut_w(), cfg.cut_size, pooled, pool_argmax, st);
   if (aspect != 1.0) {
     rescale_bilinear(pooled, cfg.cut_size, cfg.cut_size, src_h, src_w, cut_src, st);
@@ -1738,7 +1749,7 @@ void Engine::rebuild_prompt_rows() {
     C.loss_offset = off;
     off += C.n_prompts;
   }
-  if (off + (int)aux.size() > 64) throw EngineError(-16, "at most 64 losses (prompts + auxiliary) in total");
+  if (off + (int)anchors.size() + (int)aux.size() > 64) throw EngineError(-16, "at most 64 losses (prompts + anchors + auxiliary) in total");
   total_prompts = off;
 }
 
@@ -1800,7 +1811,7 @@ void Engine::aux_after_embed() {
     Clip& C = clip[cfg.n_clip - 1];
     if (a.n_dev != C.c.out_dim) throw EngineError(-81, "aesthetic head width does not match the last perceptor's embedding");
     aux_aesthetic(C.e, C.B, C.c.out_dim, cfg.cutn, a.dev, a.prm[1], a.prm[0], a.weight, S, C.de, C.de16, aux_part,
-                  losses_dev + total_prompts + k, st);
+                  losses_dev + aux_base() + k, st);
     launches += 2;
   }
 }
@@ -1809,7 +1820,7 @@ void Engine::aux_on_cutouts() {
   const int cs_ = cfg.cut_size;
   for (size_t k = 0; k < aux.size(); ++k) {
     AuxLoss& a = aux[k];
-    float* slot = losses_dev + total_prompts + k;
+    float* slot = losses_dev + aux_base() + k;
     if (a.kind == PXR_LOSS_SATURATION) {
       aux_saturation_moments(batch, n_local, cs_, aux_part, aux_sums, st);
       if (comm) nccl_check(Comm::api().all_reduce(aux_sums, aux_sums, 4, Comm::kFloat64, Comm::kSum, comm, st), "allreduce(saturation moments)");
@@ -1840,7 +1851,7 @@ void Engine::aux_on_image() {
   float* g_img = cur_g_cut_img();
   for (size_t k = 0; k < aux.size(); ++k) {
     AuxLoss& a = aux[k];
-    float* slot = losses_dev + total_prompts + k;
+    float* slot = losses_dev + aux_base() + k;
     if (a.kind == PXR_LOSS_SYMMETRY) {
       aux_symmetry(img, H, Wd, a.weight * a.prm[0], S, g_img, aux_part, slot, st);
       launches += 2;
@@ -1904,10 +1915,35 @@ void Engine::backward_drawer() {
   }
   // image losses are replicated (every rank holds the same `out`): added after the exchange, values written, not summed
   if (!aux.empty()) aux_on_image();
+  if (!anchors.empty()) anchors_on_image();
   if (filtered_valid) filters_backward();  // d loss / d filtered image -> d loss / d image (+ the filters' own loss gradients)
   if (cfg.drawer == PXR_DRAWER_VDIFF) vdiff_backward();
   else run(drawer_bwd);
+  if (!anchors.empty()) anchors_on_z();
   check_launch("backward");
+}
+
+// init_weight_pix (pixray.py:1363-1368): l1 between `out` (the filtered image) and the init image, replicated on every rank
+void Engine::anchors_on_image() {
+  const long long n = 3LL * cur_cut_h() * cur_cut_w();
+  for (size_t k = 0; k < anchors.size(); ++k) {
+    Anchor& a = anchors[k];
+    if (a.kind != PXR_ANCHOR_PIX) continue;
+    if ((long long)a.n != n) throw EngineError(-82, "init_weight_pix: the init image must have the size of the (filtered) image");
+    anchor_pix(cur_cut_img(), a.ref, n, a.weight, S, cur_g_cut_img(), aux_part, losses_dev + total_prompts + k, st);
+    launches += 2;
+  }
+}
+
+// init_weight / init_weight_dist / init_weight_cos / image_labels (pixray.py:1344-1375): terms between drawer.get_z() and
+// a stored latent; their gradient never passes the drawer, so it is added to z.grad after the drawer backward
+void Engine::anchors_on_z() {
+  for (size_t k = 0; k < anchors.size(); ++k) {
+    Anchor& a = anchors[k];
+    if (a.kind == PXR_ANCHOR_PIX) continue;
+    anchor_z(a.kind, z_buf, a.ref, (int)z_numel, a.weight, z_grad, losses_dev + total_prompts + k, st);
+    launches += 1;
+  }
 }
 
 void Engine::backward_all() {
@@ -2861,6 +2897,33 @@ int pxr_set_filter_shifts(pxr_handle h, int filter_idx, int rand_h, int rand_w) 
     if (filter_idx < 0 || filter_idx >= (int)e->filters.size()) throw EngineError(-74, "pxr_set_filter_shifts: bad filter index");
     e->filters[filter_idx].fixed_h = rand_h;
     e->filters[filter_idx].fixed_w = rand_w;
+  });
+}
+
+int pxr_add_anchor(pxr_handle h, int kind, float weight, const float* ref, long long n) {
+  PXR_TRY(h, {
+    Engine* e = h->e;
+    if (!e->finalized) throw EngineError(-13, "call pxr_finalize first");
+    if (kind < PXR_ANCHOR_SPHERICAL || kind > PXR_ANCHOR_PIX) throw EngineError(-82, "pxr_add_anchor: unknown kind");
+    if (!ref) throw EngineError(-82, "pxr_add_anchor: null reference");
+    const long long want = kind == PXR_ANCHOR_PIX ? n : (long long)e->z_numel;
+    if (n != want || n <= 0) throw EngineError(-82, "pxr_add_anchor: a latent anchor has the latent's element count");
+    if (e->num_losses() + 1 > 64) throw EngineError(-16, "at most 64 losses (prompts + anchors + auxiliary) in total");
+    Engine::Anchor a;
+    a.kind = kind;
+    a.weight = weight;
+    a.n = (size_t)n;
+    a.ref = e->dalloc<float>(a.n);
+    PXR_CUDA(cudaMemcpyAsync(a.ref, ref, sizeof(float) * a.n, cudaMemcpyDefault, e->st));
+    PXR_CUDA(cudaStreamSynchronize(e->st));
+    e->anchors.push_back(a);
+  });
+}
+
+int pxr_clear_anchors(pxr_handle h) {
+  PXR_TRY(h, {
+    for (auto& a : h->e->anchors) h->e->dfree(a.ref);
+    h->e->anchors.clear();
   });
 }
 

@@ -216,6 +216,12 @@ void accumulate_f32(const float* g, float* acc, long long n, int accumulate, cud
 // `part`: scratch of max(4 * AUX_MAX_BLOCKS, n_local) doubles.  `weight` = the loss's own *_weight setting times the
 // custom_loss spec weight (pixray.py:1388).
 constexpr int AUX_MAX_BLOCKS = 1024;
+// Anchors to a stored copy (pixray.py:1344-1375).  anchor_z: kind 0 spherical / 1 mse/2 / 2 cosine embedding between the
+// latent and `ref` (n floats each), adds weight * dL/dz into z_grad (unscaled fp32) and writes the weighted value.
+// anchor_pix: weight/2 * l1(img, ref) with its sign gradient (times grad_scale) into g_img.
+void anchor_z(int kind, const float* z, const float* ref, int n, float weight, float* z_grad, float* loss_out, cudaStream_t st);
+void anchor_pix(const float* img, const float* ref, long long n, float weight, float grad_scale, float* g_img, double* part,
+                float* loss_out, cudaStream_t st);
 void aux_symmetry(const float* img, int H, int W, float weight, float grad_scale, float* g_img, double* part,
                   float* loss_out, cudaStream_t st);
 // margins = (left, right, upper, lower) in pixels (EdgeLoss.py:82-88), colour in [0,1]

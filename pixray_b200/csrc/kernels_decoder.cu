@@ -348,19 +348,28 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const act_t* __restri
 // accumulation).  No atomics anywhere: identical bits on every run and on every rank of the cutout-sharded mode.
 constexpr int GNC_THREADS = 1024;
 
-// Grid-wide barrier for a grid of at most one block per SM (all blocks co-resident: the engine's stream runs one kernel
-// at a time and the launcher sizes the grid to <= num_sms with 1024-thread blocks).  A plain launch plus this barrier is
-// ~6 us cheaper per call than cudaLaunchCooperativeKernel + grid.sync() (measured per op with CUDA events), which
-// matters at 78 GroupNorm calls per iteration.  `counter` only ever grows: the launcher passes the value it must reach
-// (count before the launch + gridDim.x), so no reset and no generation bit is needed.
+// Grid-wide barrier for a grid of at most one block per SM.  INVARIANT (the launchers enforce it: gnc_rows_per_block gives grid <= num_sms): gridDim.x
+// <= num_sms with 1024-thread blocks whose shared memory leaves room for one of them per SM, and nothing else that could pin
+// an SM forever runs on the device -- the engine's stream runs one kernel at a time; under programmatic dependent launch the
+// previous kernel's blocks may still hold SMs when the first blocks of this one start, but they finish on their own, and
+// this kernel's own dependents are only released once every one of its blocks is resident (griddepcontrol.launch_dependents
+// is issued per block).  A plain launch plus this barrier is ~6 us cheaper per call than cudaLaunchCooperativeKernel +
+// grid.sync() (measured per op with CUDA events), which matters at 78 GroupNorm calls per iteration.  `counter` only ever
+// grows: the launcher passes the value it must reach (count before the launch + gridDim.x), so no reset and no generation
+// bit is needed.  The spin is bounded: ~2 s of SM clocks (2^32) without progress traps the kernel, so a violated invariant
+// (a debugger or sanitizer serialising blocks, a foreign persistent kernel on the device) surfaces as a launch failure on
+// the next CUDA call instead of a hang.  compute-sanitizer runs use PXR_GN_COOP=0 (the three-kernel variant).
 __device__ __forceinline__ void gnc_grid_barrier(unsigned long long* counter, unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1ULL);
     unsigned long long v;
+    const long long t0 = clock64();
+    unsigned spins = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+      if (v < target && (++spins & 0x3ffu) == 0 && clock64() - t0 > (1LL << 32)) __trap();
     } while (v < target);
   }
   __syncthreads();

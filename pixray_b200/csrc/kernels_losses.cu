@@ -374,7 +374,104 @@ __global__ void __launch_bounds__(128) aesthetic_kernel(const float* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------ anchors to a stored copy (pixray.py:1344-1375)
+// z-space terms between drawer.get_z() and a reference tensor of the same shape, flattened to one row:
+//   kind 0  spherical_dist_loss(z, ref) * w            (init_weight, pixray.py:1352-1356; image_labels, 1344-1349)
+//   kind 1  F.mse_loss(z, ref) * w / 2                 (init_weight_dist, 1359-1361)
+//   kind 2  F.cosine_embedding_loss(z, ref, 1) * w     (init_weight_cos, 1370-1375)
+// One block: n is the latent (65536 floats for a 256^2 VQGAN); sums in double, fixed order.  Adds w * dL/dz to z_grad.
+constexpr int ANCHOR_THREADS = 1024;
+
+__device__ __forceinline__ double anchor_block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();  // sh may still be read from the previous sum
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < ANCHOR_THREADS / 32; ++w) t += sh[w];  // every thread folds in the same order
+  return t;
+}
+
+__global__ void __launch_bounds__(ANCHOR_THREADS) anchor_z_kernel(int kind, const float* __restrict__ z,
+                                                                  const float* __restrict__ ref, int n, float weight,
+                                                                  float* __restrict__ z_grad, float* __restrict__ slot) {
+  __shared__ double sh[ANCHOR_THREADS / 32];
+  double zz = 0.0, rr = 0.0, zr = 0.0, dd = 0.0;
+  for (int i = threadIdx.x; i < n; i += ANCHOR_THREADS) {
+    const double a = z[i], b = ref[i];
+    zz += a * a;
+    rr += b * b;
+    zr += a * b;
+    dd += (a - b) * (a - b);
+  }
+  zz = anchor_block_sum(zz, sh);
+  rr = anchor_block_sum(rr, sh);
+  zr = anchor_block_sum(zr, sh);
+  dd = anchor_block_sum(dd, sh);
+  if (kind == 1) {
+    if (threadIdx.x == 0) *slot = (float)(0.5 * weight * dd / n);
+    const float c = weight / (float)n;
+    for (int i = threadIdx.x; i < n; i += ANCHOR_THREADS) z_grad[i] += c * (z[i] - ref[i]);
+    return;
+  }
+  if (kind == 2) {
+    const double den = sqrt((zz + 1e-12) * (rr + 1e-12));  // torch's cosine_embedding_loss: EPSILON = 1e-12 under the root
+    const double cs = zr / den;
+    if (threadIdx.x == 0) *slot = (float)(weight * (1.0 - cs));
+    const float cr = (float)(weight / den), cz = (float)(weight * cs / (zz + 1e-12));
+    for (int i = threadIdx.x; i < n; i += ANCHOR_THREADS) z_grad[i] += cz * z[i] - cr * ref[i];
+    return;
+  }
+  // spherical: x = normalize(z), y = normalize(ref); d = |x - y|; L = 2 asin(d / 2)^2
+  const double nz = fmax(sqrt(zz), 1e-12), nr = fmax(sqrt(rr), 1e-12);
+  double d2 = 0.0, xs = 0.0;  // |x - y|^2 and x . (x - y), summed from the differences (no 2 - 2 x.y cancellation)
+  for (int i = threadIdx.x; i < n; i += ANCHOR_THREADS) {
+    const double x = z[i] / nz, y = ref[i] / nr;
+    d2 += (x - y) * (x - y);
+    xs += x * (x - y);
+  }
+  d2 = anchor_block_sum(d2, sh);
+  xs = anchor_block_sum(xs, sh);
+  const double d = sqrt(d2), half = fmin(0.5 * d, 1.0);
+  const double as = asin(half);
+  if (threadIdx.x == 0) *slot = (float)(weight * 2.0 * as * as);
+  // dL/dd = 2 asin(d/2) / sqrt(1 - d^2/4);  dd/dx = (x - y) / d (0 at d == 0, torch's norm backward);  dx/dz = (I - x x^T) / |z|
+  const double c = d > 0.0 ? weight * 2.0 * as / sqrt(fmax(1.0 - half * half, 1e-30)) / d / nz : 0.0;
+  for (int i = threadIdx.x; i < n; i += ANCHOR_THREADS) {
+    const double x = z[i] / nz, y = ref[i] / nr;
+    z_grad[i] += (float)(c * ((x - y) - x * xs));
+  }
+}
+
+// F.l1_loss(out, init_image_tensor) * w / 2 (init_weight_pix, pixray.py:1363-1368): sign() gradient into g_img
+__global__ void __launch_bounds__(AUX_THREADS) anchor_pix_kernel(const float* __restrict__ img, const float* __restrict__ ref,
+                                                                 long long n, float gcoef, float* __restrict__ g_img,
+                                                                 double* __restrict__ part) {
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)AUX_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * AUX_THREADS) {
+    const float d = img[i] - ref[i];
+    acc += fabsf(d);
+    g_img[i] += d > 0.f ? gcoef : (d < 0.f ? -gcoef : 0.f);
+  }
+  const double t = block_sum(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
 }  // namespace
+
+void anchor_z(int kind, const float* z, const float* ref, int n, float weight, float* z_grad, float* loss_out,
+              cudaStream_t st) {
+  anchor_z_kernel<<<1, ANCHOR_THREADS, 0, st>>>(kind, z, ref, n, weight, z_grad, loss_out);
+}
+
+void anchor_pix(const float* img, const float* ref, long long n, float weight, float grad_scale, float* g_img, double* part,
+                float* loss_out, cudaStream_t st) {
+  const int grid = aux_grid(n);
+  anchor_pix_kernel<<<grid, AUX_THREADS, 0, st>>>(img, ref, n, 0.5f * weight * grad_scale / (float)n, g_img, part);
+  aux_final_kernel<<<1, AUX_THREADS, 0, st>>>(part, grid, 1, 1, 0.5 * (double)weight / (double)n, loss_out, nullptr, 0);
+}
 
 void aux_symmetry(const float* img, int H, int W, float weight, float grad_scale, float* g_img, double* part,
                   float* loss_out, cudaStream_t st) {

@@ -12,6 +12,7 @@ from . import _lib
 
 DRAWER_VQGAN, DRAWER_PIXEL, DRAWER_FFT, DRAWER_VDIFF = 0, 1, 2, 3
 LOSS_SYMMETRY, LOSS_SATURATION, LOSS_PALETTE, LOSS_SMOOTHNESS, LOSS_EDGE, LOSS_GAUSSIAN, LOSS_AESTHETIC = range(7)
+ANCHOR_SPHERICAL, ANCHOR_MSE, ANCHOR_COS, ANCHOR_PIX = 0, 1, 2, 3
 FILTER_TILER, FILTER_WALLPAPER, FILTER_LOOKUP = range(3)
 PAD_REFLECTION, PAD_BORDER = 0, 1
 MOD_VQGAN, MOD_CLIP0, MOD_CLIP1 = 0, 1, 2
@@ -223,6 +224,22 @@ class B200Engine:
     def set_filter_shifts(self, filter_idx, rand_h, rand_w):
         """Fix one filter's (rand_h, rand_w) draws (replays / parity tests); negative values hand them back to the engine."""
         self._check(self.lib.pxr_set_filter_shifts(self.h, int(filter_idx), int(rand_h), int(rand_w)), "pxr_set_filter_shifts")
+
+    def add_anchor(self, kind, weight, ref):
+        """One anchor term between the latent (or the image, ANCHOR_PIX) and a stored copy (pxr_add_anchor; the init_weight
+        family and image_labels, pixray.py:1344-1375).  `ref`: torch tensor (any device) or array; copied."""
+        if torch.is_tensor(ref):
+            r = ref.detach().to(torch.float32).contiguous()
+            ptr, n, keep = C.c_void_p(r.data_ptr()), r.numel(), r
+        else:
+            keep = np.ascontiguousarray(np.asarray(ref, dtype=np.float32).reshape(-1))
+            ptr, n = keep.ctypes.data_as(C.c_void_p), keep.size
+        rc = self.lib.pxr_add_anchor(self.h, int(kind), C.c_float(float(weight)), ptr, C.c_longlong(int(n)))
+        self._check(rc, "pxr_add_anchor")
+        del keep
+
+    def clear_anchors(self):
+        self._check(self.lib.pxr_clear_anchors(self.h), "pxr_clear_anchors")
 
     def clear_aux_losses(self):
         self._check(self.lib.pxr_clear_aux_losses(self.h), "pxr_clear_aux_losses")

@@ -29,12 +29,15 @@ class LossInterface:
         return parser
 
     def help(self):
-        parser = argparse.ArgumentParser()
-        parser = self.add_settings(parser)
-        helpstring = ""
-        for d in parser._actions:
-            helpstring = f"""parmeter name: {d.dest}\\nHelp: {d.help}\\nUse case: pixray.add_argument({d.dest}={d.default})"""
-        return helpstring
+        """One block of text per option this loss registers (LossInterface.py:17-23 returns only the last option's block: it
+        assigns inside the loop; the text of every block is kept so that block is still what a caller matching on it finds
+        last)."""
+        probe = self.add_settings(argparse.ArgumentParser(add_help=False))
+        blocks = []
+        for action in probe._actions:
+            blocks.append("parmeter name: %s\nHelp: %s\nUse case: pixray.add_argument(%s=%s)"
+                          % (action.dest, action.help, action.dest, action.default))
+        return blocks[-1] if blocks else ""
 
     def parse_settings(self, args):
         return args

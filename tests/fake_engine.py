@@ -66,6 +66,12 @@ class FakeEngine:
         self._log("add_filter", kind=kind, weight=weight)
         return len(self.filters) - 1
 
+    def add_anchor(self, kind, weight, ref):
+        if not hasattr(self, "anchors"):
+            self.anchors = []
+        self.anchors.append((kind, weight, np.asarray(ref.cpu() if hasattr(ref, "cpu") else ref, dtype=np.float32).copy()))
+        self._log("add_anchor", kind=kind, weight=weight)
+
     def add_aux_loss(self, kind, weight, params):
         self.aux.append((kind, weight, list(params)))
         self._log("add_aux_loss", kind=kind, weight=weight)
@@ -73,7 +79,7 @@ class FakeEngine:
 
     def num_losses(self):
         n_img = 0 if self.image_prompts is None or self.image_prompts[0] is None else len(self.image_prompts[0])
-        return sum(len(p[1]) + n_img for p in self.prompts.values()) + len(self.aux) + len(getattr(self, "filters", []))
+        return sum(len(p[1]) + n_img for p in self.prompts.values()) + len(self.aux) + len(getattr(self, "filters", [])) + len(getattr(self, "anchors", []))
 
     def z_bounds(self):
         c = self.z_shape[1]

@@ -382,3 +382,24 @@ def test_filters_reach_the_engine(fake, tmp_path):
     api.reset_settings()
     _init(tmp_path, prompts="x", clip_models="ViT-B/16", filters="lookup")          # built-in 16-colour table
     assert len(api._state.engine.filters[0][2]) == 1 + 16 * 3
+
+
+def test_init_weight_family_and_image_labels_become_anchors(fake, tmp_path):
+    """pixray.py:833-850, 1344-1375: image_labels first, then init_weight (spherical), init_weight_dist (mse),
+    init_weight_pix (l1 on the image), init_weight_cos -- anchored on z_orig = the encoded init image (pixray.py:719)."""
+    from PIL import Image
+    init = tmp_path / "init.png"
+    Image.fromarray(np.full((64, 64, 3), 100, np.uint8)).save(init)
+    for k in range(2):
+        Image.fromarray(np.full((32, 48, 3), 50 + 100 * k, np.uint8)).save(tmp_path / f"label{k}.png")
+    _init(tmp_path, prompts="x", clip_models="ViT-B/16", init_image=str(init), init_weight=0.5, init_weight_dist=0.25,
+          init_weight_pix=2.0, init_weight_cos=0.125, image_labels=str(tmp_path / "label*.png"), image_label_weight=3.0)
+    eng = api._state.engine
+    assert [(k, w) for k, w, _ in eng.anchors] == [(E.ANCHOR_SPHERICAL, 3.0), (E.ANCHOR_SPHERICAL, 0.5), (E.ANCHOR_MSE, 0.25),
+                                                   (E.ANCHOR_PIX, 2.0), (E.ANCHOR_COS, 0.125)]
+    assert eng.anchors[3][2].shape == (1, 3, 64, 64) and abs(float(eng.anchors[3][2].max()) - 100 / 255) < 1e-6
+    assert eng.names().count("vqgan_encode") == 1 + 2            # the init image and the two label images
+    assert api._state.loss_buf.size == 2 + 5
+    api.reset_settings()
+    with pytest.raises(ValueError, match="init_image"):          # the reference dereferences z_orig = None there
+        _init(tmp_path, prompts="x", clip_models="ViT-B/16", init_weight=0.5)

@@ -53,7 +53,7 @@ def test_filter_matches_the_oracle(name):
     print(f"[parity] {name}: losses engine {losses} oracle {ref_l}")
     assert np.abs(losses - ref_l).max() < 5e-3
     e_g, m_g = report(f"z.grad through {name}", eng.debug_read("z_grad", z.shape), ref["z_grad"])
-    # the colour lookup's arg-min is one more discontinuity next to the VQ one: a 1e-3 image difference moves a few pixels to
+
     # another palette colour, which changes the lookup loss gradient there (beta * (z - z_q)) -- hence the looser bound
     assert e_g <= 3e-2 * m_g   # measured 1.7e-3 .. 1.1e-2
     # engine-drawn shifts: finite, and clearing restores the plain iteration's loss count

@@ -125,5 +125,5 @@ def test_cutout_sharded_two_ranks_with_image_prompts_and_color_jitter(tmp_path):
     err = (r0["zg"] - ref["zg"]).abs().max().item()
     mag = ref["zg"].abs().max().item()
     print(f"[parity] 2-rank sharded z.grad with image prompts + jitter: max_abs_err={err:.3e} ref_max={mag:.3e}; losses {r0['losses']} vs {ref['losses']}")
-    assert err <= 8e-2 * mag
+    assert err <= 4e-2 * mag
     assert np.abs(r0["losses"] - ref["losses"].numpy()).max() < 5e-3
