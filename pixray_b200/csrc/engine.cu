@@ -35,6 +35,7 @@ class Engine {
   float S = 4096.f;  // grad scale
   bool fuse_softmax = false;  // PXR_FUSE_SOFTMAX=1: attention softmax inside the GEMM epilogue
   bool gn_coop = true;        // PXR_GN_COOP=0: three-kernel GroupNorm instead of the cooperative single-kernel one
+  bool stream16 = false;      // PXR_CLIP_STREAM=16: the ViT residual stream and its gradient in fp16 (the reference's CUDA path: CLIP in half)
   bool fused_attn = true;     // PXR_FUSED_ATTN=0: fall back to the batched-GEMM attention (attn_tc.cu covers T <= 256)
   std::map<std::string, HostWeight> weights[3];
   std::vector<void*> allocs;
@@ -140,7 +141,8 @@ class Engine {
       float *bqkv, *bo, *bfc, *bproj;
       NormW ln1, ln2;
       // saved activations
-      float *x_in, *x_mid, *stats1, *stats2;
+      void *x_in, *x_mid;  // residual stream before / between the two sub-blocks: fp32, or fp16 with stream16
+      float *stats1, *stats2;
       act_t *qkv, *P, *u;
       act_t* o = nullptr;     // fused attention: per-layer attention output (backward needs D = dO . O)
       float* lse = nullptr;   // fused attention: row log-sum-exp [B, heads, T]
@@ -149,7 +151,8 @@ class Engine {
     std::vector<Layer> layers;
     // buffers
     act_t *patches, *g_patches, *h16, *o16, *gact, *g4, *gh, *go, *gqkv, *dP, *gx16;
-    float *t, *x_out, *stats_pre, *stats_post, *e, *e_unit, *de, *gx;
+    float *t, *stats_pre, *stats_post, *e, *e_unit, *de, *gx;
+    void* x_out;  // residual stream after the last block (fp32 / fp16)
     act_t *proj16, *hcls, *gcls, *de16;
     // prompts
     float *prompts = nullptr, *pweights = nullptr, *pstops = nullptr, *losses = nullptr;
@@ -610,6 +613,7 @@ void Engine::create() {
   if (cfg.grad_scale > 0) S = cfg.grad_scale;
   if (const char* fs = getenv("PXR_FUSE_SOFTMAX")) fuse_softmax = atoi(fs) != 0;
   if (const char* fa = getenv("PXR_FUSED_ATTN")) fused_attn = atoi(fa) != 0;
+  if (const char* cs16 = getenv("PXR_CLIP_STREAM")) stream16 = atoi(cs16) == 16;
   if (const char* gc = getenv("PXR_GN_COOP")) gn_coop = atoi(gc) != 0;
   if (const char* sk = getenv("PXR_CONV_SPLITK")) conv_splitk = atoi(sk) != 0;
   if (const char* tr = getenv("PXR_TRACE")) trace = atoi(tr) != 0;
@@ -1426,7 +1430,11 @@ void Engine::build_clip(int i) {
   C.gqkv = dalloc<act_t>((size_t)M * 3 * Wd);
   const bool fuse_attn = fused_attn && attn_supported(T, d, Wd);  // attn_tc.cu: one kernel per direction, T <= 256
   C.dP = fuse_attn ? nullptr : dalloc<act_t>((size_t)B * Hh * T * ldT);
-  C.gx = dalloc<float>((size_t)M * Wd);
+  const bool s16 = stream16;
+  const size_t xbytes = (size_t)M * Wd * (s16 ? sizeof(act_t) : sizeof(float));
+  auto xalloc = [&]() -> void* { return dalloc<unsigned char>(xbytes); };
+  // fp16 stream: its gradient lives in gx16 alone; fp32 stream: fp32 master gx + the fp16 copy the dgrad GEMMs read
+  C.gx = s16 ? nullptr : dalloc<float>((size_t)M * Wd);
   C.gx16 = dalloc<act_t>((size_t)M * Wd);
   C.stats_pre = dalloc<float>((size_t)M * 2);
   C.stats_post = dalloc<float>((size_t)B * 2);
@@ -1436,8 +1444,29 @@ void Engine::build_clip(int i) {
   C.de16 = dalloc<act_t>((size_t)B * D);
   C.hcls = dalloc<act_t>((size_t)B * Wd);
   C.gcls = dalloc<act_t>((size_t)B * Wd);
-  float* x_cur = dalloc<float>((size_t)M * Wd);
-  float* x0 = x_cur;
+  void* x_cur = xalloc();
+  void* x0 = x_cur;
+  // LayerNorm on either stream type
+  auto ln_fwd = [s16, cs](const void* x, long long stride, const float* pos, int T_, const NormW& nw, int rows, int W_,
+                          act_t* y16, float* y32, float* stats) {
+    if (s16) layernorm_forward(static_cast<const act_t*>(x), stride, pos, T_, nw.gamma, nw.beta, rows, W_, 1e-5f, y16, y32, stats, cs);
+    else layernorm_forward(static_cast<const float*>(x), stride, pos, T_, nw.gamma, nw.beta, rows, W_, 1e-5f, y16, y32, stats, cs);
+  };
+  auto ln_bwd = [s16, cs](const act_t* dy, const void* x, long long stride, const float* stats, const NormW& nw, int rows,
+                          int W_, int accumulate, float* gx, act_t* gx16) {
+    if (s16) layernorm_backward(dy, static_cast<const act_t*>(x), stride, nullptr, 1, stats, nw.gamma, rows, W_, accumulate, gx, gx16, cs);
+    else layernorm_backward(dy, static_cast<const float*>(x), stride, nullptr, 1, stats, nw.gamma, rows, W_, accumulate, gx, gx16, cs);
+  };
+  // residual epilogue x_out = x_res + A B^T + bias on either stream type
+  auto residual_epilogue = [s16](GemmEpilogue& e, const void* res, void* out) {
+    if (s16) {
+      e.res_f16 = static_cast<const act_t*>(res);
+      e.out_f16 = static_cast<act_t*>(out);
+    } else {
+      e.res_f32 = static_cast<const float*>(res);
+      e.out_f32 = static_cast<float*>(out);
+    }
+  };
   C.layers.resize(L);
   const float scale = 1.f / std::sqrt((float)d);
   const bool fuse_sm = fuse_softmax && T <= 256;  // attention row fits one tile: softmax fused into the GEMM epilogue
@@ -1453,8 +1482,11 @@ void Engine::build_clip(int i) {
   }
   {
     Clip* c = &C;
-    float* xo = x0;
-    C.fwd.add(1, [=] { layernorm_forward(c->t, Wd, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, nullptr, xo, c->stats_pre, cs); }, 0.0, "layernorm_forward");
+    void* xo = x0;
+    C.fwd.add(1, [=] {
+      layernorm_forward(c->t, Wd, c->pos, T, c->ln_pre.gamma, c->ln_pre.beta, M, Wd, 1e-5f, s16 ? static_cast<act_t*>(xo) : nullptr,
+                        s16 ? nullptr : static_cast<float*>(xo), c->stats_pre, cs);
+    }, 0.0, "layernorm_forward");
   }
   for (int l = 0; l < L; ++l) {
     Clip::Layer& Ly = C.layers[l];
@@ -1470,8 +1502,8 @@ void Engine::build_clip(int i) {
     Ly.ln1 = load_norm(mod, p + ".ln_1", Wd);
     Ly.ln2 = load_norm(mod, p + ".ln_2", Wd);
     Ly.x_in = x_cur;
-    Ly.x_mid = dalloc<float>((size_t)M * Wd);
-    float* x_next = dalloc<float>((size_t)M * Wd);
+    Ly.x_mid = xalloc();
+    void* x_next = xalloc();
     Ly.stats1 = dalloc<float>((size_t)M * 2);
     Ly.stats2 = dalloc<float>((size_t)M * 2);
     Ly.qkv = dalloc<act_t>((size_t)M * 3 * Wd);
@@ -1488,7 +1520,7 @@ void Engine::build_clip(int i) {
     }
     Clip::Layer ly = Ly;
     Clip* c = &C;
-    C.fwd.add(1, [=] { layernorm_forward(ly.x_in, Wd, nullptr, T, ly.ln1.gamma, ly.ln1.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats1, cs); }, 0.0, "layernorm_forward");
+    C.fwd.add(1, [=] { ln_fwd(ly.x_in, Wd, nullptr, T, ly.ln1, M, Wd, c->h16, nullptr, ly.stats1); }, 0.0, "layernorm_forward");
     {
       GemmEpilogue e;
       e.bias = ly.bqkv;
@@ -1533,12 +1565,11 @@ void Engine::build_clip(int i) {
     {  // x_mid = x_in + O Wo^T + bo
       GemmEpilogue e;
       e.bias = ly.bo;
-      e.res_f32 = ly.x_in;
-      e.out_f32 = ly.x_mid;
+      residual_epilogue(e, ly.x_in, ly.x_mid);
       e.ldc = Wd;
       add_gemm(C.fwd, opK(fuse_attn ? ly.o : C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
     }
-    C.fwd.add(1, [=] { layernorm_forward(ly.x_mid, Wd, nullptr, T, ly.ln2.gamma, ly.ln2.beta, M, Wd, 1e-5f, c->h16, nullptr, ly.stats2, cs); }, 0.0, "layernorm_forward");
+    C.fwd.add(1, [=] { ln_fwd(ly.x_mid, Wd, nullptr, T, ly.ln2, M, Wd, c->h16, nullptr, ly.stats2); }, 0.0, "layernorm_forward");
     {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u
       GemmEpilogue e;
       e.bias = ly.bfc;
@@ -1551,8 +1582,7 @@ void Engine::build_clip(int i) {
     {  // x_next = x_mid + gact Wproj^T + bproj
       GemmEpilogue e;
       e.bias = ly.bproj;
-      e.res_f32 = ly.x_mid;
-      e.out_f32 = x_next;
+      residual_epilogue(e, ly.x_mid, x_next);
       e.ldc = Wd;
       add_gemm(C.fwd, opK(C.gact, 4 * Wd, M, 4 * Wd), opK(ly.wproj, 4 * Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
     }
@@ -1561,7 +1591,7 @@ void Engine::build_clip(int i) {
   C.x_out = x_cur;
   {  // head: ln_post on the class-token rows (row stride T*W), then e = ln @ proj as a GEMM (proj [W, D] is MN-major)
     Clip* c = &C;
-    C.fwd.add(1, [=] { layernorm_forward(c->x_out, (long long)T * Wd, nullptr, T, c->ln_post.gamma, c->ln_post.beta, B, Wd, 1e-5f, c->hcls, nullptr, c->stats_post, cs); }, 0.0, "layernorm_forward");
+    C.fwd.add(1, [=] { ln_fwd(c->x_out, (long long)T * Wd, nullptr, T, c->ln_post, B, Wd, c->hcls, nullptr, c->stats_post); }, 0.0, "layernorm_forward");
     GemmEpilogue e;
     e.out_f32 = C.e;
     e.ldc = D;
@@ -1577,9 +1607,9 @@ void Engine::build_clip(int i) {
     add_gemm(C.bwd, opK(C.de16, D, B, D), opK(C.proj16, D, Wd, D), B, Wd, D, e);
     const size_t nbytes32 = (size_t)M * Wd * sizeof(float), nbytes16 = (size_t)M * Wd * sizeof(act_t);
     C.bwd.add(1, [=] {
-      cudaMemsetAsync(c->gx, 0, nbytes32, cs);
+      if (c->gx) cudaMemsetAsync(c->gx, 0, nbytes32, cs);
       cudaMemsetAsync(c->gx16, 0, nbytes16, cs);
-      layernorm_backward(c->gcls, c->x_out, (long long)T * Wd, nullptr, T, c->stats_post, c->ln_post.gamma, B, Wd, 0, c->gx, c->gx16, cs);
+      ln_bwd(c->gcls, c->x_out, (long long)T * Wd, c->stats_post, c->ln_post, B, Wd, 0, c->gx, c->gx16);
     });
   }
   for (int l = L - 1; l >= 0; --l) {
@@ -1601,7 +1631,7 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.g4, 4 * Wd, M, 4 * Wd), opMN(ly.wfc, Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
     }
-    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_mid, Wd, nullptr, T, ly.stats2, ly.ln2.gamma, M, Wd, 1, c->gx, c->gx16, cs); }, 0.0, "layernorm_backward");
+    C.bwd.add(1, [=] { ln_bwd(c->gh, ly.x_mid, Wd, ly.stats2, ly.ln2, M, Wd, 1, c->gx, c->gx16); }, 0.0, "layernorm_backward");
     {  // go = gx Wo
       GemmEpilogue e;
       e.out_f16 = C.go;
@@ -1665,7 +1695,7 @@ void Engine::build_clip(int i) {
       e.ldc = Wd;
       add_gemm(C.bwd, opK(C.gqkv, 3 * Wd, M, 3 * Wd), opMN(ly.wqkv, Wd, Wd, 3 * Wd), M, Wd, 3 * Wd, e);
     }
-    C.bwd.add(1, [=] { layernorm_backward(c->gh, ly.x_in, Wd, nullptr, T, ly.stats1, ly.ln1.gamma, M, Wd, 1, c->gx, c->gx16, cs); }, 0.0, "layernorm_backward");
+    C.bwd.add(1, [=] { ln_bwd(c->gh, ly.x_in, Wd, ly.stats1, ly.ln1, M, Wd, 1, c->gx, c->gx16); }, 0.0, "layernorm_backward");
   }
   {  // ln_pre backward (x = t + pos), then patch-embed dgrad on token rows 1..np of every image
     Clip* c = &C;
@@ -2234,14 +2264,15 @@ void Engine::finalize() {
       reg(p + "patches", C.patches, (size_t)C.B * C.np * C.Kp * 2);
       reg(p + "g_patches", C.g_patches, (size_t)C.B * C.np * C.Kp * 2);
       reg(p + "t", C.t, mw * 4);
-      reg(p + "x0", C.layers[0].x_in, mw * 4);
-      reg(p + "x_mid0", C.layers[0].x_mid, mw * 4);
+      const size_t xb = stream16 ? 2 : 4;  // bytes per residual-stream element
+      reg(p + "x0", C.layers[0].x_in, mw * xb);
+      reg(p + "x_mid0", C.layers[0].x_mid, mw * xb);
       reg(p + "qkv0", C.layers[0].qkv, mw * 3 * 2);
       if (C.layers[0].P) reg(p + "P0", C.layers[0].P, (size_t)C.B * C.c.heads * C.T * C.ldT * 2);
-      reg(p + "x_out", C.x_out, mw * 4);
+      reg(p + "x_out", C.x_out, mw * xb);
       reg(p + "e", C.e, (size_t)C.B * C.c.out_dim * 4);
       reg(p + "de", C.de, (size_t)C.B * C.c.out_dim * 4);
-      reg(p + "gx", C.gx, mw * 4);
+      if (C.gx) reg(p + "gx", C.gx, mw * 4);
     }
   }
   for (auto& m : weights) m.clear();  // host copies no longer needed

@@ -145,9 +145,17 @@ void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* ran
 void layernorm_forward(const float* x, long long x_stride, const float* pos, int T, const float* gamma,
                        const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
                        cudaStream_t st);
+// the same on an fp16 residual stream (x fp16)
+void layernorm_forward(const act_t* x, long long x_stride, const float* pos, int T, const float* gamma,
+                       const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
+                       cudaStream_t st);
 // gx (+)= LN'(x) applied to dy (fp16, scaled); also writes gx16 = fp16(gx).  accumulate=0 overwrites gx.
 // dy is compact [rows, W]; x, gx, gx16 rows are x_stride apart
 void layernorm_backward(const act_t* dy, const float* x, long long x_stride, const float* pos, int T,
+                        const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
+                        act_t* gx16, cudaStream_t st);
+// fp16 residual stream: x fp16; with gx == nullptr the stream gradient lives in gx16 alone (accumulate reads it there)
+void layernorm_backward(const act_t* dy, const act_t* x, long long x_stride, const float* pos, int T,
                         const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
                         act_t* gx16, cudaStream_t st);
 // in-place row softmax over the first `cols` of each row of length ld (pad columns zeroed); rows total

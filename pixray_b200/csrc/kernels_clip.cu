@@ -34,9 +34,14 @@ __device__ __forceinline__ float4 ld_half4(const act_t* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// one warp per row; 16-byte vector accesses; x rows are x_stride apart (class-token rows: T * W)
-template <int NV>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long x_stride,
+// 4 consecutive elements of a residual-stream row, fp32 (16-byte load) or fp16 (8-byte load)
+__device__ __forceinline__ float4 ld_x4(const float* p, int c4) { return reinterpret_cast<const float4*>(p)[c4]; }
+__device__ __forceinline__ float4 ld_x4(const act_t* p, int c4) { return ld_half4(p + 4 * c4); }
+
+// one warp per row; vector accesses; x rows are x_stride apart (class-token rows: T * W).  XT = float: the fp32 residual
+// stream; XT = act_t: the fp16 one (what the reference's own CUDA path keeps, slip.py:176 / clip.load(..., jit=False).half()).
+template <int NV, typename XT>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const XT* __restrict__ x, long long x_stride,
                                                             const float* __restrict__ pos, int T,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int rows, int W, float eps,
@@ -47,12 +52,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   float4 v[NV];
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_stride);
+  const XT* xr = x + (size_t)row * x_stride;
   const float4* pr = pos ? reinterpret_cast<const float4*>(pos + (size_t)(row % T) * W) : nullptr;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    float4 t = xr[lane + 32 * i];
+    float4 t = ld_x4(xr, lane + 32 * i);
     if (pr) {
       float4 q = pr[lane + 32 * i];
       t.x += q.x;
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restrict__ dy, const float* __restrict__ x,
+// gx == nullptr: the gradient of the residual stream lives in gx16 alone (fp16 stream): accumulate reads it from there
+template <int NV, typename XT>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restrict__ dy, const XT* __restrict__ x,
                                                             long long x_stride, const float* __restrict__ pos, int T,
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, int rows, int W,
@@ -100,16 +106,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * x_stride);
+  const XT* xr = x + (size_t)row * x_stride;
   const float4* pr = pos ? reinterpret_cast<const float4*>(pos + (size_t)(row % T) * W) : nullptr;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4* gxr = reinterpret_cast<float4*>(gx + (size_t)row * x_stride);
+  float4* gxr = gx ? reinterpret_cast<float4*>(gx + (size_t)row * x_stride) : nullptr;
   float4 g[NV], xh[NV], prev[NV];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c4 = lane + 32 * i;
-    float4 t = xr[c4];
+    float4 t = ld_x4(xr, c4);
     if (pr) {
       float4 q = pr[c4];
       t.x += q.x;
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
       t.z += q.z;
       t.w += q.w;
     }
-    if (accumulate) prev[i] = gxr[c4];
+    if (accumulate) prev[i] = gxr ? gxr[c4] : ld_half4(gx16 + (size_t)row * x_stride + 4 * c4);
     float4 d = ld_half4(dy + (size_t)row * W + 4 * c4), gm = g4[c4];
     xh[i] = make_float4((t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd);
     g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
       d.z += prev[i].z;
       d.w += prev[i].w;
     }
-    gxr[c4] = d;
+    if (gxr) gxr[c4] = d;
     if (gx16) st_half4(gx16 + (size_t)row * x_stride + 4 * c4, d.x, d.y, d.z, d.w);
   }
 }
@@ -455,25 +461,35 @@ __global__ void cast_kernel(const float* x, act_t* y, long long n, float scale) 
 
 }  // namespace
 
-#define LN_DISPATCH(KERNEL, ...)                                                   \
+#define LN_DISPATCH(KERNEL, XT, ...)                                                   \
   switch (W / 128) {                                                              \
-    case 1: launch_pdl(KERNEL<1>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
-    case 2: launch_pdl(KERNEL<2>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
-    case 4: launch_pdl(KERNEL<4>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
-    case 6: launch_pdl(KERNEL<6>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
-    case 8: launch_pdl(KERNEL<8>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 1: launch_pdl(KERNEL<1, XT>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 2: launch_pdl(KERNEL<2, XT>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 4: launch_pdl(KERNEL<4, XT>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 6: launch_pdl(KERNEL<6, XT>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
+    case 8: launch_pdl(KERNEL<8, XT>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
     default: break;                                                               \
   }
 
 void layernorm_forward(const float* x, long long x_stride, const float* pos, int T, const float* gamma,
                        const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
                        cudaStream_t st) {
-  LN_DISPATCH(layernorm_fwd_kernel, x, x_stride, pos, T, gamma, beta, rows, W, eps, y16, y32, stats)
+  LN_DISPATCH(layernorm_fwd_kernel, float, x, x_stride, pos, T, gamma, beta, rows, W, eps, y16, y32, stats)
+}
+void layernorm_forward(const act_t* x, long long x_stride, const float* pos, int T, const float* gamma,
+                       const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
+                       cudaStream_t st) {
+  LN_DISPATCH(layernorm_fwd_kernel, act_t, x, x_stride, pos, T, gamma, beta, rows, W, eps, y16, y32, stats)
 }
 void layernorm_backward(const act_t* dy, const float* x, long long x_stride, const float* pos, int T,
                         const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
                         act_t* gx16, cudaStream_t st) {
-  LN_DISPATCH(layernorm_bwd_kernel, dy, x, x_stride, pos, T, stats, gamma, rows, W, accumulate, gx, gx16)
+  LN_DISPATCH(layernorm_bwd_kernel, float, dy, x, x_stride, pos, T, stats, gamma, rows, W, accumulate, gx, gx16)
+}
+void layernorm_backward(const act_t* dy, const act_t* x, long long x_stride, const float* pos, int T,
+                        const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
+                        act_t* gx16, cudaStream_t st) {
+  LN_DISPATCH(layernorm_bwd_kernel, act_t, dy, x, x_stride, pos, T, stats, gamma, rows, W, accumulate, gx, gx16)
 }
 void softmax_forward(act_t* s, int rows, int cols, int ld, cudaStream_t st) {
   const int nv = (ld / 8 + 31) / 32;

@@ -58,7 +58,8 @@ def test_anchor_terms_match_the_oracle(which):
     ref_l = np.array([float(l) for l in ref["losses"]], dtype=np.float32)
     print(f"[parity] anchors {which}: losses engine {losses} oracle {ref_l}")
     a0, a1 = len(prompts), len(prompts) + len(anchors)
-    assert np.abs(losses[:a0] - ref_l[:a0]).max() < 5e-3 and np.abs(losses[a1:] - ref_l[a1:]).max() < 5e-3
+    rest = np.concatenate([losses[:a0] - ref_l[:a0], losses[a1:] - ref_l[a1:]])
+    assert np.abs(rest).max() < 5e-3
     for k, got, want in zip(order, losses[a0:a1], ref_l[a0:a1]):
         # latent terms: fp32 kernel vs autograd of the same closed form; pix: l1 against the engine's fp16-decoder image
         assert abs(got - want) <= (2e-2 if k == "pix" else 2e-5) * abs(want), (k, got, want)
