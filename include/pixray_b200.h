@@ -310,6 +310,15 @@ int pxr_test_pool_bounds(int in_size, int out_size, int* starts, int* ends);
 int pxr_test_attention(const void* qkv, void* o, float* lse, const void* d_o, void* gqkv, int B, int T, int H, int W,
                        float scale, int repeat, char* err, int errlen);
 
+/* GroupNorm(32, C, eps 1e-6)(+ swish) of the VQGAN decoder (taming Normalize + nonlinearity), forward and -- when dy or
+ * ws_dy is given -- backward, on DEVICE NHWC fp16 tensors [pixels, C].  variant 0: single-kernel grid-barrier version,
+ * 1: one thread-block cluster per group; with ws / ws_dy (variant 1) the kernel is also the epilogue of a split-K
+ * convolution (fp32 partial sums [splits][pixels][C]).  scratch: 64 * (num_sms + 2) floats + 8 zeroed bytes. */
+int pxr_test_groupnorm(int variant, const void* x, const float* ws, int splits, const float* bias, const void* res,
+                       void* x_out, const float* gamma, const float* beta, int pixels, int C, int swish, void* y,
+                       float* stats, const void* dy, const float* ws_dy, int splits_dy, const void* dres, void* dx,
+                       float* scratch, int repeat);
+
 #ifdef __cplusplus
 }
 #endif

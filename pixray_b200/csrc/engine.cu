@@ -12,6 +12,7 @@
 #include "transforms.h"
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -35,7 +36,7 @@ class Engine {
   float S = 4096.f;  // grad scale
   bool fuse_softmax = false;  // PXR_FUSE_SOFTMAX=1: attention softmax inside the GEMM epilogue
   bool gn_coop = true;        // PXR_GN_COOP=0: three-kernel GroupNorm instead of the cooperative single-kernel one
-  bool stream16 = false;      // PXR_CLIP_STREAM=16: the ViT residual stream and its gradient in fp16 (the reference's CUDA path: CLIP in half)
+  bool stream16 = true;       // the ViT residual stream and its gradient in fp16, like the reference's CUDA path (clip.load gives a half model, slip.py:176); PXR_CLIP_STREAM=32 keeps them in fp32
   bool fused_attn = true;     // PXR_FUSED_ATTN=0: fall back to the batched-GEMM attention (attn_tc.cu covers T <= 256)
   std::map<std::string, HostWeight> weights[3];
   std::vector<void*> allocs;
@@ -403,6 +404,28 @@ class Engine {
   // bound by the per-SM operand feed; split-K spreads the taps over the idle SMs (fp32 partial sums to a workspace, then
   // one fixed-order reduce + bias / residual / fp16 epilogue kernel: deterministic).
   bool conv_splitk = true;  // PXR_CONV_SPLITK=0 disables
+  bool gn_group = true;     // PXR_GN_GROUP=0: never use the cluster-per-group GroupNorm (kernels_gn_group.cu)
+  bool gn_fuse_sk = true;   // PXR_GN_FUSE_SPLITK=0: keep splitk_reduce and GroupNorm as two kernels
+  // the split-K reduce most recently appended by add_conv: a GroupNorm over exactly its output, appended next to the same
+  // list, replaces that op by the fused reduce + GroupNorm kernel
+  // (one slot per op list: forward and backward lists are built interleaved)
+  struct PendingSplitK {
+    size_t op_index = 0;
+    const act_t* out = nullptr;
+    int ld_out = 0, n_out = 0;
+    long long px = 0;
+    GnSplitK sk;
+  };
+  std::map<const OpList*, PendingSplitK> pend_sk;
+  const GnSplitK* take_pending_splitk(OpList& l, const act_t* tensor, int px, int C, bool need_plain) {
+    auto it = pend_sk.find(&l);
+    if (!gn_fuse_sk || it == pend_sk.end()) return nullptr;
+    const PendingSplitK& q = it->second;
+    if (l.ops.empty() || q.op_index != l.ops.size() - 1 || q.out != tensor || q.px != px || q.n_out != C || q.ld_out != C)
+      return nullptr;
+    if (need_plain && (q.sk.bias || q.sk.res)) return nullptr;
+    return &q.sk;
+  }
   float* splitk_ws = nullptr;
   size_t splitk_ws_elems = 0;
   void add_conv(OpList& l, const act_t* in, int H, int Wd, int cin, const act_t* wt, int cout_pad, int n_out, int ks,
@@ -441,10 +464,22 @@ class Engine {
       const int ld_out = (int)e.ldc;
       const long long px = (long long)H * Wd;
       std::string label = gemm_label(kind, *plan, OP_KMAJOR, OP_KMAJOR, e) + " splitK=" + std::to_string(plan->p.k_splits);
-      l.add(2, [=] {
-        gemm_launch(*plan, s);
-        splitk_reduce(ws, plan->p.k_splits, px, n_out, n_out, bias, res, out, ld_out, s);
-      }, plan->flops, label, plan->bytes);
+      l.add(1, [=] { gemm_launch(*plan, s); }, plan->flops, label, plan->bytes);
+      // the reduce is its own op so that a GroupNorm right behind it can absorb it (add_gn / add_gn_bwd)
+      l.add(1, [=] { splitk_reduce(ws, plan->p.k_splits, px, n_out, n_out, bias, res, out, ld_out, s); }, 0.0,
+            "splitk_reduce px=" + std::to_string(px) + " N=" + std::to_string(n_out) + " splits=" + std::to_string(plan->p.k_splits));
+      PendingSplitK& q = pend_sk[&l];
+      q.op_index = l.ops.size() - 1;
+      q.out = out;
+      q.ld_out = ld_out;
+      q.px = px;
+      q.n_out = n_out;
+      q.sk.ws = ws;
+      q.sk.splits = plan->p.k_splits;
+      q.sk.ld_ws = n_out;
+      q.sk.bias = bias;
+      q.sk.res = res;
+      q.sk.out = out;
       return;
     }
     int rc = conv_plan_make(plan.get(), in, cin, 1, H, Wd, cin, wt, cout_pad, n_out, ks, e, bn, fmt, num_sms, buf,
@@ -613,9 +648,11 @@ void Engine::create() {
   if (cfg.grad_scale > 0) S = cfg.grad_scale;
   if (const char* fs = getenv("PXR_FUSE_SOFTMAX")) fuse_softmax = atoi(fs) != 0;
   if (const char* fa = getenv("PXR_FUSED_ATTN")) fused_attn = atoi(fa) != 0;
-  if (const char* cs16 = getenv("PXR_CLIP_STREAM")) stream16 = atoi(cs16) == 16;
+  if (const char* cs16 = getenv("PXR_CLIP_STREAM")) stream16 = atoi(cs16) != 32;
   if (const char* gc = getenv("PXR_GN_COOP")) gn_coop = atoi(gc) != 0;
   if (const char* sk = getenv("PXR_CONV_SPLITK")) conv_splitk = atoi(sk) != 0;
+  if (const char* gg = getenv("PXR_GN_GROUP")) gn_group = atoi(gg) != 0;
+  if (const char* gf = getenv("PXR_GN_FUSE_SPLITK")) gn_fuse_sk = atoi(gf) != 0;
   if (const char* tr = getenv("PXR_TRACE")) trace = atoi(tr) != 0;
   if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
   if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
@@ -675,7 +712,18 @@ Engine::GNSaved Engine::add_gn(OpList& l, const Act& x, const NormW& n, int swis
   cudaStream_t cs = st;
   NormW nn = n;
   const int nsm = num_sms;
-  if (gn_coop && gn_coop_supported(px, C, nsm)) {
+  if (gn_group && gn_group_supported(px, C)) {
+    const std::string shape = " px=" + std::to_string(px) + " C=" + std::to_string(C);
+    if (const GnSplitK* pk = take_pending_splitk(l, xp, px, C, false)) {
+      const GnSplitK sk = *pk;
+      l.ops.back() = [=] { gn_forward_group(nullptr, &sk, nn.gamma, nn.beta, px, C, swish, 1e-6f, stats, y, cs); };
+      l.names.back() = "splitk_reduce+gn_fwd_group" + shape + " splits=" + std::to_string(sk.splits);
+      pend_sk.erase(&l);
+    } else {
+      l.add(1, [=] { gn_forward_group(xp, nullptr, nn.gamma, nn.beta, px, C, swish, 1e-6f, stats, y, cs); }, 0.0,
+            "gn_fwd_group" + shape);
+    }
+  } else if (gn_coop && gn_coop_supported(px, C, nsm)) {
     GridBarrier* gb = &gn_bar;
     l.add(1, [=] { gn_forward_coop(xp, nn.gamma, nn.beta, px, C, swish, 1e-6f, part, stats, y, nsm, gb, cs); }, 0.0,
           "gn_fwd_coop px=" + std::to_string(px) + " C=" + std::to_string(C));
@@ -694,7 +742,18 @@ void Engine::add_gn_bwd(OpList& l, const act_t* dy, const act_t* x, const GNSave
   cudaStream_t cs = st;
   const int nsm = num_sms;
   GridBarrier* gb = &gn_bar;
-  if (gn_coop && gn_coop_supported(px, C, nsm))
+  if (gn_group && gn_group_supported(px, C)) {
+    const std::string shape = " px=" + std::to_string(px) + " C=" + std::to_string(C);
+    if (const GnSplitK* pk = take_pending_splitk(l, dy, px, C, true)) {
+      const GnSplitK sk = *pk;  // dy itself is never written: the reduced gradient lives in registers only
+      l.ops.back() = [=] { gn_backward_group(nullptr, &sk, x, s.stats, n.gamma, n.beta, px, C, swish, dres, dx, cs); };
+      l.names.back() = "splitk_reduce+gn_bwd_group" + shape + " splits=" + std::to_string(sk.splits);
+      pend_sk.erase(&l);
+    } else {
+      l.add(1, [=] { gn_backward_group(dy, nullptr, x, s.stats, n.gamma, n.beta, px, C, swish, dres, dx, cs); }, 0.0,
+            "gn_bwd_group" + shape);
+    }
+  } else if (gn_coop && gn_coop_supported(px, C, nsm))
     l.add(1, [=] { gn_backward_coop(dy, x, s.stats, n.gamma, n.beta, px, C, swish, dres, part, dx, nsm, gb, cs); }, 0.0,
           "gn_bwd_coop px=" + std::to_string(px) + " C=" + std::to_string(C));
   else
@@ -943,7 +1002,45 @@ void Engine::build_vqgan() {
   cudaStream_t cs = st;
   float* zb = z_buf = dalloc<float>(z_numel);
   z_grad = dalloc<float>(z_numel);
-  drawer_fwd.add(2, [=] { vq_nearest(zb, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq.p, cs); }, 0.0, "vq_nearest");
+  bool vq_tc = vq_tc_supported(zc, ne);
+  if (const char* e = getenv("PXR_VQ_TC")) vq_tc = vq_tc && atoi(e) != 0;
+  if (vq_tc) {
+    // distance matrix on the tensor cores, decision in exact fp32 (kernels_vq_tc.cu)
+    float amax = 0.f, cmax2 = 0.f, cmax1 = 0.f;
+    for (int j = 0; j < ne; ++j) {
+      double s2 = 0.0, s1 = 0.0;
+      for (int k = 0; k < zc; ++k) {
+        const float v = std::fabs(cb.data[(size_t)j * zc + k]);
+        amax = std::max(amax, v);
+        s2 += (double)v * v;
+        s1 += v;
+      }
+      cmax2 = std::max(cmax2, (float)std::sqrt(s2) * 1.000001f);
+      cmax1 = std::max(cmax1, (float)s1 * 1.000001f);
+    }
+    int ex = 0;
+    if (amax > 0.f) std::frexp(amax, &ex);
+    const float cb_scale = std::ldexp(1.f, -ex);  // power of two: max |c| lands in [0.5, 1)
+    std::vector<float> cbs(cb.data.size());
+    for (size_t i = 0; i < cbs.size(); ++i) cbs[i] = cb.data[i] * cb_scale;
+    act_t* cbh = upload_f16(cbs);
+    act_t* zh = dalloc<act_t>((size_t)hw * zc);
+    float* pinfo = dalloc<float>((size_t)hw * 4);
+    float* scores = dalloc<float>((size_t)hw * ne, false);
+    int* vq_stats = dalloc<int>(2);
+    drawer_fwd.add(1, [=] { vq_prep(zb, zc, hw, zh, pinfo, cs); }, 0.0, "vq_prep");
+    {
+      GemmEpilogue e;
+      e.out_f32 = scores;
+      e.ldc = ne;
+      add_gemm(drawer_fwd, opK(zh, zc, hw, zc), opK(cbh, zc, ne, zc), hw, ne, zc, e);
+    }
+    drawer_fwd.add(1, [=] { vq_select(scores, ne, zb, d_cb, d_c2, pinfo, cb_scale, cmax2, cmax1, zc, hw, ne, idx, zq.p, vq_stats, cs); },
+                   0.0, "vq_select");
+    reg("vq_stats", vq_stats, sizeof(int) * 2);  // {candidates rechecked in fp32, positions that fell back to the full search}, cumulative
+  } else {
+    drawer_fwd.add(2, [=] { vq_nearest(zb, d_cbT, d_c2, d_cb, zc, hw, ne, part_d, part_i, idx, zq.p, cs); }, 0.0, "vq_nearest");
+  }
   reg("vq_idx", idx, sizeof(int) * hw);  // argmin code per latent position (vqgan.py:62): integer bookkeeping
 
   // post_quant_conv + decoder

@@ -17,6 +17,16 @@ typedef __half act_t;
 //   part_d/part_i: scratch [hw, n_chunks]; idx: [hw]; zq: [hw, C] fp16; cb: [n_e, C] fp32
 void vq_nearest(const float* z, const float* cbT, const float* c2, const float* cb, int C, int hw, int n_e,
                 float* part_d, int* part_i, int* idx, act_t* zq, cudaStream_t st);
+// The same search with the hw x n_e dot products on the tensor cores (kernels_vq_tc.cu): vq_prep -> one gemm_tc GEMM
+// (zh [hw, C] x cbh [n_e, C]^T -> scores [hw, ld] fp32) -> vq_select, which re-evaluates in exact fp32 every code whose
+// approximate distance lies within the rounding bound of the minimum, so the index is the one vq_nearest picks.
+// pinfo: [hw][4] = {|x|^2, power-of-two scale, |x|_2, |x|_1}; cb_scale: the power of two the fp16 codebook copy carries;
+// cmax2 / cmax1: max_j |c_j|_2, |c_j|_1; stats (may be null): {candidates rechecked, positions that fell back}, cumulative.
+bool vq_tc_supported(int C, int n_e);
+void vq_prep(const float* z, int C, int hw, act_t* zh, float* pinfo, cudaStream_t st);
+void vq_select(const float* scores, int ld, const float* z, const float* cb, const float* c2, const float* pinfo,
+               float cb_scale, float cmax2, float cmax1, int C, int hw, int n_e, int* idx, act_t* zq, int* stats,
+               cudaStream_t st);
 // z_grad[C, hw] fp32 = dzq[hw, C] fp16 / grad_scale   (ReplaceGrad: gradient of z_q goes to z unchanged)
 void vq_backward(const act_t* dzq, float inv_scale, int C, int hw, float* z_grad, cudaStream_t st);
 
@@ -53,6 +63,25 @@ void gn_forward_coop(const act_t* x, const float* gamma, const float* beta, int 
 void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const float* gamma, const float* beta,
                       int pixels, int C, int swish, const act_t* dres, float* part, act_t* dx, int num_sms,
                       GridBarrier* gb, cudaStream_t st, GnOpts o = GnOpts());
+
+// GroupNorm(32, C) with one thread-block cluster per GROUP (kernels_gn_group.cu): no grid-wide barrier, for the layers
+// whose group fits the registers of <= 8 CTAs (C/32 in {8, 16, 32} channels per group, pixels * C/256 <= 16384 units).
+// `sk` (optional) makes the kernel the epilogue of a split-K convolution as well: forward sums the fp32 partials
+// [splits][pixels][ld_ws] (+ bias + res), writes the result to sk->out (pitch C) and normalises it in the same pass;
+// backward takes dy from the partials (no bias / res) instead of from memory.
+struct GnSplitK {
+  const float* ws = nullptr;
+  int splits = 0, ld_ws = 0;
+  const float* bias = nullptr;
+  const act_t* res = nullptr;
+  act_t* out = nullptr;
+};
+bool gn_group_supported(int pixels, int C);  // covered AND inside the size range where it is the faster kernel
+bool gn_group_possible(int pixels, int C);   // covered at all (the launchers accept these)
+void gn_forward_group(const act_t* x, const GnSplitK* sk, const float* gamma, const float* beta, int pixels, int C,
+                      int swish, float eps, float* stats, act_t* y, cudaStream_t st);
+void gn_backward_group(const act_t* dy, const GnSplitK* sk, const act_t* x, const float* stats, const float* gamma,
+                       const float* beta, int pixels, int C, int swish, const act_t* dres, act_t* dx, cudaStream_t st);
 
 // ---- VQGAN encoder side (taming Encoder; VqganDrawer.init_from_tensor, vqgan.py:174-185): forward only, init time
 // image [3, H, W] fp32 in [-1, 1] -> NHWC fp16 [pixels, 64] (channels 3..63 zero: conv_in's padded reduction)

@@ -5,6 +5,7 @@
 #include "attn_tc.cuh"
 #include "color_jitter.cuh"
 #include "pool_bounds.cuh"
+#include "kernels.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -170,4 +171,51 @@ extern "C" int pxr_test_pool_bounds(int in_size, int out_size, int* starts, int*
   if (in_size < 1 || out_size < 1 || !starts || !ends) return -1;
   pool_bounds_kernel<<<(out_size + 255) / 256, 256>>>(in_size, out_size, starts, ends);
   return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+
+// GroupNorm(32, C, eps 1e-6)(+ swish) forward, and backward when dy (or ws_dy) is given, on caller DEVICE tensors
+// (NHWC fp16 [pixels, C]).  variant 0: the single-kernel grid-barrier GroupNorm; 1: one cluster per group
+// (kernels_gn_group.cu).  variant 1 only: ws != NULL makes the forward the epilogue of a split-K convolution
+// (x_out = fp16(sum_s ws[s] + bias + res), then normalised); ws_dy != NULL feeds the backward from split-K partials.
+// scratch: >= 64 * (num_sms + 2) floats + one zero-initialised u64 at its END (variant 0's grid barrier).
+extern "C" int pxr_test_groupnorm(int variant, const void* x, const float* ws, int splits, const float* bias, const void* res,
+                                  void* x_out, const float* gamma, const float* beta, int pixels, int C, int swish, void* y,
+                                  float* stats, const void* dy, const float* ws_dy, int splits_dy, const void* dres, void* dx,
+                                  float* scratch, int repeat) {
+  const act_t* xin = static_cast<const act_t*>(x);
+  const int nsm = num_sms();
+  GridBarrier gb;  // the caller hands in a zeroed counter with every call
+  gb.counter = reinterpret_cast<unsigned long long*>(scratch + 64 * (nsm + 2));
+  if (variant == 0) {
+    if (ws || ws_dy || !gn_coop_supported(pixels, C, nsm)) return -1;
+  } else {
+    if (!gn_group_possible(pixels, C)) return -2;
+  }
+  for (int it = 0; it < (repeat > 0 ? repeat : 1); ++it) {
+    if (variant == 0) {
+      gn_forward_coop(xin, gamma, beta, pixels, C, swish, 1e-6f, scratch, stats, static_cast<act_t*>(y), nsm, &gb, nullptr);
+      if (dy)
+        gn_backward_coop(static_cast<const act_t*>(dy), xin, stats, gamma, beta, pixels, C, swish,
+                         static_cast<const act_t*>(dres), scratch, static_cast<act_t*>(dx), nsm, &gb, nullptr);
+    } else {
+      GnSplitK sk, skd;
+      sk.ws = ws;
+      sk.splits = splits;
+      sk.ld_ws = C;
+      sk.bias = bias;
+      sk.res = static_cast<const act_t*>(res);
+      sk.out = static_cast<act_t*>(x_out);
+      skd.ws = ws_dy;
+      skd.splits = splits_dy;
+      skd.ld_ws = C;
+      gn_forward_group(xin, ws ? &sk : nullptr, gamma, beta, pixels, C, swish, 1e-6f, stats, static_cast<act_t*>(y), nullptr);
+      const act_t* xs = ws ? static_cast<const act_t*>(x_out) : xin;
+      if (dy || ws_dy)
+        gn_backward_group(static_cast<const act_t*>(dy), ws_dy ? &skd : nullptr, xs, stats, gamma, beta, pixels, C, swish,
+                          static_cast<const act_t*>(dres), static_cast<act_t*>(dx), nullptr);
+    }
+  }
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : -100;
 }

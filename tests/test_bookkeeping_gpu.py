@@ -83,6 +83,52 @@ def test_vq_code_indices_bit_exact():
         print(f"[parity] VQ indices trial {trial}: {int(same.sum())}/256 equal the fp64 argmin, {int(amb.sum())} fp32-ambiguous")
 
 
+def test_vq_tensor_core_search_equals_the_fp32_search():
+    """The nearest-code search with the distance matrix on the tensor cores + exact fp32 recheck of the candidates
+    (kernels_vq_tc.cu) picks the same index as the all-fp32 search (PXR_VQ_TC=0) -- full-size codebook, latents from
+    'on a code' to 'far between codes', plus a degenerate codebook with duplicated rows (exact ties: the first index wins)."""
+    import os
+    from pixray_b200 import synthetic as S
+    clip_cfg = dict(width=128, layers=1, heads=2, patch=32, image_res=224, out_dim=64)
+    vq_sd = S.vqgan_state_dict(E.VQGAN_F16_16384, 0)
+    cb = vq_sd["quantize.embedding.weight"]
+    cb_dup = cb.clone()
+    cb_dup[8000:8100] = cb[100:200]          # duplicated rows: ties between j and j + 7900
+    engines = {}
+    for name, sd_cb in (("plain", cb), ("dup", cb_dup)):
+        sd = dict(vq_sd)
+        sd["quantize.embedding.weight"] = sd_cb
+        for tc in ("1", "0"):
+            os.environ["PXR_VQ_TC"] = tc
+            try:
+                e = E.B200Engine(drawer=E.DRAWER_VQGAN, image_hw=(256, 256), cutn=8, clip=[clip_cfg], seed=0)
+                e.load_module(E.MOD_VQGAN, sd)
+                e.load_module(E.MOD_CLIP0, S.clip_state_dict(clip_cfg, 1))
+                e.finalize()
+            finally:
+                os.environ.pop("PXR_VQ_TC", None)
+            engines[(name, tc)] = e
+    g = torch.Generator().manual_seed(9)
+    for name, sd_cb in (("plain", cb), ("dup", cb_dup)):
+        for trial, sigma in enumerate([0.0, 0.02, 0.3, 1.0, 3.0]):
+            pick = torch.randint(16384, (256,), generator=g)
+            if name == "dup":
+                pick[:64] = torch.randint(100, 200, (64,), generator=g)      # land on duplicated rows
+            z = (sd_cb[pick].T.reshape(1, 256, 16, 16) + sigma * sd_cb.std() * torch.randn(1, 256, 16, 16, generator=g)).contiguous()
+            if trial == 4:
+                z = z * 40.0        # far outside the codebook's range (the scaling path)
+            out = {}
+            for tc in ("1", "0"):
+                engines[(name, tc)].synth(z)
+                out[tc] = engines[(name, tc)].debug_read("vq_idx", (256,), dtype=torch.int32).cpu()
+            assert torch.equal(out["1"], out["0"]), (name, trial, int((out["1"] != out["0"]).sum()))
+            if name == "dup" and sigma == 0.0:
+                assert int(out["1"][:64].max()) < 200   # first index of the tied pair
+        st = engines[(name, "1")].debug_read("vq_stats", (2,), dtype=torch.int32).cpu()
+        print(f"[parity] VQ tensor-core search ({name}): {int(st[0])} candidates rechecked over {5 * 256} positions, "
+              f"{int(st[1])} positions fell back to the full search")
+
+
 def test_pixel_drawer_matches_the_oracle():
     """FastPixelDrawer.synth (fast_pixeldrawer.py:83-91): nearest upsample of the colour grid + clamp_with_grad; forward
     image, z.grad and the Adam / clip_z([0,1]) update, through the engine's PXR_DRAWER_PIXEL path.  Includes a grid that
