@@ -118,6 +118,7 @@ class Engine {
   float *cut_src = nullptr, *g_cut_src = nullptr;  // [3, src_h, src_w]; == pooled / g_pooled when square
   int* pool_argmax = nullptr;
   float *part_min = nullptr, *part_max = nullptr, *range = nullptr, *sums = nullptr;
+  long long *sums_fx = nullptr, *grad_fx = nullptr;  // 64-bit fixed-point accumulators (order-independent sums, kernels_cutouts.cu)
   int *part_imin = nullptr, *part_imax = nullptr, *irange = nullptr;
   int n_parts = 0;
   static constexpr int RING = 8;
@@ -406,6 +407,7 @@ class Engine {
   bool conv_splitk = true;  // PXR_CONV_SPLITK=0 disables
   bool gn_group = true;     // PXR_GN_GROUP=0: never use the cluster-per-group GroupNorm (kernels_gn_group.cu)
   bool gn_fuse_sk = true;   // PXR_GN_FUSE_SPLITK=0: keep splitk_reduce and GroupNorm as two kernels
+  bool gn_fuse_fwd = true, gn_fuse_bwd = true;  // PXR_GN_FUSE_FWD / PXR_GN_FUSE_BWD = 0: per direction (diagnostics)
   // the split-K reduce most recently appended by add_conv: a GroupNorm over exactly its output, appended next to the same
   // list, replaces that op by the fused reduce + GroupNorm kernel
   // (one slot per op list: forward and backward lists are built interleaved)
@@ -653,6 +655,8 @@ void Engine::create() {
   if (const char* sk = getenv("PXR_CONV_SPLITK")) conv_splitk = atoi(sk) != 0;
   if (const char* gg = getenv("PXR_GN_GROUP")) gn_group = atoi(gg) != 0;
   if (const char* gf = getenv("PXR_GN_FUSE_SPLITK")) gn_fuse_sk = atoi(gf) != 0;
+  if (const char* gf = getenv("PXR_GN_FUSE_FWD")) gn_fuse_fwd = atoi(gf) != 0;
+  if (const char* gf = getenv("PXR_GN_FUSE_BWD")) gn_fuse_bwd = atoi(gf) != 0;
   if (const char* tr = getenv("PXR_TRACE")) trace = atoi(tr) != 0;
   if (cfg.beta1 <= 0) cfg.beta1 = 0.9f;
   if (cfg.beta2 <= 0) cfg.beta2 = 0.999f;
@@ -714,7 +718,7 @@ Engine::GNSaved Engine::add_gn(OpList& l, const Act& x, const NormW& n, int swis
   const int nsm = num_sms;
   if (gn_group && gn_group_supported(px, C)) {
     const std::string shape = " px=" + std::to_string(px) + " C=" + std::to_string(C);
-    if (const GnSplitK* pk = take_pending_splitk(l, xp, px, C, false)) {
+    if (const GnSplitK* pk = gn_fuse_fwd ? take_pending_splitk(l, xp, px, C, false) : nullptr) {
       const GnSplitK sk = *pk;
       l.ops.back() = [=] { gn_forward_group(nullptr, &sk, nn.gamma, nn.beta, px, C, swish, 1e-6f, stats, y, cs); };
       l.names.back() = "splitk_reduce+gn_fwd_group" + shape + " splits=" + std::to_string(sk.splits);
@@ -744,7 +748,7 @@ void Engine::add_gn_bwd(OpList& l, const act_t* dy, const act_t* x, const GNSave
   GridBarrier* gb = &gn_bar;
   if (gn_group && gn_group_supported(px, C)) {
     const std::string shape = " px=" + std::to_string(px) + " C=" + std::to_string(C);
-    if (const GnSplitK* pk = take_pending_splitk(l, dy, px, C, true)) {
+    if (const GnSplitK* pk = gn_fuse_bwd ? take_pending_splitk(l, dy, px, C, true) : nullptr) {
       const GnSplitK sk = *pk;  // dy itself is never written: the reduced gradient lives in registers only
       l.ops.back() = [=] { gn_backward_group(nullptr, &sk, x, s.stats, n.gamma, n.beta, px, C, swish, dres, dx, cs); };
       l.names.back() = "splitk_reduce+gn_bwd_group" + shape + " splits=" + std::to_string(sk.splits);
@@ -1360,6 +1364,7 @@ void Engine::build_cutouts() {
     cut_src = pooled;
     g_cut_src = g_pooled;
   }
+  grad_fx = dalloc<long long>((size_t)3 * std::max(src_h * src_w, cs_ * cs_));  // zeroed; each use clears it again
   pool_argmax = dalloc<int>((size_t)3 * cs_ * cs_);
   batch = dalloc<float>((size_t)n_local * 3 * cs_ * cs_);
   g_batch = dalloc<float>((size_t)n_local * 3 * cs_ * cs_);
@@ -1371,6 +1376,7 @@ void Engine::build_cutouts() {
   range = dalloc<float>(4);
   irange = dalloc<int>(4);
   sums = dalloc<float>(4);
+  sums_fx = dalloc<long long>(2);  // zero-initialised; every pass leaves it zeroed again
   xbuf = dalloc<float>(4);
   minv_dev = dalloc<float>((size_t)n_local * 12);  // 9 homography + 3 ColorJitter floats per cutout, one H2D copy
   facs_dev = dalloc<float>(n_local);
@@ -1997,26 +2003,25 @@ void Engine::aux_on_image() {
 // d loss / d pooled [-> un-stretch] [-> spot mask] -> d loss / d image (= or +=).  `a` = the cutout parameters of the pass
 // whose activations are live; mask_which >= 0: a spot pass (only the perceptors with spot prompts of that kind ran).
 void Engine::backward_to_image(const CutoutArgs& a, int mask_which, bool accumulate_img, bool main_pass) {
-  PXR_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(float), st));
   bool first = true;
   for (int i = 0; i < cfg.n_clip; ++i) {
     Clip& C = clip[i];
     if (mask_which >= 0 && C.spot[mask_which].n == 0) continue;
     run(C.bwd);
-    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, !first, g_batch, sums, st);
+    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, !first, g_batch, sums_fx, st);
     first = false;
     launches += 1;
   }
   if (main_pass && !aux.empty()) aux_on_cutouts();
+  range_sums_finish(sums_fx, sums, st);  // fixed point -> fp32 (and the accumulator is clean for the next pass)
   if (comm)  // d/dmin, d/dmax terms need the sums over ALL cutouts
     nccl_check(Comm::api().all_reduce(sums, sums, 2, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(sums)");
-  PXR_CUDA(cudaMemsetAsync(g_cut_src, 0, sizeof(float) * 3 * src_h * src_w, st));
-  cutout_backward(a, g_batch, range, irange, sums, g_cut_src, st);
+  cutout_backward(a, g_batch, range, irange, sums, grad_fx, g_cut_src, st);
+  launches += 2;
   const int ncs = 3 * cfg.cut_size * cfg.cut_size;
   if (aspect != 1.0) {
-    PXR_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * ncs, st));
-    rescale_bilinear_backward(g_cut_src, cfg.cut_size, cfg.cut_size, src_h, src_w, g_pooled, st);
-    launches += 1;
+    rescale_bilinear_backward(g_cut_src, cfg.cut_size, cfg.cut_size, src_h, src_w, grad_fx, g_pooled, st);
+    launches += 2;
   }
   if (mask_which >= 0) {  // cutout[0][mask_indexes] = 0 (pixray.py:466): no gradient through the zeroed pixels
     spot_mask_apply(g_pooled, spot_mask, mask_which == 1, ncs, g_pooled, st);

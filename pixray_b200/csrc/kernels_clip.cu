@@ -151,6 +151,135 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const act_t* __restr
   }
 }
 
+// fp16 residual stream, W % 256 == 0: every access is a 16-byte vector of 8 halfs (lane owns NV8 = W / 256 of them per
+// tensor) -- half the load / store instructions of the 8-byte form above for the same bytes.
+__device__ __forceinline__ void ln_unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 ln_pack8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+template <int NV8>
+__global__ void __launch_bounds__(256) layernorm_fwd16_kernel(const act_t* __restrict__ x, long long x_stride,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int rows, int W, float eps,
+                                                              act_t* __restrict__ y16, float* __restrict__ stats) {
+  pdl_prologue();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * x_stride);
+  uint4 raw[NV8];
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) raw[i] = xr[lane + 32 * i];
+  float v[NV8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    ln_unpack8(raw[i], v[i]);
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) s += (v[i][j] + v[i][j + 1]) + (v[i][j + 2] + v[i][j + 3]);
+  }
+  const float mean = warp_sum(s) / W;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float a = v[i][j] - mean, b = v[i][j + 1] - mean, c = v[i][j + 2] - mean, d = v[i][j + 3] - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / W + eps);
+  if (lane == 0) {
+    stats[2 * row] = mean;
+    stats[2 * row + 1] = rstd;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint4* yr = reinterpret_cast<uint4*>(y16 + (size_t)row * W);
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c8 = lane + 32 * i;
+    const float4 ga = g4[2 * c8], gb = g4[2 * c8 + 1], ba = b4[2 * c8], bb = b4[2 * c8 + 1];
+    const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float b[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+    yr[c8] = ln_pack8(o);
+  }
+}
+
+template <int NV8>
+__global__ void __launch_bounds__(256) layernorm_bwd16_kernel(const act_t* __restrict__ dy, const act_t* __restrict__ x,
+                                                              long long x_stride, const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, int rows, int W,
+                                                              int accumulate, act_t* __restrict__ gx16) {
+  pdl_prologue();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * x_stride);
+  const uint4* dr = reinterpret_cast<const uint4*>(dy + (size_t)row * W);
+  uint4* gr = reinterpret_cast<uint4*>(gx16 + (size_t)row * x_stride);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  uint4 rx[NV8], rd[NV8], rp[NV8];
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {  // every load of the row in flight before the first use
+    rx[i] = xr[lane + 32 * i];
+    rd[i] = dr[lane + 32 * i];
+    if (accumulate) rp[i] = gr[lane + 32 * i];
+  }
+  float g[NV8][8], xh[NV8][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int c8 = lane + 32 * i;
+    const float4 ga = g4[2 * c8], gb = g4[2 * c8 + 1];
+    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    float xv[8], dv[8];
+    ln_unpack8(rx[i], xv);
+    ln_unpack8(rd[i], dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[i][j] = (xv[j] - mean) * rstd;
+      g[i][j] = dv[j] * gm[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      s1 += (g[i][j] + g[i][j + 1]) + (g[i][j + 2] + g[i][j + 3]);
+      s2 += (g[i][j] * xh[i][j] + g[i][j + 1] * xh[i][j + 1]) + (g[i][j + 2] * xh[i][j + 2] + g[i][j + 3] * xh[i][j + 3]);
+    }
+  }
+  s1 = warp_sum(s1) / W;
+  s2 = warp_sum(s2) / W;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    float d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+    if (accumulate) {
+      float pv[8];
+      ln_unpack8(rp[i], pv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += pv[j];
+    }
+    gr[lane + 32 * i] = ln_pack8(d);
+  }
+}
+
 // one warp per row; lane owns NV 16-byte vectors (8 halfs) of the row: ld % 8 == 0, ld <= 256 * NV
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(act_t* __restrict__ s, long long rows, int cols, int ld) {
@@ -461,6 +590,15 @@ __global__ void cast_kernel(const float* x, act_t* y, long long n, float scale) 
 
 }  // namespace
 
+// PXR_LN16_WIDE=0 keeps the 8-byte-vector LayerNorm kernels on the fp16 stream (A/B switch)
+static bool ln16_wide_ok() {
+  static const bool on = [] {
+    const char* e = getenv("PXR_LN16_WIDE");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+
 #define LN_DISPATCH(KERNEL, XT, ...)                                                   \
   switch (W / 128) {                                                              \
     case 1: launch_pdl(KERNEL<1, XT>, dim3((rows + 7) / 8), dim3(256), 0, st, __VA_ARGS__); break;        \
@@ -479,6 +617,16 @@ void layernorm_forward(const float* x, long long x_stride, const float* pos, int
 void layernorm_forward(const act_t* x, long long x_stride, const float* pos, int T, const float* gamma,
                        const float* beta, int rows, int W, float eps, act_t* y16, float* y32, float* stats,
                        cudaStream_t st) {
+  if (ln16_wide_ok() && !pos && !y32 && y16 && W % 256 == 0 && x_stride % 8 == 0) {
+    const dim3 grid((rows + 7) / 8), block(256);
+    switch (W / 256) {
+      case 1: launch_pdl(layernorm_fwd16_kernel<1>, grid, block, 0, st, x, x_stride, gamma, beta, rows, W, eps, y16, stats); return;
+      case 2: launch_pdl(layernorm_fwd16_kernel<2>, grid, block, 0, st, x, x_stride, gamma, beta, rows, W, eps, y16, stats); return;
+      case 3: launch_pdl(layernorm_fwd16_kernel<3>, grid, block, 0, st, x, x_stride, gamma, beta, rows, W, eps, y16, stats); return;
+      case 4: launch_pdl(layernorm_fwd16_kernel<4>, grid, block, 0, st, x, x_stride, gamma, beta, rows, W, eps, y16, stats); return;
+      default: break;
+    }
+  }
   LN_DISPATCH(layernorm_fwd_kernel, act_t, x, x_stride, pos, T, gamma, beta, rows, W, eps, y16, y32, stats)
 }
 void layernorm_backward(const act_t* dy, const float* x, long long x_stride, const float* pos, int T,
@@ -489,6 +637,16 @@ void layernorm_backward(const act_t* dy, const float* x, long long x_stride, con
 void layernorm_backward(const act_t* dy, const act_t* x, long long x_stride, const float* pos, int T,
                         const float* stats, const float* gamma, int rows, int W, int accumulate, float* gx,
                         act_t* gx16, cudaStream_t st) {
+  if (ln16_wide_ok() && !pos && !gx && gx16 && W % 256 == 0 && x_stride % 8 == 0) {
+    const dim3 grid((rows + 7) / 8), block(256);
+    switch (W / 256) {
+      case 1: launch_pdl(layernorm_bwd16_kernel<1>, grid, block, 0, st, dy, x, x_stride, stats, gamma, rows, W, accumulate, gx16); return;
+      case 2: launch_pdl(layernorm_bwd16_kernel<2>, grid, block, 0, st, dy, x, x_stride, stats, gamma, rows, W, accumulate, gx16); return;
+      case 3: launch_pdl(layernorm_bwd16_kernel<3>, grid, block, 0, st, dy, x, x_stride, stats, gamma, rows, W, accumulate, gx16); return;
+      case 4: launch_pdl(layernorm_bwd16_kernel<4>, grid, block, 0, st, dy, x, x_stride, stats, gamma, rows, W, accumulate, gx16); return;
+      default: break;
+    }
+  }
   LN_DISPATCH(layernorm_bwd_kernel, act_t, dy, x, x_stride, pos, T, stats, gamma, rows, W, accumulate, gx, gx16)
 }
 void softmax_forward(act_t* s, int rows, int cols, int ld, cudaStream_t st) {

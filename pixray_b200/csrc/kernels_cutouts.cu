@@ -177,8 +177,32 @@ __global__ void rescale_fwd_kernel(const float* __restrict__ x, int in_h, int in
   y[i] = (1.f - ly) * top + ly * bot;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Order-independent accumulation.  The scatter of the warp adjoint, the un-stretch adjoint and the two range sums add
+// many contributions to one address from many blocks; float atomics would make the result depend on the arrival order (a
+// last-bit difference that flips fp16 roundings further down the drawer backward: measured as a two-state jitter of 7e-4 of
+// max|z.grad| between identical runs).  They accumulate in 64-bit FIXED POINT instead -- integer addition is associative,
+// so the sum is the same bits on every run and on every rank -- and one small kernel converts to fp32 (and clears the
+// accumulator for the next pass).  Scales: 2^36 for gradient images (range +-1.3e8, step 1.5e-11: finer than an fp32 add at
+// the magnitudes that occur, grad_scale * dL ~ 1e-2 ... 1e2), 2^30 for the two range sums (range +-8.6e9).
+constexpr float FX_GRAD = 68719476736.f;       // 2^36
+constexpr float FX_GRAD_INV = 1.f / 68719476736.f;
+constexpr float FX_SUM = 1073741824.f;         // 2^30
+constexpr float FX_SUM_INV = 1.f / 1073741824.f;
+__device__ __forceinline__ void fx_add(long long* p, float v, float scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(v * scale)));
+}
+__global__ void __launch_bounds__(256) fx_to_float_kernel(long long* __restrict__ acc, float* __restrict__ out, int n,
+                                                          float inv_scale) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (float)acc[i] * inv_scale;
+  acc[i] = 0;
+}
+
 __global__ void rescale_bwd_kernel(const float* __restrict__ gy, int in_h, int in_w, int out_h, int out_w,
-                                   float* __restrict__ gx) {
+                                   long long* __restrict__ gx) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * out_h * out_w) return;
@@ -187,12 +211,12 @@ __global__ void rescale_bwd_kernel(const float* __restrict__ gy, int in_h, int i
   float lx, ly;
   lin_taps(ox, in_w, out_w, x0, x1, lx);
   lin_taps(oy, in_h, out_h, y0, y1, ly);
-  float* p = gx + (size_t)c * in_h * in_w;
+  long long* p = gx + (size_t)c * in_h * in_w;
   const float g = gy[i];
-  atomicAdd(p + y0 * in_w + x0, (1.f - ly) * (1.f - lx) * g);
-  atomicAdd(p + y0 * in_w + x1, (1.f - ly) * lx * g);
-  atomicAdd(p + y1 * in_w + x0, ly * (1.f - lx) * g);
-  atomicAdd(p + y1 * in_w + x1, ly * lx * g);
+  fx_add(p + y0 * in_w + x0, (1.f - ly) * (1.f - lx) * g, FX_GRAD);
+  fx_add(p + y0 * in_w + x1, (1.f - ly) * lx * g, FX_GRAD);
+  fx_add(p + y1 * in_w + x0, ly * (1.f - lx) * g, FX_GRAD);
+  fx_add(p + y1 * in_w + x1, ly * lx * g, FX_GRAD);
 }
 
 constexpr int CUT_THREADS = 256;
@@ -507,7 +531,7 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
                                                            const float* __restrict__ batch,
                                                            const float* __restrict__ range, int n, int cs, int P,
                                                            int ld, int accumulate, float* __restrict__ g_batch,
-                                                           float* __restrict__ sums) {
+                                                           long long* __restrict__ sums) {
   pdl_prologue();
   const int gp = cs / P;
   const int vec_per_row = 3 * P * P / 8;
@@ -566,8 +590,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
       a += r1[i];
       b += r2[i];
     }
-    atomicAdd(&sums[0], a);
-    atomicAdd(&sums[1], b);
+    fx_add(&sums[0], a, FX_SUM);
+    fx_add(&sums[1], b, FX_SUM);
   }
 }
 
@@ -596,7 +620,7 @@ __global__ void __launch_bounds__(256) patchify_bwd_generic_kernel(const act_t* 
                                                                    const float* __restrict__ range, int n, int cs,
                                                                    int P, int ld, int accumulate,
                                                                    float* __restrict__ g_batch,
-                                                                   float* __restrict__ sums) {
+                                                                   long long* __restrict__ sums) {
   pdl_prologue();
   const int gp = cs / P;
   const long long total = (long long)n * 3 * cs * cs;
@@ -633,8 +657,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_generic_kernel(const act_t* 
       a += r1[i];
       b2 += r2[i];
     }
-    atomicAdd(&sums[0], a);
-    atomicAdd(&sums[1], b2);
+    fx_add(&sums[0], a, FX_SUM);
+    fx_add(&sums[1], b2, FX_SUM);
   }
 }
 
@@ -642,7 +666,7 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
                                                                  const float* __restrict__ range,
                                                                  const int* __restrict__ irange,
                                                                  const float* __restrict__ sums,
-                                                                 float* __restrict__ g_pooled) {
+                                                                 long long* __restrict__ g_pooled) {
   pdl_prologue();
   const int n = blockIdx.y;
   const int n_global = a.first_global + n;
@@ -697,13 +721,13 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float* p = g_pooled + (size_t)c * a.src_h * a.src_w;
+      long long* p = g_pooled + (size_t)c * a.src_h * a.src_w;
       const int sw = a.src_w;
       float gv = gpre[c];
-      if (t.in[0]) atomicAdd(p + t.y0 * sw + t.x0, t.w[0] * gv);
-      if (t.in[1]) atomicAdd(p + t.y0 * sw + t.x0 + 1, t.w[1] * gv);
-      if (t.in[2]) atomicAdd(p + (t.y0 + 1) * sw + t.x0, t.w[2] * gv);
-      if (t.in[3]) atomicAdd(p + (t.y0 + 1) * sw + t.x0 + 1, t.w[3] * gv);
+      if (t.in[0]) fx_add(p + t.y0 * sw + t.x0, t.w[0] * gv, FX_GRAD);
+      if (t.in[1]) fx_add(p + t.y0 * sw + t.x0 + 1, t.w[1] * gv, FX_GRAD);
+      if (t.in[2]) fx_add(p + (t.y0 + 1) * sw + t.x0, t.w[2] * gv, FX_GRAD);
+      if (t.in[3]) fx_add(p + (t.y0 + 1) * sw + t.x0 + 1, t.w[3] * gv, FX_GRAD);
     }
   }
 }
@@ -724,8 +748,13 @@ void spot_mask_apply(const float* x, const unsigned char* mask, int zero_where_s
 void rescale_bilinear(const float* x, int in_h, int in_w, int out_h, int out_w, float* y, cudaStream_t st) {
   launch_pdl(rescale_fwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, x, in_h, in_w, out_h, out_w, y);
 }
-void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, float* gx, cudaStream_t st) {
-  launch_pdl(rescale_bwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, gy, in_h, in_w, out_h, out_w, gx);
+void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, long long* acc, float* gx,
+                               cudaStream_t st) {
+  launch_pdl(rescale_bwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, gy, in_h, in_w, out_h, out_w, acc);
+  launch_pdl(fx_to_float_kernel, dim3((3 * in_h * in_w + 255) / 256), dim3(256), 0, st, acc, gx, 3 * in_h * in_w, FX_GRAD_INV);
+}
+void range_sums_finish(long long* acc, float* sums, cudaStream_t st) {
+  launch_pdl(fx_to_float_kernel, dim3(1), dim3(256), 0, st, acc, sums, 2, FX_SUM_INV);
 }
 
 int cutout_num_blocks(int n_local, int cs) { return n_local * ((cs * cs / 4 + CUT_THREADS - 1) / CUT_THREADS); }
@@ -768,7 +797,7 @@ void patchify_forward(const float* batch, const float* range, int n, int cs, int
   launch_pdl(patchify_fwd_kernel, dim3(patch_grid(total)), dim3(256), 0, st, batch, range, n, cs, P, ld, patches);
 }
 void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
-                       int accumulate, float* g_batch, float* sums, cudaStream_t st) {
+                       int accumulate, float* g_batch, long long* sums, cudaStream_t st) {
   if (P % 8) {
     const long long tot = (long long)n * 3 * cs * cs;
     launch_pdl(patchify_bwd_generic_kernel, dim3(patch_grid(tot)), dim3(256), 0, st, g_patches, batch, range, n, cs, P, ld, accumulate,
@@ -780,9 +809,11 @@ void patchify_backward(const act_t* g_patches, const float* batch, const float* 
                                                          sums);
 }
 void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* range, const int* irange,
-                     const float* sums, float* g_pooled, cudaStream_t st) {
+                     const float* sums, long long* acc, float* g_pooled, cudaStream_t st) {
   dim3 grid((a.cs * a.cs / 4 + CUT_THREADS - 1) / CUT_THREADS, a.n_local);
-  launch_pdl(cutout_bwd_kernel, dim3(grid), dim3(CUT_THREADS), 0, st, a, g_batch, range, irange, sums, g_pooled);
+  launch_pdl(cutout_bwd_kernel, dim3(grid), dim3(CUT_THREADS), 0, st, a, g_batch, range, irange, sums, acc);
+  const int n = 3 * a.src_h * a.src_w;
+  launch_pdl(fx_to_float_kernel, dim3((n + 255) / 256), dim3(256), 0, st, acc, g_pooled, n, FX_GRAD_INV);
 }
 
 }  // namespace pxr

@@ -99,8 +99,40 @@ def run(hw, seed=3):
     zz2 = z.clone().requires_grad_(True)
     R.vqgan_synth(vq, zz2).backward(gi)
     rel("engine z.grad vs oracle-bwd(engine g_img)", eng.debug_read("z_grad", z.shape), zz2.grad)
+    # ClampWithGrad (vqgan.py:76-79) passes a gradient where the unclamped pixel is inside [0, 1] or the gradient pushes it
+    # back: a pixel within the fp16 forward error of the clamp boundary can sit on the other side in the engine
+    with torch.no_grad():
+        zq, _ = R.vector_quantize(z.movedim(1, 3), vq.quantize.embedding.weight)
+        pre_o = vq.decode(zq.movedim(3, 1)).add(1).div(2)
+    pre_e = eng.debug_read("img_pre", (1, 3, H, W)).cpu()
+    side = lambda t: (t > 1).int() - (t < 0).int()  # noqa: E731
+    flip = side(pre_e) != side(pre_o)
+    print(f"  pixels whose clamp side differs between engine and oracle: {int(flip.sum())} of {flip.numel()} "
+          f"(max |pre-clamp difference| {float((pre_e - pre_o).abs().max()):.3e})")
+    if int(flip.sum()):
+        # oracle backward with the ENGINE's clamp decisions: the same gradient through the same piece of the function
+        zz3 = z.clone().requires_grad_(True)
+        zq3, _ = R.vector_quantize(zz3.movedim(1, 3), vq.quantize.embedding.weight)
+        pre3 = vq.decode(zq3.movedim(3, 1)).add(1).div(2)
+        gi_in = gi.clone()
+        pe = pre_e
+        passes = ((pe >= 0) & (pe <= 1)) | ((pe < 0) & (gi_in < 0)) | ((pe > 1) & (gi_in > 0))  # g * (g * (x - clamp(x)) >= 0)
+        pre3.backward(gi_in * passes)
+        rel("engine z.grad vs oracle-bwd, engine's clamp mask", eng.debug_read("z_grad", z.shape), zz3.grad)
 
 
 if __name__ == "__main__":
-    for hw in [(32, 48), (48, 32), (18, 32), (64, 32)]:
-        run(hw)
+    import os
+    if len(sys.argv) > 1 and sys.argv[1] == "seeds":
+        # is the 48x32 decoder-backward error a property of the shape or of the data?  (also: PXR_GN_GROUP=0 /
+        # PXR_CONV_SPLITK=0 in the environment switch the candidate kernels off)
+        print("env:", {k: v for k, v in os.environ.items() if k.startswith("PXR_")})
+        for hw in [(48, 32), (32, 48)]:
+            for seed in (3, 4, 5, 6):
+                run(hw, seed)
+    elif len(sys.argv) > 1 and sys.argv[1] == "one":
+        print("env:", {k: v for k, v in os.environ.items() if k.startswith("PXR_")})
+        run((48, 32), 3)
+    else:
+        for hw in [(32, 48), (48, 32), (18, 32), (64, 32)]:
+            run(hw)

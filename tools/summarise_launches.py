@@ -3,7 +3,7 @@ tools/profile_c2.py into the per-kernel summary and the tcgen05-family DRAM traf
 
     python tools/summarise_launches.py gpurun_out/launches.csv profiles/r02_ncu_launches_c2
 
-Keeps the LAST complete iteration (from the last-but-one vq_partial_kernel launch to the last one)."""
+Keeps the LAST complete iteration (from the last-but-one vq_prep_kernel / vq_partial_kernel launch to the last one)."""
 import csv
 import json
 import re
@@ -21,8 +21,8 @@ for r in csv.DictReader(lines, fieldnames=["ID", "pid", "pname", "host", "kernel
     d = rows.setdefault(int(r["ID"]), {"kernel": r["kernel"], "grid": r["grid"], "block": r["block"]})
     d[r["metric"]] = float(r["value"].replace(",", ""))
 ids = sorted(rows)
-starts = [i for i in ids if "vq_partial_kernel" in rows[i]["kernel"]]
-assert starts, "no iteration start (vq_partial_kernel) in the capture"
+starts = [i for i in ids if "vq_partial_kernel" in rows[i]["kernel"] or "vq_prep_kernel" in rows[i]["kernel"]]
+assert starts, "no iteration start (vq_prep_kernel / vq_partial_kernel) in the capture"
 sel = [i for i in ids if starts[-2] <= i < starts[-1]] if len(starts) >= 2 else [i for i in ids if i >= starts[0]]
 
 
