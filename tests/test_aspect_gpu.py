@@ -57,13 +57,18 @@ def test_non_square_canvas_matches_the_oracle(hw):
     e_g, m_g = report("z.grad", eng.debug_read("z_grad", z.shape), ref["z_grad"])
     assert e_img < 5e-3 and e_src < 1e-5 and e_b < 1e-4 and e_bb < 1e-4
     assert np.abs(losses - ref_l).max() < 5e-3
-    zg = eng.debug_read("z_grad", z.shape).cpu().double()
-    rel_l2 = float((zg - ref["z_grad"].double()).norm() / ref["z_grad"].double().norm())
-    print(f"[parity] z.grad {H}x{W}: rel-L2 err {rel_l2:.3e}")
-    # max-abs can be dominated by ONE arg-max flip of the adaptive max pool (the engine's fp16 image differs from the
-    # oracle's by 1.4e-3 and the up-sampling pool has 1-2 pixel windows): the 48x32 case sits at 3.1e-2 of max with a small
-    # rel-L2 error, the other two at 3e-3
-    assert e_g <= 3e-2 * m_g or (rel_l2 <= 1.5e-2 and e_g <= 5e-2 * m_g)
+    if e_g > 3e-2 * m_g:
+        # a pixel on the other side of ClampWithGrad's discontinuity (see vqgan_synth_with_engine_clamp_sides): compare
+        # against the oracle evaluated on the engine's side of the clamp for that pixel -- few pixels, same bound
+        from test_pipeline_gpu import vqgan_synth_with_engine_clamp_sides
+        synth, side_e = vqgan_synth_with_engine_clamp_sides(vq, eng, (H, W))
+        ref2 = R.iterate(synth, z, [clip], [prompts], torch.from_numpy(T), cs, "reflection", 0.4, facs, noise, aspect=aspect)
+        assert (ref2["image"] - ref["image"]).abs().max().item() == 0.0      # same forward
+        moved = (ref2["z_grad"] - ref["z_grad"]).abs().max().item()
+        print(f"[parity] {H}x{W}: oracle z.grad moves by {moved / m_g:.3e} of max when its clamp sides follow the engine's")
+        assert moved > 0, "the sides agree: the error has another cause"
+        e_g, m_g = report("z.grad (oracle on the engine's clamp sides)", eng.debug_read("z_grad", z.shape), ref2["z_grad"])
+    assert e_g <= 3e-2 * m_g
     # the engine's own draws (Philox sampler of csrc/transforms.h) stay finite and inside the stretched source
     eng.iterate(zc, 0.05, 1, losses_out=losses)
     assert np.isfinite(losses).all() and torch.isfinite(zc).all()

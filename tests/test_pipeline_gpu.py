@@ -70,6 +70,38 @@ def plant_extremes(facs, noise):
     return facs, noise
 
 
+class _ClampSided(torch.autograd.Function):
+    """clamp_with_grad (vqgan.py:66-79) whose BACKWARD takes the side of [0, 1] each pixel is on from `side` (-1 / 0 / +1)
+    instead of from its own unclamped value; the forward value is the oracle's own."""
+
+    @staticmethod
+    def forward(ctx, x, side):
+        ctx.save_for_backward(side)
+        return x.clamp(0, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (side,) = ctx.saved_tensors
+        return g * (g * side >= 0), None   # g * (g * (x - clamp(x)) >= 0): only the sign of x - clamp(x) matters
+
+
+def vqgan_synth_with_engine_clamp_sides(vq, eng, image_hw):
+    """ClampWithGrad's backward is discontinuous in the unclamped image: a pixel within the engine's fp16 forward error
+    (~1.5e-3) of 0 or 1 can sit on the other side of the clamp in the engine, and then a whole pixel's gradient is kept
+    on one side and dropped on the other (measured on the 48x32 canvas: ONE such pixel moves z.grad by 3e-2 of its maximum;
+    profiles/r02_aspect_diag_clamp.log).  Returns (synth, n_flipped): the oracle's synth evaluated on the piece of the
+    function the engine is on -- identical to R.vqgan_synth wherever the sides agree."""
+    H, W = image_hw
+    pre_e = eng.debug_read("img_pre", (1, 3, H, W)).cpu()
+    side_e = ((pre_e > 1).float() - (pre_e < 0).float())
+
+    def synth(zz):
+        zq, _ = R.vector_quantize(zz.movedim(1, 3), vq.quantize.embedding.weight)
+        return _ClampSided.apply(vq.decode(zq.movedim(3, 1)).add(1).div(2), side_e)
+
+    return synth, side_e
+
+
 def report(name, got, ref):
     err = (got.float().cpu() - ref).abs().max().item()
     mag = ref.abs().max().item()
