@@ -563,8 +563,11 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t gnc_smem[];
   float* red = reinterpret_cast<float*>(gnc_smem);
-  act_t* cx = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);
-  act_t* cd = cx + (size_t)rpb * C;  // only touched when cache_dy
+  // The slab kept in shared memory between the two phases is dxh = dy * act'(a) * gamma (fp16), NOT x: the activation's
+  // derivative (exp + reciprocal per element) is then evaluated once instead of once per phase -- at the 256^2 level the
+  // kernel was bound by exactly those instructions (33 us for 64 MB of L2 traffic) -- and phase 2 re-reads x from L2
+  // in place of dy: the same bytes.  (cache_dy is ignored; kept in the signature for the launcher.)
+  act_t* cg = reinterpret_cast<act_t*>(gnc_smem + 4 * GNC_THREADS * 4);
   __shared__ double acc4[GNC_THREADS];  // gnc_fold: [16 lanes][64 slots]
   __shared__ double sh[64];
   const int vecs = C / 8, cpg = C / GN_G;
@@ -588,10 +591,9 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   for (int p = p_begin + pl; p < p_end; p += plane) {
     const uint4 ux = *reinterpret_cast<const uint4*>(x + (size_t)p * C + c0);
     const uint4 ud = *reinterpret_cast<const uint4*>(dy + (size_t)p * C + c0);
-    *reinterpret_cast<uint4*>(cx + (size_t)(p - p_begin) * C + c0) = ux;
-    if (cache_dy) *reinterpret_cast<uint4*>(cd + (size_t)(p - p_begin) * C + c0) = ud;
     const __half2* hx = reinterpret_cast<const __half2*>(&ux);
     const __half2* hd = reinterpret_cast<const __half2*>(&ud);
+    float t8[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 tx = __half22float2(hx[i]), td = __half22float2(hd[i]);
@@ -607,7 +609,23 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
         } else if (swish == 2) {
           d = (g8[e] * xh + b8[e]) > 0.f ? d : 0.f;
         }
-        const float dxh = d * g8[e];
+        t8[e] = d * g8[e];
+      }
+    }
+    // the sums see the fp16-rounded dxh: phase 2 subtracts the means from exactly these values
+    uint4 ut;
+    __half2* ht = reinterpret_cast<__half2*>(&ut);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ht[i] = __floats2half2_rn(t8[2 * i], t8[2 * i + 1]);
+    *reinterpret_cast<uint4*>(cg + (size_t)(p - p_begin) * C + c0) = ut;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 tx = __half22float2(hx[i]), tt = __half22float2(ht[i]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = 2 * i + k;
+        const float xh = ((k ? tx.y : tx.x) - mean2[e >> 2]) * rstd2[e >> 2];
+        const float dxh = k ? tt.y : tt.x;
         s[e >> 2][0] += dxh;
         s[e >> 2][1] += dxh * xh;
       }
@@ -632,24 +650,14 @@ __global__ void __launch_bounds__(GNC_THREADS, 1)
   }
 #pragma unroll 2
   for (int p = p_begin + pl; p < p_end; p += plane) {
-    float xv[8], dv[8], rv[8];
-    load8(cx + (size_t)(p - p_begin) * C + c0, xv);
-    if (cache_dy) load8(cd + (size_t)(p - p_begin) * C + c0, dv);
-    else load8(dy + (size_t)p * C + c0, dv);
+    float xv[8], tv[8], rv[8];
+    load8(x + (size_t)p * C + c0, xv);
+    load8(cg + (size_t)(p - p_begin) * C + c0, tv);
     if (dres) load8(dres + (size_t)p * C + c0, rv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float xh = (xv[i] - mean2[i >> 2]) * rstd2[i >> 2];
-      float d = dv[i];
-      if (swish == 1) {
-        const float a = g8[i] * xh + b8[i];
-        const float sg = 1.f / (1.f + __expf(-a));
-        d *= sg * (1.f + a * (1.f - sg));
-      } else if (swish == 2) {
-        d = (g8[i] * xh + b8[i]) > 0.f ? d : 0.f;
-      }
-      const float dxh = d * g8[i];
-      const float r = rstd2[i >> 2] * (dxh - gs0[i >> 2] - xh * gs1[i >> 2]);
+      const float r = rstd2[i >> 2] * (tv[i] - gs0[i >> 2] - xh * gs1[i >> 2]);
       xv[i] = dres ? r + rv[i] : r;
     }
     store8(dx + (size_t)p * C + c0, xv);
@@ -926,8 +934,8 @@ void gn_backward_coop(const act_t* dy, const act_t* x, const float* stats, const
   int rpb = gnc_rows_per_block(pixels, num_sms);
   const int grid = (pixels + rpb - 1) / rpb;
   const size_t slab = (size_t)rpb * C * 2;
-  int cache_dy = (4 * GNC_THREADS * 4 + 2 * slab <= (size_t)GNC_SMEM_MAX) ? 1 : 0;
-  const size_t smem = 4 * GNC_THREADS * 4 + (cache_dy ? 2 : 1) * slab;
+  const int cache_dy = 0;  // the kernel keeps ONE slab (dxh) since round 2
+  const size_t smem = 4 * GNC_THREADS * 4 + slab;
   launch_pdl(gn_coop_bwd_kernel<false>, dim3(grid), dim3(GNC_THREADS), smem, st, dy, x, stats, gamma, beta, pixels, C, swish, dres, rpb,
                                                              cache_dy, part, dx, gb->counter, gb->issued + grid, o);
   if (cudaPeekAtLastError() == cudaSuccess) gb->issued += grid;
