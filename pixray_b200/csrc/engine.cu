@@ -119,6 +119,14 @@ class Engine {
   int* pool_argmax = nullptr;
   float *part_min = nullptr, *part_max = nullptr, *range = nullptr, *sums = nullptr;
   long long *sums_fx = nullptr, *grad_fx = nullptr;  // 64-bit fixed-point accumulators (order-independent sums, kernels_cutouts.cu)
+  unsigned int* fx_poison = nullptr;                   // [2]: pass id of the last non-finite contribution to {gradient images, range sums}
+  unsigned int fx_pass = 0;
+  FxPass next_fx(int word) {
+    FxPass f;
+    f.poison = fx_poison + word;
+    f.pass = ++fx_pass;
+    return f;
+  }
   int *part_imin = nullptr, *part_imax = nullptr, *irange = nullptr;
   int n_parts = 0;
   static constexpr int RING = 8;
@@ -1377,6 +1385,7 @@ void Engine::build_cutouts() {
   irange = dalloc<int>(4);
   sums = dalloc<float>(4);
   sums_fx = dalloc<long long>(2);  // zero-initialised; every pass leaves it zeroed again
+  fx_poison = dalloc<unsigned int>(2);
   xbuf = dalloc<float>(4);
   minv_dev = dalloc<float>((size_t)n_local * 12);  // 9 homography + 3 ColorJitter floats per cutout, one H2D copy
   facs_dev = dalloc<float>(n_local);
@@ -2004,23 +2013,24 @@ void Engine::aux_on_image() {
 // whose activations are live; mask_which >= 0: a spot pass (only the perceptors with spot prompts of that kind ran).
 void Engine::backward_to_image(const CutoutArgs& a, int mask_which, bool accumulate_img, bool main_pass) {
   bool first = true;
+  const FxPass fx_sums = next_fx(1);
   for (int i = 0; i < cfg.n_clip; ++i) {
     Clip& C = clip[i];
     if (mask_which >= 0 && C.spot[mask_which].n == 0) continue;
     run(C.bwd);
-    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, !first, g_batch, sums_fx, st);
+    patchify_backward(C.g_patches, batch, range, n_local, cfg.cut_size, C.c.patch, C.Kp, !first, g_batch, sums_fx, fx_sums, st);
     first = false;
     launches += 1;
   }
   if (main_pass && !aux.empty()) aux_on_cutouts();
-  range_sums_finish(sums_fx, sums, st);  // fixed point -> fp32 (and the accumulator is clean for the next pass)
+  range_sums_finish(sums_fx, fx_sums, sums, st);  // fixed point -> fp32 (and the accumulator is clean for the next pass)
   if (comm)  // d/dmin, d/dmax terms need the sums over ALL cutouts
     nccl_check(Comm::api().all_reduce(sums, sums, 2, Comm::kFloat32, Comm::kSum, comm, st), "allreduce(sums)");
-  cutout_backward(a, g_batch, range, irange, sums, grad_fx, g_cut_src, st);
+  cutout_backward(a, g_batch, range, irange, sums, grad_fx, next_fx(0), g_cut_src, st);
   launches += 2;
   const int ncs = 3 * cfg.cut_size * cfg.cut_size;
   if (aspect != 1.0) {
-    rescale_bilinear_backward(g_cut_src, cfg.cut_size, cfg.cut_size, src_h, src_w, grad_fx, g_pooled, st);
+    rescale_bilinear_backward(g_cut_src, cfg.cut_size, cfg.cut_size, src_h, src_w, grad_fx, next_fx(0), g_pooled, st);
     launches += 2;
   }
   if (mask_which >= 0) {  // cutout[0][mask_indexes] = 0 (pixray.py:466): no gradient through the zeroed pixels

@@ -128,8 +128,14 @@ void spot_mask_apply(const float* x, const unsigned char* mask, int zero_where_s
 // kornia.geometry.transform.rescale of the pooled image for non-square canvases (pixray.py:468-472): bilinear,
 // align_corners=False ([3, in_h, in_w] -> [3, out_h, out_w]), and its adjoint (g_in must be zeroed by the caller)
 void rescale_bilinear(const float* x, int in_h, int in_w, int out_h, int out_w, float* y, cudaStream_t st);
-// acc: zeroed 64-bit fixed-point accumulator of 3 * in_h * in_w entries (order-independent scatter; cleared again on return)
-void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, long long* acc, float* gx,
+// 64-bit fixed-point accumulation (order-independent sums).  A pass that meets a NaN / Inf / out-of-range contribution
+// writes its id to *poison; the conversion to fp32 then yields NaN for the whole tensor (ids only ever grow: no reset).
+struct FxPass {
+  unsigned int* poison = nullptr;  // device word
+  unsigned int pass = 0;           // > 0, unique per accumulate + convert pair on that word
+};
+// acc: zeroed 64-bit fixed-point accumulator of 3 * in_h * in_w entries (cleared again on return)
+void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, long long* acc, FxPass fx, float* gx,
                                cudaStream_t st);
 
 struct CutoutArgs {
@@ -165,12 +171,12 @@ void patchify_forward(const float* batch, const float* range, int n, int cs, int
 // g_batch (=|+=) d/d(batch) of the direct term; sums_fx[0] += sum g_a, sums_fx[1] += sum g_a * a / R in 64-bit fixed point
 // (order-independent: identical bits on every run); range_sums_finish converts to fp32 and clears the accumulator
 void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
-                       int accumulate, float* g_batch, long long* sums_fx, cudaStream_t st);
-void range_sums_finish(long long* sums_fx, float* sums, cudaStream_t st);
+                       int accumulate, float* g_batch, long long* sums_fx, FxPass fx, cudaStream_t st);
+void range_sums_finish(long long* sums_fx, FxPass fx, float* sums, cudaStream_t st);
 // adds the argmin / argmax terms of the global range normalise, then scatters through the bilinear taps
 // g_pooled: [3, src_h, src_w] (overwritten); acc: zeroed fixed-point accumulator of the same extent (cleared again on return)
 void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* range, const int* irange,
-                     const float* sums, long long* acc, float* g_pooled, cudaStream_t st);
+                     const float* sums, long long* acc, FxPass fx, float* g_pooled, cudaStream_t st);
 
 // ------------------------------------------------------------------ CLIP ViT (slip.py:62-66; SLIP/models.py:18-64)
 // y = LN(x [+ pos[row % T]]) * gamma + beta ; x fp32 [rows, W]; outputs optional fp16 / fp32; stats [rows][2]

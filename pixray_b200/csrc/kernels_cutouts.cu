@@ -187,22 +187,29 @@ __global__ void rescale_fwd_kernel(const float* __restrict__ x, int in_h, int in
 // the magnitudes that occur, grad_scale * dL ~ 1e-2 ... 1e2), 2^30 for the two range sums (range +-8.6e9).
 constexpr float FX_GRAD = 68719476736.f;       // 2^36
 constexpr float FX_GRAD_INV = 1.f / 68719476736.f;
+constexpr float FX_GRAD_MAX = 67108864.f;      // 2^26: half the range; beyond it (or NaN / Inf) the pass is poisoned
 constexpr float FX_SUM = 1073741824.f;         // 2^30
 constexpr float FX_SUM_INV = 1.f / 1073741824.f;
-__device__ __forceinline__ void fx_add(long long* p, float v, float scale) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(v * scale)));
+constexpr float FX_SUM_MAX = 4294967296.f;     // 2^32
+// A NaN / Inf / out-of-range contribution cannot be represented in the integer sum (and must not vanish into it: the
+// reference's blow-ups surface as NaN gradients).  It marks the pass instead -- `poison` keeps the id of the last pass that
+// saw one -- and the conversion kernel writes NaN for the whole tensor of such a pass.
+__device__ __forceinline__ void fx_add(long long* p, float v, float scale, float vmax, unsigned int* poison, unsigned int pass) {
+  if (fabsf(v) < vmax) atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(v * scale)));
+  else atomicMax(poison, pass);
 }
 __global__ void __launch_bounds__(256) fx_to_float_kernel(long long* __restrict__ acc, float* __restrict__ out, int n,
-                                                          float inv_scale) {
+                                                          float inv_scale, const unsigned int* __restrict__ poison,
+                                                          unsigned int pass) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = (float)acc[i] * inv_scale;
+  out[i] = (*poison == pass) ? __int_as_float(0x7fc00000) : (float)acc[i] * inv_scale;
   acc[i] = 0;
 }
 
 __global__ void rescale_bwd_kernel(const float* __restrict__ gy, int in_h, int in_w, int out_h, int out_w,
-                                   long long* __restrict__ gx) {
+                                   long long* __restrict__ gx, unsigned int* poison, unsigned int pass) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * out_h * out_w) return;
@@ -213,10 +220,10 @@ __global__ void rescale_bwd_kernel(const float* __restrict__ gy, int in_h, int i
   lin_taps(oy, in_h, out_h, y0, y1, ly);
   long long* p = gx + (size_t)c * in_h * in_w;
   const float g = gy[i];
-  fx_add(p + y0 * in_w + x0, (1.f - ly) * (1.f - lx) * g, FX_GRAD);
-  fx_add(p + y0 * in_w + x1, (1.f - ly) * lx * g, FX_GRAD);
-  fx_add(p + y1 * in_w + x0, ly * (1.f - lx) * g, FX_GRAD);
-  fx_add(p + y1 * in_w + x1, ly * lx * g, FX_GRAD);
+  fx_add(p + y0 * in_w + x0, (1.f - ly) * (1.f - lx) * g, FX_GRAD, FX_GRAD_MAX, poison, pass);
+  fx_add(p + y0 * in_w + x1, (1.f - ly) * lx * g, FX_GRAD, FX_GRAD_MAX, poison, pass);
+  fx_add(p + y1 * in_w + x0, ly * (1.f - lx) * g, FX_GRAD, FX_GRAD_MAX, poison, pass);
+  fx_add(p + y1 * in_w + x1, ly * lx * g, FX_GRAD, FX_GRAD_MAX, poison, pass);
 }
 
 constexpr int CUT_THREADS = 256;
@@ -531,7 +538,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
                                                            const float* __restrict__ batch,
                                                            const float* __restrict__ range, int n, int cs, int P,
                                                            int ld, int accumulate, float* __restrict__ g_batch,
-                                                           long long* __restrict__ sums) {
+                                                           long long* __restrict__ sums, unsigned int* poison,
+                                                           unsigned int pass) {
   pdl_prologue();
   const int gp = cs / P;
   const int vec_per_row = 3 * P * P / 8;
@@ -590,8 +598,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(const act_t* __restri
       a += r1[i];
       b += r2[i];
     }
-    fx_add(&sums[0], a, FX_SUM);
-    fx_add(&sums[1], b, FX_SUM);
+    fx_add(&sums[0], a, FX_SUM, FX_SUM_MAX, poison, pass);
+    fx_add(&sums[1], b, FX_SUM, FX_SUM_MAX, poison, pass);
   }
 }
 
@@ -620,7 +628,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_generic_kernel(const act_t* 
                                                                    const float* __restrict__ range, int n, int cs,
                                                                    int P, int ld, int accumulate,
                                                                    float* __restrict__ g_batch,
-                                                                   long long* __restrict__ sums) {
+                                                                   long long* __restrict__ sums, unsigned int* poison,
+                                                           unsigned int pass) {
   pdl_prologue();
   const int gp = cs / P;
   const long long total = (long long)n * 3 * cs * cs;
@@ -657,8 +666,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_generic_kernel(const act_t* 
       a += r1[i];
       b2 += r2[i];
     }
-    fx_add(&sums[0], a, FX_SUM);
-    fx_add(&sums[1], b2, FX_SUM);
+    fx_add(&sums[0], a, FX_SUM, FX_SUM_MAX, poison, pass);
+    fx_add(&sums[1], b2, FX_SUM, FX_SUM_MAX, poison, pass);
   }
 }
 
@@ -666,7 +675,8 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
                                                                  const float* __restrict__ range,
                                                                  const int* __restrict__ irange,
                                                                  const float* __restrict__ sums,
-                                                                 long long* __restrict__ g_pooled) {
+                                                                 long long* __restrict__ g_pooled, unsigned int* poison,
+                                                                 unsigned int pass) {
   pdl_prologue();
   const int n = blockIdx.y;
   const int n_global = a.first_global + n;
@@ -724,10 +734,10 @@ __global__ void __launch_bounds__(CUT_THREADS) cutout_bwd_kernel(CutoutArgs a, c
       long long* p = g_pooled + (size_t)c * a.src_h * a.src_w;
       const int sw = a.src_w;
       float gv = gpre[c];
-      if (t.in[0]) fx_add(p + t.y0 * sw + t.x0, t.w[0] * gv, FX_GRAD);
-      if (t.in[1]) fx_add(p + t.y0 * sw + t.x0 + 1, t.w[1] * gv, FX_GRAD);
-      if (t.in[2]) fx_add(p + (t.y0 + 1) * sw + t.x0, t.w[2] * gv, FX_GRAD);
-      if (t.in[3]) fx_add(p + (t.y0 + 1) * sw + t.x0 + 1, t.w[3] * gv, FX_GRAD);
+      if (t.in[0]) fx_add(p + t.y0 * sw + t.x0, t.w[0] * gv, FX_GRAD, FX_GRAD_MAX, poison, pass);
+      if (t.in[1]) fx_add(p + t.y0 * sw + t.x0 + 1, t.w[1] * gv, FX_GRAD, FX_GRAD_MAX, poison, pass);
+      if (t.in[2]) fx_add(p + (t.y0 + 1) * sw + t.x0, t.w[2] * gv, FX_GRAD, FX_GRAD_MAX, poison, pass);
+      if (t.in[3]) fx_add(p + (t.y0 + 1) * sw + t.x0 + 1, t.w[3] * gv, FX_GRAD, FX_GRAD_MAX, poison, pass);
     }
   }
 }
@@ -748,13 +758,16 @@ void spot_mask_apply(const float* x, const unsigned char* mask, int zero_where_s
 void rescale_bilinear(const float* x, int in_h, int in_w, int out_h, int out_w, float* y, cudaStream_t st) {
   launch_pdl(rescale_fwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, x, in_h, in_w, out_h, out_w, y);
 }
-void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, long long* acc, float* gx,
+void rescale_bilinear_backward(const float* gy, int in_h, int in_w, int out_h, int out_w, long long* acc, FxPass fx, float* gx,
                                cudaStream_t st) {
-  launch_pdl(rescale_bwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, gy, in_h, in_w, out_h, out_w, acc);
-  launch_pdl(fx_to_float_kernel, dim3((3 * in_h * in_w + 255) / 256), dim3(256), 0, st, acc, gx, 3 * in_h * in_w, FX_GRAD_INV);
+  launch_pdl(rescale_bwd_kernel, dim3((3 * out_h * out_w + 255) / 256), dim3(256), 0, st, gy, in_h, in_w, out_h, out_w, acc, fx.poison,
+             fx.pass);
+  launch_pdl(fx_to_float_kernel, dim3((3 * in_h * in_w + 255) / 256), dim3(256), 0, st, acc, gx, 3 * in_h * in_w, FX_GRAD_INV,
+             static_cast<const unsigned int*>(fx.poison), fx.pass);
 }
-void range_sums_finish(long long* acc, float* sums, cudaStream_t st) {
-  launch_pdl(fx_to_float_kernel, dim3(1), dim3(256), 0, st, acc, sums, 2, FX_SUM_INV);
+void range_sums_finish(long long* acc, FxPass fx, float* sums, cudaStream_t st) {
+  launch_pdl(fx_to_float_kernel, dim3(1), dim3(256), 0, st, acc, sums, 2, FX_SUM_INV, static_cast<const unsigned int*>(fx.poison),
+             fx.pass);
 }
 
 int cutout_num_blocks(int n_local, int cs) { return n_local * ((cs * cs / 4 + CUT_THREADS - 1) / CUT_THREADS); }
@@ -797,23 +810,24 @@ void patchify_forward(const float* batch, const float* range, int n, int cs, int
   launch_pdl(patchify_fwd_kernel, dim3(patch_grid(total)), dim3(256), 0, st, batch, range, n, cs, P, ld, patches);
 }
 void patchify_backward(const act_t* g_patches, const float* batch, const float* range, int n, int cs, int P, int ld,
-                       int accumulate, float* g_batch, long long* sums, cudaStream_t st) {
+                       int accumulate, float* g_batch, long long* sums, FxPass fx, cudaStream_t st) {
   if (P % 8) {
     const long long tot = (long long)n * 3 * cs * cs;
     launch_pdl(patchify_bwd_generic_kernel, dim3(patch_grid(tot)), dim3(256), 0, st, g_patches, batch, range, n, cs, P, ld, accumulate,
-                                                                 g_batch, sums);
+                                                                 g_batch, sums, fx.poison, fx.pass);
     return;
   }
   const long long total = (long long)n * (cs / P) * (cs / P) * (3 * P * P / 8);
   launch_pdl(patchify_bwd_kernel, dim3(patch_grid(total)), dim3(256), 0, st, g_patches, batch, range, n, cs, P, ld, accumulate, g_batch,
-                                                         sums);
+                                                         sums, fx.poison, fx.pass);
 }
 void cutout_backward(const CutoutArgs& a, const float* g_batch, const float* range, const int* irange,
-                     const float* sums, long long* acc, float* g_pooled, cudaStream_t st) {
+                     const float* sums, long long* acc, FxPass fx, float* g_pooled, cudaStream_t st) {
   dim3 grid((a.cs * a.cs / 4 + CUT_THREADS - 1) / CUT_THREADS, a.n_local);
-  launch_pdl(cutout_bwd_kernel, dim3(grid), dim3(CUT_THREADS), 0, st, a, g_batch, range, irange, sums, acc);
+  launch_pdl(cutout_bwd_kernel, dim3(grid), dim3(CUT_THREADS), 0, st, a, g_batch, range, irange, sums, acc, fx.poison, fx.pass);
   const int n = 3 * a.src_h * a.src_w;
-  launch_pdl(fx_to_float_kernel, dim3((n + 255) / 256), dim3(256), 0, st, acc, g_pooled, n, FX_GRAD_INV);
+  launch_pdl(fx_to_float_kernel, dim3((n + 255) / 256), dim3(256), 0, st, acc, g_pooled, n, FX_GRAD_INV,
+             static_cast<const unsigned int*>(fx.poison), fx.pass);
 }
 
 }  // namespace pxr

@@ -154,6 +154,35 @@ def test_pipeline_stagewise_small():
     assert e_g <= 3e-2 * m_g
 
 
+def test_a_nan_gradient_is_not_swallowed_by_the_fixed_point_sums():
+    """The scatters of the cutout backward accumulate in 64-bit fixed point (order-independent); a NaN contribution has no
+    integer representation and must still surface as a NaN gradient, as it does in the reference -- and the next, clean
+    iteration must be clean again."""
+    cutn, cs = 8, 224
+    vq, clip, eng, prompts, z = build(cutn=cutn, seed=2)
+    T = random_transforms(cutn, cs, 6)
+    g = torch.Generator().manual_seed(3)
+    facs, noise = plant_extremes(torch.rand(cutn, generator=g) * 0.1, torch.randn(cutn, 3, cs, cs, generator=g))
+    losses = np.zeros(2, dtype=np.float32)
+    zc = z.clone().cuda()
+    eng.iterate(zc, 0.0, 0, params=dict(transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.4, noise_facs=facs.numpy(), noise=noise),
+                losses_out=losses)
+    clean = eng.debug_read("z_grad", z.shape).cpu()
+    assert torch.isfinite(clean).all()
+    bad = noise.clone()
+    bad[3, 1, 17, 40] = float("nan")
+    zc = z.clone().cuda()
+    eng.iterate(zc, 0.0, 1, params=dict(transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.4, noise_facs=facs.numpy(), noise=bad),
+                losses_out=losses)
+    poisoned = eng.debug_read("z_grad", z.shape).cpu()
+    assert torch.isnan(poisoned).any(), "a NaN in the cutout batch must reach z.grad"
+    zc = z.clone().cuda()
+    eng.iterate(zc, 0.0, 2, params=dict(transforms=T, zoom_padding=E.PAD_REFLECTION, fill=0.4, noise_facs=facs.numpy(), noise=noise),
+                losses_out=losses)
+    again = eng.debug_read("z_grad", z.shape).cpu()
+    assert torch.equal(again, clean), "the pass after a poisoned one is clean and bit-identical to the first"
+
+
 def test_intermediate_gradients_small():
     """d loss / d image and d loss / d cutout-batch against autograd on the oracle (finer than z.grad)."""
     cutn, cs = 8, 224
