@@ -369,6 +369,22 @@ class Engine {
   // (3 waves for 2.007 waves of work) but 396 tiles of 192 (3 cheaper waves).
   int pick_bn(int N, bool b_mn, long long m_tiles) const {
     const int step = b_mn ? 64 : 16;
+    {  // PXR_GEMM_BN="3072:256,768:192": tile width by output width, for A/B measurements of the cost model's choices
+      static const std::map<int, int> forced = [] {
+        std::map<int, int> m;
+        if (const char* e = getenv("PXR_GEMM_BN")) {
+          int n = 0, bn = 0, used = 0;
+          while (sscanf(e, "%d:%d%n", &n, &bn, &used) == 2) {
+            m[n] = bn;
+            e += used;
+            if (*e == ',') ++e;
+          }
+        }
+        return m;
+      }();
+      auto it = forced.find(N);
+      if (it != forced.end() && it->second % step == 0 && m_tiles > 16) return it->second;
+    }
     if (N <= 256 && m_tiles * 1 >= num_sms / 2) return round_up(N, step);
     int best = 0;
     double best_cost = 1e30;
