@@ -439,7 +439,12 @@ def run_engine(args, cfg, rank, world):
                      "launches_per_iter": prof["gemm_launches"], "gemm_ms_per_iter": prof["gemm_ms"],
                      "other_ms_per_iter": prof["other_ms"], "iter_ms_profiled": prof["total_ms"],
                      "algorithmic_flops_per_launch": prof["gemm_flops"] / nl,
-                     "whole_iter_tflops": S_flops * args.steps / (ms * 1e-3) / 1e12},
+                     # FLOPs the tensor-core launches of one iteration actually execute (sum of 2 M N K over the plans).
+                     # Below config.algorithmic_flops_per_iter -- the full model on every row, what the reference's
+                     # PyTorch path computes -- by the dead rows of the last ViT layer (only the class token's row of
+                     # each image reaches the embedding).  whole_iter_tflops uses the EXECUTED count.
+                     "executed_flops_per_iter": prof["gemm_flops"],
+                     "whole_iter_tflops": min(S_flops, prof["gemm_flops"]) * args.steps / (ms * 1e-3) / 1e12},
     }
     if not args.no_cpu_baseline:
         r = run_cpu_reference(cfg, steps=1, budget_s=25.0)

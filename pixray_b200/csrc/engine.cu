@@ -429,6 +429,7 @@ class Engine {
   // bound by the per-SM operand feed; split-K spreads the taps over the idle SMs (fp32 partial sums to a workspace, then
   // one fixed-order reduce + bias / residual / fp16 epilogue kernel: deterministic).
   bool conv_splitk = true;  // PXR_CONV_SPLITK=0 disables
+  bool clip_last_cls = true;  // PXR_CLIP_LAST_CLS=0: the last ViT layer's row-wise tail on all rows instead of the class rows
   bool gn_group = true;     // PXR_GN_GROUP=0: never use the cluster-per-group GroupNorm (kernels_gn_group.cu)
   bool gn_fuse_sk = true;   // PXR_GN_FUSE_SPLITK=0: keep splitk_reduce and GroupNorm as two kernels
   bool gn_fuse_fwd = true, gn_fuse_bwd = true;  // PXR_GN_FUSE_FWD / PXR_GN_FUSE_BWD = 0: per direction (diagnostics)
@@ -677,6 +678,7 @@ void Engine::create() {
   if (const char* cs16 = getenv("PXR_CLIP_STREAM")) stream16 = atoi(cs16) != 32;
   if (const char* gc = getenv("PXR_GN_COOP")) gn_coop = atoi(gc) != 0;
   if (const char* sk = getenv("PXR_CONV_SPLITK")) conv_splitk = atoi(sk) != 0;
+  if (const char* lc = getenv("PXR_CLIP_LAST_CLS")) clip_last_cls = atoi(lc) != 0;
   if (const char* gg = getenv("PXR_GN_GROUP")) gn_group = atoi(gg) != 0;
   if (const char* gf = getenv("PXR_GN_FUSE_SPLITK")) gn_fuse_sk = atoi(gf) != 0;
   if (const char* gf = getenv("PXR_GN_FUSE_FWD")) gn_fuse_fwd = atoi(gf) != 0;
@@ -1690,29 +1692,36 @@ void Engine::build_clip(int i) {
                T, e, 64);
     }
     }
+    // Last layer: only the class token's row of every image reaches ln_post / proj (slip.py:62-66 ->
+    // VisionTransformer.forward takes x[:, 0, :]), and everything after the attention is row-wise -- out_proj, ln_2, the MLP
+    // and their backward run on those B rows (row pitch T * W inside the [M, W] buffers) instead of on all M = B T rows.
+    // Exact: the other rows' outputs are never read and their gradients are zero.  PXR_CLIP_LAST_CLS=0 computes all rows.
+    const bool cls_only = clip_last_cls && l == L - 1;
+    const int Mr = cls_only ? B : M;                                     // rows of the row-wise tail of this layer
+    const long long xld = cls_only ? (long long)T * Wd : (long long)Wd;   // their pitch inside the token-major buffers
     {  // x_mid = x_in + O Wo^T + bo
       GemmEpilogue e;
       e.bias = ly.bo;
       residual_epilogue(e, ly.x_in, ly.x_mid);
-      e.ldc = Wd;
-      add_gemm(C.fwd, opK(fuse_attn ? ly.o : C.o16, Wd, M, Wd), opK(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
+      e.ldc = xld;
+      add_gemm(C.fwd, opK(fuse_attn ? ly.o : C.o16, xld, Mr, Wd), opK(ly.wo, Wd, Wd, Wd), Mr, Wd, Wd, e);
     }
-    C.fwd.add(1, [=] { ln_fwd(ly.x_mid, Wd, nullptr, T, ly.ln2, M, Wd, c->h16, nullptr, ly.stats2); }, 0.0, "layernorm_forward");
-    {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u
+    C.fwd.add(1, [=] { ln_fwd(ly.x_mid, xld, nullptr, T, ly.ln2, Mr, Wd, c->h16, nullptr, ly.stats2); }, 0.0, "layernorm_forward");
+    {  // gact = quickgelu(h Wfc^T + bfc), keep pre-activation u   (h16 / gact / u hold the Mr rows compactly)
       GemmEpilogue e;
       e.bias = ly.bfc;
       e.act = ACT_QUICKGELU;
       e.aux_out = ly.u;
       e.out_f16 = C.gact;
       e.ldc = 4 * Wd;
-      add_gemm(C.fwd, opK(C.h16, Wd, M, Wd), opK(ly.wfc, Wd, 4 * Wd, Wd), M, 4 * Wd, Wd, e);
+      add_gemm(C.fwd, opK(C.h16, Wd, Mr, Wd), opK(ly.wfc, Wd, 4 * Wd, Wd), Mr, 4 * Wd, Wd, e);
     }
     {  // x_next = x_mid + gact Wproj^T + bproj
       GemmEpilogue e;
       e.bias = ly.bproj;
       residual_epilogue(e, ly.x_mid, x_next);
-      e.ldc = Wd;
-      add_gemm(C.fwd, opK(C.gact, 4 * Wd, M, 4 * Wd), opK(ly.wproj, 4 * Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
+      e.ldc = xld;
+      add_gemm(C.fwd, opK(C.gact, 4 * Wd, Mr, 4 * Wd), opK(ly.wproj, 4 * Wd, Wd, 4 * Wd), Mr, Wd, 4 * Wd, e);
     }
     x_cur = x_next;
   }
@@ -1745,26 +1754,33 @@ void Engine::build_clip(int i) {
     Clip* c = &C;
     const long long qs0 = d, qs1 = (long long)T * 3 * Wd, ps0 = (long long)T * ldT, ps1 = (long long)Hh * T * ldT;
     const long long os0 = d, os1 = (long long)T * Wd;
+    const bool cls_only = clip_last_cls && l == L - 1;  // see the forward: the row-wise tail of the last layer, class rows only
+    const int Mr = cls_only ? B : M;
+    const long long xld = cls_only ? (long long)T * Wd : (long long)Wd;
     {  // g4 = (gx Wproj) * quickgelu'(u)
       GemmEpilogue e;
       e.act = ACT_QUICKGELU_BWD;
       e.aux_in = ly.u;
       e.out_f16 = C.g4;
       e.ldc = 4 * Wd;
-      add_gemm(C.bwd, opK(C.gx16, Wd, M, Wd), opMN(ly.wproj, 4 * Wd, 4 * Wd, Wd), M, 4 * Wd, Wd, e);
+      add_gemm(C.bwd, opK(C.gx16, xld, Mr, Wd), opMN(ly.wproj, 4 * Wd, 4 * Wd, Wd), Mr, 4 * Wd, Wd, e);
     }
     {  // gh = g4 Wfc
       GemmEpilogue e;
       e.out_f16 = C.gh;
       e.ldc = Wd;
-      add_gemm(C.bwd, opK(C.g4, 4 * Wd, M, 4 * Wd), opMN(ly.wfc, Wd, Wd, 4 * Wd), M, Wd, 4 * Wd, e);
+      add_gemm(C.bwd, opK(C.g4, 4 * Wd, Mr, 4 * Wd), opMN(ly.wfc, Wd, Wd, 4 * Wd), Mr, Wd, 4 * Wd, e);
     }
-    C.bwd.add(1, [=] { ln_bwd(c->gh, ly.x_mid, Wd, ly.stats2, ly.ln2, M, Wd, 1, c->gx, c->gx16); }, 0.0, "layernorm_backward");
+    C.bwd.add(1, [=] { ln_bwd(c->gh, ly.x_mid, xld, ly.stats2, ly.ln2, Mr, Wd, 1, c->gx, c->gx16); }, 0.0, "layernorm_backward");
+    if (cls_only) {  // the attention backward reads dO = go for every token: zero outside the class rows
+      const size_t go_bytes = (size_t)M * Wd * sizeof(act_t);
+      C.bwd.add(1, [=] { cudaMemsetAsync(c->go, 0, go_bytes, cs); }, 0.0, "memset go");
+    }
     {  // go = gx Wo
       GemmEpilogue e;
       e.out_f16 = C.go;
-      e.ldc = Wd;
-      add_gemm(C.bwd, opK(C.gx16, Wd, M, Wd), opMN(ly.wo, Wd, Wd, Wd), M, Wd, Wd, e);
+      e.ldc = xld;
+      add_gemm(C.bwd, opK(C.gx16, xld, Mr, Wd), opMN(ly.wo, Wd, Wd, Wd), Mr, Wd, Wd, e);
     }
     if (fuse_attn) {  // dQ, dK, dV in one kernel (recomputes P from Q, K and the saved log-sum-exp)
       std::shared_ptr<AttnPlan> ap = ly.attn;
