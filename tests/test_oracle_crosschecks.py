@@ -54,3 +54,46 @@ def test_adaptive_pool_bounds_match_torch():
         want_avg = torch.nn.functional.adaptive_avg_pool2d(x, (1, n_out)).reshape(-1)
         mine = torch.tensor([(s + e - 1) / 2.0 for s, e in zip(starts, ends)])
         assert torch.allclose(want_avg, mine, atol=1e-4)
+
+
+def test_last_vit_layer_on_class_rows_only_is_exact():
+    """The engine runs the LAST transformer block's out_proj / ln_2 / MLP (and their backward) on the class-token row of each
+    image only (pixray_b200/csrc/engine.cu, build_clip: `cls_only`).  VisionTransformer.forward keeps x[:, 0, :] after the last
+    block and everything behind that block's attention is row-wise, so this must change neither the embedding nor the gradient
+    with respect to the input: checked here on the oracle's ViT in float64, with the attention output's gradient zeroed outside
+    the class rows exactly as the engine does it."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    clip = R.init_clip_weights(R.ClipVisual(64, 16, 64, 3, 1, 32), 5).double()
+    v = clip.visual
+    x_img = torch.randn(3, 3, 64, 64, dtype=torch.float64, requires_grad=True)
+    full = v(x_img)
+    (g_full,) = torch.autograd.grad(full.square().sum() + full.sum(), x_img)
+
+    # the same network with the last block's tail restricted to the class rows
+    x2 = x_img.detach().clone().requires_grad_(True)
+    t = v.conv1(x2)
+    t = t.reshape(t.shape[0], t.shape[1], -1).permute(0, 2, 1)
+    cls = v.class_embedding + torch.zeros(t.shape[0], 1, t.shape[-1], dtype=t.dtype)
+    t = v.ln_pre(torch.cat([cls, t], dim=1) + v.positional_embedding)
+    t = t.permute(1, 0, 2)                                      # [T, B, W]
+    blocks = list(v.transformer.resblocks)
+    for blk in blocks[:-1]:
+        t = blk(t)
+    last = blocks[-1]
+    h = last.ln_1(t)
+    W = h.shape[-1]
+    q, k, vv = F.linear(h, last.attn.in_proj_weight, last.attn.in_proj_bias).chunk(3, dim=-1)
+    nh = last.attn.num_heads
+    hd = W // nh
+    Tn, Bn = h.shape[0], h.shape[1]
+    split = lambda z: z.reshape(Tn, Bn * nh, hd).transpose(0, 1)      # noqa: E731  [B*heads, T, hd]
+    att = torch.softmax(split(q) @ split(k).transpose(1, 2) / hd ** 0.5, dim=-1) @ split(vv)
+    o = att.transpose(0, 1).reshape(Tn, Bn, W)                   # attention output of EVERY token (the engine computes all)
+    o_cls = o[0]                                                 # ... but only the class rows go on
+    x_mid = t[0] + F.linear(o_cls, last.attn.out_proj.weight, last.attn.out_proj.bias)
+    x_out = x_mid + last.mlp(last.ln_2(x_mid))
+    short = v.ln_post(x_out) @ v.proj
+    (g_short,) = torch.autograd.grad(short.square().sum() + short.sum(), x2)
+    assert (short - full).abs().max().item() < 1e-12
+    assert (g_short - g_full).abs().max().item() < 1e-12 * max(1.0, g_full.abs().max().item())
